@@ -1,0 +1,678 @@
+// kernel_long.cuh -- the hot path: fused IMDCT + window + overlap-add for runs of consecutive
+// long blocks (n = 2048) of one channel.  One WARP owns one run: it walks the run's packets in
+// order, keeps the previous block's right half in registers (the only inter-packet state,
+// audio.rs:847-861), and emits 1024 f32 PCM samples per packet with fully coalesced stores.
+// HBM traffic is the algorithmic minimum: 4 KB spectrum in (TMA bulk copy into shared memory,
+// three tiles in flight per warp) + 4 KB PCM out per block.
+//
+// Arithmetic = the reference's butterfly network (imdct.rs:291-659), every add/sub/mul in the
+// reference's operand order, unfused (bit parity); what is ours is the schedule:
+//
+//   complex view: z_c = U[2c+1] + i*U[2c], c in [0,512).  The step-3 stages are a radix-2 DIF FFT
+//   over the 9 bits of c: step 2 flips bit 8, stage l flips bit 7-l, ld654 covers bits 2,1,0.
+//   Each lane holds 16 complex values = 2 groups x 8 "slots"; the slot index carries 3 bits of c:
+//     phase A: slot = bits 8,7,6   -> step 0 (pre-twiddle), step 2, stages 0 and 1, in registers
+//     phase B: slot = bits 5,4,3   -> stages 2, 3, 4
+//     phase C: slot = bits 2,1,0   -> ld654, bit-reverse (free: renaming), step 7, step 8, OLA
+//   with two swizzled shared-memory transposes in between (conflict-free 32-bit accesses).
+//   The two groups of a lane are chosen so that
+//     * phase A: one float4 of spectrum feeds both groups (c and 511-c come from the same quad),
+//     * phase C: the step-7 partner (c' <-> 511-c') of every value lives in the same lane,
+//     * output index m = 64*rev3(slot) + lane (or 63-lane): every store is a full 128 B line.
+//   Every operation is written on V = (group a, group b) pairs, which maps 1:1 onto Blackwell's
+//   packed add/sub/mul.rn.f32x2 (SASS FADD2/FMUL2; IEEE RN per lane, so parity-safe) and halves
+//   the FP issue slots of this issue-bound, non-FMA-able kernel.
+//   Twiddles/window: a per-lane "pack" (built once per setup on the host from the uploaded
+//   tables) is staged in shared memory per CTA; phases A/B keep theirs in registers across the
+//   whole run, phase C reads its 48 pairs per block from the shared copy.
+//
+// The per-lane phase functions are plain inline functions of (lane, registers, twiddles): they
+// also compile for the host, where tests/emu runs all 32 lanes sequentially against the oracle
+// (test infrastructure only; the product never executes them on the CPU).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define LWB_HD __host__ __device__ __forceinline__
+#else
+#define LWB_HD inline
+#endif
+
+namespace lwb {
+
+constexpr int kLongBs = 11;
+constexpr int kLongN = 2048;
+constexpr int kLongN2 = 1024;
+
+// one run = consecutive packets of one channel of one stream
+struct LongRun {
+    const float *in;        // first packet's spectrum (1024 floats); next packet at +in_stride
+    float *out;             // first emitted packet's PCM; next at +1024
+    float *state;           // stream state row of this channel (1024 floats)
+    uint32_t in_stride;
+    uint32_t n_packets;     // including a primer packet if prime != 0
+    uint8_t has_prev;       // 1: packet 0 overlaps with `state`;  0: packet 0 emits nothing
+    uint8_t write_state;    // 1: store the last packet's right half to `state`
+    uint8_t pad[2];
+};
+
+struct V { float x, y; };    // (group a, group b)
+
+#if defined(__CUDA_ARCH__)
+#ifndef LWB_PACKED_F32X2
+#define LWB_PACKED_F32X2 1
+#endif
+#if LWB_PACKED_F32X2
+__device__ __forceinline__ unsigned long long v_bits(V a)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ V v_from(unsigned long long r)
+{
+    V a;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+    return a;
+}
+__device__ __forceinline__ V vadd(V a, V b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(v_bits(a)), "l"(v_bits(b)));
+    return v_from(r);
+}
+__device__ __forceinline__ V vsub(V a, V b)
+{
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(v_bits(a)), "l"(v_bits(b)));
+    return v_from(r);
+}
+__device__ __forceinline__ V vmul(V a, V b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(v_bits(a)), "l"(v_bits(b)));
+    return v_from(r);
+}
+#else
+__device__ __forceinline__ V vadd(V a, V b) { return V{__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)}; }
+__device__ __forceinline__ V vsub(V a, V b) { return V{__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)}; }
+__device__ __forceinline__ V vmul(V a, V b) { return V{__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)}; }
+#endif
+// Add/sub whose operands are PRODUCTS.  ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 even with explicit .rn and -fmad=false (it also rewrites fma(a,b,-0) and fma(a,1,c) back
+// to mul/add first), which would merge two of the reference's roundings into one.  Scalar
+// add.rn.f32 is never contracted, so the product-consuming adds stay scalar (FADD) while all
+// other adds and all multiplies are packed (FADD2 / FMUL2).
+__device__ __forceinline__ V vadd_p(V a, V b) { return V{__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)}; }
+__device__ __forceinline__ V vsub_p(V a, V b) { return V{__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)}; }
+#else
+// host (pack builder is host code; the phase functions run here only inside tests/emu).
+// Compiled with -ffp-contract=off: one rounding per operation, like the device path.
+inline V vadd(V a, V b) { return V{a.x + b.x, a.y + b.y}; }
+inline V vsub(V a, V b) { return V{a.x - b.x, a.y - b.y}; }
+inline V vmul(V a, V b) { return V{a.x * b.x, a.y * b.y}; }
+inline V vadd_p(V a, V b) { return vadd(a, b); }
+inline V vsub_p(V a, V b) { return vsub(a, b); }
+#endif
+
+// ---- pack layout: V slots per lane, stored slot-major [slot][lane] --------------------------
+enum {
+    P_S0W0 = 0, P_S0W1 = 8,            // step 0 pre-twiddle, per slot
+    P_S2W0 = 16, P_S2W1 = 20,          // step 2, butterflies (slot j, j+4), j < 4
+    P_L0W0 = 24, P_L0W1 = 26,          // stage 0: index = slot & 1
+    P_L1W0 = 28, P_L1W1 = 29,          // stage 1
+    P_A_END = 30,
+    P_L2W0 = 30, P_L2W1 = 34,          // stage 2: index = slot & 3
+    P_L3W0 = 38, P_L3W1 = 40,          // stage 3: index = slot & 1
+    P_L4W0 = 42, P_L4W1 = 43,          // stage 4
+    P_B_END = 44,
+    P_A2 = 44,                         // A[n/8] (ld654)
+    P_S7C0 = 45, P_S7C1 = 49,          // step 7, odd slots 1,3,5,7 -> index slot >> 1
+    P_B0 = 53, P_B1 = 61, P_NB0 = 69,  // step 8 per slot (NB0 = -B0)
+    P_WLO = 77, P_WHI = 85,            // window w[m], w[1023-m] per slot
+    P_END = 93
+};
+constexpr int kLongPackFloats = P_END * 32 * 2;
+
+LWB_HD int rev3(int j) { return ((j & 1) << 2) | (j & 2) | ((j >> 2) & 1); }
+LWB_HD int rev6(int t) { return (rev3(t & 7) << 3) | rev3((t >> 3) & 7); }
+LWB_HD int rev9(int c) { return (rev3(c & 7) << 6) | (rev3((c >> 3) & 7) << 3) | rev3((c >> 6) & 7); }
+
+// shared-memory index of complex element c in the transpose planes: conflict-free for all four
+// access patterns (phase A store / phase B load+store / phase C load), see DESIGN.md
+LWB_HD int swz(int c)
+{
+    return c ^ (((c >> 5) & 1) | (((c >> 6) & 1) << 1) | (((c >> 4) & 1) << 2) |
+                (((c >> 7) & 1) << 3) | (((c >> 8) & 1) << 4));
+}
+
+// Which complex element sits in (lane, slot, half) in each phase
+LWB_HD int elemA(int lane, int slot, int half) { return (half ? 63 - lane : lane) + 64 * slot; }
+LWB_HD int elemB(int lane, int slot, int half)
+{
+    return (((lane >> 3) * 2 + half) << 6) | (slot << 3) | (lane & 7);
+}
+LWB_HD int elemC(int lane, int slot, int half)
+{
+    const int T = half ? 63 - rev6(lane) : rev6(lane);
+    return 8 * T + slot;
+}
+// output index m (0..511) of (lane, slot, half) AFTER the step-7 half swap of even slots
+LWB_HD int outIndex(int lane, int slot, int half)
+{
+    const int flip = (slot & 1) ? half : !half;
+    return 64 * rev3(slot) + (flip ? 63 - lane : lane);
+}
+
+// Host: build the per-lane pack from the blocksize-11 tables (a,b: 1024; c: 512; w: 1024).
+inline void long_build_pack(const float *a, const float *b, const float *c, const float *w, float *pack)
+{
+    V *P = reinterpret_cast<V *>(pack);
+    for (int lane = 0; lane < 32; lane++) {
+        auto put = [&](int slot, float x, float y) { P[slot * 32 + lane] = V{x, y}; };
+        float tx[2], ty[2];
+        // phase A
+        for (int j = 0; j < 8; j++) {
+            for (int h = 0; h < 2; h++) {
+                const int cc = elemA(lane, j, h);
+                const float s = cc < 256 ? -1.0f : 1.0f;       // (-x)*A == x*(-A): sign moved into the table
+                tx[h] = s * a[1022 - 2 * cc];
+                ty[h] = s * a[1023 - 2 * cc];
+            }
+            put(P_S0W0 + j, tx[0], tx[1]);
+            put(P_S0W1 + j, ty[0], ty[1]);
+        }
+        for (int j = 0; j < 4; j++) {
+            for (int h = 0; h < 2; h++) {
+                const int cc = elemA(lane, j, h);              // lower element of the step-2 butterfly
+                tx[h] = a[1020 - 4 * cc];
+                ty[h] = a[1021 - 4 * cc];
+            }
+            put(P_S2W0 + j, tx[0], tx[1]);
+            put(P_S2W1 + j, ty[0], ty[1]);
+        }
+        for (int u = 0; u < 2; u++) {
+            for (int h = 0; h < 2; h++) {
+                const int r = (~elemA(lane, 2 + u, h)) & 127;  // stage 0: a = r * 8
+                tx[h] = a[8 * r];
+                ty[h] = a[8 * r + 1];
+            }
+            put(P_L0W0 + u, tx[0], tx[1]);
+            put(P_L0W1 + u, ty[0], ty[1]);
+        }
+        for (int h = 0; h < 2; h++) {
+            const int r = (~elemA(lane, 1, h)) & 63;           // stage 1: a = r * 16
+            tx[h] = a[16 * r];
+            ty[h] = a[16 * r + 1];
+        }
+        put(P_L1W0, tx[0], tx[1]);
+        put(P_L1W1, ty[0], ty[1]);
+        // phase B (both groups share the twiddle: same low bits)
+        for (int u = 0; u < 4; u++) {
+            const int r = (~elemB(lane, 4 + u, 0)) & 31;       // stage 2: a = r * 32
+            put(P_L2W0 + u, a[32 * r], a[32 * r]);
+            put(P_L2W1 + u, a[32 * r + 1], a[32 * r + 1]);
+        }
+        for (int u = 0; u < 2; u++) {
+            const int r = (~elemB(lane, 2 + u, 0)) & 15;       // stage 3: a = r * 64
+            put(P_L3W0 + u, a[64 * r], a[64 * r]);
+            put(P_L3W1 + u, a[64 * r + 1], a[64 * r + 1]);
+        }
+        {
+            const int r = (~elemB(lane, 1, 0)) & 7;            // stage 4: a = r * 128
+            put(P_L4W0, a[128 * r], a[128 * r]);
+            put(P_L4W1, a[128 * r + 1], a[128 * r + 1]);
+        }
+        // phase C
+        put(P_A2, a[kLongN >> 3], a[kLongN >> 3]);
+        for (int jj = 0; jj < 4; jj++) {
+            for (int h = 0; h < 2; h++) {
+                const int p = 511 - rev9(elemC(lane, 2 * jj + 1, h));   // step-7 index of the D side
+                tx[h] = c[2 * p];
+                ty[h] = c[2 * p + 1];
+            }
+            put(P_S7C0 + jj, tx[0], tx[1]);
+            put(P_S7C1 + jj, ty[0], ty[1]);
+        }
+        for (int j = 0; j < 8; j++) {
+            float b0[2], b1[2], wl[2], wh[2];
+            for (int h = 0; h < 2; h++) {
+                const int m = outIndex(lane, j, h);
+                const int cp = 511 - m;                        // V element feeding output m
+                b0[h] = b[2 * cp];
+                b1[h] = b[2 * cp + 1];
+                wl[h] = w[m];
+                wh[h] = w[1023 - m];
+            }
+            put(P_B0 + j, b0[0], b0[1]);
+            put(P_B1 + j, b1[0], b1[1]);
+            put(P_NB0 + j, -b0[0], -b0[1]);
+            put(P_WLO + j, wl[0], wl[1]);
+            put(P_WHI + j, wh[0], wh[1]);
+        }
+    }
+}
+
+// ---- the per-lane arithmetic ----------------------------------------------------------------
+struct Q4 { float x, y, z, w; };
+
+// step-3 butterfly (imdct.rs:36-41): hi/lo are complex values (O = odd index, E = even index)
+LWB_HD void bfly(V &Oh, V &Eh, V &Ol, V &El, V w0, V w1)
+{
+    const V k00 = vsub(Oh, Ol);
+    const V k01 = vsub(Eh, El);
+    Oh = vadd(Oh, Ol);
+    Eh = vadd(Eh, El);
+    Ol = vsub_p(vmul(k00, w0), vmul(k01, w1));
+    El = vadd_p(vmul(k01, w0), vmul(k00, w1));
+}
+
+// Phase A.  F1[m] = spectrum quad #(lane + 64 m), F2[m] = quad #(63 - lane + 64 m).
+// Step 0 (imdct.rs:337-371): quad #f yields c = f from (q1,q3) and c = 511-f from (q0,q2).
+template <class TW>
+LWB_HD void phase_a(const Q4 F1[4], const Q4 F2[4], TW tw, V O[8], V E[8])
+{
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        V qa, qb;
+        if (j < 4) { qa = V{F1[j].w, F2[j].w}; qb = V{F1[j].y, F2[j].y}; }
+        else { qa = V{F2[7 - j].x, F1[7 - j].x}; qb = V{F2[7 - j].z, F1[7 - j].z}; }
+        const V w0 = tw(P_S0W0 + j), w1 = tw(P_S0W1 + j);
+        O[j] = vsub_p(vmul(qa, w0), vmul(qb, w1));
+        E[j] = vadd_p(vmul(qa, w1), vmul(qb, w0));
+    }
+    // step 2 (imdct.rs:385-430): bit 8
+#pragma unroll
+    for (int j = 0; j < 4; j++) bfly(O[j + 4], E[j + 4], O[j], E[j], tw(P_S2W0 + j), tw(P_S2W1 + j));
+    // stage 0 (imdct.rs:445-446): bit 7
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (j & 2) bfly(O[j], E[j], O[j - 2], E[j - 2], tw(P_L0W0 + (j & 1)), tw(P_L0W1 + (j & 1)));
+    // stage 1 (imdct.rs:449-452): bit 6
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (j & 1) bfly(O[j], E[j], O[j - 1], E[j - 1], tw(P_L1W0), tw(P_L1W1));
+}
+
+// Phase B: stages 2,3,4 (imdct.rs:454-477): bits 5,4,3 = slot bits 2,1,0
+template <class TW>
+LWB_HD void phase_b(TW tw, V O[8], V E[8])
+{
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (j & 4) bfly(O[j], E[j], O[j - 4], E[j - 4], tw(P_L2W0 + (j & 3)), tw(P_L2W1 + (j & 3)));
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (j & 2) bfly(O[j], E[j], O[j - 2], E[j - 2], tw(P_L3W0 + (j & 1)), tw(P_L3W1 + (j & 1)));
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (j & 1) bfly(O[j], E[j], O[j - 1], E[j - 1], tw(P_L4W0), tw(P_L4W1));
+}
+
+// imdct.rs:201-232 on slots s+3..s (z7[0] = O[s+3], z7[-1] = E[s+3], ...).  PROD: slots s+2 and
+// s hold products (the ld654 multiplies by A[n/8]), so the four adds that read them use the
+// never-contracted scalar form.
+template <bool PROD>
+LWB_HD void iter54(V O[8], V E[8], int s)
+{
+    const V k00 = vsub(O[s + 3], O[s + 1]);
+    const V y0 = vadd(O[s + 3], O[s + 1]);
+    const V y2 = PROD ? vadd_p(O[s + 2], O[s]) : vadd(O[s + 2], O[s]);
+    const V k22 = PROD ? vsub_p(O[s + 2], O[s]) : vsub(O[s + 2], O[s]);
+    O[s + 3] = vadd(y0, y2);
+    O[s + 2] = vsub(y0, y2);
+    const V k33 = PROD ? vsub_p(E[s + 2], E[s]) : vsub(E[s + 2], E[s]);
+    O[s + 1] = vadd(k00, k33);
+    O[s] = vsub(k00, k33);
+    const V k11 = vsub(E[s + 3], E[s + 1]);
+    const V y1 = vadd(E[s + 3], E[s + 1]);
+    const V y3 = PROD ? vadd_p(E[s + 2], E[s]) : vadd(E[s + 2], E[s]);
+    E[s + 3] = vadd(y1, y3);
+    E[s + 2] = vsub(y1, y3);
+    E[s + 1] = vsub(k11, k22);
+    E[s] = vadd(k11, k22);
+}
+
+// Phase C part 1: ld654 (imdct.rs:234-288), then the half swap of the even slots and step 7
+// (imdct.rs:533-580).  After it slot j holds, per half, the V-buffer element 511 - outIndex(..).
+template <class TW>
+LWB_HD void phase_c_fft(TW tw, V O[8], V E[8])
+{
+    const V a2 = tw(P_A2);
+    V k00, k11;
+    k00 = vsub(O[7], O[3]); k11 = vsub(E[7], E[3]);
+    O[7] = vadd(O[7], O[3]); E[7] = vadd(E[7], E[3]);
+    O[3] = k00; E[3] = k11;
+    k00 = vsub(O[6], O[2]); k11 = vsub(E[6], E[2]);
+    O[6] = vadd(O[6], O[2]); E[6] = vadd(E[6], E[2]);
+    O[2] = vmul(vadd(k00, k11), a2);
+    E[2] = vmul(vsub(k11, k00), a2);
+    k00 = vsub(O[1], O[5]); k11 = vsub(E[5], E[1]);
+    O[5] = vadd(O[5], O[1]); E[5] = vadd(E[5], E[1]);
+    O[1] = k11; E[1] = k00;
+    k00 = vsub(O[0], O[4]); k11 = vsub(E[4], E[0]);
+    O[4] = vadd(O[4], O[0]); E[4] = vadd(E[4], E[0]);
+    O[0] = vmul(vadd(k00, k11), a2);
+    E[0] = vmul(vsub(k00, k11), a2);
+    iter54<false>(O, E, 4);
+    iter54<true>(O, E, 0);
+    // steps 4-6 (imdct.rs:490-528) are pure renaming: U element 8T+j becomes V element
+    // 511 - rev9(8T+j) with (V.even, V.odd) = (U.odd, U.even) = (O, E).
+    // step 7 pairs V element p (odd slot j, "D") with 511-p (slot 7-j of the OTHER group, "E"):
+    // swap the halves of the even slots so partners line up.
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        O[j] = V{O[j].y, O[j].x};
+        E[j] = V{E[j].y, E[j].x};
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+        const int d = 2 * jj + 1, e = 7 - d;
+        const V c0 = tw(P_S7C0 + jj), c1 = tw(P_S7C1 + jj);
+        const V a02 = vsub(O[d], O[e]);
+        const V a11 = vadd(E[d], E[e]);
+        const V b0 = vadd_p(vmul(c1, a02), vmul(c0, a11));
+        const V b1 = vsub_p(vmul(c1, a11), vmul(c0, a02));
+        const V b2 = vadd(O[d], O[e]);
+        const V b3 = vsub(E[d], E[e]);
+        O[d] = vadd(b2, b0);
+        E[d] = vadd(b3, b1);
+        O[e] = vsub(b2, b0);
+        E[e] = vsub(b1, b3);
+    }
+}
+
+// Phase C part 2 for one slot: step 8 (imdct.rs:589-658) + window/overlap-add (audio.rs:1112-1118).
+//   p_odd  = out[m] = -out[1023-m];   p_even = out[1024+m] = out[2047-m]
+//   pcm[m]      = p_odd * w[m] + prev[m] * w[1023-m]
+//   pcm[1023-m] = (-p_odd) * w[1023-m] + prev[1023-m] * w[m]   (== prev*w[m] - p_odd*w[1023-m])
+template <class TW>
+LWB_HD void phase_c_out(TW tw, int j, V Oj, V Ej, V prev_lo, V prev_hi, V &pcm_lo, V &pcm_hi, V &p_even)
+{
+    const V b0 = tw(P_B0 + j), b1 = tw(P_B1 + j), nb0 = tw(P_NB0 + j);
+    const V wlo = tw(P_WLO + j), whi = tw(P_WHI + j);
+    const V p_odd = vsub_p(vmul(Oj, b1), vmul(Ej, b0));
+    p_even = vsub_p(vmul(Oj, nb0), vmul(Ej, b1));
+    pcm_lo = vadd_p(vmul(p_odd, wlo), vmul(prev_lo, whi));
+    pcm_hi = vsub_p(vmul(prev_hi, wlo), vmul(p_odd, whi));
+}
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------------------
+#ifndef LWB_LONG_WARPS
+#define LWB_LONG_WARPS 12
+#endif
+constexpr int kLongWarps = LWB_LONG_WARPS;     // warps per CTA, one CTA per SM
+constexpr int kLongRing = 3;                   // spectrum tiles in flight per warp
+constexpr int kLongTileBytes = kLongN2 * 4;
+// [tiles: warps x ring x 4 KB, 2 KB-aligned at run time][pack][mbarriers]
+constexpr size_t kLongSmemBytes = 2048 + (size_t)kLongWarps * kLongRing * kLongTileBytes +
+                                  (size_t)kLongPackFloats * 4 + kLongWarps * kLongRing * 8 + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D TMA: global -> shared, completion counted on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// transpose planes: E at [addr], O at [addr + 2048]
+__device__ __forceinline__ void sts_eo(uint32_t addr, float e, float o)
+{
+    asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+2048], %2;" ::"r"(addr), "f"(e), "f"(o) : "memory");
+}
+__device__ __forceinline__ void lds_eo(uint32_t addr, float &e, float &o)
+{
+    asm volatile("ld.shared.f32 %0, [%2];\n\tld.shared.f32 %1, [%2+2048];" : "=f"(e), "=f"(o) : "r"(addr) : "memory");
+}
+
+struct TwRegs {
+    const V *r;
+    __device__ __forceinline__ V operator()(int slot) const { return r[slot]; }
+};
+struct TwSmem {
+    const V *lane_base;           // &pack[lane]
+    __device__ __forceinline__ V operator()(int slot) const { return lane_base[slot * 32]; }
+};
+
+// Shared-memory byte offsets of the transposes: swz(elem(lane, slot, half)) * 4 splits into a
+// lane part and a (slot, half) part combined by XOR (the tiles are 2 KB aligned, so the XOR can
+// be applied to the full address): one LOP3 per access.
+__device__ __forceinline__ uint32_t laneA(int lane, int half) { return 4u * (uint32_t)swz(elemA(lane, 0, half)); }
+__device__ __forceinline__ uint32_t laneB(int lane) { return 4u * (uint32_t)swz(elemB(lane, 0, 0)); }
+__device__ __forceinline__ uint32_t laneC(int lane, int half) { return 4u * (uint32_t)swz(elemC(lane, 0, half)); }
+// compile-time (slot, half) parts: swz is XOR-linear, so swz(L ^ K) = swz(L) ^ swz(K) when L and K
+// occupy disjoint bits of the element index
+#define LWB_KA(j) (4u * (uint32_t)swz(64 * (j)))
+#define LWB_KB(j, h) (4u * (uint32_t)swz(((h) << 6) | ((j) << 3)))
+#define LWB_KC(j) (4u * (uint32_t)swz(j))
+
+// Step 8 + window + overlap-add + stores for all 8 slots.  FROM_STATE: the previous right half
+// comes from the stream state in HBM (first packet of a run with history); EMIT: store PCM.
+template <bool FROM_STATE, bool EMIT>
+__device__ __forceinline__ void out_stage(const TwSmem &twc, int lane, const V O[8], const V E[8], V pe[8],
+                                          const float *__restrict__ state, float *__restrict__ out)
+{
+    float *o_lo = out + lane, *o_hi = out + 63 - lane;       // out[mx], out[my] bases
+    const float *s_lo = state + lane, *s_hi = state + 63 - lane;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int r64 = 64 * rev3(j);
+        const bool nat = (j & 1);             // odd slots: half x -> lane, half y -> 63 - lane
+        V plo = pe[j], phi = pe[j];
+        if (FROM_STATE) {
+            // prev[m] and prev[1023 - m] read separately: an imported state need not be symmetric
+            const float ax = nat ? s_lo[r64] : s_hi[r64], ay = nat ? s_hi[r64] : s_lo[r64];
+            const float bx = nat ? s_hi[960 - r64] : s_lo[960 - r64], by = nat ? s_lo[960 - r64] : s_hi[960 - r64];
+            plo = V{ax, ay};
+            phi = V{bx, by};
+        }
+        V lo, hi, pev;
+        phase_c_out(twc, j, O[j], E[j], plo, phi, lo, hi, pev);
+        pe[j] = pev;
+        if (EMIT) {
+            // m = r64 + lane (or + 63 - lane); 1023 - m = 960 - r64 + 63 - lane (or + lane)
+            if (nat) {
+                o_lo[r64] = lo.x; o_hi[r64] = lo.y;
+                o_hi[960 - r64] = hi.x; o_lo[960 - r64] = hi.y;
+            } else {
+                o_hi[r64] = lo.x; o_lo[r64] = lo.y;
+                o_lo[960 - r64] = hi.x; o_hi[960 - r64] = hi.y;
+            }
+        }
+    }
+}
+
+// pack: the twiddle pack of the setup's blocksize-11 tables (long_build_pack); ticket: a zeroed
+// counter from which warps draw run indices.
+__global__ void __launch_bounds__(kLongWarps * 32, 1)
+k_long(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restrict__ pack,
+       unsigned int *__restrict__ ticket)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // tiles first, aligned to 2 KB in the shared window
+    const uint32_t raw_s = smem_u32(smem_raw);
+    const uint32_t align_pad = (2048u - (raw_s & 2047u)) & 2047u;
+    unsigned char *base = smem_raw + align_pad;
+    float *tiles = reinterpret_cast<float *>(base) + (size_t)warp * kLongRing * kLongN2;
+    V *s_pack = reinterpret_cast<V *>(base + (size_t)kLongWarps * kLongRing * kLongTileBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)kLongWarps * kLongRing * kLongTileBytes +
+                                                  (size_t)kLongPackFloats * 4) + warp * kLongRing;
+    if (n_runs == 0) return;
+
+    // stage the pack once per CTA
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(pack);
+        float4 *dst = reinterpret_cast<float4 *>(s_pack);
+        for (int i = threadIdx.x; i < kLongPackFloats / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (lane == 0) {
+        for (int i = 0; i < kLongRing; i++) mbar_init(smem_u32(&bars[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // phase A/B twiddles stay in registers for the whole kernel
+    V twAB[P_B_END];
+#pragma unroll
+    for (int s = 0; s < P_B_END; s++) twAB[s] = s_pack[s * 32 + lane];
+    const TwRegs twab{twAB};
+    const TwSmem twc{s_pack + lane};
+
+    const uint32_t tiles_s = smem_u32(tiles);
+    const uint32_t bars_s = smem_u32(bars);
+    const uint32_t lA0 = laneA(lane, 0), lA1 = laneA(lane, 1);
+    const uint32_t lB = laneB(lane);
+    const uint32_t lC0 = laneC(lane, 0), lC1 = laneC(lane, 1);
+    uint32_t phase_bits = 0;                  // parity of each ring slot's mbarrier
+
+    for (;;) {
+        uint32_t run_idx = 0;
+        if (lane == 0) run_idx = atomicAdd(ticket, 1u);
+        run_idx = __shfl_sync(0xffffffffu, run_idx, 0);
+        if (run_idx >= n_runs) break;
+        const LongRun run = runs[run_idx];
+        const uint32_t npk = run.n_packets;
+        // prime the ring
+        if (lane == 0) {
+            fence_proxy_async();
+            for (uint32_t i = 0; i < (uint32_t)kLongRing && i < npk; i++) {
+                const uint32_t bar = bars_s + 8 * i;
+                mbar_expect_tx(bar, kLongTileBytes);
+                tma_load_1d(tiles_s + i * kLongTileBytes, run.in + (size_t)i * run.in_stride, kLongTileBytes, bar);
+            }
+        }
+        V pe[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) pe[j] = V{0.f, 0.f};
+        float *out = run.out;
+        uint32_t slot_i = 0;
+        for (uint32_t p = 0; p < npk; p++) {
+            const uint32_t tile_s = tiles_s + slot_i * kLongTileBytes;
+            mbar_wait(bars_s + 8 * slot_i, (phase_bits >> slot_i) & 1u);
+            phase_bits ^= 1u << slot_i;
+
+            V O[8], E[8];
+            {
+                Q4 F1[4], F2[4];
+                const float4 *t4 = reinterpret_cast<const float4 *>(tiles + slot_i * kLongN2);
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const float4 u = t4[lane + 64 * m], v = t4[63 - lane + 64 * m];
+                    F1[m] = Q4{u.x, u.y, u.z, u.w};
+                    F2[m] = Q4{v.x, v.y, v.z, v.w};
+                }
+                __syncwarp();       // every lane has its quads: the tile may now be overwritten
+                phase_a(F1, F2, twab, O, E);
+            }
+            // transpose 1: the consumed tile is the scratch (E plane | O plane)
+            {
+                const uint32_t a0 = tile_s + lA0, a1 = tile_s + lA1, b0 = tile_s + lB;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    sts_eo(a0 ^ LWB_KA(j), E[j].x, O[j].x);
+                    sts_eo(a1 ^ LWB_KA(j), E[j].y, O[j].y);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    lds_eo(b0 ^ LWB_KB(j, 0), E[j].x, O[j].x);
+                    lds_eo(b0 ^ LWB_KB(j, 1), E[j].y, O[j].y);
+                }
+                __syncwarp();
+                phase_b(twab, O, E);
+                // transpose 2
+                const uint32_t c0 = tile_s + lC0, c1 = tile_s + lC1;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    sts_eo(b0 ^ LWB_KB(j, 0), E[j].x, O[j].x);
+                    sts_eo(b0 ^ LWB_KB(j, 1), E[j].y, O[j].y);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    lds_eo(c0 ^ LWB_KC(j), E[j].x, O[j].x);
+                    lds_eo(c1 ^ LWB_KC(j), E[j].y, O[j].y);
+                }
+                __syncwarp();
+            }
+            // the tile is free again: refill it with packet p + ring
+            if (lane == 0 && p + kLongRing < npk) {
+                fence_proxy_async();
+                const uint32_t bar = bars_s + 8 * slot_i;
+                mbar_expect_tx(bar, kLongTileBytes);
+                tma_load_1d(tile_s, run.in + (size_t)(p + kLongRing) * run.in_stride, kLongTileBytes, bar);
+            }
+            phase_c_fft(twc, O, E);
+            if (p > 0) {
+                out_stage<false, true>(twc, lane, O, E, pe, run.state, out);
+                out += kLongN2;
+            } else if (run.has_prev) {
+                out_stage<true, true>(twc, lane, O, E, pe, run.state, out);
+                out += kLongN2;
+            } else {
+                out_stage<false, false>(twc, lane, O, E, pe, run.state, out);
+            }
+            slot_i = (slot_i + 1 == (uint32_t)kLongRing) ? 0 : slot_i + 1;
+        }
+        if (run.write_state) {
+            float *s_lo = run.state + lane, *s_hi = run.state + 63 - lane;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int r64 = 64 * rev3(j);
+                const float vx = (j & 1) ? pe[j].x : pe[j].y, vy = (j & 1) ? pe[j].y : pe[j].x;
+                s_lo[r64] = vx; s_hi[r64] = vy;                 // state[m]
+                s_hi[960 - r64] = vx; s_lo[960 - r64] = vy;     // state[1023 - m]: same value (imdct.rs:622-649)
+            }
+        }
+        // every load issued for this run was waited on, so the ring is idle here; the next run
+        // starts again at slot 0 and the per-slot parity bits carry over.
+        __syncwarp();
+    }
+}
+
+inline void long_kernel_configure()
+{
+    cudaFuncSetAttribute(k_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes);
+}
+
+// returns 0 on success; `ticket` is a device word this call zeroes on the stream
+inline int long_launch(cudaStream_t stream, const LongRun *d_runs, uint32_t n_runs, const float *d_pack,
+                       unsigned int *ticket, int sm_count)
+{
+    if (cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream) != cudaSuccess) return 1;
+    const uint32_t want = (n_runs + kLongWarps - 1) / kLongWarps;
+    const uint32_t grid = want < (uint32_t)sm_count ? want : (uint32_t)sm_count;
+    k_long<<<grid, kLongWarps * 32, kLongSmemBytes, stream>>>(d_runs, n_runs, d_pack, ticket);
+    return cudaGetLastError() != cudaSuccess;
+}
+#endif  // __CUDACC__
+
+}  // namespace lwb

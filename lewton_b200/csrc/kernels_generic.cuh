@@ -1,0 +1,439 @@
+// kernels_generic.cuh -- the general synthesis path: any blocksize 6..13, any channel count,
+// mixed short/long sequences, all output formats.  Four kernels, fully parallel over packets:
+//
+//   k_prologue  : inverse coupling -> floor-1 render -> floor x residue   (audio.rs:991-1039)
+//   k_imdct     : inverse MDCT of one (packet, channel) block in shared memory (imdct.rs:291-659)
+//   k_overlap   : window / overlap-add / slice / sample conversion         (audio.rs:1079-1157)
+//   k_save_state: PreviousWindowRight update                                (audio.rs:1121,1154)
+//
+// Bandwidth: this path round-trips the spectrum and the un-windowed IMDCT output through HBM
+// (about 32 B per output sample instead of the algorithmic 8); the fused kernel in
+// kernel_long.cuh is the hot path for the headline configuration, this one is the general
+// fallback every configuration is correct on.
+//
+// Arithmetic rules (parity with the reference): binary32, round-to-nearest, no FMA contraction
+// (-fmad=false), denormals kept (-ftz=false); every butterfly uses the reference's operand order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lwb_common.h"
+
+namespace lwb {
+
+__constant__ float c_inverse_db[256] = {
+#include "floor1_inverse_db.inc"
+};
+
+// ---------------------------------------------------------------------------------------------
+// floor-1, audio.rs:354-435 -- run by one thread per (packet, channel); <= 65 posts, serial
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t d_render_point(uint32_t x0, uint32_t y0, uint32_t x1,
+                                                   uint32_t y1, uint32_t x)
+{
+    // audio.rs:354-367, u32/i32 wrapping like a release build
+    const int32_t dy = (int32_t)(y1 - y0);
+    const uint32_t adx = x1 - x0;
+    const uint32_t ady = (uint32_t)(dy < 0 ? -dy : dy);
+    const uint32_t off = (ady * (x - x0)) / adx;
+    return dy < 0 ? y0 - off : y0 + off;
+}
+
+// Writes the flagged posts in x order as (sx, sy = y * multiplier); returns their count
+// (+1 if a flat tail to n2 was appended, audio.rs:546-547).
+__device__ int d_floor1_posts(const DevFloor1 &fl, const uint32_t *__restrict__ y_in, int n2,
+                              uint16_t *sx, uint16_t *sy)
+{
+    uint32_t fy[LWB_MAX_POSTS];
+    uint64_t flag_lo = 3;        // posts 0..63
+    bool flag64 = false;         // post 64
+    const int np = fl.nposts;
+    const int32_t range = fl.mult == 1 ? 256 : fl.mult == 2 ? 128 : fl.mult == 3 ? 86 : 64;
+    fy[0] = y_in[0];
+    fy[1] = y_in[1];
+    for (int i = 2; i < np; i++) {           // audio.rs:401-429
+        const int li = fl.lo[i], hi = fl.hi[i];
+        const int32_t predicted =
+            (int32_t)d_render_point(fl.x[li], fy[li], fl.x[hi], fy[hi], fl.x[i]);
+        const int32_t val = (int32_t)y_in[i];
+        const int32_t highroom = range - predicted;
+        const int32_t lowroom = predicted;
+        const int32_t room = (highroom < lowroom ? highroom : lowroom) * 2;
+        if (val > 0) {
+            flag_lo |= (1ull << li) | (1ull << hi);     // li, hi < i <= 64
+            if (i < 64) flag_lo |= 1ull << i; else flag64 = true;
+            int32_t r;
+            if (val >= room) {
+                r = highroom > lowroom ? predicted + val - lowroom : predicted - val + highroom - 1;
+            } else {
+                const int32_t t = (val % 2 == 1) ? (-val - 1) : val;
+                r = predicted + (t >> 1);
+            }
+            fy[i] = (uint32_t)r;
+        } else {
+            fy[i] = (uint32_t)predicted;
+        }
+    }
+    int m = 0;
+    uint32_t hx = 0, hy = 0;
+    for (int j = 0; j < np; j++) {           // audio.rs:528-545, in sorted order
+        const int si = fl.sorted[j];
+        const bool flagged = si < 64 ? ((flag_lo >> si) & 1ull) : flag64;
+        if (j == 0 || flagged) {
+            uint32_t v = fy[si];
+            if (v > (uint32_t)range - 1) v = (uint32_t)range - 1;     // audio.rs:431-433
+            hy = v * fl.mult;
+            hx = fl.x[si];
+            sx[m] = (uint16_t)hx;
+            sy[m] = (uint16_t)hy;
+            m++;
+        }
+    }
+    if (hx < (uint32_t)n2) {                 // audio.rs:546-547 flat tail
+        sx[m] = (uint16_t)n2;
+        sy[m] = (uint16_t)hy;
+        m++;
+    }
+    return m;
+}
+
+// Value of the rendered integer curve at bin k: the closed form of render_line (audio.rs:503-524):
+// y0 + sign(dy) * floor(|dy| * (k - x0) / adx) for the segment [x0, x1) containing k.
+__device__ __forceinline__ uint32_t d_floor1_y_at(const uint16_t *sx, const uint16_t *sy, int m, int k)
+{
+    int lo = 0, hi = m - 1;                  // sx[lo] <= k < sx[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)sx[mid] <= k) lo = mid; else hi = mid;
+    }
+    const int x0 = sx[lo], x1 = sx[lo + 1];
+    const int y0 = sy[lo], y1 = sy[lo + 1];
+    const int dy = y1 - y0;
+    const int ady = dy < 0 ? -dy : dy;
+    const int off = (ady * (k - x0)) / (x1 - x0);
+    return (uint32_t)(dy < 0 ? y0 - off : y0 + off);
+}
+
+// audio.rs:762-777
+__device__ __forceinline__ void d_inverse_couple(float &m, float &a)
+{
+    const float m0 = m, a0 = a;
+    if (m0 > 0.f) {
+        if (a0 > 0.f) { a = __fsub_rn(m0, a0); }
+        else { a = m0; m = __fadd_rn(m0, a0); }
+    } else {
+        if (a0 > 0.f) { a = __fadd_rn(m0, a0); }
+        else { a = m0; m = __fsub_rn(m0, a0); }
+    }
+}
+
+constexpr int kPrologueThreads = 256;
+constexpr int kPrologueGroup = 8;            // channels whose floor posts sit in smem at once
+
+// grid.x = packets.  spec[packet] = [channels][n/2] receives floor x decoupled residue.
+__global__ void __launch_bounds__(kPrologueThreads)
+k_prologue(const DevPacket *__restrict__ pkts, const float *__restrict__ residue,
+           const float *__restrict__ dense_floor, const uint8_t *__restrict__ floor_kind,
+           const uint32_t *__restrict__ floor1_y, float *__restrict__ spec)
+{
+    const DevPacket &p = pkts[blockIdx.x];
+    const DevSetup &su = *p.setup;
+    const DevMapping &mp = su.mappings[p.mapping];
+    const int C = p.channels;
+    const int n2 = p.n >> 1;
+    const float *res = residue + p.coeff_off;
+    float *out = spec + p.coeff_off;
+    const int nsteps = mp.n_coupling;
+
+    // 1. inverse coupling, steps in reverse (audio.rs:991-1002).  Every thread owns its bins
+    //    through all steps, so the working copy in `out` needs no synchronisation.
+    for (int k = threadIdx.x; k < n2; k += kPrologueThreads) {
+        if (C <= 8) {
+            float r[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) r[c] = c < C ? res[(size_t)c * n2 + k] : 0.f;
+            for (int s = nsteps - 1; s >= 0; s--) {
+                const int mi = mp.mag[s], ai = mp.ang[s];
+                float mv = 0.f, av = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; c++) { if (c == mi) mv = r[c]; if (c == ai) av = r[c]; }
+                d_inverse_couple(mv, av);
+#pragma unroll
+                for (int c = 0; c < 8; c++) { if (c == mi) r[c] = mv; if (c == ai) r[c] = av; }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) if (c < C) out[(size_t)c * n2 + k] = r[c];
+        } else {
+            for (int c = 0; c < C; c++) out[(size_t)c * n2 + k] = res[(size_t)c * n2 + k];
+            for (int s = nsteps - 1; s >= 0; s--) {
+                float mv = out[(size_t)mp.mag[s] * n2 + k], av = out[(size_t)mp.ang[s] * n2 + k];
+                d_inverse_couple(mv, av);
+                out[(size_t)mp.mag[s] * n2 + k] = mv;
+                out[(size_t)mp.ang[s] * n2 + k] = av;
+            }
+        }
+    }
+
+    // 2. floor curve x residue (audio.rs:1006-1039), kPrologueGroup channels at a time
+    __shared__ uint16_t s_x[kPrologueGroup][LWB_MAX_POSTS + 1];
+    __shared__ uint16_t s_y[kPrologueGroup][LWB_MAX_POSTS + 1];
+    __shared__ int s_m[kPrologueGroup];
+    const uint8_t *kinds = floor_kind + p.pkt_index * C;
+    for (int c0 = 0; c0 < C; c0 += kPrologueGroup) {
+        __syncthreads();
+        const int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0 && c0 + w < C && kinds[c0 + w] == LWB_FLOOR_ONE) {
+            const int c = c0 + w;
+            const DevFloor1 &fl = su.floors[mp.floor_of_channel[c]];
+            s_m[w] = d_floor1_posts(fl, floor1_y + (p.pkt_index * C + c) * LWB_MAX_POSTS, n2,
+                                    s_x[w], s_y[w]);
+        }
+        __syncthreads();
+        for (int g = 0; g < kPrologueGroup && c0 + g < C; g++) {
+            const int c = c0 + g;
+            const int kind = kinds[c];
+            float *oc = out + (size_t)c * n2;
+            for (int k = threadIdx.x; k < n2; k += kPrologueThreads) {
+                float f;
+                if (kind == LWB_FLOOR_ONE)
+                    f = c_inverse_db[d_floor1_y_at(s_x[g], s_y[g], s_m[g], k) & 255u];
+                else if (kind == LWB_FLOOR_DENSE)
+                    f = dense_floor[p.coeff_off + (size_t)c * n2 + k];
+                else
+                    f = 0.f;                           // audio.rs:1021-1024
+                oc[k] = __fmul_rn(f, oc[k]);           // audio.rs:1035-1037
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// inverse MDCT, imdct.rs:291-659, stage by stage in shared memory
+// ---------------------------------------------------------------------------------------------
+// One rotate-and-sum butterfly of step 3 (imdct.rs:36-41 / 94-99 / 161-166): `hi` is the odd
+// index of the upper pair, `lo` of the lower pair.
+__device__ __forceinline__ void d_bfly(float *e, int hi, int lo, float w0, float w1)
+{
+    const float k00 = __fsub_rn(e[hi], e[lo]);
+    const float k01 = __fsub_rn(e[hi - 1], e[lo - 1]);
+    e[hi] = __fadd_rn(e[hi], e[lo]);
+    e[hi - 1] = __fadd_rn(e[hi - 1], e[lo - 1]);
+    e[lo] = __fsub_rn(__fmul_rn(k00, w0), __fmul_rn(k01, w1));
+    e[lo - 1] = __fadd_rn(__fmul_rn(k01, w0), __fmul_rn(k00, w1));
+}
+
+// imdct.rs:201-232, z7 = &zm7[7]
+__device__ __forceinline__ void d_iter_54(float *z7)
+{
+    const float k00 = __fsub_rn(z7[0], z7[-4]);
+    const float y0 = __fadd_rn(z7[0], z7[-4]);
+    const float y2 = __fadd_rn(z7[-2], z7[-6]);
+    const float k22 = __fsub_rn(z7[-2], z7[-6]);
+    z7[0] = __fadd_rn(y0, y2);
+    z7[-2] = __fsub_rn(y0, y2);
+    const float k33 = __fsub_rn(z7[-3], z7[-7]);
+    z7[-4] = __fadd_rn(k00, k33);
+    z7[-6] = __fsub_rn(k00, k33);
+    const float k11 = __fsub_rn(z7[-1], z7[-5]);
+    const float y1 = __fadd_rn(z7[-1], z7[-5]);
+    const float y3 = __fadd_rn(z7[-3], z7[-7]);
+    z7[-1] = __fadd_rn(y1, y3);
+    z7[-3] = __fsub_rn(y1, y3);
+    z7[-5] = __fsub_rn(k11, k22);
+    z7[-7] = __fadd_rn(k11, k22);
+}
+
+constexpr int kImdctThreads = 128;
+
+// grid = (packets, max channels); dynamic smem = n floats (U and V halves).
+// in: spectrum [channels][n/2] at coeff_off; out: x [channels][n] at x_off.
+__global__ void __launch_bounds__(kImdctThreads)
+k_imdct(const DevPacket *__restrict__ pkts, const float *__restrict__ spec, float *__restrict__ xout)
+{
+    const DevPacket &p = pkts[blockIdx.x];
+    const int ch = blockIdx.y;
+    if (ch >= p.channels) return;
+    const DevTables &tb = p.setup->tab[p.blockflag];
+    const int n = p.n, n2 = n >> 1, n4 = n >> 2, n8 = n >> 3;
+    const int ld = tb.bs;
+    const float *__restrict__ A = tb.a;
+    const float *__restrict__ B = tb.b;
+    const float *__restrict__ Cc = tb.c;
+    const float *__restrict__ X = spec + p.coeff_off + (size_t)ch * n2;
+    float *__restrict__ out = xout + p.x_off + (size_t)ch * n;
+    extern __shared__ float smem[];
+    float *U = smem, *V = smem + n2;
+    const int tid = threadIdx.x;
+
+    // step 0 (imdct.rs:337-371): V <- rotated, reflected spectrum
+    for (int t = tid; t < n8; t += kImdctThreads) {
+        const float x0 = X[4 * t], x2 = X[4 * t + 2];
+        const float a0 = A[2 * t], a1 = A[2 * t + 1];
+        V[n2 - 1 - 2 * t] = __fsub_rn(__fmul_rn(x0, a0), __fmul_rn(x2, a1));
+        V[n2 - 2 - 2 * t] = __fadd_rn(__fmul_rn(x0, a1), __fmul_rn(x2, a0));
+        const int d = n4 - 2 - 2 * t, ao = n4 + 2 * t, e = n2 - 3 - 4 * t;
+        const float ne2 = -X[e + 2], ne0 = -X[e];
+        const float b0 = A[ao], b1 = A[ao + 1];
+        V[d + 1] = __fsub_rn(__fmul_rn(ne2, b0), __fmul_rn(ne0, b1));
+        V[d] = __fadd_rn(__fmul_rn(ne2, b1), __fmul_rn(ne0, b0));
+    }
+    __syncthreads();
+    // step 2 (imdct.rs:385-430): U <- V
+    for (int t = tid; t < (n >> 4); t += kImdctThreads) {
+        const int ao = n2 - 8 - 8 * t, hi = n4 + 4 * t, lo = 4 * t;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int o = 2 * h;                  // pair (0,1) uses A[ao+4..5], pair (2,3) A[ao..ao+1]
+            const float w0 = A[ao + 4 - 4 * h], w1 = A[ao + 5 - 4 * h];
+            const float v1 = __fsub_rn(V[hi + o + 1], V[lo + o + 1]);
+            const float v0 = __fsub_rn(V[hi + o], V[lo + o]);
+            U[hi + o + 1] = __fadd_rn(V[hi + o + 1], V[lo + o + 1]);
+            U[hi + o] = __fadd_rn(V[hi + o], V[lo + o]);
+            U[lo + o + 1] = __fsub_rn(__fmul_rn(v1, w0), __fmul_rn(v0, w1));
+            U[lo + o] = __fadd_rn(__fmul_rn(v0, w0), __fmul_rn(v1, w1));
+        }
+    }
+    __syncthreads();
+    // step 3 (imdct.rs:445-477), literal schedule: stage 0, stage 1 (a no-op for n = 64),
+    // stages 2..ld-7.  For n = 64/128 this overlaps what ld654 does again below -- the
+    // reference's behaviour, kept bit for bit.
+    for (int l = 0; l < 2 || l <= ld - 7; l++) {
+        if (l == 1 && n < 128) continue;          // r_loop(lim = n >> 5 = 2): lim >> 2 == 0 iterations
+        const int k0 = n >> (l + 2), k1 = 1 << (l + 3);
+        const int rbits = ld - l - 4;             // r < n >> (l+4)
+        for (int q = tid; q < n8; q += kImdctThreads) {
+            const int r = q & ((1 << rbits) - 1), s = q >> rbits;
+            const int i = n2 - 1 - k0 * s - 2 * r;
+            d_bfly(U, i, i - (k0 >> 1), A[r * k1], A[r * k1 + 1]);
+        }
+        __syncthreads();
+    }
+    // imdct.rs:234-288 (ld654): last three stages per 16-float group
+    {
+        const float a2 = A[n >> 3];
+        for (int g = tid; g < (n >> 5); g += kImdctThreads) {
+            float *z = U + (n2 - 1 - 16 * g);
+            float k00, k11;
+            k00 = __fsub_rn(z[0], z[-8]);   k11 = __fsub_rn(z[-1], z[-9]);
+            z[0] = __fadd_rn(z[0], z[-8]);  z[-1] = __fadd_rn(z[-1], z[-9]);
+            z[-8] = k00;                    z[-9] = k11;
+            k00 = __fsub_rn(z[-2], z[-10]); k11 = __fsub_rn(z[-3], z[-11]);
+            z[-2] = __fadd_rn(z[-2], z[-10]); z[-3] = __fadd_rn(z[-3], z[-11]);
+            z[-10] = __fmul_rn(__fadd_rn(k00, k11), a2);
+            z[-11] = __fmul_rn(__fsub_rn(k11, k00), a2);
+            k00 = __fsub_rn(z[-12], z[-4]); k11 = __fsub_rn(z[-5], z[-13]);
+            z[-4] = __fadd_rn(z[-4], z[-12]); z[-5] = __fadd_rn(z[-5], z[-13]);
+            z[-12] = k11;                   z[-13] = k00;
+            k00 = __fsub_rn(z[-14], z[-6]); k11 = __fsub_rn(z[-7], z[-15]);
+            z[-6] = __fadd_rn(z[-6], z[-14]); z[-7] = __fadd_rn(z[-7], z[-15]);
+            z[-14] = __fmul_rn(__fadd_rn(k00, k11), a2);
+            z[-15] = __fmul_rn(__fsub_rn(k00, k11), a2);
+            d_iter_54(z);
+            d_iter_54(z - 8);
+        }
+    }
+    __syncthreads();
+    // steps 4-6 (imdct.rs:490-528): bit-reverse shuffle U -> V
+    for (int q = tid; q < (n >> 4); q += kImdctThreads) {
+        const int d0 = n4 - 4 - 4 * q, d1 = n2 - 4 - 4 * q;
+        int k4 = tb.bitrev[2 * q];
+        V[d1 + 3] = U[k4 + 0]; V[d1 + 2] = U[k4 + 1]; V[d0 + 3] = U[k4 + 2]; V[d0 + 2] = U[k4 + 3];
+        k4 = tb.bitrev[2 * q + 1];
+        V[d1 + 1] = U[k4 + 0]; V[d1 + 0] = U[k4 + 1]; V[d0 + 1] = U[k4 + 2]; V[d0 + 0] = U[k4 + 3];
+    }
+    __syncthreads();
+    // step 7 (imdct.rs:533-580), in place on V
+    for (int t = tid; t < (n >> 4); t += kImdctThreads) {
+        const int d = 4 * t, e = n2 - 4 - 4 * t, co = 4 * t;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int dd = d + 2 * h, ee = e + 2 - 2 * h;
+            const float c0 = Cc[co + 2 * h], c1 = Cc[co + 2 * h + 1];
+            const float a02 = __fsub_rn(V[dd], V[ee]);
+            const float a11 = __fadd_rn(V[dd + 1], V[ee + 1]);
+            const float b0 = __fadd_rn(__fmul_rn(c1, a02), __fmul_rn(c0, a11));
+            const float b1 = __fsub_rn(__fmul_rn(c1, a11), __fmul_rn(c0, a02));
+            const float b2 = __fadd_rn(V[dd], V[ee]);
+            const float b3 = __fsub_rn(V[dd + 1], V[ee + 1]);
+            V[dd] = __fadd_rn(b2, b0);
+            V[dd + 1] = __fadd_rn(b3, b1);
+            V[ee] = __fsub_rn(b2, b0);
+            V[ee + 1] = __fsub_rn(b1, b3);
+        }
+    }
+    __syncthreads();
+    // step 8 + decode (imdct.rs:589-658)
+    for (int m = tid; m < n4; m += kImdctThreads) {
+        const int ee = n2 - 2 - 2 * m;            // V/B pair consumed for output index m
+        const float v0 = V[ee], v1 = V[ee + 1];
+        const float b0 = B[ee], b1 = B[ee + 1];
+        const float p_odd = __fsub_rn(__fmul_rn(v0, b1), __fmul_rn(v1, b0));
+        const float p_even = __fsub_rn(__fmul_rn(-v0, b0), __fmul_rn(v1, b1));
+        out[m] = p_odd;
+        out[n2 - 1 - m] = -p_odd;
+        out[n2 + m] = p_even;
+        out[n - 1 - m] = p_even;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// window / overlap-add / slice / sample conversion, audio.rs:1079-1157 + samples.rs
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int16_t d_sample_i16(float v)
+{
+    // samples.rs:92-103; Rust's `as i16` truncates toward zero and maps NaN to 0
+    const float fl = __fmul_rn(v, 32768.0f);
+    if (fl > 32767.f) return 32767;
+    if (fl < -32768.f) return -32768;
+    if (fl != fl) return 0;
+    return (int16_t)(int)fl;
+}
+
+constexpr int kOverlapThreads = 256;
+
+template <int FORMAT>
+__global__ void __launch_bounds__(kOverlapThreads)
+k_overlap(const DevPacket *__restrict__ pkts, const float *__restrict__ x, void *__restrict__ pcm)
+{
+    const DevPacket &p = pkts[blockIdx.x];
+    const int ch = blockIdx.y;
+    if (ch >= p.channels || p.plen == 0) return;      // audio.rs:1140-1151: no previous -> no output
+    const int n = p.n;
+    const float *__restrict__ xc = x + p.x_off + (size_t)ch * n;
+    const float *__restrict__ prev;
+    if (p.prev_packet >= 0) {
+        const DevPacket &q = pkts[p.prev_packet];
+        prev = x + q.x_off + (size_t)ch * q.n + p.prev_rs;
+    } else {
+        prev = p.state + (size_t)ch * p.state_stride;
+    }
+    const float *__restrict__ w = p.setup->tab[p.slope_sel].window;
+    const int plen = p.plen, ls = p.ls, olen = p.rs - p.ls;
+    for (int i = threadIdx.x; i < olen; i += kOverlapThreads) {
+        float v = xc[ls + i];
+        if (i < plen)                                  // audio.rs:1116-1118
+            v = __fadd_rn(__fmul_rn(v, w[i]), __fmul_rn(prev[i], w[plen - 1 - i]));
+        if (FORMAT == LWB_OUT_F32_PLANAR)
+            ((float *)pcm)[p.out_off + (size_t)ch * p.out_stride + i] = v;
+        else if (FORMAT == LWB_OUT_I16_PLANAR)
+            ((int16_t *)pcm)[p.out_off + (size_t)ch * p.out_stride + i] = d_sample_i16(v);
+        else if (FORMAT == LWB_OUT_F32_INTERLEAVED)
+            ((float *)pcm)[p.out_off + (size_t)i * p.channels + ch] = v;
+        else
+            ((int16_t *)pcm)[p.out_off + (size_t)i * p.channels + ch] = d_sample_i16(v);
+    }
+}
+
+// grid = (packets, max channels): packets flagged save_state copy x[rs..re) into the stream state.
+__global__ void __launch_bounds__(kOverlapThreads)
+k_save_state(const DevPacket *__restrict__ pkts, const float *__restrict__ x)
+{
+    const DevPacket &p = pkts[blockIdx.x];
+    const int ch = blockIdx.y;
+    if (!p.save_state || ch >= p.channels) return;
+    const float *__restrict__ xc = x + p.x_off + (size_t)ch * p.n + p.rs;
+    float *__restrict__ st = p.state + (size_t)ch * p.state_stride;
+    for (int i = threadIdx.x; i < p.re - p.rs; i += kOverlapThreads) st[i] = xc[i];
+}
+
+}  // namespace lwb

@@ -1,0 +1,1029 @@
+// lwb_api.cu -- the C ABI (include/lewton_b200.h): context, setup, stream state and batch
+// submission.  Host logic mirrors the control flow of lewton's read_audio_packet_generic back
+// half (src/audio.rs:988-1157): which window shape a packet has, whether a previous right half
+// exists, what the packet returns -- all of that is decided here on the host from the mode bits
+// (it never depends on sample values), so the kernels receive fully resolved descriptors and the
+// device never has to be synchronised to learn a length.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernel_long.cuh"
+#include "kernels_generic.cuh"
+#include "lwb_common.h"
+
+namespace lwb {
+int generate_tables(int bs, float *a, float *b, float *c, float *window, uint32_t *bitrev);
+int prepare_floor1(const lwb_floor_desc &d, DevFloor1 *out);
+}  // namespace lwb
+
+using namespace lwb;
+
+// ---------------------------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct lwb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    // grow-only device arenas
+    DevBuf coeffs, dense, pcm, spec, x, desc, kinds, ys, chains, ticket;
+    // pinned staging for descriptors
+    void *h_desc = nullptr;
+    size_t h_desc_cap = 0;
+    size_t x_cap_elems = (size_t)64 << 20;     // IMDCT scratch per round of the generic path (256 MiB)
+};
+
+struct lwb_setup {
+    lwb_ctx *ctx = nullptr;
+    DevSetup host;                 // device pointers inside
+    DevSetup *d_setup = nullptr;
+    std::vector<void *> allocs;
+    uint8_t channels = 0, bs0 = 0, bs1 = 0;
+    uint32_t n_modes = 0;
+    uint32_t n_mappings = 0;
+    std::vector<DevMapping> mappings;   // host copy (validation)
+};
+
+struct lwb_stream {
+    lwb_ctx *ctx = nullptr;
+    const lwb_setup *setup = nullptr;
+    float *d_state = nullptr;      // [channels][n1/2]
+    bool has = false;              // PreviousWindowRight.data.is_some()
+    uint32_t plen = 0;             // per-channel length of the saved right half
+    uint64_t busy_epoch = 0;       // guards against one stream appearing twice in a batch
+};
+
+static int fail(lwb_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (ctx) {
+        ctx->err = what;
+        if (e != cudaSuccess) {
+            ctx->err += ": ";
+            ctx->err += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+
+#define CU(ctx, call)                                                        \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return fail((ctx), LWB_ERR_CUDA, #call, e__); \
+    } while (0)
+
+static int ensure(lwb_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return LWB_OK;
+    if (b.p) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        CU(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 4096;
+    CU(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return LWB_OK;
+}
+
+static int ensure_pinned(lwb_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->h_desc_cap) return LWB_OK;
+    if (ctx->h_desc) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFreeHost(ctx->h_desc);
+        ctx->h_desc = nullptr;
+        ctx->h_desc_cap = 0;
+    }
+    size_t want = bytes * 2 + 4096;
+    CU(ctx, cudaHostAlloc(&ctx->h_desc, want, cudaHostAllocDefault));
+    ctx->h_desc_cap = want;
+    return LWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// library / context
+// ---------------------------------------------------------------------------------------------
+extern "C" int lwb_abi_version(void) { return LWB_ABI_VERSION; }
+
+extern "C" int lwb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int lwb_ctx_create(int device, lwb_ctx **out)
+{
+    if (!out) return LWB_ERR_INVALID;
+    *out = nullptr;
+    int n = lwb_device_count();
+    if (n <= 0 || device < 0 || device >= n) return LWB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LWB_ERR_NO_DEVICE;
+    if (prop.major != 10) return LWB_ERR_NO_DEVICE;       // kernels are built for sm_100a only
+    lwb_ctx *ctx = new (std::nothrow) lwb_ctx();
+    if (!ctx) return LWB_ERR_BUFFER;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return LWB_ERR_CUDA;
+    }
+    if (const char *e = getenv("LWB_SCRATCH_MB")) {
+        long mb = atol(e);
+        if (mb >= 1) ctx->x_cap_elems = (size_t)mb << 18;
+    }
+    long_kernel_configure();
+    *out = ctx;
+    return LWB_OK;
+}
+
+extern "C" void lwb_ctx_destroy(lwb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf *b : {&ctx->coeffs, &ctx->dense, &ctx->pcm, &ctx->spec, &ctx->x, &ctx->desc,
+                      &ctx->kinds, &ctx->ys, &ctx->chains, &ctx->ticket})
+        if (b->p) cudaFree(b->p);
+    if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_in);
+    cudaStreamDestroy(ctx->copy_out);
+    delete ctx;
+}
+
+extern "C" int lwb_ctx_synchronize(lwb_ctx *ctx)
+{
+    if (!ctx) return LWB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return LWB_OK;
+}
+
+extern "C" const char *lwb_last_error(const lwb_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+extern "C" void *lwb_ctx_cuda_stream(lwb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" uint64_t lwb_ctx_launch_count(const lwb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" void *lwb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void lwb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" int lwb_device_alloc(lwb_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) return LWB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMalloc(out, bytes ? bytes : 1));
+    return LWB_OK;
+}
+extern "C" void lwb_device_free(lwb_ctx *ctx, void *p)
+{
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(p);
+}
+extern "C" int lwb_memcpy_h2d(lwb_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return LWB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return LWB_OK;
+}
+extern "C" int lwb_memcpy_d2h(lwb_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return LWB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return LWB_OK;
+}
+
+extern "C" int lwb_tables_generate(int bs, float *a, float *b, float *c, float *window, uint32_t *bitrev)
+{
+    return generate_tables(bs, a, b, c, window, bitrev);
+}
+
+// ---------------------------------------------------------------------------------------------
+// setup
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int upload(lwb_setup *su, const T *host, size_t count, const T **dev)
+{
+    void *p = nullptr;
+    lwb_ctx *ctx = su->ctx;
+    CU(ctx, cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16)));
+    su->allocs.push_back(p);
+    if (count) CU(ctx, cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *dev = (const T *)p;
+    return LWB_OK;
+}
+
+extern "C" void lwb_setup_destroy(lwb_setup *su)
+{
+    if (!su) return;
+    cudaSetDevice(su->ctx->device);
+    cudaStreamSynchronize(su->ctx->stream);
+    for (void *p : su->allocs) cudaFree(p);
+    delete su;
+}
+
+extern "C" int lwb_setup_create(lwb_ctx *ctx, const lwb_setup_desc *d, lwb_setup **out)
+{
+    if (!ctx || !d || !out) return LWB_ERR_INVALID;
+    *out = nullptr;
+    // header.rs:239-243 (blocksizes, channels)
+    if (d->blocksize_0 < 6 || d->blocksize_0 > 13 || d->blocksize_1 < 6 || d->blocksize_1 > 13 ||
+        d->blocksize_0 > d->blocksize_1 || d->audio_channels == 0)
+        return fail(ctx, LWB_ERR_BAD_FORMAT, "setup: blocksizes/channels out of range");
+    if (d->n_modes == 0 || d->n_modes > LWB_MAX_MODES || d->n_mappings == 0 || d->n_mappings > 64 ||
+        d->n_floors == 0 || d->n_floors > 64 || !d->modes || !d->mappings || !d->floors)
+        return fail(ctx, LWB_ERR_INVALID, "setup: counts out of range");
+    CU(ctx, cudaSetDevice(ctx->device));
+    lwb_setup *su = new (std::nothrow) lwb_setup();
+    if (!su) return LWB_ERR_BUFFER;
+    su->ctx = ctx;
+    su->channels = d->audio_channels;
+    su->bs0 = d->blocksize_0;
+    su->bs1 = d->blocksize_1;
+    su->n_modes = d->n_modes;
+    su->n_mappings = d->n_mappings;
+    std::memset(&su->host, 0, sizeof(su->host));
+    int rc = LWB_OK;
+    // tables (header_cached.rs:33-41): the caller's own, or generated here
+    for (int i = 0; i < 2 && rc == LWB_OK; i++) {
+        const int bs = i ? d->blocksize_1 : d->blocksize_0;
+        const size_t n = (size_t)1 << bs;
+        std::vector<float> a(n / 2), b(n / 2), c(n / 4), w(n / 2);
+        std::vector<uint32_t> br(n / 8);
+        const lwb_tables_ref &t = d->tables[i];
+        if (t.a) {
+            if (!t.b || !t.c || !t.window || !t.bitrev) { rc = LWB_ERR_INVALID; break; }
+            std::copy(t.a, t.a + n / 2, a.begin());
+            std::copy(t.b, t.b + n / 2, b.begin());
+            std::copy(t.c, t.c + n / 4, c.begin());
+            std::copy(t.window, t.window + n / 2, w.begin());
+            std::copy(t.bitrev, t.bitrev + n / 8, br.begin());
+        } else {
+            generate_tables(bs, a.data(), b.data(), c.data(), w.data(), br.data());
+        }
+        DevTables &dt = su->host.tab[i];
+        dt.bs = bs;
+        if ((rc = upload(su, a.data(), a.size(), &dt.a)) || (rc = upload(su, b.data(), b.size(), &dt.b)) ||
+            (rc = upload(su, c.data(), c.size(), &dt.c)) || (rc = upload(su, w.data(), w.size(), &dt.window)) ||
+            (rc = upload(su, br.data(), br.size(), &dt.bitrev)))
+            break;
+        dt.pack = nullptr;
+        if (bs == kLongBs) {
+            std::vector<float> pack(kLongPackFloats);
+            long_build_pack(a.data(), b.data(), c.data(), w.data(), pack.data());
+            if ((rc = upload(su, pack.data(), pack.size(), &dt.pack))) break;
+        }
+        // the synchronous copies above read from vectors that die here
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = LWB_ERR_CUDA;
+    }
+    std::vector<DevFloor1> floors(d->n_floors);
+    for (uint32_t i = 0; i < d->n_floors && rc == LWB_OK; i++) rc = prepare_floor1(d->floors[i], &floors[i]);
+    su->mappings.resize(d->n_mappings);
+    for (uint32_t i = 0; i < d->n_mappings && rc == LWB_OK; i++) {
+        const lwb_mapping_desc &m = d->mappings[i];
+        DevMapping &dm = su->mappings[i];
+        std::memset(&dm, 0, sizeof(dm));
+        if (m.coupling_steps > LWB_MAX_COUPLING || m.submaps == 0 || m.submaps > LWB_MAX_SUBMAPS) {
+            rc = LWB_ERR_BAD_FORMAT;
+            break;
+        }
+        dm.n_coupling = m.coupling_steps;
+        for (int s = 0; s < m.coupling_steps; s++) {
+            // header.rs:1006-1011
+            if (m.magnitudes[s] == m.angles[s] || m.magnitudes[s] >= d->audio_channels ||
+                m.angles[s] >= d->audio_channels) {
+                rc = LWB_ERR_BAD_FORMAT;
+                break;
+            }
+            dm.mag[s] = m.magnitudes[s];
+            dm.ang[s] = m.angles[s];
+        }
+        for (int c = 0; c < d->audio_channels && rc == LWB_OK; c++) {
+            if (m.mux[c] >= m.submaps || m.submap_floors[m.mux[c]] >= d->n_floors) {
+                rc = LWB_ERR_BAD_FORMAT;      // header.rs:1023-1026, 1043-1047
+                break;
+            }
+            dm.floor_of_channel[c] = m.submap_floors[m.mux[c]];
+        }
+    }
+    for (uint32_t i = 0; i < d->n_modes && rc == LWB_OK; i++) {
+        if (d->modes[i].mapping >= d->n_mappings) { rc = LWB_ERR_BAD_FORMAT; break; }   // header.rs:1067-1072
+        su->host.mode_blockflag[i] = d->modes[i].blockflag ? 1 : 0;
+        su->host.mode_mapping[i] = d->modes[i].mapping;
+    }
+    if (rc == LWB_OK) rc = upload(su, floors.data(), floors.size(), &su->host.floors);
+    if (rc == LWB_OK) rc = upload(su, su->mappings.data(), su->mappings.size(), &su->host.mappings);
+    su->host.channels = d->audio_channels;
+    su->host.bs0 = d->blocksize_0;
+    su->host.bs1 = d->blocksize_1;
+    su->host.n_floors = (uint8_t)d->n_floors;
+    if (rc == LWB_OK) {
+        const DevSetup *dp = nullptr;
+        rc = upload(su, &su->host, 1, &dp);
+        su->d_setup = const_cast<DevSetup *>(dp);
+    }
+    if (rc == LWB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = LWB_ERR_CUDA;
+    if (rc != LWB_OK) {
+        lwb_setup_destroy(su);
+        if (ctx->err.empty() || rc != LWB_ERR_CUDA) ctx->err = "setup: rejected (see header.rs validation rules)";
+        return rc;
+    }
+    *out = su;
+    return LWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stream state
+// ---------------------------------------------------------------------------------------------
+static size_t state_stride(const lwb_setup *su) { return (size_t)1 << (su->bs1 - 1); }
+
+extern "C" int lwb_stream_open(lwb_ctx *ctx, const lwb_setup *su, lwb_stream **out)
+{
+    if (!ctx || !su || !out || su->ctx != ctx) return LWB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    lwb_stream *s = new (std::nothrow) lwb_stream();
+    if (!s) return LWB_ERR_BUFFER;
+    s->ctx = ctx;
+    s->setup = su;
+    cudaError_t e = cudaMalloc((void **)&s->d_state, su->channels * state_stride(su) * sizeof(float));
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(ctx, LWB_ERR_CUDA, "stream_open: cudaMalloc", e);
+    }
+    *out = s;
+    return LWB_OK;
+}
+
+extern "C" void lwb_stream_destroy(lwb_stream *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    cudaFree(s->d_state);
+    delete s;
+}
+
+extern "C" int lwb_stream_reset(lwb_stream *s)
+{
+    if (!s) return LWB_ERR_INVALID;
+    s->has = false;
+    s->plen = 0;
+    return LWB_OK;
+}
+extern "C" int lwb_stream_is_empty(const lwb_stream *s) { return (!s || !s->has) ? 1 : 0; }
+extern "C" uint32_t lwb_stream_state_len(const lwb_stream *s) { return (s && s->has) ? s->plen : 0; }
+
+extern "C" int lwb_stream_clone(const lwb_stream *s, lwb_stream **out)
+{
+    if (!s || !out) return LWB_ERR_INVALID;
+    int rc = lwb_stream_open(s->ctx, s->setup, out);
+    if (rc) return rc;
+    (*out)->has = s->has;
+    (*out)->plen = s->plen;
+    lwb_ctx *ctx = s->ctx;
+    CU(ctx, cudaMemcpyAsync((*out)->d_state, s->d_state,
+                            s->setup->channels * state_stride(s->setup) * sizeof(float),
+                            cudaMemcpyDeviceToDevice, ctx->stream));
+    return LWB_OK;
+}
+
+extern "C" int lwb_stream_export_state(lwb_stream *s, float *out)
+{
+    if (!s || !out) return LWB_ERR_INVALID;
+    if (!s->has) return LWB_OK;
+    lwb_ctx *ctx = s->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpy2DAsync(out, s->plen * sizeof(float), s->d_state, state_stride(s->setup) * sizeof(float),
+                              s->plen * sizeof(float), s->setup->channels, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return LWB_OK;
+}
+
+extern "C" int lwb_stream_import_state(lwb_stream *s, const float *data, uint32_t len)
+{
+    if (!s || (!data && len)) return LWB_ERR_INVALID;
+    if (len > state_stride(s->setup)) return LWB_ERR_BUFFER;
+    lwb_ctx *ctx = s->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (len) {
+        CU(ctx, cudaMemcpy2DAsync(s->d_state, state_stride(s->setup) * sizeof(float), data, len * sizeof(float),
+                                  len * sizeof(float), s->setup->channels, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    s->has = true;
+    s->plen = len;
+    return LWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// window geometry, audio.rs:1056-1073 (and its twin :889-908)
+// ---------------------------------------------------------------------------------------------
+struct Geom {
+    uint32_t n, ls, le, rs, re;
+    uint8_t blockflag, slope_sel, mapping;
+};
+
+static int geometry(const lwb_setup *su, uint8_t mode, int prev_flag, int next_flag, Geom *g)
+{
+    if (mode >= su->n_modes) return LWB_ERR_BAD_FORMAT;          // audio.rs:926-930
+    const bool lng = su->host.mode_blockflag[mode] != 0;
+    const uint32_t n = 1u << (lng ? su->bs1 : su->bs0);
+    const uint32_t n0 = 1u << su->bs0;
+    const bool prev = lng ? (prev_flag != 0) : true;             // short blocks: map_or(true, ..)
+    const bool next = lng ? (next_flag != 0) : true;
+    g->n = n;
+    g->blockflag = lng;
+    g->mapping = su->host.mode_mapping[mode];
+    if (prev) { g->ls = 0; g->le = n >> 1; g->slope_sel = lng; }
+    else { g->ls = (n - n0) >> 2; g->le = (n + n0) >> 2; g->slope_sel = 0; }
+    if (next) { g->rs = n >> 1; g->re = n; }
+    else { g->rs = (n * 3 - n0) >> 2; g->re = (n * 3 + n0) >> 2; }
+    return LWB_OK;
+}
+
+extern "C" int lwb_decoded_sample_count(const lwb_setup *su, uint8_t mode, int prev_flag, int next_flag,
+                                        uint32_t *n_samples)
+{
+    if (!su || !n_samples) return LWB_ERR_INVALID;
+    Geom g;
+    int rc = geometry(su, mode, prev_flag, next_flag, &g);
+    if (rc) return rc;
+    *n_samples = g.rs - g.ls;
+    return LWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch planning
+// ---------------------------------------------------------------------------------------------
+struct PlanPacket {
+    Geom g;
+    uint32_t plen;          // 0: no previous half -> 0 samples out
+    uint64_t coeff_off;     // absolute element offset
+    uint64_t sample_pos;    // samples (per channel) produced by the chain before this packet
+};
+
+struct PlanChain {
+    lwb_chain *c;
+    std::vector<PlanPacket> pk;
+    bool end_has;           // stream state after the planned packets
+    uint32_t end_plen;
+    bool clear_after;       // OLA guard fired on packet pk.size(): state becomes empty
+};
+
+static size_t elem_size(int fmt) { return (fmt == LWB_OUT_F32_PLANAR || fmt == LWB_OUT_F32_INTERLEAVED) ? 4 : 2; }
+static bool is_planar(int fmt) { return fmt == LWB_OUT_F32_PLANAR || fmt == LWB_OUT_I16_PLANAR; }
+
+static int plan_chain(lwb_chain *c, PlanChain *pc)
+{
+    const lwb_stream *s = c->stream;
+    const lwb_setup *su = s->setup;
+    bool has = s->has;
+    uint32_t plen = s->plen;
+    uint64_t coeff = c->coeff_offset, pos = 0;
+    pc->c = c;
+    pc->clear_after = false;
+    c->status = LWB_OK;
+    pc->pk.reserve(c->n_packets);
+    for (uint32_t i = 0; i < c->n_packets; i++) {
+        PlanPacket pp;
+        int rc = geometry(su, c->mode_numbers[i], c->prev_window_flags ? c->prev_window_flags[i] : 1,
+                          c->next_window_flags ? c->next_window_flags[i] : 1, &pp.g);
+        if (rc) { c->status = rc; break; }
+        if (has) {
+            const uint32_t slope_len = 1u << ((pp.g.slope_sel ? su->bs1 : su->bs0) - 1);
+            if (slope_len < plen) {             // audio.rs:1107-1111; :1083 has already taken the state
+                c->status = LWB_ERR_BAD_FORMAT;
+                pc->clear_after = true;
+                break;
+            }
+            if (pp.g.ls + plen > pp.g.n) {      // chan[range] would be out of bounds: a panic in the reference
+                c->status = LWB_ERR_MISMATCH;
+                break;
+            }
+        }
+        pp.plen = has ? plen : 0;
+        pp.coeff_off = coeff;
+        pp.sample_pos = pos;
+        coeff += (uint64_t)su->channels * (pp.g.n >> 1);
+        if (has) pos += pp.g.rs - pp.g.ls;
+        has = true;
+        plen = pp.g.re - pp.g.rs;
+        pc->pk.push_back(pp);
+    }
+    pc->end_has = pc->clear_after ? false : has;
+    pc->end_plen = pc->clear_after ? 0 : plen;
+    c->packets_done = (uint32_t)pc->pk.size();
+    c->n_samples = (uint32_t)pos;
+    return LWB_OK;
+}
+
+template <typename K, typename... Args>
+static int launch(lwb_ctx *ctx, K kernel, dim3 grid, dim3 block, size_t smem, Args... args)
+{
+    kernel<<<grid, block, smem, ctx->stream>>>(args...);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, LWB_ERR_CUDA, "kernel launch", e);
+    return LWB_OK;
+}
+
+struct DevArenas {
+    const float *coeffs;      // device
+    const float *dense;       // device or null
+    const uint8_t *kinds;     // device or null
+    const uint32_t *ys;       // device or null
+    uint64_t kinds_row0;      // first packet row uploaded
+    void *pcm;                // device
+    uint64_t coeff_base;      // element offset that device coeffs[0] corresponds to
+    uint64_t pcm_base;        // element offset that device pcm[0] corresponds to
+};
+
+// Generic path: rounds of packets bounded by the IMDCT scratch.
+static int run_generic(lwb_ctx *ctx, std::vector<PlanChain> &plan, const lwb_batch_io *io, const DevArenas &ar)
+{
+    size_t maxp = 0;
+    for (auto &pc : plan) maxp = std::max(maxp, pc.pk.size());
+    if (maxp == 0) return LWB_OK;
+    // x elements of one "packet column" (packet i of every chain), to size the rounds
+    std::vector<uint32_t> start(plan.size(), 0);
+    const bool planar = is_planar(io->out_format);
+    while (true) {
+        // pick how many packets per chain go into this round
+        size_t x_elems = 0, n_desc = 0, spec_lo = ~(size_t)0, spec_hi = 0;
+        std::vector<uint32_t> take(plan.size(), 0);
+        bool any = false;
+        for (uint32_t step = 0;; step++) {
+            size_t add = 0;
+            bool more = false;
+            for (size_t ci = 0; ci < plan.size(); ci++) {
+                const uint32_t i = start[ci] + step;
+                if (i < plan[ci].pk.size() && take[ci] == step) {
+                    add += (size_t)plan[ci].c->stream->setup->channels * plan[ci].pk[i].g.n;
+                    more = true;
+                }
+            }
+            if (!more) break;
+            if (x_elems && x_elems + add > ctx->x_cap_elems) break;
+            for (size_t ci = 0; ci < plan.size(); ci++) {
+                const uint32_t i = start[ci] + step;
+                if (i < plan[ci].pk.size() && take[ci] == step) { take[ci]++; n_desc++; }
+            }
+            x_elems += add;
+            any = true;
+        }
+        if (!any) break;
+        int rc;
+        if ((rc = ensure_pinned(ctx, n_desc * sizeof(DevPacket)))) return rc;
+        if ((rc = ensure(ctx, ctx->desc, n_desc * sizeof(DevPacket)))) return rc;
+        if ((rc = ensure(ctx, ctx->x, x_elems * sizeof(float)))) return rc;
+        // the pinned descriptor staging is reused every round: wait for the previous upload
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        DevPacket *hp = (DevPacket *)ctx->h_desc;
+        size_t di = 0, xo = 0;
+        unsigned maxc = 1, maxn = 64;
+        for (size_t ci = 0; ci < plan.size(); ci++) {
+            PlanChain &pc = plan[ci];
+            const lwb_stream *s = pc.c->stream;
+            const lwb_setup *su = s->setup;
+            const unsigned C = su->channels;
+            for (uint32_t k = 0; k < take[ci]; k++) {
+                const PlanPacket &pp = pc.pk[start[ci] + k];
+                DevPacket &d = hp[di];
+                std::memset(&d, 0, sizeof(d));
+                d.setup = su->d_setup;
+                d.state = s->d_state;
+                d.coeff_off = pp.coeff_off - ar.coeff_base;
+                d.x_off = xo;
+                d.out_stride = pc.c->out_stride;
+                d.out_off = pc.c->out_offset - ar.pcm_base + (planar ? pp.sample_pos : pp.sample_pos * C);
+                d.pkt_index = pc.c->packet_index + start[ci] + k - ar.kinds_row0;
+                d.prev_packet = k ? (int32_t)(di - 1) : -1;
+                d.prev_rs = k ? hp[di - 1].rs : 0;
+                d.state_stride = (uint32_t)state_stride(su);
+                d.n = (uint16_t)pp.g.n;
+                d.ls = (uint16_t)pp.g.ls;
+                d.rs = (uint16_t)pp.g.rs;
+                d.re = (uint16_t)pp.g.re;
+                d.plen = (uint16_t)pp.plen;
+                d.blockflag = pp.g.blockflag;
+                d.mapping = pp.g.mapping;
+                d.slope_sel = pp.g.slope_sel;
+                d.channels = (uint8_t)C;
+                d.save_state = (k + 1 == take[ci]);
+                xo += (size_t)C * pp.g.n;
+                spec_lo = std::min<size_t>(spec_lo, d.coeff_off);
+                spec_hi = std::max<size_t>(spec_hi, d.coeff_off + (size_t)C * (pp.g.n >> 1));
+                maxc = std::max(maxc, C);
+                maxn = std::max<unsigned>(maxn, pp.g.n);
+                di++;
+            }
+            start[ci] += take[ci];
+        }
+        CU(ctx, cudaMemcpyAsync(ctx->desc.p, hp, n_desc * sizeof(DevPacket), cudaMemcpyHostToDevice, ctx->stream));
+        const DevPacket *dp = (const DevPacket *)ctx->desc.p;
+        const float *spec = ar.coeffs;
+        if (io->entry == LWB_ENTRY_RESIDUE) {
+            if ((rc = ensure(ctx, ctx->spec, spec_hi * sizeof(float)))) return rc;
+            if ((rc = launch(ctx, k_prologue, dim3((unsigned)n_desc), dim3(kPrologueThreads), 0, dp, ar.coeffs,
+                             ar.dense, ar.kinds, ar.ys, (float *)ctx->spec.p)))
+                return rc;
+            spec = (const float *)ctx->spec.p;
+        }
+        if ((rc = launch(ctx, k_imdct, dim3((unsigned)n_desc, maxc), dim3(kImdctThreads), maxn * sizeof(float), dp,
+                         spec, (float *)ctx->x.p)))
+            return rc;
+        dim3 g2((unsigned)n_desc, maxc), b2(kOverlapThreads);
+        switch (io->out_format) {
+        case LWB_OUT_F32_PLANAR: rc = launch(ctx, k_overlap<LWB_OUT_F32_PLANAR>, g2, b2, 0, dp, (const float *)ctx->x.p, ar.pcm); break;
+        case LWB_OUT_I16_PLANAR: rc = launch(ctx, k_overlap<LWB_OUT_I16_PLANAR>, g2, b2, 0, dp, (const float *)ctx->x.p, ar.pcm); break;
+        case LWB_OUT_F32_INTERLEAVED: rc = launch(ctx, k_overlap<LWB_OUT_F32_INTERLEAVED>, g2, b2, 0, dp, (const float *)ctx->x.p, ar.pcm); break;
+        default: rc = launch(ctx, k_overlap<LWB_OUT_I16_INTERLEAVED>, g2, b2, 0, dp, (const float *)ctx->x.p, ar.pcm); break;
+        }
+        if (rc) return rc;
+        if ((rc = launch(ctx, k_save_state, g2, b2, 0, dp, (const float *)ctx->x.p))) return rc;
+    }
+    return LWB_OK;
+}
+
+// Fused path (kernel_long.cuh): every packet of the batch is a long block with long neighbours
+// of the fast blocksize, spectrum entry, planar f32 out.
+static bool long_eligible(const std::vector<PlanChain> &plan, const lwb_batch_io *io)
+{
+    if (io->entry != LWB_ENTRY_SPECTRUM || io->out_format != LWB_OUT_F32_PLANAR) return false;
+    if (getenv("LWB_FORCE_GENERIC")) return false;
+    for (auto &pc : plan) {
+        const lwb_setup *su = pc.c->stream->setup;
+        if (su->bs1 != kLongBs) return false;
+        if ((pc.c->out_offset & 3) || (pc.c->out_stride & 3) || (pc.c->coeff_offset & 3)) return false;
+        for (auto &pp : pc.pk) {
+            if (!pp.g.blockflag || pp.g.ls != 0 || pp.g.rs != (pp.g.n >> 1) || pp.g.re != pp.g.n) return false;
+            if (pp.plen != 0 && pp.plen != (pp.g.n >> 1)) return false;
+        }
+    }
+    return true;
+}
+
+// Runs for the fused kernel.  A chain (one channel of one stream) is cut into several runs when
+// there are too few chains to fill the machine; every run after the first re-transforms the
+// packet before its first one as a primer (its right half is all the run needs), which keeps
+// runs independent at the cost of one extra IMDCT per cut.
+static int run_long(lwb_ctx *ctx, std::vector<PlanChain> &plan, const DevArenas &ar)
+{
+    size_t n_chan_chains = 0, total_blocks = 0;
+    for (auto &pc : plan)
+        if (!pc.pk.empty()) {
+            n_chan_chains += pc.c->stream->setup->channels;
+            total_blocks += pc.pk.size() * pc.c->stream->setup->channels;
+        }
+    if (!n_chan_chains) return LWB_OK;
+    const size_t warp_slots = (size_t)ctx->sm_count * kLongWarps;
+    size_t target_runs = warp_slots * 4;                   // ~4 runs per warp evens out the tail
+    if (const char *e = getenv("LWB_LONG_TARGET_RUNS")) target_runs = (size_t)atol(e);
+    const size_t min_run = 8;                              // packets per run below which cutting costs > 12%
+    // group chains by twiddle pack (one launch per pack; normally exactly one)
+    std::vector<const float *> packs;
+    for (auto &pc : plan) {
+        if (pc.pk.empty()) continue;
+        const float *pk = pc.c->stream->setup->host.tab[1].pack;
+        if (std::find(packs.begin(), packs.end(), pk) == packs.end()) packs.push_back(pk);
+    }
+    int rc;
+    if (!ctx->ticket.p && (rc = ensure(ctx, ctx->ticket, 256))) return rc;
+    for (const float *pack : packs) {
+        std::vector<LongRun> runs;
+        for (auto &pc : plan) {
+            if (pc.pk.empty()) continue;
+            const lwb_stream *s = pc.c->stream;
+            const lwb_setup *su = s->setup;
+            if (su->host.tab[1].pack != pack) continue;
+            const unsigned C = su->channels;
+            const size_t P = pc.pk.size();
+            size_t cuts = 1;
+            if (n_chan_chains < target_runs) cuts = (target_runs + n_chan_chains - 1) / n_chan_chains;
+            cuts = std::max<size_t>(1, std::min(cuts, P / min_run));
+            const bool has_prev = pc.pk[0].plen != 0;
+            for (unsigned ch = 0; ch < C; ch++) {
+                const float *in0 = ar.coeffs + (pc.pk[0].coeff_off - ar.coeff_base) + (size_t)ch * kLongN2;
+                float *out0 = (float *)ar.pcm + (pc.c->out_offset - ar.pcm_base) + (size_t)ch * pc.c->out_stride;
+                for (size_t k = 0; k < cuts; k++) {
+                    const size_t p0 = P * k / cuts, p1 = P * (k + 1) / cuts;   // this run emits packets [p0, p1)
+                    LongRun r;
+                    std::memset(&r, 0, sizeof(r));
+                    r.in_stride = (uint32_t)(C * kLongN2);
+                    r.state = s->d_state + (size_t)ch * state_stride(su);
+                    r.write_state = (k + 1 == cuts);
+                    if (k == 0) {
+                        r.in = in0;
+                        r.n_packets = (uint32_t)(p1 - p0);
+                        r.has_prev = has_prev;
+                        r.out = out0;
+                    } else {
+                        r.in = in0 + (p0 - 1) * (size_t)r.in_stride;           // primer = packet p0 - 1
+                        r.n_packets = (uint32_t)(p1 - p0 + 1);
+                        r.has_prev = 0;
+                        // samples emitted before packet p0: packets 0..p0-1, minus the first if no state
+                        r.out = out0 + (size_t)(p0 - (has_prev ? 0 : 1)) * kLongN2;
+                    }
+                    runs.push_back(r);
+                }
+            }
+        }
+        if (runs.empty()) continue;
+        if ((rc = ensure_pinned(ctx, runs.size() * sizeof(LongRun)))) return rc;
+        if ((rc = ensure(ctx, ctx->chains, runs.size() * sizeof(LongRun)))) return rc;
+        CU(ctx, cudaStreamSynchronize(ctx->stream));          // pinned staging is reused
+        std::memcpy(ctx->h_desc, runs.data(), runs.size() * sizeof(LongRun));
+        CU(ctx, cudaMemcpyAsync(ctx->chains.p, ctx->h_desc, runs.size() * sizeof(LongRun), cudaMemcpyHostToDevice,
+                                ctx->stream));
+        if (long_launch(ctx->stream, (const LongRun *)ctx->chains.p, (uint32_t)runs.size(), pack,
+                        (unsigned int *)ctx->ticket.p, ctx->sm_count))
+            return fail(ctx, LWB_ERR_CUDA, "long kernel launch", cudaGetLastError());
+        ctx->launches++;
+    }
+    return LWB_OK;
+}
+
+extern "C" int lwb_decode_chains(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io)
+{
+    if (!ctx || (!chains && n_chains) || !io) return LWB_ERR_INVALID;
+    if (io->entry != LWB_ENTRY_SPECTRUM && io->entry != LWB_ENTRY_RESIDUE) return fail(ctx, LWB_ERR_INVALID, "bad entry");
+    if (io->memory != LWB_MEM_HOST && io->memory != LWB_MEM_DEVICE) return fail(ctx, LWB_ERR_INVALID, "bad memory space");
+    if (io->out_format < 0 || io->out_format > LWB_OUT_I16_INTERLEAVED) return fail(ctx, LWB_ERR_INVALID, "bad out_format");
+    if (n_chains == 0) return LWB_OK;
+    if (!io->coeffs || !io->pcm) return fail(ctx, LWB_ERR_INVALID, "null arena");
+    CU(ctx, cudaSetDevice(ctx->device));
+    static uint64_t epoch = 0;
+    epoch++;
+    const bool residue = io->entry == LWB_ENTRY_RESIDUE;
+    const bool planar = is_planar(io->out_format);
+    std::vector<PlanChain> plan(n_chains);
+    uint64_t c_lo = ~0ull, c_hi = 0, o_lo = ~0ull, o_hi = 0, r_lo = ~0ull, r_hi = 0;
+    int uniform_c = -1;
+    bool need_dense = false;
+    for (size_t i = 0; i < n_chains; i++) {
+        lwb_chain *c = &chains[i];
+        if (!c->stream || c->stream->ctx != ctx || (c->n_packets && !c->mode_numbers))
+            return fail(ctx, LWB_ERR_INVALID, "chain: bad stream or mode list");
+        if (c->stream->busy_epoch == epoch) return fail(ctx, LWB_ERR_INVALID, "a stream appears in two chains of one batch");
+        c->stream->busy_epoch = epoch;
+        const int C = c->stream->setup->channels;
+        if (residue) {
+            if (uniform_c < 0) uniform_c = C;
+            if (uniform_c != C) return fail(ctx, LWB_ERR_INVALID, "residue batches need one channel count");
+            if (!io->floor_kind) return fail(ctx, LWB_ERR_INVALID, "residue entry needs floor_kind");
+        }
+        plan_chain(c, &plan[i]);
+        PlanChain &pc = plan[i];
+        if (pc.pk.empty()) continue;
+        const PlanPacket &last = pc.pk.back();
+        c_lo = std::min(c_lo, c->coeff_offset);
+        c_hi = std::max(c_hi, last.coeff_off + (uint64_t)C * (last.g.n >> 1));
+        const uint64_t ext = planar ? (uint64_t)(C - 1) * c->out_stride + c->n_samples : (uint64_t)c->n_samples * C;
+        if (planar && c->out_stride < c->n_samples) return fail(ctx, LWB_ERR_BUFFER, "chain: out_stride smaller than the samples produced");
+        o_lo = std::min(o_lo, c->out_offset);
+        o_hi = std::max(o_hi, c->out_offset + ext);
+        if (residue) {
+            r_lo = std::min(r_lo, c->packet_index);
+            r_hi = std::max<uint64_t>(r_hi, c->packet_index + pc.pk.size());
+            for (uint64_t r = c->packet_index * C; r < (c->packet_index + pc.pk.size()) * C; r++) {
+                const uint8_t kd = io->floor_kind[r];
+                if (kd > LWB_FLOOR_DENSE) return fail(ctx, LWB_ERR_INVALID, "floor_kind out of range");
+                if (kd == LWB_FLOOR_ONE && !io->floor1_y) return fail(ctx, LWB_ERR_INVALID, "floor1_y missing");
+                if (kd == LWB_FLOOR_DENSE) need_dense = true;
+            }
+        }
+    }
+    if (need_dense && !io->dense_floor) return fail(ctx, LWB_ERR_INVALID, "dense_floor missing");
+    int rc = LWB_OK;
+    if (c_hi > c_lo) {
+        DevArenas ar;
+        std::memset(&ar, 0, sizeof(ar));
+        const size_t esz = elem_size(io->out_format);
+        if (io->memory == LWB_MEM_HOST) {
+            // stage: H2D of the used coefficient range, D2H of the used pcm range
+            if ((rc = ensure(ctx, ctx->coeffs, (c_hi - c_lo) * sizeof(float)))) return rc;
+            if (o_hi > o_lo && (rc = ensure(ctx, ctx->pcm, (o_hi - o_lo) * esz))) return rc;
+            CU(ctx, cudaMemcpyAsync(ctx->coeffs.p, io->coeffs + c_lo, (c_hi - c_lo) * sizeof(float),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+            ar.coeffs = (const float *)ctx->coeffs.p;
+            ar.coeff_base = c_lo;
+            if (need_dense) {
+                if ((rc = ensure(ctx, ctx->dense, (c_hi - c_lo) * sizeof(float)))) return rc;
+                CU(ctx, cudaMemcpyAsync(ctx->dense.p, io->dense_floor + c_lo, (c_hi - c_lo) * sizeof(float),
+                                        cudaMemcpyHostToDevice, ctx->stream));
+                ar.dense = (const float *)ctx->dense.p;
+            }
+            ar.pcm = ctx->pcm.p;
+            ar.pcm_base = o_lo;
+        } else {
+            ar.coeffs = io->coeffs;
+            ar.dense = io->dense_floor;
+            ar.pcm = io->pcm;
+        }
+        if (residue) {
+            const size_t rows = (size_t)(r_hi - r_lo) * uniform_c;
+            if ((rc = ensure(ctx, ctx->kinds, rows))) return rc;
+            CU(ctx, cudaMemcpyAsync(ctx->kinds.p, io->floor_kind + r_lo * uniform_c, rows, cudaMemcpyHostToDevice, ctx->stream));
+            ar.kinds = (const uint8_t *)ctx->kinds.p;
+            if (io->floor1_y) {
+                if ((rc = ensure(ctx, ctx->ys, rows * LWB_MAX_POSTS * sizeof(uint32_t)))) return rc;
+                CU(ctx, cudaMemcpyAsync(ctx->ys.p, io->floor1_y + r_lo * uniform_c * LWB_MAX_POSTS,
+                                        rows * LWB_MAX_POSTS * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+                ar.ys = (const uint32_t *)ctx->ys.p;
+            }
+            ar.kinds_row0 = r_lo;
+        }
+        if (long_eligible(plan, io)) rc = run_long(ctx, plan, ar);
+        else rc = run_generic(ctx, plan, io, ar);
+        if (rc) return rc;
+        if (io->memory == LWB_MEM_HOST) {
+            if (o_hi > o_lo)
+                CU(ctx, cudaMemcpyAsync((char *)io->pcm + o_lo * esz, ctx->pcm.p, (o_hi - o_lo) * esz,
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    // commit the host-side view of every stream's state
+    for (auto &pc : plan) {
+        lwb_stream *s = pc.c->stream;
+        if (!pc.pk.empty() || pc.clear_after) {
+            s->has = pc.end_has;
+            s->plen = pc.end_plen;
+        }
+    }
+    return LWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one packet
+// ---------------------------------------------------------------------------------------------
+static int one_packet(lwb_stream *s, int entry, uint8_t mode, int prev_flag, int next_flag, const float *coeffs,
+                      const lwb_packet *pkt, int out_format, void *out, size_t cap, size_t *n_samples)
+{
+    if (!s || !coeffs || !out || !n_samples) return LWB_ERR_INVALID;
+    *n_samples = 0;
+    Geom g;
+    int rc = geometry(s->setup, mode, prev_flag, next_flag, &g);
+    if (rc) return rc;
+    const size_t produce = s->has ? g.rs - g.ls : 0;
+    if (produce > cap) return LWB_ERR_BUFFER;          // checked before anything is consumed
+    uint8_t m = mode, pf = (uint8_t)(prev_flag != 0), nf = (uint8_t)(next_flag != 0);
+    lwb_chain c;
+    std::memset(&c, 0, sizeof(c));
+    c.stream = s;
+    c.n_packets = 1;
+    c.mode_numbers = &m;
+    c.prev_window_flags = &pf;
+    c.next_window_flags = &nf;
+    c.out_stride = cap;
+    lwb_batch_io io;
+    std::memset(&io, 0, sizeof(io));
+    io.entry = entry;
+    io.memory = LWB_MEM_HOST;
+    io.coeffs = coeffs;
+    if (pkt) {
+        io.dense_floor = pkt->dense_floor;
+        io.floor_kind = pkt->floor_kind;
+        io.floor1_y = pkt->floor1_y;
+    }
+    io.out_format = out_format;
+    io.pcm = out;
+    rc = lwb_decode_chains(s->ctx, &c, 1, &io);
+    if (rc) return rc;
+    if (c.status) return c.status;
+    *n_samples = c.n_samples;
+    return LWB_OK;
+}
+
+extern "C" int lwb_decode_packet(lwb_stream *s, const lwb_packet *pkt, int out_format, void *out, size_t cap,
+                                 size_t *n_samples)
+{
+    if (!pkt || !pkt->floor_kind || !pkt->residue) return LWB_ERR_INVALID;
+    return one_packet(s, LWB_ENTRY_RESIDUE, pkt->mode_number, pkt->prev_window_flag, pkt->next_window_flag,
+                      pkt->residue, pkt, out_format, out, cap, n_samples);
+}
+
+extern "C" int lwb_decode_spectrum(lwb_stream *s, uint8_t mode, int prev_flag, int next_flag, const float *spectrum,
+                                   int out_format, void *out, size_t cap, size_t *n_samples)
+{
+    return one_packet(s, LWB_ENTRY_SPECTRUM, mode, prev_flag, next_flag, spectrum, nullptr, out_format, out, cap,
+                      n_samples);
+}
+
+// ---------------------------------------------------------------------------------------------
+// debug taps (lib.rs:56-94): intermediates of one packet, state untouched
+// ---------------------------------------------------------------------------------------------
+extern "C" int lwb_debug_packet_taps(lwb_stream *s, const lwb_packet *pkt, float *post_inverse, float *pre_mdct,
+                                     float *post_mdct)
+{
+    if (!s || !pkt || !pkt->floor_kind || !pkt->residue) return LWB_ERR_INVALID;
+    lwb_ctx *ctx = s->ctx;
+    const lwb_setup *su = s->setup;
+    Geom g;
+    int rc = geometry(su, pkt->mode_number, pkt->prev_window_flag, pkt->next_window_flag, &g);
+    if (rc) return rc;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t C = su->channels, n2 = g.n >> 1;
+    bool need_dense = false, need_y = false;
+    for (size_t c = 0; c < C; c++) {
+        if (pkt->floor_kind[c] > LWB_FLOOR_DENSE) return LWB_ERR_INVALID;
+        need_dense |= pkt->floor_kind[c] == LWB_FLOOR_DENSE;
+        need_y |= pkt->floor_kind[c] == LWB_FLOOR_ONE;
+    }
+    if ((need_dense && !pkt->dense_floor) || (need_y && !pkt->floor1_y)) return LWB_ERR_INVALID;
+    if ((rc = ensure(ctx, ctx->coeffs, C * n2 * 4)) || (rc = ensure(ctx, ctx->spec, C * n2 * 4)) ||
+        (rc = ensure(ctx, ctx->x, C * g.n * 4)) || (rc = ensure(ctx, ctx->kinds, C)) ||
+        (rc = ensure(ctx, ctx->ys, C * LWB_MAX_POSTS * 4)) || (rc = ensure(ctx, ctx->dense, C * n2 * 4)) ||
+        (rc = ensure(ctx, ctx->desc, sizeof(DevPacket))) || (rc = ensure_pinned(ctx, sizeof(DevPacket))))
+        return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    DevPacket *d = (DevPacket *)ctx->h_desc;
+    std::memset(d, 0, sizeof(*d));
+    d->setup = su->d_setup;
+    d->state = s->d_state;
+    d->prev_packet = -1;
+    d->state_stride = (uint32_t)state_stride(su);
+    d->n = (uint16_t)g.n;
+    d->ls = (uint16_t)g.ls; d->rs = (uint16_t)g.rs; d->re = (uint16_t)g.re;
+    d->blockflag = g.blockflag; d->mapping = g.mapping; d->slope_sel = g.slope_sel;
+    d->channels = (uint8_t)C;
+    cudaStream_t st = ctx->stream;
+    CU(ctx, cudaMemcpyAsync(ctx->desc.p, d, sizeof(*d), cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->coeffs.p, pkt->residue, C * n2 * 4, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->kinds.p, pkt->floor_kind, C, cudaMemcpyHostToDevice, st));
+    if (need_y) CU(ctx, cudaMemcpyAsync(ctx->ys.p, pkt->floor1_y, C * LWB_MAX_POSTS * 4, cudaMemcpyHostToDevice, st));
+    if (need_dense) CU(ctx, cudaMemcpyAsync(ctx->dense.p, pkt->dense_floor, C * n2 * 4, cudaMemcpyHostToDevice, st));
+    const DevPacket *dp = (const DevPacket *)ctx->desc.p;
+    if (post_inverse) {
+        // audio.rs:1004 tap: coupling only -- run the prologue with every floor "dense = 1.0"?  No:
+        // the tap is taken by running the prologue on a copy with all floors unused replaced by a
+        // unit curve, so that floor x residue leaves the decoupled residue unchanged.
+        std::vector<float> ones(C * n2, 1.0f);
+        std::vector<uint8_t> kd(C, LWB_FLOOR_DENSE);
+        void *tmp_dense = nullptr, *tmp_kinds = nullptr;
+        CU(ctx, cudaMalloc(&tmp_dense, C * n2 * 4));
+        CU(ctx, cudaMalloc(&tmp_kinds, C));
+        CU(ctx, cudaMemcpyAsync(tmp_dense, ones.data(), C * n2 * 4, cudaMemcpyHostToDevice, st));
+        CU(ctx, cudaMemcpyAsync(tmp_kinds, kd.data(), C, cudaMemcpyHostToDevice, st));
+        rc = launch(ctx, k_prologue, dim3(1), dim3(kPrologueThreads), 0, dp, (const float *)ctx->coeffs.p,
+                    (const float *)tmp_dense, (const uint8_t *)tmp_kinds, (const uint32_t *)ctx->ys.p,
+                    (float *)ctx->spec.p);
+        if (!rc) {
+            cudaError_t e = cudaMemcpyAsync(post_inverse, ctx->spec.p, C * n2 * 4, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) rc = fail(ctx, LWB_ERR_CUDA, "tap copy", e);
+        }
+        cudaFree(tmp_dense);
+        cudaFree(tmp_kinds);
+        if (rc) return rc;
+    }
+    if ((rc = launch(ctx, k_prologue, dim3(1), dim3(kPrologueThreads), 0, dp, (const float *)ctx->coeffs.p,
+                     (const float *)ctx->dense.p, (const uint8_t *)ctx->kinds.p, (const uint32_t *)ctx->ys.p,
+                     (float *)ctx->spec.p)))
+        return rc;
+    if (pre_mdct) CU(ctx, cudaMemcpyAsync(pre_mdct, ctx->spec.p, C * n2 * 4, cudaMemcpyDeviceToHost, st));
+    if (post_mdct) {
+        if ((rc = launch(ctx, k_imdct, dim3(1, (unsigned)C), dim3(kImdctThreads), g.n * sizeof(float), dp,
+                         (const float *)ctx->spec.p, (float *)ctx->x.p)))
+            return rc;
+        CU(ctx, cudaMemcpyAsync(post_mdct, ctx->x.p, C * g.n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU(ctx, cudaStreamSynchronize(st));
+    return LWB_OK;
+}

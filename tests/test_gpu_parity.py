@@ -1,0 +1,424 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Bar (north_star): f32 PCM bit-identical (modulo sign of zero / NaN payload), i16 PCM
+bit-identical."""
+import os
+
+import numpy as np
+import pytest
+
+import lewton_b200 as L
+from lewton_b200 import _cabi as cabi
+from helpers import (RefStream, bits_equal, make_setup, mismatch_report, mode_sequence, random_floor1,
+                     random_floor1_y)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = L.Context(0)
+    yield c
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# inverse MDCT alone (imdct.rs:291), through the post-MDCT debug tap
+# ------------------------------------------------------------------------------------------------
+def imdct_via_tap(ctx, bs, spectra):
+    su = make_setup(ctx, 1, bs, bs, modes=((1, 0),))
+    pwr = L.PreviousWindowRight(su)
+    out = []
+    for sp in spectra:
+        pk = L.DecodedPacket(0, sp[None, :], [np.ones(len(sp), np.float32)])
+        _, pre, post = L.debug_taps(su, pk, pwr)
+        assert bits_equal(pre[0], sp)          # 1.0 * x is exact
+        out.append(post[0])
+    return out
+
+
+@pytest.mark.parametrize("bs", range(6, 14))
+def test_imdct_all_blocksizes_bit_exact(ctx, oracle, bs):
+    rng = np.random.default_rng(1000 + bs)
+    n2 = (1 << bs) // 2
+    spectra = [rng.standard_normal(n2).astype(np.float32) * s for s in (1.0, 1e-2, 1e3)]
+    spectra.append(np.zeros(n2, np.float32))
+    e = np.zeros(n2, np.float32)
+    e[n2 // 3] = 1.0
+    spectra.append(e)
+    for sp, got in zip(spectra, imdct_via_tap(ctx, bs, spectra)):
+        want = oracle.inverse_mdct(sp, bs)
+        assert bits_equal(got, want), mismatch_report(got, want)
+
+
+def test_imdct_reference_kat(ctx):
+    """The reference's own KATs (imdct_test.rs) through the GPU path, at the reference's tolerance."""
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "imdct_kat.json")) as f:
+        kat = {k: np.array([np.float32(v) for v in a], np.float32) for k, a in json.load(f)["arrays"].items()}
+    for idx, bs, eps in ((1, 8, 5e-5), (2, 8, 5e-5), (3, 11, 5e-4)):
+        got = imdct_via_tap(ctx, bs, [kat[f"IMDCT_INPUT_TEST_ARR_{idx}"]])[0]
+        want = kat[f"IMDCT_OUTPUT_TEST_ARR_{idx}"]
+        assert int(np.sum(np.abs(got - want) >= np.float32(eps))) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# packet by packet, spectrum entry: window geometry, OLA, state, formats (audio.rs:1041-1157)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("channels,bs0,bs1,seed", [(1, 8, 11, 0), (2, 8, 11, 1), (6, 8, 11, 2), (2, 6, 9, 3),
+                                                   (1, 7, 13, 4), (3, 10, 10, 5)])
+def test_packet_sequence_mixed_blocks(ctx, oracle, channels, bs0, bs1, seed):
+    rng = np.random.default_rng(seed)
+    su = make_setup(ctx, channels, bs0, bs1)
+    pwr = L.PreviousWindowRight(su)
+    ref = RefStream(oracle, channels, bs0, bs1, [(0, 0), (1, 0)])
+    modes, prev, nxt = mode_sequence(rng, 14)
+    assert pwr.is_empty()
+    for i in range(len(modes)):
+        n2 = (1 << (bs1 if modes[i] else bs0)) // 2
+        spec = (rng.standard_normal((channels, n2)) * 0.1).astype(np.float32)
+        rc, want = ref.spectrum(int(modes[i]), int(prev[i]), int(nxt[i]), spec)
+        assert L.get_decoded_sample_count(su, int(modes[i]), prev[i], nxt[i]) == \
+            (want.shape[1] if i else L.get_decoded_sample_count(su, int(modes[i]), prev[i], nxt[i]))
+        if rc:
+            with pytest.raises(L.AudioReadError) as e:
+                L.decode_spectrum(su, int(modes[i]), spec, pwr, prev[i], nxt[i])
+            assert e.value.kind == "AudioBadFormat"
+            assert pwr.is_empty() and ref.pwr.is_empty()
+            continue
+        fmt = i % 4
+        if fmt == 0:
+            got = L.decode_spectrum(su, int(modes[i]), spec, pwr, prev[i], nxt[i])
+            assert bits_equal(got, want), mismatch_report(got, want)
+        elif fmt == 1:
+            got = L.decode_spectrum(su, int(modes[i]), spec, pwr, prev[i], nxt[i], sample="i16")
+            assert np.array_equal(got, oracle.quantise_i16(want))
+        elif fmt == 2:
+            got = L.decode_spectrum(su, int(modes[i]), spec, pwr, prev[i], nxt[i], interleaved=True)
+            assert bits_equal(got, want.T)
+        else:
+            got = L.decode_spectrum(su, int(modes[i]), spec, pwr, prev[i], nxt[i], sample="i16", interleaved=True)
+            assert np.array_equal(got, oracle.quantise_i16(want).T)
+        assert len(pwr) == len(ref.pwr)
+        assert bits_equal(pwr.data(), ref.pwr.data())
+
+
+def test_first_packet_and_reset_semantics(ctx, oracle):
+    """audio.rs:1140-1151: no previous half -> 0 samples; reset/clone behave like the Rust type."""
+    rng = np.random.default_rng(7)
+    su = make_setup(ctx, 2, 8, 11)
+    pwr = L.PreviousWindowRight.new(su)
+    spec = rng.standard_normal((2, 1024)).astype(np.float32)
+    out = L.decode_spectrum(su, 1, spec, pwr)
+    assert out.shape == (2, 0) and not pwr.is_empty() and len(pwr) == 1024
+    x = np.stack([oracle.inverse_mdct(spec[c], 11) for c in range(2)])
+    assert bits_equal(pwr.data(), x[:, 1024:])
+    twin = pwr.clone()
+    a = L.decode_spectrum(su, 1, spec, pwr)
+    b = L.decode_spectrum(su, 1, spec, twin)
+    assert a.shape == (2, 1024) and bits_equal(a, b)
+    pwr.reset()
+    assert pwr.is_empty()
+    assert L.decode_spectrum(su, 1, spec, pwr).shape == (2, 0)
+
+
+def test_ola_guard_is_bad_format_and_empties_state(ctx, oracle):
+    """audio.rs:1107-1111 (fuzzing regression): slope shorter than the previous half."""
+    rng = np.random.default_rng(8)
+    su = make_setup(ctx, 1, 8, 11)
+    pwr = L.PreviousWindowRight(su)
+    L.decode_spectrum(su, 1, rng.standard_normal((1, 1024)).astype(np.float32), pwr)      # long, next=long
+    with pytest.raises(L.AudioReadError) as e:
+        L.decode_spectrum(su, 0, rng.standard_normal((1, 128)).astype(np.float32), pwr)    # short follows
+    assert e.value.kind == "AudioBadFormat" and pwr.is_empty()
+    with pytest.raises(L.AudioReadError) as e:
+        L.decode_spectrum(su, 7, np.zeros((1, 128), np.float32), pwr)                      # audio.rs:926-930
+    assert e.value.kind == "AudioBadFormat"
+
+
+# ------------------------------------------------------------------------------------------------
+# full packets: coupling + floor-1 + multiply (audio.rs:988-1039)
+# ------------------------------------------------------------------------------------------------
+def _random_packet_case(rng, channels, bs0, bs1):
+    n2s = ((1 << bs0) // 2, (1 << bs1) // 2)
+    floors = [random_floor1(rng, n2s[1]) for _ in range(3)]
+    steps = []
+    for _ in range(int(rng.integers(0, 2 * channels))):
+        m, a = rng.choice(channels, 2, replace=False) if channels > 1 else (0, 0)
+        if m != a:
+            steps.append((int(m), int(a)))
+    mappings = [{"coupling": steps, "floor_of_channel": [int(rng.integers(0, 3)) for _ in range(channels)]},
+                {"coupling": [], "floor_of_channel": [0] * channels}]
+    modes = [(0, 0), (1, 0), (1, 1), (0, 1)]
+    return floors, mappings, modes
+
+
+@pytest.mark.parametrize("channels,bs0,bs1,seed", [(2, 8, 11, 10), (6, 8, 11, 11), (1, 6, 8, 12), (12, 7, 10, 13),
+                                                   (3, 9, 13, 14)])
+def test_full_packets_coupling_and_floor1(ctx, oracle, channels, bs0, bs1, seed):
+    rng = np.random.default_rng(seed)
+    floors, mappings, modes = _random_packet_case(rng, channels, bs0, bs1)
+    su = make_setup(ctx, channels, bs0, bs1, modes=modes, mappings=mappings, floors=floors)
+    pwr = L.PreviousWindowRight(su)
+    ref = RefStream(oracle, channels, bs0, bs1, modes, mappings, floors)
+    bf, prev, nxt = mode_sequence(rng, 10)
+    for i in range(len(bf)):
+        mode = int(rng.choice([m for m in range(4) if modes[m][0] == bf[i]]))
+        n2 = (1 << (bs1 if bf[i] else bs0)) // 2
+        # sparse, signed residue with exact zeros (exercises all inverse_couple branches)
+        res = (rng.standard_normal((channels, n2)) * rng.integers(0, 2, (channels, n2))).astype(np.float32)
+        mp = mappings[modes[mode][1]]
+        fl = []
+        for c in range(channels):
+            r = rng.random()
+            if r < 0.2:
+                fl.append(None)
+            elif r < 0.3:
+                fl.append(rng.random(n2).astype(np.float32))
+            else:
+                mult, xs = floors[mp["floor_of_channel"][c]]
+                fl.append(random_floor1_y(rng, mult, len(xs), wild=(seed % 2 == 0)))
+        rc, want = ref.packet(mode, int(prev[i]), int(nxt[i]), res, fl)
+        pk = L.DecodedPacket(mode, res, fl, prev[i], nxt[i])
+        if rc:
+            with pytest.raises(L.AudioReadError):
+                L.read_audio_packet_generic(su, pk, pwr)
+            assert pwr.is_empty() == ref.pwr.is_empty()
+            continue
+        if i % 2:
+            got = L.read_audio_packet(su, pk, pwr)                  # Vec<Vec<i16>>
+            assert np.array_equal(got, oracle.quantise_i16(want))
+        else:
+            got = L.read_audio_packet_generic(su, pk, pwr)
+            assert bits_equal(got, want), mismatch_report(got, want)
+        assert bits_equal(pwr.data(), ref.pwr.data())
+
+
+def test_debug_taps_match_oracle_stages(ctx, oracle):
+    """record_residue_post_inverse / record_pre_mdct / record_post_mdct (audio.rs:1004,1041,1054)."""
+    rng = np.random.default_rng(21)
+    channels, bs0, bs1 = 4, 8, 11
+    floors, mappings, modes = _random_packet_case(rng, channels, bs0, bs1)
+    mappings[0]["coupling"] = [(0, 1), (2, 3), (0, 2)]          # chain through a shared channel
+    su = make_setup(ctx, channels, bs0, bs1, modes=modes, mappings=mappings, floors=floors)
+    pwr = L.PreviousWindowRight(su)
+    res = (rng.standard_normal((channels, 1024)) * rng.integers(0, 2, (channels, 1024))).astype(np.float32)
+    fl = [random_floor1_y(rng, *(lambda f: (f[0], len(f[1])))(floors[mappings[0]["floor_of_channel"][c]]))
+          for c in range(channels)]
+    post_inv, pre, post = L.debug_taps(su, L.DecodedPacket(1, res, fl), pwr)
+    r = res.copy()
+    for m, a in reversed(mappings[0]["coupling"]):
+        r[m], r[a] = oracle.inverse_couple(r[m], r[a])
+    assert bits_equal(post_inv, r)
+    for c in range(channels):
+        mult, xs = floors[mappings[0]["floor_of_channel"][c]]
+        ofl = oracle.make_floor1(mult, xs)
+        fy, s2 = oracle.floor1_amplitude(ofl, fl[c])
+        curve = oracle.floor1_synthesis(ofl, fy, s2, 1024)
+        assert bits_equal(pre[c], curve * r[c]), c
+        assert bits_equal(post[c], oracle.inverse_mdct(pre[c], 11))
+    assert pwr.is_empty()                                         # taps do not touch the state
+
+
+# ------------------------------------------------------------------------------------------------
+# batches (lwb_decode_chains): generic and fused paths, host and device memory
+# ------------------------------------------------------------------------------------------------
+def run_batch(ctx, su, pwrs, spec, n_packets, memory, env=None):
+    """spec [S][P][C][1024] -> pcm [S][C][P*1024] (planar f32), all long/long."""
+    S, P, C, n2 = spec.shape
+    stride = P * n2
+    chains = [L.ChainSpec(pwrs[s], np.ones(P, np.uint8), coeff_offset=s * P * C * n2, out_offset=s * C * stride,
+                          out_stride=stride) for s in range(S)]
+    pcm = np.zeros((S, C, stride), np.float32)
+    old = {}
+    for k, v in (env or {}).items():
+        old[k] = os.environ.get(k)
+        os.environ[k] = v
+    try:
+        if memory == cabi.MEM_HOST:
+            L.decode_chains(ctx, chains, cabi.ENTRY_SPECTRUM, memory, spec, pcm, cabi.OUT_F32_PLANAR)
+        else:
+            d_in = ctx.device_alloc(spec.nbytes)
+            d_out = ctx.device_alloc(pcm.nbytes)
+            ctx.h2d(d_out, pcm)
+            ctx.h2d(d_in, spec)
+            L.decode_chains(ctx, chains, cabi.ENTRY_SPECTRUM, memory, d_in, d_out, cabi.OUT_F32_PLANAR)
+            ctx.synchronize()
+            ctx.d2h(pcm, d_out)
+            ctx.device_free(d_in)
+            ctx.device_free(d_out)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+    return chains, pcm
+
+
+def oracle_batch(oracle, spec, states=None):
+    S, P, C, n2 = spec.shape
+    outs, finals = [], []
+    for s in range(S):
+        pwr = oracle.Pwr(C, 11)
+        if states is not None and states[s] is not None:
+            pwr.set_data(states[s])
+        parts = []
+        for p in range(P):
+            rc, pcm = oracle.synth_spectrum(8, 11, 1, 1, 1, spec[s, p], pwr)
+            assert rc == 0
+            parts.append(pcm)
+        outs.append(np.concatenate(parts, axis=1))
+        finals.append(pwr.data())
+    return outs, finals
+
+
+@pytest.mark.parametrize("memory", [cabi.MEM_HOST, cabi.MEM_DEVICE])
+@pytest.mark.parametrize("env", [None, {"LWB_FORCE_GENERIC": "1"}, {"LWB_LONG_TARGET_RUNS": "100000"}])
+def test_batch_long_blocks_vs_oracle(ctx, oracle, memory, env):
+    """S stereo streams x P long blocks, fresh streams then a second batch that continues them;
+    fused path, fused path with forced run cuts (primer packets), and the generic path."""
+    rng = np.random.default_rng(31)
+    S, P, C = 5, 19, 2
+    su = make_setup(ctx, C, 8, 11)
+    pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+    spec1 = (rng.standard_normal((S, P, C, 1024)) * 0.05).astype(np.float32)
+    spec2 = (rng.standard_normal((S, P, C, 1024)) * 0.05).astype(np.float32)
+    chains, pcm1 = run_batch(ctx, su, pwrs, spec1, P, memory, env)
+    want1, st1 = oracle_batch(oracle, spec1)
+    for s in range(S):
+        assert chains[s].status == 0 and chains[s].packets_done == P and chains[s].n_samples == (P - 1) * 1024
+        assert bits_equal(pcm1[s][:, : (P - 1) * 1024], want1[s]), (s, mismatch_report(pcm1[s][:, : (P - 1) * 1024], want1[s]))
+        assert bits_equal(pwrs[s].data(), st1[s])
+    chains, pcm2 = run_batch(ctx, su, pwrs, spec2, P, memory, env)
+    want2, st2 = oracle_batch(oracle, spec2, st1)
+    for s in range(S):
+        assert chains[s].n_samples == P * 1024
+        assert bits_equal(pcm2[s], want2[s]), (s, mismatch_report(pcm2[s], want2[s]))
+        assert bits_equal(pwrs[s].data(), st2[s])
+
+
+def test_fused_path_with_imported_asymmetric_state(ctx, oracle):
+    """A state that did not come from a long block (not mirror-symmetric) must still be honoured."""
+    rng = np.random.default_rng(33)
+    su = make_setup(ctx, 1, 8, 11)
+    pwr = L.PreviousWindowRight(su)
+    st = rng.standard_normal((1, 1024)).astype(np.float32)
+    pwr.set_data(st)
+    spec = rng.standard_normal((1, 3, 1, 1024)).astype(np.float32)
+    _, pcm = run_batch(ctx, su, [pwr], spec, 3, cabi.MEM_HOST)
+    want, fin = oracle_batch(oracle, spec, [st])
+    assert bits_equal(pcm[0], want[0]) and bits_equal(pwr.data(), fin[0])
+
+
+def test_fused_and_generic_agree_at_scale(ctx, oracle):
+    """Size-independent property at a larger size: the fused kernel and the generic path are
+    two independent schedules of the same arithmetic and must agree bit for bit; a sample of
+    chains is also checked against the oracle."""
+    rng = np.random.default_rng(35)
+    S, P, C = 96, 24, 2
+    su = make_setup(ctx, C, 8, 11)
+    spec = (rng.standard_normal((S, P, C, 1024)) * 0.02).astype(np.float32)
+    pa = [L.PreviousWindowRight(su) for _ in range(S)]
+    pb = [L.PreviousWindowRight(su) for _ in range(S)]
+    _, fused = run_batch(ctx, su, pa, spec, P, cabi.MEM_DEVICE)
+    _, generic = run_batch(ctx, su, pb, spec, P, cabi.MEM_DEVICE, {"LWB_FORCE_GENERIC": "1"})
+    assert np.array_equal(fused.view(np.uint32), generic.view(np.uint32))
+    want, _ = oracle_batch(oracle, spec[:3])
+    for s in range(3):
+        assert bits_equal(fused[s][:, : (P - 1) * 1024], want[s])
+    # linearity of the whole path in exact arithmetic: scaling the input by 2 scales the output by 2
+    pc = [L.PreviousWindowRight(su) for _ in range(S)]
+    _, doubled = run_batch(ctx, su, pc, spec * np.float32(2), P, cabi.MEM_DEVICE)
+    assert np.array_equal(doubled.view(np.uint32), (fused * np.float32(2)).view(np.uint32))
+
+
+def test_batch_mixed_blocks_residue_entry(ctx, oracle):
+    """Chains with mixed short/long packets, coupling and floor-1, i16 interleaved output."""
+    rng = np.random.default_rng(37)
+    channels, bs0, bs1, S, P = 2, 8, 11, 4, 9
+    floors, mappings, modes = _random_packet_case(rng, channels, bs0, bs1)
+    mappings[0]["coupling"] = [(0, 1)]
+    su = make_setup(ctx, channels, bs0, bs1, modes=modes, mappings=mappings, floors=floors)
+    pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+    refs = [RefStream(oracle, channels, bs0, bs1, modes, mappings, floors) for _ in range(S)]
+    coeffs, kinds, ys, specs, want = [], [], [], [], []
+    chains = []
+    coeff_off = pkt_idx = out_off = 0
+    for s in range(S):
+        bf, prev, nxt = mode_sequence(rng, P, p_short=0.4)
+        mode_ids = np.array([0 if not b else 1 for b in bf], np.uint8)
+        total = 0
+        parts = []
+        c_off0, p_idx0 = coeff_off, pkt_idx
+        for i in range(P):
+            n2 = (1 << (bs1 if bf[i] else bs0)) // 2
+            res = (rng.standard_normal((channels, n2)) * rng.integers(0, 2, (channels, n2))).astype(np.float32)
+            fl = []
+            for c in range(channels):
+                mult, xs = floors[mappings[0]["floor_of_channel"][c]]
+                fl.append(None if rng.random() < 0.15 else random_floor1_y(rng, mult, len(xs)))
+            rc, pcm = refs[s].packet(int(mode_ids[i]), int(prev[i]), int(nxt[i]), res, fl)
+            assert rc == 0
+            parts.append(pcm)
+            total += pcm.shape[1]
+            coeffs.append(res.ravel())
+            k, y, _ = L.DecodedPacket(int(mode_ids[i]), res, fl).pack()
+            kinds.append(k)
+            ys.append(y)
+            coeff_off += res.size
+            pkt_idx += 1
+        want.append(np.concatenate(parts, axis=1))
+        chains.append(L.ChainSpec(pwrs[s], mode_ids, prev, nxt, coeff_offset=c_off0, packet_index=p_idx0,
+                                  out_offset=out_off, out_stride=0))
+        out_off += total * channels
+    coeffs = np.concatenate(coeffs)
+    kinds = np.concatenate(kinds)
+    ys = np.concatenate(ys)
+    pcm = np.zeros(out_off, np.int16)
+    L.decode_chains(ctx, chains, cabi.ENTRY_RESIDUE, cabi.MEM_HOST, coeffs, pcm, cabi.OUT_I16_INTERLEAVED,
+                    floor_kind=kinds, floor1_y=ys)
+    pos = 0
+    for s in range(S):
+        n = want[s].shape[1]
+        assert chains[s].status == 0 and chains[s].n_samples == n
+        got = pcm[pos: pos + n * channels].reshape(n, channels)
+        assert np.array_equal(got, oracle.quantise_i16(want[s]).T), s
+        pos += n * channels
+        assert bits_equal(pwrs[s].data(), refs[s].pwr.data())
+
+
+def test_batch_error_mid_chain(ctx, oracle):
+    """A chain whose 3rd packet trips the OLA guard: earlier packets are decoded, the chain
+    reports AudioBadFormat at index 2 and the stream ends up empty (audio.rs:1083,1107-1111)."""
+    rng = np.random.default_rng(39)
+    su = make_setup(ctx, 1, 8, 11)
+    pwr = L.PreviousWindowRight(su)
+    modes = np.array([1, 1, 0, 1], np.uint8)           # long, long(next=long), short -> guard
+    spec = rng.standard_normal(1024 * 2 + 128 + 1024).astype(np.float32)
+    pcm = np.zeros(4096, np.float32)
+    ch = L.ChainSpec(pwr, modes, out_stride=4096)
+    L.decode_chains(ctx, [ch], cabi.ENTRY_SPECTRUM, cabi.MEM_HOST, spec, pcm, cabi.OUT_F32_PLANAR)
+    assert ch.status == cabi.ERR_BAD_FORMAT and ch.packets_done == 2 and ch.n_samples == 1024
+    assert pwr.is_empty()
+    ref = oracle.Pwr(1, 11)
+    oracle.synth_spectrum(8, 11, 1, 1, 1, spec[None, :1024], ref)
+    _, want = oracle.synth_spectrum(8, 11, 1, 1, 1, spec[None, 1024:2048], ref)
+    assert bits_equal(pcm[:1024], want[0])
+
+
+def test_special_values_on_gpu(ctx, oracle):
+    """Denormals are kept (no flush-to-zero), inf/NaN propagate like on the CPU."""
+    rng = np.random.default_rng(41)
+    su = make_setup(ctx, 1, 8, 11)
+    spec = rng.standard_normal((1, 4, 1, 1024)).astype(np.float32)
+    spec[0, 0, 0, :100] = 1e-42
+    spec[0, 1, 0, 3] = np.inf
+    spec[0, 2, 0, 9] = np.nan
+    spec[0, 3, 0] *= 1e-38
+    for env in (None, {"LWB_FORCE_GENERIC": "1"}):
+        pwr = L.PreviousWindowRight(su)
+        _, pcm = run_batch(ctx, su, [pwr], spec, 4, cabi.MEM_HOST, env)
+        want, fin = oracle_batch(oracle, spec)
+        assert bits_equal(pcm[0][:, :3072], want[0])
+        assert bits_equal(pwr.data(), fin[0])
+    assert np.any((np.abs(want[0]) > 0) & (np.abs(want[0]) < 1.2e-38)), "test should exercise denormal outputs"
