@@ -70,16 +70,20 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference(streams, packets, threads, seed=1234):
-    """The oracle port (lewton-equivalent C restatement) on the host cores; returns samples/s."""
+def cpu_reference(streams, packets, threads, target_sec=2.0, seed=1234):
+    """The oracle port (lewton-equivalent C restatement) on the host cores; returns
+    (samples/s, seconds, reps).  The same synthetic input is swept `reps` times so that the timed
+    region lasts about target_sec of wall clock on all `threads` cores."""
     from oracle import oracle
     oracle.build()
     rng = np.random.default_rng(seed)
     chains = streams * 2
     spec = (rng.standard_normal((chains, packets, N2)) * 1e-2).astype(np.float32)
-    sec, _ = oracle.bench_chains(11, spec, threads)
-    samples = chains * (packets - 1) * N2          # the first packet of a fresh chain emits nothing
-    return samples / sec, sec
+    sec1, _ = oracle.bench_chains(11, spec, threads, 1)            # calibration pass (also warms caches)
+    reps = max(1, int(target_sec / max(sec1, 1e-4)))
+    sec, _ = oracle.bench_chains(11, spec, threads, reps)
+    samples = chains * (packets - 1) * N2 * reps     # the first packet of a fresh chain emits nothing
+    return samples / sec, sec, reps
 
 
 def run_reference(args):
@@ -89,10 +93,10 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    streams, packets = 256, 17                    # 8704 blocks ~ 0.1-0.3 s of CPU work per step
+    streams, packets = 8 * threads, 17            # 16 chains per thread, swept ~0.5 s per step
     vals = []
     for i in range(args.warmup + args.steps):
-        v, sec = cpu_reference(streams, packets, threads, seed=1234 + i)
+        v, sec, reps = cpu_reference(streams, packets, threads, target_sec=0.5, seed=1234 + i)
         if i >= args.warmup:
             vals.append((v, sec))
     v = float(np.mean([a for a, _ in vals]))
@@ -104,7 +108,8 @@ def run_reference(args):
             "config": {"workload": "stereo long-block (n=2048) packets, IMDCT+window+OLA, CPU oracle port",
                        "streams": streams, "packets_per_stream": packets, "channels": 2},
             "cpu_baseline": {"value": v / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
-                             "sample": f"{streams} stereo streams x {packets} long packets per step"},
+                             "sample": f"{streams} stereo streams x {packets} long packets swept ~0.5 s per step, "
+                                       "lewton-equivalent C restatement (oracle/), the crate itself is Rust"},
             "e2e": {"value": v / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -119,7 +124,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="stereo streams per GPU per step")
     ap.add_argument("--packets", type=int, default=16, help="consecutive long packets per stream per step")
-    ap.add_argument("--e2e-streams", type=int, default=512)
+    ap.add_argument("--e2e-streams", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -157,9 +162,9 @@ def main():
     chains = [L.ChainSpec(pwrs[s], modes, coeff_offset=s * P * C * N2, out_offset=s * C * stride, out_stride=stride)
               for s in range(S)]
 
-    def step():
-        L.decode_chains(ctx, chains, cabi.ENTRY_SPECTRUM, cabi.MEM_DEVICE, spec.data_ptr(), pcm.data_ptr(),
-                        cabi.OUT_F32_PLANAR)
+    batch = L.Batch(ctx, chains, cabi.ENTRY_SPECTRUM, cabi.MEM_DEVICE, spec.data_ptr(), pcm.data_ptr(),
+                    cabi.OUT_F32_PLANAR)
+    step = batch.run
 
     def barrier():
         ctx.synchronize()
@@ -204,8 +209,8 @@ def main():
     e_chains = [L.ChainSpec(e_pwrs[s], modes, coeff_offset=s * P * C * N2, out_offset=s * C * stride,
                             out_stride=stride) for s in range(Se)]
 
-    def e2e_step():
-        L.decode_chains(ctx, e_chains, cabi.ENTRY_SPECTRUM, cabi.MEM_HOST, h_spec, h_pcm, cabi.OUT_F32_PLANAR)
+    e_batch = L.Batch(ctx, e_chains, cabi.ENTRY_SPECTRUM, cabi.MEM_HOST, h_spec, h_pcm, cabi.OUT_F32_PLANAR)
+    e2e_step = e_batch.run
 
     for _ in range(3):
         e2e_step()
@@ -245,10 +250,11 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, sec = cpu_reference(128 * max(1, threads // 4), 17, threads)
+            v, sec, reps = cpu_reference(8 * threads, 17, threads, target_sec=2.0)
             line["cpu_baseline"] = {"value": v / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
-                                    "sample": f"{128 * max(1, threads // 4)} stereo streams x 17 long packets, "
-                                              f"{sec:.2f} s, lewton-equivalent C restatement (oracle/)"}
+                                    "sample": f"{8 * threads} stereo streams x 17 long packets swept {reps}x = "
+                                              f"{sec:.2f} s wall on {threads} threads ({sec * threads:.0f} core-s); "
+                                              "lewton-equivalent C restatement (oracle/), the crate itself is Rust"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

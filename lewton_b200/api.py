@@ -11,6 +11,7 @@ This module is plumbing for tests, the bench and Python callers; the product is 
 library.  It never computes audio on the CPU: without the library / a B200 it raises.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -46,6 +47,7 @@ class Context:
             self._h = None
             raise AudioReadError(rc, "lwb_ctx_create failed (no sm_100 device? there is no CPU fallback)")
         self.device = device
+        self._children = weakref.WeakSet()      # setups / streams: destroyed before the ctx
 
     def check(self, rc):
         if rc:
@@ -79,6 +81,9 @@ class Context:
 
     def close(self):
         if self._h:
+            for kind in (PreviousWindowRight, Setup):          # streams first, then setups
+                for ch in [c for c in list(self._children) if isinstance(c, kind)]:
+                    ch.close()
             cabi.lib().lwb_ctx_destroy(self._h)
             self._h = None
 
@@ -183,13 +188,17 @@ class Setup:
         if rc:
             self._h = None
             raise AudioReadError(rc, cabi.lib().lwb_last_error(ctx._h).decode())
+        ctx._children.add(self)
 
     def blocksize(self, mode_number):
+        if not 0 <= mode_number < len(self.modes):
+            raise AudioReadError(cabi.ERR_BAD_FORMAT, "mode number out of range (audio.rs:926-930)")
         return 1 << (self.blocksize_1 if self.modes[mode_number].mode_blockflag else self.blocksize_0)
 
     def close(self):
         if self._h:
-            cabi.lib().lwb_setup_destroy(self._h)
+            if self.ctx._h:
+                cabi.lib().lwb_setup_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -207,6 +216,7 @@ class PreviousWindowRight:
         self._h = _handle or C.c_void_p()
         if _handle is None:
             setup.ctx.check(cabi.lib().lwb_stream_open(setup.ctx._h, setup._h, C.byref(self._h)))
+        setup.ctx._children.add(self)
 
     @classmethod
     def new(cls, setup):
@@ -240,7 +250,8 @@ class PreviousWindowRight:
 
     def close(self):
         if self._h:
-            cabi.lib().lwb_stream_destroy(self._h)
+            if self.setup.ctx._h:
+                cabi.lib().lwb_stream_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -303,7 +314,7 @@ def read_audio_packet_generic(setup, packet, pwr, sample="f32", interleaved=Fals
     Raises AudioReadError (kind 'AudioBadFormat' for the guard at audio.rs:1107-1111)."""
     fmt, dt = _FORMATS[(sample, interleaved)]
     ch = setup.audio_channels
-    cap = setup.blocksize(packet.mode_number) if packet.mode_number < len(setup.modes) else 1
+    cap = setup.blocksize(packet.mode_number)
     kinds, ys, dense = packet.pack()
     p = cabi.Packet()
     p.mode_number = packet.mode_number
@@ -374,34 +385,57 @@ class ChainSpec:
         self.n_samples = self.packets_done = self.status = 0
 
 
+class Batch:
+    """A prepared lwb_decode_chains call: the lwb_chain array and lwb_batch_io are built once, so a
+    hot loop pays only the C call (the per-step Python cost of marshalling thousands of chains
+    would otherwise exceed the kernel time)."""
+
+    def __init__(self, ctx, chains, entry, memory, coeffs, pcm, out_format, floor_kind=None, floor1_y=None,
+                 dense_floor=None):
+        self.ctx, self.chains = ctx, list(chains)
+        self._keep = (coeffs, pcm, floor_kind, floor1_y, dense_floor)
+        self._arr = arr = (cabi.Chain * len(self.chains))()
+        for i, c in enumerate(self.chains):
+            arr[i].stream = c.pwr._h
+            arr[i].n_packets = len(c.modes)
+            arr[i].mode_numbers = _ptr(c.modes, cabi.u8p)
+            if c.prev is not None:
+                arr[i].prev_window_flags = _ptr(c.prev, cabi.u8p)
+            if c.next is not None:
+                arr[i].next_window_flags = _ptr(c.next, cabi.u8p)
+            arr[i].coeff_offset, arr[i].packet_index = c.coeff_offset, c.packet_index
+            arr[i].out_offset, arr[i].out_stride = c.out_offset, c.out_stride
+
+        def addr(x):
+            if x is None:
+                return None
+            if isinstance(x, np.ndarray):
+                return x.ctypes.data
+            return int(x)
+
+        self._io = io = cabi.BatchIo()
+        io.entry, io.memory, io.out_format = entry, memory, out_format
+        io.coeffs, io.pcm, io.dense_floor = addr(coeffs), addr(pcm), addr(dense_floor)
+        io.floor_kind, io.floor1_y = addr(floor_kind), addr(floor1_y)
+        self._fn = cabi.lib().lwb_decode_chains
+        self._n = len(self.chains)
+
+    def run(self):
+        """One submission.  Results land in the chain array; call collect() to copy them back."""
+        rc = self._fn(self.ctx._h, self._arr, self._n, C.byref(self._io))
+        if rc:
+            self.ctx.check(rc)
+
+    def collect(self):
+        for i, c in enumerate(self.chains):
+            c.n_samples, c.packets_done, c.status = self._arr[i].n_samples, self._arr[i].packets_done, self._arr[i].status
+        return self.chains
+
+
 def decode_chains(ctx, chains, entry, memory, coeffs, pcm, out_format, floor_kind=None, floor1_y=None,
                   dense_floor=None):
     """lwb_decode_chains.  coeffs/pcm/dense_floor: numpy arrays (MEM_HOST) or integer device
     pointers (MEM_DEVICE); floor_kind/floor1_y: numpy arrays (always host)."""
-    arr = (cabi.Chain * len(chains))()
-    for i, c in enumerate(chains):
-        arr[i].stream = c.pwr._h
-        arr[i].n_packets = len(c.modes)
-        arr[i].mode_numbers = _ptr(c.modes, cabi.u8p)
-        if c.prev is not None:
-            arr[i].prev_window_flags = _ptr(c.prev, cabi.u8p)
-        if c.next is not None:
-            arr[i].next_window_flags = _ptr(c.next, cabi.u8p)
-        arr[i].coeff_offset, arr[i].packet_index = c.coeff_offset, c.packet_index
-        arr[i].out_offset, arr[i].out_stride = c.out_offset, c.out_stride
-
-    def addr(x):
-        if x is None:
-            return None
-        if isinstance(x, np.ndarray):
-            return x.ctypes.data
-        return int(x)
-
-    io = cabi.BatchIo()
-    io.entry, io.memory, io.out_format = entry, memory, out_format
-    io.coeffs, io.pcm, io.dense_floor = addr(coeffs), addr(pcm), addr(dense_floor)
-    io.floor_kind, io.floor1_y = addr(floor_kind), addr(floor1_y)
-    ctx.check(cabi.lib().lwb_decode_chains(ctx._h, arr, len(chains), C.byref(io)))
-    for i, c in enumerate(chains):
-        c.n_samples, c.packets_done, c.status = arr[i].n_samples, arr[i].packets_done, arr[i].status
-    return chains
+    b = Batch(ctx, chains, entry, memory, coeffs, pcm, out_format, floor_kind, floor1_y, dense_floor)
+    b.run()
+    return b.collect()

@@ -106,6 +106,8 @@ __device__ __forceinline__ V vmul(V a, V b) { return V{__fmul_rn(a.x, b.x), __fm
 // other adds and all multiplies are packed (FADD2 / FMUL2).
 __device__ __forceinline__ V vadd_p(V a, V b) { return V{__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)}; }
 __device__ __forceinline__ V vsub_p(V a, V b) { return V{__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)}; }
+// -(a) - b for products: the scalar FADD takes both negations as free operand modifiers
+__device__ __forceinline__ V vnsub_p(V a, V b) { return V{__fsub_rn(-a.x, b.x), __fsub_rn(-a.y, b.y)}; }
 #else
 // host (pack builder is host code; the phase functions run here only inside tests/emu).
 // Compiled with -ffp-contract=off: one rounding per operation, like the device path.
@@ -114,6 +116,7 @@ inline V vsub(V a, V b) { return V{a.x - b.x, a.y - b.y}; }
 inline V vmul(V a, V b) { return V{a.x * b.x, a.y * b.y}; }
 inline V vadd_p(V a, V b) { return vadd(a, b); }
 inline V vsub_p(V a, V b) { return vsub(a, b); }
+inline V vnsub_p(V a, V b) { return V{-a.x - b.x, -a.y - b.y}; }
 #endif
 
 // ---- pack layout: V slots per lane, stored slot-major [slot][lane] --------------------------
@@ -129,9 +132,9 @@ enum {
     P_B_END = 44,
     P_A2 = 44,                         // A[n/8] (ld654)
     P_S7C0 = 45, P_S7C1 = 49,          // step 7, odd slots 1,3,5,7 -> index slot >> 1
-    P_B0 = 53, P_B1 = 61, P_NB0 = 69,  // step 8 per slot (NB0 = -B0)
-    P_WLO = 77, P_WHI = 85,            // window w[m], w[1023-m] per slot
-    P_END = 93
+    P_B0 = 53, P_B1 = 61,              // step 8 per slot
+    P_WLO = 69, P_WHI = 77,            // window w[m], w[1023-m] per slot
+    P_END = 85
 };
 constexpr int kLongPackFloats = P_END * 32 * 2;
 
@@ -247,7 +250,6 @@ inline void long_build_pack(const float *a, const float *b, const float *c, cons
             }
             put(P_B0 + j, b0[0], b0[1]);
             put(P_B1 + j, b1[0], b1[1]);
-            put(P_NB0 + j, -b0[0], -b0[1]);
             put(P_WLO + j, wl[0], wl[1]);
             put(P_WHI + j, wh[0], wh[1]);
         }
@@ -390,10 +392,10 @@ LWB_HD void phase_c_fft(TW tw, V O[8], V E[8])
 template <class TW>
 LWB_HD void phase_c_out(TW tw, int j, V Oj, V Ej, V prev_lo, V prev_hi, V &pcm_lo, V &pcm_hi, V &p_even)
 {
-    const V b0 = tw(P_B0 + j), b1 = tw(P_B1 + j), nb0 = tw(P_NB0 + j);
+    const V b0 = tw(P_B0 + j), b1 = tw(P_B1 + j);
     const V wlo = tw(P_WLO + j), whi = tw(P_WHI + j);
     const V p_odd = vsub_p(vmul(Oj, b1), vmul(Ej, b0));
-    p_even = vsub_p(vmul(Oj, nb0), vmul(Ej, b1));
+    p_even = vnsub_p(vmul(Oj, b0), vmul(Ej, b1));       // (-V.e)*B0 - V.o*B1, imdct.rs:620
     pcm_lo = vadd_p(vmul(p_odd, wlo), vmul(prev_lo, whi));
     pcm_hi = vsub_p(vmul(prev_hi, wlo), vmul(p_odd, whi));
 }
@@ -408,9 +410,10 @@ LWB_HD void phase_c_out(TW tw, int j, V Oj, V Ej, V prev_lo, V prev_hi, V &pcm_l
 constexpr int kLongWarps = LWB_LONG_WARPS;     // warps per CTA, one CTA per SM
 constexpr int kLongRing = 3;                   // spectrum tiles in flight per warp
 constexpr int kLongTileBytes = kLongN2 * 4;
-// [tiles: warps x ring x 4 KB, 2 KB-aligned at run time][pack][mbarriers]
+// [tiles: warps x ring x 4 KB, 2 KB-aligned at run time][pack][mbarriers][next-run descriptors]
 constexpr size_t kLongSmemBytes = 2048 + (size_t)kLongWarps * kLongRing * kLongTileBytes +
-                                  (size_t)kLongPackFloats * 4 + kLongWarps * kLongRing * 8 + 64;
+                                  (size_t)kLongPackFloats * 4 + kLongWarps * kLongRing * 8 +
+                                  kLongWarps * sizeof(LongRun) + 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -452,13 +455,23 @@ __device__ __forceinline__ void lds_eo(uint32_t addr, float &e, float &o)
     asm volatile("ld.shared.f32 %0, [%2];\n\tld.shared.f32 %1, [%2+2048];" : "=f"(e), "=f"(o) : "r"(addr) : "memory");
 }
 
-struct TwRegs {
-    const V *r;
-    __device__ __forceinline__ V operator()(int slot) const { return r[slot]; }
-};
-struct TwSmem {
-    const V *lane_base;           // &pack[lane]
-    __device__ __forceinline__ V operator()(int slot) const { return lane_base[slot * 32]; }
+// Twiddle residency: pack slots [kTwReg0, kTwReg1) live in registers for the whole kernel, the
+// rest is read from the CTA's shared copy of the pack when used (compile-time choice per slot).
+#ifndef LWB_TW_S0_SMEM
+#define LWB_TW_S0_SMEM 0
+#endif
+#ifndef LWB_TW_B_SMEM
+#define LWB_TW_B_SMEM 0
+#endif
+constexpr int kTwReg0 = LWB_TW_S0_SMEM ? P_S2W0 : 0;
+constexpr int kTwReg1 = LWB_TW_B_SMEM ? P_A_END : P_B_END;
+struct TwMix {
+    const V *r;                   // registers: slots [kTwReg0, kTwReg1)
+    const V *lane_base;           // &pack[lane] in shared memory
+    __device__ __forceinline__ V operator()(int slot) const
+    {
+        return (slot >= kTwReg0 && slot < kTwReg1) ? r[slot - kTwReg0] : lane_base[slot * 32];
+    }
 };
 
 // Shared-memory byte offsets of the transposes: swz(elem(lane, slot, half)) * 4 splits into a
@@ -474,9 +487,10 @@ __device__ __forceinline__ uint32_t laneC(int lane, int half) { return 4u * (uin
 #define LWB_KC(j) (4u * (uint32_t)swz(j))
 
 // Step 8 + window + overlap-add + stores for all 8 slots.  FROM_STATE: the previous right half
-// comes from the stream state in HBM (first packet of a run with history); EMIT: store PCM.
+// comes from the stream state in HBM (first packet of a run with history); EMIT: store PCM
+// (streaming stores: written once, never read back by this kernel).
 template <bool FROM_STATE, bool EMIT>
-__device__ __forceinline__ void out_stage(const TwSmem &twc, int lane, const V O[8], const V E[8], V pe[8],
+__device__ __forceinline__ void out_stage(const TwMix &tw, int lane, const V O[8], const V E[8], V pe[8],
                                           const float *__restrict__ state, float *__restrict__ out)
 {
     float *o_lo = out + lane, *o_hi = out + 63 - lane;       // out[mx], out[my] bases
@@ -494,20 +508,29 @@ __device__ __forceinline__ void out_stage(const TwSmem &twc, int lane, const V O
             phi = V{bx, by};
         }
         V lo, hi, pev;
-        phase_c_out(twc, j, O[j], E[j], plo, phi, lo, hi, pev);
+        phase_c_out(tw, j, O[j], E[j], plo, phi, lo, hi, pev);
         pe[j] = pev;
         if (EMIT) {
             // m = r64 + lane (or + 63 - lane); 1023 - m = 960 - r64 + 63 - lane (or + lane)
             if (nat) {
-                o_lo[r64] = lo.x; o_hi[r64] = lo.y;
-                o_hi[960 - r64] = hi.x; o_lo[960 - r64] = hi.y;
+                __stcs(o_lo + r64, lo.x); __stcs(o_hi + r64, lo.y);
+                __stcs(o_hi + 960 - r64, hi.x); __stcs(o_lo + 960 - r64, hi.y);
             } else {
-                o_hi[r64] = lo.x; o_lo[r64] = lo.y;
-                o_lo[960 - r64] = hi.x; o_hi[960 - r64] = hi.y;
+                __stcs(o_hi + r64, lo.x); __stcs(o_lo + r64, lo.y);
+                __stcs(o_lo + 960 - r64, hi.x); __stcs(o_hi + 960 - r64, hi.y);
             }
         }
     }
 }
+
+// Uniform (per-warp) view of a run while it is being processed
+struct RunCur {
+    const float *in;
+    float *out;
+    float *state;
+    uint32_t in_stride, npk;
+    uint32_t has_prev, write_state;
+};
 
 // pack: the twiddle pack of the setup's blocksize-11 tables (long_build_pack); ticket: a zeroed
 // counter from which warps draw run indices.
@@ -525,6 +548,8 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restric
     V *s_pack = reinterpret_cast<V *>(base + (size_t)kLongWarps * kLongRing * kLongTileBytes);
     uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)kLongWarps * kLongRing * kLongTileBytes +
                                                   (size_t)kLongPackFloats * 4) + warp * kLongRing;
+    LongRun *s_next = reinterpret_cast<LongRun *>(base + (size_t)kLongWarps * kLongRing * kLongTileBytes +
+                                                  (size_t)kLongPackFloats * 4 + (size_t)kLongWarps * kLongRing * 8) + warp;
     if (n_runs == 0) return;
 
     // stage the pack once per CTA
@@ -539,12 +564,10 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restric
     }
     __syncthreads();
 
-    // phase A/B twiddles stay in registers for the whole kernel
-    V twAB[P_B_END];
+    V twR[kTwReg1 - kTwReg0];
 #pragma unroll
-    for (int s = 0; s < P_B_END; s++) twAB[s] = s_pack[s * 32 + lane];
-    const TwRegs twab{twAB};
-    const TwSmem twc{s_pack + lane};
+    for (int s = kTwReg0; s < kTwReg1; s++) twR[s - kTwReg0] = s_pack[s * 32 + lane];
+    const TwMix tw{twR, s_pack + lane};
 
     const uint32_t tiles_s = smem_u32(tiles);
     const uint32_t bars_s = smem_u32(bars);
@@ -552,29 +575,40 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restric
     const uint32_t lB = laneB(lane);
     const uint32_t lC0 = laneC(lane, 0), lC1 = laneC(lane, 1);
     uint32_t phase_bits = 0;                  // parity of each ring slot's mbarrier
+    uint32_t slot_i = 0;                      // ring slot of the packet being processed
 
-    for (;;) {
-        uint32_t run_idx = 0;
-        if (lane == 0) run_idx = atomicAdd(ticket, 1u);
-        run_idx = __shfl_sync(0xffffffffu, run_idx, 0);
-        if (run_idx >= n_runs) break;
-        const LongRun run = runs[run_idx];
-        const uint32_t npk = run.n_packets;
-        // prime the ring
+    // ---- run hand-over state (only lane 0's copy of the load cursor matters) --------------------
+    // Loads are issued in processing order across run boundaries: once all tiles of the current
+    // run are in flight, lane 0 draws the next ticket, stages that run's descriptor in shared
+    // memory and starts loading ITS first tiles into the ring slots as they free up, so a warp
+    // never idles through ticket + descriptor + first-tile latency between runs.
+    uint32_t lc = 0;                          // tiles of the current run issued so far
+    uint32_t nx_state = 0;                    // 0 unknown, 1 valid (descriptor in s_next), 2 none
+    uint32_t nx_lc = 0, nx_npk = 0;
+    RunCur cur;
+    {
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(ticket, 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= n_runs) return;
+        const LongRun r = runs[idx];
+        cur = RunCur{r.in, r.out, r.state, r.in_stride, r.n_packets, r.has_prev, r.write_state};
         if (lane == 0) {
             fence_proxy_async();
-            for (uint32_t i = 0; i < (uint32_t)kLongRing && i < npk; i++) {
-                const uint32_t bar = bars_s + 8 * i;
+            for (; lc < (uint32_t)kLongRing && lc < cur.npk; lc++) {
+                const uint32_t bar = bars_s + 8 * lc;
                 mbar_expect_tx(bar, kLongTileBytes);
-                tma_load_1d(tiles_s + i * kLongTileBytes, run.in + (size_t)i * run.in_stride, kLongTileBytes, bar);
+                tma_load_1d(tiles_s + lc * kLongTileBytes, cur.in + (size_t)lc * cur.in_stride, kLongTileBytes, bar);
             }
         }
+    }
+
+    for (;;) {
         V pe[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) pe[j] = V{0.f, 0.f};
-        float *out = run.out;
-        uint32_t slot_i = 0;
-        for (uint32_t p = 0; p < npk; p++) {
+        float *out = cur.out;
+        for (uint32_t p = 0; p < cur.npk; p++) {
             const uint32_t tile_s = tiles_s + slot_i * kLongTileBytes;
             mbar_wait(bars_s + 8 * slot_i, (phase_bits >> slot_i) & 1u);
             phase_bits ^= 1u << slot_i;
@@ -589,10 +623,10 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restric
                     F1[m] = Q4{u.x, u.y, u.z, u.w};
                     F2[m] = Q4{v.x, v.y, v.z, v.w};
                 }
-                __syncwarp();       // every lane has its quads: the tile may now be overwritten
-                phase_a(F1, F2, twab, O, E);
+                phase_a(F1, F2, tw, O, E);
             }
-            // transpose 1: the consumed tile is the scratch (E plane | O plane)
+            __syncwarp();           // every lane has consumed its quads: the tile becomes the scratch
+            // transpose 1 (E plane | O plane)
             {
                 const uint32_t a0 = tile_s + lA0, a1 = tile_s + lA1, b0 = tile_s + lB;
 #pragma unroll
@@ -607,7 +641,7 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restric
                     lds_eo(b0 ^ LWB_KB(j, 1), E[j].y, O[j].y);
                 }
                 __syncwarp();
-                phase_b(twab, O, E);
+                phase_b(tw, O, E);
                 // transpose 2
                 const uint32_t c0 = tile_s + lC0, c1 = tile_s + lC1;
 #pragma unroll
@@ -623,27 +657,51 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restric
                 }
                 __syncwarp();
             }
-            // the tile is free again: refill it with packet p + ring
-            if (lane == 0 && p + kLongRing < npk) {
-                fence_proxy_async();
-                const uint32_t bar = bars_s + 8 * slot_i;
-                mbar_expect_tx(bar, kLongTileBytes);
-                tma_load_1d(tile_s, run.in + (size_t)(p + kLongRing) * run.in_stride, kLongTileBytes, bar);
+            // the tile is free again: refill it with the next tile in processing order
+            if (lane == 0) {
+                const float *src = nullptr;
+                if (lc < cur.npk) {
+                    src = cur.in + (size_t)lc * cur.in_stride;
+                    lc++;
+                } else {
+                    if (nx_state == 0) {
+                        const uint32_t idx = atomicAdd(ticket, 1u);
+                        if (idx < n_runs) {
+                            const LongRun r = runs[idx];
+                            *s_next = r;
+                            nx_state = 1;
+                            nx_npk = r.n_packets;
+                            nx_lc = 0;
+                        } else {
+                            nx_state = 2;
+                        }
+                    }
+                    if (nx_state == 1 && nx_lc < nx_npk) {
+                        src = s_next->in + (size_t)nx_lc * s_next->in_stride;
+                        nx_lc++;
+                    }
+                }
+                if (src) {
+                    fence_proxy_async();
+                    const uint32_t bar = bars_s + 8 * slot_i;
+                    mbar_expect_tx(bar, kLongTileBytes);
+                    tma_load_1d(tile_s, src, kLongTileBytes, bar);
+                }
             }
-            phase_c_fft(twc, O, E);
+            phase_c_fft(tw, O, E);
             if (p > 0) {
-                out_stage<false, true>(twc, lane, O, E, pe, run.state, out);
+                out_stage<false, true>(tw, lane, O, E, pe, cur.state, out);
                 out += kLongN2;
-            } else if (run.has_prev) {
-                out_stage<true, true>(twc, lane, O, E, pe, run.state, out);
+            } else if (cur.has_prev) {
+                out_stage<true, true>(tw, lane, O, E, pe, cur.state, out);
                 out += kLongN2;
             } else {
-                out_stage<false, false>(twc, lane, O, E, pe, run.state, out);
+                out_stage<false, false>(tw, lane, O, E, pe, cur.state, out);
             }
             slot_i = (slot_i + 1 == (uint32_t)kLongRing) ? 0 : slot_i + 1;
         }
-        if (run.write_state) {
-            float *s_lo = run.state + lane, *s_hi = run.state + 63 - lane;
+        if (cur.write_state) {
+            float *s_lo = cur.state + lane, *s_hi = cur.state + 63 - lane;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int r64 = 64 * rev3(j);
@@ -652,9 +710,37 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restric
                 s_hi[960 - r64] = vx; s_lo[960 - r64] = vy;     // state[1023 - m]: same value (imdct.rs:622-649)
             }
         }
-        // every load issued for this run was waited on, so the ring is idle here; the next run
-        // starts again at slot 0 and the per-slot parity bits carry over.
+        // hand over to the run lane 0 has (maybe) already started loading
+        uint32_t st = nx_state, nlc = nx_lc;
+        if (lane == 0 && st == 0) {                // the current run was shorter than the ring: draw now
+            const uint32_t idx = atomicAdd(ticket, 1u);
+            if (idx < n_runs) { *s_next = runs[idx]; st = 1; nlc = 0; }
+            else st = 2;
+        }
+        st = __shfl_sync(0xffffffffu, st, 0);
+        nlc = __shfl_sync(0xffffffffu, nlc, 0);
+        if (st != 1) break;
         __syncwarp();
+        {
+            const LongRun r = *s_next;
+            cur = RunCur{r.in, r.out, r.state, r.in_stride, r.n_packets, r.has_prev, r.write_state};
+        }
+        __syncwarp();                              // s_next may be overwritten from here on
+        lc = nlc;
+        nx_state = 0; nx_lc = 0; nx_npk = 0;
+        // ring slots ahead of slot_i that hold nothing yet (new run longer than what was prefetched,
+        // previous run shorter than the ring): top the ring up
+        if (lane == 0) {
+            // slots in flight for the new run: lc tiles starting at slot_i; fill up to the ring depth
+            fence_proxy_async();
+            for (uint32_t k = lc; k < (uint32_t)kLongRing && k < cur.npk; k++) {
+                const uint32_t s = (slot_i + k) % kLongRing;
+                const uint32_t bar = bars_s + 8 * s;
+                mbar_expect_tx(bar, kLongTileBytes);
+                tma_load_1d(tiles_s + s * kLongTileBytes, cur.in + (size_t)k * cur.in_stride, kLongTileBytes, bar);
+                lc = k + 1;
+            }
+        }
     }
 }
 

@@ -38,6 +38,7 @@ struct lwb_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[16] = {}, ev_done[16] = {};
     std::string err;
     uint64_t launches = 0;
     // grow-only device arenas
@@ -681,101 +682,230 @@ static int run_generic(lwb_ctx *ctx, std::vector<PlanChain> &plan, const lwb_bat
     return LWB_OK;
 }
 
-// Fused path (kernel_long.cuh): every packet of the batch is a long block with long neighbours
-// of the fast blocksize, spectrum entry, planar f32 out.
-static bool long_eligible(const std::vector<PlanChain> &plan, const lwb_batch_io *io)
+// ---------------------------------------------------------------------------------------------
+// Fused path (kernel_long.cuh).  Eligible batches: spectrum entry, planar f32 out, every packet a
+// long block of blocksize 2^11 with long neighbours, every stream either empty or holding a
+// 1024-sample right half.  Planned directly from the chain list in O(chains + mode bytes) -- at
+// 0.8 G blocks/s per GPU a per-packet host plan would be the bottleneck.
+// ---------------------------------------------------------------------------------------------
+struct LongItem {
+    lwb_chain *c;
+    uint32_t P;
+    bool has_prev;
+};
+
+struct Staging {
+    void *h = nullptr;
+    size_t cap = 0;
+    cudaEvent_t ev = nullptr;
+    bool pending = false;
+};
+static Staging g_stage[4][3];          // per device ordinal (ctx is per device), ring of 3
+static int g_stage_next[4];
+
+static int acquire_staging(lwb_ctx *ctx, size_t bytes, Staging **out)
 {
-    if (io->entry != LWB_ENTRY_SPECTRUM || io->out_format != LWB_OUT_F32_PLANAR) return false;
-    if (getenv("LWB_FORCE_GENERIC")) return false;
-    for (auto &pc : plan) {
-        const lwb_setup *su = pc.c->stream->setup;
-        if (su->bs1 != kLongBs) return false;
-        if ((pc.c->out_offset & 3) || (pc.c->out_stride & 3) || (pc.c->coeff_offset & 3)) return false;
-        for (auto &pp : pc.pk) {
-            if (!pp.g.blockflag || pp.g.ls != 0 || pp.g.rs != (pp.g.n >> 1) || pp.g.re != pp.g.n) return false;
-            if (pp.plen != 0 && pp.plen != (pp.g.n >> 1)) return false;
-        }
+    const int d = ctx->device & 3;
+    Staging &st = g_stage[d][g_stage_next[d]];
+    g_stage_next[d] = (g_stage_next[d] + 1) % 3;
+    if (!st.ev) CU(ctx, cudaEventCreateWithFlags(&st.ev, cudaEventDisableTiming));
+    if (st.pending) {
+        CU(ctx, cudaEventSynchronize(st.ev));      // waits for the descriptor copy only, not for kernels
+        st.pending = false;
     }
-    return true;
+    if (st.cap < bytes) {
+        if (st.h) cudaFreeHost(st.h);
+        st.h = nullptr;
+        st.cap = 0;
+        CU(ctx, cudaHostAlloc(&st.h, bytes * 2 + 4096, cudaHostAllocDefault));
+        st.cap = bytes * 2 + 4096;
+    }
+    *out = &st;
+    return LWB_OK;
 }
 
-// Runs for the fused kernel.  A chain (one channel of one stream) is cut into several runs when
-// there are too few chains to fill the machine; every run after the first re-transforms the
+// Appends the runs of one chain.  A chain (one channel of one stream) is cut into several runs
+// when there are too few chains to fill the machine; every run after the first re-transforms the
 // packet before its first one as a primer (its right half is all the run needs), which keeps
 // runs independent at the cost of one extra IMDCT per cut.
-static int run_long(lwb_ctx *ctx, std::vector<PlanChain> &plan, const DevArenas &ar)
+static void long_runs_of(const LongItem &it, size_t cuts, const float *coeffs, uint64_t coeff_base, float *pcm,
+                         uint64_t pcm_base, LongRun *&w)
 {
-    size_t n_chan_chains = 0, total_blocks = 0;
-    for (auto &pc : plan)
-        if (!pc.pk.empty()) {
-            n_chan_chains += pc.c->stream->setup->channels;
-            total_blocks += pc.pk.size() * pc.c->stream->setup->channels;
+    const lwb_stream *s = it.c->stream;
+    const lwb_setup *su = s->setup;
+    const unsigned C = su->channels;
+    const size_t P = it.P;
+    for (unsigned ch = 0; ch < C; ch++) {
+        const float *in0 = coeffs + (it.c->coeff_offset - coeff_base) + (size_t)ch * kLongN2;
+        float *out0 = pcm + (it.c->out_offset - pcm_base) + (size_t)ch * it.c->out_stride;
+        for (size_t k = 0; k < cuts; k++) {
+            const size_t p0 = P * k / cuts, p1 = P * (k + 1) / cuts;   // this run emits packets [p0, p1)
+            LongRun &r = *w++;
+            std::memset(&r, 0, sizeof(r));
+            r.in_stride = (uint32_t)(C * kLongN2);
+            r.state = s->d_state + (size_t)ch * state_stride(su);
+            r.write_state = (k + 1 == cuts);
+            if (k == 0) {
+                r.in = in0;
+                r.n_packets = (uint32_t)(p1 - p0);
+                r.has_prev = it.has_prev;
+                r.out = out0;
+            } else {
+                r.in = in0 + (p0 - 1) * (size_t)r.in_stride;           // primer = packet p0 - 1
+                r.n_packets = (uint32_t)(p1 - p0 + 1);
+                r.has_prev = 0;
+                // samples emitted before packet p0: packets 0..p0-1, minus the first if no state
+                r.out = out0 + (size_t)(p0 - (it.has_prev ? 0 : 1)) * kLongN2;
+            }
         }
-    if (!n_chan_chains) return LWB_OK;
+    }
+}
+
+static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch,
+                    bool *handled)
+{
+    *handled = false;
+    if (io->entry != LWB_ENTRY_SPECTRUM || io->out_format != LWB_OUT_F32_PLANAR) return LWB_OK;
+    if (getenv("LWB_FORCE_GENERIC")) return LWB_OK;
+    std::vector<LongItem> items;
+    items.reserve(n_chains);
+    const float *pack = nullptr;
+    size_t chan_chains = 0;
+    for (size_t i = 0; i < n_chains; i++) {
+        lwb_chain *c = &chains[i];
+        if (!c->stream || c->stream->ctx != ctx || (c->n_packets && !c->mode_numbers)) return LWB_OK;   // generic path reports it
+        const lwb_stream *s = c->stream;
+        const lwb_setup *su = s->setup;
+        if (su->bs1 != kLongBs || !su->host.tab[1].pack) return LWB_OK;
+        if (pack && pack != su->host.tab[1].pack) return LWB_OK;          // one twiddle pack per launch
+        pack = su->host.tab[1].pack;
+        if ((c->out_offset & 3) || (c->out_stride & 3) || (c->coeff_offset & 3)) return LWB_OK;
+        if (s->has && s->plen != (uint32_t)kLongN2) return LWB_OK;
+        const uint32_t P = c->n_packets;
+        for (uint32_t k = 0; k < P; k++) {
+            const uint8_t m = c->mode_numbers[k];
+            if (m >= su->n_modes || !su->host.mode_blockflag[m]) return LWB_OK;
+            if (c->prev_window_flags && !c->prev_window_flags[k]) return LWB_OK;
+            if (c->next_window_flags && !c->next_window_flags[k]) return LWB_OK;
+        }
+        items.push_back(LongItem{c, P, s->has});
+        if (P) chan_chains += su->channels;
+    }
+    *handled = true;
+    // from here on this path owns the batch
+    uint64_t c_lo = ~0ull, c_hi = 0, o_lo = ~0ull, o_hi = 0;
+    for (auto &it : items) {
+        lwb_chain *c = it.c;
+        if (c->stream->busy_epoch == epoch) return fail(ctx, LWB_ERR_INVALID, "a stream appears in two chains of one batch");
+        c->stream->busy_epoch = epoch;
+        const unsigned C = c->stream->setup->channels;
+        c->status = LWB_OK;
+        c->packets_done = it.P;
+        c->n_samples = it.P ? (uint32_t)((it.P - (it.has_prev ? 0 : 1)) * kLongN2) : 0;
+        if (!it.P) continue;
+        if (c->out_stride < c->n_samples) return fail(ctx, LWB_ERR_BUFFER, "chain: out_stride smaller than the samples produced");
+        c_lo = std::min(c_lo, c->coeff_offset);
+        c_hi = std::max(c_hi, c->coeff_offset + (uint64_t)it.P * C * kLongN2);
+        o_lo = std::min(o_lo, c->out_offset);
+        o_hi = std::max(o_hi, c->out_offset + (uint64_t)(C - 1) * c->out_stride + c->n_samples);
+    }
+    if (!chan_chains) return LWB_OK;
     const size_t warp_slots = (size_t)ctx->sm_count * kLongWarps;
     size_t target_runs = warp_slots * 4;                   // ~4 runs per warp evens out the tail
     if (const char *e = getenv("LWB_LONG_TARGET_RUNS")) target_runs = (size_t)atol(e);
-    const size_t min_run = 8;                              // packets per run below which cutting costs > 12%
-    // group chains by twiddle pack (one launch per pack; normally exactly one)
-    std::vector<const float *> packs;
-    for (auto &pc : plan) {
-        if (pc.pk.empty()) continue;
-        const float *pk = pc.c->stream->setup->host.tab[1].pack;
-        if (std::find(packs.begin(), packs.end(), pk) == packs.end()) packs.push_back(pk);
-    }
+    const size_t min_run = 8;                              // packets per run below which a cut costs > 12%
     int rc;
     if (!ctx->ticket.p && (rc = ensure(ctx, ctx->ticket, 256))) return rc;
-    for (const float *pack : packs) {
-        std::vector<LongRun> runs;
-        for (auto &pc : plan) {
-            if (pc.pk.empty()) continue;
-            const lwb_stream *s = pc.c->stream;
-            const lwb_setup *su = s->setup;
-            if (su->host.tab[1].pack != pack) continue;
-            const unsigned C = su->channels;
-            const size_t P = pc.pk.size();
-            size_t cuts = 1;
-            if (n_chan_chains < target_runs) cuts = (target_runs + n_chan_chains - 1) / n_chan_chains;
-            cuts = std::max<size_t>(1, std::min(cuts, P / min_run));
-            const bool has_prev = pc.pk[0].plen != 0;
-            for (unsigned ch = 0; ch < C; ch++) {
-                const float *in0 = ar.coeffs + (pc.pk[0].coeff_off - ar.coeff_base) + (size_t)ch * kLongN2;
-                float *out0 = (float *)ar.pcm + (pc.c->out_offset - ar.pcm_base) + (size_t)ch * pc.c->out_stride;
-                for (size_t k = 0; k < cuts; k++) {
-                    const size_t p0 = P * k / cuts, p1 = P * (k + 1) / cuts;   // this run emits packets [p0, p1)
-                    LongRun r;
-                    std::memset(&r, 0, sizeof(r));
-                    r.in_stride = (uint32_t)(C * kLongN2);
-                    r.state = s->d_state + (size_t)ch * state_stride(su);
-                    r.write_state = (k + 1 == cuts);
-                    if (k == 0) {
-                        r.in = in0;
-                        r.n_packets = (uint32_t)(p1 - p0);
-                        r.has_prev = has_prev;
-                        r.out = out0;
-                    } else {
-                        r.in = in0 + (p0 - 1) * (size_t)r.in_stride;           // primer = packet p0 - 1
-                        r.n_packets = (uint32_t)(p1 - p0 + 1);
-                        r.has_prev = 0;
-                        // samples emitted before packet p0: packets 0..p0-1, minus the first if no state
-                        r.out = out0 + (size_t)(p0 - (has_prev ? 0 : 1)) * kLongN2;
-                    }
-                    runs.push_back(r);
-                }
+
+    const bool host = io->memory == LWB_MEM_HOST;
+    // host memory: chunks of chains, H2D / kernel / D2H of consecutive chunks overlap on three streams
+    size_t n_chunks = 1;
+    if (host) {
+        const size_t bytes = (size_t)(c_hi - c_lo) * 4;
+        n_chunks = std::min<size_t>(std::max<size_t>(1, bytes >> 24), std::min<size_t>(16, items.size()));
+        if (const char *e = getenv("LWB_E2E_CHUNKS")) n_chunks = std::max<size_t>(1, std::min<size_t>((size_t)atol(e), items.size()));
+    }
+    const float *d_coeffs = io->coeffs;
+    float *d_pcm = (float *)io->pcm;
+    uint64_t cbase = 0, obase = 0;
+    if (host) {
+        if ((rc = ensure(ctx, ctx->coeffs, (size_t)(c_hi - c_lo) * 4))) return rc;
+        if (o_hi > o_lo && (rc = ensure(ctx, ctx->pcm, (size_t)(o_hi - o_lo) * 4))) return rc;
+        d_coeffs = (const float *)ctx->coeffs.p;
+        d_pcm = (float *)ctx->pcm.p;
+        cbase = c_lo;
+        obase = o_lo;
+        if (!ctx->ev_in[0])
+            for (int k = 0; k < 16; k++) {
+                CU(ctx, cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming));
+                CU(ctx, cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming));
             }
+        // the copy streams must not run ahead of work already queued on the compute stream that
+        // still reads/writes the arenas (previous call): order them behind it
+        CU(ctx, cudaEventRecord(ctx->ev_done[15], ctx->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[15], 0));
+    }
+    // count runs
+    std::vector<size_t> cuts(items.size(), 1);
+    size_t total_runs = 0;
+    for (size_t i = 0; i < items.size(); i++) {
+        if (!items[i].P) { cuts[i] = 0; continue; }
+        // per launch (chunk) the machine should see >= target_runs runs
+        const size_t per_launch = std::max<size_t>(1, chan_chains / n_chunks);
+        size_t k = 1;
+        if (per_launch < target_runs) k = (target_runs + per_launch - 1) / per_launch;
+        cuts[i] = std::max<size_t>(1, std::min(k, items[i].P / min_run));
+        total_runs += cuts[i] * items[i].c->stream->setup->channels;
+    }
+    Staging *st;
+    if ((rc = acquire_staging(ctx, total_runs * sizeof(LongRun), &st))) return rc;
+    if ((rc = ensure(ctx, ctx->chains, total_runs * sizeof(LongRun)))) return rc;
+    LongRun *h_runs = (LongRun *)st->h, *w = h_runs;
+    for (size_t k = 0; k < n_chunks; k++) {
+        const size_t i0 = items.size() * k / n_chunks, i1 = items.size() * (k + 1) / n_chunks;
+        LongRun *w0 = w;
+        uint64_t kc_lo = ~0ull, kc_hi = 0, ko_lo = ~0ull, ko_hi = 0;
+        for (size_t i = i0; i < i1; i++) {
+            if (!items[i].P) continue;
+            long_runs_of(items[i], cuts[i], d_coeffs, cbase, d_pcm, obase, w);
+            const lwb_chain *c = items[i].c;
+            const unsigned C = c->stream->setup->channels;
+            kc_lo = std::min(kc_lo, c->coeff_offset);
+            kc_hi = std::max(kc_hi, c->coeff_offset + (uint64_t)items[i].P * C * kLongN2);
+            ko_lo = std::min(ko_lo, c->out_offset);
+            ko_hi = std::max(ko_hi, c->out_offset + (uint64_t)(C - 1) * c->out_stride + c->n_samples);
         }
-        if (runs.empty()) continue;
-        if ((rc = ensure_pinned(ctx, runs.size() * sizeof(LongRun)))) return rc;
-        if ((rc = ensure(ctx, ctx->chains, runs.size() * sizeof(LongRun)))) return rc;
-        CU(ctx, cudaStreamSynchronize(ctx->stream));          // pinned staging is reused
-        std::memcpy(ctx->h_desc, runs.data(), runs.size() * sizeof(LongRun));
-        CU(ctx, cudaMemcpyAsync(ctx->chains.p, ctx->h_desc, runs.size() * sizeof(LongRun), cudaMemcpyHostToDevice,
-                                ctx->stream));
-        if (long_launch(ctx->stream, (const LongRun *)ctx->chains.p, (uint32_t)runs.size(), pack,
-                        (unsigned int *)ctx->ticket.p, ctx->sm_count))
+        const size_t nr = (size_t)(w - w0);
+        if (!nr) continue;
+        if (host) {
+            CU(ctx, cudaMemcpyAsync((float *)ctx->coeffs.p + (kc_lo - cbase), io->coeffs + kc_lo, (size_t)(kc_hi - kc_lo) * 4,
+                                    cudaMemcpyHostToDevice, ctx->copy_in));
+            CU(ctx, cudaEventRecord(ctx->ev_in[k], ctx->copy_in));
+            CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[k], 0));
+        }
+        LongRun *d_runs = (LongRun *)ctx->chains.p + (w0 - h_runs);
+        CU(ctx, cudaMemcpyAsync(d_runs, w0, nr * sizeof(LongRun), cudaMemcpyHostToDevice, ctx->stream));
+        if (long_launch(ctx->stream, d_runs, (uint32_t)nr, pack, (unsigned int *)ctx->ticket.p, ctx->sm_count))
             return fail(ctx, LWB_ERR_CUDA, "long kernel launch", cudaGetLastError());
         ctx->launches++;
+        if (host && ko_hi > ko_lo) {
+            CU(ctx, cudaEventRecord(ctx->ev_done[k], ctx->stream));
+            CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[k], 0));
+            CU(ctx, cudaMemcpyAsync((float *)io->pcm + ko_lo, (float *)ctx->pcm.p + (ko_lo - obase), (size_t)(ko_hi - ko_lo) * 4,
+                                    cudaMemcpyDeviceToHost, ctx->copy_out));
+        }
     }
+    CU(ctx, cudaEventRecord(st->ev, ctx->stream));
+    st->pending = true;
+    if (host) {
+        CU(ctx, cudaStreamSynchronize(ctx->copy_out));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    for (auto &it : items)
+        if (it.P) {
+            it.c->stream->has = true;
+            it.c->stream->plen = kLongN2;
+        }
     return LWB_OK;
 }
 
@@ -790,6 +920,11 @@ extern "C" int lwb_decode_chains(lwb_ctx *ctx, lwb_chain *chains, size_t n_chain
     CU(ctx, cudaSetDevice(ctx->device));
     static uint64_t epoch = 0;
     epoch++;
+    {
+        bool handled = false;
+        int rc0 = try_long(ctx, chains, n_chains, io, epoch, &handled);
+        if (rc0 || handled) return rc0;
+    }
     const bool residue = io->entry == LWB_ENTRY_RESIDUE;
     const bool planar = is_planar(io->out_format);
     std::vector<PlanChain> plan(n_chains);
@@ -869,8 +1004,7 @@ extern "C" int lwb_decode_chains(lwb_ctx *ctx, lwb_chain *chains, size_t n_chain
             }
             ar.kinds_row0 = r_lo;
         }
-        if (long_eligible(plan, io)) rc = run_long(ctx, plan, ar);
-        else rc = run_generic(ctx, plan, io, ar);
+        rc = run_generic(ctx, plan, io, ar);
         if (rc) return rc;
         if (io->memory == LWB_MEM_HOST) {
             if (o_hi > o_lo)

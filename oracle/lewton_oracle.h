@@ -144,10 +144,11 @@ int lwo_synth_spectrum(const lwo_tables *t0, const lwo_tables *t1, int channels,
 
 /* CPU baseline (bench.py cpu_baseline / --impl reference): S chains x P
  * long/long blocks, IMDCT + window + OLA, `threads` pthreads, static partition
- * over chains.  spectrum [S][P][n2]; out [S][P*n2].  Returns seconds of the
- * timed region (steady_clock), scratch preallocated outside it. */
+ * over chains, the pass repeated `reps` times over the same input.  spectrum [S][P][n2];
+ * out [S][P*n2].  Returns seconds of the timed region (CLOCK_MONOTONIC), scratch
+ * preallocated outside it. */
 double lwo_bench_chains(int bs, int chains, int packets, const float *spectrum,
-                        float *out, int threads);
+                        float *out, int threads, int reps);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ void lwo_inverse_mdct_with_scratch(const lwo_tables *t, float *buffer, float *bu
 
 typedef struct {
     const lwo_tables *t;
-    int c0, c1, packets;
+    int c0, c1, packets, reps;
     const float *spectrum;
     float *out;
 } job_t;
@@ -36,6 +36,7 @@ static void *worker(void *arg)
     float *x = (float *)malloc(sizeof(float) * n);
     float *scratch = (float *)malloc(sizeof(float) * n2);
     float *prev = (float *)malloc(sizeof(float) * n2);
+    for (int rep = 0; rep < j->reps; rep++)
     for (int c = j->c0; c < j->c1; c++) {
         int has = 0;
         float *o = j->out + (size_t)c * j->packets * n2;
@@ -57,7 +58,7 @@ static void *worker(void *arg)
 }
 
 double lwo_bench_chains(int bs, int chains, int packets, const float *spectrum,
-                        float *out, int threads)
+                        float *out, int threads, int reps)
 {
     lwo_tables *t = lwo_tables_new(bs);
     if (!t) return -1.0;
@@ -72,6 +73,7 @@ double lwo_bench_chains(int bs, int chains, int packets, const float *spectrum,
         jobs[i].c0 = (int)((long)chains * i / threads);
         jobs[i].c1 = (int)((long)chains * (i + 1) / threads);
         jobs[i].packets = packets;
+        jobs[i].reps = reps < 1 ? 1 : reps;
         jobs[i].spectrum = spectrum;
         jobs[i].out = out;
         pthread_create(&th[i], NULL, worker, &jobs[i]);

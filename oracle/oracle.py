@@ -95,7 +95,7 @@ def lib():
                                    C.POINTER(ChannelIn), vp, vp, C.POINTER(C.c_int)]
     L.lwo_synth_spectrum.argtypes = [vp, vp, ip, ip, ip, ip, vp, vp, vp, C.POINTER(C.c_int)]
     L.lwo_bench_chains.restype = C.c_double
-    L.lwo_bench_chains.argtypes = [ip, ip, ip, vp, vp, ip]
+    L.lwo_bench_chains.argtypes = [ip, ip, ip, vp, vp, ip, ip]
     _lib = L
     return L
 
@@ -337,10 +337,10 @@ def synth_packet(bs0, bs1, blockflag, prev_flag, next_flag, coupling, floors, re
     return rc, out[:, : olen.value].copy()
 
 
-def bench_chains(bs, spectrum, threads):
-    """spectrum [chains][packets][n/2] -> (seconds, out [chains][(packets-1)*n/2 used])."""
+def bench_chains(bs, spectrum, threads, reps=1):
+    """spectrum [chains][packets][n/2] -> (seconds for `reps` passes, out [chains][(packets-1)*n/2 used])."""
     sp = np.ascontiguousarray(spectrum, np.float32)
     chains, packets, n2 = sp.shape
     out = np.zeros((chains, packets * n2), np.float32)
-    sec = lib().lwo_bench_chains(bs, chains, packets, _ptr(sp), _ptr(out), threads)
+    sec = lib().lwo_bench_chains(bs, chains, packets, _ptr(sp), _ptr(out), threads, reps)
     return sec, out

@@ -410,15 +410,19 @@ def test_special_values_on_gpu(ctx, oracle):
     """Denormals are kept (no flush-to-zero), inf/NaN propagate like on the CPU."""
     rng = np.random.default_rng(41)
     su = make_setup(ctx, 1, 8, 11)
-    spec = rng.standard_normal((1, 4, 1, 1024)).astype(np.float32)
-    spec[0, 0, 0, :100] = 1e-42
-    spec[0, 1, 0, 3] = np.inf
-    spec[0, 2, 0, 9] = np.nan
-    spec[0, 3, 0] *= 1e-38
+    spec = rng.standard_normal((2, 4, 1, 1024)).astype(np.float32)
+    spec[0, 0, 0, :100] = 1e-42          # denormal inputs
+    spec[0, 1, 0] *= 1e-38               # outputs around / below the normal range
+    spec[0, 2, 0] *= 1e-41
+    spec[0, 3, 0] = 0.0
+    spec[1, 1, 0, 3] = np.inf            # second stream: inf / NaN
+    spec[1, 2, 0, 9] = np.nan
+    want, fin = oracle_batch(oracle, spec)
+    assert np.any((np.abs(want[0]) > 0) & (np.abs(want[0]) < 1.1e-38)), "test should exercise denormal outputs"
+    assert np.any(np.isnan(want[1]))
     for env in (None, {"LWB_FORCE_GENERIC": "1"}):
-        pwr = L.PreviousWindowRight(su)
-        _, pcm = run_batch(ctx, su, [pwr], spec, 4, cabi.MEM_HOST, env)
-        want, fin = oracle_batch(oracle, spec)
-        assert bits_equal(pcm[0][:, :3072], want[0])
-        assert bits_equal(pwr.data(), fin[0])
-    assert np.any((np.abs(want[0]) > 0) & (np.abs(want[0]) < 1.2e-38)), "test should exercise denormal outputs"
+        pwrs = [L.PreviousWindowRight(su) for _ in range(2)]
+        _, pcm = run_batch(ctx, su, pwrs, spec, 4, cabi.MEM_HOST, env)
+        for s in range(2):
+            assert bits_equal(pcm[s][:, :3072], want[s]), (env, s, mismatch_report(pcm[s][:, :3072], want[s]))
+            assert bits_equal(pwrs[s].data(), fin[s])
