@@ -54,7 +54,8 @@ struct LongRun {
     uint32_t n_packets;     // including a primer packet if prime != 0
     uint8_t has_prev;       // 1: packet 0 overlaps with `state`;  0: packet 0 emits nothing
     uint8_t write_state;    // 1: store the last packet's right half to `state`
-    uint8_t pad[2];
+    uint8_t dummy;          // 1: filler partner of an unpaired run: transformed, never stored
+    uint8_t pad[1];
 };
 
 struct V { float x, y; };    // (group a, group b)
@@ -257,7 +258,21 @@ inline void long_build_pack(const float *a, const float *b, const float *c, cons
 }
 
 // ---- the per-lane arithmetic ----------------------------------------------------------------
+// All phase functions are templated on NB = blocks a warp transforms in lockstep (1 or 2).  With
+// NB = 2 every twiddle fetched from shared memory serves two independent blocks and the two
+// instruction streams interleave, which is what hides the FP / shared-memory latencies at 12
+// warps per SM.
 struct Q4 { float x, y, z, w; };
+
+LWB_HD Q4 ld_q4(const float *p)
+{
+#if defined(__CUDA_ARCH__)
+    const float4 v = *reinterpret_cast<const float4 *>(p);
+    return Q4{v.x, v.y, v.z, v.w};
+#else
+    return Q4{p[0], p[1], p[2], p[3]};
+#endif
+}
 
 // step-3 butterfly (imdct.rs:36-41): hi/lo are complex values (O = odd index, E = even index)
 LWB_HD void bfly(V &Oh, V &Eh, V &Ol, V &El, V w0, V w1)
@@ -270,46 +285,93 @@ LWB_HD void bfly(V &Oh, V &Eh, V &Ol, V &El, V w0, V w1)
     El = vadd_p(vmul(k01, w0), vmul(k00, w1));
 }
 
-// Phase A.  F1[m] = spectrum quad #(lane + 64 m), F2[m] = quad #(63 - lane + 64 m).
-// Step 0 (imdct.rs:337-371): quad #f yields c = f from (q1,q3) and c = 511-f from (q0,q2).
-template <class TW>
-LWB_HD void phase_a(const Q4 F1[4], const Q4 F2[4], TW tw, V O[8], V E[8])
+// Phase A.  tile[b] = the block's 1024 spectrum floats.  Quad #f (4 floats at 4f) yields element
+// c = f from (q1,q3) and c = 511-f from (q0,q2)  (step 0, imdct.rs:337-371).  The lane reads quads
+// #(lane + 64 m) and #(63 - lane + 64 m), m < 4: they feed slots m and 7-m of both groups.
+template <int NB, class TW>
+LWB_HD void phase_a(const float *const tile[NB], int lane, TW tw, V O[NB][8], V E[NB][8])
 {
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        V qa, qb;
-        if (j < 4) { qa = V{F1[j].w, F2[j].w}; qb = V{F1[j].y, F2[j].y}; }
-        else { qa = V{F2[7 - j].x, F1[7 - j].x}; qb = V{F2[7 - j].z, F1[7 - j].z}; }
-        const V w0 = tw(P_S0W0 + j), w1 = tw(P_S0W1 + j);
-        O[j] = vsub_p(vmul(qa, w0), vmul(qb, w1));
-        E[j] = vadd_p(vmul(qa, w1), vmul(qb, w0));
+    for (int m = 0; m < 4; m++) {
+        Q4 f1[NB], f2[NB];
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            f1[b] = ld_q4(tile[b] + 4 * (lane + 64 * m));
+            f2[b] = ld_q4(tile[b] + 4 * (63 - lane + 64 * m));
+        }
+        {
+            const V w0 = tw(P_S0W0 + m), w1 = tw(P_S0W1 + m);
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const V qa = V{f1[b].w, f2[b].w}, qb = V{f1[b].y, f2[b].y};
+                O[b][m] = vsub_p(vmul(qa, w0), vmul(qb, w1));
+                E[b][m] = vadd_p(vmul(qa, w1), vmul(qb, w0));
+            }
+        }
+        {
+            const int j = 7 - m;
+            const V w0 = tw(P_S0W0 + j), w1 = tw(P_S0W1 + j);
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const V qa = V{f2[b].x, f1[b].x}, qb = V{f2[b].z, f1[b].z};
+                O[b][j] = vsub_p(vmul(qa, w0), vmul(qb, w1));
+                E[b][j] = vadd_p(vmul(qa, w1), vmul(qb, w0));
+            }
+        }
     }
     // step 2 (imdct.rs:385-430): bit 8
 #pragma unroll
-    for (int j = 0; j < 4; j++) bfly(O[j + 4], E[j + 4], O[j], E[j], tw(P_S2W0 + j), tw(P_S2W1 + j));
+    for (int j = 0; j < 4; j++) {
+        const V w0 = tw(P_S2W0 + j), w1 = tw(P_S2W1 + j);
+#pragma unroll
+        for (int b = 0; b < NB; b++) bfly(O[b][j + 4], E[b][j + 4], O[b][j], E[b][j], w0, w1);
+    }
     // stage 0 (imdct.rs:445-446): bit 7
 #pragma unroll
-    for (int j = 0; j < 8; j++)
-        if (j & 2) bfly(O[j], E[j], O[j - 2], E[j - 2], tw(P_L0W0 + (j & 1)), tw(P_L0W1 + (j & 1)));
-    // stage 1 (imdct.rs:449-452): bit 6
+    for (int u = 0; u < 2; u++) {
+        const V w0 = tw(P_L0W0 + u), w1 = tw(P_L0W1 + u);
 #pragma unroll
-    for (int j = 0; j < 8; j++)
-        if (j & 1) bfly(O[j], E[j], O[j - 1], E[j - 1], tw(P_L1W0), tw(P_L1W1));
+        for (int b = 0; b < NB; b++) {
+            bfly(O[b][2 + u], E[b][2 + u], O[b][u], E[b][u], w0, w1);
+            bfly(O[b][6 + u], E[b][6 + u], O[b][4 + u], E[b][4 + u], w0, w1);
+        }
+    }
+    // stage 1 (imdct.rs:449-452): bit 6
+    {
+        const V w0 = tw(P_L1W0), w1 = tw(P_L1W1);
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+            for (int j = 1; j < 8; j += 2) bfly(O[b][j], E[b][j], O[b][j - 1], E[b][j - 1], w0, w1);
+    }
 }
 
 // Phase B: stages 2,3,4 (imdct.rs:454-477): bits 5,4,3 = slot bits 2,1,0
-template <class TW>
-LWB_HD void phase_b(TW tw, V O[8], V E[8])
+template <int NB, class TW>
+LWB_HD void phase_b(TW tw, V O[NB][8], V E[NB][8])
 {
 #pragma unroll
-    for (int j = 0; j < 8; j++)
-        if (j & 4) bfly(O[j], E[j], O[j - 4], E[j - 4], tw(P_L2W0 + (j & 3)), tw(P_L2W1 + (j & 3)));
+    for (int u = 0; u < 4; u++) {
+        const V w0 = tw(P_L2W0 + u), w1 = tw(P_L2W1 + u);
 #pragma unroll
-    for (int j = 0; j < 8; j++)
-        if (j & 2) bfly(O[j], E[j], O[j - 2], E[j - 2], tw(P_L3W0 + (j & 1)), tw(P_L3W1 + (j & 1)));
+        for (int b = 0; b < NB; b++) bfly(O[b][4 + u], E[b][4 + u], O[b][u], E[b][u], w0, w1);
+    }
 #pragma unroll
-    for (int j = 0; j < 8; j++)
-        if (j & 1) bfly(O[j], E[j], O[j - 1], E[j - 1], tw(P_L4W0), tw(P_L4W1));
+    for (int u = 0; u < 2; u++) {
+        const V w0 = tw(P_L3W0 + u), w1 = tw(P_L3W1 + u);
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            bfly(O[b][2 + u], E[b][2 + u], O[b][u], E[b][u], w0, w1);
+            bfly(O[b][6 + u], E[b][6 + u], O[b][4 + u], E[b][4 + u], w0, w1);
+        }
+    }
+    {
+        const V w0 = tw(P_L4W0), w1 = tw(P_L4W1);
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+            for (int j = 1; j < 8; j += 2) bfly(O[b][j], E[b][j], O[b][j - 1], E[b][j - 1], w0, w1);
+    }
 }
 
 // imdct.rs:201-232 on slots s+3..s (z7[0] = O[s+3], z7[-1] = E[s+3], ...).  PROD: slots s+2 and
@@ -336,12 +398,9 @@ LWB_HD void iter54(V O[8], V E[8], int s)
     E[s] = vadd(k11, k22);
 }
 
-// Phase C part 1: ld654 (imdct.rs:234-288), then the half swap of the even slots and step 7
-// (imdct.rs:533-580).  After it slot j holds, per half, the V-buffer element 511 - outIndex(..).
-template <class TW>
-LWB_HD void phase_c_fft(TW tw, V O[8], V E[8])
+// ld654 (imdct.rs:234-288) for one block
+LWB_HD void ld654(V O[8], V E[8], V a2)
 {
-    const V a2 = tw(P_A2);
     V k00, k11;
     k00 = vsub(O[7], O[3]); k11 = vsub(E[7], E[3]);
     O[7] = vadd(O[7], O[3]); E[7] = vadd(E[7], E[3]);
@@ -359,41 +418,53 @@ LWB_HD void phase_c_fft(TW tw, V O[8], V E[8])
     E[0] = vmul(vsub(k00, k11), a2);
     iter54<false>(O, E, 4);
     iter54<true>(O, E, 0);
-    // steps 4-6 (imdct.rs:490-528) are pure renaming: U element 8T+j becomes V element
-    // 511 - rev9(8T+j) with (V.even, V.odd) = (U.odd, U.even) = (O, E).
-    // step 7 pairs V element p (odd slot j, "D") with 511-p (slot 7-j of the OTHER group, "E"):
-    // swap the halves of the even slots so partners line up.
+}
+
+// Phase C part 1: ld654, then the half swap of the even slots and step 7 (imdct.rs:533-580).
+// Steps 4-6 (imdct.rs:490-528) are pure renaming: U element 8T+j becomes V element
+// 511 - rev9(8T+j) with (V.even, V.odd) = (U.odd, U.even) = (O, E).  Step 7 pairs V element p
+// (odd slot j, "D") with 511-p (slot 7-j of the OTHER group, "E"): swapping the halves of the even
+// slots lines partners up.  Afterwards slot j holds, per half, V element 511 - outIndex(..).
+template <int NB, class TW>
+LWB_HD void phase_c_fft(TW tw, V O[NB][8], V E[NB][8])
+{
+    const V a2 = tw(P_A2);
 #pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-        O[j] = V{O[j].y, O[j].x};
-        E[j] = V{E[j].y, E[j].x};
+    for (int b = 0; b < NB; b++) {
+        ld654(O[b], E[b], a2);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            O[b][j] = V{O[b][j].y, O[b][j].x};
+            E[b][j] = V{E[b][j].y, E[b][j].x};
+        }
     }
 #pragma unroll
     for (int jj = 0; jj < 4; jj++) {
         const int d = 2 * jj + 1, e = 7 - d;
         const V c0 = tw(P_S7C0 + jj), c1 = tw(P_S7C1 + jj);
-        const V a02 = vsub(O[d], O[e]);
-        const V a11 = vadd(E[d], E[e]);
-        const V b0 = vadd_p(vmul(c1, a02), vmul(c0, a11));
-        const V b1 = vsub_p(vmul(c1, a11), vmul(c0, a02));
-        const V b2 = vadd(O[d], O[e]);
-        const V b3 = vsub(E[d], E[e]);
-        O[d] = vadd(b2, b0);
-        E[d] = vadd(b3, b1);
-        O[e] = vsub(b2, b0);
-        E[e] = vsub(b1, b3);
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const V a02 = vsub(O[b][d], O[b][e]);
+            const V a11 = vadd(E[b][d], E[b][e]);
+            const V b0 = vadd_p(vmul(c1, a02), vmul(c0, a11));
+            const V b1 = vsub_p(vmul(c1, a11), vmul(c0, a02));
+            const V b2 = vadd(O[b][d], O[b][e]);
+            const V b3 = vsub(E[b][d], E[b][e]);
+            O[b][d] = vadd(b2, b0);
+            E[b][d] = vadd(b3, b1);
+            O[b][e] = vsub(b2, b0);
+            E[b][e] = vsub(b1, b3);
+        }
     }
 }
 
-// Phase C part 2 for one slot: step 8 (imdct.rs:589-658) + window/overlap-add (audio.rs:1112-1118).
+// Phase C part 2 for one slot of one block: step 8 (imdct.rs:589-658) + window/overlap-add
+// (audio.rs:1112-1118).
 //   p_odd  = out[m] = -out[1023-m];   p_even = out[1024+m] = out[2047-m]
 //   pcm[m]      = p_odd * w[m] + prev[m] * w[1023-m]
 //   pcm[1023-m] = (-p_odd) * w[1023-m] + prev[1023-m] * w[m]   (== prev*w[m] - p_odd*w[1023-m])
-template <class TW>
-LWB_HD void phase_c_out(TW tw, int j, V Oj, V Ej, V prev_lo, V prev_hi, V &pcm_lo, V &pcm_hi, V &p_even)
+LWB_HD void step8_ola(V b0, V b1, V wlo, V whi, V Oj, V Ej, V prev_lo, V prev_hi, V &pcm_lo, V &pcm_hi, V &p_even)
 {
-    const V b0 = tw(P_B0 + j), b1 = tw(P_B1 + j);
-    const V wlo = tw(P_WLO + j), whi = tw(P_WHI + j);
     const V p_odd = vsub_p(vmul(Oj, b1), vmul(Ej, b0));
     p_even = vnsub_p(vmul(Oj, b0), vmul(Ej, b1));       // (-V.e)*B0 - V.o*B1, imdct.rs:620
     pcm_lo = vadd_p(vmul(p_odd, wlo), vmul(prev_lo, whi));
@@ -404,16 +475,24 @@ LWB_HD void phase_c_out(TW tw, int j, V Oj, V Ej, V prev_lo, V prev_hi, V &pcm_l
 // ---------------------------------------------------------------------------------------------
 // device side
 // ---------------------------------------------------------------------------------------------
+#ifndef LWB_LONG_NB
+#define LWB_LONG_NB 1
+#endif
 #ifndef LWB_LONG_WARPS
 #define LWB_LONG_WARPS 12
 #endif
+#ifndef LWB_LONG_RING
+#define LWB_LONG_RING (LWB_LONG_NB == 2 ? 2 : 3)
+#endif
+constexpr int kLongNB = LWB_LONG_NB;           // blocks (runs) a warp transforms in lockstep
 constexpr int kLongWarps = LWB_LONG_WARPS;     // warps per CTA, one CTA per SM
-constexpr int kLongRing = 3;                   // spectrum tiles in flight per warp
+constexpr int kLongRing = LWB_LONG_RING;       // ring stages per warp, each holding kLongNB tiles
 constexpr int kLongTileBytes = kLongN2 * 4;
-// [tiles: warps x ring x 4 KB, 2 KB-aligned at run time][pack][mbarriers][next-run descriptors]
-constexpr size_t kLongSmemBytes = 2048 + (size_t)kLongWarps * kLongRing * kLongTileBytes +
+constexpr int kLongStageBytes = kLongNB * kLongTileBytes;
+// [tiles: warps x ring x NB x 4 KB, 2 KB-aligned at run time][pack][mbarriers][next-run descriptors]
+constexpr size_t kLongSmemBytes = 2048 + (size_t)kLongWarps * kLongRing * kLongStageBytes +
                                   (size_t)kLongPackFloats * 4 + kLongWarps * kLongRing * 8 +
-                                  kLongWarps * sizeof(LongRun) + 64;
+                                  kLongWarps * kLongNB * sizeof(LongRun) + 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -457,14 +536,18 @@ __device__ __forceinline__ void lds_eo(uint32_t addr, float &e, float &o)
 
 // Twiddle residency: pack slots [kTwReg0, kTwReg1) live in registers for the whole kernel, the
 // rest is read from the CTA's shared copy of the pack when used (compile-time choice per slot).
-#ifndef LWB_TW_S0_SMEM
-#define LWB_TW_S0_SMEM 0
+// Default (measured best on B200, profiles/): one block per warp, 12 warps, step-2 / stage-0 /
+// stage-1 twiddles resident (slots 16..29), everything else fetched per block -- 156 registers,
+// no spills.  Two blocks per warp (NB = 2) doubles the loop body past the instruction cache and
+// measured 2x slower; 16 warps with no resident twiddles is shared-memory bound.
+#ifndef LWB_TW_REG0
+#define LWB_TW_REG0 (LWB_LONG_NB == 2 ? 0 : 16)
 #endif
-#ifndef LWB_TW_B_SMEM
-#define LWB_TW_B_SMEM 0
+#ifndef LWB_TW_REG1
+#define LWB_TW_REG1 (LWB_LONG_NB == 2 ? 0 : 30)
 #endif
-constexpr int kTwReg0 = LWB_TW_S0_SMEM ? P_S2W0 : 0;
-constexpr int kTwReg1 = LWB_TW_B_SMEM ? P_A_END : P_B_END;
+constexpr int kTwReg0 = LWB_TW_REG0;
+constexpr int kTwReg1 = LWB_TW_REG1;
 struct TwMix {
     const V *r;                   // registers: slots [kTwReg0, kTwReg1)
     const V *lane_base;           // &pack[lane] in shared memory
@@ -486,71 +569,88 @@ __device__ __forceinline__ uint32_t laneC(int lane, int half) { return 4u * (uin
 #define LWB_KB(j, h) (4u * (uint32_t)swz(((h) << 6) | ((j) << 3)))
 #define LWB_KC(j) (4u * (uint32_t)swz(j))
 
-// Step 8 + window + overlap-add + stores for all 8 slots.  FROM_STATE: the previous right half
-// comes from the stream state in HBM (first packet of a run with history); EMIT: store PCM
-// (streaming stores: written once, never read back by this kernel).
-template <bool FROM_STATE, bool EMIT>
-__device__ __forceinline__ void out_stage(const TwMix &tw, int lane, const V O[8], const V E[8], V pe[8],
-                                          const float *__restrict__ state, float *__restrict__ out)
+// Uniform (per-warp) view of the runs being processed
+struct RunCur {
+    const float *in;
+    float *out;
+    float *state;
+    uint32_t in_stride;
+    uint32_t flags;               // bit0 has_prev, bit1 write_state, bit2 dummy
+};
+__device__ __forceinline__ RunCur run_cur(const LongRun &r)
 {
-    float *o_lo = out + lane, *o_hi = out + 63 - lane;       // out[mx], out[my] bases
-    const float *s_lo = state + lane, *s_hi = state + 63 - lane;
+    return RunCur{r.in, r.out, r.state, r.in_stride,
+                  (uint32_t)(r.has_prev ? 1u : 0u) | (r.write_state ? 2u : 0u) | (r.dummy ? 4u : 0u)};
+}
+
+// Step 8 + window + overlap-add + stores, all 8 slots of all NB blocks.  `first`: packet 0 of the
+// run (its previous right half comes from the stream state in HBM if has_prev, else nothing is
+// emitted).  Streaming stores: PCM is written once and never read back by this kernel.
+template <int NB, bool FIRST>
+__device__ __forceinline__ void out_stage(const TwMix &tw, int lane, const V O[NB][8], const V E[NB][8], V pe[NB][8],
+                                          const RunCur cur[NB], float *out[NB])
+{
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         const int r64 = 64 * rev3(j);
         const bool nat = (j & 1);             // odd slots: half x -> lane, half y -> 63 - lane
-        V plo = pe[j], phi = pe[j];
-        if (FROM_STATE) {
-            // prev[m] and prev[1023 - m] read separately: an imported state need not be symmetric
-            const float ax = nat ? s_lo[r64] : s_hi[r64], ay = nat ? s_hi[r64] : s_lo[r64];
-            const float bx = nat ? s_hi[960 - r64] : s_lo[960 - r64], by = nat ? s_lo[960 - r64] : s_hi[960 - r64];
-            plo = V{ax, ay};
-            phi = V{bx, by};
-        }
-        V lo, hi, pev;
-        phase_c_out(tw, j, O[j], E[j], plo, phi, lo, hi, pev);
-        pe[j] = pev;
-        if (EMIT) {
-            // m = r64 + lane (or + 63 - lane); 1023 - m = 960 - r64 + 63 - lane (or + lane)
-            if (nat) {
-                __stcs(o_lo + r64, lo.x); __stcs(o_hi + r64, lo.y);
-                __stcs(o_hi + 960 - r64, hi.x); __stcs(o_lo + 960 - r64, hi.y);
-            } else {
-                __stcs(o_hi + r64, lo.x); __stcs(o_lo + r64, lo.y);
-                __stcs(o_lo + 960 - r64, hi.x); __stcs(o_hi + 960 - r64, hi.y);
+        const V b0 = tw(P_B0 + j), b1 = tw(P_B1 + j);
+        const V wlo = tw(P_WLO + j), whi = tw(P_WHI + j);
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            V plo = pe[b][j], phi = pe[b][j];
+            bool emit = !(cur[b].flags & 4u);
+            if (FIRST) {
+                emit = emit && (cur[b].flags & 1u);
+                if (cur[b].flags & 1u) {
+                    // prev[m] and prev[1023 - m] read separately: an imported state need not be symmetric
+                    const float *s_lo = cur[b].state + lane, *s_hi = cur[b].state + 63 - lane;
+                    const float ax = nat ? s_lo[r64] : s_hi[r64], ay = nat ? s_hi[r64] : s_lo[r64];
+                    const float bx = nat ? s_hi[960 - r64] : s_lo[960 - r64];
+                    const float by = nat ? s_lo[960 - r64] : s_hi[960 - r64];
+                    plo = V{ax, ay};
+                    phi = V{bx, by};
+                }
+            }
+            V lo, hi, pev;
+            step8_ola(b0, b1, wlo, whi, O[b][j], E[b][j], plo, phi, lo, hi, pev);
+            pe[b][j] = pev;
+            if (emit) {
+                // m = r64 + lane (or + 63 - lane); 1023 - m = 960 - r64 + 63 - lane (or + lane)
+                float *o_lo = out[b] + lane, *o_hi = out[b] + 63 - lane;
+                if (nat) {
+                    __stcs(o_lo + r64, lo.x); __stcs(o_hi + r64, lo.y);
+                    __stcs(o_hi + 960 - r64, hi.x); __stcs(o_lo + 960 - r64, hi.y);
+                } else {
+                    __stcs(o_hi + r64, lo.x); __stcs(o_lo + r64, lo.y);
+                    __stcs(o_lo + 960 - r64, hi.x); __stcs(o_hi + 960 - r64, hi.y);
+                }
             }
         }
     }
 }
 
-// Uniform (per-warp) view of a run while it is being processed
-struct RunCur {
-    const float *in;
-    float *out;
-    float *state;
-    uint32_t in_stride, npk;
-    uint32_t has_prev, write_state;
-};
-
-// pack: the twiddle pack of the setup's blocksize-11 tables (long_build_pack); ticket: a zeroed
-// counter from which warps draw run indices.
+// runs: groups of kLongNB consecutive entries with equal n_packets (the host pads with dummy
+// runs); pack: the twiddle pack of the setup's blocksize-11 tables (long_build_pack); ticket: a
+// zeroed counter from which warps draw group indices.
 __global__ void __launch_bounds__(kLongWarps * 32, 1)
-k_long(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restrict__ pack,
+k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restrict__ pack,
        unsigned int *__restrict__ ticket)
 {
+    constexpr int NB = kLongNB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // tiles first, aligned to 2 KB in the shared window
     const uint32_t raw_s = smem_u32(smem_raw);
     const uint32_t align_pad = (2048u - (raw_s & 2047u)) & 2047u;
     unsigned char *base = smem_raw + align_pad;
-    float *tiles = reinterpret_cast<float *>(base) + (size_t)warp * kLongRing * kLongN2;
-    V *s_pack = reinterpret_cast<V *>(base + (size_t)kLongWarps * kLongRing * kLongTileBytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)kLongWarps * kLongRing * kLongTileBytes +
-                                                  (size_t)kLongPackFloats * 4) + warp * kLongRing;
-    LongRun *s_next = reinterpret_cast<LongRun *>(base + (size_t)kLongWarps * kLongRing * kLongTileBytes +
-                                                  (size_t)kLongPackFloats * 4 + (size_t)kLongWarps * kLongRing * 8) + warp;
-    if (n_runs == 0) return;
+    constexpr size_t kTilesBytes = (size_t)kLongWarps * kLongRing * kLongStageBytes;
+    float *tiles = reinterpret_cast<float *>(base) + (size_t)warp * kLongRing * NB * kLongN2;
+    V *s_pack = reinterpret_cast<V *>(base + kTilesBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + kTilesBytes + (size_t)kLongPackFloats * 4) + warp * kLongRing;
+    LongRun *s_next = reinterpret_cast<LongRun *>(base + kTilesBytes + (size_t)kLongPackFloats * 4 +
+                                                  (size_t)kLongWarps * kLongRing * 8) + warp * NB;
+    if (n_groups == 0) return;
 
     // stage the pack once per CTA
     {
@@ -564,7 +664,7 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restric
     }
     __syncthreads();
 
-    V twR[kTwReg1 - kTwReg0];
+    V twR[kTwReg1 - kTwReg0 > 0 ? kTwReg1 - kTwReg0 : 1];
 #pragma unroll
     for (int s = kTwReg0; s < kTwReg1; s++) twR[s - kTwReg0] = s_pack[s * 32 + lane];
     const TwMix tw{twR, s_pack + lane};
@@ -574,170 +674,194 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restric
     const uint32_t lA0 = laneA(lane, 0), lA1 = laneA(lane, 1);
     const uint32_t lB = laneB(lane);
     const uint32_t lC0 = laneC(lane, 0), lC1 = laneC(lane, 1);
-    uint32_t phase_bits = 0;                  // parity of each ring slot's mbarrier
-    uint32_t slot_i = 0;                      // ring slot of the packet being processed
+    uint32_t phase_bits = 0;                  // parity of each ring stage's mbarrier
+    uint32_t slot_i = 0;                      // ring stage of the packets being processed
 
-    // ---- run hand-over state (only lane 0's copy of the load cursor matters) --------------------
-    // Loads are issued in processing order across run boundaries: once all tiles of the current
-    // run are in flight, lane 0 draws the next ticket, stages that run's descriptor in shared
-    // memory and starts loading ITS first tiles into the ring slots as they free up, so a warp
+    // ---- group hand-over (only lane 0's copy of the load cursor matters) -------------------------
+    // Loads are issued in processing order across group boundaries: once all tiles of the current
+    // group are in flight, lane 0 draws the next ticket, stages those runs' descriptors in shared
+    // memory and starts loading THEIR first tiles into the ring stages as they free up, so a warp
     // never idles through ticket + descriptor + first-tile latency between runs.
-    uint32_t lc = 0;                          // tiles of the current run issued so far
-    uint32_t nx_state = 0;                    // 0 unknown, 1 valid (descriptor in s_next), 2 none
+    uint32_t lc = 0;                          // stages of the current group issued so far
+    uint32_t nx_state = 0;                    // 0 unknown, 1 valid (descriptors in s_next), 2 none
     uint32_t nx_lc = 0, nx_npk = 0;
-    RunCur cur;
+    RunCur cur[NB];
+    uint32_t npk;
+
+    auto issue_stage = [&](uint32_t stage, const LongRun *r, uint32_t pkt) {     // lane 0 only
+        const uint32_t bar = bars_s + 8 * stage;
+        mbar_expect_tx(bar, kLongStageBytes);
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+            tma_load_1d(tiles_s + stage * kLongStageBytes + b * kLongTileBytes,
+                        r[b].in + (size_t)pkt * r[b].in_stride, kLongTileBytes, bar);
+    };
+    auto issue_stage_cur = [&](uint32_t stage, uint32_t pkt) {                   // lane 0 only
+        const uint32_t bar = bars_s + 8 * stage;
+        mbar_expect_tx(bar, kLongStageBytes);
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+            tma_load_1d(tiles_s + stage * kLongStageBytes + b * kLongTileBytes,
+                        cur[b].in + (size_t)pkt * cur[b].in_stride, kLongTileBytes, bar);
+    };
+
     {
         uint32_t idx = 0;
         if (lane == 0) idx = atomicAdd(ticket, 1u);
         idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx >= n_runs) return;
-        const LongRun r = runs[idx];
-        cur = RunCur{r.in, r.out, r.state, r.in_stride, r.n_packets, r.has_prev, r.write_state};
+        if (idx >= n_groups) return;
+#pragma unroll
+        for (int b = 0; b < NB; b++) cur[b] = run_cur(runs[idx * NB + b]);
+        npk = runs[idx * NB].n_packets;
         if (lane == 0) {
             fence_proxy_async();
-            for (; lc < (uint32_t)kLongRing && lc < cur.npk; lc++) {
-                const uint32_t bar = bars_s + 8 * lc;
-                mbar_expect_tx(bar, kLongTileBytes);
-                tma_load_1d(tiles_s + lc * kLongTileBytes, cur.in + (size_t)lc * cur.in_stride, kLongTileBytes, bar);
-            }
+            for (; lc < (uint32_t)kLongRing && lc < npk; lc++) issue_stage_cur(lc, lc);
         }
     }
 
     for (;;) {
-        V pe[8];
+        V pe[NB][8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) pe[j] = V{0.f, 0.f};
-        float *out = cur.out;
-        for (uint32_t p = 0; p < cur.npk; p++) {
-            const uint32_t tile_s = tiles_s + slot_i * kLongTileBytes;
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) pe[b][j] = V{0.f, 0.f};
+        float *out[NB];
+#pragma unroll
+        for (int b = 0; b < NB; b++) out[b] = cur[b].out;
+
+        for (uint32_t p = 0; p < npk; p++) {
+            const uint32_t stage_s = tiles_s + slot_i * kLongStageBytes;
             mbar_wait(bars_s + 8 * slot_i, (phase_bits >> slot_i) & 1u);
             phase_bits ^= 1u << slot_i;
 
-            V O[8], E[8];
+            V O[NB][8], E[NB][8];
             {
-                Q4 F1[4], F2[4];
-                const float4 *t4 = reinterpret_cast<const float4 *>(tiles + slot_i * kLongN2);
+                const float *tp[NB];
 #pragma unroll
-                for (int m = 0; m < 4; m++) {
-                    const float4 u = t4[lane + 64 * m], v = t4[63 - lane + 64 * m];
-                    F1[m] = Q4{u.x, u.y, u.z, u.w};
-                    F2[m] = Q4{v.x, v.y, v.z, v.w};
-                }
-                phase_a(F1, F2, tw, O, E);
+                for (int b = 0; b < NB; b++) tp[b] = tiles + (slot_i * NB + b) * kLongN2;
+                phase_a<NB>(tp, lane, tw, O, E);
             }
-            __syncwarp();           // every lane has consumed its quads: the tile becomes the scratch
-            // transpose 1 (E plane | O plane)
-            {
-                const uint32_t a0 = tile_s + lA0, a1 = tile_s + lA1, b0 = tile_s + lB;
+            __syncwarp();           // every lane has consumed its quads: the tiles become the scratch
+            // transpose 1 (per block: E plane | O plane in its own tile)
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const uint32_t t = stage_s + b * kLongTileBytes;
+                const uint32_t a0 = t + lA0, a1 = t + lA1;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    sts_eo(a0 ^ LWB_KA(j), E[j].x, O[j].x);
-                    sts_eo(a1 ^ LWB_KA(j), E[j].y, O[j].y);
+                    sts_eo(a0 ^ LWB_KA(j), E[b][j].x, O[b][j].x);
+                    sts_eo(a1 ^ LWB_KA(j), E[b][j].y, O[b][j].y);
                 }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    lds_eo(b0 ^ LWB_KB(j, 0), E[j].x, O[j].x);
-                    lds_eo(b0 ^ LWB_KB(j, 1), E[j].y, O[j].y);
-                }
-                __syncwarp();
-                phase_b(tw, O, E);
-                // transpose 2
-                const uint32_t c0 = tile_s + lC0, c1 = tile_s + lC1;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    sts_eo(b0 ^ LWB_KB(j, 0), E[j].x, O[j].x);
-                    sts_eo(b0 ^ LWB_KB(j, 1), E[j].y, O[j].y);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    lds_eo(c0 ^ LWB_KC(j), E[j].x, O[j].x);
-                    lds_eo(c1 ^ LWB_KC(j), E[j].y, O[j].y);
-                }
-                __syncwarp();
             }
-            // the tile is free again: refill it with the next tile in processing order
+            __syncwarp();
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const uint32_t b0 = stage_s + b * kLongTileBytes + lB;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    lds_eo(b0 ^ LWB_KB(j, 0), E[b][j].x, O[b][j].x);
+                    lds_eo(b0 ^ LWB_KB(j, 1), E[b][j].y, O[b][j].y);
+                }
+            }
+            __syncwarp();
+            phase_b<NB>(tw, O, E);
+            // transpose 2
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const uint32_t b0 = stage_s + b * kLongTileBytes + lB;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    sts_eo(b0 ^ LWB_KB(j, 0), E[b][j].x, O[b][j].x);
+                    sts_eo(b0 ^ LWB_KB(j, 1), E[b][j].y, O[b][j].y);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const uint32_t t = stage_s + b * kLongTileBytes;
+                const uint32_t c0 = t + lC0, c1 = t + lC1;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    lds_eo(c0 ^ LWB_KC(j), E[b][j].x, O[b][j].x);
+                    lds_eo(c1 ^ LWB_KC(j), E[b][j].y, O[b][j].y);
+                }
+            }
+            __syncwarp();
+            // the stage is free again: refill it with the next tiles in processing order
             if (lane == 0) {
-                const float *src = nullptr;
-                if (lc < cur.npk) {
-                    src = cur.in + (size_t)lc * cur.in_stride;
+                if (lc < npk) {
+                    fence_proxy_async();
+                    issue_stage_cur(slot_i, lc);
                     lc++;
                 } else {
                     if (nx_state == 0) {
                         const uint32_t idx = atomicAdd(ticket, 1u);
-                        if (idx < n_runs) {
-                            const LongRun r = runs[idx];
-                            *s_next = r;
+                        if (idx < n_groups) {
+#pragma unroll
+                            for (int b = 0; b < NB; b++) s_next[b] = runs[idx * NB + b];
                             nx_state = 1;
-                            nx_npk = r.n_packets;
+                            nx_npk = s_next[0].n_packets;
                             nx_lc = 0;
                         } else {
                             nx_state = 2;
                         }
                     }
                     if (nx_state == 1 && nx_lc < nx_npk) {
-                        src = s_next->in + (size_t)nx_lc * s_next->in_stride;
+                        fence_proxy_async();
+                        issue_stage(slot_i, s_next, nx_lc);
                         nx_lc++;
                     }
                 }
-                if (src) {
-                    fence_proxy_async();
-                    const uint32_t bar = bars_s + 8 * slot_i;
-                    mbar_expect_tx(bar, kLongTileBytes);
-                    tma_load_1d(tile_s, src, kLongTileBytes, bar);
-                }
             }
-            phase_c_fft(tw, O, E);
-            if (p > 0) {
-                out_stage<false, true>(tw, lane, O, E, pe, cur.state, out);
-                out += kLongN2;
-            } else if (cur.has_prev) {
-                out_stage<true, true>(tw, lane, O, E, pe, cur.state, out);
-                out += kLongN2;
-            } else {
-                out_stage<false, false>(tw, lane, O, E, pe, cur.state, out);
-            }
+            phase_c_fft<NB>(tw, O, E);
+            if (p > 0) out_stage<NB, false>(tw, lane, O, E, pe, cur, out);
+            else out_stage<NB, true>(tw, lane, O, E, pe, cur, out);
+#pragma unroll
+            for (int b = 0; b < NB; b++)
+                if (p > 0 || (cur[b].flags & 1u)) out[b] += kLongN2;
             slot_i = (slot_i + 1 == (uint32_t)kLongRing) ? 0 : slot_i + 1;
         }
-        if (cur.write_state) {
-            float *s_lo = cur.state + lane, *s_hi = cur.state + 63 - lane;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int r64 = 64 * rev3(j);
-                const float vx = (j & 1) ? pe[j].x : pe[j].y, vy = (j & 1) ? pe[j].y : pe[j].x;
-                s_lo[r64] = vx; s_hi[r64] = vy;                 // state[m]
-                s_hi[960 - r64] = vx; s_lo[960 - r64] = vy;     // state[1023 - m]: same value (imdct.rs:622-649)
+        for (int b = 0; b < NB; b++) {
+            if ((cur[b].flags & 6u) == 2u) {       // write_state and not dummy
+                float *s_lo = cur[b].state + lane, *s_hi = cur[b].state + 63 - lane;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int r64 = 64 * rev3(j);
+                    const float vx = (j & 1) ? pe[b][j].x : pe[b][j].y, vy = (j & 1) ? pe[b][j].y : pe[b][j].x;
+                    s_lo[r64] = vx; s_hi[r64] = vy;                 // state[m]
+                    s_hi[960 - r64] = vx; s_lo[960 - r64] = vy;     // state[1023 - m]: same value (imdct.rs:622-649)
+                }
             }
         }
-        // hand over to the run lane 0 has (maybe) already started loading
+        // hand over to the group lane 0 has (maybe) already started loading
         uint32_t st = nx_state, nlc = nx_lc;
-        if (lane == 0 && st == 0) {                // the current run was shorter than the ring: draw now
+        if (lane == 0 && st == 0) {                // the current group was shorter than the ring: draw now
             const uint32_t idx = atomicAdd(ticket, 1u);
-            if (idx < n_runs) { *s_next = runs[idx]; st = 1; nlc = 0; }
-            else st = 2;
+            if (idx < n_groups) {
+#pragma unroll
+                for (int b = 0; b < NB; b++) s_next[b] = runs[idx * NB + b];
+                st = 1;
+                nlc = 0;
+            } else {
+                st = 2;
+            }
         }
         st = __shfl_sync(0xffffffffu, st, 0);
         nlc = __shfl_sync(0xffffffffu, nlc, 0);
         if (st != 1) break;
         __syncwarp();
-        {
-            const LongRun r = *s_next;
-            cur = RunCur{r.in, r.out, r.state, r.in_stride, r.n_packets, r.has_prev, r.write_state};
-        }
+#pragma unroll
+        for (int b = 0; b < NB; b++) cur[b] = run_cur(s_next[b]);
+        npk = s_next[0].n_packets;
         __syncwarp();                              // s_next may be overwritten from here on
         lc = nlc;
         nx_state = 0; nx_lc = 0; nx_npk = 0;
-        // ring slots ahead of slot_i that hold nothing yet (new run longer than what was prefetched,
-        // previous run shorter than the ring): top the ring up
+        // top the ring up (new group longer than what was prefetched so far)
         if (lane == 0) {
-            // slots in flight for the new run: lc tiles starting at slot_i; fill up to the ring depth
             fence_proxy_async();
-            for (uint32_t k = lc; k < (uint32_t)kLongRing && k < cur.npk; k++) {
-                const uint32_t s = (slot_i + k) % kLongRing;
-                const uint32_t bar = bars_s + 8 * s;
-                mbar_expect_tx(bar, kLongTileBytes);
-                tma_load_1d(tiles_s + s * kLongTileBytes, cur.in + (size_t)k * cur.in_stride, kLongTileBytes, bar);
+            for (uint32_t k = lc; k < (uint32_t)kLongRing && k < npk; k++) {
+                issue_stage_cur((slot_i + k) % kLongRing, k);
                 lc = k + 1;
             }
         }
@@ -749,14 +873,14 @@ inline void long_kernel_configure()
     cudaFuncSetAttribute(k_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes);
 }
 
-// returns 0 on success; `ticket` is a device word this call zeroes on the stream
-inline int long_launch(cudaStream_t stream, const LongRun *d_runs, uint32_t n_runs, const float *d_pack,
+// d_runs: n_groups * kLongNB descriptors.  Returns 0 on success; `ticket` must point at a zeroed
+// device word no other launch in flight uses.
+inline int long_launch(cudaStream_t stream, const LongRun *d_runs, uint32_t n_groups, const float *d_pack,
                        unsigned int *ticket, int sm_count)
 {
-    if (cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream) != cudaSuccess) return 1;
-    const uint32_t want = (n_runs + kLongWarps - 1) / kLongWarps;
+    const uint32_t want = (n_groups + kLongWarps - 1) / kLongWarps;
     const uint32_t grid = want < (uint32_t)sm_count ? want : (uint32_t)sm_count;
-    k_long<<<grid, kLongWarps * 32, kLongSmemBytes, stream>>>(d_runs, n_runs, d_pack, ticket);
+    k_long<<<grid, kLongWarps * 32, kLongSmemBytes, stream>>>(d_runs, n_groups, d_pack, ticket);
     return cudaGetLastError() != cudaSuccess;
 }
 #endif  // __CUDACC__

@@ -39,6 +39,12 @@ struct lwb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_in[16] = {}, ev_done[16] = {};
+    // fused path: descriptor arrays are double buffered and uploaded on the copy stream so that the
+    // upload of step k+1 overlaps kernel k; tickets come from a pool zeroed once per wrap
+    DevBuf runs_buf[2];
+    cudaEvent_t ev_desc[2] = {}, ev_kdone[2] = {};
+    int runs_par = 0;
+    uint32_t ticket_next = 0;
     std::string err;
     uint64_t launches = 0;
     // grow-only device arenas
@@ -167,7 +173,7 @@ extern "C" void lwb_ctx_destroy(lwb_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->coeffs, &ctx->dense, &ctx->pcm, &ctx->spec, &ctx->x, &ctx->desc,
-                      &ctx->kinds, &ctx->ys, &ctx->chains, &ctx->ticket})
+                      &ctx->kinds, &ctx->ys, &ctx->chains, &ctx->ticket, &ctx->runs_buf[0], &ctx->runs_buf[1]})
         if (b->p) cudaFree(b->p);
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
     cudaStreamDestroy(ctx->stream);
@@ -729,7 +735,7 @@ static int acquire_staging(lwb_ctx *ctx, size_t bytes, Staging **out)
 // packet before its first one as a primer (its right half is all the run needs), which keeps
 // runs independent at the cost of one extra IMDCT per cut.
 static void long_runs_of(const LongItem &it, size_t cuts, const float *coeffs, uint64_t coeff_base, float *pcm,
-                         uint64_t pcm_base, LongRun *&w)
+                         uint64_t pcm_base, std::vector<LongRun> &w)
 {
     const lwb_stream *s = it.c->stream;
     const lwb_setup *su = s->setup;
@@ -740,7 +746,8 @@ static void long_runs_of(const LongItem &it, size_t cuts, const float *coeffs, u
         float *out0 = pcm + (it.c->out_offset - pcm_base) + (size_t)ch * it.c->out_stride;
         for (size_t k = 0; k < cuts; k++) {
             const size_t p0 = P * k / cuts, p1 = P * (k + 1) / cuts;   // this run emits packets [p0, p1)
-            LongRun &r = *w++;
+            w.emplace_back();
+            LongRun &r = w.back();
             std::memset(&r, 0, sizeof(r));
             r.in_stride = (uint32_t)(C * kLongN2);
             r.state = s->d_state + (size_t)ch * state_stride(su);
@@ -810,12 +817,19 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
         o_hi = std::max(o_hi, c->out_offset + (uint64_t)(C - 1) * c->out_stride + c->n_samples);
     }
     if (!chan_chains) return LWB_OK;
-    const size_t warp_slots = (size_t)ctx->sm_count * kLongWarps;
-    size_t target_runs = warp_slots * 4;                   // ~4 runs per warp evens out the tail
+    const size_t warp_slots = (size_t)ctx->sm_count * kLongWarps * kLongNB;
+    size_t target_runs = warp_slots * 4;                   // ~4 groups per warp evens out the tail
     if (const char *e = getenv("LWB_LONG_TARGET_RUNS")) target_runs = (size_t)atol(e);
     const size_t min_run = 8;                              // packets per run below which a cut costs > 12%
     int rc;
-    if (!ctx->ticket.p && (rc = ensure(ctx, ctx->ticket, 256))) return rc;
+    constexpr uint32_t kTicketPool = 1024;
+    if (!ctx->ticket.p) {
+        if ((rc = ensure(ctx, ctx->ticket, kTicketPool * sizeof(unsigned int)))) return rc;
+        for (int k = 0; k < 2; k++) {
+            CU(ctx, cudaEventCreateWithFlags(&ctx->ev_desc[k], cudaEventDisableTiming));
+            CU(ctx, cudaEventCreateWithFlags(&ctx->ev_kdone[k], cudaEventDisableTiming));
+        }
+    }
 
     const bool host = io->memory == LWB_MEM_HOST;
     // host memory: chunks of chains, H2D / kernel / D2H of consecutive chunks overlap on three streams
@@ -857,17 +871,27 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
         cuts[i] = std::max<size_t>(1, std::min(k, items[i].P / min_run));
         total_runs += cuts[i] * items[i].c->stream->setup->channels;
     }
+    // the kernel takes groups of kLongNB runs of equal length; unpaired runs get a dummy partner
+    const size_t cap_runs = total_runs * (kLongNB > 1 ? 2 : 1) + kLongNB;
     Staging *st;
-    if ((rc = acquire_staging(ctx, total_runs * sizeof(LongRun), &st))) return rc;
-    if ((rc = ensure(ctx, ctx->chains, total_runs * sizeof(LongRun)))) return rc;
+    if ((rc = acquire_staging(ctx, cap_runs * sizeof(LongRun), &st))) return rc;
+    const int par = ctx->runs_par;
+    ctx->runs_par ^= 1;
+    if ((rc = ensure(ctx, ctx->runs_buf[par], cap_runs * sizeof(LongRun)))) return rc;
+    LongRun *const d_runs_base = (LongRun *)ctx->runs_buf[par].p;
     LongRun *h_runs = (LongRun *)st->h, *w = h_runs;
+    std::vector<LongRun> tmp;
+    struct ChunkPlan { size_t r0, nr; uint64_t kc_lo, kc_hi, ko_lo, ko_hi; };
+    std::vector<ChunkPlan> cplan;
+    std::vector<uint32_t> order;
     for (size_t k = 0; k < n_chunks; k++) {
         const size_t i0 = items.size() * k / n_chunks, i1 = items.size() * (k + 1) / n_chunks;
         LongRun *w0 = w;
         uint64_t kc_lo = ~0ull, kc_hi = 0, ko_lo = ~0ull, ko_hi = 0;
+        tmp.clear();
         for (size_t i = i0; i < i1; i++) {
             if (!items[i].P) continue;
-            long_runs_of(items[i], cuts[i], d_coeffs, cbase, d_pcm, obase, w);
+            long_runs_of(items[i], cuts[i], d_coeffs, cbase, d_pcm, obase, tmp);
             const lwb_chain *c = items[i].c;
             const unsigned C = c->stream->setup->channels;
             kc_lo = std::min(kc_lo, c->coeff_offset);
@@ -875,28 +899,69 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
             ko_lo = std::min(ko_lo, c->out_offset);
             ko_hi = std::max(ko_hi, c->out_offset + (uint64_t)(C - 1) * c->out_stride + c->n_samples);
         }
-        const size_t nr = (size_t)(w - w0);
-        if (!nr) continue;
+        if (tmp.empty()) continue;
+        if (kLongNB == 1) {
+            std::memcpy(w, tmp.data(), tmp.size() * sizeof(LongRun));
+            w += tmp.size();
+        } else {
+            // group runs of equal packet count (consecutive channels of a stream already are)
+            bool sorted = true;
+            for (size_t i = 1; i < tmp.size() && sorted; i++) sorted = tmp[i].n_packets == tmp[0].n_packets;
+            order.resize(tmp.size());
+            for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+            if (!sorted)
+                std::stable_sort(order.begin(), order.end(),
+                                 [&](uint32_t a, uint32_t b) { return tmp[a].n_packets < tmp[b].n_packets; });
+            size_t i = 0;
+            while (i < order.size()) {
+                size_t j = i;
+                while (j < order.size() && tmp[order[j]].n_packets == tmp[order[i]].n_packets) j++;
+                for (size_t q = i; q < j; q++) *w++ = tmp[order[q]];
+                size_t fill = (kLongNB - (j - i) % kLongNB) % kLongNB;
+                while (fill--) {
+                    LongRun d = tmp[order[j - 1]];       // reads valid memory, stores nothing
+                    d.dummy = 1;
+                    d.write_state = 0;
+                    d.has_prev = 0;
+                    *w++ = d;
+                }
+                i = j;
+            }
+        }
+        cplan.push_back(ChunkPlan{(size_t)(w0 - h_runs), (size_t)(w - w0), kc_lo, kc_hi, ko_lo, ko_hi});
+    }
+    // one descriptor upload for the whole call, on the copy stream, behind the kernel that last read
+    // this half of the double buffer
+    const size_t all_runs = (size_t)(w - h_runs);
+    if (!all_runs) return LWB_OK;
+    CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_kdone[par], 0));
+    CU(ctx, cudaMemcpyAsync(d_runs_base, h_runs, all_runs * sizeof(LongRun), cudaMemcpyHostToDevice, ctx->copy_out));
+    CU(ctx, cudaEventRecord(ctx->ev_desc[par], ctx->copy_out));
+    CU(ctx, cudaEventRecord(st->ev, ctx->copy_out));
+    st->pending = true;
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_desc[par], 0));
+    for (size_t k = 0; k < cplan.size(); k++) {
+        const ChunkPlan &cp = cplan[k];
         if (host) {
-            CU(ctx, cudaMemcpyAsync((float *)ctx->coeffs.p + (kc_lo - cbase), io->coeffs + kc_lo, (size_t)(kc_hi - kc_lo) * 4,
-                                    cudaMemcpyHostToDevice, ctx->copy_in));
+            CU(ctx, cudaMemcpyAsync((float *)ctx->coeffs.p + (cp.kc_lo - cbase), io->coeffs + cp.kc_lo,
+                                    (size_t)(cp.kc_hi - cp.kc_lo) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
             CU(ctx, cudaEventRecord(ctx->ev_in[k], ctx->copy_in));
             CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[k], 0));
         }
-        LongRun *d_runs = (LongRun *)ctx->chains.p + (w0 - h_runs);
-        CU(ctx, cudaMemcpyAsync(d_runs, w0, nr * sizeof(LongRun), cudaMemcpyHostToDevice, ctx->stream));
-        if (long_launch(ctx->stream, d_runs, (uint32_t)nr, pack, (unsigned int *)ctx->ticket.p, ctx->sm_count))
+        if (ctx->ticket_next % kTicketPool == 0)
+            CU(ctx, cudaMemsetAsync(ctx->ticket.p, 0, kTicketPool * sizeof(unsigned int), ctx->stream));
+        unsigned int *ticket = (unsigned int *)ctx->ticket.p + (ctx->ticket_next++ % kTicketPool);
+        if (long_launch(ctx->stream, d_runs_base + cp.r0, (uint32_t)(cp.nr / kLongNB), pack, ticket, ctx->sm_count))
             return fail(ctx, LWB_ERR_CUDA, "long kernel launch", cudaGetLastError());
         ctx->launches++;
-        if (host && ko_hi > ko_lo) {
+        if (host && cp.ko_hi > cp.ko_lo) {
             CU(ctx, cudaEventRecord(ctx->ev_done[k], ctx->stream));
             CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[k], 0));
-            CU(ctx, cudaMemcpyAsync((float *)io->pcm + ko_lo, (float *)ctx->pcm.p + (ko_lo - obase), (size_t)(ko_hi - ko_lo) * 4,
-                                    cudaMemcpyDeviceToHost, ctx->copy_out));
+            CU(ctx, cudaMemcpyAsync((float *)io->pcm + cp.ko_lo, (float *)ctx->pcm.p + (cp.ko_lo - obase),
+                                    (size_t)(cp.ko_hi - cp.ko_lo) * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
         }
     }
-    CU(ctx, cudaEventRecord(st->ev, ctx->stream));
-    st->pending = true;
+    CU(ctx, cudaEventRecord(ctx->ev_kdone[par], ctx->stream));
     if (host) {
         CU(ctx, cudaStreamSynchronize(ctx->copy_out));
         CU(ctx, cudaStreamSynchronize(ctx->stream));

@@ -39,95 +39,120 @@ extern "C" void lwb_emu_build_pack(const float *a, const float *b, const float *
     long_build_pack(a, b, c, w, pack);
 }
 
-// spectrum: [n_packets][1024]; state: 1024 floats (read if has_prev, written at the end);
-// out: [emitted][1024].  Returns the worst bank-conflict degree seen (1 = conflict-free).
-extern "C" int lwb_emu_long_run(const float *pack_f, const float *spectrum, int n_packets, int has_prev,
-                                float *state, float *out)
+// One run (NB = 1) or two runs in lockstep (NB = 2, both of n_packets packets), exactly like a
+// warp of k_long.  spectrum: [NB][n_packets][1024]; state: [NB][1024] (read if has_prev[b], written
+// at the end); out: [NB][n_packets][1024] (emitted packets packed from the front).  Returns the
+// worst bank-conflict degree seen (1 = conflict-free).
+template <int NB>
+static int emu_run(const float *pack_f, const float *spectrum, int n_packets, const int *has_prev, float *state,
+                   float *out_all)
 {
     const V *pack = reinterpret_cast<const V *>(pack_f);
     g_max_conflict = 0;
-    std::vector<float> tile(1024);
-    V O[32][8], E[32][8], pe[32][8];
+    std::vector<float> tiles((size_t)NB * 1024);
+    static V O[32][NB][8], E[32][NB][8], pe[32][NB][8];
     std::memset(pe, 0, sizeof(pe));
+    float *out[NB];
+    for (int b = 0; b < NB; b++) out[b] = out_all + (size_t)b * n_packets * 1024;
     for (int p = 0; p < n_packets; p++) {
-        std::memcpy(tile.data(), spectrum + (size_t)p * 1024, 4096);
-        for (int lane = 0; lane < 32; lane++) {
-            Q4 F1[4], F2[4];
-            for (int m = 0; m < 4; m++) {
-                const float *u = &tile[4 * (lane + 64 * m)], *v = &tile[4 * (63 - lane + 64 * m)];
-                F1[m] = Q4{u[0], u[1], u[2], u[3]};
-                F2[m] = Q4{v[0], v[1], v[2], v[3]};
-            }
-            phase_a(F1, F2, TwHost{pack, lane}, O[lane], E[lane]);
+        const float *tp[NB];
+        for (int b = 0; b < NB; b++) {
+            std::memcpy(&tiles[(size_t)b * 1024], spectrum + ((size_t)b * n_packets + p) * 1024, 4096);
+            tp[b] = &tiles[(size_t)b * 1024];
         }
-        float *pe_plane = tile.data(), *po_plane = tile.data() + 512;
+        for (int lane = 0; lane < 32; lane++) phase_a<NB>(tp, lane, TwHost{pack, lane}, O[lane], E[lane]);
         int idx[32];
-        for (int j = 0; j < 8; j++)
-            for (int h = 0; h < 2; h++) {
-                for (int lane = 0; lane < 32; lane++) {
-                    const int i = swz(elemA(lane, j, h));
-                    idx[lane] = i;
-                    pe_plane[i] = h ? E[lane][j].y : E[lane][j].x;
-                    po_plane[i] = h ? O[lane][j].y : O[lane][j].x;
+        for (int b = 0; b < NB; b++) {
+            float *pe_plane = &tiles[(size_t)b * 1024], *po_plane = pe_plane + 512;
+            for (int j = 0; j < 8; j++)
+                for (int h = 0; h < 2; h++) {
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int i = swz(elemA(lane, j, h));
+                        idx[lane] = i;
+                        pe_plane[i] = h ? E[lane][b][j].y : E[lane][b][j].x;
+                        po_plane[i] = h ? O[lane][b][j].y : O[lane][b][j].x;
+                    }
+                    note_banks(idx);
                 }
-                note_banks(idx);
-            }
-        for (int j = 0; j < 8; j++)
-            for (int h = 0; h < 2; h++) {
-                for (int lane = 0; lane < 32; lane++) {
-                    const int i = swz(elemB(lane, j, h));
-                    idx[lane] = i;
-                    (h ? E[lane][j].y : E[lane][j].x) = pe_plane[i];
-                    (h ? O[lane][j].y : O[lane][j].x) = po_plane[i];
+            for (int j = 0; j < 8; j++)
+                for (int h = 0; h < 2; h++) {
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int i = swz(elemB(lane, j, h));
+                        idx[lane] = i;
+                        (h ? E[lane][b][j].y : E[lane][b][j].x) = pe_plane[i];
+                        (h ? O[lane][b][j].y : O[lane][b][j].x) = po_plane[i];
+                    }
+                    note_banks(idx);
                 }
-                note_banks(idx);
-            }
-        for (int lane = 0; lane < 32; lane++) phase_b(TwHost{pack, lane}, O[lane], E[lane]);
-        for (int j = 0; j < 8; j++)
-            for (int h = 0; h < 2; h++)
-                for (int lane = 0; lane < 32; lane++) {
-                    const int i = swz(elemB(lane, j, h));
-                    pe_plane[i] = h ? E[lane][j].y : E[lane][j].x;
-                    po_plane[i] = h ? O[lane][j].y : O[lane][j].x;
+        }
+        for (int lane = 0; lane < 32; lane++) phase_b<NB>(TwHost{pack, lane}, O[lane], E[lane]);
+        for (int b = 0; b < NB; b++) {
+            float *pe_plane = &tiles[(size_t)b * 1024], *po_plane = pe_plane + 512;
+            for (int j = 0; j < 8; j++)
+                for (int h = 0; h < 2; h++)
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int i = swz(elemB(lane, j, h));
+                        pe_plane[i] = h ? E[lane][b][j].y : E[lane][b][j].x;
+                        po_plane[i] = h ? O[lane][b][j].y : O[lane][b][j].x;
+                    }
+            for (int j = 0; j < 8; j++)
+                for (int h = 0; h < 2; h++) {
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int i = swz(elemC(lane, j, h));
+                        idx[lane] = i;
+                        (h ? E[lane][b][j].y : E[lane][b][j].x) = pe_plane[i];
+                        (h ? O[lane][b][j].y : O[lane][b][j].x) = po_plane[i];
+                    }
+                    note_banks(idx);
                 }
-        for (int j = 0; j < 8; j++)
-            for (int h = 0; h < 2; h++) {
-                for (int lane = 0; lane < 32; lane++) {
-                    const int i = swz(elemC(lane, j, h));
-                    idx[lane] = i;
-                    (h ? E[lane][j].y : E[lane][j].x) = pe_plane[i];
-                    (h ? O[lane][j].y : O[lane][j].x) = po_plane[i];
-                }
-                note_banks(idx);
-            }
-        const bool emit = p > 0 || has_prev;
-        const bool from_state = p == 0 && has_prev;
+        }
         for (int lane = 0; lane < 32; lane++) {
             const TwHost tw{pack, lane};
-            phase_c_fft(tw, O[lane], E[lane]);
+            phase_c_fft<NB>(tw, O[lane], E[lane]);
             for (int j = 0; j < 8; j++) {
                 const int mx = outIndex(lane, j, 0), my = outIndex(lane, j, 1);
-                V plo = pe[lane][j], phi = pe[lane][j];
-                if (from_state) {
-                    plo = V{state[mx], state[my]};
-                    phi = V{state[1023 - mx], state[1023 - my]};
-                }
-                V lo, hi, pev;
-                phase_c_out(tw, j, O[lane][j], E[lane][j], plo, phi, lo, hi, pev);
-                pe[lane][j] = pev;
-                if (emit) {
-                    out[mx] = lo.x; out[my] = lo.y;
-                    out[1023 - mx] = hi.x; out[1023 - my] = hi.y;
+                const V b0 = tw(P_B0 + j), b1 = tw(P_B1 + j), wlo = tw(P_WLO + j), whi = tw(P_WHI + j);
+                for (int b = 0; b < NB; b++) {
+                    const bool emit = p > 0 || has_prev[b];
+                    const bool from_state = p == 0 && has_prev[b];
+                    const float *st = state + (size_t)b * 1024;
+                    V plo = pe[lane][b][j], phi = pe[lane][b][j];
+                    if (from_state) {
+                        plo = V{st[mx], st[my]};
+                        phi = V{st[1023 - mx], st[1023 - my]};
+                    }
+                    V lo, hi, pev;
+                    step8_ola(b0, b1, wlo, whi, O[lane][b][j], E[lane][b][j], plo, phi, lo, hi, pev);
+                    pe[lane][b][j] = pev;
+                    if (emit) {
+                        out[b][mx] = lo.x; out[b][my] = lo.y;
+                        out[b][1023 - mx] = hi.x; out[b][1023 - my] = hi.y;
+                    }
                 }
             }
         }
-        if (emit) out += 1024;
+        for (int b = 0; b < NB; b++)
+            if (p > 0 || has_prev[b]) out[b] += 1024;
     }
-    for (int lane = 0; lane < 32; lane++)
-        for (int j = 0; j < 8; j++) {
-            const int mx = outIndex(lane, j, 0), my = outIndex(lane, j, 1);
-            state[mx] = pe[lane][j].x; state[my] = pe[lane][j].y;
-            state[1023 - mx] = pe[lane][j].x; state[1023 - my] = pe[lane][j].y;
-        }
+    for (int b = 0; b < NB; b++)
+        for (int lane = 0; lane < 32; lane++)
+            for (int j = 0; j < 8; j++) {
+                const int mx = outIndex(lane, j, 0), my = outIndex(lane, j, 1);
+                float *st = state + (size_t)b * 1024;
+                st[mx] = pe[lane][b][j].x; st[my] = pe[lane][b][j].y;
+                st[1023 - mx] = pe[lane][b][j].x; st[1023 - my] = pe[lane][b][j].y;
+            }
     return g_max_conflict;
+}
+
+extern "C" int lwb_emu_long_run(const float *pack_f, const float *spectrum, int n_packets, int has_prev,
+                                float *state, float *out)
+{
+    return emu_run<1>(pack_f, spectrum, n_packets, &has_prev, state, out);
+}
+
+extern "C" int lwb_emu_long_run2(const float *pack_f, const float *spectrum, int n_packets, const int *has_prev,
+                                 float *state, float *out)
+{
+    return emu_run<2>(pack_f, spectrum, n_packets, has_prev, state, out);
 }

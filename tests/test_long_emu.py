@@ -28,6 +28,7 @@ def emu():
     vp = C.c_void_p
     L.lwb_emu_build_pack.argtypes = [vp] * 5
     L.lwb_emu_long_run.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+    L.lwb_emu_long_run2.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     return L
 
 
@@ -87,3 +88,22 @@ def test_emulated_kernel_special_values(emu, pack, oracle):
     got = out[:2].ravel()
     same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
     assert np.all(same)
+
+
+@pytest.mark.parametrize("seed,npk,prev", [(20, 4, (0, 0)), (21, 3, (1, 0)), (22, 1, (0, 1)), (23, 5, (1, 1))])
+def test_emulated_dual_block_matches_oracle(emu, pack, oracle, seed, npk, prev):
+    """NB = 2: a warp transforms two runs in lockstep (the shipped configuration)."""
+    rng = np.random.default_rng(seed)
+    spec = rng.standard_normal((2, npk, 1024)).astype(np.float32)
+    states = rng.standard_normal((2, 1024)).astype(np.float32)
+    st = states.copy()
+    out = np.zeros((2, npk, 1024), np.float32)
+    hp = np.array(prev, np.int32)
+    conflicts = emu.lwb_emu_long_run2(P(pack), P(spec), npk, P(hp), P(st), P(out))
+    assert conflicts == 1
+    for b in range(2):
+        want, want_state = oracle_run(oracle, spec[b], states[b] if prev[b] else None)
+        emitted = npk if prev[b] else npk - 1
+        got = out[b, :emitted].ravel()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), b
+        assert np.array_equal(st[b].view(np.uint32), want_state.view(np.uint32)), b
