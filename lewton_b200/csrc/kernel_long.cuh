@@ -46,7 +46,7 @@ constexpr int kLongN = 2048;
 constexpr int kLongN2 = 1024;
 
 // one run = consecutive packets of one channel of one stream
-struct LongRun {
+struct alignas(16) LongRun {      // 48 bytes: fetched by the kernel with one 1-D TMA copy
     const float *in;        // first packet's spectrum (1024 floats); next packet at +in_stride
     float *out;             // first emitted packet's PCM; next at +1024
     float *state;           // stream state row of this channel (1024 floats)
@@ -55,8 +55,9 @@ struct LongRun {
     uint8_t has_prev;       // 1: packet 0 overlaps with `state`;  0: packet 0 emits nothing
     uint8_t write_state;    // 1: store the last packet's right half to `state`
     uint8_t dummy;          // 1: filler partner of an unpaired run: transformed, never stored
-    uint8_t pad[1];
+    uint8_t pad[13];
 };
+static_assert(sizeof(LongRun) == 48, "LongRun is copied by TMA in 16-byte units");
 
 struct V { float x, y; };    // (group a, group b)
 
@@ -489,9 +490,9 @@ constexpr int kLongWarps = LWB_LONG_WARPS;     // warps per CTA, one CTA per SM
 constexpr int kLongRing = LWB_LONG_RING;       // ring stages per warp, each holding kLongNB tiles
 constexpr int kLongTileBytes = kLongN2 * 4;
 constexpr int kLongStageBytes = kLongNB * kLongTileBytes;
-// [tiles: warps x ring x NB x 4 KB, 2 KB-aligned at run time][pack][mbarriers][next-run descriptors]
-constexpr size_t kLongSmemBytes = 2048 + (size_t)kLongWarps * kLongRing * kLongStageBytes +
-                                  (size_t)kLongPackFloats * 4 + kLongWarps * kLongRing * 8 +
+// [tiles: warps x ring x NB x 4 KB, 2 KB-aligned at run time][state tiles][pack][next-run descriptors][mbarriers]
+constexpr size_t kLongSmemBytes = 2048 + (size_t)kLongWarps * (kLongRing + 1) * kLongStageBytes +
+                                  (size_t)kLongPackFloats * 4 + kLongWarps * (kLongRing + 2) * 8 +
                                   kLongWarps * kLongNB * sizeof(LongRun) + 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -583,12 +584,13 @@ __device__ __forceinline__ RunCur run_cur(const LongRun &r)
                   (uint32_t)(r.has_prev ? 1u : 0u) | (r.write_state ? 2u : 0u) | (r.dummy ? 4u : 0u)};
 }
 
-// Step 8 + window + overlap-add + stores, all 8 slots of all NB blocks.  `first`: packet 0 of the
-// run (its previous right half comes from the stream state in HBM if has_prev, else nothing is
-// emitted).  Streaming stores: PCM is written once and never read back by this kernel.
+// Step 8 + window + overlap-add + stores, all 8 slots of all NB blocks.  FIRST: packet 0 of the
+// run -- its previous right half comes from the stream state (staged in shared memory by TMA
+// while the run's first tile was in flight) if has_prev, else nothing is emitted.  Streaming
+// stores: PCM is written once and never read back by this kernel.
 template <int NB, bool FIRST>
 __device__ __forceinline__ void out_stage(const TwMix &tw, int lane, const V O[NB][8], const V E[NB][8], V pe[NB][8],
-                                          const RunCur cur[NB], float *out[NB])
+                                          const RunCur cur[NB], float *out[NB], const float *s_state)
 {
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -604,7 +606,7 @@ __device__ __forceinline__ void out_stage(const TwMix &tw, int lane, const V O[N
                 emit = emit && (cur[b].flags & 1u);
                 if (cur[b].flags & 1u) {
                     // prev[m] and prev[1023 - m] read separately: an imported state need not be symmetric
-                    const float *s_lo = cur[b].state + lane, *s_hi = cur[b].state + 63 - lane;
+                    const float *s_lo = s_state + b * kLongN2 + lane, *s_hi = s_state + b * kLongN2 + 63 - lane;
                     const float ax = nat ? s_lo[r64] : s_hi[r64], ay = nat ? s_hi[r64] : s_lo[r64];
                     const float bx = nat ? s_hi[960 - r64] : s_lo[960 - r64];
                     const float by = nat ? s_lo[960 - r64] : s_hi[960 - r64];
@@ -633,6 +635,13 @@ __device__ __forceinline__ void out_stage(const TwMix &tw, int lane, const V O[N
 // runs: groups of kLongNB consecutive entries with equal n_packets (the host pads with dummy
 // runs); pack: the twiddle pack of the setup's blocksize-11 tables (long_build_pack); ticket: a
 // zeroed counter from which warps draw group indices.
+//
+// Latency plan per warp (lane 0 drives all asynchronous traffic; nothing below stalls the math):
+//   * spectrum tiles: 1-D TMA into a ring, issued in processing order ACROSS run boundaries;
+//   * the ticket for the next group is drawn (atomicAdd) when a group starts and first looked at
+//     a packet later; its descriptors then arrive by TMA into shared memory;
+//   * the stream state a run overlaps with (has_prev) arrives by TMA into a per-warp state tile
+//     while the run's first spectrum tile is in flight.
 __global__ void __launch_bounds__(kLongWarps * 32, 1)
 k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restrict__ pack,
        unsigned int *__restrict__ ticket)
@@ -645,11 +654,14 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
     const uint32_t align_pad = (2048u - (raw_s & 2047u)) & 2047u;
     unsigned char *base = smem_raw + align_pad;
     constexpr size_t kTilesBytes = (size_t)kLongWarps * kLongRing * kLongStageBytes;
+    constexpr size_t kStateBytes = (size_t)kLongWarps * kLongStageBytes;
     float *tiles = reinterpret_cast<float *>(base) + (size_t)warp * kLongRing * NB * kLongN2;
-    V *s_pack = reinterpret_cast<V *>(base + kTilesBytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(base + kTilesBytes + (size_t)kLongPackFloats * 4) + warp * kLongRing;
-    LongRun *s_next = reinterpret_cast<LongRun *>(base + kTilesBytes + (size_t)kLongPackFloats * 4 +
-                                                  (size_t)kLongWarps * kLongRing * 8) + warp * NB;
+    float *s_state = reinterpret_cast<float *>(base + kTilesBytes) + (size_t)warp * NB * kLongN2;
+    V *s_pack = reinterpret_cast<V *>(base + kTilesBytes + kStateBytes);
+    unsigned char *tail = base + kTilesBytes + kStateBytes + (size_t)kLongPackFloats * 4;
+    LongRun *s_next = reinterpret_cast<LongRun *>(tail) + warp * NB;                       // 16-aligned
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tail + (size_t)kLongWarps * NB * sizeof(LongRun)) +
+                     warp * (kLongRing + 2);
     if (n_groups == 0) return;
 
     // stage the pack once per CTA
@@ -659,7 +671,7 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
         for (int i = threadIdx.x; i < kLongPackFloats / 4; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     if (lane == 0) {
-        for (int i = 0; i < kLongRing; i++) mbar_init(smem_u32(&bars[i]), 1);
+        for (int i = 0; i < kLongRing + 2; i++) mbar_init(smem_u32(&bars[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -671,20 +683,21 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
 
     const uint32_t tiles_s = smem_u32(tiles);
     const uint32_t bars_s = smem_u32(bars);
+    const uint32_t bar_state = bars_s + 8 * kLongRing, bar_desc = bars_s + 8 * (kLongRing + 1);
+    const uint32_t state_s = smem_u32(s_state), next_s = smem_u32(s_next);
     const uint32_t lA0 = laneA(lane, 0), lA1 = laneA(lane, 1);
     const uint32_t lB = laneB(lane);
     const uint32_t lC0 = laneC(lane, 0), lC1 = laneC(lane, 1);
-    uint32_t phase_bits = 0;                  // parity of each ring stage's mbarrier
+    uint32_t phase_bits = 0;                  // bit i: parity of ring stage i; bits 30/31: state / descriptor barrier
     uint32_t slot_i = 0;                      // ring stage of the packets being processed
 
-    // ---- group hand-over (only lane 0's copy of the load cursor matters) -------------------------
-    // Loads are issued in processing order across group boundaries: once all tiles of the current
-    // group are in flight, lane 0 draws the next ticket, stages those runs' descriptors in shared
-    // memory and starts loading THEIR first tiles into the ring stages as they free up, so a warp
-    // never idles through ticket + descriptor + first-tile latency between runs.
+    // lane 0's cursor over the asynchronous traffic
     uint32_t lc = 0;                          // stages of the current group issued so far
-    uint32_t nx_state = 0;                    // 0 unknown, 1 valid (descriptors in s_next), 2 none
+    uint32_t nx_idx = 0;                      // ticket drawn for the next group (value used a packet later)
+    uint32_t nx_stage = 0;                    // 0 ticket drawn, 1 descriptor in flight, 2 descriptor landed, 3 none
     uint32_t nx_lc = 0, nx_npk = 0;
+    uint32_t nx_state_issued = 0;             // next group's state tile already requested
+    uint32_t desc_parity = 0;
     RunCur cur[NB];
     uint32_t npk;
 
@@ -704,6 +717,17 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
             tma_load_1d(tiles_s + stage * kLongStageBytes + b * kLongTileBytes,
                         cur[b].in + (size_t)pkt * cur[b].in_stride, kLongTileBytes, bar);
     };
+    // request the state rows of a group (lane 0 only).  Every group arms the barrier exactly once
+    // (with 0 bytes if none of its runs has history) so that the parity bookkeeping stays uniform.
+    auto issue_state = [&](const float *const st[NB], const uint32_t has[NB]) {
+        uint32_t bytes = 0;
+#pragma unroll
+        for (int b = 0; b < NB; b++) bytes += has[b] ? kLongTileBytes : 0;
+        mbar_expect_tx(bar_state, bytes);
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+            if (has[b]) tma_load_1d(state_s + b * kLongTileBytes, st[b], kLongTileBytes, bar_state);
+    };
 
     {
         uint32_t idx = 0;
@@ -715,7 +739,13 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
         npk = runs[idx * NB].n_packets;
         if (lane == 0) {
             fence_proxy_async();
+            const float *st[NB];
+            uint32_t has[NB];
+#pragma unroll
+            for (int b = 0; b < NB; b++) { st[b] = cur[b].state; has[b] = cur[b].flags & 1u; }
+            issue_state(st, has);
             for (; lc < (uint32_t)kLongRing && lc < npk; lc++) issue_stage_cur(lc, lc);
+            nx_idx = atomicAdd(ticket, 1u);            // not looked at before the next packet
         }
     }
 
@@ -789,24 +819,29 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
             __syncwarp();
             // the stage is free again: refill it with the next tiles in processing order
             if (lane == 0) {
+                if (nx_stage == 0 && p >= 1) {          // the ticket drawn a packet ago has long arrived
+                    if (nx_idx < n_groups) {
+                        fence_proxy_async();
+                        mbar_expect_tx(bar_desc, NB * (uint32_t)sizeof(LongRun));
+                        tma_load_1d(next_s, runs + (size_t)nx_idx * NB, NB * (uint32_t)sizeof(LongRun), bar_desc);
+                        nx_stage = 1;
+                    } else {
+                        nx_stage = 3;
+                    }
+                }
                 if (lc < npk) {
                     fence_proxy_async();
                     issue_stage_cur(slot_i, lc);
                     lc++;
                 } else {
-                    if (nx_state == 0) {
-                        const uint32_t idx = atomicAdd(ticket, 1u);
-                        if (idx < n_groups) {
-#pragma unroll
-                            for (int b = 0; b < NB; b++) s_next[b] = runs[idx * NB + b];
-                            nx_state = 1;
-                            nx_npk = s_next[0].n_packets;
-                            nx_lc = 0;
-                        } else {
-                            nx_state = 2;
-                        }
+                    if (nx_stage == 1) {
+                        mbar_wait(bar_desc, desc_parity);
+                        desc_parity ^= 1u;
+                        nx_stage = 2;
+                        nx_npk = s_next[0].n_packets;
+                        nx_lc = 0;
                     }
-                    if (nx_state == 1 && nx_lc < nx_npk) {
+                    if (nx_stage == 2 && nx_lc < nx_npk) {
                         fence_proxy_async();
                         issue_stage(slot_i, s_next, nx_lc);
                         nx_lc++;
@@ -814,11 +849,28 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
                 }
             }
             phase_c_fft<NB>(tw, O, E);
-            if (p > 0) out_stage<NB, false>(tw, lane, O, E, pe, cur, out);
-            else out_stage<NB, true>(tw, lane, O, E, pe, cur, out);
+            if (p > 0) {
+                out_stage<NB, false>(tw, lane, O, E, pe, cur, out, s_state);
+            } else {
+                mbar_wait(bar_state, (phase_bits >> 30) & 1u);      // armed once per group
+                phase_bits ^= 1u << 30;
+                out_stage<NB, true>(tw, lane, O, E, pe, cur, out, s_state);
+                __syncwarp();                                       // state tile consumed
+            }
 #pragma unroll
             for (int b = 0; b < NB; b++)
                 if (p > 0 || (cur[b].flags & 1u)) out[b] += kLongN2;
+            // the state tile is free after packet 0: request the next group's state rows as soon as
+            // its descriptors are known
+            if (lane == 0 && nx_stage == 2 && !nx_state_issued) {
+                const float *st[NB];
+                uint32_t has[NB];
+#pragma unroll
+                for (int b = 0; b < NB; b++) { st[b] = s_next[b].state; has[b] = s_next[b].has_prev; }
+                fence_proxy_async();
+                issue_state(st, has);
+                nx_state_issued = 1;
+            }
             slot_i = (slot_i + 1 == (uint32_t)kLongRing) ? 0 : slot_i + 1;
         }
 #pragma unroll
@@ -834,36 +886,56 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
                 }
             }
         }
-        // hand over to the group lane 0 has (maybe) already started loading
-        uint32_t st = nx_state, nlc = nx_lc;
-        if (lane == 0 && st == 0) {                // the current group was shorter than the ring: draw now
-            const uint32_t idx = atomicAdd(ticket, 1u);
-            if (idx < n_groups) {
-#pragma unroll
-                for (int b = 0; b < NB; b++) s_next[b] = runs[idx * NB + b];
-                st = 1;
-                nlc = 0;
-            } else {
-                st = 2;
+        // hand over to the group lane 0 has (maybe) already started loading.  Short groups can get
+        // here before the asynchronous steps ran: finish them synchronously.
+        uint32_t st_ = 0, nlc = 0;
+        if (lane == 0) {
+            if (nx_stage == 0) {
+                if (nx_idx < n_groups) {
+                    fence_proxy_async();
+                    mbar_expect_tx(bar_desc, NB * (uint32_t)sizeof(LongRun));
+                    tma_load_1d(next_s, runs + (size_t)nx_idx * NB, NB * (uint32_t)sizeof(LongRun), bar_desc);
+                    nx_stage = 1;
+                } else {
+                    nx_stage = 3;
+                }
             }
+            if (nx_stage == 1) {
+                mbar_wait(bar_desc, desc_parity);
+                desc_parity ^= 1u;
+                nx_stage = 2;
+                nx_npk = s_next[0].n_packets;
+                nx_lc = 0;
+            }
+            if (nx_stage == 2 && !nx_state_issued) {
+                const float *st[NB];
+                uint32_t has[NB];
+#pragma unroll
+                for (int b = 0; b < NB; b++) { st[b] = s_next[b].state; has[b] = s_next[b].has_prev; }
+                fence_proxy_async();
+                issue_state(st, has);
+            }
+            st_ = nx_stage;
+            nlc = nx_lc;
         }
-        st = __shfl_sync(0xffffffffu, st, 0);
+        st_ = __shfl_sync(0xffffffffu, st_, 0);
         nlc = __shfl_sync(0xffffffffu, nlc, 0);
-        if (st != 1) break;
-        __syncwarp();
+        if (st_ != 2) break;
+        // (the shuffle also orders lane 0's wait on the descriptor barrier before these reads)
 #pragma unroll
         for (int b = 0; b < NB; b++) cur[b] = run_cur(s_next[b]);
         npk = s_next[0].n_packets;
         __syncwarp();                              // s_next may be overwritten from here on
         lc = nlc;
-        nx_state = 0; nx_lc = 0; nx_npk = 0;
-        // top the ring up (new group longer than what was prefetched so far)
+        nx_stage = 0; nx_lc = 0; nx_npk = 0; nx_state_issued = 0;
         if (lane == 0) {
+            // top the ring up (new group longer than what was prefetched so far)
             fence_proxy_async();
             for (uint32_t k = lc; k < (uint32_t)kLongRing && k < npk; k++) {
                 issue_stage_cur((slot_i + k) % kLongRing, k);
                 lc = k + 1;
             }
+            nx_idx = atomicAdd(ticket, 1u);        // ticket for the group after this one
         }
     }
 }
