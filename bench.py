@@ -147,7 +147,11 @@ def main():
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
     ctx = L.Context(local)
-    S, P, C = args.streams, args.packets, 2
+    # weak scaling: every rank owns `--streams` streams (global stream ids [lo, hi), contiguous ranges,
+    # lewton_b200/sharding.py); no data-path collective
+    from lewton_b200.sharding import stream_range
+    lo, hi = stream_range(args.streams * world, world, rank)
+    S, P, C = hi - lo, args.packets, 2
     su = L.Setup(ctx, C, 8, 11, [L.FloorTypeOne(1, [0, 128])], [L.Mapping(C)], [L.ModeInfo(False), L.ModeInfo(True)])
     stream = torch.cuda.ExternalStream(ctx.cuda_stream, device=torch.device("cuda", local))
 

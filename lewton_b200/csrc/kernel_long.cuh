@@ -940,326 +940,9 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// k_long2: the same arithmetic, phase-major over TWO consecutive packets of the run per step.
-// Each phase's twiddles are fetched from the shared pack once per step into registers and serve
-// both packets (the loops over the step's packets are NOT unrolled, so the code size is that of
-// k_long); shared-memory traffic for twiddles halves, which matters because the shared-memory
-// pipe is the tightest resource of this kernel (profiles/).  The stream state a run overlaps
-// with travels through the tile ring as the run's first "tile".
-// ---------------------------------------------------------------------------------------------
-constexpr int kRing2 = 4;                      // tiles per warp (two steps of two tiles)
-constexpr size_t kLong2SmemBytes = 2048 + (size_t)kLongWarps * kRing2 * kLongTileBytes +
-                                   (size_t)kLongPackFloats * 4 + kLongWarps * (kRing2 + 1) * 8 +
-                                   kLongWarps * sizeof(LongRun) + 64;
-
-struct TwArr {                 // twiddles of one phase, fetched once per step
-    const V *r;
-    int base;
-    __device__ __forceinline__ V operator()(int slot) const { return r[slot - base]; }
-};
-
-__global__ void __launch_bounds__(kLongWarps * 32, 1)
-k_long2(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restrict__ pack,
-        unsigned int *__restrict__ ticket)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t raw_s = smem_u32(smem_raw);
-    const uint32_t align_pad = (2048u - (raw_s & 2047u)) & 2047u;
-    unsigned char *base = smem_raw + align_pad;
-    constexpr size_t kTilesBytes = (size_t)kLongWarps * kRing2 * kLongTileBytes;
-    float *tiles = reinterpret_cast<float *>(base) + (size_t)warp * kRing2 * kLongN2;
-    V *s_pack = reinterpret_cast<V *>(base + kTilesBytes);
-    unsigned char *tail = base + kTilesBytes + (size_t)kLongPackFloats * 4;
-    LongRun *s_next = reinterpret_cast<LongRun *>(tail) + warp;                            // 16-aligned
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tail + (size_t)kLongWarps * sizeof(LongRun)) + warp * (kRing2 + 1);
-    if (n_runs == 0) return;
-    {
-        const float4 *src = reinterpret_cast<const float4 *>(pack);
-        float4 *dst = reinterpret_cast<float4 *>(s_pack);
-        for (int i = threadIdx.x; i < kLongPackFloats / 4; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
-    if (lane == 0) {
-        for (int i = 0; i < kRing2 + 1; i++) mbar_init(smem_u32(&bars[i]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    const V *pk = s_pack + lane;
-    const uint32_t tiles_s = smem_u32(tiles);
-    const uint32_t bars_s = smem_u32(bars);
-    const uint32_t bar_desc = bars_s + 8 * kRing2;
-    const uint32_t next_s = smem_u32(s_next);
-    const uint32_t lA0 = laneA(lane, 0), lA1 = laneA(lane, 1);
-    const uint32_t lB = laneB(lane);
-    const uint32_t lC0 = laneC(lane, 0), lC1 = laneC(lane, 1);
-    uint32_t phase_bits = 0;                  // bit i: parity of tile i's mbarrier
-    uint32_t slot = 0;                        // ring slot of the next tile to consume
-
-    // A run is a sequence of tiles: [state row, if has_prev] packet 0, packet 1, ...  lane 0 issues
-    // them in consumption order across run boundaries (cursor lc over the current run's tiles,
-    // nx_lc over the next run's), exactly like k_long.
-    uint32_t lc = 0, nx_idx = 0, nx_stage = 0, nx_lc = 0, nx_tiles = 0, desc_parity = 0;
-    RunCur cur;
-    uint32_t npk, hp;                         // packets of the run; 1 if it starts with a state tile
-
-    auto tile_src = [&](const float *in, uint32_t in_stride, const float *state, uint32_t has, uint32_t t) {
-        return (has && t == 0) ? state : in + (size_t)(t - has) * in_stride;
-    };
-    auto issue_tile = [&](uint32_t s, const float *src) {                        // lane 0 only
-        const uint32_t bar = bars_s + 8 * s;
-        mbar_expect_tx(bar, kLongTileBytes);
-        tma_load_1d(tiles_s + s * kLongTileBytes, src, kLongTileBytes, bar);
-    };
-    // refill ring slot s (just consumed) with the next tile in consumption order
-    auto refill = [&](uint32_t s, bool may_start_desc) {                         // lane 0 only
-        if (nx_stage == 0 && may_start_desc) {
-            if (nx_idx < n_runs) {
-                fence_proxy_async();
-                mbar_expect_tx(bar_desc, (uint32_t)sizeof(LongRun));
-                tma_load_1d(next_s, runs + nx_idx, (uint32_t)sizeof(LongRun), bar_desc);
-                nx_stage = 1;
-            } else {
-                nx_stage = 3;
-            }
-        }
-        if (lc < hp + npk) {
-            fence_proxy_async();
-            issue_tile(s, tile_src(cur.in, cur.in_stride, cur.state, hp, lc));
-            lc++;
-        } else {
-            if (nx_stage == 1) {
-                mbar_wait(bar_desc, desc_parity);
-                desc_parity ^= 1u;
-                nx_stage = 2;
-                nx_tiles = s_next->n_packets + (s_next->has_prev ? 1u : 0u);
-                nx_lc = 0;
-            }
-            if (nx_stage == 2 && nx_lc < nx_tiles) {
-                fence_proxy_async();
-                issue_tile(s, tile_src(s_next->in, s_next->in_stride, s_next->state, s_next->has_prev ? 1u : 0u, nx_lc));
-                nx_lc++;
-            }
-        }
-    };
-
-    {
-        uint32_t idx = 0;
-        if (lane == 0) idx = atomicAdd(ticket, 1u);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx >= n_runs) return;
-        cur = run_cur(runs[idx]);
-        npk = runs[idx].n_packets;
-        hp = cur.flags & 1u;
-        if (lane == 0) {
-            fence_proxy_async();
-            for (; lc < (uint32_t)kRing2 && lc < hp + npk; lc++)
-                issue_tile(lc, tile_src(cur.in, cur.in_stride, cur.state, hp, lc));
-            nx_idx = atomicAdd(ticket, 1u);            // not looked at before the second step
-        }
-    }
-
-    for (;;) {
-        V pe[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) pe[j] = V{0.f, 0.f};
-        float *out = cur.out;
-        const bool store = !(cur.flags & 4u);
-        uint32_t p = 0;
-        uint32_t step = 0;
-        while (p < npk) {
-            // tiles of this step: an optional leading state tile (first step of a run with history),
-            // then n packets
-            const uint32_t lead = (step == 0) ? hp : 0u;
-            const uint32_t n = (npk - p < 2u - lead) ? (npk - p) : (2u - lead);
-            const uint32_t s0 = slot;                                  // first tile of the step
-            const uint32_t sp = (s0 + lead) & (kRing2 - 1);            // first packet tile
-            V O[8], E[8];
-            // ---- phase A over the step's packets ------------------------------------------------
-            {
-                V twA[P_A_END];
-#pragma unroll
-                for (int s = 0; s < P_A_END; s++) twA[s] = pk[s * 32];
-                const TwArr tw{twA, 0};
-#pragma unroll 1
-                for (uint32_t it = 0; it < n; it++) {
-                    const uint32_t ts = (sp + it) & (kRing2 - 1);
-                    mbar_wait(bars_s + 8 * ts, (phase_bits >> ts) & 1u);
-                    phase_bits ^= 1u << ts;
-                    const float *tp[1] = {tiles + ts * kLongN2};
-                    V (*Op)[8] = reinterpret_cast<V (*)[8]>(O);
-                    V (*Ep)[8] = reinterpret_cast<V (*)[8]>(E);
-                    phase_a<1>(tp, lane, tw, Op, Ep);
-                    __syncwarp();
-                    const uint32_t t = tiles_s + ts * kLongTileBytes;
-                    const uint32_t a0 = t + lA0, a1 = t + lA1;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        sts_eo(a0 ^ LWB_KA(j), E[j].x, O[j].x);
-                        sts_eo(a1 ^ LWB_KA(j), E[j].y, O[j].y);
-                    }
-                }
-            }
-            __syncwarp();
-            // ---- phase B ---------------------------------------------------------------------------
-            {
-                V twB[P_B_END - P_A_END];
-#pragma unroll
-                for (int s = P_A_END; s < P_B_END; s++) twB[s - P_A_END] = pk[s * 32];
-                const TwArr tw{twB, P_A_END};
-#pragma unroll 1
-                for (uint32_t it = 0; it < n; it++) {
-                    const uint32_t ts = (sp + it) & (kRing2 - 1);
-                    const uint32_t b0 = tiles_s + ts * kLongTileBytes + lB;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        lds_eo(b0 ^ LWB_KB(j, 0), E[j].x, O[j].x);
-                        lds_eo(b0 ^ LWB_KB(j, 1), E[j].y, O[j].y);
-                    }
-                    __syncwarp();
-                    V (*Op)[8] = reinterpret_cast<V (*)[8]>(O);
-                    V (*Ep)[8] = reinterpret_cast<V (*)[8]>(E);
-                    phase_b<1>(tw, Op, Ep);
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        sts_eo(b0 ^ LWB_KB(j, 0), E[j].x, O[j].x);
-                        sts_eo(b0 ^ LWB_KB(j, 1), E[j].y, O[j].y);
-                    }
-                }
-            }
-            __syncwarp();
-            // ---- phase C + output -------------------------------------------------------------------
-            {
-                V twC[P_END - P_B_END];
-#pragma unroll
-                for (int s = P_B_END; s < P_END; s++) twC[s - P_B_END] = pk[s * 32];
-                const TwArr tw{twC, P_B_END};
-#pragma unroll 1
-                for (uint32_t it = 0; it < n; it++) {
-                    const uint32_t ts = (sp + it) & (kRing2 - 1);
-                    const uint32_t t = tiles_s + ts * kLongTileBytes;
-                    const uint32_t c0 = t + lC0, c1 = t + lC1;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        lds_eo(c0 ^ LWB_KC(j), E[j].x, O[j].x);
-                        lds_eo(c1 ^ LWB_KC(j), E[j].y, O[j].y);
-                    }
-                    __syncwarp();
-                    // ring slots are refilled in the order they are consumed: with a leading state
-                    // tile (still needed below) the packet tile waits its turn
-                    if (lane == 0 && !lead) refill(ts, step >= 1 || it >= 1);
-                    V (*Op)[8] = reinterpret_cast<V (*)[8]>(O);
-                    V (*Ep)[8] = reinterpret_cast<V (*)[8]>(E);
-                    phase_c_fft<1>(tw, Op, Ep);
-                    const bool first = (p + it == 0);
-                    const bool emit = store && (!first || hp);
-                    const float *st_tile = tiles + s0 * kLongN2;      // the run's state row (first step only)
-                    if (first && hp) {
-                        mbar_wait(bars_s + 8 * s0, (phase_bits >> s0) & 1u);
-                        phase_bits ^= 1u << s0;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const int r64 = 64 * rev3(j);
-                        const bool nat = (j & 1);
-                        V plo = pe[j], phi = pe[j];
-                        if (first && hp) {
-                            const float *s_lo = st_tile + lane, *s_hi = st_tile + 63 - lane;
-                            const float ax = nat ? s_lo[r64] : s_hi[r64], ay = nat ? s_hi[r64] : s_lo[r64];
-                            const float bx = nat ? s_hi[960 - r64] : s_lo[960 - r64];
-                            const float by = nat ? s_lo[960 - r64] : s_hi[960 - r64];
-                            plo = V{ax, ay};
-                            phi = V{bx, by};
-                        }
-                        V lo, hi, pev;
-                        step8_ola(tw(P_B0 + j), tw(P_B1 + j), tw(P_WLO + j), tw(P_WHI + j), O[j], E[j], plo, phi, lo, hi, pev);
-                        pe[j] = pev;
-                        if (emit) {
-                            float *o_lo = out + lane, *o_hi = out + 63 - lane;
-                            if (nat) {
-                                __stcs(o_lo + r64, lo.x); __stcs(o_hi + r64, lo.y);
-                                __stcs(o_hi + 960 - r64, hi.x); __stcs(o_lo + 960 - r64, hi.y);
-                            } else {
-                                __stcs(o_hi + r64, lo.x); __stcs(o_lo + r64, lo.y);
-                                __stcs(o_lo + 960 - r64, hi.x); __stcs(o_hi + 960 - r64, hi.y);
-                            }
-                        }
-                    }
-                    if (!first || hp) out += kLongN2;
-                    if (lead) {
-                        __syncwarp();                                 // state tile consumed by every lane
-                        if (lane == 0) {
-                            refill(s0, false);
-                            refill(ts, false);
-                        }
-                    }
-                }
-            }
-            p += n;
-            slot = (s0 + lead + n) & (kRing2 - 1);
-            step++;
-        }
-        if ((cur.flags & 6u) == 2u) {              // write_state and not dummy
-            float *s_lo = cur.state + lane, *s_hi = cur.state + 63 - lane;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int r64 = 64 * rev3(j);
-                const float vx = (j & 1) ? pe[j].x : pe[j].y, vy = (j & 1) ? pe[j].y : pe[j].x;
-                s_lo[r64] = vx; s_hi[r64] = vy;
-                s_hi[960 - r64] = vx; s_lo[960 - r64] = vy;
-            }
-        }
-        // hand-over (finish the asynchronous steps synchronously if the run was too short for them)
-        uint32_t st_ = 0, nlc = 0;
-        if (lane == 0) {
-            if (nx_stage == 0) {
-                if (nx_idx < n_runs) {
-                    fence_proxy_async();
-                    mbar_expect_tx(bar_desc, (uint32_t)sizeof(LongRun));
-                    tma_load_1d(next_s, runs + nx_idx, (uint32_t)sizeof(LongRun), bar_desc);
-                    nx_stage = 1;
-                } else {
-                    nx_stage = 3;
-                }
-            }
-            if (nx_stage == 1) {
-                mbar_wait(bar_desc, desc_parity);
-                desc_parity ^= 1u;
-                nx_stage = 2;
-                nx_lc = 0;
-            }
-            st_ = nx_stage;
-            nlc = nx_lc;
-        }
-        st_ = __shfl_sync(0xffffffffu, st_, 0);
-        nlc = __shfl_sync(0xffffffffu, nlc, 0);
-        if (st_ != 2) break;
-        cur = run_cur(*s_next);
-        npk = s_next->n_packets;
-        hp = cur.flags & 1u;
-        __syncwarp();                              // s_next may be overwritten from here on
-        lc = nlc;
-        nx_stage = 0; nx_lc = 0; nx_tiles = 0;
-        if (lane == 0) {
-            fence_proxy_async();
-            for (uint32_t k = lc; k < (uint32_t)kRing2 && k < hp + npk; k++) {
-                issue_tile((slot + k) & (kRing2 - 1), tile_src(cur.in, cur.in_stride, cur.state, hp, k));
-                lc = k + 1;
-            }
-            nx_idx = atomicAdd(ticket, 1u);
-        }
-    }
-}
-
-#ifndef LWB_LONG_KERNEL
-#define LWB_LONG_KERNEL 2
-#endif
-
 inline void long_kernel_configure()
 {
     cudaFuncSetAttribute(k_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes);
-    cudaFuncSetAttribute(k_long2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLong2SmemBytes);
 }
 
 // d_runs: n_groups * kLongNB descriptors.  Returns 0 on success; `ticket` must point at a zeroed
@@ -1269,10 +952,7 @@ inline int long_launch(cudaStream_t stream, const LongRun *d_runs, uint32_t n_gr
 {
     const uint32_t want = (n_groups + kLongWarps - 1) / kLongWarps;
     const uint32_t grid = want < (uint32_t)sm_count ? want : (uint32_t)sm_count;
-    if (LWB_LONG_KERNEL == 2 && kLongNB == 1)
-        k_long2<<<grid, kLongWarps * 32, kLong2SmemBytes, stream>>>(d_runs, n_groups, d_pack, ticket);
-    else
-        k_long<<<grid, kLongWarps * 32, kLongSmemBytes, stream>>>(d_runs, n_groups, d_pack, ticket);
+    k_long<<<grid, kLongWarps * 32, kLongSmemBytes, stream>>>(d_runs, n_groups, d_pack, ticket);
     return cudaGetLastError() != cudaSuccess;
 }
 #endif  // __CUDACC__
