@@ -186,8 +186,10 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
+    h0 = time.perf_counter()
     for _ in range(args.steps):
         step()
+    host_us = (time.perf_counter() - h0) * 1e6 / args.steps      # host cost of one submission (enqueue only)
     ev1.record(stream)
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -251,7 +253,7 @@ def main():
                 "e2e": {"value": e2e_value / 1e6, "unit": "Msamples/s",
                         "h2d_bytes_per_step": Se * P * C * N2 * 4, "d2h_bytes_per_step": Se * C * stride * 4,
                         "streams": Se, "steps": e_steps, "timer": "host wall clock around synchronous calls"},
-                "gpu_launches": int(launches), "clocks": clocks}
+                "gpu_launches": int(launches), "host_enqueue_us_per_step": host_us, "clocks": clocks}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, sec, reps = cpu_reference(8 * threads, 17, threads, target_sec=2.0)

@@ -224,6 +224,19 @@ typedef struct lwb_batch_io {
  * with LWB_MEM_DEVICE it returns after the launches are enqueued on lwb_ctx_cuda_stream(). */
 int lwb_decode_chains(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io);
 
+/* Prepared batches.  A decode server submits the same batch shape step after step (same streams,
+ * same packets per stream, same arenas); planning it again each time costs more host time than
+ * the GPU needs to run it.  lwb_plan_create captures the chain array, the io block and the
+ * per-chain mode / flag arrays BY REFERENCE (they must stay valid and unchanged until
+ * lwb_plan_destroy); lwb_plan_execute is then equivalent to lwb_decode_chains on that batch
+ * -- same results, same stream-state updates, same per-chain outputs in the captured chain
+ * array -- but reuses the device descriptors whenever no stream state has changed shape since they
+ * were built (it re-plans by itself otherwise, e.g. on the first execution after a reset). */
+typedef struct lwb_plan lwb_plan;
+int lwb_plan_create(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, lwb_plan **out);
+int lwb_plan_execute(lwb_plan *plan);
+void lwb_plan_destroy(lwb_plan *plan);
+
 /* Debug taps at the reference's record_* points (lib.rs:56-94; audio.rs:1004, 1041, 1054):
  * run one packet and return the intermediate vectors instead of PCM.  taps: any may be NULL.
  * post_inverse / pre_mdct: [channels][n/2]; post_mdct: [channels][n].  Does not touch the state. */

@@ -99,6 +99,9 @@ SYMBOLS = {
     "lwb_decode_spectrum": (C.c_int, [vp, C.c_uint8, C.c_int, C.c_int, vp, C.c_int, vp, C.c_size_t,
                                       C.POINTER(C.c_size_t)]),
     "lwb_decode_chains": (C.c_int, [vp, C.POINTER(Chain), C.c_size_t, C.POINTER(BatchIo)]),
+    "lwb_plan_create": (C.c_int, [vp, C.POINTER(Chain), C.c_size_t, C.POINTER(BatchIo), C.POINTER(vp)]),
+    "lwb_plan_execute": (C.c_int, [vp]),
+    "lwb_plan_destroy": (None, [vp]),
     "lwb_debug_packet_taps": (C.c_int, [vp, C.POINTER(Packet), vp, vp, vp]),
 }
 

@@ -81,7 +81,7 @@ class Context:
 
     def close(self):
         if self._h:
-            for kind in (PreviousWindowRight, Setup):          # streams first, then setups
+            for kind in (Batch, PreviousWindowRight, Setup):   # plans first, then streams, then setups
                 for ch in [c for c in list(self._children) if isinstance(c, kind)]:
                     ch.close()
             cabi.lib().lwb_ctx_destroy(self._h)
@@ -417,14 +417,29 @@ class Batch:
         io.entry, io.memory, io.out_format = entry, memory, out_format
         io.coeffs, io.pcm, io.dense_floor = addr(coeffs), addr(pcm), addr(dense_floor)
         io.floor_kind, io.floor1_y = addr(floor_kind), addr(floor1_y)
-        self._fn = cabi.lib().lwb_decode_chains
         self._n = len(self.chains)
+        self._plan = C.c_void_p()
+        ctx.check(cabi.lib().lwb_plan_create(ctx._h, self._arr, self._n, C.byref(self._io), C.byref(self._plan)))
+        ctx._children.add(self)
+        self._fn = cabi.lib().lwb_plan_execute
 
     def run(self):
-        """One submission.  Results land in the chain array; call collect() to copy them back."""
-        rc = self._fn(self.ctx._h, self._arr, self._n, C.byref(self._io))
+        """One submission (lwb_plan_execute).  Results land in the chain array; collect() copies them back."""
+        rc = self._fn(self._plan)
         if rc:
             self.ctx.check(rc)
+
+    def close(self):
+        if self._plan:
+            if self.ctx._h:
+                cabi.lib().lwb_plan_destroy(self._plan)
+            self._plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def collect(self):
         for i, c in enumerate(self.chains):
@@ -437,5 +452,8 @@ def decode_chains(ctx, chains, entry, memory, coeffs, pcm, out_format, floor_kin
     """lwb_decode_chains.  coeffs/pcm/dense_floor: numpy arrays (MEM_HOST) or integer device
     pointers (MEM_DEVICE); floor_kind/floor1_y: numpy arrays (always host)."""
     b = Batch(ctx, chains, entry, memory, coeffs, pcm, out_format, floor_kind, floor1_y, dense_floor)
-    b.run()
-    return b.collect()
+    try:
+        b.run()
+        return b.collect()
+    finally:
+        b.close()

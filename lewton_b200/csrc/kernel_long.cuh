@@ -48,7 +48,7 @@ constexpr int kLongN2 = 1024;
 // one run = consecutive packets of one channel of one stream
 struct alignas(16) LongRun {      // 48 bytes: fetched by the kernel with one 1-D TMA copy
     const float *in;        // first packet's spectrum (1024 floats); next packet at +in_stride
-    float *out;             // first emitted packet's PCM; next at +1024
+    void *out;              // first emitted packet's PCM (f32 or i16 elements); next at +1024
     float *state;           // stream state row of this channel (1024 floats)
     uint32_t in_stride;
     uint32_t n_packets;     // including a primer packet if prime != 0
@@ -573,7 +573,7 @@ __device__ __forceinline__ uint32_t laneC(int lane, int half) { return 4u * (uin
 // Uniform (per-warp) view of the runs being processed
 struct RunCur {
     const float *in;
-    float *out;
+    void *out;
     float *state;
     uint32_t in_stride;
     uint32_t flags;               // bit0 has_prev, bit1 write_state, bit2 dummy
@@ -584,13 +584,25 @@ __device__ __forceinline__ RunCur run_cur(const LongRun &r)
                   (uint32_t)(r.has_prev ? 1u : 0u) | (r.write_state ? 2u : 0u) | (r.dummy ? 4u : 0u)};
 }
 
+// samples.rs:92-103 (`Sample for i16`): x * 32768, clamp, truncate toward zero, NaN -> 0
+__device__ __forceinline__ int16_t d_sample_i16(float v)
+{
+    const float fl = __fmul_rn(v, 32768.0f);
+    if (fl > 32767.f) return 32767;
+    if (fl < -32768.f) return -32768;
+    if (fl != fl) return 0;
+    return (int16_t)(int)fl;
+}
+__device__ __forceinline__ void st_pcm(float *p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_pcm(int16_t *p, float v) { __stcs(reinterpret_cast<short *>(p), (short)d_sample_i16(v)); }
+
 // Step 8 + window + overlap-add + stores, all 8 slots of all NB blocks.  FIRST: packet 0 of the
 // run -- its previous right half comes from the stream state (staged in shared memory by TMA
 // while the run's first tile was in flight) if has_prev, else nothing is emitted.  Streaming
 // stores: PCM is written once and never read back by this kernel.
-template <int NB, bool FIRST>
+template <int NB, bool FIRST, typename OutT>
 __device__ __forceinline__ void out_stage(const TwMix &tw, int lane, const V O[NB][8], const V E[NB][8], V pe[NB][8],
-                                          const RunCur cur[NB], float *out[NB], const float *s_state)
+                                          const RunCur cur[NB], OutT *out[NB], const float *s_state)
 {
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -619,13 +631,13 @@ __device__ __forceinline__ void out_stage(const TwMix &tw, int lane, const V O[N
             pe[b][j] = pev;
             if (emit) {
                 // m = r64 + lane (or + 63 - lane); 1023 - m = 960 - r64 + 63 - lane (or + lane)
-                float *o_lo = out[b] + lane, *o_hi = out[b] + 63 - lane;
+                OutT *o_lo = out[b] + lane, *o_hi = out[b] + 63 - lane;
                 if (nat) {
-                    __stcs(o_lo + r64, lo.x); __stcs(o_hi + r64, lo.y);
-                    __stcs(o_hi + 960 - r64, hi.x); __stcs(o_lo + 960 - r64, hi.y);
+                    st_pcm(o_lo + r64, lo.x); st_pcm(o_hi + r64, lo.y);
+                    st_pcm(o_hi + 960 - r64, hi.x); st_pcm(o_lo + 960 - r64, hi.y);
                 } else {
-                    __stcs(o_hi + r64, lo.x); __stcs(o_lo + r64, lo.y);
-                    __stcs(o_lo + 960 - r64, hi.x); __stcs(o_hi + 960 - r64, hi.y);
+                    st_pcm(o_hi + r64, lo.x); st_pcm(o_lo + r64, lo.y);
+                    st_pcm(o_lo + 960 - r64, hi.x); st_pcm(o_hi + 960 - r64, hi.y);
                 }
             }
         }
@@ -642,6 +654,7 @@ __device__ __forceinline__ void out_stage(const TwMix &tw, int lane, const V O[N
 //     a packet later; its descriptors then arrive by TMA into shared memory;
 //   * the stream state a run overlaps with (has_prev) arrives by TMA into a per-warp state tile
 //     while the run's first spectrum tile is in flight.
+template <typename OutT>
 __global__ void __launch_bounds__(kLongWarps * 32, 1)
 k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restrict__ pack,
        unsigned int *__restrict__ ticket)
@@ -755,9 +768,9 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
         for (int b = 0; b < NB; b++)
 #pragma unroll
             for (int j = 0; j < 8; j++) pe[b][j] = V{0.f, 0.f};
-        float *out[NB];
+        OutT *out[NB];
 #pragma unroll
-        for (int b = 0; b < NB; b++) out[b] = cur[b].out;
+        for (int b = 0; b < NB; b++) out[b] = static_cast<OutT *>(cur[b].out);
 
         for (uint32_t p = 0; p < npk; p++) {
             const uint32_t stage_s = tiles_s + slot_i * kLongStageBytes;
@@ -850,11 +863,11 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
             }
             phase_c_fft<NB>(tw, O, E);
             if (p > 0) {
-                out_stage<NB, false>(tw, lane, O, E, pe, cur, out, s_state);
+                out_stage<NB, false, OutT>(tw, lane, O, E, pe, cur, out, s_state);
             } else {
                 mbar_wait(bar_state, (phase_bits >> 30) & 1u);      // armed once per group
                 phase_bits ^= 1u << 30;
-                out_stage<NB, true>(tw, lane, O, E, pe, cur, out, s_state);
+                out_stage<NB, true, OutT>(tw, lane, O, E, pe, cur, out, s_state);
                 __syncwarp();                                       // state tile consumed
             }
 #pragma unroll
@@ -942,17 +955,19 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
 
 inline void long_kernel_configure()
 {
-    cudaFuncSetAttribute(k_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes);
+    cudaFuncSetAttribute(k_long<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes);
+    cudaFuncSetAttribute(k_long<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes);
 }
 
 // d_runs: n_groups * kLongNB descriptors.  Returns 0 on success; `ticket` must point at a zeroed
 // device word no other launch in flight uses.
 inline int long_launch(cudaStream_t stream, const LongRun *d_runs, uint32_t n_groups, const float *d_pack,
-                       unsigned int *ticket, int sm_count)
+                       unsigned int *ticket, int sm_count, bool i16_out)
 {
     const uint32_t want = (n_groups + kLongWarps - 1) / kLongWarps;
     const uint32_t grid = want < (uint32_t)sm_count ? want : (uint32_t)sm_count;
-    k_long<<<grid, kLongWarps * 32, kLongSmemBytes, stream>>>(d_runs, n_groups, d_pack, ticket);
+    if (i16_out) k_long<int16_t><<<grid, kLongWarps * 32, kLongSmemBytes, stream>>>(d_runs, n_groups, d_pack, ticket);
+    else k_long<float><<<grid, kLongWarps * 32, kLongSmemBytes, stream>>>(d_runs, n_groups, d_pack, ticket);
     return cudaGetLastError() != cudaSuccess;
 }
 #endif  // __CUDACC__

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "kernel_long.cuh"
 #include "lwb_common.h"
 
 namespace lwb {
@@ -379,15 +380,7 @@ k_imdct(const DevPacket *__restrict__ pkts, const float *__restrict__ spec, floa
 // ---------------------------------------------------------------------------------------------
 // window / overlap-add / slice / sample conversion, audio.rs:1079-1157 + samples.rs
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int16_t d_sample_i16(float v)
-{
-    // samples.rs:92-103; Rust's `as i16` truncates toward zero and maps NaN to 0
-    const float fl = __fmul_rn(v, 32768.0f);
-    if (fl > 32767.f) return 32767;
-    if (fl < -32768.f) return -32768;
-    if (fl != fl) return 0;
-    return (int16_t)(int)fl;
-}
+// d_sample_i16 (samples.rs:92-103) lives in kernel_long.cuh, shared by both paths
 
 constexpr int kOverlapThreads = 256;
 

@@ -45,6 +45,7 @@ struct lwb_ctx {
     cudaEvent_t ev_desc[2] = {}, ev_kdone[2] = {};
     int runs_par = 0;
     uint32_t ticket_next = 0;
+    uint64_t state_gen = 1;        // bumped whenever any stream's (has, len) changes: plans key on it
     std::string err;
     uint64_t launches = 0;
     // grow-only device arenas
@@ -66,6 +67,20 @@ struct lwb_setup {
     std::vector<DevMapping> mappings;   // host copy (validation)
 };
 
+struct lwb_plan {
+    lwb_ctx *ctx = nullptr;
+    lwb_chain *chains = nullptr;
+    size_t n_chains = 0;
+    lwb_batch_io io;
+    // captured fused-path launch (valid while ctx->state_gen == gen)
+    bool captured = false;
+    uint64_t gen = 0;
+    DevBuf runs;
+    uint32_t n_groups = 0;
+    const float *pack = nullptr;
+    bool i16 = false;
+};
+
 struct lwb_stream {
     lwb_ctx *ctx = nullptr;
     const lwb_setup *setup = nullptr;
@@ -74,6 +89,15 @@ struct lwb_stream {
     uint32_t plen = 0;             // per-channel length of the saved right half
     uint64_t busy_epoch = 0;       // guards against one stream appearing twice in a batch
 };
+
+static inline void set_stream_state(lwb_stream *s, bool has, uint32_t plen)
+{
+    if (s->has != has || s->plen != plen) {
+        s->has = has;
+        s->plen = plen;
+        s->ctx->state_gen++;
+    }
+}
 
 static int fail(lwb_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess)
 {
@@ -409,8 +433,7 @@ extern "C" void lwb_stream_destroy(lwb_stream *s)
 extern "C" int lwb_stream_reset(lwb_stream *s)
 {
     if (!s) return LWB_ERR_INVALID;
-    s->has = false;
-    s->plen = 0;
+    set_stream_state(s, false, 0);
     return LWB_OK;
 }
 extern "C" int lwb_stream_is_empty(const lwb_stream *s) { return (!s || !s->has) ? 1 : 0; }
@@ -453,6 +476,7 @@ extern "C" int lwb_stream_import_state(lwb_stream *s, const float *data, uint32_
                                   len * sizeof(float), s->setup->channels, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    s->ctx->state_gen++;           // contents changed even if the shape did not
     s->has = true;
     s->plen = len;
     return LWB_OK;
@@ -734,8 +758,8 @@ static int acquire_staging(lwb_ctx *ctx, size_t bytes, Staging **out)
 // when there are too few chains to fill the machine; every run after the first re-transforms the
 // packet before its first one as a primer (its right half is all the run needs), which keeps
 // runs independent at the cost of one extra IMDCT per cut.
-static void long_runs_of(const LongItem &it, size_t cuts, const float *coeffs, uint64_t coeff_base, float *pcm,
-                         uint64_t pcm_base, std::vector<LongRun> &w)
+static void long_runs_of(const LongItem &it, size_t cuts, const float *coeffs, uint64_t coeff_base, char *pcm,
+                         uint64_t pcm_base, size_t esz, LongRun *&w)
 {
     const lwb_stream *s = it.c->stream;
     const lwb_setup *su = s->setup;
@@ -743,11 +767,10 @@ static void long_runs_of(const LongItem &it, size_t cuts, const float *coeffs, u
     const size_t P = it.P;
     for (unsigned ch = 0; ch < C; ch++) {
         const float *in0 = coeffs + (it.c->coeff_offset - coeff_base) + (size_t)ch * kLongN2;
-        float *out0 = pcm + (it.c->out_offset - pcm_base) + (size_t)ch * it.c->out_stride;
+        char *out0 = pcm + ((it.c->out_offset - pcm_base) + (size_t)ch * it.c->out_stride) * esz;
         for (size_t k = 0; k < cuts; k++) {
             const size_t p0 = P * k / cuts, p1 = P * (k + 1) / cuts;   // this run emits packets [p0, p1)
-            w.emplace_back();
-            LongRun &r = w.back();
+            LongRun &r = *w++;
             std::memset(&r, 0, sizeof(r));
             r.in_stride = (uint32_t)(C * kLongN2);
             r.state = s->d_state + (size_t)ch * state_stride(su);
@@ -762,18 +785,27 @@ static void long_runs_of(const LongItem &it, size_t cuts, const float *coeffs, u
                 r.n_packets = (uint32_t)(p1 - p0 + 1);
                 r.has_prev = 0;
                 // samples emitted before packet p0: packets 0..p0-1, minus the first if no state
-                r.out = out0 + (size_t)(p0 - (it.has_prev ? 0 : 1)) * kLongN2;
+                r.out = out0 + (size_t)(p0 - (it.has_prev ? 0 : 1)) * kLongN2 * esz;
             }
         }
     }
 }
 
+// `spectrum_dev`: when non-null the spectrum has already been formed on the device (residue entry:
+// k_prologue wrote it to ctx->spec, element offset `spectrum_base` = its [0]); the input side of the
+// batch is then neither validated as a spectrum entry nor copied.
 static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch,
-                    bool *handled)
+                    bool *handled, const float *spectrum_dev = nullptr, uint64_t spectrum_base = 0,
+                    lwb_plan *plan = nullptr)
 {
     *handled = false;
-    if (io->entry != LWB_ENTRY_SPECTRUM || io->out_format != LWB_OUT_F32_PLANAR) return LWB_OK;
+    const uint64_t gen_at_entry = ctx->state_gen;
+    if (plan) plan->captured = false;
+    if (!spectrum_dev && io->entry != LWB_ENTRY_SPECTRUM) return LWB_OK;
+    if (io->out_format != LWB_OUT_F32_PLANAR && io->out_format != LWB_OUT_I16_PLANAR) return LWB_OK;
     if (getenv("LWB_FORCE_GENERIC")) return LWB_OK;
+    const bool i16 = io->out_format == LWB_OUT_I16_PLANAR;
+    const size_t esz = i16 ? 2 : 4;
     std::vector<LongItem> items;
     items.reserve(n_chains);
     const float *pack = nullptr;
@@ -803,8 +835,10 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
     uint64_t c_lo = ~0ull, c_hi = 0, o_lo = ~0ull, o_hi = 0;
     for (auto &it : items) {
         lwb_chain *c = it.c;
-        if (c->stream->busy_epoch == epoch) return fail(ctx, LWB_ERR_INVALID, "a stream appears in two chains of one batch");
-        c->stream->busy_epoch = epoch;
+        if (!spectrum_dev) {       // (the residue path has already run this check while planning)
+            if (c->stream->busy_epoch == epoch) return fail(ctx, LWB_ERR_INVALID, "a stream appears in two chains of one batch");
+            c->stream->busy_epoch = epoch;
+        }
         const unsigned C = c->stream->setup->channels;
         c->status = LWB_OK;
         c->packets_done = it.P;
@@ -831,7 +865,8 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
         }
     }
 
-    const bool host = io->memory == LWB_MEM_HOST;
+    const bool host = io->memory == LWB_MEM_HOST;          // the pcm arena is in host memory
+    const bool in_host = host && !spectrum_dev;            // ... and so is the coefficient arena
     // host memory: chunks of chains, H2D / kernel / D2H of consecutive chunks overlap on three streams
     size_t n_chunks = 1;
     if (host) {
@@ -839,15 +874,17 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
         n_chunks = std::min<size_t>(std::max<size_t>(1, bytes >> 24), std::min<size_t>(16, items.size()));
         if (const char *e = getenv("LWB_E2E_CHUNKS")) n_chunks = std::max<size_t>(1, std::min<size_t>((size_t)atol(e), items.size()));
     }
-    const float *d_coeffs = io->coeffs;
-    float *d_pcm = (float *)io->pcm;
-    uint64_t cbase = 0, obase = 0;
+    const float *d_coeffs = spectrum_dev ? spectrum_dev : io->coeffs;
+    char *d_pcm = (char *)io->pcm;
+    uint64_t cbase = spectrum_dev ? spectrum_base : 0, obase = 0;
     if (host) {
-        if ((rc = ensure(ctx, ctx->coeffs, (size_t)(c_hi - c_lo) * 4))) return rc;
-        if (o_hi > o_lo && (rc = ensure(ctx, ctx->pcm, (size_t)(o_hi - o_lo) * 4))) return rc;
-        d_coeffs = (const float *)ctx->coeffs.p;
-        d_pcm = (float *)ctx->pcm.p;
-        cbase = c_lo;
+        if (in_host) {
+            if ((rc = ensure(ctx, ctx->coeffs, (size_t)(c_hi - c_lo) * 4))) return rc;
+            d_coeffs = (const float *)ctx->coeffs.p;
+            cbase = c_lo;
+        }
+        if (o_hi > o_lo && (rc = ensure(ctx, ctx->pcm, (size_t)(o_hi - o_lo) * esz))) return rc;
+        d_pcm = (char *)ctx->pcm.p;
         obase = o_lo;
         if (!ctx->ev_in[0])
             for (int k = 0; k < 16; k++) {
@@ -877,8 +914,11 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
     if ((rc = acquire_staging(ctx, cap_runs * sizeof(LongRun), &st))) return rc;
     const int par = ctx->runs_par;
     ctx->runs_par ^= 1;
-    if ((rc = ensure(ctx, ctx->runs_buf[par], cap_runs * sizeof(LongRun)))) return rc;
-    LongRun *const d_runs_base = (LongRun *)ctx->runs_buf[par].p;
+    // a plan (device-memory batches) owns its descriptor buffer so that later executions can reuse it
+    const bool capture = plan && !host && !spectrum_dev && n_chunks == 1;
+    DevBuf &rb = capture ? plan->runs : ctx->runs_buf[par];
+    if ((rc = ensure(ctx, rb, cap_runs * sizeof(LongRun)))) return rc;
+    LongRun *const d_runs_base = (LongRun *)rb.p;
     LongRun *h_runs = (LongRun *)st->h, *w = h_runs;
     std::vector<LongRun> tmp;
     struct ChunkPlan { size_t r0, nr; uint64_t kc_lo, kc_hi, ko_lo, ko_hi; };
@@ -888,10 +928,19 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
         const size_t i0 = items.size() * k / n_chunks, i1 = items.size() * (k + 1) / n_chunks;
         LongRun *w0 = w;
         uint64_t kc_lo = ~0ull, kc_hi = 0, ko_lo = ~0ull, ko_hi = 0;
-        tmp.clear();
+        // NB == 1: descriptors are written straight into the pinned staging; otherwise into a scratch
+        // vector that is regrouped below
+        size_t chunk_runs = 0;
+        for (size_t i = i0; i < i1; i++)
+            if (items[i].P) chunk_runs += cuts[i] * items[i].c->stream->setup->channels;
+        LongRun *gen = w;
+        if (kLongNB > 1) {
+            tmp.resize(chunk_runs);
+            gen = tmp.data();
+        }
         for (size_t i = i0; i < i1; i++) {
             if (!items[i].P) continue;
-            long_runs_of(items[i], cuts[i], d_coeffs, cbase, d_pcm, obase, tmp);
+            long_runs_of(items[i], cuts[i], d_coeffs, cbase, d_pcm, obase, esz, gen);
             const lwb_chain *c = items[i].c;
             const unsigned C = c->stream->setup->channels;
             kc_lo = std::min(kc_lo, c->coeff_offset);
@@ -899,10 +948,9 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
             ko_lo = std::min(ko_lo, c->out_offset);
             ko_hi = std::max(ko_hi, c->out_offset + (uint64_t)(C - 1) * c->out_stride + c->n_samples);
         }
-        if (tmp.empty()) continue;
+        if (!chunk_runs) continue;
         if (kLongNB == 1) {
-            std::memcpy(w, tmp.data(), tmp.size() * sizeof(LongRun));
-            w += tmp.size();
+            w = gen;
         } else {
             // group runs of equal packet count (consecutive channels of a stream already are)
             bool sorted = true;
@@ -942,7 +990,7 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
     CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_desc[par], 0));
     for (size_t k = 0; k < cplan.size(); k++) {
         const ChunkPlan &cp = cplan[k];
-        if (host) {
+        if (in_host) {
             CU(ctx, cudaMemcpyAsync((float *)ctx->coeffs.p + (cp.kc_lo - cbase), io->coeffs + cp.kc_lo,
                                     (size_t)(cp.kc_hi - cp.kc_lo) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
             CU(ctx, cudaEventRecord(ctx->ev_in[k], ctx->copy_in));
@@ -951,30 +999,85 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
         if (ctx->ticket_next % kTicketPool == 0)
             CU(ctx, cudaMemsetAsync(ctx->ticket.p, 0, kTicketPool * sizeof(unsigned int), ctx->stream));
         unsigned int *ticket = (unsigned int *)ctx->ticket.p + (ctx->ticket_next++ % kTicketPool);
-        if (long_launch(ctx->stream, d_runs_base + cp.r0, (uint32_t)(cp.nr / kLongNB), pack, ticket, ctx->sm_count))
+        if (long_launch(ctx->stream, d_runs_base + cp.r0, (uint32_t)(cp.nr / kLongNB), pack, ticket, ctx->sm_count, i16))
             return fail(ctx, LWB_ERR_CUDA, "long kernel launch", cudaGetLastError());
         ctx->launches++;
         if (host && cp.ko_hi > cp.ko_lo) {
             CU(ctx, cudaEventRecord(ctx->ev_done[k], ctx->stream));
             CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[k], 0));
-            CU(ctx, cudaMemcpyAsync((float *)io->pcm + cp.ko_lo, (float *)ctx->pcm.p + (cp.ko_lo - obase),
-                                    (size_t)(cp.ko_hi - cp.ko_lo) * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+            CU(ctx, cudaMemcpyAsync((char *)io->pcm + cp.ko_lo * esz, (char *)ctx->pcm.p + (cp.ko_lo - obase) * esz,
+                                    (size_t)(cp.ko_hi - cp.ko_lo) * esz, cudaMemcpyDeviceToHost, ctx->copy_out));
         }
     }
     CU(ctx, cudaEventRecord(ctx->ev_kdone[par], ctx->stream));
+    if (capture && cplan.size() == 1) {
+        plan->captured = true;
+        plan->gen = gen_at_entry;          // valid while no stream changed shape since planning
+        plan->n_groups = (uint32_t)(cplan[0].nr / kLongNB);
+        plan->pack = pack;
+        plan->i16 = i16;
+    }
     if (host) {
         CU(ctx, cudaStreamSynchronize(ctx->copy_out));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
     for (auto &it : items)
-        if (it.P) {
-            it.c->stream->has = true;
-            it.c->stream->plen = kLongN2;
-        }
+        if (it.P) set_stream_state(it.c->stream, true, kLongN2);
     return LWB_OK;
 }
 
-extern "C" int lwb_decode_chains(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io)
+// Residue-entry batches whose every packet is a long block with long neighbours (what the fused
+// kernel takes) -- decided from the generic plan.
+static bool plan_is_long(const std::vector<PlanChain> &plan, const lwb_batch_io *io)
+{
+    if (io->out_format != LWB_OUT_F32_PLANAR && io->out_format != LWB_OUT_I16_PLANAR) return false;
+    if (getenv("LWB_FORCE_GENERIC")) return false;
+    for (auto &pc : plan) {
+        const lwb_setup *su = pc.c->stream->setup;
+        if (su->bs1 != kLongBs || !su->host.tab[1].pack) return false;
+        if (pc.c->status != LWB_OK) return false;
+        for (auto &pp : pc.pk) {
+            if (!pp.g.blockflag || pp.g.ls != 0 || pp.g.rs != (pp.g.n >> 1) || pp.g.re != pp.g.n) return false;
+            if (pp.plen != 0 && pp.plen != (pp.g.n >> 1)) return false;
+        }
+    }
+    return true;
+}
+
+// k_prologue over every packet of the plan: ctx->spec[coeff_off] <- floor x decoupled residue.
+static int run_prologue_all(lwb_ctx *ctx, std::vector<PlanChain> &plan, const DevArenas &ar, size_t spec_elems)
+{
+    size_t n_desc = 0;
+    for (auto &pc : plan) n_desc += pc.pk.size();
+    if (!n_desc) return LWB_OK;
+    int rc;
+    if ((rc = ensure_pinned(ctx, n_desc * sizeof(DevPacket)))) return rc;
+    if ((rc = ensure(ctx, ctx->desc, n_desc * sizeof(DevPacket)))) return rc;
+    if ((rc = ensure(ctx, ctx->spec, spec_elems * sizeof(float)))) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));          // pinned descriptor staging is reused
+    DevPacket *hp = (DevPacket *)ctx->h_desc;
+    size_t di = 0;
+    for (auto &pc : plan) {
+        const lwb_setup *su = pc.c->stream->setup;
+        for (size_t k = 0; k < pc.pk.size(); k++) {
+            const PlanPacket &pp = pc.pk[k];
+            DevPacket &d = hp[di++];
+            std::memset(&d, 0, sizeof(d));
+            d.setup = su->d_setup;
+            d.coeff_off = pp.coeff_off - ar.coeff_base;
+            d.pkt_index = pc.c->packet_index + k - ar.kinds_row0;
+            d.n = (uint16_t)pp.g.n;
+            d.blockflag = pp.g.blockflag;
+            d.mapping = pp.g.mapping;
+            d.channels = su->channels;
+        }
+    }
+    CU(ctx, cudaMemcpyAsync(ctx->desc.p, hp, n_desc * sizeof(DevPacket), cudaMemcpyHostToDevice, ctx->stream));
+    return launch(ctx, k_prologue, dim3((unsigned)n_desc), dim3(kPrologueThreads), 0, (const DevPacket *)ctx->desc.p,
+                  ar.coeffs, ar.dense, ar.kinds, ar.ys, (float *)ctx->spec.p);
+}
+
+static int decode_chains_impl(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, lwb_plan *prepared)
 {
     if (!ctx || (!chains && n_chains) || !io) return LWB_ERR_INVALID;
     if (io->entry != LWB_ENTRY_SPECTRUM && io->entry != LWB_ENTRY_RESIDUE) return fail(ctx, LWB_ERR_INVALID, "bad entry");
@@ -987,7 +1090,7 @@ extern "C" int lwb_decode_chains(lwb_ctx *ctx, lwb_chain *chains, size_t n_chain
     epoch++;
     {
         bool handled = false;
-        int rc0 = try_long(ctx, chains, n_chains, io, epoch, &handled);
+        int rc0 = try_long(ctx, chains, n_chains, io, epoch, &handled, nullptr, 0, prepared);
         if (rc0 || handled) return rc0;
     }
     const bool residue = io->entry == LWB_ENTRY_RESIDUE;
@@ -1069,6 +1172,15 @@ extern "C" int lwb_decode_chains(lwb_ctx *ctx, lwb_chain *chains, size_t n_chain
             }
             ar.kinds_row0 = r_lo;
         }
+        if (residue && plan_is_long(plan, io)) {
+            // residue entry, uniform long blocks: k_prologue forms the spectrum on the device, the fused
+            // kernel does the rest (one extra spectrum round trip compared with the spectrum entry)
+            if ((rc = run_prologue_all(ctx, plan, ar, (size_t)(c_hi - c_lo)))) return rc;
+            bool handled = false;
+            rc = try_long(ctx, chains, n_chains, io, epoch, &handled, (const float *)ctx->spec.p, ar.coeff_base);
+            if (rc) return rc;
+            if (handled) return LWB_OK;            // try_long has committed results and stream states
+        }
         rc = run_generic(ctx, plan, io, ar);
         if (rc) return rc;
         if (io->memory == LWB_MEM_HOST) {
@@ -1081,12 +1193,62 @@ extern "C" int lwb_decode_chains(lwb_ctx *ctx, lwb_chain *chains, size_t n_chain
     // commit the host-side view of every stream's state
     for (auto &pc : plan) {
         lwb_stream *s = pc.c->stream;
-        if (!pc.pk.empty() || pc.clear_after) {
-            s->has = pc.end_has;
-            s->plen = pc.end_plen;
-        }
+        if (!pc.pk.empty() || pc.clear_after) set_stream_state(s, pc.end_has, pc.end_plen);
     }
     return LWB_OK;
+}
+
+extern "C" int lwb_decode_chains(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io)
+{
+    return decode_chains_impl(ctx, chains, n_chains, io, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// prepared batches
+// ---------------------------------------------------------------------------------------------
+extern "C" int lwb_plan_create(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, lwb_plan **out)
+{
+    if (!ctx || !out || (!chains && n_chains) || !io) return LWB_ERR_INVALID;
+    lwb_plan *p = new (std::nothrow) lwb_plan();
+    if (!p) return LWB_ERR_BUFFER;
+    p->ctx = ctx;
+    p->chains = chains;
+    p->n_chains = n_chains;
+    p->io = *io;
+    *out = p;
+    return LWB_OK;
+}
+
+extern "C" void lwb_plan_destroy(lwb_plan *p)
+{
+    if (!p) return;
+    if (p->runs.p) {
+        cudaSetDevice(p->ctx->device);
+        cudaStreamSynchronize(p->ctx->stream);
+        cudaFree(p->runs.p);
+    }
+    delete p;
+}
+
+extern "C" int lwb_plan_execute(lwb_plan *p)
+{
+    if (!p) return LWB_ERR_INVALID;
+    lwb_ctx *ctx = p->ctx;
+    if (p->captured && p->gen == ctx->state_gen && !getenv("LWB_FORCE_GENERIC")) {
+        // steady state: nothing about the batch or the stream states has changed shape since the
+        // descriptors were built -- the per-chain results in the caller's array are still right,
+        // the stream states stay (has, 1024): just launch.
+        CU(ctx, cudaSetDevice(ctx->device));
+        constexpr uint32_t kTicketPool = 1024;
+        if (ctx->ticket_next % kTicketPool == 0)
+            CU(ctx, cudaMemsetAsync(ctx->ticket.p, 0, kTicketPool * sizeof(unsigned int), ctx->stream));
+        unsigned int *ticket = (unsigned int *)ctx->ticket.p + (ctx->ticket_next++ % kTicketPool);
+        if (long_launch(ctx->stream, (const LongRun *)p->runs.p, p->n_groups, p->pack, ticket, ctx->sm_count, p->i16))
+            return fail(ctx, LWB_ERR_CUDA, "long kernel launch", cudaGetLastError());
+        ctx->launches++;
+        return LWB_OK;
+    }
+    return decode_chains_impl(ctx, p->chains, p->n_chains, &p->io, p);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -426,3 +426,135 @@ def test_special_values_on_gpu(ctx, oracle):
         for s in range(2):
             assert bits_equal(pcm[s][:, :3072], want[s]), (env, s, mismatch_report(pcm[s][:, :3072], want[s]))
             assert bits_equal(pwrs[s].data(), fin[s])
+
+
+@pytest.mark.parametrize("memory", [cabi.MEM_HOST, cabi.MEM_DEVICE])
+def test_fused_i16_planar_output(ctx, oracle, memory):
+    """Vec<Vec<i16>> (samples.rs:92-103) straight out of the fused kernel: bit-exact after the quantise."""
+    rng = np.random.default_rng(51)
+    S, P, C = 6, 11, 2
+    su = make_setup(ctx, C, 8, 11)
+    pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+    spec = (rng.standard_normal((S, P, C, 1024)) * 0.4).astype(np.float32)     # loud: exercises the clamp
+    stride = P * 1024
+    chains = [L.ChainSpec(pwrs[s], np.ones(P, np.uint8), coeff_offset=s * P * C * 1024, out_offset=s * C * stride,
+                          out_stride=stride) for s in range(S)]
+    pcm = np.zeros((S, C, stride), np.int16)
+    if memory == cabi.MEM_HOST:
+        L.decode_chains(ctx, chains, cabi.ENTRY_SPECTRUM, memory, spec, pcm, cabi.OUT_I16_PLANAR)
+    else:
+        d_in, d_out = ctx.device_alloc(spec.nbytes), ctx.device_alloc(pcm.nbytes)
+        ctx.h2d(d_in, spec)
+        ctx.h2d(d_out, pcm)
+        L.decode_chains(ctx, chains, cabi.ENTRY_SPECTRUM, memory, d_in, d_out, cabi.OUT_I16_PLANAR)
+        ctx.synchronize()
+        ctx.d2h(pcm, d_out)
+        ctx.device_free(d_in)
+        ctx.device_free(d_out)
+    want, fin = oracle_batch(oracle, spec)
+    assert any(np.any(np.abs(w) > 1.0) for w in want), "test should exercise the i16 clamp"
+    for s in range(S):
+        assert chains[s].n_samples == (P - 1) * 1024
+        assert np.array_equal(pcm[s][:, : (P - 1) * 1024], oracle.quantise_i16(want[s])), s
+        assert bits_equal(pwrs[s].data(), fin[s])
+
+
+@pytest.mark.parametrize("memory,fmt", [(cabi.MEM_HOST, "f32"), (cabi.MEM_DEVICE, "f32"), (cabi.MEM_HOST, "i16")])
+def test_residue_entry_long_batch_uses_prologue_plus_fused(ctx, oracle, memory, fmt):
+    """Full packets (coupling + floor-1 + multiply) in uniform long batches: k_prologue forms the
+    spectrum, the fused kernel does IMDCT/window/OLA.  Two consecutive batches (second one overlaps
+    with the stream state)."""
+    rng = np.random.default_rng(53)
+    channels, bs0, bs1, S, P = 2, 8, 11, 5, 9
+    floors, mappings, modes = _random_packet_case(rng, channels, bs0, bs1)
+    mappings[0]["coupling"] = [(0, 1)]
+    su = make_setup(ctx, channels, bs0, bs1, modes=modes, mappings=mappings, floors=floors)
+    pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+    refs = [RefStream(oracle, channels, bs0, bs1, modes, mappings, floors) for _ in range(S)]
+    launches0 = ctx.launch_count
+    for batch in range(2):
+        res = (rng.standard_normal((S, P, channels, 1024)) * rng.integers(0, 2, (S, P, channels, 1024))).astype(np.float32)
+        kinds = np.zeros((S, P, channels), np.uint8)
+        ys = np.zeros((S, P, channels, cabi.MAX_POSTS), np.uint32)
+        want = []
+        for s in range(S):
+            parts = []
+            for p in range(P):
+                fl = []
+                for c in range(channels):
+                    mult, xs = floors[mappings[0]["floor_of_channel"][c]]
+                    fl.append(None if rng.random() < 0.1 else random_floor1_y(rng, mult, len(xs)))
+                k, y, _ = L.DecodedPacket(1, res[s, p], fl).pack()
+                kinds[s, p], ys[s, p] = k, y
+                rc, pcm = refs[s].packet(1, 1, 1, res[s, p], fl)
+                assert rc == 0
+                parts.append(pcm)
+            want.append(np.concatenate(parts, axis=1))
+        stride = P * 1024
+        chains = [L.ChainSpec(pwrs[s], np.ones(P, np.uint8), coeff_offset=s * P * channels * 1024, packet_index=s * P,
+                              out_offset=s * channels * stride, out_stride=stride) for s in range(S)]
+        dt = np.float32 if fmt == "f32" else np.int16
+        of = cabi.OUT_F32_PLANAR if fmt == "f32" else cabi.OUT_I16_PLANAR
+        pcm = np.zeros((S, channels, stride), dt)
+        if memory == cabi.MEM_HOST:
+            L.decode_chains(ctx, chains, cabi.ENTRY_RESIDUE, memory, res, pcm, of, floor_kind=kinds, floor1_y=ys)
+        else:
+            d_in, d_out = ctx.device_alloc(res.nbytes), ctx.device_alloc(pcm.nbytes)
+            ctx.h2d(d_in, res)
+            ctx.h2d(d_out, pcm)
+            L.decode_chains(ctx, chains, cabi.ENTRY_RESIDUE, memory, d_in, d_out, of, floor_kind=kinds, floor1_y=ys)
+            ctx.synchronize()
+            ctx.d2h(pcm, d_out)
+            ctx.device_free(d_in)
+            ctx.device_free(d_out)
+        for s in range(S):
+            n = want[s].shape[1]
+            assert chains[s].status == 0 and chains[s].n_samples == n
+            if fmt == "f32":
+                assert bits_equal(pcm[s][:, :n], want[s]), (batch, s, mismatch_report(pcm[s][:, :n], want[s]))
+            else:
+                assert np.array_equal(pcm[s][:, :n], oracle.quantise_i16(want[s])), (batch, s)
+            assert bits_equal(pwrs[s].data(), refs[s].pwr.data())
+    # 2 batches x (prologue + fused kernel) = 4 launches: the generic IMDCT/overlap kernels did not run
+    assert ctx.launch_count - launches0 == 4
+
+
+def test_prepared_batch_reuses_descriptors_and_replans_on_state_change(ctx, oracle):
+    """lwb_plan_*: same results as lwb_decode_chains across state transitions (empty -> history),
+    a reset of one stream in between (forces a re-plan), and many steady-state executions."""
+    rng = np.random.default_rng(57)
+    S, P, C = 6, 9, 2
+    su = make_setup(ctx, C, 8, 11)
+    pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+    refs = [oracle.Pwr(C, 11) for _ in range(S)]
+    spec = np.zeros((S, P, C, 1024), np.float32)
+    stride = P * 1024
+    pcm = np.zeros((S, C, stride), np.float32)
+    d_in, d_out = ctx.device_alloc(spec.nbytes), ctx.device_alloc(pcm.nbytes)
+    chains = [L.ChainSpec(pwrs[s], np.ones(P, np.uint8), coeff_offset=s * P * C * 1024, out_offset=s * C * stride,
+                          out_stride=stride) for s in range(S)]
+    batch = L.Batch(ctx, chains, cabi.ENTRY_SPECTRUM, cabi.MEM_DEVICE, d_in, d_out, cabi.OUT_F32_PLANAR)
+    for it in range(6):
+        spec[:] = (rng.standard_normal(spec.shape) * 0.05).astype(np.float32)
+        if it == 3:
+            pwrs[2].reset()
+            refs[2].reset()
+        ctx.h2d(d_in, spec)
+        ctx.h2d(d_out, np.zeros_like(pcm))
+        batch.run()
+        ctx.synchronize()
+        ctx.d2h(pcm, d_out)
+        batch.collect()
+        for s in range(S):
+            parts = []
+            for p in range(P):
+                rc, o = oracle.synth_spectrum(8, 11, 1, 1, 1, spec[s, p], refs[s])
+                assert rc == 0
+                parts.append(o)
+            want = np.concatenate(parts, axis=1)
+            assert chains[s].n_samples == want.shape[1] and chains[s].status == 0, (it, s)
+            assert bits_equal(pcm[s][:, : want.shape[1]], want), (it, s)
+            assert bits_equal(pwrs[s].data(), refs[s].data())
+    batch.close()
+    ctx.device_free(d_in)
+    ctx.device_free(d_out)
