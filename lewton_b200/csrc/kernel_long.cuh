@@ -480,10 +480,10 @@ LWB_HD void step8_ola(V b0, V b1, V wlo, V whi, V Oj, V Ej, V prev_lo, V prev_hi
 #define LWB_LONG_NB 1
 #endif
 #ifndef LWB_LONG_WARPS
-#define LWB_LONG_WARPS 12
+#define LWB_LONG_WARPS 8
 #endif
 #ifndef LWB_LONG_RING
-#define LWB_LONG_RING (LWB_LONG_NB == 2 ? 2 : 3)
+#define LWB_LONG_RING (LWB_LONG_NB == 2 ? 2 : 5)
 #endif
 constexpr int kLongNB = LWB_LONG_NB;           // blocks (runs) a warp transforms in lockstep
 constexpr int kLongWarps = LWB_LONG_WARPS;     // warps per CTA, one CTA per SM
@@ -537,15 +537,17 @@ __device__ __forceinline__ void lds_eo(uint32_t addr, float &e, float &o)
 
 // Twiddle residency: pack slots [kTwReg0, kTwReg1) live in registers for the whole kernel, the
 // rest is read from the CTA's shared copy of the pack when used (compile-time choice per slot).
-// Default (measured best on B200, profiles/): one block per warp, 12 warps, step-2 / stage-0 /
-// stage-1 twiddles resident (slots 16..29), everything else fetched per block -- 156 registers,
-// no spills.  Two blocks per warp (NB = 2) doubles the loop body past the instruction cache and
-// measured 2x slower; 16 warps with no resident twiddles is shared-memory bound.
+// Default (measured best on B200, profiles/variants_r1*.log): one block per warp, 8 warps per SM
+// (2 per scheduler, 242 registers, no spills), a 5-tile ring, phase A / B / step-7 twiddles resident
+// (slots 0..52) and the step-8 / window pairs fetched per block: 0.745 of the measured HBM peak.
+// 12 warps x 164 registers with slots 16..29 resident: 0.734; 16 warps x 128 registers, nothing
+// resident: 0.700; scalar instead of packed FP: -8 %; two blocks per warp (NB = 2) doubles the loop
+// body past the instruction cache: 2x slower.
 #ifndef LWB_TW_REG0
-#define LWB_TW_REG0 (LWB_LONG_NB == 2 ? 0 : 16)
+#define LWB_TW_REG0 0
 #endif
 #ifndef LWB_TW_REG1
-#define LWB_TW_REG1 (LWB_LONG_NB == 2 ? 0 : 30)
+#define LWB_TW_REG1 (LWB_LONG_NB == 2 ? 0 : 53)
 #endif
 constexpr int kTwReg0 = LWB_TW_REG0;
 constexpr int kTwReg1 = LWB_TW_REG1;

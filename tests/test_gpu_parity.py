@@ -558,3 +558,43 @@ def test_prepared_batch_reuses_descriptors_and_replans_on_state_change(ctx, orac
     batch.close()
     ctx.device_free(d_in)
     ctx.device_free(d_out)
+
+
+def test_full_bench_size_exact_by_replication(ctx, oracle):
+    """BASELINE full size (4096 stereo streams x 16 long packets per step, 1 GiB of I/O): the batch
+    is 512 copies of 8 distinct base streams, so every one of the 4096 outputs must be bit-identical
+    to the oracle's output for its base stream -- an exact check at full size at 1/512 of the oracle
+    cost ("checksum of checksums").  Two steps: fresh streams, then with history."""
+    rng = np.random.default_rng(61)
+    S, P, C, B = 4096, 16, 2, 8
+    su = make_setup(ctx, C, 8, 11)
+    pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+    stride = P * 1024
+    d_in, d_out = ctx.device_alloc(S * P * C * 1024 * 4), ctx.device_alloc(S * C * stride * 4)
+    chains = [L.ChainSpec(pwrs[s], np.ones(P, np.uint8), coeff_offset=s * P * C * 1024, out_offset=s * C * stride,
+                          out_stride=stride) for s in range(S)]
+    batch = L.Batch(ctx, chains, cabi.ENTRY_SPECTRUM, cabi.MEM_DEVICE, d_in, d_out, cabi.OUT_F32_PLANAR)
+    refs = [oracle.Pwr(C, 11) for _ in range(B)]
+    pcm = np.zeros((S, C, stride), np.float32)
+    for step in range(2):
+        base = (rng.standard_normal((B, P, C, 1024)) * 1e-2).astype(np.float32)
+        spec = np.ascontiguousarray(np.tile(base, (S // B, 1, 1, 1)))          # stream s uses base s % B
+        ctx.h2d(d_in, spec)
+        ctx.h2d(d_out, np.zeros_like(pcm))
+        batch.run()
+        ctx.synchronize()
+        ctx.d2h(pcm, d_out)
+        want = []
+        for b in range(B):
+            parts = [oracle.synth_spectrum(8, 11, 1, 1, 1, base[b, p], refs[b])[1] for p in range(P)]
+            want.append(np.concatenate(parts, axis=1))
+        n = want[0].shape[1]
+        assert n == (P - 1 + step) * 1024
+        got = pcm[:, :, :n].reshape(S // B, B, C, n)
+        for b in range(B):
+            assert np.array_equal(got[:, b].view(np.uint32), np.broadcast_to(want[b].view(np.uint32), (S // B, C, n))), (step, b)
+    for s in (0, 1, 7, 4095):
+        assert bits_equal(pwrs[s].data(), refs[s % B].data())
+    batch.close()
+    ctx.device_free(d_in)
+    ctx.device_free(d_out)
