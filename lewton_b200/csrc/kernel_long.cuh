@@ -507,13 +507,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
+    // try_wait suspends the warp until the phase completes or the hint (ns) expires, so a blocked
+    // warp costs the scheduler almost no issue slots
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(200000u) : "memory");
 }
 // 1-D TMA: global -> shared, completion counted on the mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
