@@ -12,7 +12,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liblewton_b200.so")
-SOURCES = ["lwb_api.cu", "tables_host.cpp", "lwb_common.h", "kernels_generic.cuh", "kernel_long.cuh", "kernel_long_ws.cuh",
+SOURCES = ["lwb_api.cu", "tables_host.cpp", "lwb_common.h", "kernels_generic.cuh", "kernel_long.cuh",
            "floor1_inverse_db.inc", "Makefile"]
 
 

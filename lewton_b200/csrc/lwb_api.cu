@@ -15,7 +15,6 @@
 #include <vector>
 
 #include "kernel_long.cuh"
-#include "kernel_long_ws.cuh"
 #include "kernels_generic.cuh"
 #include "lwb_common.h"
 
@@ -47,7 +46,6 @@ struct lwb_ctx {
     int runs_par = 0;
     uint32_t ticket_next = 0;
     uint64_t state_gen = 1;        // bumped whenever any stream's (has, len) changes: plans key on it
-    bool use_ws = true;            // warp-specialised fused kernel (kernel_long_ws.cuh); LWB_LONG_KERNEL=mono selects k_long
     std::string err;
     uint64_t launches = 0;
     // grow-only device arenas
@@ -189,9 +187,6 @@ extern "C" int lwb_ctx_create(int device, lwb_ctx **out)
         if (mb >= 1) ctx->x_cap_elems = (size_t)mb << 18;
     }
     long_kernel_configure();
-    long_ws_configure();
-    if (const char *e = getenv("LWB_LONG_KERNEL")) ctx->use_ws = std::strcmp(e, "mono") != 0;
-    if (kLongNB != 1) ctx->use_ws = false;
     *out = ctx;
     return LWB_OK;
 }
@@ -856,7 +851,7 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
         o_hi = std::max(o_hi, c->out_offset + (uint64_t)(C - 1) * c->out_stride + c->n_samples);
     }
     if (!chan_chains) return LWB_OK;
-    const size_t warp_slots = (size_t)ctx->sm_count * (ctx->use_ws ? kWsPairs : kLongWarps * kLongNB);
+    const size_t warp_slots = (size_t)ctx->sm_count * kLongWarps * kLongNB;
     size_t target_runs = warp_slots * 4;                   // ~4 groups per warp evens out the tail
     if (const char *e = getenv("LWB_LONG_TARGET_RUNS")) target_runs = (size_t)atol(e);
     const size_t min_run = 8;                              // packets per run below which a cut costs > 12%
@@ -1004,11 +999,8 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
         if (ctx->ticket_next % kTicketPool == 0)
             CU(ctx, cudaMemsetAsync(ctx->ticket.p, 0, kTicketPool * sizeof(unsigned int), ctx->stream));
         unsigned int *ticket = (unsigned int *)ctx->ticket.p + (ctx->ticket_next++ % kTicketPool);
-        const int lrc = ctx->use_ws
-                            ? long_ws_launch(ctx->stream, d_runs_base + cp.r0, (uint32_t)cp.nr, pack, ticket, ctx->sm_count, i16)
-                            : long_launch(ctx->stream, d_runs_base + cp.r0, (uint32_t)(cp.nr / kLongNB), pack, ticket,
-                                          ctx->sm_count, i16);
-        if (lrc) return fail(ctx, LWB_ERR_CUDA, "long kernel launch", cudaGetLastError());
+        if (long_launch(ctx->stream, d_runs_base + cp.r0, (uint32_t)(cp.nr / kLongNB), pack, ticket, ctx->sm_count, i16))
+            return fail(ctx, LWB_ERR_CUDA, "long kernel launch", cudaGetLastError());
         ctx->launches++;
         if (host && cp.ko_hi > cp.ko_lo) {
             CU(ctx, cudaEventRecord(ctx->ev_done[k], ctx->stream));
@@ -1251,10 +1243,8 @@ extern "C" int lwb_plan_execute(lwb_plan *p)
         if (ctx->ticket_next % kTicketPool == 0)
             CU(ctx, cudaMemsetAsync(ctx->ticket.p, 0, kTicketPool * sizeof(unsigned int), ctx->stream));
         unsigned int *ticket = (unsigned int *)ctx->ticket.p + (ctx->ticket_next++ % kTicketPool);
-        const int lrc = ctx->use_ws
-                            ? long_ws_launch(ctx->stream, (const LongRun *)p->runs.p, p->n_groups, p->pack, ticket, ctx->sm_count, p->i16)
-                            : long_launch(ctx->stream, (const LongRun *)p->runs.p, p->n_groups, p->pack, ticket, ctx->sm_count, p->i16);
-        if (lrc) return fail(ctx, LWB_ERR_CUDA, "long kernel launch", cudaGetLastError());
+        if (long_launch(ctx->stream, (const LongRun *)p->runs.p, p->n_groups, p->pack, ticket, ctx->sm_count, p->i16))
+            return fail(ctx, LWB_ERR_CUDA, "long kernel launch", cudaGetLastError());
         ctx->launches++;
         return LWB_OK;
     }
