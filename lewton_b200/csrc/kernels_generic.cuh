@@ -246,41 +246,34 @@ __device__ __forceinline__ void d_iter_54(float *z7)
 
 constexpr int kImdctThreads = 128;
 
-// grid = (packets, max channels); dynamic smem = n floats (U and V halves).
-// in: spectrum [channels][n/2] at coeff_off; out: x [channels][n] at x_off.
-__global__ void __launch_bounds__(kImdctThreads)
-k_imdct(const DevPacket *__restrict__ pkts, const float *__restrict__ spec, float *__restrict__ xout)
+// Steps 0-7 of inverse_mdct (imdct.rs:337-580) for one block, cooperatively by NT threads (`tid` in
+// [0, NT)) that `sync()` synchronises (a warp, a named-barrier group, or the CTA).
+// X: n/2 spectrum coefficients (global or shared; may alias U); on return V holds the post-step-7
+// buffer that step 8 reads.  Literal schedule, including the reference's behaviour for n = 64/128.
+template <class Sync>
+__device__ __forceinline__ void d_imdct_to_v(const DevTables &tb, int n, const float *X, float *U, float *V, int tid,
+                                             int NT, Sync sync)
 {
-    const DevPacket &p = pkts[blockIdx.x];
-    const int ch = blockIdx.y;
-    if (ch >= p.channels) return;
-    const DevTables &tb = p.setup->tab[p.blockflag];
-    const int n = p.n, n2 = n >> 1, n4 = n >> 2, n8 = n >> 3;
+    const int n2 = n >> 1, n4 = n >> 2, n8 = n >> 3;
     const int ld = tb.bs;
     const float *__restrict__ A = tb.a;
-    const float *__restrict__ B = tb.b;
     const float *__restrict__ Cc = tb.c;
-    const float *__restrict__ X = spec + p.coeff_off + (size_t)ch * n2;
-    float *__restrict__ out = xout + p.x_off + (size_t)ch * n;
-    extern __shared__ float smem[];
-    float *U = smem, *V = smem + n2;
-    const int tid = threadIdx.x;
 
     // step 0 (imdct.rs:337-371): V <- rotated, reflected spectrum
-    for (int t = tid; t < n8; t += kImdctThreads) {
+    for (int t = tid; t < n8; t += NT) {
         const float x0 = X[4 * t], x2 = X[4 * t + 2];
         const float a0 = A[2 * t], a1 = A[2 * t + 1];
-        V[n2 - 1 - 2 * t] = __fsub_rn(__fmul_rn(x0, a0), __fmul_rn(x2, a1));
-        V[n2 - 2 - 2 * t] = __fadd_rn(__fmul_rn(x0, a1), __fmul_rn(x2, a0));
         const int d = n4 - 2 - 2 * t, ao = n4 + 2 * t, e = n2 - 3 - 4 * t;
         const float ne2 = -X[e + 2], ne0 = -X[e];
         const float b0 = A[ao], b1 = A[ao + 1];
+        V[n2 - 1 - 2 * t] = __fsub_rn(__fmul_rn(x0, a0), __fmul_rn(x2, a1));
+        V[n2 - 2 - 2 * t] = __fadd_rn(__fmul_rn(x0, a1), __fmul_rn(x2, a0));
         V[d + 1] = __fsub_rn(__fmul_rn(ne2, b0), __fmul_rn(ne0, b1));
         V[d] = __fadd_rn(__fmul_rn(ne2, b1), __fmul_rn(ne0, b0));
     }
-    __syncthreads();
+    sync();
     // step 2 (imdct.rs:385-430): U <- V
-    for (int t = tid; t < (n >> 4); t += kImdctThreads) {
+    for (int t = tid; t < (n >> 4); t += NT) {
         const int ao = n2 - 8 - 8 * t, hi = n4 + 4 * t, lo = 4 * t;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -294,7 +287,7 @@ k_imdct(const DevPacket *__restrict__ pkts, const float *__restrict__ spec, floa
             U[lo + o] = __fadd_rn(__fmul_rn(v0, w0), __fmul_rn(v1, w1));
         }
     }
-    __syncthreads();
+    sync();
     // step 3 (imdct.rs:445-477), literal schedule: stage 0, stage 1 (a no-op for n = 64),
     // stages 2..ld-7.  For n = 64/128 this overlaps what ld654 does again below -- the
     // reference's behaviour, kept bit for bit.
@@ -302,17 +295,17 @@ k_imdct(const DevPacket *__restrict__ pkts, const float *__restrict__ spec, floa
         if (l == 1 && n < 128) continue;          // r_loop(lim = n >> 5 = 2): lim >> 2 == 0 iterations
         const int k0 = n >> (l + 2), k1 = 1 << (l + 3);
         const int rbits = ld - l - 4;             // r < n >> (l+4)
-        for (int q = tid; q < n8; q += kImdctThreads) {
+        for (int q = tid; q < n8; q += NT) {
             const int r = q & ((1 << rbits) - 1), s = q >> rbits;
             const int i = n2 - 1 - k0 * s - 2 * r;
             d_bfly(U, i, i - (k0 >> 1), A[r * k1], A[r * k1 + 1]);
         }
-        __syncthreads();
+        sync();
     }
     // imdct.rs:234-288 (ld654): last three stages per 16-float group
     {
         const float a2 = A[n >> 3];
-        for (int g = tid; g < (n >> 5); g += kImdctThreads) {
+        for (int g = tid; g < (n >> 5); g += NT) {
             float *z = U + (n2 - 1 - 16 * g);
             float k00, k11;
             k00 = __fsub_rn(z[0], z[-8]);   k11 = __fsub_rn(z[-1], z[-9]);
@@ -333,18 +326,18 @@ k_imdct(const DevPacket *__restrict__ pkts, const float *__restrict__ spec, floa
             d_iter_54(z - 8);
         }
     }
-    __syncthreads();
+    sync();
     // steps 4-6 (imdct.rs:490-528): bit-reverse shuffle U -> V
-    for (int q = tid; q < (n >> 4); q += kImdctThreads) {
+    for (int q = tid; q < (n >> 4); q += NT) {
         const int d0 = n4 - 4 - 4 * q, d1 = n2 - 4 - 4 * q;
         int k4 = tb.bitrev[2 * q];
         V[d1 + 3] = U[k4 + 0]; V[d1 + 2] = U[k4 + 1]; V[d0 + 3] = U[k4 + 2]; V[d0 + 2] = U[k4 + 3];
         k4 = tb.bitrev[2 * q + 1];
         V[d1 + 1] = U[k4 + 0]; V[d1 + 0] = U[k4 + 1]; V[d0 + 1] = U[k4 + 2]; V[d0 + 0] = U[k4 + 3];
     }
-    __syncthreads();
+    sync();
     // step 7 (imdct.rs:533-580), in place on V
-    for (int t = tid; t < (n >> 4); t += kImdctThreads) {
+    for (int t = tid; t < (n >> 4); t += NT) {
         const int d = 4 * t, e = n2 - 4 - 4 * t, co = 4 * t;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -362,7 +355,26 @@ k_imdct(const DevPacket *__restrict__ pkts, const float *__restrict__ spec, floa
             V[ee + 1] = __fsub_rn(b1, b3);
         }
     }
-    __syncthreads();
+    sync();
+}
+
+// grid = (packets, max channels); dynamic smem = n floats (U and V halves).
+// in: spectrum [channels][n/2] at coeff_off; out: x [channels][n] at x_off.
+__global__ void __launch_bounds__(kImdctThreads)
+k_imdct(const DevPacket *__restrict__ pkts, const float *__restrict__ spec, float *__restrict__ xout)
+{
+    const DevPacket &p = pkts[blockIdx.x];
+    const int ch = blockIdx.y;
+    if (ch >= p.channels) return;
+    const DevTables &tb = p.setup->tab[p.blockflag];
+    const int n = p.n, n2 = n >> 1, n4 = n >> 2;
+    const float *__restrict__ B = tb.b;
+    const float *__restrict__ X = spec + p.coeff_off + (size_t)ch * n2;
+    float *__restrict__ out = xout + p.x_off + (size_t)ch * n;
+    extern __shared__ float smem[];
+    float *U = smem, *V = smem + n2;
+    const int tid = threadIdx.x;
+    d_imdct_to_v(tb, n, X, U, V, tid, kImdctThreads, [] { __syncthreads(); });
     // step 8 + decode (imdct.rs:589-658)
     for (int m = tid; m < n4; m += kImdctThreads) {
         const int ee = n2 - 2 - 2 * m;            // V/B pair consumed for output index m

@@ -16,6 +16,7 @@
 
 #include "kernel_long.cuh"
 #include "kernels_generic.cuh"
+#include "kernel_chain.cuh"
 #include "lwb_common.h"
 
 namespace lwb {
@@ -49,7 +50,7 @@ struct lwb_ctx {
     std::string err;
     uint64_t launches = 0;
     // grow-only device arenas
-    DevBuf coeffs, dense, pcm, spec, x, desc, kinds, ys, chains, ticket;
+    DevBuf coeffs, dense, pcm, spec, x, desc, kinds, ys, chains, ticket, cdesc, cbytes;
     // pinned staging for descriptors
     void *h_desc = nullptr;
     size_t h_desc_cap = 0;
@@ -197,7 +198,8 @@ extern "C" void lwb_ctx_destroy(lwb_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->coeffs, &ctx->dense, &ctx->pcm, &ctx->spec, &ctx->x, &ctx->desc,
-                      &ctx->kinds, &ctx->ys, &ctx->chains, &ctx->ticket, &ctx->runs_buf[0], &ctx->runs_buf[1]})
+                      &ctx->kinds, &ctx->ys, &ctx->chains, &ctx->ticket, &ctx->runs_buf[0], &ctx->runs_buf[1],
+                      &ctx->cdesc, &ctx->cbytes})
         if (b->p) cudaFree(b->p);
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
     cudaStreamDestroy(ctx->stream);
@@ -791,6 +793,32 @@ static void long_runs_of(const LongItem &it, size_t cuts, const float *coeffs, u
     }
 }
 
+// Every packet a long block of the fast blocksize with long neighbours, every stream empty or
+// holding a 1024-sample right half, arenas aligned: what the fused kernel takes.
+static bool batch_is_uniform_long(lwb_ctx *ctx, const lwb_chain *chains, size_t n_chains, const lwb_batch_io *io)
+{
+    if (io->out_format != LWB_OUT_F32_PLANAR && io->out_format != LWB_OUT_I16_PLANAR) return false;
+    const float *pack = nullptr;
+    for (size_t i = 0; i < n_chains; i++) {
+        const lwb_chain *c = &chains[i];
+        if (!c->stream || c->stream->ctx != ctx || (c->n_packets && !c->mode_numbers)) return false;
+        const lwb_stream *s = c->stream;
+        const lwb_setup *su = s->setup;
+        if (su->bs1 != kLongBs || !su->host.tab[1].pack) return false;
+        if (pack && pack != su->host.tab[1].pack) return false;
+        pack = su->host.tab[1].pack;
+        if ((c->out_offset & 3) || (c->out_stride & 3) || (c->coeff_offset & 3)) return false;
+        if (s->has && s->plen != (uint32_t)kLongN2) return false;
+        for (uint32_t k = 0; k < c->n_packets; k++) {
+            const uint8_t m = c->mode_numbers[k];
+            if (m >= su->n_modes || !su->host.mode_blockflag[m]) return false;
+            if (c->prev_window_flags && !c->prev_window_flags[k]) return false;
+            if (c->next_window_flags && !c->next_window_flags[k]) return false;
+        }
+    }
+    return true;
+}
+
 // `spectrum_dev`: when non-null the spectrum has already been formed on the device (residue entry:
 // k_prologue wrote it to ctx->spec, element offset `spectrum_base` = its [0]); the input side of the
 // batch is then neither validated as a spectrum entry nor copied.
@@ -1077,6 +1105,205 @@ static int run_prologue_all(lwb_ctx *ctx, std::vector<PlanChain> &plan, const De
                   ar.coeffs, ar.dense, ar.kinds, ar.ys, (float *)ctx->spec.p);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Chain kernel path (kernel_chain.cuh): everything the fused long-block kernel does not take,
+// as long as channels <= 8 and the per-channel buffers fit in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int ENTRY>
+static int launch_chain(lwb_ctx *ctx, int fmt, unsigned n_chains, unsigned warps, size_t smem, const ChainDesc *d,
+                        const uint8_t *bytes, const float *coeffs, const float *dense, const uint8_t *kinds,
+                        const uint32_t *ys, void *pcm, int n1max, int wpc)
+{
+#define LWB_CHAIN_CASE(F)                                                                                    \
+    case F:                                                                                                  \
+        if (wpc == 1) {                                                                                      \
+            cudaFuncSetAttribute(k_chain<F, ENTRY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            return launch(ctx, k_chain<F, ENTRY, false>, dim3(n_chains), dim3(warps * 32), smem, d, bytes, coeffs, dense, \
+                          kinds, ys, pcm, n1max, wpc);                                                        \
+        }                                                                                                    \
+        cudaFuncSetAttribute(k_chain<F, ENTRY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        return launch(ctx, k_chain<F, ENTRY, true>, dim3(n_chains), dim3(warps * 32), smem, d, bytes, coeffs, dense, kinds, \
+                      ys, pcm, n1max, wpc);
+    switch (fmt) {
+        LWB_CHAIN_CASE(LWB_OUT_F32_PLANAR)
+        LWB_CHAIN_CASE(LWB_OUT_I16_PLANAR)
+        LWB_CHAIN_CASE(LWB_OUT_F32_INTERLEAVED)
+        LWB_CHAIN_CASE(LWB_OUT_I16_INTERLEAVED)
+    }
+#undef LWB_CHAIN_CASE
+    return LWB_ERR_INVALID;
+}
+
+static int try_chain(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch,
+                     bool *handled)
+{
+    *handled = false;
+    if (const char *e = getenv("LWB_FORCE_GENERIC"))
+        if (std::strcmp(e, "1") == 0) return LWB_OK;          // "1": the four-kernel path; "2": no fused kernel only
+    const bool residue = io->entry == LWB_ENTRY_RESIDUE;
+    const bool planar = is_planar(io->out_format);
+    const size_t esz = elem_size(io->out_format);
+    unsigned maxc = 1;
+    int n1max = 64;
+    size_t total_packets = 0;
+    for (size_t i = 0; i < n_chains; i++) {
+        const lwb_chain *c = &chains[i];
+        if (!c->stream || c->stream->ctx != ctx || (c->n_packets && !c->mode_numbers)) return LWB_OK;   // generic path reports it
+        const lwb_setup *su = c->stream->setup;
+        if (su->channels > 8) return LWB_OK;
+        maxc = std::max<unsigned>(maxc, su->channels);
+        n1max = std::max(n1max, 1 << su->bs1);
+        total_packets += c->n_packets;
+    }
+    const size_t smem = (size_t)maxc * (n1max + n1max / 2) * 4 + 8 * (LWB_MAX_POSTS + 1) * 2 * 2 + 64;
+    if (smem > 200 * 1024) return LWB_OK;
+    // warps per channel: one per 1024 samples of the largest block, at most 32 warps per CTA
+    int wpc = std::max(1, std::min(8, n1max / 1024));
+    while (wpc > 1 && (unsigned)wpc * maxc > 32) wpc >>= 1;
+    if (residue && !io->floor_kind) return fail(ctx, LWB_ERR_INVALID, "residue entry needs floor_kind");
+    *handled = true;
+
+    // light walk of every chain: geometry, OLA guard, output size (audio.rs:1056-1073, 1083-1154)
+    int rc;
+    Staging *st;
+    const size_t desc_bytes = n_chains * sizeof(ChainDesc), byte_bytes = total_packets * 3 + 16;
+    if ((rc = acquire_staging(ctx, desc_bytes + byte_bytes, &st))) return rc;
+    ChainDesc *hd = (ChainDesc *)st->h;
+    uint8_t *hb = (uint8_t *)st->h + desc_bytes;
+    uint64_t c_lo = ~0ull, c_hi = 0, o_lo = ~0ull, o_hi = 0, r_lo = ~0ull, r_hi = 0;
+    int uniform_c = -1;
+    bool need_dense = false;
+    size_t boff = 0, n_launch = 0;
+    struct End { lwb_stream *s; bool has; uint32_t plen; bool touched; };
+    std::vector<End> ends(n_chains);
+    for (size_t i = 0; i < n_chains; i++) {
+        lwb_chain *c = &chains[i];
+        lwb_stream *s = c->stream;
+        const lwb_setup *su = s->setup;
+        if (s->busy_epoch == epoch) return fail(ctx, LWB_ERR_INVALID, "a stream appears in two chains of one batch");
+        s->busy_epoch = epoch;
+        const unsigned C = su->channels;
+        if (residue) {
+            if (uniform_c < 0) uniform_c = (int)C;
+            if (uniform_c != (int)C) return fail(ctx, LWB_ERR_INVALID, "residue batches need one channel count");
+        }
+        bool has = s->has, clear_after = false;
+        uint32_t plen = s->plen;
+        uint64_t coeff = c->coeff_offset, pos = 0;
+        uint32_t done = 0;
+        c->status = LWB_OK;
+        for (uint32_t k = 0; k < c->n_packets; k++) {
+            Geom g;
+            int grc = geometry(su, c->mode_numbers[k], c->prev_window_flags ? c->prev_window_flags[k] : 1,
+                               c->next_window_flags ? c->next_window_flags[k] : 1, &g);
+            if (grc) { c->status = grc; break; }
+            if (has) {
+                const uint32_t slope_len = 1u << ((g.slope_sel ? su->bs1 : su->bs0) - 1);
+                if (slope_len < plen) { c->status = LWB_ERR_BAD_FORMAT; clear_after = true; break; }   // audio.rs:1107-1111
+                if (g.ls + plen > g.n) { c->status = LWB_ERR_MISMATCH; break; }
+                pos += g.rs - g.ls;
+            }
+            hb[boff + 3 * k] = c->mode_numbers[k];
+            hb[boff + 3 * k + 1] = c->prev_window_flags ? c->prev_window_flags[k] : 1;
+            hb[boff + 3 * k + 2] = c->next_window_flags ? c->next_window_flags[k] : 1;
+            coeff += (uint64_t)C * (g.n >> 1);
+            has = true;
+            plen = g.re - g.rs;
+            done++;
+        }
+        c->packets_done = done;
+        c->n_samples = (uint32_t)pos;
+        ends[i] = End{s, clear_after ? false : has, clear_after ? 0u : plen, done > 0 || clear_after};
+        if (!done) continue;
+        if (planar && c->out_stride < pos) return fail(ctx, LWB_ERR_BUFFER, "chain: out_stride smaller than the samples produced");
+        ChainDesc &d = hd[n_launch++];
+        std::memset(&d, 0, sizeof(d));
+        d.setup = su->d_setup;
+        d.state = s->d_state;
+        d.coeff_off = c->coeff_offset;
+        d.out_off = c->out_offset;
+        d.out_stride = c->out_stride;
+        d.pkt_index = c->packet_index;
+        d.n_packets = done;
+        d.byte_off = (uint32_t)boff;
+        d.state_stride = (uint32_t)state_stride(su);
+        d.plen0 = (uint16_t)s->plen;
+        d.has0 = s->has;
+        d.channels = (uint8_t)C;
+        boff += (size_t)done * 3;
+        c_lo = std::min(c_lo, c->coeff_offset);
+        c_hi = std::max(c_hi, coeff);
+        const uint64_t ext = planar ? (uint64_t)(C - 1) * c->out_stride + pos : pos * C;
+        o_lo = std::min(o_lo, c->out_offset);
+        o_hi = std::max(o_hi, c->out_offset + ext);
+        if (residue) {
+            r_lo = std::min(r_lo, c->packet_index);
+            r_hi = std::max<uint64_t>(r_hi, c->packet_index + done);
+            for (uint64_t r = c->packet_index * C; r < (c->packet_index + done) * C; r++) {
+                const uint8_t kd = io->floor_kind[r];
+                if (kd > LWB_FLOOR_DENSE) return fail(ctx, LWB_ERR_INVALID, "floor_kind out of range");
+                if (kd == LWB_FLOOR_ONE && !io->floor1_y) return fail(ctx, LWB_ERR_INVALID, "floor1_y missing");
+                if (kd == LWB_FLOOR_DENSE) need_dense = true;
+            }
+        }
+    }
+    if (need_dense && !io->dense_floor) return fail(ctx, LWB_ERR_INVALID, "dense_floor missing");
+    if (n_launch) {
+        const bool host = io->memory == LWB_MEM_HOST;
+        const float *d_coeffs = io->coeffs, *d_dense = io->dense_floor;
+        char *d_pcm = (char *)io->pcm;
+        cudaStream_t sm = ctx->stream;
+        if (host) {
+            // arenas are addressed with the caller's element offsets: bias the device pointers instead of the descriptors
+            if ((rc = ensure(ctx, ctx->coeffs, (size_t)(c_hi - c_lo) * 4))) return rc;
+            if (o_hi > o_lo && (rc = ensure(ctx, ctx->pcm, (size_t)(o_hi - o_lo) * esz))) return rc;
+            CU(ctx, cudaMemcpyAsync(ctx->coeffs.p, io->coeffs + c_lo, (size_t)(c_hi - c_lo) * 4, cudaMemcpyHostToDevice, sm));
+            d_coeffs = (const float *)ctx->coeffs.p - c_lo;
+            if (need_dense) {
+                if ((rc = ensure(ctx, ctx->dense, (size_t)(c_hi - c_lo) * 4))) return rc;
+                CU(ctx, cudaMemcpyAsync(ctx->dense.p, io->dense_floor + c_lo, (size_t)(c_hi - c_lo) * 4, cudaMemcpyHostToDevice, sm));
+                d_dense = (const float *)ctx->dense.p - c_lo;
+            }
+            d_pcm = (char *)ctx->pcm.p - o_lo * esz;
+        }
+        const uint8_t *d_kinds = nullptr;
+        const uint32_t *d_ys = nullptr;
+        if (residue) {
+            const size_t rows = (size_t)(r_hi - r_lo) * uniform_c;
+            if ((rc = ensure(ctx, ctx->kinds, rows))) return rc;
+            CU(ctx, cudaMemcpyAsync(ctx->kinds.p, io->floor_kind + r_lo * uniform_c, rows, cudaMemcpyHostToDevice, sm));
+            d_kinds = (const uint8_t *)ctx->kinds.p - r_lo * uniform_c;
+            if (io->floor1_y) {
+                if ((rc = ensure(ctx, ctx->ys, rows * LWB_MAX_POSTS * 4))) return rc;
+                CU(ctx, cudaMemcpyAsync(ctx->ys.p, io->floor1_y + r_lo * uniform_c * LWB_MAX_POSTS, rows * LWB_MAX_POSTS * 4,
+                                        cudaMemcpyHostToDevice, sm));
+                d_ys = (const uint32_t *)ctx->ys.p - r_lo * uniform_c * LWB_MAX_POSTS;
+            }
+        }
+        if ((rc = ensure(ctx, ctx->cdesc, n_launch * sizeof(ChainDesc)))) return rc;
+        if ((rc = ensure(ctx, ctx->cbytes, boff + 16))) return rc;
+        CU(ctx, cudaMemcpyAsync(ctx->cdesc.p, hd, n_launch * sizeof(ChainDesc), cudaMemcpyHostToDevice, sm));
+        CU(ctx, cudaMemcpyAsync(ctx->cbytes.p, hb, boff + 16, cudaMemcpyHostToDevice, sm));
+        CU(ctx, cudaEventRecord(st->ev, sm));
+        st->pending = true;
+        if (residue)
+            rc = launch_chain<LWB_ENTRY_RESIDUE>(ctx, io->out_format, (unsigned)n_launch, maxc * wpc, smem, (const ChainDesc *)ctx->cdesc.p,
+                                                 (const uint8_t *)ctx->cbytes.p, d_coeffs, d_dense, d_kinds, d_ys, d_pcm, n1max, wpc);
+        else
+            rc = launch_chain<LWB_ENTRY_SPECTRUM>(ctx, io->out_format, (unsigned)n_launch, maxc * wpc, smem, (const ChainDesc *)ctx->cdesc.p,
+                                                  (const uint8_t *)ctx->cbytes.p, d_coeffs, d_dense, d_kinds, d_ys, d_pcm, n1max, wpc);
+        if (rc) return rc;
+        if (host) {
+            if (o_hi > o_lo)
+                CU(ctx, cudaMemcpyAsync((char *)io->pcm + o_lo * esz, ctx->pcm.p, (size_t)(o_hi - o_lo) * esz, cudaMemcpyDeviceToHost, sm));
+            CU(ctx, cudaStreamSynchronize(sm));
+        }
+    }
+    for (auto &e : ends)
+        if (e.touched) set_stream_state(e.s, e.has, e.plen);
+    return LWB_OK;
+}
+
 static int decode_chains_impl(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, lwb_plan *prepared)
 {
     if (!ctx || (!chains && n_chains) || !io) return LWB_ERR_INVALID;
@@ -1090,8 +1317,17 @@ static int decode_chains_impl(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, 
     epoch++;
     {
         bool handled = false;
-        int rc0 = try_long(ctx, chains, n_chains, io, epoch, &handled, nullptr, 0, prepared);
+        const char *fg = getenv("LWB_FORCE_GENERIC");
+        const bool no_fused = fg && std::strcmp(fg, "2") == 0;
+        int rc0 = no_fused ? LWB_OK : try_long(ctx, chains, n_chains, io, epoch, &handled, nullptr, 0, prepared);
         if (rc0 || handled) return rc0;
+        // residue-entry batches of uniform long blocks go prologue + fused kernel (below); everything
+        // else that fits goes to the chain kernel
+        const bool residue_long = !no_fused && !fg && io->entry == LWB_ENTRY_RESIDUE && batch_is_uniform_long(ctx, chains, n_chains, io);
+        if (!residue_long) {
+            rc0 = try_chain(ctx, chains, n_chains, io, epoch, &handled);
+            if (rc0 || handled) return rc0;
+        }
     }
     const bool residue = io->entry == LWB_ENTRY_RESIDUE;
     const bool planar = is_planar(io->out_format);

@@ -273,7 +273,8 @@ def oracle_batch(oracle, spec, states=None):
 
 
 @pytest.mark.parametrize("memory", [cabi.MEM_HOST, cabi.MEM_DEVICE])
-@pytest.mark.parametrize("env", [None, {"LWB_FORCE_GENERIC": "1"}, {"LWB_LONG_TARGET_RUNS": "100000"}])
+@pytest.mark.parametrize("env", [None, {"LWB_FORCE_GENERIC": "1"}, {"LWB_FORCE_GENERIC": "2"},
+                                 {"LWB_LONG_TARGET_RUNS": "100000"}])
 def test_batch_long_blocks_vs_oracle(ctx, oracle, memory, env):
     """S stereo streams x P long blocks, fresh streams then a second batch that continues them;
     fused path, fused path with forced run cuts (primer packets), and the generic path."""
@@ -420,7 +421,7 @@ def test_special_values_on_gpu(ctx, oracle):
     want, fin = oracle_batch(oracle, spec)
     assert np.any((np.abs(want[0]) > 0) & (np.abs(want[0]) < 1.1e-38)), "test should exercise denormal outputs"
     assert np.any(np.isnan(want[1]))
-    for env in (None, {"LWB_FORCE_GENERIC": "1"}):
+    for env in (None, {"LWB_FORCE_GENERIC": "1"}, {"LWB_FORCE_GENERIC": "2"}):
         pwrs = [L.PreviousWindowRight(su) for _ in range(2)]
         _, pcm = run_batch(ctx, su, pwrs, spec, 4, cabi.MEM_HOST, env)
         for s in range(2):
@@ -598,3 +599,83 @@ def test_full_bench_size_exact_by_replication(ctx, oracle):
     batch.close()
     ctx.device_free(d_in)
     ctx.device_free(d_out)
+
+
+@pytest.mark.parametrize("channels,bs0,bs1,fmt,seed", [(2, 8, 11, cabi.OUT_F32_PLANAR, 70), (6, 8, 11, cabi.OUT_I16_INTERLEAVED, 71),
+                                                       (1, 6, 13, cabi.OUT_F32_INTERLEAVED, 72), (8, 7, 9, cabi.OUT_I16_PLANAR, 73)])
+def test_chain_kernel_vs_four_kernel_path_mixed_sequences(ctx, oracle, channels, bs0, bs1, fmt, seed):
+    """The chain kernel (one launch, shared-memory resident) and the four-kernel path are independent
+    schedules of the same arithmetic: bit-identical on random mixed short/long chains with full
+    packets (coupling + floor-1 / dense / unused floors), and both equal to the oracle."""
+    rng = np.random.default_rng(seed)
+    S, P = 5, 12
+    floors, mappings, modes = _random_packet_case(rng, channels, bs0, bs1)
+    su = make_setup(ctx, channels, bs0, bs1, modes=modes, mappings=mappings, floors=floors)
+    refs = [RefStream(oracle, channels, bs0, bs1, modes, mappings, floors) for _ in range(S)]
+    coeffs, dense, kinds, ys, want, seqs = [], [], [], [], [], []
+    for s in range(S):
+        bf, prev, nxt = mode_sequence(rng, P, p_short=0.45)
+        mode_ids = np.array([int(rng.choice([m for m in range(4) if modes[m][0] == b])) for b in bf], np.uint8)
+        parts = []
+        for i in range(P):
+            n2 = (1 << (bs1 if bf[i] else bs0)) // 2
+            res = (rng.standard_normal((channels, n2)) * rng.integers(0, 2, (channels, n2))).astype(np.float32)
+            mp = mappings[modes[mode_ids[i]][1]]
+            fl = []
+            for c in range(channels):
+                mult, xs = floors[mp["floor_of_channel"][c]]
+                r = rng.random()
+                fl.append(None if r < 0.15 else (rng.random(n2).astype(np.float32) if r < 0.25
+                                                 else random_floor1_y(rng, mult, len(xs))))
+            rc, pcm = refs[s].packet(int(mode_ids[i]), int(prev[i]), int(nxt[i]), res, fl)
+            assert rc == 0
+            parts.append(pcm)
+            k, y, d = L.DecodedPacket(int(mode_ids[i]), res, fl).pack()
+            coeffs.append(res.ravel())
+            dense.append((d if d is not None else np.zeros_like(res)).ravel())
+            kinds.append(k)
+            ys.append(y)
+        want.append(np.concatenate(parts, axis=1))
+        seqs.append((mode_ids, prev, nxt))
+    coeffs, dense = np.concatenate(coeffs), np.concatenate(dense)
+    kinds, ys = np.concatenate(kinds), np.concatenate(ys)
+    outs = {}
+    interleaved = fmt in (cabi.OUT_F32_INTERLEAVED, cabi.OUT_I16_INTERLEAVED)
+    dt = np.float32 if fmt in (cabi.OUT_F32_PLANAR, cabi.OUT_F32_INTERLEAVED) else np.int16
+    for name, env in (("chain", None), ("four", {"LWB_FORCE_GENERIC": "1"})):
+        pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+        chains, coeff_off, out_off = [], 0, 0
+        for s in range(S):
+            n = want[s].shape[1]
+            mode_ids, prev, nxt = seqs[s]
+            chains.append(L.ChainSpec(pwrs[s], mode_ids, prev, nxt, coeff_offset=coeff_off, packet_index=s * P,
+                                      out_offset=out_off, out_stride=0 if interleaved else n))
+            coeff_off += sum(channels * ((1 << (bs1 if modes[m][0] else bs0)) // 2) for m in mode_ids)
+            out_off += n * channels
+        pcm = np.zeros(out_off, dt)
+        old = os.environ.get("LWB_FORCE_GENERIC")
+        if env:
+            os.environ.update(env)
+        try:
+            L.decode_chains(ctx, chains, cabi.ENTRY_RESIDUE, cabi.MEM_HOST, coeffs, pcm, fmt, floor_kind=kinds, floor1_y=ys,
+                            dense_floor=dense)
+        finally:
+            if env:
+                if old is None:
+                    del os.environ["LWB_FORCE_GENERIC"]
+                else:
+                    os.environ["LWB_FORCE_GENERIC"] = old
+        outs[name] = pcm
+        pos = 0
+        for s in range(S):
+            n = want[s].shape[1]
+            assert chains[s].status == 0 and chains[s].n_samples == n, (name, s)
+            blk = pcm[pos: pos + n * channels]
+            got = blk.reshape(n, channels).T if interleaved else blk.reshape(channels, n)
+            if dt == np.float32:
+                assert bits_equal(got, want[s]), (name, s, mismatch_report(got, want[s]))
+            else:
+                assert np.array_equal(got, oracle.quantise_i16(want[s])), (name, s)
+            pos += n * channels
+            assert bits_equal(pwrs[s].data(), refs[s].pwr.data()), (name, s)
+    assert np.array_equal(outs["chain"].view(np.uint8), outs["four"].view(np.uint8))
