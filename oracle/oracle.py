@@ -121,9 +121,12 @@ class Tables:
         self.bitrev = np.ctypeslib.as_array(L.lwo_tables_bitrev(self._h), (n // 8,)).copy()
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().lwo_tables_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None) and _lib is not None:
+                _lib.lwo_tables_free(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 _tables = {}
@@ -279,9 +282,12 @@ class Pwr:
         lib().lwo_pwr_set(self._h, arr.shape[1])
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().lwo_pwr_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None) and _lib is not None:
+                _lib.lwo_pwr_free(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 def synth_spectrum(bs0, bs1, blockflag, prev_flag, next_flag, spectrum, pwr):
