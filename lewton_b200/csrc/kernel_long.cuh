@@ -55,7 +55,9 @@ struct alignas(16) LongRun {      // 48 bytes: fetched by the kernel with one 1-
     uint8_t has_prev;       // 1: packet 0 overlaps with `state`;  0: packet 0 emits nothing
     uint8_t write_state;    // 1: store the last packet's right half to `state`
     uint8_t dummy;          // 1: filler partner of an unpaired run: transformed, never stored
-    uint8_t pad[13];
+    uint8_t first_short;    // 1: packet 0 follows a short block (previous_window_flag == 0, audio.rs:1059-1065)
+    uint8_t last_short;     // 1: the last packet precedes a short block (next_window_flag == 0, audio.rs:1067-1073)
+    uint8_t pad[11];
 };
 static_assert(sizeof(LongRun) == 48, "LongRun is copied by TMA in 16-byte units");
 
@@ -580,12 +582,13 @@ struct RunCur {
     void *out;
     float *state;
     uint32_t in_stride;
-    uint32_t flags;               // bit0 has_prev, bit1 write_state, bit2 dummy
+    uint32_t flags;               // bit0 has_prev, bit1 write_state, bit2 dummy, bit3 first_short, bit4 last_short
 };
 __device__ __forceinline__ RunCur run_cur(const LongRun &r)
 {
     return RunCur{r.in, r.out, r.state, r.in_stride,
-                  (uint32_t)(r.has_prev ? 1u : 0u) | (r.write_state ? 2u : 0u) | (r.dummy ? 4u : 0u)};
+                  (uint32_t)(r.has_prev ? 1u : 0u) | (r.write_state ? 2u : 0u) | (r.dummy ? 4u : 0u) |
+                      (r.first_short ? 8u : 0u) | (r.last_short ? 16u : 0u)};
 }
 
 // samples.rs:92-103 (`Sample for i16`): x * 32768, clamp, truncate toward zero, NaN -> 0
@@ -648,6 +651,45 @@ __device__ __forceinline__ void out_stage(const TwMix &tw, int lane, const V O[N
     }
 }
 
+// Packet 0 of a run that follows a short block (previous_window_flag == 0): the left window slope
+// is the short one, centred in the left half (audio.rs:1059-1065 -> window_left_start = ls =
+// (2048 - n0) / 4), the saved right half is pl = n0 / 2 samples long, and the packet emits
+// x[ls .. 1024): pl windowed samples, then the rest of the left half as is (audio.rs:1112-1120).
+// Rare (once per burst of short blocks), so plain scalar code; w = the short window slope.
+template <int NB, typename OutT>
+__device__ __forceinline__ void out_first_short(const TwMix &tw, int lane, const V O[NB][8], const V E[NB][8], V pe[NB][8],
+                                                const RunCur cur[NB], OutT *out[NB], const float *s_state,
+                                                const float *__restrict__ w, int ls)
+{
+    const int pl = kLongN2 - 2 * ls;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int r64 = 64 * rev3(j);
+        const bool nat = (j & 1);
+        const V b0 = tw(P_B0 + j), b1 = tw(P_B1 + j);
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const V p_odd = vsub_p(vmul(O[b][j], b1), vmul(E[b][j], b0));
+            pe[b][j] = vnsub_p(vmul(O[b][j], b0), vmul(E[b][j], b1));
+            if ((cur[b].flags & 5u) != 1u) continue;           // no history (or a dummy): nothing is emitted
+            const float *prev = s_state + b * kLongN2;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const float po = h ? p_odd.y : p_odd.x;
+                const int m = r64 + ((h == 0) == nat ? lane : 63 - lane);    // x[m] = p_odd, x[1023 - m] = -p_odd
+                if (m >= ls) {
+                    const int i = m - ls;                                      // < pl / 2
+                    st_pcm(out[b] + i, __fadd_rn(__fmul_rn(po, __ldg(w + i)), __fmul_rn(prev[i], __ldg(w + pl - 1 - i))));
+                }
+                const int i = kLongN2 - 1 - m - ls;                            // >= pl / 2
+                float v = -po;
+                if (i < pl) v = __fadd_rn(__fmul_rn(v, __ldg(w + i)), __fmul_rn(prev[i], __ldg(w + pl - 1 - i)));
+                st_pcm(out[b] + i, v);
+            }
+        }
+    }
+}
+
 // runs: groups of kLongNB consecutive entries with equal n_packets (the host pads with dummy
 // runs); pack: the twiddle pack of the setup's blocksize-11 tables (long_build_pack); ticket: a
 // zeroed counter from which warps draw group indices.
@@ -661,7 +703,7 @@ __device__ __forceinline__ void out_stage(const TwMix &tw, int lane, const V O[N
 template <typename OutT>
 __global__ void __launch_bounds__(kLongWarps * 32, 1)
 k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restrict__ pack,
-       unsigned int *__restrict__ ticket)
+       unsigned int *__restrict__ ticket, const float *__restrict__ w_short, int ls)
 {
     constexpr int NB = kLongNB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -846,22 +888,32 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
                         nx_stage = 3;
                     }
                 }
-                if (lc < npk) {
-                    fence_proxy_async();
-                    issue_stage_cur(slot_i, lc);
-                    lc++;
-                } else {
-                    if (nx_stage == 1) {
-                        mbar_wait(bar_desc, desc_parity);
-                        desc_parity ^= 1u;
-                        nx_stage = 2;
-                        nx_npk = s_next[0].n_packets;
-                        nx_lc = 0;
-                    }
-                    if (nx_stage == 2 && nx_lc < nx_npk) {
+                // Stages are filled strictly in processing order: `ahead` tiles are in flight behind the
+                // one just consumed, in stages slot_i+1 .. slot_i+ahead, so the next tile goes to
+                // slot_i+1+ahead (== slot_i once the ring is full).  One tile per packet: a ring left
+                // under-filled by groups shorter than itself is topped up at the next hand-over (a
+                // catch-up loop here costs 2-9% of the steady state, profiles/variants_r1k.log).
+                uint32_t ahead = lc - (p + 1) + nx_lc;
+                if (ahead < (uint32_t)kLongRing) {
+                    uint32_t tgt = slot_i + 1 + ahead;
+                    if (tgt >= (uint32_t)kLongRing) tgt -= kLongRing;
+                    if (lc < npk) {
                         fence_proxy_async();
-                        issue_stage(slot_i, s_next, nx_lc);
-                        nx_lc++;
+                        issue_stage_cur(tgt, lc);
+                        lc++;
+                    } else {
+                        if (nx_stage == 1) {
+                            mbar_wait(bar_desc, desc_parity);
+                            desc_parity ^= 1u;
+                            nx_stage = 2;
+                            nx_npk = s_next[0].n_packets;
+                            nx_lc = 0;
+                        }
+                        if (nx_stage == 2 && nx_lc < nx_npk) {
+                            fence_proxy_async();
+                            issue_stage(tgt, s_next, nx_lc);
+                            nx_lc++;
+                        }
                     }
                 }
             }
@@ -871,12 +923,15 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
             } else {
                 mbar_wait(bar_state, (phase_bits >> 30) & 1u);      // armed once per group
                 phase_bits ^= 1u << 30;
-                out_stage<NB, true, OutT>(tw, lane, O, E, pe, cur, out, s_state);
+                if (NB == 1 && (cur[0].flags & 8u))
+                    out_first_short<NB, OutT>(tw, lane, O, E, pe, cur, out, s_state, w_short, ls);
+                else
+                    out_stage<NB, true, OutT>(tw, lane, O, E, pe, cur, out, s_state);
                 __syncwarp();                                       // state tile consumed
             }
 #pragma unroll
             for (int b = 0; b < NB; b++)
-                if (p > 0 || (cur[b].flags & 1u)) out[b] += kLongN2;
+                if (p > 0 || (cur[b].flags & 1u)) out[b] += (p == 0 && (cur[b].flags & 8u)) ? kLongN2 - ls : kLongN2;
             // the state tile is free after packet 0: request the next group's state rows as soon as
             // its descriptors are known
             if (lane == 0 && nx_stage == 2 && !nx_state_issued) {
@@ -892,7 +947,28 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
         }
 #pragma unroll
         for (int b = 0; b < NB; b++) {
-            if ((cur[b].flags & 6u) == 2u) {       // write_state and not dummy
+            if ((cur[b].flags & 16u)) {
+                // the last packet precedes a short block (next_window_flag == 0, audio.rs:1067-1073):
+                // window_right_start = 1024 + ls, so x[1024 .. 1024 + ls) leaves with this packet and the
+                // pl samples after them are what the short block overlaps with
+                const bool emitted = (npk > 1 || (cur[b].flags & 1u)) && !(cur[b].flags & 4u);
+                const bool keep = (cur[b].flags & 6u) == 2u;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int r64 = 64 * rev3(j);
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const float v = ((j & 1) != 0) == (h == 0) ? pe[b][j].x : pe[b][j].y;
+                        const int m = r64 + (h ? 63 - lane : lane);          // x[1024 + m] = x[2047 - m] = v
+                        if (m < ls) {
+                            if (emitted) st_pcm(out[b] + m, v);
+                        } else if (keep) {
+                            cur[b].state[m - ls] = v;
+                            cur[b].state[kLongN2 - 1 - ls - m] = v;
+                        }
+                    }
+                }
+            } else if ((cur[b].flags & 6u) == 2u) {       // write_state and not dummy
                 float *s_lo = cur[b].state + lane, *s_hi = cur[b].state + 63 - lane;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
@@ -966,12 +1042,12 @@ inline void long_kernel_configure()
 // d_runs: n_groups * kLongNB descriptors.  Returns 0 on success; `ticket` must point at a zeroed
 // device word no other launch in flight uses.
 inline int long_launch(cudaStream_t stream, const LongRun *d_runs, uint32_t n_groups, const float *d_pack,
-                       unsigned int *ticket, int sm_count, bool i16_out)
+                       unsigned int *ticket, int sm_count, bool i16_out, const float *d_w_short = nullptr, int ls = 0)
 {
     const uint32_t want = (n_groups + kLongWarps - 1) / kLongWarps;
     const uint32_t grid = want < (uint32_t)sm_count ? want : (uint32_t)sm_count;
-    if (i16_out) k_long<int16_t><<<grid, kLongWarps * 32, kLongSmemBytes, stream>>>(d_runs, n_groups, d_pack, ticket);
-    else k_long<float><<<grid, kLongWarps * 32, kLongSmemBytes, stream>>>(d_runs, n_groups, d_pack, ticket);
+    if (i16_out) k_long<int16_t><<<grid, kLongWarps * 32, kLongSmemBytes, stream>>>(d_runs, n_groups, d_pack, ticket, d_w_short, ls);
+    else k_long<float><<<grid, kLongWarps * 32, kLongSmemBytes, stream>>>(d_runs, n_groups, d_pack, ticket, d_w_short, ls);
     return cudaGetLastError() != cudaSuccess;
 }
 #endif  // __CUDACC__

@@ -679,3 +679,239 @@ def test_chain_kernel_vs_four_kernel_path_mixed_sequences(ctx, oracle, channels,
             pos += n * channels
             assert bits_equal(pwrs[s].data(), refs[s].pwr.data()), (name, s)
     assert np.array_equal(outs["chain"].view(np.uint8), outs["four"].view(np.uint8))
+
+
+@pytest.mark.parametrize("entry,memory,fmt,seed", [("spectrum", cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 80),
+                                                   ("spectrum", cabi.MEM_DEVICE, cabi.OUT_I16_PLANAR, 81),
+                                                   ("residue", cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 82),
+                                                   ("residue", cabi.MEM_DEVICE, cabi.OUT_F32_PLANAR, 83)])
+def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle, entry, memory, fmt, seed):
+    """The standard 256/2048 stream shape: mostly long blocks with bursts of short ones.  The host cuts
+    every chain into long-run segments (fused kernel) and the rest (chain kernel) and runs them round
+    by round, handing PreviousWindowRight over through the device state.  Bit-exact against the oracle,
+    over two consecutive batches (state carried across), and identical to the chain-kernel-only path."""
+    rng = np.random.default_rng(seed)
+    channels, bs0, bs1, S, P = 2, 8, 11, 6, 40
+    residue = entry == "residue"
+    floors, mappings, modes = _random_packet_case(rng, channels, bs0, bs1)
+    su = make_setup(ctx, channels, bs0, bs1, modes=modes, mappings=mappings, floors=floors)
+    f32 = fmt == cabi.OUT_F32_PLANAR
+    dt = np.float32 if f32 else np.int16
+    outs = {}
+    cases = []
+    refs = [RefStream(oracle, channels, bs0, bs1, modes, mappings, floors) for _ in range(S)]
+    # one consistent sequence of 2P packets per stream, decoded as two batches of P
+    full = [mode_sequence(rng, 2 * P, p_short=0.12 if s else 0.5) for s in range(S)]
+    bf, prev, nxt = full[1]
+    bf[P - 1:] = 1; prev[P:] = 1; nxt[P - 1:] = 1           # an all-long chain inside the second batch
+    prev[P - 1] = bf[P - 2]
+    if bf[P - 2]:
+        nxt[P - 2] = 1
+    for batch in range(2):
+        coeffs, dense, kinds, ys, want, seqs = [], [], [], [], [], []
+        for s in range(S):
+            bf, prev, nxt = (a[batch * P:(batch + 1) * P] for a in full[s])
+            mode_ids = np.array([int(rng.choice([m for m in range(4) if modes[m][0] == b])) for b in bf], np.uint8)
+            parts = []
+            for i in range(P):
+                n2 = (1 << (bs1 if bf[i] else bs0)) // 2
+                res = (rng.standard_normal((channels, n2)) * rng.integers(0, 2, (channels, n2))).astype(np.float32)
+                if residue:
+                    mp = mappings[modes[mode_ids[i]][1]]
+                    fl = []
+                    for c in range(channels):
+                        mult, xs = floors[mp["floor_of_channel"][c]]
+                        r = rng.random()
+                        fl.append(None if r < 0.1 else (rng.random(n2).astype(np.float32) if r < 0.2
+                                                        else random_floor1_y(rng, mult, len(xs))))
+                    rc, pcm = refs[s].packet(int(mode_ids[i]), int(prev[i]), int(nxt[i]), res, fl)
+                    k, y, d = L.DecodedPacket(int(mode_ids[i]), res, fl).pack()
+                    dense.append((d if d is not None else np.zeros_like(res)).ravel())
+                    kinds.append(k)
+                    ys.append(y)
+                else:
+                    rc, pcm = refs[s].spectrum(int(mode_ids[i]), int(prev[i]), int(nxt[i]), res)
+                assert rc == 0
+                parts.append(pcm)
+                coeffs.append(res.ravel())
+            want.append(np.concatenate(parts, axis=1))
+            seqs.append((mode_ids, prev, nxt))
+        cases.append((np.concatenate(coeffs), np.concatenate(dense) if residue else None,
+                      np.concatenate(kinds) if residue else None, np.concatenate(ys) if residue else None, want, seqs,
+                      [r.pwr.data().copy() for r in refs]))
+    for name, env in (("mixed", None), ("chain", {"LWB_NO_MIXED": "1"})):
+        pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+        for batch, (coeffs, dense, kinds, ys, want, seqs, end_state) in enumerate(cases):
+            chains, coeff_off, out_off = [], 0, 0
+            for s in range(S):
+                n = want[s].shape[1]
+                mode_ids, prev, nxt = seqs[s]
+                chains.append(L.ChainSpec(pwrs[s], mode_ids, prev, nxt, coeff_offset=coeff_off, packet_index=s * P,
+                                          out_offset=out_off, out_stride=n))
+                coeff_off += sum(channels * ((1 << (bs1 if modes[m][0] else bs0)) // 2) for m in mode_ids)
+                out_off += n * channels
+            pcm = np.zeros(out_off, dt)
+            if env:
+                os.environ.update(env)
+            launches0 = ctx.launch_count
+            try:
+                kw = dict(floor_kind=kinds, floor1_y=ys, dense_floor=dense) if residue else {}
+                if memory == cabi.MEM_DEVICE:
+                    d_in = ctx.device_alloc(coeffs.nbytes)
+                    d_out = ctx.device_alloc(max(pcm.nbytes, 4))
+                    ctx.h2d(d_in, coeffs)
+                    if residue:
+                        d_dense = ctx.device_alloc(dense.nbytes)
+                        ctx.h2d(d_dense, dense)
+                        kw["dense_floor"] = d_dense
+                    L.decode_chains(ctx, chains, cabi.ENTRY_RESIDUE if residue else cabi.ENTRY_SPECTRUM, memory, d_in, d_out, fmt, **kw)
+                    ctx.d2h(pcm, d_out)
+                    ctx.device_free(d_in)
+                    ctx.device_free(d_out)
+                    if residue:
+                        ctx.device_free(d_dense)
+                else:
+                    L.decode_chains(ctx, chains, cabi.ENTRY_RESIDUE if residue else cabi.ENTRY_SPECTRUM, memory, coeffs, pcm, fmt, **kw)
+            finally:
+                if env:
+                    for k in env:
+                        del os.environ[k]
+            n_launch = ctx.launch_count - launches0
+            if name == "mixed":
+                assert n_launch >= 3, n_launch        # at least fused + chain + fused/chain rounds
+            else:
+                assert n_launch == 1, n_launch
+            outs[(name, batch)] = pcm
+            pos = 0
+            for s in range(S):
+                n = want[s].shape[1]
+                assert chains[s].status == 0 and chains[s].n_samples == n, (name, batch, s)
+                got = pcm[pos: pos + n * channels].reshape(channels, n)
+                if f32:
+                    assert bits_equal(got, want[s]), (name, batch, s, mismatch_report(got, want[s]))
+                else:
+                    assert np.array_equal(got, oracle.quantise_i16(want[s])), (name, batch, s)
+                pos += n * channels
+                assert bits_equal(pwrs[s].data(), end_state[s]), (name, batch, s)
+    for batch in range(2):
+        assert np.array_equal(outs[("mixed", batch)].view(np.uint8), outs[("chain", batch)].view(np.uint8))
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 5, 6])
+def test_fused_kernel_many_short_runs_per_warp(ctx, oracle, P):
+    """More runs than warps, each shorter than (or as long as) the kernel's tile ring: every warp walks
+    several groups and its prefetch crosses several run boundaries.  All chains carry the same few
+    distinct inputs, so the oracle decodes 7 streams and the comparison covers all of them."""
+    rng = np.random.default_rng(90 + P)
+    S, D = 6000, 7
+    su = make_setup(ctx, 1, 8, 11)
+    spec_d = rng.standard_normal((D, P, 1024)).astype(np.float32)
+    want = []
+    for d in range(D):
+        ref = RefStream(oracle, 1, 8, 11, [(0, 0), (1, 0)])
+        parts = []
+        for i in range(P):
+            rc, pcm = ref.spectrum(1, 1, 1, spec_d[d, i][None])
+            assert rc == 0
+            parts.append(pcm)
+        want.append((np.concatenate(parts, axis=1), ref.pwr.data().copy()))
+    n = want[0][0].shape[1]
+    spec = np.ascontiguousarray(spec_d[np.arange(S) % D]).ravel()
+    pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+    modes = np.ones(P, np.uint8)
+    stride = max(n, 4)
+    chains = [L.ChainSpec(pwrs[s], modes, coeff_offset=s * P * 1024, out_offset=s * stride, out_stride=stride) for s in range(S)]
+    pcm = np.full(S * stride, np.nan, np.float32)
+    launches0 = ctx.launch_count
+    L.decode_chains(ctx, chains, cabi.ENTRY_SPECTRUM, cabi.MEM_HOST, spec, pcm, cabi.OUT_F32_PLANAR)
+    assert ctx.launch_count - launches0 <= 8            # fused kernel (one launch per host chunk)
+    got = pcm.reshape(S, stride)[:, :n]
+    for s in range(S):
+        assert chains[s].status == 0 and chains[s].n_samples == n
+    for d in range(D):
+        blk = got[d::D]
+        assert np.array_equal(blk.view(np.uint32), np.broadcast_to(want[d][0].view(np.uint32), blk.shape)), d
+    for s in (0, 1, S // 2, S - 1):
+        assert bits_equal(pwrs[s].data(), want[s % D][1])
+    # second batch on top of the saved state
+    want2 = []
+    for d in range(D):
+        ref = RefStream(oracle, 1, 8, 11, [(0, 0), (1, 0)])
+        parts = []
+        for rep in range(2):
+            for i in range(P):
+                rc, o = ref.spectrum(1, 1, 1, spec_d[d, i][None])
+                if rep:
+                    parts.append(o)
+        want2.append(np.concatenate(parts, axis=1))
+    n2 = want2[0].shape[1]
+    pcm2 = np.full(S * P * 1024, np.nan, np.float32)
+    chains2 = [L.ChainSpec(pwrs[s], modes, coeff_offset=s * P * 1024, out_offset=s * P * 1024, out_stride=P * 1024) for s in range(S)]
+    L.decode_chains(ctx, chains2, cabi.ENTRY_SPECTRUM, cabi.MEM_HOST, spec, pcm2, cabi.OUT_F32_PLANAR)
+    got2 = pcm2.reshape(S, P * 1024)[:, :n2]
+    assert n2 == P * 1024
+    for d in range(D):
+        blk = got2[d::D]
+        assert np.array_equal(blk.view(np.uint32), np.broadcast_to(want2[d].view(np.uint32), blk.shape)), d
+    for p_ in pwrs:
+        p_.close()
+
+
+def test_prepared_mixed_batch_replays_captured_rounds(ctx, oracle):
+    """A prepared batch of mixed short/long chains in device memory: the first execution plans and
+    runs, the second re-plans (the streams now hold state), later ones replay the captured launch
+    sequence without host planning.  Every execution is checked against the oracle, which decodes
+    the same packets again on top of its own state."""
+    rng = np.random.default_rng(95)
+    channels, bs0, bs1, S, P = 2, 8, 11, 5, 30
+    su = make_setup(ctx, channels, bs0, bs1)
+    refs = [RefStream(oracle, channels, bs0, bs1, [(0, 0), (1, 0)]) for _ in range(S)]
+    seqs, specs = [], []
+    for s in range(S):
+        bf = (rng.random(P) >= 0.15).astype(np.uint8)
+        bf[0] = bf[-1] = 1                        # the sequence is decoded repeatedly: it must close on itself
+        prev, nxt = np.ones(P, np.uint8), np.ones(P, np.uint8)
+        for i in range(P):
+            if bf[i]:
+                prev[i] = bf[i - 1] if i else 1
+                nxt[i] = bf[i + 1] if i + 1 < P else 1
+        seqs.append((bf, prev, nxt))
+        specs.append([rng.standard_normal((channels, 1024 if b else 128)).astype(np.float32) for b in bf])
+    spec = np.concatenate([x.ravel() for sp in specs for x in sp])
+    pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+    stride = P * 1024
+    chains, coeff_off = [], 0
+    for s in range(S):
+        chains.append(L.ChainSpec(pwrs[s], seqs[s][0], seqs[s][1], seqs[s][2], coeff_offset=coeff_off,
+                                  out_offset=s * channels * stride, out_stride=stride))
+        coeff_off += sum(x.size for x in specs[s])
+    d_in = ctx.device_alloc(spec.nbytes)
+    d_out = ctx.device_alloc(S * channels * stride * 4)
+    ctx.h2d(d_in, spec)
+    batch = L.Batch(ctx, chains, cabi.ENTRY_SPECTRUM, cabi.MEM_DEVICE, d_in, d_out, cabi.OUT_F32_PLANAR)
+    counts = []
+    for it in range(4):
+        pcm = np.full(S * channels * stride, np.nan, np.float32)
+        ctx.h2d(d_out, pcm)
+        l0 = ctx.launch_count
+        batch.run()
+        counts.append(ctx.launch_count - l0)
+        ctx.synchronize()
+        ctx.d2h(pcm, d_out)
+        batch.collect()
+        for s in range(S):
+            parts = []
+            for i in range(P):
+                rc, o = refs[s].spectrum(int(seqs[s][0][i]), int(seqs[s][1][i]), int(seqs[s][2][i]), specs[s][i])
+                assert rc == 0
+                parts.append(o)
+            want = np.concatenate(parts, axis=1)
+            n = want.shape[1]
+            assert chains[s].status == 0 and chains[s].n_samples == n, (it, s)
+            got = pcm[s * channels * stride:(s + 1) * channels * stride].reshape(channels, stride)[:, :n]
+            assert bits_equal(got, want), (it, s, mismatch_report(got, want))
+            assert bits_equal(pwrs[s].data(), refs[s].pwr.data()), (it, s)
+    assert counts[1] == counts[2] == counts[3] and counts[1] >= 3, counts
+    batch.close()
+    ctx.device_free(d_in)
+    ctx.device_free(d_out)
