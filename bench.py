@@ -70,6 +70,23 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def host_threads():
+    """Threads the CPU arm can really use: the smaller of the logical CPUs, this process's affinity
+    mask and the container's CPU quota (cgroup v2 cpu.max)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def cpu_reference(streams, packets, threads, target_sec=2.0, seed=1234):
     """The oracle port (lewton-equivalent C restatement) on the host cores; returns
     (samples/s, seconds, reps).  The same synthetic input is swept `reps` times so that the timed
@@ -92,7 +109,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     streams, packets = 8 * threads, 17            # 16 chains per thread, swept ~0.5 s per step
     vals = []
     for i in range(args.warmup + args.steps):
@@ -255,9 +272,11 @@ def main():
                         "streams": Se, "steps": e_steps, "timer": "host wall clock around synchronous calls"},
                 "gpu_launches": int(launches), "host_enqueue_us_per_step": host_us, "clocks": clocks}
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = host_threads()
+            v1, _, _ = cpu_reference(8, 17, 1, target_sec=0.5)
             v, sec, reps = cpu_reference(8 * threads, 17, threads, target_sec=2.0)
             line["cpu_baseline"] = {"value": v / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
+                                    "single_thread_value": v1 / 1e6,
                                     "sample": f"{8 * threads} stereo streams x 17 long packets swept {reps}x = "
                                               f"{sec:.2f} s wall on {threads} threads ({sec * threads:.0f} core-s); "
                                               "lewton-equivalent C restatement (oracle/), the crate itself is Rust"}
