@@ -36,6 +36,27 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(streams, packets):
+    """DRAM bytes (read + write) per k_long launch from the committed `ncu --set full` capture of this
+    same workload (profiles/*_k_long_ncu_summary.txt, newest round); None for any other workload."""
+    if (streams, packets) != (4096, 16):
+        return None, None
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_long_ncu_summary.txt")))
+    if not files:
+        return None, None
+    txt = open(files[-1]).read()
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        m = re.search(re.escape(key) + r"\s+([0-9.]+)\s+(\w+)", txt)
+        if not m or m.group(2) not in unit:
+            return None, None
+        tot += float(m.group(1)) * unit[m.group(2)]
+    return tot, os.path.relpath(files[-1], ROOT)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -254,6 +275,7 @@ def main():
         peak, peak_src = peaks()
         per_gpu = value / world
         achieved = per_gpu * ALG_BYTES_PER_SAMPLE / 1e9
+        traffic, traffic_src = ncu_traffic(S, P)
         line = {"metric": "Msamples/s IMDCT+window+OLA, 2048-pt long blocks", "value": value / 1e6,
                 "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -265,7 +287,9 @@ def main():
                            "l2_policy": "inputs+outputs per step (1 GiB at defaults) exceed the 126 MB L2",
                            "parallelism": f"streams sharded over {world} rank(s), no data-path collective"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                             "traffic_source": traffic_src, "algorithmic_bytes_per_launch": S * P * C * N2 * ALG_BYTES_PER_SAMPLE,
+                             "peak_source": peak_src,
                              "kernel": "k_long", "algorithmic_bytes_per_sample": ALG_BYTES_PER_SAMPLE},
                 "e2e": {"value": e2e_value / 1e6, "unit": "Msamples/s",
                         "h2d_bytes_per_step": Se * P * C * N2 * 4, "d2h_bytes_per_step": Se * C * stride * 4,

@@ -437,6 +437,9 @@ def test_fused_i16_planar_output(ctx, oracle, memory):
     su = make_setup(ctx, C, 8, 11)
     pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
     spec = (rng.standard_normal((S, P, C, 1024)) * 0.4).astype(np.float32)     # loud: exercises the clamp
+    spec[4, 2, 0] *= 1e6                 # far out of range on both sides
+    spec[5, 3, 0, 7] = np.inf            # +-inf and NaN samples (NaN -> 0, samples.rs:92-103 `as i16`)
+    spec[5, 6, 1, 9] = np.nan
     stride = P * 1024
     chains = [L.ChainSpec(pwrs[s], np.ones(P, np.uint8), coeff_offset=s * P * C * 1024, out_offset=s * C * stride,
                           out_stride=stride) for s in range(S)]
@@ -454,6 +457,7 @@ def test_fused_i16_planar_output(ctx, oracle, memory):
         ctx.device_free(d_out)
     want, fin = oracle_batch(oracle, spec)
     assert any(np.any(np.abs(w) > 1.0) for w in want), "test should exercise the i16 clamp"
+    assert np.any(np.isnan(want[5])) and np.any(np.abs(want[4]) > 1e3)
     for s in range(S):
         assert chains[s].n_samples == (P - 1) * 1024
         assert np.array_equal(pcm[s][:, : (P - 1) * 1024], oracle.quantise_i16(want[s])), s
