@@ -1146,10 +1146,43 @@ static int launch_chain(lwb_ctx *ctx, int fmt, unsigned n_chains, unsigned warps
     return LWB_ERR_INVALID;
 }
 
+// one launch of the fused kernel and one of the chain kernel per round, in stream order
+static int mixed_launch_rounds(lwb_ctx *ctx, const MixLaunch &ml, const std::vector<MixRound> &rounds)
+{
+    constexpr uint32_t kTicketPool = 1024;
+    cudaStream_t sm = ctx->stream;
+    int rc = LWB_OK;
+    for (const MixRound &rd : rounds) {
+        if (rd.nr) {
+            if (ctx->ticket_next % kTicketPool == 0)
+                CU(ctx, cudaMemsetAsync(ctx->ticket.p, 0, kTicketPool * sizeof(unsigned int), sm));
+            unsigned int *ticket = (unsigned int *)ctx->ticket.p + (ctx->ticket_next++ % kTicketPool);
+            if (kLongNB != 1) return fail(ctx, LWB_ERR_INVALID, "mixed path needs one run per warp");
+            if (long_launch(sm, (const LongRun *)ml.db + rd.r0, (uint32_t)rd.nr, ml.pack, ticket, ctx->sm_count, ml.i16, ml.w_short, ml.ls))
+                return fail(ctx, LWB_ERR_CUDA, "long kernel launch", cudaGetLastError());
+            ctx->launches++;
+        }
+        if (rd.nc) {
+            const ChainDesc *dcd = (const ChainDesc *)(ml.db + ml.off_cd) + rd.c0;
+            const uint8_t *dby = (const uint8_t *)(ml.db + ml.off_by);
+            if (ml.residue)
+                rc = launch_chain<LWB_ENTRY_RESIDUE>(ctx, ml.out_format, (unsigned)rd.nc, ml.warps, ml.smem, dcd, dby, ml.coeffs, ml.dense,
+                                                     ml.kinds, ml.ys, ml.pcm, ml.n1max, ml.wpc);
+            else
+                rc = launch_chain<LWB_ENTRY_SPECTRUM>(ctx, ml.out_format, (unsigned)rd.nc, ml.warps, ml.smem, dcd, dby, ml.coeffs, ml.dense,
+                                                      ml.kinds, ml.ys, ml.pcm, ml.n1max, ml.wpc);
+            if (rc) return rc;
+        }
+    }
+    return LWB_OK;
+}
+
 static int try_chain(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch,
-                     bool *handled)
+                     bool *handled, lwb_plan *plan = nullptr)
 {
     *handled = false;
+    const uint64_t gen_at_entry = ctx->state_gen;
+    if (plan) plan->mixed_captured = false;
     if (const char *e = getenv("LWB_FORCE_GENERIC"))
         if (std::strcmp(e, "1") == 0) return LWB_OK;          // "1": the four-kernel path; "2": no fused kernel only
     const bool residue = io->entry == LWB_ENTRY_RESIDUE;
@@ -1292,19 +1325,28 @@ static int try_chain(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 d_ys = (const uint32_t *)ctx->ys.p - r_lo * uniform_c * LWB_MAX_POSTS;
             }
         }
-        if ((rc = ensure(ctx, ctx->cdesc, n_launch * sizeof(ChainDesc)))) return rc;
-        if ((rc = ensure(ctx, ctx->cbytes, boff + 16))) return rc;
-        CU(ctx, cudaMemcpyAsync(ctx->cdesc.p, hd, n_launch * sizeof(ChainDesc), cudaMemcpyHostToDevice, sm));
-        CU(ctx, cudaMemcpyAsync(ctx->cbytes.p, hb, boff + 16, cudaMemcpyHostToDevice, sm));
+        // descriptors and mode bytes share one device buffer; a prepared batch (device memory, spectrum
+        // entry) owns it and replays the launch while no stream changes shape
+        const bool capture = plan && !host && !residue;
+        DevBuf &dbuf = capture ? plan->mix : ctx->cdesc;
+        const size_t used_desc = n_launch * sizeof(ChainDesc);
+        if ((rc = ensure(ctx, dbuf, used_desc + boff + 16))) return rc;
+        CU(ctx, cudaMemcpyAsync(dbuf.p, hd, used_desc, cudaMemcpyHostToDevice, sm));
+        CU(ctx, cudaMemcpyAsync((char *)dbuf.p + used_desc, hb, boff + 16, cudaMemcpyHostToDevice, sm));
         CU(ctx, cudaEventRecord(st->ev, sm));
         st->pending = true;
-        if (residue)
-            rc = launch_chain<LWB_ENTRY_RESIDUE>(ctx, io->out_format, (unsigned)n_launch, maxc * wpc, smem, (const ChainDesc *)ctx->cdesc.p,
-                                                 (const uint8_t *)ctx->cbytes.p, d_coeffs, d_dense, d_kinds, d_ys, d_pcm, n1max, wpc);
-        else
-            rc = launch_chain<LWB_ENTRY_SPECTRUM>(ctx, io->out_format, (unsigned)n_launch, maxc * wpc, smem, (const ChainDesc *)ctx->cdesc.p,
-                                                  (const uint8_t *)ctx->cbytes.p, d_coeffs, d_dense, d_kinds, d_ys, d_pcm, n1max, wpc);
-        if (rc) return rc;
+        MixLaunch ml;
+        ml.db = (char *)dbuf.p; ml.off_cd = 0; ml.off_by = used_desc; ml.pack = nullptr; ml.w_short = nullptr; ml.ls = 0;
+        ml.i16 = false; ml.residue = residue; ml.out_format = io->out_format; ml.warps = maxc * wpc; ml.smem = smem;
+        ml.n1max = n1max; ml.wpc = wpc; ml.coeffs = d_coeffs; ml.dense = d_dense; ml.kinds = d_kinds; ml.ys = d_ys; ml.pcm = d_pcm;
+        std::vector<MixRound> rounds(1, MixRound{0, 0, 0, n_launch});
+        if ((rc = mixed_launch_rounds(ctx, ml, rounds))) return rc;
+        if (capture) {
+            plan->mixed_captured = true;
+            plan->gen = gen_at_entry;
+            plan->mix_launch = ml;
+            plan->mix_rounds = std::move(rounds);
+        }
         if (host) {
             if (o_hi > o_lo)
                 CU(ctx, cudaMemcpyAsync((char *)io->pcm + o_lo * esz, ctx->pcm.p, (size_t)(o_hi - o_lo) * esz, cudaMemcpyDeviceToHost, sm));
@@ -1322,37 +1364,6 @@ static int try_chain(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
 // the chain kernel -- and the segments of all chains are executed round by round, handing the
 // overlap state over through the stream's device state (PreviousWindowRight) between launches.
 // ---------------------------------------------------------------------------------------------
-// one launch of the fused kernel and one of the chain kernel per round, in stream order
-static int mixed_launch_rounds(lwb_ctx *ctx, const MixLaunch &ml, const std::vector<MixRound> &rounds)
-{
-    constexpr uint32_t kTicketPool = 1024;
-    cudaStream_t sm = ctx->stream;
-    int rc = LWB_OK;
-    for (const MixRound &rd : rounds) {
-        if (rd.nr) {
-            if (ctx->ticket_next % kTicketPool == 0)
-                CU(ctx, cudaMemsetAsync(ctx->ticket.p, 0, kTicketPool * sizeof(unsigned int), sm));
-            unsigned int *ticket = (unsigned int *)ctx->ticket.p + (ctx->ticket_next++ % kTicketPool);
-            if (kLongNB != 1) return fail(ctx, LWB_ERR_INVALID, "mixed path needs one run per warp");
-            if (long_launch(sm, (const LongRun *)ml.db + rd.r0, (uint32_t)rd.nr, ml.pack, ticket, ctx->sm_count, ml.i16, ml.w_short, ml.ls))
-                return fail(ctx, LWB_ERR_CUDA, "long kernel launch", cudaGetLastError());
-            ctx->launches++;
-        }
-        if (rd.nc) {
-            const ChainDesc *dcd = (const ChainDesc *)(ml.db + ml.off_cd) + rd.c0;
-            const uint8_t *dby = (const uint8_t *)(ml.db + ml.off_by);
-            if (ml.residue)
-                rc = launch_chain<LWB_ENTRY_RESIDUE>(ctx, ml.out_format, (unsigned)rd.nc, ml.warps, ml.smem, dcd, dby, ml.coeffs, ml.dense,
-                                                     ml.kinds, ml.ys, ml.pcm, ml.n1max, ml.wpc);
-            else
-                rc = launch_chain<LWB_ENTRY_SPECTRUM>(ctx, ml.out_format, (unsigned)rd.nc, ml.warps, ml.smem, dcd, dby, ml.coeffs, ml.dense,
-                                                      ml.kinds, ml.ys, ml.pcm, ml.n1max, ml.wpc);
-            if (rc) return rc;
-        }
-    }
-    return LWB_OK;
-}
-
 static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch, bool *handled,
                      lwb_plan *plan = nullptr)
 {
@@ -1690,7 +1701,7 @@ static int decode_chains_impl(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, 
                 rc0 = try_mixed(ctx, chains, n_chains, io, epoch, &handled, prepared);
                 if (rc0 || handled) return rc0;
             }
-            rc0 = try_chain(ctx, chains, n_chains, io, epoch, &handled);
+            rc0 = try_chain(ctx, chains, n_chains, io, epoch, &handled, prepared);
             if (rc0 || handled) return rc0;
         }
     }
@@ -1850,7 +1861,7 @@ extern "C" int lwb_plan_execute(lwb_plan *p)
         ctx->launches++;
         return LWB_OK;
     }
-    if (p->mixed_captured && p->gen == ctx->state_gen && !getenv("LWB_FORCE_GENERIC") && !getenv("LWB_NO_MIXED")) {
+    if (p->mixed_captured && p->gen == ctx->state_gen && !getenv("LWB_FORCE_GENERIC")) {
         CU(ctx, cudaSetDevice(ctx->device));
         return mixed_launch_rounds(ctx, p->mix_launch, p->mix_rounds);
     }

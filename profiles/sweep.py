@@ -30,10 +30,10 @@ def main():
     ctx = L.Context(0)
     stream = torch.cuda.ExternalStream(ctx.cuda_stream)
     P = 8                                   # packets per chain
-    for bs in range(6, 14):
+    for bs in [int(x) for x in os.environ.get("SWEEP_BS", "6,7,8,9,10,11,12,13").split(",")]:
         n = 1 << bs
         su = L.Setup(ctx, 1, bs, bs, [L.FloorTypeOne(1, [0, 128])], [L.Mapping(1)], [L.ModeInfo(True)])
-        for log_b in (0, 4, 8, 12, 16):
+        for log_b in [int(x) for x in os.environ.get("SWEEP_LOGB", "0,4,8,12,16").split(",")]:
             blocks = 1 << log_b
             chains_n = max(1, blocks // P)
             pk = min(P, blocks)
@@ -63,7 +63,7 @@ def main():
             samples = chains_n * pk * n2          # steady state: every packet emits n/2 samples
             line = {"n": n, "blocks": chains_n * pk, "ms": ms, "msamples_per_s": samples / ms / 1e3,
                     "achieved_gbs": samples * 8 / ms / 1e6, "frac_of_hbm_peak": samples * 8 / ms / 1e6 / peak,
-                    "path": "fused k_long" if bs == 11 else "generic"}
+                    "path": "fused k_long" if bs == 11 else "chain kernel"}
             print(json.dumps(line), flush=True)
             batch.close()
             for p in pw:
