@@ -81,6 +81,9 @@ class Context:
 
     def close(self):
         if self._h:
+            # readers (frontend.OggStreamReader) own streams and setups of their own: they go first
+            for ch in [c for c in list(self._children) if not isinstance(c, (Batch, PreviousWindowRight, Setup))]:
+                ch.close()
             for kind in (Batch, PreviousWindowRight, Setup):   # plans first, then streams, then setups
                 for ch in [c for c in list(self._children) if isinstance(c, kind)]:
                     ch.close()
@@ -189,6 +192,19 @@ class Setup:
             self._h = None
             raise AudioReadError(rc, cabi.lib().lwb_last_error(ctx._h).decode())
         ctx._children.add(self)
+
+    @classmethod
+    def _adopt(cls, ctx, handle, audio_channels, blocksize_0, blocksize_1, mode_blockflags=()):
+        """Wrap an lwb_setup built by the library itself (lwf_headers_make_setup)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.audio_channels, self.blocksize_0, self.blocksize_1 = audio_channels, blocksize_0, blocksize_1
+        self.floors, self.mappings = [], []
+        self.modes = [ModeInfo(bool(b)) for b in mode_blockflags]
+        self._keep = []
+        self._h = C.c_void_p(handle)
+        ctx._children.add(self)
+        return self
 
     def blocksize(self, mode_number):
         if not 0 <= mode_number < len(self.modes):

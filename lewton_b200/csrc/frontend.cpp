@@ -1,0 +1,1521 @@
+// frontend.cpp -- the HOST front half in front of the CUDA synthesis path (include/lewton_frontend.h):
+// Vorbis header parsing, audio-packet entropy decode up to the cut at audio.rs:986, Ogg paging and
+// the OggStreamReader loop.  Bit-serial CPU work by nature; every function cites the reference code
+// whose behaviour (including its quirks) it restates.  f32 arithmetic is written in the reference's
+// expression order and compiled without contraction (-ffp-contract=off, csrc/Makefile).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/lewton_frontend.h"
+
+namespace lwf {
+
+// ---------------------------------------------------------------------------------------------
+// bitpacking.rs: BitpackCursor.  LSB-first; a read succeeds iff all its bits lie inside the buffer
+// and leaves the cursor untouched otherwise (bpc_read_body!, bitpacking.rs:93-160); a dynamic read
+// of 0 bits is Ok(0) (:283-290).
+// ---------------------------------------------------------------------------------------------
+struct BitReader {
+    const uint8_t *p;
+    size_t len;
+    size_t pos = 0;        // bit position
+    BitReader(const uint8_t *d, size_t n) : p(d), len(n) {}
+    bool read(unsigned nbits, uint64_t *out)
+    {
+        if (nbits == 0) { *out = 0; return true; }
+        if (pos + nbits > len * 8) return false;
+        uint64_t v = 0;
+        size_t bp = pos;
+        unsigned got = 0;
+        while (got < nbits) {
+            const unsigned off = bp & 7, take = std::min(8 - off, nbits - got);
+            v |= (uint64_t)((p[bp >> 3] >> off) & ((1u << take) - 1)) << got;
+            got += take;
+            bp += take;
+        }
+        pos = bp;
+        *out = v;
+        return true;
+    }
+    bool u(unsigned nbits, uint32_t *out)
+    {
+        uint64_t v;
+        if (!read(nbits, &v)) return false;
+        *out = (uint32_t)v;
+        return true;
+    }
+    bool flag(bool *out)
+    {
+        uint64_t v;
+        if (!read(1, &v)) return false;
+        *out = v == 1;
+        return true;
+    }
+};
+
+// lib.rs:166-172
+static inline uint8_t ilog(uint64_t val)
+{
+    uint8_t r = 0;
+    while (val) { r++; val >>= 1; }
+    return r;
+}
+
+// bitpacking.rs:304-314
+static inline float float32_unpack(uint32_t val)
+{
+    const uint32_t sgn = val & 0x80000000u, exp = (val & 0x7fe00000u) >> 21;
+    const double mantissa = (double)(val & 0x1fffffu);
+    const double signed_mantissa = sgn ? -mantissa : mantissa;
+    return (float)signed_mantissa * exp2f((float)exp - 788.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// huffman_tree.rs: VorbisHuffmanTree.  Entries are inserted in order, each at the leftmost free
+// position of its depth (HuffTree::insert_rec, :60-108); the flat program (:156-180) is
+// [has_children << 31 | payload, left, right] per node.
+// ---------------------------------------------------------------------------------------------
+enum { HUFF_OK = 0, HUFF_OVERSPECIFIED, HUFF_UNDERPOPULATED, HUFF_INVALID_SINGLE };
+
+struct Huffman {
+    std::vector<uint32_t> prog;
+    bool single = false;        // one entry of length 1: both bit values decode to it (:131-143)
+    uint32_t single_payload = 0;
+    bool empty = true;          // no used entry: the reference would index out of bounds on a read
+
+    struct Node { bool even = true; bool has_payload = false; uint32_t payload = 0; int l = -1, r = -1; };
+
+    static bool insert(std::vector<Node> &t, int at, uint32_t payload, unsigned depth)
+    {
+        if (t[at].has_payload) return false;
+        if (depth == 0) {
+            if (t[at].l >= 0 || t[at].r >= 0) return false;
+            t[at].has_payload = true;
+            t[at].payload = payload;
+            return true;
+        }
+        if (t[at].even) {
+            if (t[at].l >= 0) return false;
+            const int nn = (int)t.size();
+            t.push_back(Node());
+            insert(t, nn, payload, depth - 1);
+            t[at].l = nn;
+            t[at].even = false;
+            return true;
+        }
+        const int left = t[at].l;
+        if (!t[left].even) {
+            if (insert(t, left, payload, depth - 1)) {
+                t[at].even = t[left].even && (t[at].r >= 0 ? t[t[at].r].even : false);
+                return true;
+            }
+        }
+        if (t[at].r >= 0) {
+            const bool ok = insert(t, t[at].r, payload, depth - 1);
+            t[at].even = t[left].even && t[t[at].r].even;
+            return ok;
+        }
+        const int nn = (int)t.size();
+        t.push_back(Node());
+        const bool ok = insert(t, nn, payload, depth - 1);
+        t[at].even = t[left].even && t[nn].even;
+        t[at].r = nn;
+        return ok;
+    }
+
+    uint32_t flatten(const std::vector<Node> &t, int at)
+    {
+        const uint32_t cur = (uint32_t)prog.size();
+        const bool kids = t[at].l >= 0 || t[at].r >= 0;
+        prog.push_back(((uint32_t)kids << 31) | (t[at].has_payload ? t[at].payload : 0));
+        if (kids) {
+            prog.push_back(0);
+            prog.push_back(0);
+            const uint32_t l = flatten(t, t[at].l);
+            prog[cur + 1] = l;
+            const uint32_t r = flatten(t, t[at].r);
+            prog[cur + 2] = r;
+        }
+        return cur;
+    }
+
+    // VorbisHuffmanTree::load_from_array, huffman_tree.rs:113-214
+    int load(const std::vector<uint8_t> &lengths)
+    {
+        std::vector<Node> t(1);
+        t.reserve(lengths.size() * 2 + 2);
+        size_t cnt = 0, last = 0;
+        for (size_t i = 0; i < lengths.size(); i++) {
+            if (!lengths[i]) continue;
+            cnt++;
+            last = i;
+            if (!insert(t, 0, (uint32_t)i, lengths[i])) return HUFF_OVERSPECIFIED;
+        }
+        empty = cnt == 0;
+        if (cnt == 1) {
+            if (lengths[last] != 1) return HUFF_INVALID_SINGLE;
+            single = true;
+            single_payload = (uint32_t)last;
+            return HUFF_OK;
+        }
+        if (!t[0].even) return HUFF_UNDERPOPULATED;
+        if (!empty) flatten(t, 0);
+        return HUFF_OK;
+    }
+
+    // BitpackCursor::read_huffman, bitpacking.rs:455-486 (the 8-bit peek table is a shortcut for the
+    // same walk); false = the packet ended inside the codeword, all remaining bits consumed
+    bool read(BitReader &rdr, uint32_t *out) const
+    {
+        if (single) {
+            bool b;
+            if (!rdr.flag(&b)) return false;
+            *out = single_payload;
+            return true;
+        }
+        if (empty) return false;
+        uint32_t at = 0;
+        for (;;) {
+            bool b;
+            if (!rdr.flag(&b)) return false;
+            at = prog[at + 1 + (b ? 1 : 0)];
+            const uint32_t e = prog[at];
+            if (!(e & 0x80000000u)) { *out = e; return true; }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// header.rs
+// ---------------------------------------------------------------------------------------------
+struct Codebook {                    // header.rs:360-368
+    uint16_t dimensions = 0;
+    bool has_vq = false;
+    std::vector<float> vq;           // codebook_vq_lookup_vec: [entries][dimensions]
+    Huffman tree;
+};
+
+struct ResidueBook { uint8_t vals_used = 0; uint8_t val[8] = {0, 0, 0, 0, 0, 0, 0, 0}; };
+
+struct Residue {                     // header.rs:370-379
+    uint8_t type = 0;
+    uint32_t begin = 0, end = 0, partition_size = 0;
+    uint8_t classifications = 0, classbook = 0;
+    std::vector<ResidueBook> books;
+};
+
+struct Mapping {                     // header.rs:381-388
+    std::vector<uint8_t> magnitudes, angles, mux, submap_floors, submap_residues;
+};
+
+struct ModeInfo { bool blockflag = false; uint8_t mapping = 0; };
+
+struct Floor0 {                      // header.rs:399-407
+    uint8_t order = 0, amplitude_bits = 0, amplitude_offset = 0, number_of_books = 0;
+    std::vector<uint8_t> book_list;
+    std::vector<float> bark_cos_omega[2];
+};
+
+struct Floor1 {                      // header.rs:409-419
+    uint8_t multiplier = 1;
+    std::vector<uint8_t> partition_class, class_dimensions, class_subclasses, class_masterbooks;
+    std::vector<std::vector<int16_t>> subclass_books;
+    std::vector<uint32_t> x_list;
+};
+
+struct Floor { int type = 1; Floor0 f0; Floor1 f1; };
+
+struct Ident {                       // header.rs:188-211
+    uint8_t audio_channels = 0, blocksize_0 = 0, blocksize_1 = 0;
+    uint32_t audio_sample_rate = 0;
+    int32_t bitrate_maximum = 0, bitrate_nominal = 0, bitrate_minimum = 0;
+};
+
+struct Headers {
+    Ident ident;
+    std::string vendor;
+    std::vector<std::pair<std::string, std::string>> comments;
+    std::vector<Codebook> codebooks;
+    std::vector<Floor> floors;
+    std::vector<Residue> residues;
+    std::vector<Mapping> mappings;
+    std::vector<ModeInfo> modes;
+};
+
+#define RD(expr) do { if (!(expr)) return LWF_ERR_END_OF_PACKET; } while (0)
+#define BAD() return LWF_ERR_HEADER_BAD_FORMAT
+
+// read_header_begin, header.rs:131-155
+static int read_header_begin(BitReader &rdr, uint8_t *type)
+{
+    uint32_t v;
+    RD(rdr.u(8, &v));
+    if (!(v & 1)) return LWF_ERR_HEADER_IS_AUDIO;
+    *type = (uint8_t)v;
+    static const uint8_t magic[6] = {0x76, 0x6f, 0x72, 0x62, 0x69, 0x73};
+    for (int i = 0; i < 6; i++) {
+        uint32_t c;
+        RD(rdr.u(8, &c));
+        if (c != magic[i]) return LWF_ERR_NOT_VORBIS_HEADER;      // && short-circuits: stop at the first mismatch
+    }
+    return LWB_OK;
+}
+
+// read_header_ident, header.rs:221-259
+static int read_ident(const uint8_t *d, size_t n, Ident *out)
+{
+    BitReader rdr(d, n);
+    uint8_t type;
+    int rc = read_header_begin(rdr, &type);
+    if (rc) return rc;
+    if (type != 1) return LWF_ERR_HEADER_BAD_TYPE;
+    uint32_t ver, ch, rate, bmax, bnom, bmin, b0, b1, framing;
+    RD(rdr.u(32, &ver));
+    if (ver != 0) return LWF_ERR_UNSUPPORTED_VERSION;
+    RD(rdr.u(8, &ch));
+    RD(rdr.u(32, &rate));
+    RD(rdr.u(32, &bmax));
+    RD(rdr.u(32, &bnom));
+    RD(rdr.u(32, &bmin));
+    RD(rdr.u(4, &b0));
+    RD(rdr.u(4, &b1));
+    RD(rdr.u(8, &framing));
+    if (b0 < 6 || b0 > 13 || b1 < 6 || b1 > 13 || framing != 1 || b0 > b1 || ch == 0 || rate == 0) BAD();
+    out->audio_channels = (uint8_t)ch;
+    out->audio_sample_rate = rate;
+    out->bitrate_maximum = (int32_t)bmax;
+    out->bitrate_nominal = (int32_t)bnom;
+    out->bitrate_minimum = (int32_t)bmin;
+    out->blocksize_0 = (uint8_t)b0;
+    out->blocksize_1 = (uint8_t)b1;
+    return LWB_OK;
+}
+
+static bool valid_utf8(const uint8_t *s, size_t n)
+{
+    size_t i = 0;
+    while (i < n) {
+        const uint8_t c = s[i];
+        size_t extra;
+        uint32_t cp;
+        if (c < 0x80) { i++; continue; }
+        else if ((c & 0xe0) == 0xc0) { extra = 1; cp = c & 0x1f; }
+        else if ((c & 0xf0) == 0xe0) { extra = 2; cp = c & 0x0f; }
+        else if ((c & 0xf8) == 0xf0) { extra = 3; cp = c & 0x07; }
+        else return false;
+        if (i + extra >= n) return false;
+        for (size_t k = 1; k <= extra; k++) {
+            if ((s[i + k] & 0xc0) != 0x80) return false;
+            cp = (cp << 6) | (s[i + k] & 0x3f);
+        }
+        if ((extra == 1 && cp < 0x80) || (extra == 2 && cp < 0x800) || (extra == 3 && cp < 0x10000) || cp > 0x10ffff ||
+            (cp >= 0xd800 && cp <= 0xdfff))
+            return false;
+        i += extra + 1;
+    }
+    return true;
+}
+
+// read_header_comment, header.rs:309-358 (byte-oriented Cursor, little endian)
+static int read_comment(const uint8_t *d, size_t n, Headers *h)
+{
+    BitReader rdr(d, n);
+    uint8_t type;
+    int rc = read_header_begin(rdr, &type);
+    if (rc) return rc;
+    if (type != 3) return LWF_ERR_HEADER_BAD_TYPE;
+    size_t at = 7;
+    auto u32le = [&](uint32_t *v) {
+        if (at + 4 > n) return false;
+        *v = (uint32_t)d[at] | ((uint32_t)d[at + 1] << 8) | ((uint32_t)d[at + 2] << 16) | ((uint32_t)d[at + 3] << 24);
+        at += 4;
+        return true;
+    };
+    uint32_t vlen;
+    RD(u32le(&vlen));
+    if (at + vlen > n) return LWF_ERR_END_OF_PACKET;
+    if (!valid_utf8(d + at, vlen)) return LWF_ERR_UTF8;
+    h->vendor.assign((const char *)d + at, vlen);
+    at += vlen;
+    uint32_t count;
+    RD(u32le(&count));
+    for (uint32_t i = 0; i < count; i++) {
+        uint32_t clen;
+        RD(u32le(&clen));
+        if (at + clen > n) return LWF_ERR_END_OF_PACKET;
+        const uint8_t *c = d + at;
+        at += clen;
+        if (!valid_utf8(c, clen)) continue;                 // tolerated, header.rs:329-339
+        const void *eq = std::memchr(c, '=', clen);
+        if (!eq) continue;                                  // tolerated, header.rs:340-345
+        const size_t k = (const uint8_t *)eq - c;
+        h->comments.emplace_back(std::string((const char *)c, k), std::string((const char *)c + k + 1, clen - k - 1));
+    }
+    if (at + 1 > n) return LWF_ERR_END_OF_PACKET;
+    if (d[at] != 1) BAD();
+    return LWB_OK;
+}
+
+// header.rs:563-583, 585-608, 616-649
+static const uint32_t kMaxBases[32] = {0xffffffff, 0xffffffff, 0x0000ffff, 0x00000659, 0x000000ff, 0x00000054, 0x00000028,
+                                       0x00000017, 0x0000000f, 0x0000000b, 0x00000009, 0x00000007, 0x00000006, 0x00000005,
+                                       0x00000004, 0x00000004, 3, 3, 3, 3, 3, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2};
+static const uint8_t kMaxBaseBits[32] = {0x1f, 0x1f, 0x0f, 0x0a, 0x07, 0x06, 0x05, 0x04, 0x03, 0x03, 0x03, 0x02, 0x02, 0x02, 0x02, 0x02,
+                                         1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+
+static uint32_t exp_fast(uint32_t base, uint8_t exponent)
+{
+    uint32_t res = 1, selfmul = base;
+    for (int i = 0; i < 8; i++) {
+        if ((1u << i) & exponent) res *= selfmul;
+        const uint64_t sq = (uint64_t)selfmul * selfmul;
+        if (sq > 0xffffffffull) return res;                 // the reference panics only if the square were needed
+        selfmul = (uint32_t)sq;
+    }
+    return res;
+}
+
+static uint32_t lookup1_values(uint32_t entries, uint16_t dimensions)
+{
+    if (dimensions >= 32) return entries == 0 ? 0 : 1;
+    const uint8_t max_bits = kMaxBaseBits[dimensions];
+    const uint32_t max_base = kMaxBases[dimensions];
+    uint32_t base_bits = 0;
+    for (int i = 0; i <= max_bits; i++) {
+        const uint32_t bit = 1u << (max_bits - i);
+        base_bits |= bit;
+        if (max_base < base_bits || exp_fast(base_bits, (uint8_t)dimensions) > entries) base_bits &= ~bit;
+    }
+    return base_bits;
+}
+
+// read_codebook, header.rs:673-768; lookup_vec_val_decode, :495-534
+static int read_codebook(BitReader &rdr, Codebook *cb)
+{
+    uint32_t sync, dims, entries;
+    RD(rdr.u(24, &sync));
+    if (sync != 0x564342) BAD();
+    RD(rdr.u(16, &dims));
+    RD(rdr.u(24, &entries));
+    bool ordered;
+    RD(rdr.flag(&ordered));
+    std::vector<uint8_t> lengths;
+    lengths.reserve(entries);
+    if (!ordered) {
+        bool sparse;
+        RD(rdr.flag(&sparse));
+        for (uint32_t i = 0; i < entries; i++) {
+            uint32_t len = 0;
+            if (sparse) {
+                bool f;
+                RD(rdr.flag(&f));
+                if (f) { RD(rdr.u(5, &len)); len += 1; }
+            } else {
+                RD(rdr.u(5, &len));
+                len += 1;
+            }
+            lengths.push_back((uint8_t)len);
+        }
+    } else {
+        uint32_t cur = 0, len;
+        RD(rdr.u(5, &len));
+        len += 1;
+        while (cur < entries) {
+            uint32_t number;
+            RD(rdr.u(ilog(entries - cur), &number));
+            for (uint32_t k = 0; k < number; k++) lengths.push_back((uint8_t)len);
+            cur += number;
+            len += 1;
+            if (cur > entries) BAD();
+        }
+    }
+    uint32_t lookup_type;
+    RD(rdr.u(4, &lookup_type));
+    if (lookup_type > 2) BAD();
+    cb->dimensions = (uint16_t)dims;
+    if (lookup_type != 0) {
+        uint32_t raw_min, raw_delta, vbits;
+        RD(rdr.u(32, &raw_min));
+        RD(rdr.u(32, &raw_delta));
+        const float minimum = float32_unpack(raw_min), delta = float32_unpack(raw_delta);
+        RD(rdr.u(4, &vbits));
+        vbits += 1;
+        bool sequence_p;
+        RD(rdr.flag(&sequence_p));
+        const uint64_t lookup_values = lookup_type == 1 ? lookup1_values(entries, (uint16_t)dims) : (uint64_t)entries * dims;
+        if (lookup_values > (1ull << 32)) return LWB_ERR_BUFFER;
+        std::vector<uint32_t> mult;
+        mult.reserve((size_t)lookup_values);
+        for (uint64_t i = 0; i < lookup_values; i++) {
+            uint32_t m;
+            RD(rdr.u(vbits, &m));
+            mult.push_back(m);
+        }
+        cb->has_vq = true;
+        cb->vq.reserve((size_t)entries * dims);
+        if (lookup_type == 1) {
+            const size_t lv = mult.size();
+            for (uint32_t off = 0; off < entries; off++) {
+                float last = 0.f;
+                size_t divisor = 1;
+                for (uint32_t k = 0; k < dims; k++) {
+                    // with lv == 0 the reference divides by zero (panic); such a book has no entries to decode
+                    const size_t mo = lv ? (size_t)(off / (uint32_t)divisor) % lv : 0;
+                    const float e = (float)(lv ? mult[mo] : 0) * delta + minimum + last;
+                    if (sequence_p) last = e;
+                    cb->vq.push_back(e);
+                    divisor *= lv;
+                }
+            }
+        } else {
+            for (uint32_t off = 0; off < entries; off++) {
+                float last = 0.f;
+                size_t mo = (size_t)off * dims;
+                for (uint32_t k = 0; k < dims; k++) {
+                    const float e = (float)mult[mo] * delta + minimum + last;
+                    if (sequence_p) last = e;
+                    cb->vq.push_back(e);
+                    mo++;
+                }
+            }
+        }
+    }
+    if (cb->tree.load(lengths) != HUFF_OK) BAD();          // From<HuffmanError>, header.rs:74-78
+    return LWB_OK;
+}
+
+// header_cached.rs:129-158
+static inline float bark(float x)
+{
+    return 13.1f * atanf(0.00074f * x) + 2.24f * atanf(0.0000000185f * x * x) + 0.0001f * x;
+}
+static std::vector<float> bark_map_cos_omega(uint16_t n, uint16_t rate, uint16_t bark_map_size)
+{
+    std::vector<float> res;
+    res.reserve(n);
+    const float hfl = (float)rate / 2.0f;
+    const float hfl_dn = hfl / (float)n;
+    const float const_part = (float)bark_map_size / bark(hfl);
+    const float bms_m1 = (float)bark_map_size - 1.0f;
+    const float omega_factor = 3.14159265358979323846f / (float)bark_map_size;
+    for (uint32_t i = 0; i < n; i++) {
+        const float fb = floorf(bark((float)i * hfl_dn) * const_part);
+        const float map_elem = fminf(fb, bms_m1);
+        res.push_back(cosf(map_elem * omega_factor));
+    }
+    return res;
+}
+
+// read_floor, header.rs:771-920
+static int read_floor(BitReader &rdr, uint16_t codebook_cnt, uint8_t bs0, uint8_t bs1, Floor *fl)
+{
+    uint32_t type;
+    RD(rdr.u(16, &type));
+    if (type == 0) {
+        uint32_t order, rate, bms, abits, aoff, nbooks;
+        RD(rdr.u(8, &order));
+        RD(rdr.u(16, &rate));
+        RD(rdr.u(16, &bms));
+        RD(rdr.u(6, &abits));
+        if (abits > 64) BAD();
+        RD(rdr.u(8, &aoff));
+        RD(rdr.u(4, &nbooks));
+        nbooks += 1;
+        fl->type = 0;
+        Floor0 &f = fl->f0;
+        f.order = (uint8_t)order;
+        f.amplitude_bits = (uint8_t)abits;
+        f.amplitude_offset = (uint8_t)aoff;
+        f.number_of_books = (uint8_t)nbooks;
+        for (uint32_t i = 0; i < nbooks; i++) {
+            uint32_t v;
+            RD(rdr.u(8, &v));
+            if (v > codebook_cnt) BAD();                    // `>`: the reference's check, header.rs:796
+            f.book_list.push_back((uint8_t)v);
+        }
+        f.bark_cos_omega[0] = bark_map_cos_omega((uint16_t)(1u << (bs0 - 1)), (uint16_t)rate, (uint16_t)bms);
+        f.bark_cos_omega[1] = bark_map_cos_omega((uint16_t)(1u << (bs1 - 1)), (uint16_t)rate, (uint16_t)bms);
+        return LWB_OK;
+    }
+    if (type != 1) BAD();
+    fl->type = 1;
+    Floor1 &f = fl->f1;
+    uint32_t partitions;
+    RD(rdr.u(5, &partitions));
+    int max_class = -1;
+    for (uint32_t i = 0; i < partitions; i++) {
+        uint32_t c;
+        RD(rdr.u(4, &c));
+        max_class = std::max(max_class, (int)c);
+        f.partition_class.push_back((uint8_t)c);
+    }
+    for (int c = 0; c <= max_class; c++) {
+        uint32_t dim, sub;
+        RD(rdr.u(3, &dim));
+        f.class_dimensions.push_back((uint8_t)(dim + 1));
+        RD(rdr.u(2, &sub));
+        f.class_subclasses.push_back((uint8_t)sub);
+        if (sub != 0) {
+            uint32_t mb;
+            RD(rdr.u(8, &mb));
+            if (mb >= codebook_cnt) BAD();
+            f.class_masterbooks.push_back((uint8_t)mb);
+        } else {
+            f.class_masterbooks.push_back(0);
+        }
+        std::vector<int16_t> books;
+        for (uint32_t k = 0; k < (1u << sub); k++) {
+            uint32_t b;
+            RD(rdr.u(8, &b));
+            const int16_t book = (int16_t)b - 1;
+            if (book >= (int16_t)codebook_cnt) BAD();
+            books.push_back(book);
+        }
+        f.subclass_books.push_back(std::move(books));
+    }
+    uint32_t mult, rangebits;
+    RD(rdr.u(2, &mult));
+    f.multiplier = (uint8_t)(mult + 1);
+    RD(rdr.u(4, &rangebits));
+    uint32_t values = 2;
+    for (uint8_t c : f.partition_class) values += f.class_dimensions[c];
+    if (values > 65) BAD();
+    f.x_list.push_back(0);
+    f.x_list.push_back(1u << rangebits);
+    for (uint8_t c : f.partition_class)
+        for (uint8_t k = 0; k < f.class_dimensions[c]; k++) {
+            uint32_t x;
+            RD(rdr.u(rangebits, &x));
+            f.x_list.push_back(x);
+        }
+    // uniqueness (header.rs:887-901): sorted, no two equal; the scan starts with last = 1, so an
+    // x value of 1 directly after the leading 0 ... is compared against the previous element only
+    std::vector<uint32_t> sorted(f.x_list);
+    std::stable_sort(sorted.begin(), sorted.end());
+    uint32_t last = 1;
+    for (uint32_t x : sorted) {
+        if (x == last) BAD();
+        last = x;
+    }
+    return LWB_OK;
+}
+
+// read_residue, header.rs:922-983; ResidueBook::read_book, :445-468 (reads 7 of the 8 cascade bits)
+static int read_residue(BitReader &rdr, const std::vector<Codebook> &codebooks, Residue *r)
+{
+    uint32_t type, begin, end, psize, classes, classbook;
+    RD(rdr.u(16, &type));
+    if (type > 2) BAD();
+    RD(rdr.u(24, &begin));
+    RD(rdr.u(24, &end));
+    if (begin > end) BAD();
+    RD(rdr.u(24, &psize));
+    RD(rdr.u(6, &classes));
+    RD(rdr.u(8, &classbook));
+    classes += 1;
+    std::vector<uint8_t> cascade;
+    for (uint32_t i = 0; i < classes; i++) {
+        uint32_t low, high = 0;
+        bool f;
+        RD(rdr.u(3, &low));
+        RD(rdr.flag(&f));
+        if (f) RD(rdr.u(5, &high));
+        cascade.push_back((uint8_t)((high << 3) | low));
+    }
+    for (uint8_t c : cascade) {
+        ResidueBook b;
+        b.vals_used = c;
+        for (int i = 0; i < 7; i++) {
+            if (!(c & (1 << i))) continue;
+            uint32_t v;
+            RD(rdr.u(8, &v));
+            if (v >= codebooks.size() || !codebooks[v].has_vq) BAD();
+            b.val[i] = (uint8_t)v;
+        }
+        r->books.push_back(b);
+    }
+    if (classbook >= codebooks.size()) BAD();
+    r->type = (uint8_t)type;
+    r->begin = begin;
+    r->end = end;
+    r->partition_size = psize + 1;
+    r->classifications = (uint8_t)classes;
+    r->classbook = (uint8_t)classbook;
+    return LWB_OK;
+}
+
+// read_mapping, header.rs:985-1058
+static int read_mapping(BitReader &rdr, uint8_t chan_ilog, uint8_t channels, uint8_t floor_count, uint8_t residue_count, Mapping *m)
+{
+    uint32_t type;
+    RD(rdr.u(16, &type));
+    if (type > 0) BAD();
+    bool f;
+    uint32_t submaps = 1, steps = 0;
+    RD(rdr.flag(&f));
+    if (f) { RD(rdr.u(4, &submaps)); submaps += 1; }
+    RD(rdr.flag(&f));
+    if (f) { RD(rdr.u(8, &steps)); steps += 1; }
+    for (uint32_t i = 0; i < steps; i++) {
+        uint32_t mag, ang;
+        RD(rdr.u(chan_ilog, &mag));
+        RD(rdr.u(chan_ilog, &ang));
+        if (ang == mag || mag >= channels || ang >= channels) BAD();
+        m->magnitudes.push_back((uint8_t)mag);
+        m->angles.push_back((uint8_t)ang);
+    }
+    uint32_t reserved;
+    RD(rdr.u(2, &reserved));
+    if (reserved != 0) BAD();
+    if (submaps > 1) {
+        for (uint32_t c = 0; c < channels; c++) {
+            uint32_t v;
+            RD(rdr.u(4, &v));
+            if (v >= submaps) BAD();
+            m->mux.push_back((uint8_t)v);
+        }
+    } else {
+        m->mux.assign(channels, 0);
+    }
+    for (uint32_t s = 0; s < submaps; s++) {
+        uint32_t skip, fl, rs;
+        RD(rdr.u(8, &skip));
+        RD(rdr.u(8, &fl));
+        RD(rdr.u(8, &rs));
+        if (fl >= floor_count || rs >= residue_count) BAD();
+        m->submap_floors.push_back((uint8_t)fl);
+        m->submap_residues.push_back((uint8_t)rs);
+    }
+    return LWB_OK;
+}
+
+// read_header_setup, header.rs:1082-1155; read_mode_info, :1060-1077
+static int read_setup(const uint8_t *d, size_t n, Headers *h)
+{
+    BitReader rdr(d, n);
+    uint8_t type;
+    int rc = read_header_begin(rdr, &type);
+    if (rc) return rc;
+    if (type != 5) return LWF_ERR_HEADER_BAD_TYPE;
+    const uint8_t channels = h->ident.audio_channels;
+    const uint8_t chan_ilog = ilog((uint64_t)(channels - 1));
+    uint32_t v;
+    RD(rdr.u(8, &v));
+    const uint16_t codebook_cnt = (uint16_t)(v + 1);
+    h->codebooks.resize(codebook_cnt);
+    for (auto &cb : h->codebooks)
+        if ((rc = read_codebook(rdr, &cb))) return rc;
+    RD(rdr.u(6, &v));
+    for (uint32_t i = 0; i < v + 1; i++) {
+        uint32_t t;
+        RD(rdr.u(16, &t));
+        if (t != 0) BAD();
+    }
+    RD(rdr.u(6, &v));
+    const uint8_t floor_count = (uint8_t)(v + 1);
+    h->floors.resize(floor_count);
+    for (auto &fl : h->floors)
+        if ((rc = read_floor(rdr, codebook_cnt, h->ident.blocksize_0, h->ident.blocksize_1, &fl))) return rc;
+    RD(rdr.u(6, &v));
+    const uint8_t residue_count = (uint8_t)(v + 1);
+    h->residues.resize(residue_count);
+    for (auto &r : h->residues)
+        if ((rc = read_residue(rdr, h->codebooks, &r))) return rc;
+    RD(rdr.u(6, &v));
+    const uint8_t mapping_count = (uint8_t)(v + 1);
+    h->mappings.resize(mapping_count);
+    for (auto &m : h->mappings)
+        if ((rc = read_mapping(rdr, chan_ilog, channels, floor_count, residue_count, &m))) return rc;
+    RD(rdr.u(6, &v));
+    const uint8_t mode_count = (uint8_t)(v + 1);
+    for (uint32_t i = 0; i < mode_count; i++) {
+        bool bf;
+        uint32_t wt, tt, mp;
+        RD(rdr.flag(&bf));
+        RD(rdr.u(16, &wt));
+        RD(rdr.u(16, &tt));
+        RD(rdr.u(8, &mp));
+        if (wt != 0 || tt != 0 || mp >= mapping_count) BAD();
+        ModeInfo mi;
+        mi.blockflag = bf;
+        mi.mapping = (uint8_t)mp;
+        h->modes.push_back(mi);
+    }
+    bool framing;
+    RD(rdr.flag(&framing));
+    if (!framing) BAD();
+    return LWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// audio.rs front half
+// ---------------------------------------------------------------------------------------------
+enum { FL_OK = 0, FL_UNUSED = 1, FL_UNDECODABLE = 2 };
+
+// read_huffman_vq, header.rs:546-560: 0 ok, 1 end of packet, 2 no value mapping
+static int read_huffman_vq(BitReader &rdr, const Codebook &cb, const float **vec)
+{
+    uint32_t idx;
+    if (!cb.tree.read(rdr, &idx)) return 1;
+    if (!cb.has_vq) return 2;
+    *vec = cb.vq.data() + (size_t)idx * cb.dimensions;
+    return 0;
+}
+
+// floor_zero_decode, audio.rs:109-158: cosines of the coefficients + amplitude
+static int floor0_decode(BitReader &rdr, const std::vector<Codebook> &codebooks, const Floor0 &fl, std::vector<float> *coeff,
+                         uint64_t *amplitude)
+{
+    if (!rdr.read(fl.amplitude_bits, amplitude)) return FL_UNUSED;
+    if (*amplitude == 0) return FL_UNUSED;
+    uint32_t booknumber;
+    if (!rdr.u(ilog(fl.number_of_books), &booknumber)) return FL_UNUSED;
+    if (booknumber >= fl.book_list.size()) return FL_UNDECODABLE;
+    const size_t bi = fl.book_list[booknumber];
+    if (bi >= codebooks.size()) return FL_UNDECODABLE;      // the reference indexes out of bounds here (header check is `>`)
+    const Codebook &cb = codebooks[bi];
+    coeff->clear();
+    float last = 0.f;
+    for (;;) {
+        float last_new = last;
+        const float *tv;
+        const int rc = read_huffman_vq(rdr, cb, &tv);
+        if (rc == 1) return FL_UNUSED;
+        if (rc == 2) return FL_UNDECODABLE;
+        for (uint32_t k = 0; k < cb.dimensions; k++) {
+            coeff->push_back(cosf(last + tv[k]));
+            last_new = tv[k];
+            if (coeff->size() == fl.order) return FL_OK;
+        }
+        last += last_new;
+        if (coeff->size() >= fl.order) return FL_OK;
+        if (cb.dimensions == 0) return FL_UNDECODABLE;      // would loop forever in the reference
+    }
+}
+
+// floor_zero_compute_curve, audio.rs:160-212
+static void floor0_curve(const std::vector<float> &cosc, uint64_t amplitude, const Floor0 &fl, bool blockflag, uint32_t n, float *out)
+{
+    const std::vector<float> &bark_cos = fl.bark_cos_omega[blockflag ? 1 : 0];
+    const float common = (float)amplitude * (float)fl.amplitude_offset / (float)(((uint64_t)1 << fl.amplitude_bits) - 1);
+    size_t i = 0;
+    size_t w = 0;
+    while (i < n) {
+        const float cos_omega = bark_cos[i];
+        size_t pu, qu;
+        float p, q;
+        if (fl.order & 1) {
+            pu = ((size_t)fl.order - 3) / 2;
+            qu = ((size_t)fl.order - 1) / 2;
+            p = 1.0f - cos_omega * cos_omega;
+            q = 0.25f;
+        } else {
+            pu = qu = ((size_t)fl.order - 2) / 2;
+            p = (1.0f - cos_omega) / 2.0f;
+            q = (1.0f + cos_omega) / 2.0f;
+        }
+        for (size_t j = 0; j <= pu; j++) {
+            const float pm = cosc[2 * j + 1] - cos_omega;
+            p *= 4.0f * pm * pm;
+        }
+        for (size_t j = 0; j <= qu; j++) {
+            const float qm = cosc[2 * j] - cos_omega;
+            q *= 4.0f * qm * qm;
+        }
+        const float lfv = expf(0.11512925f * (common / sqrtf(p + q) - (float)fl.amplitude_offset));
+        float cond = cos_omega;
+        while (cos_omega == cond) {
+            out[w++] = lfv;
+            i++;
+            if (i >= bark_cos.size()) break;
+            cond = bark_cos[i];
+        }
+        if (i >= bark_cos.size()) break;
+    }
+    for (; w < n; w++) out[w] = 0.f;
+}
+
+// floor_one_decode, audio.rs:215-251
+static int floor1_decode(BitReader &rdr, const std::vector<Codebook> &codebooks, const Floor1 &fl, uint32_t *y, uint32_t *count)
+{
+    bool nonzero;
+    if (!rdr.flag(&nonzero)) return FL_UNUSED;
+    if (!nonzero) return FL_UNUSED;
+    static const uint32_t ranges[4] = {256, 128, 86, 64};
+    const uint8_t b = ilog(ranges[fl.multiplier - 1] - 1);
+    uint32_t n = 0, v;
+    if (!rdr.u(b, &v)) return FL_UNUSED;
+    y[n++] = v;
+    if (!rdr.u(b, &v)) return FL_UNUSED;
+    y[n++] = v;
+    for (uint8_t cls : fl.partition_class) {
+        const uint8_t cdim = fl.class_dimensions[cls], cbits = fl.class_subclasses[cls];
+        const uint32_t csub = (1u << cbits) - 1;
+        uint32_t cval = 0;
+        if (cbits > 0)
+            if (!codebooks[fl.class_masterbooks[cls]].tree.read(rdr, &cval)) return FL_UNUSED;
+        for (uint8_t k = 0; k < cdim; k++) {
+            const int16_t book = fl.subclass_books[cls][cval & csub];
+            cval >>= cbits;
+            if (book >= 0) {
+                if (!codebooks[(size_t)book].tree.read(rdr, &v)) return FL_UNUSED;
+                y[n++] = v;
+            } else {
+                y[n++] = 0;
+            }
+        }
+    }
+    *count = n;
+    return FL_OK;
+}
+
+// residue_packet_read_partition, audio.rs:588-619: 0 ok, 1 end of packet
+static int residue_partition(BitReader &rdr, const Codebook &cb, const Residue &r, float *v, size_t vlen)
+{
+    const float *e;
+    if (r.type == 0) {
+        const size_t dims = cb.dimensions;
+        if (dims == 0) return 0;                            // division by zero in the reference
+        const size_t step = r.partition_size / dims;
+        for (size_t i = 0; i < step; i++) {
+            const int rc = read_huffman_vq(rdr, cb, &e);
+            if (rc) return 1;
+            for (size_t j = 0; j < dims; j++) {
+                if (i + j * step >= vlen) return 0;         // slice index out of range panics in the reference
+                v[i + j * step] += e[j];
+            }
+        }
+    } else {
+        const size_t psize = r.partition_size;
+        size_t i = 0;
+        while (i < psize) {
+            const int rc = read_huffman_vq(rdr, cb, &e);
+            if (rc) return 1;
+            if (i + cb.dimensions > vlen) break;
+            for (size_t k = 0; k < cb.dimensions; k++) v[i + k] += e[k];
+            i += cb.dimensions;
+            if (cb.dimensions == 0) break;
+        }
+    }
+    return 0;
+}
+
+// residue_packet_decode_inner, audio.rs:621-716.  `vectors`: [ch][blocksize/2], zeroed here.
+static int residue_decode_inner(BitReader &rdr, uint32_t cur_blocksize, const std::vector<uint8_t> &dnd, const Residue &r,
+                                const std::vector<Codebook> &codebooks, std::vector<float> &vectors)
+{
+    const size_t ch = dnd.size(), actual = cur_blocksize / 2;
+    const size_t lim_begin = std::min<size_t>(r.begin, actual), lim_end = std::min<size_t>(r.end, actual);
+    const Codebook &classbook = codebooks[r.classbook];
+    const size_t cpc = classbook.dimensions;
+    const size_t n_to_read = lim_end - lim_begin;
+    const size_t parts = n_to_read / r.partition_size;
+    vectors.assign(ch * actual, 0.f);
+    if (n_to_read == 0) return 0;
+    if (cpc == 0) return 1;
+    const size_t stride = parts + cpc;
+    std::vector<uint32_t> cls(ch * stride, 0);
+    for (int pass = 0; pass < 8; pass++) {
+        size_t pc = 0;
+        while (pc < parts) {
+            if (pass == 0) {
+                for (size_t j = 0; j < ch; j++) {
+                    if (dnd[j]) continue;
+                    uint32_t temp;
+                    if (!classbook.tree.read(rdr, &temp)) return 0;           // end of packet is normal
+                    for (size_t i = cpc; i-- > 0;) {
+                        cls[j * stride + i + pc] = temp % r.classifications;
+                        temp /= r.classifications;
+                    }
+                }
+            }
+            for (size_t k = 0; k < cpc; k++) {
+                if (pc >= parts) break;
+                for (size_t j = 0; j < ch; j++) {
+                    if (dnd[j]) continue;
+                    const size_t offs = lim_begin + pc * r.partition_size;
+                    const uint32_t vqclass = cls[j * stride + pc];
+                    const ResidueBook &rb = r.books[vqclass];
+                    if (rb.vals_used & (1u << pass)) {
+                        const Codebook &cb = codebooks[rb.val[pass]];
+                        if (!cb.has_vq) return 1;           // the reference panics ("must have a value mapping")
+                        if (residue_partition(rdr, cb, r, vectors.data() + j * actual + offs, actual - offs)) return 0;
+                    }
+                }
+                pc++;
+            }
+        }
+    }
+    return 0;
+}
+
+// residue_packet_decode, audio.rs:721-760
+static int residue_decode(BitReader &rdr, uint32_t cur_blocksize, const std::vector<uint8_t> &dnd, const Residue &r,
+                          const std::vector<Codebook> &codebooks, std::vector<float> &out)
+{
+    const size_t ch = dnd.size(), vec = cur_blocksize / 2;
+    if (r.type != 2) return residue_decode_inner(rdr, cur_blocksize, dnd, r, codebooks, out);
+    bool any = false;
+    for (uint8_t d : dnd) any |= !d;
+    if (!any) {
+        out.assign(ch * vec, 0.f);
+        return 0;
+    }
+    std::vector<uint8_t> one(1, 0);
+    std::vector<float> inter;
+    // cur_blocksize * ch as u16: the product wraps at 16 bits in the reference
+    const uint32_t bs2 = (uint32_t)(uint16_t)(cur_blocksize * ch);
+    if (residue_decode_inner(rdr, bs2, one, r, codebooks, inter)) return 1;
+    out.assign(ch * vec, 0.f);
+    for (size_t j = 0; j < ch; j++)
+        for (size_t i = 0; i < vec; i++) {
+            const size_t src = i * ch + j;
+            if (src < inter.size()) out[j * vec + i] = inter[src];
+        }
+    return 0;
+}
+
+struct PacketHead { uint8_t mode; bool blockflag; bool prev, next; uint32_t n; };
+
+// audio.rs:921-939 (and :877-888)
+static int packet_head(const Headers &h, BitReader &rdr, PacketHead *ph)
+{
+    bool is_header;
+    if (!rdr.flag(&is_header)) return LWF_ERR_END_OF_PACKET;
+    if (is_header) return LWF_ERR_AUDIO_IS_HEADER;
+    uint32_t mode;
+    if (!rdr.u(ilog((uint64_t)h.modes.size() - 1), &mode)) return LWF_ERR_END_OF_PACKET;
+    if (mode >= h.modes.size()) return LWB_ERR_BAD_FORMAT;
+    ph->mode = (uint8_t)mode;
+    ph->blockflag = h.modes[mode].blockflag;
+    ph->n = 1u << (ph->blockflag ? h.ident.blocksize_1 : h.ident.blocksize_0);
+    ph->prev = ph->next = true;
+    if (ph->blockflag) {
+        if (!rdr.flag(&ph->prev)) return LWF_ERR_END_OF_PACKET;
+        if (!rdr.flag(&ph->next)) return LWF_ERR_END_OF_PACKET;
+    }
+    return LWB_OK;
+}
+
+static int packet_decode(const Headers &h, const uint8_t *packet, size_t len, lwf_decoded_packet *out)
+{
+    BitReader rdr(packet, len);
+    PacketHead ph;
+    int rc = packet_head(h, rdr, &ph);
+    if (rc) return rc;
+    const ModeInfo &mode = h.modes[ph.mode];
+    const Mapping &mp = h.mappings[mode.mapping];
+    const size_t C = h.ident.audio_channels, n2 = ph.n / 2;
+    out->mode_number = ph.mode;
+    out->blockflag = ph.blockflag;
+    out->prev_window_flag = ph.prev;
+    out->next_window_flag = ph.next;
+    out->n = ph.n;
+    // floor_decode, audio.rs:557-586
+    std::vector<uint8_t> no_residue(C);
+    std::vector<float> cosc;
+    for (size_t c = 0; c < C; c++) {
+        const Floor &fl = h.floors[mp.submap_floors[mp.mux[c]]];
+        int fr;
+        if (fl.type == 0) {
+            uint64_t amp = 0;
+            fr = floor0_decode(rdr, h.codebooks, fl.f0, &cosc, &amp);
+            if (fr == FL_OK) {
+                out->floor_kind[c] = LWB_FLOOR_DENSE;
+                floor0_curve(cosc, amp, fl.f0, ph.blockflag, (uint32_t)n2, out->dense_floor + c * n2);
+            }
+        } else {
+            uint32_t cnt = 0;
+            uint32_t *y = out->floor1_y + c * LWB_MAX_POSTS;
+            std::memset(y, 0, sizeof(uint32_t) * LWB_MAX_POSTS);
+            fr = floor1_decode(rdr, h.codebooks, fl.f1, y, &cnt);
+            if (fr == FL_OK) out->floor_kind[c] = LWB_FLOOR_ONE;
+        }
+        if (fr == FL_UNDECODABLE) return LWF_ERR_END_OF_PACKET;  // floor_decode's Err(()) goes through From<()> (audio.rs:46-50)
+        if (fr == FL_UNUSED) out->floor_kind[c] = LWB_FLOOR_UNUSED;
+        no_residue[c] = fr == FL_UNUSED;
+    }
+    // audio.rs:944-955
+    for (size_t s = 0; s < mp.magnitudes.size(); s++) {
+        const uint8_t m = mp.magnitudes[s], a = mp.angles[s];
+        if (!(no_residue[m] && no_residue[a])) no_residue[m] = no_residue[a] = 0;
+    }
+    // audio.rs:957-986
+    std::vector<uint8_t> dnd;
+    std::vector<float> vectors;
+    for (size_t i = 0; i < mp.submap_residues.size(); i++) {
+        dnd.clear();
+        for (size_t j = 0; j < C; j++)
+            if (mp.mux[j] == i) dnd.push_back(no_residue[j]);
+        const Residue &r = h.residues[mp.submap_residues[i]];
+        if (residue_decode(rdr, ph.n, dnd, r, h.codebooks, vectors)) return LWB_ERR_BAD_FORMAT;
+        size_t chn = 0;
+        for (size_t j = 0; j < C; j++)
+            if (mp.mux[j] == i) {
+                std::memcpy(out->residue + j * n2, vectors.data() + n2 * chn, n2 * sizeof(float));
+                chn++;
+            }
+    }
+    return LWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ogg paging: what ogg 0.8.0's PacketReader hands to inside_ogg.rs (packets with stream serial,
+// page granule position and first/last flags).  RFC 3533 framing, CRC-32 poly 0x04c11db7.
+// ---------------------------------------------------------------------------------------------
+static uint32_t crc_table[256];
+static bool crc_ready = false;
+static void crc_init()
+{
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t r = i << 24;
+        for (int k = 0; k < 8; k++) r = (r & 0x80000000u) ? (r << 1) ^ 0x04c11db7u : r << 1;
+        crc_table[i] = r;
+    }
+    crc_ready = true;
+}
+static uint32_t ogg_crc(const uint8_t *d, size_t n, size_t crc_at)
+{
+    if (!crc_ready) crc_init();
+    uint32_t c = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t b = (i >= crc_at && i < crc_at + 4) ? 0 : d[i];
+        c = (c << 8) ^ crc_table[((c >> 24) ^ b) & 0xff];
+    }
+    return c;
+}
+
+struct OggStreamState { std::vector<uint8_t> partial; bool in_packet = false; bool seen = false; bool ended = false; };
+
+struct Ogg {
+    const uint8_t *d;
+    size_t len, at = 0;
+    struct Pending { std::vector<uint8_t> data; uint32_t serial; uint64_t absgp; bool first_stream, last_stream, first_page, last_page; };
+    std::vector<Pending> queue;
+    size_t qhead = 0;
+    std::vector<std::pair<uint32_t, OggStreamState>> streams;
+    std::vector<uint8_t> current;
+
+    OggStreamState &state(uint32_t serial)
+    {
+        for (auto &s : streams)
+            if (s.first == serial) return s.second;
+        streams.emplace_back(serial, OggStreamState());
+        return streams.back().second;
+    }
+
+    // parse one page into the queue; LWF_ERR_NO_MORE_PACKETS at the end of the data
+    int read_page()
+    {
+        if (at >= len) return LWF_ERR_NO_MORE_PACKETS;
+        if (at + 27 > len) return LWF_ERR_OGG;
+        const uint8_t *p = d + at;
+        if (std::memcmp(p, "OggS", 4) != 0 || p[4] != 0) return LWF_ERR_OGG;
+        const uint8_t htype = p[5];
+        uint64_t absgp = 0;
+        for (int i = 7; i >= 0; i--) absgp = (absgp << 8) | p[6 + i];
+        const uint32_t serial = (uint32_t)p[14] | ((uint32_t)p[15] << 8) | ((uint32_t)p[16] << 16) | ((uint32_t)p[17] << 24);
+        const uint32_t crc = (uint32_t)p[22] | ((uint32_t)p[23] << 8) | ((uint32_t)p[24] << 16) | ((uint32_t)p[25] << 24);
+        const size_t nseg = p[26];
+        if (at + 27 + nseg > len) return LWF_ERR_OGG;
+        size_t body = 0;
+        for (size_t i = 0; i < nseg; i++) body += p[27 + i];
+        const size_t total = 27 + nseg + body;
+        if (at + total > len) return LWF_ERR_OGG;
+        if (ogg_crc(p, total, 22) != crc) return LWF_ERR_OGG;
+        OggStreamState &st = state(serial);
+        const bool bos = htype & 2, eos = htype & 4, continued = htype & 1;
+        if (!continued) { st.partial.clear(); st.in_packet = false; }
+        const uint8_t *bp = p + 27 + nseg;
+        const size_t q0 = queue.size();
+        bool first_in_page = true;
+        for (size_t i = 0; i < nseg; i++) {
+            const uint8_t l = p[27 + i];
+            st.partial.insert(st.partial.end(), bp, bp + l);
+            st.in_packet = true;
+            bp += l;
+            if (l < 255) {
+                Pending pk;
+                pk.data.swap(st.partial);
+                pk.serial = serial;
+                pk.absgp = absgp;
+                pk.first_stream = bos && first_in_page && !st.seen;
+                pk.last_stream = false;
+                pk.first_page = first_in_page;
+                pk.last_page = false;
+                queue.push_back(std::move(pk));
+                st.partial.clear();
+                st.in_packet = false;
+                first_in_page = false;
+                st.seen = true;
+            }
+        }
+        if (queue.size() > q0) {
+            queue.back().last_page = true;
+            if (eos) queue.back().last_stream = true;
+        }
+        at += total;
+        return LWB_OK;
+    }
+
+    int next(lwf_ogg_packet *out)
+    {
+        while (qhead >= queue.size()) {
+            queue.clear();
+            qhead = 0;
+            const int rc = read_page();
+            if (rc) return rc;
+        }
+        Pending &pk = queue[qhead++];
+        current.swap(pk.data);
+        out->data = current.data();
+        out->len = current.size();
+        out->stream_serial = pk.serial;
+        out->absgp_page = pk.absgp;
+        out->first_in_stream = pk.first_stream;
+        out->last_in_stream = pk.last_stream;
+        out->first_in_page = pk.first_page;
+        out->last_in_page = pk.last_page;
+        return LWB_OK;
+    }
+};
+
+}  // namespace lwf
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+struct lwf_headers { lwf::Headers h; };
+struct lwf_ogg { lwf::Ogg o; };
+
+extern "C" int lwf_headers_parse(const uint8_t *ident, size_t ident_len, const uint8_t *comment, size_t comment_len,
+                                 const uint8_t *setup, size_t setup_len, lwf_headers **out)
+{
+    if (!ident || !comment || !setup || !out) return LWB_ERR_INVALID;
+    std::unique_ptr<lwf_headers> h(new (std::nothrow) lwf_headers());
+    if (!h) return LWB_ERR_BUFFER;
+    int rc;
+    if ((rc = lwf::read_ident(ident, ident_len, &h->h.ident))) return rc;
+    if ((rc = lwf::read_comment(comment, comment_len, &h->h))) return rc;
+    if ((rc = lwf::read_setup(setup, setup_len, &h->h))) return rc;
+    *out = h.release();
+    return LWB_OK;
+}
+
+extern "C" void lwf_headers_destroy(lwf_headers *h) { delete h; }
+
+extern "C" int lwf_headers_info(const lwf_headers *h, lwf_info *out)
+{
+    if (!h || !out) return LWB_ERR_INVALID;
+    const lwf::Headers &s = h->h;
+    out->audio_channels = s.ident.audio_channels;
+    out->blocksize_0 = s.ident.blocksize_0;
+    out->blocksize_1 = s.ident.blocksize_1;
+    out->audio_sample_rate = s.ident.audio_sample_rate;
+    out->bitrate_maximum = s.ident.bitrate_maximum;
+    out->bitrate_nominal = s.ident.bitrate_nominal;
+    out->bitrate_minimum = s.ident.bitrate_minimum;
+    out->n_codebooks = (uint32_t)s.codebooks.size();
+    out->n_floors = (uint32_t)s.floors.size();
+    out->n_residues = (uint32_t)s.residues.size();
+    out->n_mappings = (uint32_t)s.mappings.size();
+    out->n_modes = (uint32_t)s.modes.size();
+    out->n_comments = (uint32_t)s.comments.size();
+    return LWB_OK;
+}
+
+extern "C" size_t lwf_headers_comment(const lwf_headers *h, int index, char *buf, size_t cap)
+{
+    if (!h) return 0;
+    std::string s;
+    if (index < 0) s = h->h.vendor;
+    else if ((size_t)index < h->h.comments.size()) s = h->h.comments[index].first + "=" + h->h.comments[index].second;
+    if (buf && cap) {
+        const size_t k = std::min(cap - 1, s.size());
+        std::memcpy(buf, s.data(), k);
+        buf[k] = 0;
+    }
+    return s.size();
+}
+
+extern "C" int lwf_headers_make_setup(const lwf_headers *h, lwb_ctx *ctx, lwb_setup **out)
+{
+    if (!h || !ctx || !out) return LWB_ERR_INVALID;
+    const lwf::Headers &s = h->h;
+    std::vector<lwb_floor_desc> floors(s.floors.size());
+    for (size_t i = 0; i < s.floors.size(); i++) {
+        std::memset(&floors[i], 0, sizeof(lwb_floor_desc));
+        if (s.floors[i].type == 0) {
+            floors[i].floor_type = LWB_FLOOR_TYPE_ZERO;
+        } else {
+            const lwf::Floor1 &f = s.floors[i].f1;
+            floors[i].floor_type = LWB_FLOOR_TYPE_ONE;
+            floors[i].floor1_multiplier = f.multiplier;
+            floors[i].floor1_values = (uint8_t)f.x_list.size();
+            for (size_t k = 0; k < f.x_list.size(); k++) floors[i].floor1_x_list[k] = f.x_list[k];
+        }
+    }
+    std::vector<lwb_mapping_desc> maps(s.mappings.size());
+    for (size_t i = 0; i < s.mappings.size(); i++) {
+        const lwf::Mapping &m = s.mappings[i];
+        std::memset(&maps[i], 0, sizeof(lwb_mapping_desc));
+        maps[i].coupling_steps = (uint16_t)m.magnitudes.size();
+        maps[i].submaps = (uint8_t)m.submap_floors.size();
+        for (size_t k = 0; k < m.magnitudes.size(); k++) { maps[i].magnitudes[k] = m.magnitudes[k]; maps[i].angles[k] = m.angles[k]; }
+        for (size_t k = 0; k < m.mux.size(); k++) maps[i].mux[k] = m.mux[k];
+        for (size_t k = 0; k < m.submap_floors.size(); k++) maps[i].submap_floors[k] = m.submap_floors[k];
+    }
+    std::vector<lwb_mode_desc> modes(s.modes.size());
+    for (size_t i = 0; i < s.modes.size(); i++) { modes[i].blockflag = s.modes[i].blockflag; modes[i].mapping = s.modes[i].mapping; }
+    lwb_setup_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.audio_channels = s.ident.audio_channels;
+    d.blocksize_0 = s.ident.blocksize_0;
+    d.blocksize_1 = s.ident.blocksize_1;
+    d.n_floors = (uint32_t)floors.size();
+    d.floors = floors.data();
+    d.n_mappings = (uint32_t)maps.size();
+    d.mappings = maps.data();
+    d.n_modes = (uint32_t)modes.size();
+    d.modes = modes.data();
+    return lwb_setup_create(ctx, &d, out);
+}
+
+extern "C" int lwf_packet_decode(const lwf_headers *h, const uint8_t *packet, size_t len, lwf_decoded_packet *out)
+{
+    if (!h || (!packet && len) || !out || !out->floor_kind || !out->floor1_y || !out->residue) return LWB_ERR_INVALID;
+    for (const auto &fl : h->h.floors)
+        if (fl.type == 0 && !out->dense_floor) return LWB_ERR_INVALID;
+    return lwf::packet_decode(h->h, packet, len, out);
+}
+
+// get_decoded_sample_count, audio.rs:874-909
+extern "C" int lwf_decoded_sample_count(const lwf_headers *h, const uint8_t *packet, size_t len, size_t *n_samples)
+{
+    if (!h || (!packet && len) || !n_samples) return LWB_ERR_INVALID;
+    lwf::BitReader rdr(packet, len);
+    lwf::PacketHead ph;
+    const int rc = lwf::packet_head(h->h, rdr, &ph);
+    if (rc) return rc;
+    const uint32_t n = ph.n, n0 = 1u << h->h.ident.blocksize_0;
+    const uint32_t ls = ph.prev ? 0 : (n - n0) >> 2;
+    const uint32_t rs = ph.next ? n >> 1 : (n * 3 - n0) >> 2;
+    *n_samples = rs - ls;
+    return LWB_OK;
+}
+
+extern "C" int lwf_ogg_open(const uint8_t *data, size_t len, lwf_ogg **out)
+{
+    if ((!data && len) || !out) return LWB_ERR_INVALID;
+    lwf_ogg *o = new (std::nothrow) lwf_ogg();
+    if (!o) return LWB_ERR_BUFFER;
+    o->o.d = data;
+    o->o.len = len;
+    *out = o;
+    return LWB_OK;
+}
+extern "C" void lwf_ogg_close(lwf_ogg *o) { delete o; }
+extern "C" int lwf_ogg_next_packet(lwf_ogg *o, lwf_ogg_packet *pkt)
+{
+    if (!o || !pkt) return LWB_ERR_INVALID;
+    return o->o.next(pkt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// OggStreamReader, inside_ogg.rs:60-227
+// ---------------------------------------------------------------------------------------------
+struct lwf_reader {
+    lwb_ctx *ctx = nullptr;
+    lwf_ogg *ogg = nullptr;
+    lwf_headers *hdr = nullptr;
+    lwb_setup *setup = nullptr;
+    lwb_stream *pwr = nullptr;
+    uint32_t serial = 0;
+    bool has_absgp = false;
+    uint64_t absgp = 0;
+    std::vector<uint8_t> kinds;
+    std::vector<uint32_t> ys;
+    std::vector<float> dense, residue, scratch;
+};
+
+static void reader_drop_stream(lwf_reader *r)
+{
+    if (r->pwr) lwb_stream_destroy(r->pwr);
+    if (r->setup) lwb_setup_destroy(r->setup);
+    if (r->hdr) lwf_headers_destroy(r->hdr);
+    r->pwr = nullptr;
+    r->setup = nullptr;
+    r->hdr = nullptr;
+}
+
+// read_headers, inside_ogg.rs:19-39 (`first`: the ident packet has already been read)
+static int reader_read_headers(lwf_reader *r, const lwf_ogg_packet *first)
+{
+    lwf_ogg_packet pk;
+    int rc;
+    std::vector<uint8_t> ident, comment;
+    if (first) pk = *first;
+    else if ((rc = lwf_ogg_next_packet(r->ogg, &pk))) return rc == LWF_ERR_NO_MORE_PACKETS ? LWF_ERR_OGG : rc;
+    ident.assign(pk.data, pk.data + pk.len);
+    const uint32_t serial = pk.stream_serial;
+    do {
+        if ((rc = lwf_ogg_next_packet(r->ogg, &pk))) return rc == LWF_ERR_NO_MORE_PACKETS ? LWF_ERR_OGG : rc;
+    } while (pk.stream_serial != serial);
+    comment.assign(pk.data, pk.data + pk.len);
+    do {
+        if ((rc = lwf_ogg_next_packet(r->ogg, &pk))) return rc == LWF_ERR_NO_MORE_PACKETS ? LWF_ERR_OGG : rc;
+    } while (pk.stream_serial != serial);
+    lwf_headers *h = nullptr;
+    if ((rc = lwf_headers_parse(ident.data(), ident.size(), comment.data(), comment.size(), pk.data, pk.len, &h))) return rc;
+    reader_drop_stream(r);
+    r->hdr = h;
+    if ((rc = lwf_headers_make_setup(h, r->ctx, &r->setup))) return rc;
+    if ((rc = lwb_stream_open(r->ctx, r->setup, &r->pwr))) return rc;
+    r->serial = serial;
+    r->has_absgp = false;
+    const size_t C = h->h.ident.audio_channels, n2 = (size_t)1 << (h->h.ident.blocksize_1 - 1);
+    r->kinds.assign(C, 0);
+    r->ys.assign(C * LWB_MAX_POSTS, 0);
+    r->dense.assign(C * n2, 0.f);
+    r->residue.assign(C * n2, 0.f);
+    return LWB_OK;
+}
+
+extern "C" int lwf_reader_open(lwb_ctx *ctx, const uint8_t *data, size_t len, lwf_reader **out)
+{
+    if (!ctx || (!data && len) || !out) return LWB_ERR_INVALID;
+    std::unique_ptr<lwf_reader> r(new (std::nothrow) lwf_reader());
+    if (!r) return LWB_ERR_BUFFER;
+    r->ctx = ctx;
+    int rc = lwf_ogg_open(data, len, &r->ogg);
+    if (rc) return rc;
+    rc = reader_read_headers(r.get(), nullptr);
+    if (rc) {
+        reader_drop_stream(r.get());
+        lwf_ogg_close(r->ogg);
+        return rc;
+    }
+    *out = r.release();
+    return LWB_OK;
+}
+
+extern "C" void lwf_reader_close(lwf_reader *r)
+{
+    if (!r) return;
+    reader_drop_stream(r);
+    lwf_ogg_close(r->ogg);
+    delete r;
+}
+
+extern "C" const lwf_headers *lwf_reader_headers(const lwf_reader *r) { return r ? r->hdr : nullptr; }
+
+// read_audio_packet_generic through the CUDA back half
+static int reader_decode(lwf_reader *r, const lwf_ogg_packet &pk, int out_format, void *out, size_t cap, size_t *n)
+{
+    lwf_decoded_packet dp;
+    std::memset(&dp, 0, sizeof(dp));
+    dp.floor_kind = r->kinds.data();
+    dp.floor1_y = r->ys.data();
+    dp.dense_floor = r->dense.data();
+    dp.residue = r->residue.data();
+    int rc = lwf_packet_decode(r->hdr, pk.data, pk.len, &dp);
+    if (rc) return rc;
+    lwb_packet p;
+    std::memset(&p, 0, sizeof(p));
+    p.mode_number = dp.mode_number;
+    p.prev_window_flag = dp.prev_window_flag;
+    p.next_window_flag = dp.next_window_flag;
+    p.floor_kind = dp.floor_kind;
+    p.floor1_y = dp.floor1_y;
+    p.dense_floor = dp.dense_floor;
+    p.residue = dp.residue;
+    return lwb_decode_packet(r->pwr, &p, out_format, out, cap, n);
+}
+
+// read_next_audio_packet (inside_ogg.rs:107-143) + dec_packet_generic (:213-229)
+extern "C" int lwf_reader_read_dec_packet(lwf_reader *r, int out_format, void *out, size_t cap, size_t *n_samples)
+{
+    if (!r || !out || !n_samples) return LWB_ERR_INVALID;
+    *n_samples = 0;
+    lwf_ogg_packet pk;
+    int rc;
+    for (;;) {
+        if ((rc = lwf_ogg_next_packet(r->ogg, &pk))) return rc;
+        if (pk.stream_serial == r->serial) break;
+        if (!pk.first_in_stream) continue;
+        // a chained stream begins: new headers, new state; its first audio packet is decoded and dropped
+        if ((rc = reader_read_headers(r, &pk))) return rc;
+        if ((rc = lwf_ogg_next_packet(r->ogg, &pk))) return rc;
+        const size_t C = r->hdr->h.ident.audio_channels, n1 = (size_t)1 << r->hdr->h.ident.blocksize_1;
+        r->scratch.resize(C * n1);
+        size_t dropped = 0;
+        if ((rc = reader_decode(r, pk, LWB_OUT_F32_PLANAR, r->scratch.data(), n1, &dropped))) return rc;
+        r->has_absgp = true;
+        r->absgp = pk.absgp_page;
+        if ((rc = lwf_ogg_next_packet(r->ogg, &pk))) return rc;
+        break;
+    }
+    size_t n = 0;
+    if ((rc = reader_decode(r, pk, out_format, out, cap, &n))) return rc;
+    if (r->has_absgp && pk.last_in_stream) {                      // inside_ogg.rs:219-222
+        const uint64_t target = pk.absgp_page > r->absgp ? pk.absgp_page - r->absgp : 0;
+        if (target < n) n = (size_t)target;
+    }
+    if (pk.last_in_page) {                                        // :223-227
+        r->has_absgp = true;
+        r->absgp = pk.absgp_page;
+    } else if (r->has_absgp) {
+        r->absgp += n;
+    }
+    *n_samples = n;
+    return LWB_OK;
+}
+
+extern "C" int lwf_reader_last_absgp(const lwf_reader *r, uint64_t *absgp)
+{
+    if (!r || !absgp) return LWB_ERR_INVALID;
+    if (!r->has_absgp) return 1;
+    *absgp = r->absgp;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// debug taps for the known-answer tests of the reference's own unit tests (bitpacking.rs:316-334,
+// :488-600, huffman_tree.rs:262-330, header.rs:650-671)
+// ---------------------------------------------------------------------------------------------
+extern "C" float lwf_debug_float32_unpack(uint32_t v) { return lwf::float32_unpack(v); }
+extern "C" uint32_t lwf_debug_lookup1_values(uint32_t entries, uint16_t dims) { return lwf::lookup1_values(entries, dims); }
+extern "C" uint8_t lwf_debug_ilog(uint64_t v) { return lwf::ilog(v); }
+// reads widths[i] bits each; returns how many reads succeeded
+extern "C" size_t lwf_debug_read_bits(const uint8_t *data, size_t len, const uint8_t *widths, size_t n, uint64_t *out)
+{
+    lwf::BitReader rdr(data, len);
+    size_t k = 0;
+    for (; k < n; k++)
+        if (!rdr.read(widths[k], &out[k])) break;
+    return k;
+}
+// builds the tree from codeword lengths (returns the HuffmanError class, 0 = ok) and decodes symbols
+// from `data` until it runs out
+extern "C" int lwf_debug_huffman(const uint8_t *lengths, size_t n, const uint8_t *data, size_t len, uint32_t *out, size_t max_out,
+                                 size_t *n_out)
+{
+    lwf::Huffman t;
+    const int rc = t.load(std::vector<uint8_t>(lengths, lengths + n));
+    if (n_out) *n_out = 0;
+    if (rc || !data || !out || !n_out) return rc;
+    lwf::BitReader rdr(data, len);
+    while (*n_out < max_out) {
+        uint32_t v;
+        if (!t.read(rdr, &v)) break;
+        out[(*n_out)++] = v;
+    }
+    return 0;
+}
