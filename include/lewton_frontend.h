@@ -105,9 +105,11 @@ int lwf_reader_open(lwb_ctx *ctx, const uint8_t *data, size_t len, lwf_reader **
 void lwf_reader_close(lwf_reader *r);
 const lwf_headers *lwf_reader_headers(const lwf_reader *r);
 /* read_dec_packet_generic: decodes the next audio packet through lwb_decode_packet.  `out_format`
- * LWB_OUT_*; `out` holds capacity_per_channel samples per channel.  *n_samples = samples per channel
- * after end-of-stream truncation.  LWF_ERR_NO_MORE_PACKETS = Ok(None). */
-int lwf_reader_read_dec_packet(lwf_reader *r, int out_format, void *out, size_t capacity_per_channel,
+ * LWB_OUT_*; `out` holds capacity_total elements in all: planar channel c starts at
+ * c * (capacity_total / channels), with the channel count of the stream the packet belongs to (a
+ * chained stream may change it: query lwf_reader_headers afterwards).  *n_samples = samples per
+ * channel after end-of-stream truncation.  LWF_ERR_NO_MORE_PACKETS = Ok(None). */
+int lwf_reader_read_dec_packet(lwf_reader *r, int out_format, void *out, size_t capacity_total,
                                size_t *n_samples);
 int lwf_reader_last_absgp(const lwf_reader *r, uint64_t *absgp);   /* returns 0 and sets *absgp if Some */
 

@@ -1440,7 +1440,7 @@ static int reader_decode(lwf_reader *r, const lwf_ogg_packet &pk, int out_format
 }
 
 // read_next_audio_packet (inside_ogg.rs:107-143) + dec_packet_generic (:213-229)
-extern "C" int lwf_reader_read_dec_packet(lwf_reader *r, int out_format, void *out, size_t cap, size_t *n_samples)
+extern "C" int lwf_reader_read_dec_packet(lwf_reader *r, int out_format, void *out, size_t cap_total, size_t *n_samples)
 {
     if (!r || !out || !n_samples) return LWB_ERR_INVALID;
     *n_samples = 0;
@@ -1463,6 +1463,7 @@ extern "C" int lwf_reader_read_dec_packet(lwf_reader *r, int out_format, void *o
         break;
     }
     size_t n = 0;
+    const size_t cap = cap_total / r->hdr->h.ident.audio_channels;
     if ((rc = reader_decode(r, pk, out_format, out, cap, &n))) return rc;
     if (r->has_absgp && pk.last_in_stream) {                      // inside_ogg.rs:219-222
         const uint64_t target = pk.absgp_page > r->absgp ? pk.absgp_page - r->absgp : 0;

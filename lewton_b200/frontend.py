@@ -264,6 +264,9 @@ class OggStreamReader:
                 raise OggReadError("code %d" % rc)
             ctx.check(rc)
         self._h = h.value
+        self._buf = None
+        # more than one logical stream in the data: the next one may have any channel count / blocksize
+        self._may_chain = self._data.count(b"OggS\x00\x02") > 1
         ctx._children.add(self)
         self._refresh()
 
@@ -272,25 +275,30 @@ class OggStreamReader:
         self.ident_hdr = self.headers
 
     def _read(self, fmt, dtype, interleaved):
-        Cn, n1 = self.headers.audio_channels, 1 << self.headers.blocksize_1
-        buf = np.zeros(Cn * n1, dtype)
+        total = 255 * 8192 if self._may_chain else self.headers.audio_channels << self.headers.blocksize_1
+        if self._buf is None or self._buf.size < total or self._buf.dtype != dtype:
+            self._buf = np.zeros(total, dtype)
+        buf = self._buf
         n = C.c_size_t()
-        rc = lib().lwf_reader_read_dec_packet(self._h, fmt, buf.ctypes.data, n1, C.byref(n))
+        rc = lib().lwf_reader_read_dec_packet(self._h, fmt, buf.ctypes.data, buf.size, C.byref(n))
         if rc == ERR_NO_MORE_PACKETS:
             return None
         if rc == cabi.ERR_BAD_FORMAT:
             raise AudioReadError(rc)
         if 16 <= rc <= 23:
-            raise AudioReadError(rc, "code %d" % rc)
+            e = AudioReadError(rc)
+            e.kind = {ERR_END_OF_PACKET: "EndOfPacket", ERR_AUDIO_IS_HEADER: "AudioIsHeader"}.get(rc, "Header error %d" % rc)
+            raise e
         if rc >= ERR_OGG:
             raise OggReadError("code %d" % rc)
         self.ctx.check(rc)
         if lib().lwf_reader_headers(self._h) != self.headers._h:
             self._refresh()                      # a chained stream started
-            Cn = self.headers.audio_channels
+        Cn = self.headers.audio_channels
         if interleaved:
             return buf[: n.value * Cn].copy()
-        return [buf[c * n1: c * n1 + n.value].copy() for c in range(Cn)]
+        cap = buf.size // Cn
+        return [buf[c * cap: c * cap + n.value].copy() for c in range(Cn)]
 
     def read_dec_packet(self):
         """Vec<Vec<i16>> or None"""

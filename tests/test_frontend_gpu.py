@@ -1,0 +1,200 @@
+"""End to end on the GPU: synthetic Ogg/Vorbis bytes (tests/vorbis_packer.py) -> host front half
+(Ogg paging, headers, entropy decode) -> CUDA synthesis, against the CPU oracle fed with what the
+packer knows it encoded.  Covers the OggStreamReader loop (per packet, inside_ogg.rs:60-227: sample
+counts, end-of-stream truncation, absgp accounting) and the batched residue entry driven by real
+bitstreams (SURVEY.md configs 1 and 3 shapes)."""
+import numpy as np
+import pytest
+
+import lewton_b200 as L
+import vorbis_packer as vp
+from helpers import RefStream, bits_equal, mismatch_report
+from lewton_b200 import _cabi as cabi
+from lewton_b200 import frontend as fe
+from test_frontend_cpu import floor0_expected
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = L.Context(0)
+    yield c
+    c.close()
+
+
+def consistent_modes(spec, rng, n_packets, p_short=0.3):
+    """A legal block sequence: (mode, prev_flag, next_flag) per packet, flags describing the neighbours."""
+    short_modes = [i for i, (bf, _) in enumerate(spec.modes) if not bf]
+    long_modes = [i for i, (bf, _) in enumerate(spec.modes) if bf]
+    bf = [(rng.random() >= p_short) for _ in range(n_packets)]
+    out = []
+    for i in range(n_packets):
+        mode = int(rng.choice(long_modes if bf[i] else short_modes))
+        prev = int(bf[i - 1]) if i else 1
+        nxt = int(bf[i + 1]) if i + 1 < n_packets else 1
+        out.append((mode, prev, nxt))
+    return out
+
+
+def build_stream(seed, channels, floor0, n_packets, serial=1, cut_last=0):
+    rng = np.random.default_rng(seed)
+    spec = vp.StreamSpec(rng, channels=channels, floor0=floor0)
+    seq = consistent_modes(spec, rng, n_packets)
+    packets, infos = [], []
+    for mode, prev, nxt in seq:
+        pk, info = spec.audio_packet(mode, prev, nxt, p_unused=0.15)
+        packets.append(pk)
+        infos.append(info)
+    return spec, packets, infos
+
+
+def oracle_pcm(oracle, spec, infos):
+    """Decode the packer's own record of every packet with the CPU oracle: list of [channels][n] f32."""
+    floors = [(f.multiplier, f.x_list) if isinstance(f, vp.Floor1) else (1, [0, 128]) for f in spec.floors]
+    mappings = []
+    for m in spec.mappings:
+        mappings.append({"coupling": m["coupling"], "floor_of_channel": [m["floors"][m["mux"][c]] for c in range(spec.channels)]})
+    ref = RefStream(oracle, spec.channels, spec.bs0, spec.bs1, spec.modes, mappings, floors)
+    out = []
+    for info in infos:
+        fl_exp, res = spec.expected(info)
+        n2 = info["n"] // 2
+        fl = []
+        for f in fl_exp:
+            if f is None:
+                fl.append(None)
+            elif f[0] == "one":
+                fl.append(list(f[1]))
+            else:
+                fl.append(floor0_expected(f[3], f[1], f[2], info["blockflag"], n2, spec.bs0, spec.bs1))
+        rc, pcm = ref.packet(info["mode"], info["prev"], info["next"], res, fl)
+        assert rc == 0
+        out.append(pcm)
+    return out, ref
+
+
+def page_granules(pcm_list, per_page, cut_last):
+    """absgp of each audio page = samples decoded up to its last packet; the last page claims
+    `cut_last` samples fewer (end-of-stream truncation, inside_ogg.rs:219-222)."""
+    tot, out = 0, []
+    for i in range(0, len(pcm_list), per_page):
+        tot += sum(p.shape[1] for p in pcm_list[i: i + per_page])
+        out.append(tot)
+    out[-1] -= cut_last
+    return out
+
+
+@pytest.mark.parametrize("seed,channels,floor0", [(101, 2, False), (102, 1, True), (103, 6, False), (104, 2, True)])
+def test_ogg_stream_reader_end_to_end(ctx, oracle, seed, channels, floor0):
+    spec, packets, infos = build_stream(seed, channels, floor0, 14)
+    want, ref = oracle_pcm(oracle, spec, infos)
+    cut = 37
+    assert want[-1].shape[1] > cut
+    data = vp.ogg_stream(0x1234, [spec.ident_packet(), spec.comment_packet(), spec.setup_packet()], packets,
+                         page_granules(want, 3, cut), packets_per_page=3)
+    for api in ("f32", "i16", "itl"):
+        rd = fe.OggStreamReader(ctx, data)
+        assert rd.headers.audio_channels == channels and rd.headers.vendor == spec.vendor
+        assert rd.get_last_absgp() is None
+        total = 0
+        for i, w in enumerate(want):
+            n = w.shape[1] - (cut if i == len(want) - 1 else 0)
+            if api == "f32":
+                got = rd.read_dec_packet_f32()
+                assert len(got) == channels and all(len(g) == n for g in got), (i, n, [len(g) for g in got])
+                assert bits_equal(np.array(got).reshape(channels, n), w[:, :n]), (i, mismatch_report(np.array(got), w[:, :n]))
+            elif api == "i16":
+                got = rd.read_dec_packet()
+                assert np.array_equal(np.array(got).reshape(channels, n), oracle.quantise_i16(w[:, :n])), i
+            else:
+                got = rd.read_dec_packet_itl()
+                assert np.array_equal(got.reshape(n, channels), oracle.quantise_i16(w[:, :n]).T), i
+            total += n
+            if (i + 1) % 3 == 0 or i == len(want) - 1:
+                assert rd.get_last_absgp() == sum(x.shape[1] for x in want[: i + 1]) - (cut if i == len(want) - 1 else 0)
+        assert rd.read_dec_packet() is None
+        rd.close()
+
+
+def test_chained_streams_reset_the_decoder(ctx, oracle):
+    """inside_ogg.rs:118-141: a new logical stream (other serial, bos page) brings new headers and a fresh
+    PreviousWindowRight; its first audio packet is decoded and dropped, reading continues with the second."""
+    a = build_stream(201, 2, False, 6)
+    b = build_stream(202, 1, False, 7)
+    want_a, _ = oracle_pcm(oracle, a[0], a[2])
+    want_b, _ = oracle_pcm(oracle, b[0], b[2])
+    data = (vp.ogg_stream(11, [a[0].ident_packet(), a[0].comment_packet(), a[0].setup_packet()], a[1], page_granules(want_a, 2, 0), 2) +
+            vp.ogg_stream(22, [b[0].ident_packet(), b[0].comment_packet(), b[0].setup_packet()], b[1], page_granules(want_b, 2, 0), 2))
+    rd = fe.OggStreamReader(ctx, data)
+    for w in want_a:
+        got = rd.read_dec_packet_f32()
+        assert bits_equal(np.array(got).reshape(2, -1), w)
+    got = rd.read_dec_packet_f32()                       # first packet handed out from the second stream: its packet 1
+    assert rd.headers.audio_channels == 1
+    assert bits_equal(np.array(got).reshape(1, -1), want_b[1])
+    for w in want_b[2:]:
+        got = rd.read_dec_packet_f32()
+        assert bits_equal(np.array(got).reshape(1, -1), w)
+    assert rd.read_dec_packet_f32() is None
+    rd.close()
+
+
+@pytest.mark.parametrize("memory", [cabi.MEM_HOST, cabi.MEM_DEVICE])
+def test_batched_residue_entry_from_real_bitstreams(ctx, oracle, memory):
+    """Many streams sharing one setup: the host front half decodes every packet's floors and residue,
+    one lwb_decode_chains call (residue entry) synthesises all of them; bit-identical to the oracle and
+    to the per-packet reader."""
+    rng = np.random.default_rng(301)
+    channels, S, P = 2, 9, 10
+    spec = vp.StreamSpec(rng, channels=channels)
+    hdr = fe.Headers(spec.ident_packet(), spec.comment_packet(), spec.setup_packet())
+    su = hdr.make_setup(ctx)
+    streams, wants = [], []
+    for s in range(S):
+        seq = consistent_modes(spec, rng, P, p_short=0.25)
+        infos, pkts = [], []
+        for mode, prev, nxt in seq:
+            pk, info = spec.audio_packet(mode, prev, nxt)
+            pkts.append(pk)
+            infos.append(info)
+        w, _ = oracle_pcm(oracle, spec, infos)
+        streams.append((pkts, infos))
+        wants.append(np.concatenate(w, axis=1))
+    coeffs, kinds, ys, chains = [], [], [], []
+    pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+    coeff_off = out_off = 0
+    for s, (pkts, infos) in enumerate(streams):
+        dps = [hdr.decode_packet(pk) for pk in pkts]
+        for dp in dps:
+            k, y, d = dp.pack()
+            assert d is None
+            kinds.append(k)
+            ys.append(y)
+            coeffs.append(dp.residue.ravel())
+        n = wants[s].shape[1]
+        chains.append(L.ChainSpec(pwrs[s], np.array([dp.mode_number for dp in dps], np.uint8),
+                                  np.array([dp.prev_window_flag for dp in dps], np.uint8),
+                                  np.array([dp.next_window_flag for dp in dps], np.uint8),
+                                  coeff_offset=coeff_off, packet_index=s * P, out_offset=out_off, out_stride=n))
+        coeff_off += sum(dp.residue.size for dp in dps)
+        out_off += n * channels
+    coeffs, kinds, ys = np.concatenate(coeffs), np.concatenate(kinds), np.concatenate(ys)
+    pcm = np.zeros(out_off, np.float32)
+    if memory == cabi.MEM_HOST:
+        L.decode_chains(ctx, chains, cabi.ENTRY_RESIDUE, memory, coeffs, pcm, cabi.OUT_F32_PLANAR, floor_kind=kinds, floor1_y=ys)
+    else:
+        d_in, d_out = ctx.device_alloc(coeffs.nbytes), ctx.device_alloc(pcm.nbytes)
+        ctx.h2d(d_in, coeffs)
+        L.decode_chains(ctx, chains, cabi.ENTRY_RESIDUE, memory, d_in, d_out, cabi.OUT_F32_PLANAR, floor_kind=kinds, floor1_y=ys)
+        ctx.synchronize()
+        ctx.d2h(pcm, d_out)
+        ctx.device_free(d_in)
+        ctx.device_free(d_out)
+    pos = 0
+    for s in range(S):
+        n = wants[s].shape[1]
+        assert chains[s].status == 0 and chains[s].n_samples == n, s
+        got = pcm[pos: pos + n * channels].reshape(channels, n)
+        assert bits_equal(got, wants[s]), (s, mismatch_report(got, wants[s]))
+        pos += n * channels
