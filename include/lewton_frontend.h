@@ -113,6 +113,32 @@ int lwf_reader_read_dec_packet(lwf_reader *r, int out_format, void *out, size_t 
                                size_t *n_samples);
 int lwf_reader_last_absgp(const lwf_reader *r, uint64_t *absgp);   /* returns 0 and sets *absgp if Some */
 
+/* ---- many streams at once: host entropy decode on a thread pool, one batched synthesis call ---- */
+/* The shape of a decode server (BASELINE configs 1/3 at scale): packets of many logical streams that
+ * share one set of headers are entropy-decoded in parallel on the host straight into pinned arenas
+ * (residue vectors, floor posts), then synthesised by ONE lwb_decode_chains call (residue entry,
+ * host memory).  Streams are independent; packets within a stream keep their order. */
+typedef struct lwf_stream_job {
+    lwb_stream *stream;               /* PreviousWindowRight of this logical stream                  */
+    uint32_t n_packets;
+    const uint8_t *const *packets;    /* [n_packets] audio packets in stream order                   */
+    const size_t *lengths;            /* [n_packets]                                                 */
+    uint64_t out_offset;              /* element offset of this stream's PCM in `pcm`                */
+    uint64_t out_stride;              /* planar formats: elements between channel planes             */
+    /* results */
+    uint32_t n_samples;               /* samples per channel produced                                */
+    uint32_t packets_done;            /* packets synthesised (== n_packets unless status != 0)       */
+    int32_t status;                   /* LWB_OK, or the error of packet `packets_done`               */
+} lwf_stream_job;
+
+typedef struct lwf_batcher lwf_batcher;
+/* `setup` must come from lwf_headers_make_setup(h, ctx); threads <= 0: one per host CPU */
+int lwf_batcher_create(lwb_ctx *ctx, const lwf_headers *h, int threads, lwf_batcher **out);
+void lwf_batcher_destroy(lwf_batcher *b);
+int lwf_batcher_decode(lwf_batcher *b, lwf_stream_job *jobs, size_t n_jobs, int out_format, void *pcm);
+/* wall-clock seconds of the last lwf_batcher_decode: host entropy decode, synthesis call */
+void lwf_batcher_last_timing(const lwf_batcher *b, double *entropy_seconds, double *synthesis_seconds);
+
 /* ---- debug taps (known-answer tests of the reference's unit-test vectors) ---------------------- */
 float lwf_debug_float32_unpack(uint32_t v);                          /* bitpacking.rs:304-314        */
 uint32_t lwf_debug_lookup1_values(uint32_t entries, uint16_t dims);  /* header.rs:616-649            */

@@ -4,12 +4,15 @@
 // whose behaviour (including its quirks) it restates.  f32 arithmetic is written in the reference's
 // expression order and compiled without contraction (-ffp-contract=off, csrc/Makefile).
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <memory>
 #include <new>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -1485,6 +1488,175 @@ extern "C" int lwf_reader_last_absgp(const lwf_reader *r, uint64_t *absgp)
     if (!r->has_absgp) return 1;
     *absgp = r->absgp;
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lwf_batcher: parallel host entropy decode + one batched synthesis call
+// ---------------------------------------------------------------------------------------------
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t bytes)
+    {
+        if (bytes <= cap) return true;
+        if (p) lwb_host_free(p);
+        cap = bytes + bytes / 4 + 4096;
+        p = lwb_host_alloc(cap);
+        if (!p) cap = 0;
+        return p != nullptr;
+    }
+    ~PinnedBuf() { if (p) lwb_host_free(p); }
+};
+
+struct lwf_batcher {
+    lwb_ctx *ctx = nullptr;
+    const lwf_headers *hdr = nullptr;
+    int threads = 1;
+    bool has_floor0 = false;
+    PinnedBuf coeffs, dense, kinds, ys;
+    std::vector<uint8_t> modes, prevs, nexts;
+    std::vector<lwb_chain> chains;
+    double t_entropy = 0, t_synth = 0;
+};
+
+extern "C" int lwf_batcher_create(lwb_ctx *ctx, const lwf_headers *h, int threads, lwf_batcher **out)
+{
+    if (!ctx || !h || !out) return LWB_ERR_INVALID;
+    lwf_batcher *b = new (std::nothrow) lwf_batcher();
+    if (!b) return LWB_ERR_BUFFER;
+    b->ctx = ctx;
+    b->hdr = h;
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    b->threads = std::max(1, threads);
+    for (const auto &fl : h->h.floors) b->has_floor0 |= fl.type == 0;
+    *out = b;
+    return LWB_OK;
+}
+
+extern "C" void lwf_batcher_destroy(lwf_batcher *b) { delete b; }
+
+extern "C" void lwf_batcher_last_timing(const lwf_batcher *b, double *e, double *s)
+{
+    if (!b) return;
+    if (e) *e = b->t_entropy;
+    if (s) *s = b->t_synth;
+}
+
+static double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" int lwf_batcher_decode(lwf_batcher *b, lwf_stream_job *jobs, size_t n_jobs, int out_format, void *pcm)
+{
+    if (!b || (!jobs && n_jobs) || !pcm) return LWB_ERR_INVALID;
+    const lwf::Headers &H = b->hdr->h;
+    const size_t C = H.ident.audio_channels;
+    const double t0 = now_s();
+    // pass 1 (cheap, serial): packet headers -> blocksizes -> arena offsets.  A packet whose header
+    // cannot be read ends its stream's chain there (its error is reported after the earlier ones ran).
+    struct JobPlan { uint64_t coeff0, pkt0; uint32_t usable; int32_t head_status; };
+    std::vector<JobPlan> plan(n_jobs);
+    uint64_t coeff_total = 0, pkt_total = 0;
+    for (size_t j = 0; j < n_jobs; j++) {
+        lwf_stream_job &job = jobs[j];
+        if (!job.stream || (job.n_packets && (!job.packets || !job.lengths))) return LWB_ERR_INVALID;
+        plan[j] = JobPlan{coeff_total, pkt_total, 0, LWB_OK};
+        for (uint32_t k = 0; k < job.n_packets; k++) {
+            lwf::BitReader rdr(job.packets[k], job.lengths[k]);
+            lwf::PacketHead ph;
+            const int rc = lwf::packet_head(H, rdr, &ph);
+            if (rc) { plan[j].head_status = rc; break; }
+            coeff_total += (uint64_t)C * (ph.n / 2);
+            plan[j].usable++;
+        }
+        pkt_total += plan[j].usable;
+    }
+    const size_t rows = (size_t)pkt_total * C;
+    if (!b->coeffs.ensure((size_t)coeff_total * 4 + 16) || !b->kinds.ensure(rows + 16) || !b->ys.ensure(rows * LWB_MAX_POSTS * 4 + 16) ||
+        (b->has_floor0 && !b->dense.ensure((size_t)coeff_total * 4 + 16)))
+        return LWB_ERR_BUFFER;
+    b->modes.resize(pkt_total);
+    b->prevs.resize(pkt_total);
+    b->nexts.resize(pkt_total);
+    float *coeffs = (float *)b->coeffs.p, *dense = b->has_floor0 ? (float *)b->dense.p : nullptr;
+    uint8_t *kinds = (uint8_t *)b->kinds.p;
+    uint32_t *ys = (uint32_t *)b->ys.p;
+    // pass 2 (parallel over streams): entropy decode straight into the arenas
+    std::vector<uint32_t> decoded(n_jobs, 0);
+    std::vector<int32_t> dec_status(n_jobs, LWB_OK);
+    std::atomic<size_t> next_job(0);
+    auto worker = [&]() {
+        std::vector<float> scratch_dense;
+        for (;;) {
+            const size_t j = next_job.fetch_add(1);
+            if (j >= n_jobs) break;
+            const lwf_stream_job &job = jobs[j];
+            uint64_t coff = plan[j].coeff0;
+            for (uint32_t k = 0; k < plan[j].usable; k++) {
+                const uint64_t pi = plan[j].pkt0 + k;
+                lwf_decoded_packet dp;
+                std::memset(&dp, 0, sizeof(dp));
+                dp.floor_kind = kinds + pi * C;
+                dp.floor1_y = ys + pi * C * LWB_MAX_POSTS;
+                dp.residue = coeffs + coff;
+                dp.dense_floor = dense ? dense + coff : nullptr;
+                const int rc = lwf::packet_decode(H, job.packets[k], job.lengths[k], &dp);
+                if (rc) { dec_status[j] = rc; break; }
+                b->modes[pi] = dp.mode_number;
+                b->prevs[pi] = dp.prev_window_flag;
+                b->nexts[pi] = dp.next_window_flag;
+                coff += (uint64_t)C * (dp.n / 2);
+                decoded[j]++;
+            }
+        }
+    };
+    {
+        const int nt = (int)std::min<size_t>((size_t)b->threads, std::max<size_t>(1, n_jobs));
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; t++) pool.emplace_back(worker);
+        worker();
+        for (auto &t : pool) t.join();
+    }
+    const double t1 = now_s();
+    // one synthesis call
+    b->chains.assign(n_jobs, lwb_chain());
+    for (size_t j = 0; j < n_jobs; j++) {
+        lwb_chain &c = b->chains[j];
+        std::memset(&c, 0, sizeof(c));
+        c.stream = jobs[j].stream;
+        c.n_packets = decoded[j];
+        c.mode_numbers = b->modes.data() + plan[j].pkt0;
+        c.prev_window_flags = b->prevs.data() + plan[j].pkt0;
+        c.next_window_flags = b->nexts.data() + plan[j].pkt0;
+        c.coeff_offset = plan[j].coeff0;
+        c.packet_index = plan[j].pkt0;
+        c.out_offset = jobs[j].out_offset;
+        c.out_stride = jobs[j].out_stride;
+    }
+    lwb_batch_io io;
+    std::memset(&io, 0, sizeof(io));
+    io.entry = LWB_ENTRY_RESIDUE;
+    io.memory = LWB_MEM_HOST;
+    io.coeffs = coeffs;
+    io.dense_floor = dense;
+    io.floor_kind = kinds;
+    io.floor1_y = ys;
+    io.out_format = out_format;
+    io.pcm = pcm;
+    const int rc = lwb_decode_chains(b->ctx, b->chains.data(), n_jobs, &io);
+    b->t_entropy = t1 - t0;
+    b->t_synth = now_s() - t1;
+    if (rc) return rc;
+    for (size_t j = 0; j < n_jobs; j++) {
+        const lwb_chain &c = b->chains[j];
+        jobs[j].n_samples = c.n_samples;
+        jobs[j].packets_done = c.packets_done;
+        jobs[j].status = c.status;
+        if (c.status == LWB_OK && c.packets_done == decoded[j] && decoded[j] < jobs[j].n_packets)
+            jobs[j].status = dec_status[j] != LWB_OK ? dec_status[j] : plan[j].head_status;
+    }
+    return LWB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

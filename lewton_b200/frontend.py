@@ -21,6 +21,7 @@ from .api import AudioReadError, DecodedPacket, Setup
 SYMBOLS = ["lwf_headers_parse", "lwf_headers_destroy", "lwf_headers_info", "lwf_headers_comment", "lwf_headers_make_setup",
            "lwf_packet_decode", "lwf_decoded_sample_count", "lwf_ogg_open", "lwf_ogg_close", "lwf_ogg_next_packet",
            "lwf_reader_open", "lwf_reader_close", "lwf_reader_headers", "lwf_reader_read_dec_packet", "lwf_reader_last_absgp",
+           "lwf_batcher_create", "lwf_batcher_destroy", "lwf_batcher_decode", "lwf_batcher_last_timing",
            "lwf_debug_float32_unpack", "lwf_debug_lookup1_values", "lwf_debug_ilog", "lwf_debug_read_bits", "lwf_debug_huffman"]
 
 
@@ -59,6 +60,12 @@ class _OggPacket(C.Structure):
                 ("last_in_page", C.c_uint8)]
 
 
+class _StreamJob(C.Structure):
+    _fields_ = [("stream", C.c_void_p), ("n_packets", C.c_uint32), ("packets", C.POINTER(C.c_char_p)),
+                ("lengths", C.POINTER(C.c_size_t)), ("out_offset", C.c_uint64), ("out_stride", C.c_uint64),
+                ("n_samples", C.c_uint32), ("packets_done", C.c_uint32), ("status", C.c_int32)]
+
+
 _declared = False
 
 
@@ -87,6 +94,12 @@ def lib():
         L.lwf_reader_headers.restype = vp
         L.lwf_reader_read_dec_packet.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz)]
         L.lwf_reader_last_absgp.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.lwf_batcher_create.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+        L.lwf_batcher_destroy.argtypes = [vp]
+        L.lwf_batcher_destroy.restype = None
+        L.lwf_batcher_decode.argtypes = [vp, C.POINTER(_StreamJob), sz, C.c_int, vp]
+        L.lwf_batcher_last_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.lwf_batcher_last_timing.restype = None
         L.lwf_debug_float32_unpack.argtypes = [C.c_uint32]
         L.lwf_debug_float32_unpack.restype = C.c_float
         L.lwf_debug_lookup1_values.argtypes = [C.c_uint32, C.c_uint16]
@@ -319,6 +332,57 @@ class OggStreamReader:
     def close(self):
         if self._h:
             lib().lwf_reader_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class StreamBatcher:
+    """lwf_batcher: entropy-decode the packets of many streams (one shared set of headers) on a host
+    thread pool and synthesise them with one batched call.  jobs: list of (PreviousWindowRight,
+    [packet bytes, ...]); PCM lands planar in `pcm` at out_offset = job index * channels * stride."""
+
+    def __init__(self, ctx, headers, threads=0):
+        self.ctx, self.headers = ctx, headers
+        h = C.c_void_p()
+        ctx.check(lib().lwf_batcher_create(ctx._h, headers._h, threads, C.byref(h)))
+        self._h = h.value
+        ctx._children.add(self)
+
+    def decode(self, jobs, pcm, stride, out_format=cabi.OUT_F32_PLANAR):
+        n = len(jobs)
+        arr = (_StreamJob * n)()
+        keep = []
+        Cn = self.headers.audio_channels
+        for j, (pwr, packets) in enumerate(jobs):
+            pk = (C.c_char_p * len(packets))(*packets)
+            ln = (C.c_size_t * len(packets))(*[len(p) for p in packets])
+            keep.append((pk, ln))
+            arr[j].stream = pwr._h
+            arr[j].n_packets = len(packets)
+            arr[j].packets = pk
+            arr[j].lengths = ln
+            arr[j].out_offset = j * Cn * stride
+            arr[j].out_stride = stride
+        self.prepared = (arr, keep, n)
+        return self.run(pcm, out_format)
+
+    def run(self, pcm, out_format=cabi.OUT_F32_PLANAR):
+        """Decode the jobs of the last decode() again (same packets; benchmarking)."""
+        arr, _, n = self.prepared
+        self.ctx.check(lib().lwf_batcher_decode(self._h, arr, n, out_format, pcm.ctypes.data))
+        e, s = C.c_double(), C.c_double()
+        lib().lwf_batcher_last_timing(self._h, C.byref(e), C.byref(s))
+        self.entropy_seconds, self.synthesis_seconds = e.value, s.value
+        return [(arr[j].n_samples, arr[j].packets_done, arr[j].status) for j in range(n)]
+
+    def close(self):
+        if self._h:
+            lib().lwf_batcher_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -198,3 +198,49 @@ def test_batched_residue_entry_from_real_bitstreams(ctx, oracle, memory):
         got = pcm[pos: pos + n * channels].reshape(channels, n)
         assert bits_equal(got, wants[s]), (s, mismatch_report(got, wants[s]))
         pos += n * channels
+
+
+def test_stream_batcher_parallel_entropy_decode_one_synthesis_call(ctx, oracle):
+    """lwf_batcher: 24 streams (6 distinct bitstreams x 4) decoded by 4 host threads + one batched
+    synthesis call; every stream bit-identical to the oracle; a corrupt packet ends only its own stream."""
+    rng = np.random.default_rng(401)
+    channels, P = 2, 9
+    spec = vp.StreamSpec(rng, channels=channels, floor0=True)
+    hdr = fe.Headers(spec.ident_packet(), spec.comment_packet(), spec.setup_packet())
+    su = hdr.make_setup(ctx)
+    distinct = []
+    for d in range(6):
+        seq = consistent_modes(spec, rng, P, p_short=0.3)
+        pkts, infos = [], []
+        for mode, prev, nxt in seq:
+            pk, info = spec.audio_packet(mode, prev, nxt)
+            pkts.append(pk)
+            infos.append(info)
+        w, _ = oracle_pcm(oracle, spec, infos)
+        distinct.append((pkts, w))
+    S = 24
+    jobs, pwrs = [], []
+    for s in range(S):
+        pw = L.PreviousWindowRight(su)
+        pwrs.append(pw)
+        jobs.append((pw, list(distinct[s % 6][0])))
+    # stream 5: its 4th packet claims to be a header packet
+    jobs[5] = (jobs[5][0], jobs[5][1][:3] + [b"\x01bad"] + jobs[5][1][4:])
+    stride = P * 1024
+    pcm = np.full(S * channels * stride, np.nan, np.float32)
+    bt = fe.StreamBatcher(ctx, hdr, threads=4)
+    res = bt.decode(jobs, pcm, stride)
+    for s in range(S):
+        n_samples, done, status = res[s]
+        w = distinct[s % 6][1]
+        if s == 5:
+            assert done == 3 and status == fe.ERR_AUDIO_IS_HEADER
+            w = w[:3]
+        else:
+            assert done == P and status == 0
+        want = np.concatenate(w, axis=1)
+        assert n_samples == want.shape[1]
+        got = pcm[s * channels * stride:(s + 1) * channels * stride].reshape(channels, stride)[:, :n_samples]
+        assert bits_equal(got, want), (s, mismatch_report(got, want))
+    assert bt.entropy_seconds > 0 and bt.synthesis_seconds > 0
+    bt.close()

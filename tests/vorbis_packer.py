@@ -313,7 +313,7 @@ class Floor0:
 
 
 class Residue:
-    def __init__(self, rng, books, vq_book_ids, class_book_ids, n2_long, rtype=None):
+    def __init__(self, rng, books, vq_book_ids, class_book_ids, n2_long, rtype=None, cascade_p=0.5):
         self.type = int(rng.integers(0, 3)) if rtype is None else rtype
         self.classifications = int(rng.integers(1, 5))
         # classbook: dims = classwords per codeword, entries >= classifications ** dims, all used
@@ -330,7 +330,8 @@ class Residue:
         self.cascade = []
         self.books = []
         for _ in range(self.classifications):
-            c = int(rng.integers(0, 128)) if rng.random() < 0.8 else 0        # bit 7 is never read back by lewton
+            # bit 7 is never read back by lewton (ResidueBook::read_book reads 7 books)
+            c = sum(1 << q for q in range(7) if rng.random() < cascade_p) if rng.random() < 0.8 else 0
             row = []
             for p in range(8):
                 if c & (1 << p):
@@ -443,7 +444,8 @@ class Residue:
 class StreamSpec:
     """A random valid set of headers.  channels, blocksizes (log2), and knobs for which features appear."""
 
-    def __init__(self, rng, channels=2, bs0=8, bs1=11, floor0=False, n_modes=None, sample_rate=44100, residue_types=None):
+    def __init__(self, rng, channels=2, bs0=8, bs1=11, floor0=False, n_modes=None, sample_rate=44100, residue_types=None,
+                 cascade_p=0.5):
         self.rng = rng
         self.channels, self.bs0, self.bs1, self.sample_rate = channels, bs0, bs1, sample_rate
         # codebooks: scalar books first (floor-1 values / class words), then VQ books
@@ -474,7 +476,7 @@ class StreamSpec:
         n2_long = (1 << bs1) // 2
         rts = residue_types or [None] * int(rng.integers(1, 4))
         for rt in rts:
-            self.residues.append(Residue(rng, self.books, vq_ids, class_ids, n2_long, rt))
+            self.residues.append(Residue(rng, self.books, vq_ids, class_ids, n2_long, rt, cascade_p))
         self.mappings = []
         for _ in range(int(rng.integers(1, 3))):
             submaps = int(rng.integers(1, min(3, channels) + 1))
