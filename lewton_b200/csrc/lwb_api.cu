@@ -1547,11 +1547,26 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             }
         }
         // descriptors of every round: [LongRun...][ChainDesc...][DevPacket (prologue of the long segments)...][mode bytes]
+        // A round with few fused-kernel runs leaves most of the 148 x 8 warps idle and lasts as long as its
+        // longest run: such rounds cut their runs (each cut costs one extra IMDCT, the primer packet whose
+        // right half is all the next piece needs), as the all-long path does.
+        const size_t target_runs = (size_t)ctx->sm_count * kLongWarps * 2;
+        constexpr uint32_t kMinCutRun = 6;
+        std::vector<size_t> round_long(max_rounds, 0);
+        for (size_t i = 0; i < n_chains; i++)
+            for (uint32_t q = 0; q < walks[i].n_seg; q++)
+                if (segs[walks[i].seg0 + q].is_long) round_long[q] += chains[i].stream->setup->channels;
+        std::vector<uint32_t> round_cut(max_rounds, 1);
+        if (!getenv("LWB_MIXED_NO_CUTS"))
+            for (size_t r = 0; r < max_rounds; r++)
+                if (round_long[r] && round_long[r] < target_runs)
+                    round_cut[r] = (uint32_t)std::min<size_t>(16, (target_runs + round_long[r] - 1) / round_long[r]);
+        auto cuts_of = [&](const Seg &sg, size_t r) { return std::max<uint32_t>(1, std::min(round_cut[r], sg.n / kMinCutRun)); };
         size_t n_runs = 0, n_cd = 0, n_pro = 0;
         for (size_t i = 0; i < n_chains; i++)
             for (uint32_t q = 0; q < walks[i].n_seg; q++) {
                 const Seg &sg = segs[walks[i].seg0 + q];
-                if (sg.is_long) { n_runs += chains[i].stream->setup->channels; if (residue) n_pro += sg.n; }
+                if (sg.is_long) { n_runs += (size_t)chains[i].stream->setup->channels * cuts_of(sg, q); if (residue) n_pro += sg.n; }
                 else n_cd++;
             }
         // a prepared batch (device memory, spectrum entry) owns its descriptors so that later executions replay them
@@ -1583,23 +1598,39 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 for (size_t i = 0; i < n_chains; i++) {
                     if (r >= walks[i].n_seg) continue;
                     const Seg &sg = segs[walks[i].seg0 + r];
-                    if (!sg.is_long || (sg.n >= 32 ? 0 : sg.n >= 8 ? 1 : 2) != bucket) continue;
+                    if (!sg.is_long) continue;
+                    const uint32_t cuts = cuts_of(sg, r), piece = sg.n / cuts;
+                    if ((piece >= 32 ? 0 : piece >= 8 ? 1 : 2) != bucket) continue;
                     const lwb_chain *c = &chains[i];
                     const lwb_stream *s = c->stream;
                     const lwb_setup *su = s->setup;
                     const unsigned C = su->channels;
+                    // samples packet 0 emits (0 without history; a block after a short one emits 1024 - ls)
+                    const size_t first_emit = sg.has ? (sg.first_short ? (size_t)kLongN2 - ls_long : (size_t)kLongN2) : 0;
                     for (unsigned ch = 0; ch < C; ch++) {
-                        LongRun &lr = h_runs[wr++];
-                        std::memset(&lr, 0, sizeof(lr));
-                        lr.in = (residue ? d_spec : d_coeffs) + sg.coeff + (size_t)ch * kLongN2;
-                        lr.in_stride = (uint32_t)(C * kLongN2);
-                        lr.out = d_pcm + (c->out_offset + (size_t)ch * c->out_stride + sg.pos) * esz;
-                        lr.state = s->d_state + (size_t)ch * state_stride(su);
-                        lr.n_packets = sg.n;
-                        lr.has_prev = sg.has;
-                        lr.write_state = 1;
-                        lr.first_short = sg.first_short;
-                        lr.last_short = sg.last_short;
+                        const float *in0 = (residue ? d_spec : d_coeffs) + sg.coeff + (size_t)ch * kLongN2;
+                        char *out0 = d_pcm + (c->out_offset + (size_t)ch * c->out_stride + sg.pos) * esz;
+                        for (uint32_t k = 0; k < cuts; k++) {
+                            const size_t p0 = (size_t)sg.n * k / cuts, p1 = (size_t)sg.n * (k + 1) / cuts;
+                            LongRun &lr = h_runs[wr++];
+                            std::memset(&lr, 0, sizeof(lr));
+                            lr.in_stride = (uint32_t)(C * kLongN2);
+                            lr.state = s->d_state + (size_t)ch * state_stride(su);
+                            lr.write_state = (k + 1 == cuts);
+                            lr.last_short = (k + 1 == cuts) && sg.last_short;
+                            if (k == 0) {
+                                lr.in = in0;
+                                lr.out = out0;
+                                lr.n_packets = (uint32_t)(p1 - p0);
+                                lr.has_prev = sg.has;
+                                lr.first_short = sg.first_short;
+                            } else {
+                                lr.in = in0 + (p0 - 1) * (size_t)lr.in_stride;         // primer = packet p0 - 1
+                                lr.out = out0 + (first_emit + (p0 - 1) * (size_t)kLongN2) * esz;
+                                lr.n_packets = (uint32_t)(p1 - p0 + 1);
+                                lr.has_prev = 0;
+                            }
+                        }
                     }
                     if (residue)
                         for (uint32_t q = 0; q < sg.n; q++) {

@@ -685,17 +685,20 @@ def test_chain_kernel_vs_four_kernel_path_mixed_sequences(ctx, oracle, channels,
     assert np.array_equal(outs["chain"].view(np.uint8), outs["four"].view(np.uint8))
 
 
-@pytest.mark.parametrize("entry,memory,fmt,seed", [("spectrum", cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 80),
-                                                   ("spectrum", cabi.MEM_DEVICE, cabi.OUT_I16_PLANAR, 81),
-                                                   ("residue", cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 82),
-                                                   ("residue", cabi.MEM_DEVICE, cabi.OUT_F32_PLANAR, 83)])
-def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle, entry, memory, fmt, seed):
+@pytest.mark.parametrize("entry,memory,fmt,seed,bs0", [("spectrum", cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 80, 8),
+                                                       ("spectrum", cabi.MEM_DEVICE, cabi.OUT_I16_PLANAR, 81, 8),
+                                                       ("residue", cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 82, 8),
+                                                       ("residue", cabi.MEM_DEVICE, cabi.OUT_F32_PLANAR, 83, 8),
+                                                       ("spectrum", cabi.MEM_DEVICE, cabi.OUT_F32_PLANAR, 84, 6),
+                                                       ("spectrum", cabi.MEM_HOST, cabi.OUT_I16_PLANAR, 85, 10),
+                                                       ("residue", cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 86, 11)])
+def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle, entry, memory, fmt, seed, bs0):
     """The standard 256/2048 stream shape: mostly long blocks with bursts of short ones.  The host cuts
     every chain into long-run segments (fused kernel) and the rest (chain kernel) and runs them round
     by round, handing PreviousWindowRight over through the device state.  Bit-exact against the oracle,
     over two consecutive batches (state carried across), and identical to the chain-kernel-only path."""
     rng = np.random.default_rng(seed)
-    channels, bs0, bs1, S, P = 2, 8, 11, 6, 40
+    channels, bs1, S, P = 2, 11, 6, 40
     residue = entry == "residue"
     floors, mappings, modes = _random_packet_case(rng, channels, bs0, bs1)
     su = make_setup(ctx, channels, bs0, bs1, modes=modes, mappings=mappings, floors=floors)
