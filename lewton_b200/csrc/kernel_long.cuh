@@ -1017,7 +1017,10 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
         st_ = __shfl_sync(0xffffffffu, st_, 0);
         nlc = __shfl_sync(0xffffffffu, nlc, 0);
         if (st_ != 2) break;
-        // (the shuffle also orders lane 0's wait on the descriptor barrier before these reads)
+        // lane 0 has acquired the descriptor tile through its mbarrier wait; the warp barrier extends that
+        // to the other lanes (a shuffle alone is not a memory-ordering operation).  Letting every lane
+        // wait on the mbarrier itself costs 2 % (code layout), profiles/variants_r1k.log.
+        __syncwarp();
 #pragma unroll
         for (int b = 0; b < NB; b++) cur[b] = run_cur(s_next[b]);
         npk = s_next[0].n_packets;
