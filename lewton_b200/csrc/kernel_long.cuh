@@ -603,7 +603,7 @@ __device__ __forceinline__ int16_t d_sample_i16(float v)
     asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(r) : "f"(__fmul_rn(v, 32768.0f)));
     return (int16_t)r;
 }
-__device__ __forceinline__ void st_pcm(float *p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_pcm(float *p, float v) { __stcs(p, v); }    // .cs beats .cg / default (variants_r1k.log)
 __device__ __forceinline__ void st_pcm(int16_t *p, float v) { __stcs(reinterpret_cast<short *>(p), (short)d_sample_i16(v)); }
 
 // Step 8 + window + overlap-add + stores, all 8 slots of all NB blocks.  FIRST: packet 0 of the
