@@ -58,11 +58,12 @@ __device__ __forceinline__ float d_x_at(const float *V, const float *__restrict_
 
 // MULTI = false: one warp per channel (<= 8 warps, compile-time group size, warp-level syncs);
 // MULTI = true: `wpc` warps per channel, named barriers.
+// np: blocks a channel group transforms together (spectrum entry, !MULTI; the host sizes shared memory for it).
 template <int FORMAT, int ENTRY, bool MULTI>
 __global__ void __launch_bounds__(MULTI ? 1024 : 256)
 k_chain(const ChainDesc *__restrict__ chains, const uint8_t *__restrict__ pkt_bytes, const float *__restrict__ coeffs,
         const float *__restrict__ dense_floor, const uint8_t *__restrict__ floor_kind,
-        const uint32_t *__restrict__ floor1_y, void *__restrict__ pcm, int n1max, int wpc)
+        const uint32_t *__restrict__ floor1_y, void *__restrict__ pcm, int n1max, int wpc, int np)
 {
     extern __shared__ float ch_smem[];
     const ChainDesc cd = chains[blockIdx.x];
@@ -75,8 +76,9 @@ k_chain(const ChainDesc *__restrict__ chains, const uint8_t *__restrict__ pkt_by
         if (!MULTI) __syncwarp();
         else asm volatile("bar.sync %0, %1;" ::"r"(warp + 1), "r"(gt) : "memory");
     };
-    const int per_warp = n1max + (n1max >> 1);
-    float *U = ch_smem + (size_t)warp * per_warp, *V = U + (n1max >> 1), *prev = U + n1max;
+    // per channel group: `np` blocks of U | V (n1max floats each), then the previous right half
+    const int per_warp = np * n1max + (n1max >> 1);
+    float *U = ch_smem + (size_t)warp * per_warp, *prev = U + np * n1max;
     // floor posts of up to 8 channels (residue entry)
     uint16_t *s_x = reinterpret_cast<uint16_t *>(ch_smem + (size_t)W * per_warp);
     uint16_t *s_y = s_x + 8 * (LWB_MAX_POSTS + 1);
@@ -91,21 +93,18 @@ k_chain(const ChainDesc *__restrict__ chains, const uint8_t *__restrict__ pkt_by
     uint64_t pos = 0;                     // samples per channel emitted so far
     const uint8_t *bytes = pkt_bytes + cd.byte_off;
 
-    for (uint32_t p = 0; p < cd.n_packets; p++) {
-        const int mode = bytes[3 * p];
-        const int blockflag = su.mode_blockflag[mode];
-        const bool pf = blockflag ? bytes[3 * p + 1] != 0 : true;       // short blocks: map_or(true, ..)
-        const bool nf = blockflag ? bytes[3 * p + 2] != 0 : true;
+    for (uint32_t p = 0; p < cd.n_packets;) {
+        const int blockflag = su.mode_blockflag[bytes[3 * p]];
         const DevTables &tb = su.tab[blockflag];
         const int n = 1 << tb.bs, n2 = n >> 1;
-        // audio.rs:1056-1073
-        const int ls = pf ? 0 : (n - n0) >> 2;
-        const int slope_sel = pf ? blockflag : 0;
-        const int rs = nf ? n2 : (n * 3 - n0) >> 2;
-        const int re = nf ? n : (n * 3 + n0) >> 2;
+        // consecutive packets of one blocksize are transformed together (they are independent until the
+        // overlap-add): up to `np` blocks in flight per channel group
+        uint32_t g = 1;
+        if (ENTRY == LWB_ENTRY_SPECTRUM && !MULTI)
+            while (g < (uint32_t)np && p + g < cd.n_packets && su.mode_blockflag[bytes[3 * (p + g)]] == blockflag) g++;
 
-        const float *X;
         if (ENTRY == LWB_ENTRY_RESIDUE) {
+            const int mode = bytes[3 * p];
             const DevMapping &mp = su.mappings[su.mode_mapping[mode]];
             const uint64_t row = (cd.pkt_index + p) * C;
             __syncthreads();              // previous packet finished with U/V and the post arrays
@@ -144,42 +143,65 @@ k_chain(const ChainDesc *__restrict__ chains, const uint8_t *__restrict__ pkt_by
                 }
             }
             __syncthreads();
-            X = U;
-        } else {
-            X = coeffs + coeff + (size_t)warp * n2;
         }
 
         if (active) {
-            d_imdct_to_v(tb, n, X, U, V, lane, gt, gsync);
-            const float *__restrict__ B = tb.b;
-            const int olen = rs - ls;
-            if (has) {
-                const float *__restrict__ w = su.tab[slope_sel].window;
-                for (int i = lane; i < olen; i += gt) {
-                    float v = d_x_at(V, B, n, ls + i);
-                    if (i < plen)                                  // audio.rs:1116-1118
-                        v = __fadd_rn(__fmul_rn(v, __ldg(w + i)), __fmul_rn(prev[i], __ldg(w + plen - 1 - i)));
-                    if (FORMAT == LWB_OUT_F32_PLANAR)
-                        ((float *)pcm)[cd.out_off + (size_t)warp * cd.out_stride + pos + i] = v;
-                    else if (FORMAT == LWB_OUT_I16_PLANAR)
-                        ((int16_t *)pcm)[cd.out_off + (size_t)warp * cd.out_stride + pos + i] = d_sample_i16(v);
-                    else if (FORMAT == LWB_OUT_F32_INTERLEAVED)
-                        ((float *)pcm)[cd.out_off + (pos + i) * C + warp] = v;
-                    else
-                        ((int16_t *)pcm)[cd.out_off + (pos + i) * C + warp] = d_sample_i16(v);
+            float *V0 = U + (n1max >> 1);
+            if (ENTRY == LWB_ENTRY_RESIDUE) {
+                d_imdct_to_v(tb, n, U, U, V0, lane, gt, gsync);
+            } else {
+                const float *X = coeffs + coeff + (size_t)warp * n2;
+                const size_t xs = (size_t)C * n2;
+                uint32_t q = 0;
+                while (q < g) {                                  // pieces of 4, 2, 1 blocks
+                    const uint32_t rem = g - q;
+                    if (rem >= 4) { d_imdct_to_v_np<4>(tb, n, X + q * xs, xs, U + q * n1max, V0 + q * n1max, n1max, lane, gt, gsync); q += 4; }
+                    else if (rem >= 2) { d_imdct_to_v_np<2>(tb, n, X + q * xs, xs, U + q * n1max, V0 + q * n1max, n1max, lane, gt, gsync); q += 2; }
+                    else { d_imdct_to_v(tb, n, X + q * xs, U + q * n1max, V0 + q * n1max, lane, gt, gsync); q += 1; }
                 }
-                gsync();
             }
-            plen = re - rs;                                        // audio.rs:1121
-            for (int i = lane; i < plen; i += gt) prev[i] = d_x_at(V, B, n, rs + i);
-            gsync();
-            if (has) pos += olen;
-        } else {
-            plen = re - rs;
-            if (has) pos += rs - ls;
         }
-        has = true;
-        coeff += (uint64_t)C * n2;
+        for (uint32_t q = 0; q < g; q++) {
+            const bool pf = blockflag ? bytes[3 * (p + q) + 1] != 0 : true;       // short blocks: map_or(true, ..)
+            const bool nf = blockflag ? bytes[3 * (p + q) + 2] != 0 : true;
+            // audio.rs:1056-1073
+            const int ls = pf ? 0 : (n - n0) >> 2;
+            const int slope_sel = pf ? blockflag : 0;
+            const int rs = nf ? n2 : (n * 3 - n0) >> 2;
+            const int re = nf ? n : (n * 3 + n0) >> 2;
+            if (active) {
+                const float *V = U + q * n1max + (n1max >> 1);
+                const float *__restrict__ B = tb.b;
+                const int olen = rs - ls;
+                if (has) {
+                    const float *__restrict__ w = su.tab[slope_sel].window;
+                    for (int i = lane; i < olen; i += gt) {
+                        float v = d_x_at(V, B, n, ls + i);
+                        if (i < plen)                                  // audio.rs:1116-1118
+                            v = __fadd_rn(__fmul_rn(v, __ldg(w + i)), __fmul_rn(prev[i], __ldg(w + plen - 1 - i)));
+                        if (FORMAT == LWB_OUT_F32_PLANAR)
+                            ((float *)pcm)[cd.out_off + (size_t)warp * cd.out_stride + pos + i] = v;
+                        else if (FORMAT == LWB_OUT_I16_PLANAR)
+                            ((int16_t *)pcm)[cd.out_off + (size_t)warp * cd.out_stride + pos + i] = d_sample_i16(v);
+                        else if (FORMAT == LWB_OUT_F32_INTERLEAVED)
+                            ((float *)pcm)[cd.out_off + (pos + i) * C + warp] = v;
+                        else
+                            ((int16_t *)pcm)[cd.out_off + (pos + i) * C + warp] = d_sample_i16(v);
+                    }
+                    gsync();
+                }
+                plen = re - rs;                                        // audio.rs:1121
+                for (int i = lane; i < plen; i += gt) prev[i] = d_x_at(V, B, n, rs + i);
+                gsync();
+                if (has) pos += olen;
+            } else {
+                plen = re - rs;
+                if (has) pos += rs - ls;
+            }
+            has = true;
+            coeff += (uint64_t)C * n2;
+        }
+        p += g;
     }
     if (active)
         for (int i = lane; i < plen; i += gt) cd.state[(size_t)warp * cd.state_stride + i] = prev[i];

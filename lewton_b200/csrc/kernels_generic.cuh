@@ -358,6 +358,170 @@ __device__ __forceinline__ void d_imdct_to_v(const DevTables &tb, int n, const f
     sync();
 }
 
+// The same transform for NP independent blocks of one size at once (block q: spectrum X + q * xs,
+// buffers U + q * bs and V + q * bs).  Arithmetic per block is identical to d_imdct_to_v; every stage
+// first loads the operands of all NP blocks, then computes, then stores, so that a thread has NP
+// independent dependency chains in flight instead of one -- the transform is latency-bound for small
+// n, where a stage is a single butterfly per lane (ncu: one instruction per ~54 cycles per warp).
+template <int NP, class Sync>
+__device__ __forceinline__ void d_imdct_to_v_np(const DevTables &tb, int n, const float *X, size_t xs, float *U, float *V, int bs,
+                                                int tid, int NT, Sync sync)
+{
+    const int n2 = n >> 1, n4 = n >> 2, n8 = n >> 3;
+    const int ld = tb.bs;
+    const float *__restrict__ A = tb.a;
+    const float *__restrict__ Cc = tb.c;
+    // step 0
+    for (int t = tid; t < n8; t += NT) {
+        const float a0 = A[2 * t], a1 = A[2 * t + 1];
+        const int d = n4 - 2 - 2 * t, ao = n4 + 2 * t, e = n2 - 3 - 4 * t;
+        const float b0 = A[ao], b1 = A[ao + 1];
+        float x0[NP], x2[NP], ne2[NP], ne0[NP];
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            const float *Xq = X + q * xs;
+            x0[q] = Xq[4 * t]; x2[q] = Xq[4 * t + 2]; ne2[q] = -Xq[e + 2]; ne0[q] = -Xq[e];
+        }
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            float *Vq = V + q * bs;
+            Vq[n2 - 1 - 2 * t] = __fsub_rn(__fmul_rn(x0[q], a0), __fmul_rn(x2[q], a1));
+            Vq[n2 - 2 - 2 * t] = __fadd_rn(__fmul_rn(x0[q], a1), __fmul_rn(x2[q], a0));
+            Vq[d + 1] = __fsub_rn(__fmul_rn(ne2[q], b0), __fmul_rn(ne0[q], b1));
+            Vq[d] = __fadd_rn(__fmul_rn(ne2[q], b1), __fmul_rn(ne0[q], b0));
+        }
+    }
+    sync();
+    // step 2
+    for (int t = tid; t < (n >> 4); t += NT) {
+        const int ao = n2 - 8 - 8 * t, hi = n4 + 4 * t, lo = 4 * t;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int o = 2 * h;
+            const float w0 = A[ao + 4 - 4 * h], w1 = A[ao + 5 - 4 * h];
+            float h1[NP], l1[NP], h0[NP], l0[NP];
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                const float *Vq = V + q * bs;
+                h1[q] = Vq[hi + o + 1]; l1[q] = Vq[lo + o + 1]; h0[q] = Vq[hi + o]; l0[q] = Vq[lo + o];
+            }
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                float *Uq = U + q * bs;
+                const float v1 = __fsub_rn(h1[q], l1[q]), v0 = __fsub_rn(h0[q], l0[q]);
+                Uq[hi + o + 1] = __fadd_rn(h1[q], l1[q]);
+                Uq[hi + o] = __fadd_rn(h0[q], l0[q]);
+                Uq[lo + o + 1] = __fsub_rn(__fmul_rn(v1, w0), __fmul_rn(v0, w1));
+                Uq[lo + o] = __fadd_rn(__fmul_rn(v0, w0), __fmul_rn(v1, w1));
+            }
+        }
+    }
+    sync();
+    // step 3, literal schedule
+    for (int l = 0; l < 2 || l <= ld - 7; l++) {
+        if (l == 1 && n < 128) continue;
+        const int k0 = n >> (l + 2), k1 = 1 << (l + 3);
+        const int rbits = ld - l - 4;
+        for (int qq = tid; qq < n8; qq += NT) {
+            const int r = qq & ((1 << rbits) - 1), s = qq >> rbits;
+            const int i = n2 - 1 - k0 * s - 2 * r, lo = i - (k0 >> 1);
+            const float w0 = A[r * k1], w1 = A[r * k1 + 1];
+            float eh[NP], el[NP], eh1[NP], el1[NP];
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                const float *Uq = U + q * bs;
+                eh[q] = Uq[i]; el[q] = Uq[lo]; eh1[q] = Uq[i - 1]; el1[q] = Uq[lo - 1];
+            }
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                float *Uq = U + q * bs;
+                const float k00 = __fsub_rn(eh[q], el[q]), k01 = __fsub_rn(eh1[q], el1[q]);
+                Uq[i] = __fadd_rn(eh[q], el[q]);
+                Uq[i - 1] = __fadd_rn(eh1[q], el1[q]);
+                Uq[lo] = __fsub_rn(__fmul_rn(k00, w0), __fmul_rn(k01, w1));
+                Uq[lo - 1] = __fadd_rn(__fmul_rn(k01, w0), __fmul_rn(k00, w1));
+            }
+        }
+        sync();
+    }
+    // ld654: 16-float groups; NP blocks x (n >> 5) groups share the threads
+    {
+        const float a2 = A[n >> 3];
+        const int groups = n >> 5;
+        for (int gq = tid; gq < groups * NP; gq += NT) {
+            const int q = gq / groups, g = gq - q * groups;
+            float *z = U + q * bs + (n2 - 1 - 16 * g);
+            float k00, k11;
+            k00 = __fsub_rn(z[0], z[-8]);   k11 = __fsub_rn(z[-1], z[-9]);
+            z[0] = __fadd_rn(z[0], z[-8]);  z[-1] = __fadd_rn(z[-1], z[-9]);
+            z[-8] = k00;                    z[-9] = k11;
+            k00 = __fsub_rn(z[-2], z[-10]); k11 = __fsub_rn(z[-3], z[-11]);
+            z[-2] = __fadd_rn(z[-2], z[-10]); z[-3] = __fadd_rn(z[-3], z[-11]);
+            z[-10] = __fmul_rn(__fadd_rn(k00, k11), a2);
+            z[-11] = __fmul_rn(__fsub_rn(k11, k00), a2);
+            k00 = __fsub_rn(z[-12], z[-4]); k11 = __fsub_rn(z[-5], z[-13]);
+            z[-4] = __fadd_rn(z[-4], z[-12]); z[-5] = __fadd_rn(z[-5], z[-13]);
+            z[-12] = k11;                   z[-13] = k00;
+            k00 = __fsub_rn(z[-14], z[-6]); k11 = __fsub_rn(z[-7], z[-15]);
+            z[-6] = __fadd_rn(z[-6], z[-14]); z[-7] = __fadd_rn(z[-7], z[-15]);
+            z[-14] = __fmul_rn(__fadd_rn(k00, k11), a2);
+            z[-15] = __fmul_rn(__fsub_rn(k00, k11), a2);
+            d_iter_54(z);
+            d_iter_54(z - 8);
+        }
+    }
+    sync();
+    // steps 4-6: bit-reverse shuffle U -> V
+    for (int qq = tid; qq < (n >> 4); qq += NT) {
+        const int d0 = n4 - 4 - 4 * qq, d1 = n2 - 4 - 4 * qq;
+        const int ka = tb.bitrev[2 * qq], kb = tb.bitrev[2 * qq + 1];
+        float a[NP][4], b[NP][4];
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            const float *Uq = U + q * bs;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { a[q][k] = Uq[ka + k]; b[q][k] = Uq[kb + k]; }
+        }
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            float *Vq = V + q * bs;
+            Vq[d1 + 3] = a[q][0]; Vq[d1 + 2] = a[q][1]; Vq[d0 + 3] = a[q][2]; Vq[d0 + 2] = a[q][3];
+            Vq[d1 + 1] = b[q][0]; Vq[d1 + 0] = b[q][1]; Vq[d0 + 1] = b[q][2]; Vq[d0 + 0] = b[q][3];
+        }
+    }
+    sync();
+    // step 7, in place on V
+    for (int t = tid; t < (n >> 4); t += NT) {
+        const int d = 4 * t, e = n2 - 4 - 4 * t, co = 4 * t;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int dd = d + 2 * h, ee = e + 2 - 2 * h;
+            const float c0 = Cc[co + 2 * h], c1 = Cc[co + 2 * h + 1];
+            float vd[NP], vd1[NP], ve[NP], ve1[NP];
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                const float *Vq = V + q * bs;
+                vd[q] = Vq[dd]; vd1[q] = Vq[dd + 1]; ve[q] = Vq[ee]; ve1[q] = Vq[ee + 1];
+            }
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                float *Vq = V + q * bs;
+                const float a02 = __fsub_rn(vd[q], ve[q]);
+                const float a11 = __fadd_rn(vd1[q], ve1[q]);
+                const float b0 = __fadd_rn(__fmul_rn(c1, a02), __fmul_rn(c0, a11));
+                const float b1 = __fsub_rn(__fmul_rn(c1, a11), __fmul_rn(c0, a02));
+                const float b2 = __fadd_rn(vd[q], ve[q]);
+                const float b3 = __fsub_rn(vd1[q], ve1[q]);
+                Vq[dd] = __fadd_rn(b2, b0);
+                Vq[dd + 1] = __fadd_rn(b3, b1);
+                Vq[ee] = __fsub_rn(b2, b0);
+                Vq[ee + 1] = __fsub_rn(b1, b3);
+            }
+        }
+    }
+    sync();
+}
+
 // grid = (packets, max channels); dynamic smem = n floats (U and V halves).
 // in: spectrum [channels][n/2] at coeff_off; out: x [channels][n] at x_off.
 __global__ void __launch_bounds__(kImdctThreads)

@@ -71,7 +71,7 @@ struct lwb_setup {
 struct MixRound { size_t r0, nr, c0, nc; };
 struct MixLaunch {
     char *db; size_t off_cd, off_by;
-    const float *pack, *w_short; int ls; bool i16, residue; int out_format; unsigned warps; size_t smem; int n1max, wpc;
+    const float *pack, *w_short; int ls; bool i16, residue; int out_format; unsigned warps; size_t smem; int n1max, wpc, np;
     const float *coeffs, *dense; const uint8_t *kinds; const uint32_t *ys; void *pcm;
 };
 
@@ -1121,21 +1121,35 @@ static int run_prologue_all(lwb_ctx *ctx, std::vector<PlanChain> &plan, const De
 // Chain kernel path (kernel_chain.cuh): everything the fused long-block kernel does not take,
 // as long as channels <= 8 and the per-channel buffers fit in shared memory.
 // ---------------------------------------------------------------------------------------------
+// Shared memory of the chain kernel: per channel `np` blocks of U | V plus the previous right half, and the
+// floor posts of up to 8 channels.  np (blocks a channel group transforms together) is 4 where that fits.
+static size_t chain_smem(unsigned maxc, int n1max, int np)
+{
+    return (size_t)maxc * ((size_t)np * n1max + n1max / 2) * 4 + 8 * (LWB_MAX_POSTS + 1) * 2 * 2 + 64;
+}
+static int chain_np(unsigned maxc, int n1max, int wpc, bool residue)
+{
+    if (residue || wpc != 1 || getenv("LWB_CHAIN_NP1")) return 1;
+    int np = 4;
+    while (np > 1 && chain_smem(maxc, n1max, np) > 64 * 1024) np >>= 1;
+    return np;
+}
+
 template <int ENTRY>
 static int launch_chain(lwb_ctx *ctx, int fmt, unsigned n_chains, unsigned warps, size_t smem, const ChainDesc *d,
                         const uint8_t *bytes, const float *coeffs, const float *dense, const uint8_t *kinds,
-                        const uint32_t *ys, void *pcm, int n1max, int wpc)
+                        const uint32_t *ys, void *pcm, int n1max, int wpc, int np)
 {
 #define LWB_CHAIN_CASE(F)                                                                                    \
     case F:                                                                                                  \
         if (wpc == 1) {                                                                                      \
             cudaFuncSetAttribute(k_chain<F, ENTRY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             return launch(ctx, k_chain<F, ENTRY, false>, dim3(n_chains), dim3(warps * 32), smem, d, bytes, coeffs, dense, \
-                          kinds, ys, pcm, n1max, wpc);                                                        \
+                          kinds, ys, pcm, n1max, wpc, np);                                                    \
         }                                                                                                    \
         cudaFuncSetAttribute(k_chain<F, ENTRY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         return launch(ctx, k_chain<F, ENTRY, true>, dim3(n_chains), dim3(warps * 32), smem, d, bytes, coeffs, dense, kinds, \
-                      ys, pcm, n1max, wpc);
+                      ys, pcm, n1max, wpc, 1);
     switch (fmt) {
         LWB_CHAIN_CASE(LWB_OUT_F32_PLANAR)
         LWB_CHAIN_CASE(LWB_OUT_I16_PLANAR)
@@ -1167,10 +1181,10 @@ static int mixed_launch_rounds(lwb_ctx *ctx, const MixLaunch &ml, const std::vec
             const uint8_t *dby = (const uint8_t *)(ml.db + ml.off_by);
             if (ml.residue)
                 rc = launch_chain<LWB_ENTRY_RESIDUE>(ctx, ml.out_format, (unsigned)rd.nc, ml.warps, ml.smem, dcd, dby, ml.coeffs, ml.dense,
-                                                     ml.kinds, ml.ys, ml.pcm, ml.n1max, ml.wpc);
+                                                     ml.kinds, ml.ys, ml.pcm, ml.n1max, ml.wpc, ml.np);
             else
                 rc = launch_chain<LWB_ENTRY_SPECTRUM>(ctx, ml.out_format, (unsigned)rd.nc, ml.warps, ml.smem, dcd, dby, ml.coeffs, ml.dense,
-                                                      ml.kinds, ml.ys, ml.pcm, ml.n1max, ml.wpc);
+                                                      ml.kinds, ml.ys, ml.pcm, ml.n1max, ml.wpc, ml.np);
             if (rc) return rc;
         }
     }
@@ -1200,11 +1214,12 @@ static int try_chain(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         n1max = std::max(n1max, 1 << su->bs1);
         total_packets += c->n_packets;
     }
-    const size_t smem = (size_t)maxc * (n1max + n1max / 2) * 4 + 8 * (LWB_MAX_POSTS + 1) * 2 * 2 + 64;
-    if (smem > 200 * 1024) return LWB_OK;
+    if (chain_smem(maxc, n1max, 1) > 200 * 1024) return LWB_OK;
     // warps per channel: one per 1024 samples of the largest block, at most 32 warps per CTA
     int wpc = std::max(1, std::min(8, n1max / 1024));
     while (wpc > 1 && (unsigned)wpc * maxc > 32) wpc >>= 1;
+    const int np = chain_np(maxc, n1max, wpc, residue);
+    const size_t smem = chain_smem(maxc, n1max, np);
     if (residue && !io->floor_kind) return fail(ctx, LWB_ERR_INVALID, "residue entry needs floor_kind");
     *handled = true;
 
@@ -1338,7 +1353,7 @@ static int try_chain(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         MixLaunch ml;
         ml.db = (char *)dbuf.p; ml.off_cd = 0; ml.off_by = used_desc; ml.pack = nullptr; ml.w_short = nullptr; ml.ls = 0;
         ml.i16 = false; ml.residue = residue; ml.out_format = io->out_format; ml.warps = maxc * wpc; ml.smem = smem;
-        ml.n1max = n1max; ml.wpc = wpc; ml.coeffs = d_coeffs; ml.dense = d_dense; ml.kinds = d_kinds; ml.ys = d_ys; ml.pcm = d_pcm;
+        ml.n1max = n1max; ml.wpc = wpc; ml.np = np; ml.coeffs = d_coeffs; ml.dense = d_dense; ml.kinds = d_kinds; ml.ys = d_ys; ml.pcm = d_pcm;
         std::vector<MixRound> rounds(1, MixRound{0, 0, 0, n_launch});
         if ((rc = mixed_launch_rounds(ctx, ml, rounds))) return rc;
         if (capture) {
@@ -1512,9 +1527,10 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
     if (need_dense && !io->dense_floor) return fail(ctx, LWB_ERR_INVALID, "dense_floor missing");
     int rc = LWB_OK;
     if (!chain_sees_long) n1max = n0max;
-    const size_t smem = (size_t)maxc * (n1max + n1max / 2) * 4 + 8 * (LWB_MAX_POSTS + 1) * 2 * 2 + 64;
     int wpc = std::max(1, std::min(8, n1max / 1024));
     while (wpc > 1 && (unsigned)wpc * maxc > 32) wpc >>= 1;
+    const int np = chain_np(maxc, n1max, wpc, residue);
+    const size_t smem = chain_smem(maxc, n1max, np);
     if (max_rounds) {
         const bool host = io->memory == LWB_MEM_HOST;
         cudaStream_t sm = ctx->stream;
@@ -1688,7 +1704,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         MixLaunch ml;
         ml.db = db; ml.off_cd = off_cd; ml.off_by = off_by; ml.pack = pack; ml.w_short = w_short; ml.ls = ls_long;
         ml.i16 = i16; ml.residue = residue; ml.out_format = io->out_format; ml.warps = maxc * wpc; ml.smem = smem;
-        ml.n1max = n1max; ml.wpc = wpc; ml.coeffs = d_coeffs; ml.dense = d_dense; ml.kinds = d_kinds; ml.ys = d_ys; ml.pcm = d_pcm;
+        ml.n1max = n1max; ml.wpc = wpc; ml.np = np; ml.coeffs = d_coeffs; ml.dense = d_dense; ml.kinds = d_kinds; ml.ys = d_ys; ml.pcm = d_pcm;
         if ((rc = mixed_launch_rounds(ctx, ml, rounds))) return rc;
         if (capture) {
             plan->mixed_captured = true;
