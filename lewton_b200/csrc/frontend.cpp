@@ -11,12 +11,23 @@
 #include <cstring>
 #include <memory>
 #include <new>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <utility>
 #include <vector>
 
 #include "../../include/lewton_frontend.h"
+
+// Resource caps for header fields a hostile stream controls (BufferNotAddressable, header.rs:117-125):
+// the spec allows 2^24 codebook entries; value tables beyond 2^26 floats are refused.  The fuzz harness
+// (tests/fuzz) lowers both so that it spends its time in the parser, not in the allocator.
+#ifndef LWF_MAX_ENTRIES
+#define LWF_MAX_ENTRIES (1u << 24)
+#endif
+#ifndef LWF_MAX_VQ_ELEMS
+#define LWF_MAX_VQ_ELEMS (1ull << 26)
+#endif
 
 namespace lwf {
 
@@ -409,6 +420,7 @@ static int read_codebook(BitReader &rdr, Codebook *cb)
     RD(rdr.u(24, &entries));
     bool ordered;
     RD(rdr.flag(&ordered));
+    if (entries > LWF_MAX_ENTRIES) return LWB_ERR_BUFFER;
     std::vector<uint8_t> lengths;
     lengths.reserve(entries);
     if (!ordered) {
@@ -453,7 +465,8 @@ static int read_codebook(BitReader &rdr, Codebook *cb)
         bool sequence_p;
         RD(rdr.flag(&sequence_p));
         const uint64_t lookup_values = lookup_type == 1 ? lookup1_values(entries, (uint16_t)dims) : (uint64_t)entries * dims;
-        if (lookup_values > (1ull << 32)) return LWB_ERR_BUFFER;
+        // convert_to_usize! / BufferNotAddressable (header.rs:117-125): refuse tables no host can hold
+        if (lookup_values > LWF_MAX_VQ_ELEMS || (uint64_t)entries * dims > LWF_MAX_VQ_ELEMS) return LWB_ERR_BUFFER;
         std::vector<uint32_t> mult;
         mult.reserve((size_t)lookup_values);
         for (uint64_t i = 0; i < lookup_values; i++) {
@@ -1193,8 +1206,19 @@ struct Ogg {
 }  // namespace lwf
 
 // ---------------------------------------------------------------------------------------------
-// C ABI
+// C ABI.  Nothing may unwind across it: allocation failures become LWB_ERR_BUFFER.
 // ---------------------------------------------------------------------------------------------
+#define LWF_GUARD(body)                         \
+    try {                                       \
+        body                                    \
+    } catch (const std::bad_alloc &) {          \
+        return LWB_ERR_BUFFER;                  \
+    } catch (const std::length_error &) {       \
+        return LWB_ERR_BUFFER;                  \
+    } catch (...) {                             \
+        return LWB_ERR_INVALID;                 \
+    }
+
 struct lwf_headers { lwf::Headers h; };
 struct lwf_ogg { lwf::Ogg o; };
 
@@ -1202,14 +1226,16 @@ extern "C" int lwf_headers_parse(const uint8_t *ident, size_t ident_len, const u
                                  const uint8_t *setup, size_t setup_len, lwf_headers **out)
 {
     if (!ident || !comment || !setup || !out) return LWB_ERR_INVALID;
-    std::unique_ptr<lwf_headers> h(new (std::nothrow) lwf_headers());
-    if (!h) return LWB_ERR_BUFFER;
-    int rc;
-    if ((rc = lwf::read_ident(ident, ident_len, &h->h.ident))) return rc;
-    if ((rc = lwf::read_comment(comment, comment_len, &h->h))) return rc;
-    if ((rc = lwf::read_setup(setup, setup_len, &h->h))) return rc;
-    *out = h.release();
-    return LWB_OK;
+    LWF_GUARD(
+        std::unique_ptr<lwf_headers> h(new (std::nothrow) lwf_headers());
+        if (!h) return LWB_ERR_BUFFER;
+        int rc;
+        if ((rc = lwf::read_ident(ident, ident_len, &h->h.ident))) return rc;
+        if ((rc = lwf::read_comment(comment, comment_len, &h->h))) return rc;
+        if ((rc = lwf::read_setup(setup, setup_len, &h->h))) return rc;
+        *out = h.release();
+        return LWB_OK;
+    )
 }
 
 extern "C" void lwf_headers_destroy(lwf_headers *h) { delete h; }
@@ -1296,7 +1322,7 @@ extern "C" int lwf_packet_decode(const lwf_headers *h, const uint8_t *packet, si
     if (!h || (!packet && len) || !out || !out->floor_kind || !out->floor1_y || !out->residue) return LWB_ERR_INVALID;
     for (const auto &fl : h->h.floors)
         if (fl.type == 0 && !out->dense_floor) return LWB_ERR_INVALID;
-    return lwf::packet_decode(h->h, packet, len, out);
+    LWF_GUARD(return lwf::packet_decode(h->h, packet, len, out);)
 }
 
 // get_decoded_sample_count, audio.rs:874-909
@@ -1328,7 +1354,7 @@ extern "C" void lwf_ogg_close(lwf_ogg *o) { delete o; }
 extern "C" int lwf_ogg_next_packet(lwf_ogg *o, lwf_ogg_packet *pkt)
 {
     if (!o || !pkt) return LWB_ERR_INVALID;
-    return o->o.next(pkt);
+    LWF_GUARD(return o->o.next(pkt);)
 }
 
 // ---------------------------------------------------------------------------------------------
