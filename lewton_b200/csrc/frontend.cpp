@@ -1208,9 +1208,9 @@ struct Ogg {
 // ---------------------------------------------------------------------------------------------
 // C ABI.  Nothing may unwind across it: allocation failures become LWB_ERR_BUFFER.
 // ---------------------------------------------------------------------------------------------
-#define LWF_GUARD(body)                         \
+#define LWF_GUARD(...)                          \
     try {                                       \
-        body                                    \
+        __VA_ARGS__                             \
     } catch (const std::bad_alloc &) {          \
         return LWB_ERR_BUFFER;                  \
     } catch (const std::length_error &) {       \
@@ -1534,14 +1534,18 @@ struct PinnedBuf {
     ~PinnedBuf() { if (p) lwb_host_free(p); }
 };
 
+struct BatchArena {
+    PinnedBuf coeffs, dense, kinds, ys;
+    std::vector<uint8_t> modes, prevs, nexts;
+    std::vector<lwb_chain> chains;
+};
+
 struct lwf_batcher {
     lwb_ctx *ctx = nullptr;
     const lwf_headers *hdr = nullptr;
     int threads = 1;
     bool has_floor0 = false;
-    PinnedBuf coeffs, dense, kinds, ys;
-    std::vector<uint8_t> modes, prevs, nexts;
-    std::vector<lwb_chain> chains;
+    BatchArena arena[2];           // slice i decodes into arena[i & 1] while slice i - 1 is being synthesised
     double t_entropy = 0, t_synth = 0;
 };
 
@@ -1573,20 +1577,20 @@ static double now_s()
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-extern "C" int lwf_batcher_decode(lwf_batcher *b, lwf_stream_job *jobs, size_t n_jobs, int out_format, void *pcm)
+namespace {
+struct JobPlan { uint64_t coeff0, pkt0; uint32_t usable; int32_t head_status; };
+
+// entropy decode of jobs [j0, j1) into `ar` on `threads` host threads
+int batch_entropy(lwf_batcher *b, BatchArena &ar, lwf_stream_job *jobs, size_t j0, size_t j1, std::vector<JobPlan> &plan,
+                  std::vector<uint32_t> &decoded, std::vector<int32_t> &dec_status)
 {
-    if (!b || (!jobs && n_jobs) || !pcm) return LWB_ERR_INVALID;
     const lwf::Headers &H = b->hdr->h;
     const size_t C = H.ident.audio_channels;
-    const double t0 = now_s();
     // pass 1 (cheap, serial): packet headers -> blocksizes -> arena offsets.  A packet whose header
     // cannot be read ends its stream's chain there (its error is reported after the earlier ones ran).
-    struct JobPlan { uint64_t coeff0, pkt0; uint32_t usable; int32_t head_status; };
-    std::vector<JobPlan> plan(n_jobs);
     uint64_t coeff_total = 0, pkt_total = 0;
-    for (size_t j = 0; j < n_jobs; j++) {
+    for (size_t j = j0; j < j1; j++) {
         lwf_stream_job &job = jobs[j];
-        if (!job.stream || (job.n_packets && (!job.packets || !job.lengths))) return LWB_ERR_INVALID;
         plan[j] = JobPlan{coeff_total, pkt_total, 0, LWB_OK};
         for (uint32_t k = 0; k < job.n_packets; k++) {
             lwf::BitReader rdr(job.packets[k], job.lengths[k]);
@@ -1599,90 +1603,133 @@ extern "C" int lwf_batcher_decode(lwf_batcher *b, lwf_stream_job *jobs, size_t n
         pkt_total += plan[j].usable;
     }
     const size_t rows = (size_t)pkt_total * C;
-    if (!b->coeffs.ensure((size_t)coeff_total * 4 + 16) || !b->kinds.ensure(rows + 16) || !b->ys.ensure(rows * LWB_MAX_POSTS * 4 + 16) ||
-        (b->has_floor0 && !b->dense.ensure((size_t)coeff_total * 4 + 16)))
+    if (!ar.coeffs.ensure((size_t)coeff_total * 4 + 16) || !ar.kinds.ensure(rows + 16) || !ar.ys.ensure(rows * LWB_MAX_POSTS * 4 + 16) ||
+        (b->has_floor0 && !ar.dense.ensure((size_t)coeff_total * 4 + 16)))
         return LWB_ERR_BUFFER;
-    b->modes.resize(pkt_total);
-    b->prevs.resize(pkt_total);
-    b->nexts.resize(pkt_total);
-    float *coeffs = (float *)b->coeffs.p, *dense = b->has_floor0 ? (float *)b->dense.p : nullptr;
-    uint8_t *kinds = (uint8_t *)b->kinds.p;
-    uint32_t *ys = (uint32_t *)b->ys.p;
+    ar.modes.resize(pkt_total);
+    ar.prevs.resize(pkt_total);
+    ar.nexts.resize(pkt_total);
+    float *coeffs = (float *)ar.coeffs.p, *dense = b->has_floor0 ? (float *)ar.dense.p : nullptr;
+    uint8_t *kinds = (uint8_t *)ar.kinds.p;
+    uint32_t *ys = (uint32_t *)ar.ys.p;
     // pass 2 (parallel over streams): entropy decode straight into the arenas
-    std::vector<uint32_t> decoded(n_jobs, 0);
-    std::vector<int32_t> dec_status(n_jobs, LWB_OK);
-    std::atomic<size_t> next_job(0);
+    std::atomic<size_t> next_job(j0);
+    std::atomic<int> failed(0);
     auto worker = [&]() {
-        std::vector<float> scratch_dense;
-        for (;;) {
-            const size_t j = next_job.fetch_add(1);
-            if (j >= n_jobs) break;
-            const lwf_stream_job &job = jobs[j];
-            uint64_t coff = plan[j].coeff0;
-            for (uint32_t k = 0; k < plan[j].usable; k++) {
-                const uint64_t pi = plan[j].pkt0 + k;
-                lwf_decoded_packet dp;
-                std::memset(&dp, 0, sizeof(dp));
-                dp.floor_kind = kinds + pi * C;
-                dp.floor1_y = ys + pi * C * LWB_MAX_POSTS;
-                dp.residue = coeffs + coff;
-                dp.dense_floor = dense ? dense + coff : nullptr;
-                const int rc = lwf::packet_decode(H, job.packets[k], job.lengths[k], &dp);
-                if (rc) { dec_status[j] = rc; break; }
-                b->modes[pi] = dp.mode_number;
-                b->prevs[pi] = dp.prev_window_flag;
-                b->nexts[pi] = dp.next_window_flag;
-                coff += (uint64_t)C * (dp.n / 2);
-                decoded[j]++;
+        try {
+            for (;;) {
+                const size_t j = next_job.fetch_add(1);
+                if (j >= j1) break;
+                const lwf_stream_job &job = jobs[j];
+                uint64_t coff = plan[j].coeff0;
+                for (uint32_t k = 0; k < plan[j].usable; k++) {
+                    const uint64_t pi = plan[j].pkt0 + k;
+                    lwf_decoded_packet dp;
+                    std::memset(&dp, 0, sizeof(dp));
+                    dp.floor_kind = kinds + pi * C;
+                    dp.floor1_y = ys + pi * C * LWB_MAX_POSTS;
+                    dp.residue = coeffs + coff;
+                    dp.dense_floor = dense ? dense + coff : nullptr;
+                    const int rc = lwf::packet_decode(H, job.packets[k], job.lengths[k], &dp);
+                    if (rc) { dec_status[j] = rc; break; }
+                    ar.modes[pi] = dp.mode_number;
+                    ar.prevs[pi] = dp.prev_window_flag;
+                    ar.nexts[pi] = dp.next_window_flag;
+                    coff += (uint64_t)C * (dp.n / 2);
+                    decoded[j]++;
+                }
             }
+        } catch (...) {
+            failed.store(1);
         }
     };
-    {
-        const int nt = (int)std::min<size_t>((size_t)b->threads, std::max<size_t>(1, n_jobs));
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nt; t++) pool.emplace_back(worker);
-        worker();
-        for (auto &t : pool) t.join();
-    }
-    const double t1 = now_s();
-    // one synthesis call
-    b->chains.assign(n_jobs, lwb_chain());
-    for (size_t j = 0; j < n_jobs; j++) {
-        lwb_chain &c = b->chains[j];
+    const int nt = (int)std::min<size_t>((size_t)b->threads, std::max<size_t>(1, j1 - j0));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+    if (failed.load()) return LWB_ERR_BUFFER;
+    // chains of this slice
+    ar.chains.assign(j1 - j0, lwb_chain());
+    for (size_t j = j0; j < j1; j++) {
+        lwb_chain &c = ar.chains[j - j0];
         std::memset(&c, 0, sizeof(c));
         c.stream = jobs[j].stream;
         c.n_packets = decoded[j];
-        c.mode_numbers = b->modes.data() + plan[j].pkt0;
-        c.prev_window_flags = b->prevs.data() + plan[j].pkt0;
-        c.next_window_flags = b->nexts.data() + plan[j].pkt0;
+        c.mode_numbers = ar.modes.data() + plan[j].pkt0;
+        c.prev_window_flags = ar.prevs.data() + plan[j].pkt0;
+        c.next_window_flags = ar.nexts.data() + plan[j].pkt0;
         c.coeff_offset = plan[j].coeff0;
         c.packet_index = plan[j].pkt0;
         c.out_offset = jobs[j].out_offset;
         c.out_stride = jobs[j].out_stride;
     }
+    return LWB_OK;
+}
+
+int batch_synth(lwf_batcher *b, BatchArena &ar, int out_format, void *pcm)
+{
     lwb_batch_io io;
     std::memset(&io, 0, sizeof(io));
     io.entry = LWB_ENTRY_RESIDUE;
     io.memory = LWB_MEM_HOST;
-    io.coeffs = coeffs;
-    io.dense_floor = dense;
-    io.floor_kind = kinds;
-    io.floor1_y = ys;
+    io.coeffs = (const float *)ar.coeffs.p;
+    io.dense_floor = b->has_floor0 ? (const float *)ar.dense.p : nullptr;
+    io.floor_kind = (const uint8_t *)ar.kinds.p;
+    io.floor1_y = (const uint32_t *)ar.ys.p;
     io.out_format = out_format;
     io.pcm = pcm;
-    const int rc = lwb_decode_chains(b->ctx, b->chains.data(), n_jobs, &io);
-    b->t_entropy = t1 - t0;
-    b->t_synth = now_s() - t1;
-    if (rc) return rc;
-    for (size_t j = 0; j < n_jobs; j++) {
-        const lwb_chain &c = b->chains[j];
-        jobs[j].n_samples = c.n_samples;
-        jobs[j].packets_done = c.packets_done;
-        jobs[j].status = c.status;
-        if (c.status == LWB_OK && c.packets_done == decoded[j] && decoded[j] < jobs[j].n_packets)
-            jobs[j].status = dec_status[j] != LWB_OK ? dec_status[j] : plan[j].head_status;
-    }
-    return LWB_OK;
+    return lwb_decode_chains(b->ctx, ar.chains.data(), ar.chains.size(), &io);
+}
+}  // namespace
+
+extern "C" int lwf_batcher_decode(lwf_batcher *b, lwf_stream_job *jobs, size_t n_jobs, int out_format, void *pcm)
+{
+    if (!b || (!jobs && n_jobs) || !pcm) return LWB_ERR_INVALID;
+    for (size_t j = 0; j < n_jobs; j++)
+        if (!jobs[j].stream || (jobs[j].n_packets && (!jobs[j].packets || !jobs[j].lengths))) return LWB_ERR_INVALID;
+    LWF_GUARD(
+        std::vector<JobPlan> plan(n_jobs);
+        std::vector<uint32_t> decoded(n_jobs, 0);
+        std::vector<int32_t> dec_status(n_jobs, LWB_OK);
+        // Slices of streams: while the GPU call of slice i runs (on one helper thread -- an lwb_ctx takes
+        // one caller at a time), the pool already entropy-decodes slice i + 1 into the other arena.
+        const size_t n_slices = std::max<size_t>(1, std::min<size_t>(4, n_jobs / 8));
+        double entropy_busy = 0, synth_busy = 0;
+        int synth_rc = LWB_OK, rc = LWB_OK;
+        std::thread synth;
+        struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{synth};   // also on unwinding
+        for (size_t sl = 0; sl < n_slices && rc == LWB_OK; sl++) {
+            const size_t j0 = n_jobs * sl / n_slices, j1 = n_jobs * (sl + 1) / n_slices;
+            // arena[sl & 1] was last read by the synthesis of slice sl - 2, which finished before that of
+            // slice sl - 1 was started
+            BatchArena &ar = b->arena[sl & 1];
+            const double e0 = now_s();
+            rc = batch_entropy(b, ar, jobs, j0, j1, plan, decoded, dec_status);
+            entropy_busy += now_s() - e0;
+            if (synth.joinable()) synth.join();
+            if (rc != LWB_OK || synth_rc != LWB_OK) break;
+            synth = std::thread([b, &ar, out_format, pcm, jobs, j0, j1, &plan, &decoded, &dec_status, &synth_rc, &synth_busy]() {
+                const double s0 = now_s();
+                const int r = batch_synth(b, ar, out_format, pcm);
+                synth_busy += now_s() - s0;
+                if (r) { synth_rc = r; return; }
+                for (size_t j = j0; j < j1; j++) {
+                    const lwb_chain &c = ar.chains[j - j0];
+                    jobs[j].n_samples = c.n_samples;
+                    jobs[j].packets_done = c.packets_done;
+                    jobs[j].status = c.status;
+                    if (c.status == LWB_OK && c.packets_done == decoded[j] && decoded[j] < jobs[j].n_packets)
+                        jobs[j].status = dec_status[j] != LWB_OK ? dec_status[j] : plan[j].head_status;
+                }
+            });
+        }
+        if (synth.joinable()) synth.join();
+        b->t_entropy = entropy_busy;
+        b->t_synth = synth_busy;
+        if (rc) return rc;
+        return synth_rc;
+    )
 }
 
 // ---------------------------------------------------------------------------------------------
