@@ -244,3 +244,58 @@ def test_stream_batcher_parallel_entropy_decode_one_synthesis_call(ctx, oracle):
         assert bits_equal(got, want), (s, mismatch_report(got, want))
     assert bt.entropy_seconds > 0 and bt.synthesis_seconds > 0
     bt.close()
+
+
+def test_hostile_but_parseable_streams_do_not_break_the_gpu_path(ctx, oracle):
+    """Mutated setup headers / audio packets that still parse (re-paged with valid CRCs) go through the
+    whole reader: every call must end in PCM or a reference-style error, and the context must stay usable
+    (checked with a bit-exact decode afterwards; run under compute-sanitizer in profiles/)."""
+    rng = np.random.default_rng(501)
+    spec, packets, infos = build_stream(77, 2, True, 8)
+    want, _ = oracle_pcm(oracle, spec, infos)
+    hdrs = [spec.ident_packet(), spec.comment_packet(), spec.setup_packet()]
+
+    def mutate(b):
+        b = bytearray(b)
+        for _ in range(int(rng.integers(1, 6))):
+            b[int(rng.integers(8, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        return bytes(b)
+
+    outcomes = {"ok": 0, "header": 0, "audio": 0, "ogg": 0}
+    for it in range(60):
+        h = list(hdrs)
+        pk = list(packets)
+        if it % 3 == 0:
+            h[2] = mutate(h[2])
+        else:
+            pk = [mutate(p) if len(p) > 9 and rng.random() < 0.7 else p for p in pk]
+        data = vp.ogg_stream(5, h, pk, page_granules(want, 3, 0), packets_per_page=3)
+        try:
+            rd = fe.OggStreamReader(ctx, data)
+        except fe.HeaderReadError:
+            outcomes["header"] += 1
+            continue
+        except L.AudioReadError:
+            outcomes["header"] += 1          # the device-side setup refused the (parseable) header
+            continue
+        try:
+            while True:
+                got = rd.read_dec_packet_f32()
+                if got is None:
+                    break
+            outcomes["ok"] += 1
+        except L.AudioReadError:
+            outcomes["audio"] += 1
+        except fe.OggReadError:
+            outcomes["ogg"] += 1
+        finally:
+            rd.close()
+        ctx.synchronize()
+    assert outcomes["ok"] > 10, outcomes
+    # the context still decodes bit-exactly
+    data = vp.ogg_stream(5, hdrs, packets, page_granules(want, 3, 0), packets_per_page=3)
+    rd = fe.OggStreamReader(ctx, data)
+    for w in want:
+        got = rd.read_dec_packet_f32()
+        assert bits_equal(np.array(got).reshape(2, -1), w)
+    rd.close()
