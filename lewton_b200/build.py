@@ -12,7 +12,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liblewton_b200.so")
-SOURCES = ["lwb_api.cu", "tables_host.cpp", "lwb_common.h", "kernels_generic.cuh", "kernel_long.cuh",
+SOURCES = ["lwb_api.cu", "host_objects.cuh", "path_generic.cuh", "path_long.cuh", "path_chain.cuh", "path_mixed.cuh",
+           "tables_host.cpp", "frontend.cpp", "lwb_common.h", "kernels_generic.cuh", "kernel_long.cuh", "kernel_chain.cuh",
            "floor1_inverse_db.inc", "Makefile"]
 
 
@@ -20,7 +21,8 @@ def _stale():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(HERE, "..", "include", "lewton_b200.h")]
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(HERE, "..", "include", h)
+                                                       for h in ("lewton_b200.h", "lewton_frontend.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

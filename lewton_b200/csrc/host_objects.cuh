@@ -1,0 +1,165 @@
+// host_objects.cuh -- part of the C-ABI translation unit (included by lwb_api.cu, not compiled on its own):
+// the opaque objects behind the handles (ctx, setup, stream, plan), error / buffer helpers and the
+// window geometry of audio.rs:1056-1073.
+#pragma once
+
+// ---------------------------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct lwb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[64] = {}, ev_done[65] = {};      // per chunk of a host-memory batch; [64] orders the copy streams
+    // fused path: descriptor arrays are double buffered and uploaded on the copy stream so that the
+    // upload of step k+1 overlaps kernel k; tickets come from a pool zeroed once per wrap
+    DevBuf runs_buf[2];
+    cudaEvent_t ev_desc[2] = {}, ev_kdone[2] = {};
+    int runs_par = 0;
+    uint32_t ticket_next = 0;
+    uint64_t state_gen = 1;        // bumped whenever any stream's (has, len) changes: plans key on it
+    std::string err;
+    uint64_t launches = 0;
+    // grow-only device arenas
+    DevBuf coeffs, dense, pcm, spec, x, desc, kinds, ys, chains, ticket, cdesc, cbytes;
+    // pinned staging for descriptors
+    void *h_desc = nullptr;
+    size_t h_desc_cap = 0;
+    size_t x_cap_elems = (size_t)64 << 20;     // IMDCT scratch per round of the generic path (256 MiB)
+};
+
+struct lwb_setup {
+    lwb_ctx *ctx = nullptr;
+    DevSetup host;                 // device pointers inside
+    DevSetup *d_setup = nullptr;
+    std::vector<void *> allocs;
+    uint8_t channels = 0, bs0 = 0, bs1 = 0;
+    uint32_t n_modes = 0;
+    uint32_t n_mappings = 0;
+    std::vector<DevMapping> mappings;   // host copy (validation)
+};
+
+struct MixRound { size_t r0, nr, c0, nc; };
+struct MixLaunch {
+    char *db; size_t off_cd, off_by;
+    const float *pack, *w_short; int ls; bool i16, residue; int out_format; unsigned warps; size_t smem; int n1max, wpc, np;
+    const float *coeffs, *dense; const uint8_t *kinds; const uint32_t *ys; void *pcm;
+};
+
+struct lwb_plan {
+    lwb_ctx *ctx = nullptr;
+    lwb_chain *chains = nullptr;
+    size_t n_chains = 0;
+    lwb_batch_io io;
+    // captured fused-path launch (valid while ctx->state_gen == gen)
+    bool captured = false;
+    uint64_t gen = 0;
+    DevBuf runs;
+    uint32_t n_groups = 0;
+    const float *pack = nullptr;
+    bool i16 = false;
+    // captured mixed-path launch sequence (valid while ctx->state_gen == gen)
+    bool mixed_captured = false;
+    DevBuf mix;
+    MixLaunch mix_launch;
+    std::vector<MixRound> mix_rounds;
+};
+
+struct lwb_stream {
+    lwb_ctx *ctx = nullptr;
+    const lwb_setup *setup = nullptr;
+    float *d_state = nullptr;      // [channels][n1/2]
+    bool has = false;              // PreviousWindowRight.data.is_some()
+    uint32_t plen = 0;             // per-channel length of the saved right half
+    uint64_t busy_epoch = 0;       // guards against one stream appearing twice in a batch
+};
+
+static inline void set_stream_state(lwb_stream *s, bool has, uint32_t plen)
+{
+    if (s->has != has || s->plen != plen) {
+        s->has = has;
+        s->plen = plen;
+        s->ctx->state_gen++;
+    }
+}
+
+static int fail(lwb_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (ctx) {
+        ctx->err = what;
+        if (e != cudaSuccess) {
+            ctx->err += ": ";
+            ctx->err += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+
+#define CU(ctx, call)                                                        \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return fail((ctx), LWB_ERR_CUDA, #call, e__); \
+    } while (0)
+
+static int ensure(lwb_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return LWB_OK;
+    if (b.p) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        CU(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 4096;
+    CU(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return LWB_OK;
+}
+
+static int ensure_pinned(lwb_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->h_desc_cap) return LWB_OK;
+    if (ctx->h_desc) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFreeHost(ctx->h_desc);
+        ctx->h_desc = nullptr;
+        ctx->h_desc_cap = 0;
+    }
+    size_t want = bytes * 2 + 4096;
+    CU(ctx, cudaHostAlloc(&ctx->h_desc, want, cudaHostAllocDefault));
+    ctx->h_desc_cap = want;
+    return LWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// window geometry, audio.rs:1056-1073 (and its twin :889-908)
+// ---------------------------------------------------------------------------------------------
+struct Geom {
+    uint32_t n, ls, le, rs, re;
+    uint8_t blockflag, slope_sel, mapping;
+};
+
+static int geometry(const lwb_setup *su, uint8_t mode, int prev_flag, int next_flag, Geom *g)
+{
+    if (mode >= su->n_modes) return LWB_ERR_BAD_FORMAT;          // audio.rs:926-930
+    const bool lng = su->host.mode_blockflag[mode] != 0;
+    const uint32_t n = 1u << (lng ? su->bs1 : su->bs0);
+    const uint32_t n0 = 1u << su->bs0;
+    const bool prev = lng ? (prev_flag != 0) : true;             // short blocks: map_or(true, ..)
+    const bool next = lng ? (next_flag != 0) : true;
+    g->n = n;
+    g->blockflag = lng;
+    g->mapping = su->host.mode_mapping[mode];
+    if (prev) { g->ls = 0; g->le = n >> 1; g->slope_sel = lng; }
+    else { g->ls = (n - n0) >> 2; g->le = (n + n0) >> 2; g->slope_sel = 0; }
+    if (next) { g->rs = n >> 1; g->re = n; }
+    else { g->rs = (n * 3 - n0) >> 2; g->re = (n * 3 + n0) >> 2; }
+    return LWB_OK;
+}
+

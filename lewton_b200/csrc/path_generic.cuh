@@ -1,0 +1,197 @@
+// path_generic.cuh -- part of the C-ABI translation unit (included by lwb_api.cu, not compiled on its own):
+// per-packet planning of a batch and the four-kernel path (kernels_generic.cuh).
+#pragma once
+
+// ---------------------------------------------------------------------------------------------
+// batch planning
+// ---------------------------------------------------------------------------------------------
+struct PlanPacket {
+    Geom g;
+    uint32_t plen;          // 0: no previous half -> 0 samples out
+    uint64_t coeff_off;     // absolute element offset
+    uint64_t sample_pos;    // samples (per channel) produced by the chain before this packet
+};
+
+struct PlanChain {
+    lwb_chain *c;
+    std::vector<PlanPacket> pk;
+    bool end_has;           // stream state after the planned packets
+    uint32_t end_plen;
+    bool clear_after;       // OLA guard fired on packet pk.size(): state becomes empty
+};
+
+static size_t elem_size(int fmt) { return (fmt == LWB_OUT_F32_PLANAR || fmt == LWB_OUT_F32_INTERLEAVED) ? 4 : 2; }
+static bool is_planar(int fmt) { return fmt == LWB_OUT_F32_PLANAR || fmt == LWB_OUT_I16_PLANAR; }
+
+static int plan_chain(lwb_chain *c, PlanChain *pc)
+{
+    const lwb_stream *s = c->stream;
+    const lwb_setup *su = s->setup;
+    bool has = s->has;
+    uint32_t plen = s->plen;
+    uint64_t coeff = c->coeff_offset, pos = 0;
+    pc->c = c;
+    pc->clear_after = false;
+    c->status = LWB_OK;
+    pc->pk.reserve(c->n_packets);
+    for (uint32_t i = 0; i < c->n_packets; i++) {
+        PlanPacket pp;
+        int rc = geometry(su, c->mode_numbers[i], c->prev_window_flags ? c->prev_window_flags[i] : 1,
+                          c->next_window_flags ? c->next_window_flags[i] : 1, &pp.g);
+        if (rc) { c->status = rc; break; }
+        if (has) {
+            const uint32_t slope_len = 1u << ((pp.g.slope_sel ? su->bs1 : su->bs0) - 1);
+            if (slope_len < plen) {             // audio.rs:1107-1111; :1083 has already taken the state
+                c->status = LWB_ERR_BAD_FORMAT;
+                pc->clear_after = true;
+                break;
+            }
+            if (pp.g.ls + plen > pp.g.n) {      // chan[range] would be out of bounds: a panic in the reference
+                c->status = LWB_ERR_MISMATCH;
+                break;
+            }
+        }
+        pp.plen = has ? plen : 0;
+        pp.coeff_off = coeff;
+        pp.sample_pos = pos;
+        coeff += (uint64_t)su->channels * (pp.g.n >> 1);
+        if (has) pos += pp.g.rs - pp.g.ls;
+        has = true;
+        plen = pp.g.re - pp.g.rs;
+        pc->pk.push_back(pp);
+    }
+    pc->end_has = pc->clear_after ? false : has;
+    pc->end_plen = pc->clear_after ? 0 : plen;
+    c->packets_done = (uint32_t)pc->pk.size();
+    c->n_samples = (uint32_t)pos;
+    return LWB_OK;
+}
+
+template <typename K, typename... Args>
+static int launch(lwb_ctx *ctx, K kernel, dim3 grid, dim3 block, size_t smem, Args... args)
+{
+    kernel<<<grid, block, smem, ctx->stream>>>(args...);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, LWB_ERR_CUDA, "kernel launch", e);
+    return LWB_OK;
+}
+
+struct DevArenas {
+    const float *coeffs;      // device
+    const float *dense;       // device or null
+    const uint8_t *kinds;     // device or null
+    const uint32_t *ys;       // device or null
+    uint64_t kinds_row0;      // first packet row uploaded
+    void *pcm;                // device
+    uint64_t coeff_base;      // element offset that device coeffs[0] corresponds to
+    uint64_t pcm_base;        // element offset that device pcm[0] corresponds to
+};
+
+// Generic path: rounds of packets bounded by the IMDCT scratch.
+static int run_generic(lwb_ctx *ctx, std::vector<PlanChain> &plan, const lwb_batch_io *io, const DevArenas &ar)
+{
+    size_t maxp = 0;
+    for (auto &pc : plan) maxp = std::max(maxp, pc.pk.size());
+    if (maxp == 0) return LWB_OK;
+    // x elements of one "packet column" (packet i of every chain), to size the rounds
+    std::vector<uint32_t> start(plan.size(), 0);
+    const bool planar = is_planar(io->out_format);
+    while (true) {
+        // pick how many packets per chain go into this round
+        size_t x_elems = 0, n_desc = 0, spec_lo = ~(size_t)0, spec_hi = 0;
+        std::vector<uint32_t> take(plan.size(), 0);
+        bool any = false;
+        for (uint32_t step = 0;; step++) {
+            size_t add = 0;
+            bool more = false;
+            for (size_t ci = 0; ci < plan.size(); ci++) {
+                const uint32_t i = start[ci] + step;
+                if (i < plan[ci].pk.size() && take[ci] == step) {
+                    add += (size_t)plan[ci].c->stream->setup->channels * plan[ci].pk[i].g.n;
+                    more = true;
+                }
+            }
+            if (!more) break;
+            if (x_elems && x_elems + add > ctx->x_cap_elems) break;
+            for (size_t ci = 0; ci < plan.size(); ci++) {
+                const uint32_t i = start[ci] + step;
+                if (i < plan[ci].pk.size() && take[ci] == step) { take[ci]++; n_desc++; }
+            }
+            x_elems += add;
+            any = true;
+        }
+        if (!any) break;
+        int rc;
+        if ((rc = ensure_pinned(ctx, n_desc * sizeof(DevPacket)))) return rc;
+        if ((rc = ensure(ctx, ctx->desc, n_desc * sizeof(DevPacket)))) return rc;
+        if ((rc = ensure(ctx, ctx->x, x_elems * sizeof(float)))) return rc;
+        // the pinned descriptor staging is reused every round: wait for the previous upload
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        DevPacket *hp = (DevPacket *)ctx->h_desc;
+        size_t di = 0, xo = 0;
+        unsigned maxc = 1, maxn = 64;
+        for (size_t ci = 0; ci < plan.size(); ci++) {
+            PlanChain &pc = plan[ci];
+            const lwb_stream *s = pc.c->stream;
+            const lwb_setup *su = s->setup;
+            const unsigned C = su->channels;
+            for (uint32_t k = 0; k < take[ci]; k++) {
+                const PlanPacket &pp = pc.pk[start[ci] + k];
+                DevPacket &d = hp[di];
+                std::memset(&d, 0, sizeof(d));
+                d.setup = su->d_setup;
+                d.state = s->d_state;
+                d.coeff_off = pp.coeff_off - ar.coeff_base;
+                d.x_off = xo;
+                d.out_stride = pc.c->out_stride;
+                d.out_off = pc.c->out_offset - ar.pcm_base + (planar ? pp.sample_pos : pp.sample_pos * C);
+                d.pkt_index = pc.c->packet_index + start[ci] + k - ar.kinds_row0;
+                d.prev_packet = k ? (int32_t)(di - 1) : -1;
+                d.prev_rs = k ? hp[di - 1].rs : 0;
+                d.state_stride = (uint32_t)state_stride(su);
+                d.n = (uint16_t)pp.g.n;
+                d.ls = (uint16_t)pp.g.ls;
+                d.rs = (uint16_t)pp.g.rs;
+                d.re = (uint16_t)pp.g.re;
+                d.plen = (uint16_t)pp.plen;
+                d.blockflag = pp.g.blockflag;
+                d.mapping = pp.g.mapping;
+                d.slope_sel = pp.g.slope_sel;
+                d.channels = (uint8_t)C;
+                d.save_state = (k + 1 == take[ci]);
+                xo += (size_t)C * pp.g.n;
+                spec_lo = std::min<size_t>(spec_lo, d.coeff_off);
+                spec_hi = std::max<size_t>(spec_hi, d.coeff_off + (size_t)C * (pp.g.n >> 1));
+                maxc = std::max(maxc, C);
+                maxn = std::max<unsigned>(maxn, pp.g.n);
+                di++;
+            }
+            start[ci] += take[ci];
+        }
+        CU(ctx, cudaMemcpyAsync(ctx->desc.p, hp, n_desc * sizeof(DevPacket), cudaMemcpyHostToDevice, ctx->stream));
+        const DevPacket *dp = (const DevPacket *)ctx->desc.p;
+        const float *spec = ar.coeffs;
+        if (io->entry == LWB_ENTRY_RESIDUE) {
+            if ((rc = ensure(ctx, ctx->spec, spec_hi * sizeof(float)))) return rc;
+            if ((rc = launch(ctx, k_prologue, dim3((unsigned)n_desc), dim3(kPrologueThreads), 0, dp, ar.coeffs,
+                             ar.dense, ar.kinds, ar.ys, (float *)ctx->spec.p)))
+                return rc;
+            spec = (const float *)ctx->spec.p;
+        }
+        if ((rc = launch(ctx, k_imdct, dim3((unsigned)n_desc, maxc), dim3(kImdctThreads), maxn * sizeof(float), dp,
+                         spec, (float *)ctx->x.p)))
+            return rc;
+        dim3 g2((unsigned)n_desc, maxc), b2(kOverlapThreads);
+        switch (io->out_format) {
+        case LWB_OUT_F32_PLANAR: rc = launch(ctx, k_overlap<LWB_OUT_F32_PLANAR>, g2, b2, 0, dp, (const float *)ctx->x.p, ar.pcm); break;
+        case LWB_OUT_I16_PLANAR: rc = launch(ctx, k_overlap<LWB_OUT_I16_PLANAR>, g2, b2, 0, dp, (const float *)ctx->x.p, ar.pcm); break;
+        case LWB_OUT_F32_INTERLEAVED: rc = launch(ctx, k_overlap<LWB_OUT_F32_INTERLEAVED>, g2, b2, 0, dp, (const float *)ctx->x.p, ar.pcm); break;
+        default: rc = launch(ctx, k_overlap<LWB_OUT_I16_INTERLEAVED>, g2, b2, 0, dp, (const float *)ctx->x.p, ar.pcm); break;
+        }
+        if (rc) return rc;
+        if ((rc = launch(ctx, k_save_state, g2, b2, 0, dp, (const float *)ctx->x.p))) return rc;
+    }
+    return LWB_OK;
+}
+

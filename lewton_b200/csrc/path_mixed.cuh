@@ -1,0 +1,354 @@
+// path_mixed.cuh -- part of the C-ABI translation unit (included by lwb_api.cu, not compiled on its own):
+// mixed short/long streams: segmentation between the fused kernel and the chain kernel, round by round.
+#pragma once
+
+// ---------------------------------------------------------------------------------------------
+// Mixed short/long streams (the standard 256/2048 Vorbis shape): each chain is cut into segments
+// -- maximal runs of long blocks with long neighbours go to the fused kernel, everything else to
+// the chain kernel -- and the segments of all chains are executed round by round, handing the
+// overlap state over through the stream's device state (PreviousWindowRight) between launches.
+// ---------------------------------------------------------------------------------------------
+static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch, bool *handled,
+                     lwb_plan *plan = nullptr)
+{
+    *handled = false;
+    const uint64_t gen_at_entry = ctx->state_gen;
+    if (plan) plan->mixed_captured = false;
+    if (getenv("LWB_FORCE_GENERIC") || getenv("LWB_NO_MIXED")) return LWB_OK;
+    if (io->out_format != LWB_OUT_F32_PLANAR && io->out_format != LWB_OUT_I16_PLANAR) return LWB_OK;
+    const bool residue = io->entry == LWB_ENTRY_RESIDUE;
+    const bool i16 = io->out_format == LWB_OUT_I16_PLANAR;
+    const size_t esz = i16 ? 2 : 4;
+    unsigned maxc = 1;
+    int n1max = 64, n0max = 64, bs0 = -1;
+    size_t total_packets = 0, long_like = 0;
+    const float *pack = nullptr, *w_short = nullptr;
+    for (size_t i = 0; i < n_chains; i++) {
+        const lwb_chain *c = &chains[i];
+        if (!c->stream || c->stream->ctx != ctx || (c->n_packets && !c->mode_numbers)) return LWB_OK;
+        const lwb_setup *su = c->stream->setup;
+        if (su->channels > 8 || su->bs1 != kLongBs || !su->host.tab[1].pack) return LWB_OK;
+        if (pack && pack != su->host.tab[1].pack) return LWB_OK;
+        pack = su->host.tab[1].pack;
+        // one short window for the whole batch (the fused kernel takes it as a launch argument)
+        if (bs0 >= 0 && (bs0 != su->bs0 || w_short != su->host.tab[0].window)) return LWB_OK;
+        bs0 = su->bs0;
+        w_short = su->host.tab[0].window;
+        if ((c->out_offset & 3) || (c->out_stride & 3) || (c->coeff_offset & 3)) return LWB_OK;
+        maxc = std::max<unsigned>(maxc, su->channels);
+        n1max = std::max(n1max, 1 << su->bs1);
+        n0max = std::max(n0max, 1 << su->bs0);
+        total_packets += c->n_packets;
+        for (uint32_t k = 0; k < c->n_packets; k++) {
+            const uint8_t m = c->mode_numbers[k];
+            if (m < su->n_modes && su->host.mode_blockflag[m]) long_like++;
+        }
+    }
+    // worth it only if the fused kernel gets a good share of the packets (every hand-over between the
+    // kernels costs a launch): at least half the packets long blocks
+    if (long_like * 2 < total_packets) return LWB_OK;
+    const int ls_long = (kLongN - (1 << bs0)) >> 2, pl_short = 1 << (bs0 - 1);
+    if (residue && !io->floor_kind) return fail(ctx, LWB_ERR_INVALID, "residue entry needs floor_kind");
+    *handled = true;
+
+    struct Seg { bool is_long, first_short, last_short; uint32_t p0, n; bool has; uint32_t plen; uint64_t coeff, pos; };
+    bool chain_sees_long = false;       // the chain kernel's shared memory is sized for what it actually gets
+    struct Walk { uint32_t seg0, n_seg; bool end_has; uint32_t end_plen; bool touched; uint32_t boff; };
+    std::vector<Walk> walks(n_chains);
+    std::vector<Seg> segs;
+    segs.reserve(n_chains * 2);
+    struct Pk { bool has; uint32_t plen; uint64_t coeff, pos; };
+    std::vector<Pk> pk;
+    std::vector<uint8_t> bytes(total_packets * 3 + 16);
+    size_t boff = 0, max_rounds = 0;
+    uint64_t c_lo = ~0ull, c_hi = 0, o_lo = ~0ull, o_hi = 0, r_lo = ~0ull, r_hi = 0;
+    int uniform_c = -1;
+    bool need_dense = false;
+    std::vector<uint8_t> is_l;           // bit0 fused-kernel packet, bit1 follows a short block, bit2 precedes one
+    for (size_t i = 0; i < n_chains; i++) {
+        lwb_chain *c = &chains[i];
+        lwb_stream *s = c->stream;
+        const lwb_setup *su = s->setup;
+        if (s->busy_epoch == epoch) return fail(ctx, LWB_ERR_INVALID, "a stream appears in two chains of one batch");
+        s->busy_epoch = epoch;
+        const unsigned C = su->channels;
+        if (residue) {
+            if (uniform_c < 0) uniform_c = (int)C;
+            if (uniform_c != (int)C) return fail(ctx, LWB_ERR_INVALID, "residue batches need one channel count");
+        }
+        Walk &w = walks[i];
+        w.boff = (uint32_t)boff;
+        bool has = s->has, clear_after = false;
+        uint32_t plen = s->plen, done = 0;
+        uint64_t coeff = c->coeff_offset, pos = 0;
+        c->status = LWB_OK;
+        // pass 1: geometry + which packets the fused kernel may take (state entering them is empty or 1024)
+        if (pk.size() < c->n_packets) { pk.resize(c->n_packets); is_l.resize(c->n_packets); }
+        w.seg0 = (uint32_t)segs.size();
+        w.n_seg = 0;
+        for (uint32_t k = 0; k < c->n_packets; k++) {
+            Geom g;
+            int grc = geometry(su, c->mode_numbers[k], c->prev_window_flags ? c->prev_window_flags[k] : 1,
+                               c->next_window_flags ? c->next_window_flags[k] : 1, &g);
+            if (grc) { c->status = grc; break; }
+            if (has) {
+                const uint32_t slope_len = 1u << ((g.slope_sel ? su->bs1 : su->bs0) - 1);
+                if (slope_len < plen) { c->status = LWB_ERR_BAD_FORMAT; clear_after = true; break; }
+                if (g.ls + plen > g.n) { c->status = LWB_ERR_MISMATCH; break; }
+            }
+            pk[k] = Pk{has, plen, coeff, pos};
+            is_l[k] = 0;
+            if (g.blockflag && g.n == (uint32_t)kLongN) {
+                const bool fs = g.ls != 0, lsf = g.re != g.n;
+                if (!has || plen == (fs ? (uint32_t)pl_short : (uint32_t)kLongN2)) is_l[k] = 1 | (fs ? 2 : 0) | (lsf ? 4 : 0);
+            }
+            bytes[boff + 3 * k] = c->mode_numbers[k];
+            bytes[boff + 3 * k + 1] = c->prev_window_flags ? c->prev_window_flags[k] : 1;
+            bytes[boff + 3 * k + 2] = c->next_window_flags ? c->next_window_flags[k] : 1;
+            if (has) pos += g.rs - g.ls;
+            coeff += (uint64_t)C * (g.n >> 1);
+            has = true;
+            plen = g.re - g.rs;
+            done++;
+        }
+        c->packets_done = done;
+        c->n_samples = (uint32_t)pos;
+        w.end_has = clear_after ? false : has;
+        w.end_plen = clear_after ? 0u : plen;
+        w.touched = done > 0 || clear_after;
+        boff += (size_t)done * 3;
+        if (!done) continue;
+        if (c->out_stride < pos) return fail(ctx, LWB_ERR_BUFFER, "chain: out_stride smaller than the samples produced");
+        // pass 2: segments.  A fused-kernel run starts at a long block that follows a short one and ends at
+        // one that precedes a short one; everything else is handed to the chain kernel.
+        uint32_t k = 0;
+        while (k < done) {
+            uint32_t j = k + 1;
+            if (is_l[k]) {
+                while (j < done && is_l[j] && !(is_l[j - 1] & 4) && !(is_l[j] & 2)) j++;
+                segs.push_back(Seg{true, (is_l[k] & 2) != 0, (is_l[j - 1] & 4) != 0, k, j - k, pk[k].has, pk[k].plen, pk[k].coeff,
+                                     pk[k].pos});
+            } else {
+                while (j < done && !is_l[j]) j++;
+                for (uint32_t q = k; q < j; q++)
+                    if (su->host.mode_blockflag[c->mode_numbers[q]]) chain_sees_long = true;
+                segs.push_back(Seg{false, false, false, k, j - k, pk[k].has, pk[k].plen, pk[k].coeff, pk[k].pos});
+            }
+            k = j;
+        }
+        w.n_seg = (uint32_t)segs.size() - w.seg0;
+        max_rounds = std::max<size_t>(max_rounds, w.n_seg);
+        c_lo = std::min(c_lo, c->coeff_offset);
+        c_hi = std::max(c_hi, coeff);
+        o_lo = std::min(o_lo, c->out_offset);
+        o_hi = std::max(o_hi, c->out_offset + (uint64_t)(C - 1) * c->out_stride + pos);
+        if (residue) {
+            r_lo = std::min(r_lo, c->packet_index);
+            r_hi = std::max<uint64_t>(r_hi, c->packet_index + done);
+            for (uint64_t r = c->packet_index * C; r < (c->packet_index + done) * C; r++) {
+                const uint8_t kd = io->floor_kind[r];
+                if (kd > LWB_FLOOR_DENSE) return fail(ctx, LWB_ERR_INVALID, "floor_kind out of range");
+                if (kd == LWB_FLOOR_ONE && !io->floor1_y) return fail(ctx, LWB_ERR_INVALID, "floor1_y missing");
+                if (kd == LWB_FLOOR_DENSE) need_dense = true;
+            }
+        }
+    }
+    if (need_dense && !io->dense_floor) return fail(ctx, LWB_ERR_INVALID, "dense_floor missing");
+    int rc = LWB_OK;
+    if (!chain_sees_long) n1max = n0max;
+    int wpc = std::max(1, std::min(8, n1max / 1024));
+    while (wpc > 1 && (unsigned)wpc * maxc > 32) wpc >>= 1;
+    const int np = chain_np(maxc, n1max, wpc, residue);
+    const size_t smem = chain_smem(maxc, n1max, np);
+    if (max_rounds) {
+        const bool host = io->memory == LWB_MEM_HOST;
+        cudaStream_t sm = ctx->stream;
+        const float *d_coeffs = io->coeffs, *d_dense = io->dense_floor;
+        char *d_pcm = (char *)io->pcm;
+        if (host) {
+            if ((rc = ensure(ctx, ctx->coeffs, (size_t)(c_hi - c_lo) * 4))) return rc;
+            if (o_hi > o_lo && (rc = ensure(ctx, ctx->pcm, (size_t)(o_hi - o_lo) * esz))) return rc;
+            CU(ctx, cudaMemcpyAsync(ctx->coeffs.p, io->coeffs + c_lo, (size_t)(c_hi - c_lo) * 4, cudaMemcpyHostToDevice, sm));
+            d_coeffs = (const float *)ctx->coeffs.p - c_lo;
+            if (need_dense) {
+                if ((rc = ensure(ctx, ctx->dense, (size_t)(c_hi - c_lo) * 4))) return rc;
+                CU(ctx, cudaMemcpyAsync(ctx->dense.p, io->dense_floor + c_lo, (size_t)(c_hi - c_lo) * 4, cudaMemcpyHostToDevice, sm));
+                d_dense = (const float *)ctx->dense.p - c_lo;
+            }
+            d_pcm = (char *)ctx->pcm.p - o_lo * esz;
+        }
+        const uint8_t *d_kinds = nullptr;
+        const uint32_t *d_ys = nullptr;
+        if (residue) {
+            const size_t rows = (size_t)(r_hi - r_lo) * uniform_c;
+            if ((rc = ensure(ctx, ctx->kinds, rows))) return rc;
+            CU(ctx, cudaMemcpyAsync(ctx->kinds.p, io->floor_kind + r_lo * uniform_c, rows, cudaMemcpyHostToDevice, sm));
+            d_kinds = (const uint8_t *)ctx->kinds.p - r_lo * uniform_c;
+            if (io->floor1_y) {
+                if ((rc = ensure(ctx, ctx->ys, rows * LWB_MAX_POSTS * 4))) return rc;
+                CU(ctx, cudaMemcpyAsync(ctx->ys.p, io->floor1_y + r_lo * uniform_c * LWB_MAX_POSTS, rows * LWB_MAX_POSTS * 4,
+                                        cudaMemcpyHostToDevice, sm));
+                d_ys = (const uint32_t *)ctx->ys.p - r_lo * uniform_c * LWB_MAX_POSTS;
+            }
+        }
+        // descriptors of every round: [LongRun...][ChainDesc...][DevPacket (prologue of the long segments)...][mode bytes]
+        // A round with few fused-kernel runs leaves most of the 148 x 8 warps idle and lasts as long as its
+        // longest run: such rounds cut their runs (each cut costs one extra IMDCT, the primer packet whose
+        // right half is all the next piece needs), as the all-long path does.
+        const size_t target_runs = (size_t)ctx->sm_count * kLongWarps * 2;
+        constexpr uint32_t kMinCutRun = 6;
+        std::vector<size_t> round_long(max_rounds, 0);
+        for (size_t i = 0; i < n_chains; i++)
+            for (uint32_t q = 0; q < walks[i].n_seg; q++)
+                if (segs[walks[i].seg0 + q].is_long) round_long[q] += chains[i].stream->setup->channels;
+        std::vector<uint32_t> round_cut(max_rounds, 1);
+        if (!getenv("LWB_MIXED_NO_CUTS"))
+            for (size_t r = 0; r < max_rounds; r++)
+                if (round_long[r] && round_long[r] < target_runs)
+                    round_cut[r] = (uint32_t)std::min<size_t>(16, (target_runs + round_long[r] - 1) / round_long[r]);
+        auto cuts_of = [&](const Seg &sg, size_t r) { return std::max<uint32_t>(1, std::min(round_cut[r], sg.n / kMinCutRun)); };
+        size_t n_runs = 0, n_cd = 0, n_pro = 0;
+        for (size_t i = 0; i < n_chains; i++)
+            for (uint32_t q = 0; q < walks[i].n_seg; q++) {
+                const Seg &sg = segs[walks[i].seg0 + q];
+                if (sg.is_long) { n_runs += (size_t)chains[i].stream->setup->channels * cuts_of(sg, q); if (residue) n_pro += sg.n; }
+                else n_cd++;
+            }
+        // a prepared batch (device memory, spectrum entry) owns its descriptors so that later executions replay them
+        const bool capture = plan && !host && !residue;
+        DevBuf &dbuf = capture ? plan->mix : ctx->cdesc;
+        const size_t off_cd = n_runs * sizeof(LongRun), off_pro = off_cd + n_cd * sizeof(ChainDesc);
+        const size_t off_by = off_pro + n_pro * sizeof(DevPacket), total = off_by + boff + 16;
+        Staging *st;
+        if ((rc = acquire_staging(ctx, total, &st))) return rc;
+        if ((rc = ensure(ctx, dbuf, total))) return rc;
+        char *hb = (char *)st->h, *db = (char *)dbuf.p;
+        LongRun *h_runs = (LongRun *)hb;
+        ChainDesc *h_cd = (ChainDesc *)(hb + off_cd);
+        DevPacket *h_pro = (DevPacket *)(hb + off_pro);
+        std::memcpy(hb + off_by, bytes.data(), boff);
+        const float *d_spec = nullptr;
+        if (residue && n_pro) {
+            if ((rc = ensure(ctx, ctx->spec, (size_t)(c_hi - c_lo) * 4))) return rc;
+            d_spec = (const float *)ctx->spec.p - c_lo;          // same element offsets as the coefficient arena
+        }
+        std::vector<MixRound> rounds(max_rounds);
+        size_t wr = 0, wc = 0, wp = 0;
+        for (size_t r = 0; r < max_rounds; r++) {
+            rounds[r].r0 = wr;
+            rounds[r].c0 = wc;
+            // fused-kernel runs first, longest first (three buckets): the kernel hands runs out in
+            // descriptor order, and a 64-packet run started last would be the whole round's tail
+            for (int bucket = 0; bucket < 3; bucket++)
+                for (size_t i = 0; i < n_chains; i++) {
+                    if (r >= walks[i].n_seg) continue;
+                    const Seg &sg = segs[walks[i].seg0 + r];
+                    if (!sg.is_long) continue;
+                    const uint32_t cuts = cuts_of(sg, r), piece = sg.n / cuts;
+                    if ((piece >= 32 ? 0 : piece >= 8 ? 1 : 2) != bucket) continue;
+                    const lwb_chain *c = &chains[i];
+                    const lwb_stream *s = c->stream;
+                    const lwb_setup *su = s->setup;
+                    const unsigned C = su->channels;
+                    // samples packet 0 emits (0 without history; a block after a short one emits 1024 - ls)
+                    const size_t first_emit = sg.has ? (sg.first_short ? (size_t)kLongN2 - ls_long : (size_t)kLongN2) : 0;
+                    for (unsigned ch = 0; ch < C; ch++) {
+                        const float *in0 = (residue ? d_spec : d_coeffs) + sg.coeff + (size_t)ch * kLongN2;
+                        char *out0 = d_pcm + (c->out_offset + (size_t)ch * c->out_stride + sg.pos) * esz;
+                        for (uint32_t k = 0; k < cuts; k++) {
+                            const size_t p0 = (size_t)sg.n * k / cuts, p1 = (size_t)sg.n * (k + 1) / cuts;
+                            LongRun &lr = h_runs[wr++];
+                            std::memset(&lr, 0, sizeof(lr));
+                            lr.in_stride = (uint32_t)(C * kLongN2);
+                            lr.state = s->d_state + (size_t)ch * state_stride(su);
+                            lr.write_state = (k + 1 == cuts);
+                            lr.last_short = (k + 1 == cuts) && sg.last_short;
+                            if (k == 0) {
+                                lr.in = in0;
+                                lr.out = out0;
+                                lr.n_packets = (uint32_t)(p1 - p0);
+                                lr.has_prev = sg.has;
+                                lr.first_short = sg.first_short;
+                            } else {
+                                lr.in = in0 + (p0 - 1) * (size_t)lr.in_stride;         // primer = packet p0 - 1
+                                lr.out = out0 + (first_emit + (p0 - 1) * (size_t)kLongN2) * esz;
+                                lr.n_packets = (uint32_t)(p1 - p0 + 1);
+                                lr.has_prev = 0;
+                            }
+                        }
+                    }
+                    if (residue)
+                        for (uint32_t q = 0; q < sg.n; q++) {
+                            DevPacket &d = h_pro[wp++];
+                            std::memset(&d, 0, sizeof(d));
+                            d.setup = su->d_setup;
+                            d.coeff_off = sg.coeff + (uint64_t)q * C * kLongN2;
+                            d.pkt_index = c->packet_index + sg.p0 + q;
+                            d.n = kLongN;
+                            d.blockflag = 1;
+                            d.mapping = su->host.mode_mapping[c->mode_numbers[sg.p0 + q]];
+                            d.channels = (uint8_t)C;
+                        }
+                }
+            for (size_t i = 0; i < n_chains; i++) {
+                if (r >= walks[i].n_seg) continue;
+                const Seg &sg = segs[walks[i].seg0 + r];
+                if (sg.is_long) continue;
+                const lwb_chain *c = &chains[i];
+                const lwb_stream *s = c->stream;
+                const lwb_setup *su = s->setup;
+                ChainDesc &d = h_cd[wc++];
+                std::memset(&d, 0, sizeof(d));
+                d.setup = su->d_setup;
+                d.state = s->d_state;
+                d.coeff_off = sg.coeff;
+                d.out_off = c->out_offset + sg.pos;
+                d.out_stride = c->out_stride;
+                d.pkt_index = c->packet_index + sg.p0;
+                d.n_packets = sg.n;
+                d.byte_off = walks[i].boff + 3 * sg.p0;
+                d.state_stride = (uint32_t)state_stride(su);
+                d.plen0 = (uint16_t)sg.plen;
+                d.has0 = sg.has;
+                d.channels = (uint8_t)su->channels;
+            }
+            rounds[r].nr = wr - rounds[r].r0;
+            rounds[r].nc = wc - rounds[r].c0;
+        }
+        CU(ctx, cudaMemcpyAsync(db, hb, total, cudaMemcpyHostToDevice, sm));
+        CU(ctx, cudaEventRecord(st->ev, sm));
+        st->pending = true;
+        if (residue && n_pro)
+            if ((rc = launch(ctx, k_prologue, dim3((unsigned)n_pro), dim3(kPrologueThreads), 0, (const DevPacket *)(db + off_pro),
+                             d_coeffs, d_dense, d_kinds, d_ys, const_cast<float *>(d_spec))))
+                return rc;
+        constexpr uint32_t kTicketPool = 1024;
+        if (!ctx->ticket.p) {
+            if ((rc = ensure(ctx, ctx->ticket, kTicketPool * sizeof(unsigned int)))) return rc;
+            for (int k = 0; k < 2; k++) {
+                CU(ctx, cudaEventCreateWithFlags(&ctx->ev_desc[k], cudaEventDisableTiming));
+                CU(ctx, cudaEventCreateWithFlags(&ctx->ev_kdone[k], cudaEventDisableTiming));
+            }
+        }
+        MixLaunch ml;
+        ml.db = db; ml.off_cd = off_cd; ml.off_by = off_by; ml.pack = pack; ml.w_short = w_short; ml.ls = ls_long;
+        ml.i16 = i16; ml.residue = residue; ml.out_format = io->out_format; ml.warps = maxc * wpc; ml.smem = smem;
+        ml.n1max = n1max; ml.wpc = wpc; ml.np = np; ml.coeffs = d_coeffs; ml.dense = d_dense; ml.kinds = d_kinds; ml.ys = d_ys; ml.pcm = d_pcm;
+        if ((rc = mixed_launch_rounds(ctx, ml, rounds))) return rc;
+        if (capture) {
+            plan->mixed_captured = true;
+            plan->gen = gen_at_entry;
+            plan->mix_launch = ml;
+            plan->mix_rounds = std::move(rounds);
+        }
+        if (host) {
+            if (o_hi > o_lo)
+                CU(ctx, cudaMemcpyAsync((char *)io->pcm + o_lo * esz, ctx->pcm.p, (size_t)(o_hi - o_lo) * esz, cudaMemcpyDeviceToHost, sm));
+            CU(ctx, cudaStreamSynchronize(sm));
+        }
+    }
+    for (size_t i = 0; i < n_chains; i++)
+        if (walks[i].touched) set_stream_state(chains[i].stream, walks[i].end_has, walks[i].end_plen);
+    return LWB_OK;
+}
+
