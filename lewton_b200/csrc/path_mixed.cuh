@@ -53,7 +53,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
 
     struct Seg { bool is_long, first_short, last_short; uint32_t p0, n; bool has; uint32_t plen; uint64_t coeff, pos; };
     bool chain_sees_long = false;       // the chain kernel's shared memory is sized for what it actually gets
-    struct Walk { uint32_t seg0, n_seg; bool end_has; uint32_t end_plen; bool touched; uint32_t boff; };
+    struct Walk { uint32_t seg0, n_seg; bool end_has; uint32_t end_plen; bool touched; uint32_t boff; uint64_t coeff_end; };
     std::vector<Walk> walks(n_chains);
     std::vector<Seg> segs;
     segs.reserve(n_chains * 2);
@@ -116,6 +116,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         w.end_has = clear_after ? false : has;
         w.end_plen = clear_after ? 0u : plen;
         w.touched = done > 0 || clear_after;
+        w.coeff_end = coeff;
         boff += (size_t)done * 3;
         if (!done) continue;
         if (c->out_stride < pos) return fail(ctx, LWB_ERR_BUFFER, "chain: out_stride smaller than the samples produced");
@@ -168,14 +169,27 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         if (host) {
             if ((rc = ensure(ctx, ctx->coeffs, (size_t)(c_hi - c_lo) * 4))) return rc;
             if (o_hi > o_lo && (rc = ensure(ctx, ctx->pcm, (size_t)(o_hi - o_lo) * esz))) return rc;
-            CU(ctx, cudaMemcpyAsync(ctx->coeffs.p, io->coeffs + c_lo, (size_t)(c_hi - c_lo) * 4, cudaMemcpyHostToDevice, sm));
-            d_coeffs = (const float *)ctx->coeffs.p - c_lo;
+            d_coeffs = (const float *)ctx->coeffs.p - c_lo;       // the copies themselves go chunk by chunk, below
             if (need_dense) {
                 if ((rc = ensure(ctx, ctx->dense, (size_t)(c_hi - c_lo) * 4))) return rc;
-                CU(ctx, cudaMemcpyAsync(ctx->dense.p, io->dense_floor + c_lo, (size_t)(c_hi - c_lo) * 4, cudaMemcpyHostToDevice, sm));
                 d_dense = (const float *)ctx->dense.p - c_lo;
             }
             d_pcm = (char *)ctx->pcm.p - o_lo * esz;
+            if (!ctx->ev_in[0])
+                for (int k = 0; k < 65; k++) {
+                    if (k < 64) CU(ctx, cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming));
+                    CU(ctx, cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming));
+                }
+            // the copy streams must not run ahead of work already queued on the compute stream
+            CU(ctx, cudaEventRecord(ctx->ev_done[64], sm));
+            CU(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[64], 0));
+            CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[64], 0));
+        }
+        // host memory: chunks of chains, so that H2D / kernels / D2H of consecutive chunks overlap on three streams
+        size_t n_chunks = 1;
+        if (host) {
+            n_chunks = std::min<size_t>(std::max<size_t>(1, ((size_t)(c_hi - c_lo) * 4) >> 25), std::min<size_t>(8, n_chains));
+            if (const char *e = getenv("LWB_E2E_CHUNKS")) n_chunks = std::max<size_t>(1, std::min<size_t>((size_t)atol(e), std::min<size_t>(64, n_chains)));
         }
         const uint8_t *d_kinds = nullptr;
         const uint32_t *d_ys = nullptr;
@@ -197,23 +211,46 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         // right half is all the next piece needs), as the all-long path does.
         const size_t target_runs = (size_t)ctx->sm_count * kLongWarps * 2;
         constexpr uint32_t kMinCutRun = 6;
-        std::vector<size_t> round_long(max_rounds, 0);
-        for (size_t i = 0; i < n_chains; i++)
-            for (uint32_t q = 0; q < walks[i].n_seg; q++)
-                if (segs[walks[i].seg0 + q].is_long) round_long[q] += chains[i].stream->setup->channels;
-        std::vector<uint32_t> round_cut(max_rounds, 1);
-        if (!getenv("LWB_MIXED_NO_CUTS"))
-            for (size_t r = 0; r < max_rounds; r++)
-                if (round_long[r] && round_long[r] < target_runs)
-                    round_cut[r] = (uint32_t)std::min<size_t>(16, (target_runs + round_long[r] - 1) / round_long[r]);
-        auto cuts_of = [&](const Seg &sg, size_t r) { return std::max<uint32_t>(1, std::min(round_cut[r], sg.n / kMinCutRun)); };
+        struct Chunk {
+            size_t i0, i1, p0, np_;                      // chains, prologue packets
+            uint64_t kc_lo, kc_hi, ko_lo, ko_hi;         // coefficient / pcm element ranges
+            std::vector<uint32_t> round_cut;
+            std::vector<MixRound> rounds;
+        };
+        std::vector<Chunk> chunks(n_chunks);
+        auto cuts_of = [&](const Chunk &ck, const Seg &sg, size_t r) {
+            return std::max<uint32_t>(1, std::min(ck.round_cut[r], sg.n / kMinCutRun));
+        };
         size_t n_runs = 0, n_cd = 0, n_pro = 0;
-        for (size_t i = 0; i < n_chains; i++)
-            for (uint32_t q = 0; q < walks[i].n_seg; q++) {
-                const Seg &sg = segs[walks[i].seg0 + q];
-                if (sg.is_long) { n_runs += (size_t)chains[i].stream->setup->channels * cuts_of(sg, q); if (residue) n_pro += sg.n; }
-                else n_cd++;
+        for (size_t k = 0; k < n_chunks; k++) {
+            Chunk &ck = chunks[k];
+            ck.i0 = n_chains * k / n_chunks;
+            ck.i1 = n_chains * (k + 1) / n_chunks;
+            ck.kc_lo = ck.ko_lo = ~0ull;
+            ck.kc_hi = ck.ko_hi = 0;
+            std::vector<size_t> round_long(max_rounds, 0);
+            for (size_t i = ck.i0; i < ck.i1; i++) {
+                const unsigned C = chains[i].stream->setup->channels;
+                for (uint32_t q = 0; q < walks[i].n_seg; q++)
+                    if (segs[walks[i].seg0 + q].is_long) round_long[q] += C;
+                if (!walks[i].n_seg) continue;
+                ck.kc_lo = std::min(ck.kc_lo, chains[i].coeff_offset);
+                ck.kc_hi = std::max(ck.kc_hi, walks[i].coeff_end);
+                ck.ko_lo = std::min(ck.ko_lo, chains[i].out_offset);
+                ck.ko_hi = std::max(ck.ko_hi, chains[i].out_offset + (uint64_t)(C - 1) * chains[i].out_stride + chains[i].n_samples);
             }
+            ck.round_cut.assign(max_rounds, 1);
+            if (!getenv("LWB_MIXED_NO_CUTS"))
+                for (size_t r = 0; r < max_rounds; r++)
+                    if (round_long[r] && round_long[r] < target_runs)
+                        ck.round_cut[r] = (uint32_t)std::min<size_t>(16, (target_runs + round_long[r] - 1) / round_long[r]);
+            for (size_t i = ck.i0; i < ck.i1; i++)
+                for (uint32_t q = 0; q < walks[i].n_seg; q++) {
+                    const Seg &sg = segs[walks[i].seg0 + q];
+                    if (sg.is_long) { n_runs += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, q); if (residue) n_pro += sg.n; }
+                    else n_cd++;
+                }
+        }
         // a prepared batch (device memory, spectrum entry) owns its descriptors so that later executions replay them
         const bool capture = plan && !host && !residue;
         DevBuf &dbuf = capture ? plan->mix : ctx->cdesc;
@@ -232,96 +269,96 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             if ((rc = ensure(ctx, ctx->spec, (size_t)(c_hi - c_lo) * 4))) return rc;
             d_spec = (const float *)ctx->spec.p - c_lo;          // same element offsets as the coefficient arena
         }
-        std::vector<MixRound> rounds(max_rounds);
         size_t wr = 0, wc = 0, wp = 0;
-        for (size_t r = 0; r < max_rounds; r++) {
-            rounds[r].r0 = wr;
-            rounds[r].c0 = wc;
-            // fused-kernel runs first, longest first (three buckets): the kernel hands runs out in
-            // descriptor order, and a 64-packet run started last would be the whole round's tail
-            for (int bucket = 0; bucket < 3; bucket++)
-                for (size_t i = 0; i < n_chains; i++) {
+        for (Chunk &ck : chunks) {
+            ck.rounds.assign(max_rounds, MixRound{0, 0, 0, 0});
+            ck.p0 = wp;
+            for (size_t r = 0; r < max_rounds; r++) {
+                ck.rounds[r].r0 = wr;
+                ck.rounds[r].c0 = wc;
+                // fused-kernel runs first, longest first (three buckets): the kernel hands runs out in
+                // descriptor order, and a 64-packet run started last would be the whole round's tail
+                for (int bucket = 0; bucket < 3; bucket++)
+                    for (size_t i = ck.i0; i < ck.i1; i++) {
+                        if (r >= walks[i].n_seg) continue;
+                        const Seg &sg = segs[walks[i].seg0 + r];
+                        if (!sg.is_long) continue;
+                        const uint32_t cuts = cuts_of(ck, sg, r), piece = sg.n / cuts;
+                        if ((piece >= 32 ? 0 : piece >= 8 ? 1 : 2) != bucket) continue;
+                        const lwb_chain *c = &chains[i];
+                        const lwb_stream *s = c->stream;
+                        const lwb_setup *su = s->setup;
+                        const unsigned C = su->channels;
+                        // samples packet 0 emits (0 without history; a block after a short one emits 1024 - ls)
+                        const size_t first_emit = sg.has ? (sg.first_short ? (size_t)kLongN2 - ls_long : (size_t)kLongN2) : 0;
+                        for (unsigned ch = 0; ch < C; ch++) {
+                            const float *in0 = (residue ? d_spec : d_coeffs) + sg.coeff + (size_t)ch * kLongN2;
+                            char *out0 = d_pcm + (c->out_offset + (size_t)ch * c->out_stride + sg.pos) * esz;
+                            for (uint32_t k = 0; k < cuts; k++) {
+                                const size_t p0 = (size_t)sg.n * k / cuts, p1 = (size_t)sg.n * (k + 1) / cuts;
+                                LongRun &lr = h_runs[wr++];
+                                std::memset(&lr, 0, sizeof(lr));
+                                lr.in_stride = (uint32_t)(C * kLongN2);
+                                lr.state = s->d_state + (size_t)ch * state_stride(su);
+                                lr.write_state = (k + 1 == cuts);
+                                lr.last_short = (k + 1 == cuts) && sg.last_short;
+                                if (k == 0) {
+                                    lr.in = in0;
+                                    lr.out = out0;
+                                    lr.n_packets = (uint32_t)(p1 - p0);
+                                    lr.has_prev = sg.has;
+                                    lr.first_short = sg.first_short;
+                                } else {
+                                    lr.in = in0 + (p0 - 1) * (size_t)lr.in_stride;         // primer = packet p0 - 1
+                                    lr.out = out0 + (first_emit + (p0 - 1) * (size_t)kLongN2) * esz;
+                                    lr.n_packets = (uint32_t)(p1 - p0 + 1);
+                                    lr.has_prev = 0;
+                                }
+                            }
+                        }
+                        if (residue)
+                            for (uint32_t q = 0; q < sg.n; q++) {
+                                DevPacket &d = h_pro[wp++];
+                                std::memset(&d, 0, sizeof(d));
+                                d.setup = su->d_setup;
+                                d.coeff_off = sg.coeff + (uint64_t)q * C * kLongN2;
+                                d.pkt_index = c->packet_index + sg.p0 + q;
+                                d.n = kLongN;
+                                d.blockflag = 1;
+                                d.mapping = su->host.mode_mapping[c->mode_numbers[sg.p0 + q]];
+                                d.channels = (uint8_t)C;
+                            }
+                    }
+                for (size_t i = ck.i0; i < ck.i1; i++) {
                     if (r >= walks[i].n_seg) continue;
                     const Seg &sg = segs[walks[i].seg0 + r];
-                    if (!sg.is_long) continue;
-                    const uint32_t cuts = cuts_of(sg, r), piece = sg.n / cuts;
-                    if ((piece >= 32 ? 0 : piece >= 8 ? 1 : 2) != bucket) continue;
+                    if (sg.is_long) continue;
                     const lwb_chain *c = &chains[i];
                     const lwb_stream *s = c->stream;
                     const lwb_setup *su = s->setup;
-                    const unsigned C = su->channels;
-                    // samples packet 0 emits (0 without history; a block after a short one emits 1024 - ls)
-                    const size_t first_emit = sg.has ? (sg.first_short ? (size_t)kLongN2 - ls_long : (size_t)kLongN2) : 0;
-                    for (unsigned ch = 0; ch < C; ch++) {
-                        const float *in0 = (residue ? d_spec : d_coeffs) + sg.coeff + (size_t)ch * kLongN2;
-                        char *out0 = d_pcm + (c->out_offset + (size_t)ch * c->out_stride + sg.pos) * esz;
-                        for (uint32_t k = 0; k < cuts; k++) {
-                            const size_t p0 = (size_t)sg.n * k / cuts, p1 = (size_t)sg.n * (k + 1) / cuts;
-                            LongRun &lr = h_runs[wr++];
-                            std::memset(&lr, 0, sizeof(lr));
-                            lr.in_stride = (uint32_t)(C * kLongN2);
-                            lr.state = s->d_state + (size_t)ch * state_stride(su);
-                            lr.write_state = (k + 1 == cuts);
-                            lr.last_short = (k + 1 == cuts) && sg.last_short;
-                            if (k == 0) {
-                                lr.in = in0;
-                                lr.out = out0;
-                                lr.n_packets = (uint32_t)(p1 - p0);
-                                lr.has_prev = sg.has;
-                                lr.first_short = sg.first_short;
-                            } else {
-                                lr.in = in0 + (p0 - 1) * (size_t)lr.in_stride;         // primer = packet p0 - 1
-                                lr.out = out0 + (first_emit + (p0 - 1) * (size_t)kLongN2) * esz;
-                                lr.n_packets = (uint32_t)(p1 - p0 + 1);
-                                lr.has_prev = 0;
-                            }
-                        }
-                    }
-                    if (residue)
-                        for (uint32_t q = 0; q < sg.n; q++) {
-                            DevPacket &d = h_pro[wp++];
-                            std::memset(&d, 0, sizeof(d));
-                            d.setup = su->d_setup;
-                            d.coeff_off = sg.coeff + (uint64_t)q * C * kLongN2;
-                            d.pkt_index = c->packet_index + sg.p0 + q;
-                            d.n = kLongN;
-                            d.blockflag = 1;
-                            d.mapping = su->host.mode_mapping[c->mode_numbers[sg.p0 + q]];
-                            d.channels = (uint8_t)C;
-                        }
+                    ChainDesc &d = h_cd[wc++];
+                    std::memset(&d, 0, sizeof(d));
+                    d.setup = su->d_setup;
+                    d.state = s->d_state;
+                    d.coeff_off = sg.coeff;
+                    d.out_off = c->out_offset + sg.pos;
+                    d.out_stride = c->out_stride;
+                    d.pkt_index = c->packet_index + sg.p0;
+                    d.n_packets = sg.n;
+                    d.byte_off = walks[i].boff + 3 * sg.p0;
+                    d.state_stride = (uint32_t)state_stride(su);
+                    d.plen0 = (uint16_t)sg.plen;
+                    d.has0 = sg.has;
+                    d.channels = (uint8_t)su->channels;
                 }
-            for (size_t i = 0; i < n_chains; i++) {
-                if (r >= walks[i].n_seg) continue;
-                const Seg &sg = segs[walks[i].seg0 + r];
-                if (sg.is_long) continue;
-                const lwb_chain *c = &chains[i];
-                const lwb_stream *s = c->stream;
-                const lwb_setup *su = s->setup;
-                ChainDesc &d = h_cd[wc++];
-                std::memset(&d, 0, sizeof(d));
-                d.setup = su->d_setup;
-                d.state = s->d_state;
-                d.coeff_off = sg.coeff;
-                d.out_off = c->out_offset + sg.pos;
-                d.out_stride = c->out_stride;
-                d.pkt_index = c->packet_index + sg.p0;
-                d.n_packets = sg.n;
-                d.byte_off = walks[i].boff + 3 * sg.p0;
-                d.state_stride = (uint32_t)state_stride(su);
-                d.plen0 = (uint16_t)sg.plen;
-                d.has0 = sg.has;
-                d.channels = (uint8_t)su->channels;
+                ck.rounds[r].nr = wr - ck.rounds[r].r0;
+                ck.rounds[r].nc = wc - ck.rounds[r].c0;
             }
-            rounds[r].nr = wr - rounds[r].r0;
-            rounds[r].nc = wc - rounds[r].c0;
+            ck.np_ = wp - ck.p0;
         }
         CU(ctx, cudaMemcpyAsync(db, hb, total, cudaMemcpyHostToDevice, sm));
         CU(ctx, cudaEventRecord(st->ev, sm));
         st->pending = true;
-        if (residue && n_pro)
-            if ((rc = launch(ctx, k_prologue, dim3((unsigned)n_pro), dim3(kPrologueThreads), 0, (const DevPacket *)(db + off_pro),
-                             d_coeffs, d_dense, d_kinds, d_ys, const_cast<float *>(d_spec))))
-                return rc;
         constexpr uint32_t kTicketPool = 1024;
         if (!ctx->ticket.p) {
             if ((rc = ensure(ctx, ctx->ticket, kTicketPool * sizeof(unsigned int)))) return rc;
@@ -334,16 +371,38 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         ml.db = db; ml.off_cd = off_cd; ml.off_by = off_by; ml.pack = pack; ml.w_short = w_short; ml.ls = ls_long;
         ml.i16 = i16; ml.residue = residue; ml.out_format = io->out_format; ml.warps = maxc * wpc; ml.smem = smem;
         ml.n1max = n1max; ml.wpc = wpc; ml.np = np; ml.coeffs = d_coeffs; ml.dense = d_dense; ml.kinds = d_kinds; ml.ys = d_ys; ml.pcm = d_pcm;
-        if ((rc = mixed_launch_rounds(ctx, ml, rounds))) return rc;
+        for (size_t k = 0; k < n_chunks; k++) {
+            Chunk &ck = chunks[k];
+            if (ck.kc_hi <= ck.kc_lo) continue;
+            if (host) {
+                CU(ctx, cudaMemcpyAsync((float *)ctx->coeffs.p + (ck.kc_lo - c_lo), io->coeffs + ck.kc_lo, (size_t)(ck.kc_hi - ck.kc_lo) * 4,
+                                        cudaMemcpyHostToDevice, ctx->copy_in));
+                if (need_dense)
+                    CU(ctx, cudaMemcpyAsync((float *)ctx->dense.p + (ck.kc_lo - c_lo), io->dense_floor + ck.kc_lo,
+                                            (size_t)(ck.kc_hi - ck.kc_lo) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+                CU(ctx, cudaEventRecord(ctx->ev_in[k], ctx->copy_in));
+                CU(ctx, cudaStreamWaitEvent(sm, ctx->ev_in[k], 0));
+            }
+            if (residue && ck.np_)
+                if ((rc = launch(ctx, k_prologue, dim3((unsigned)ck.np_), dim3(kPrologueThreads), 0,
+                                 (const DevPacket *)(db + off_pro) + ck.p0, d_coeffs, d_dense, d_kinds, d_ys, const_cast<float *>(d_spec))))
+                    return rc;
+            if ((rc = mixed_launch_rounds(ctx, ml, ck.rounds))) return rc;
+            if (host && ck.ko_hi > ck.ko_lo) {
+                CU(ctx, cudaEventRecord(ctx->ev_done[k], sm));
+                CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[k], 0));
+                CU(ctx, cudaMemcpyAsync((char *)io->pcm + ck.ko_lo * esz, (char *)ctx->pcm.p + (ck.ko_lo - o_lo) * esz,
+                                        (size_t)(ck.ko_hi - ck.ko_lo) * esz, cudaMemcpyDeviceToHost, ctx->copy_out));
+            }
+        }
         if (capture) {
             plan->mixed_captured = true;
             plan->gen = gen_at_entry;
             plan->mix_launch = ml;
-            plan->mix_rounds = std::move(rounds);
+            plan->mix_rounds = std::move(chunks[0].rounds);
         }
         if (host) {
-            if (o_hi > o_lo)
-                CU(ctx, cudaMemcpyAsync((char *)io->pcm + o_lo * esz, ctx->pcm.p, (size_t)(o_hi - o_lo) * esz, cudaMemcpyDeviceToHost, sm));
+            CU(ctx, cudaStreamSynchronize(ctx->copy_out));
             CU(ctx, cudaStreamSynchronize(sm));
         }
     }

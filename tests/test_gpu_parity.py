@@ -746,7 +746,10 @@ def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle
         cases.append((np.concatenate(coeffs), np.concatenate(dense) if residue else None,
                       np.concatenate(kinds) if residue else None, np.concatenate(ys) if residue else None, want, seqs,
                       [r.pwr.data().copy() for r in refs]))
-    for name, env in (("mixed", None), ("chain", {"LWB_NO_MIXED": "1"})):
+    variants = [("mixed", None), ("chain", {"LWB_NO_MIXED": "1"})]
+    if memory == cabi.MEM_HOST:
+        variants.append(("mixed_chunked", {"LWB_E2E_CHUNKS": "3"}))       # H2D / kernels / D2H pipelined over 3 chunks of chains
+    for name, env in variants:
         pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
         for batch, (coeffs, dense, kinds, ys, want, seqs, end_state) in enumerate(cases):
             chains, coeff_off, out_off = [], 0, 0
@@ -784,7 +787,7 @@ def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle
                     for k in env:
                         del os.environ[k]
             n_launch = ctx.launch_count - launches0
-            if name == "mixed":
+            if name.startswith("mixed"):
                 assert n_launch >= 3, n_launch        # at least fused + chain + fused/chain rounds
             else:
                 assert n_launch == 1, n_launch
@@ -801,7 +804,8 @@ def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle
                 pos += n * channels
                 assert bits_equal(pwrs[s].data(), end_state[s]), (name, batch, s)
     for batch in range(2):
-        assert np.array_equal(outs[("mixed", batch)].view(np.uint8), outs[("chain", batch)].view(np.uint8))
+        for name, _ in variants[1:]:
+            assert np.array_equal(outs[("mixed", batch)].view(np.uint8), outs[(name, batch)].view(np.uint8)), name
 
 
 @pytest.mark.parametrize("P", [1, 2, 3, 5, 6])
