@@ -1086,24 +1086,24 @@ static int packet_decode(const Headers &h, const uint8_t *packet, size_t len, lw
 // Ogg paging: what ogg 0.8.0's PacketReader hands to inside_ogg.rs (packets with stream serial,
 // page granule position and first/last flags).  RFC 3533 framing, CRC-32 poly 0x04c11db7.
 // ---------------------------------------------------------------------------------------------
-static uint32_t crc_table[256];
-static bool crc_ready = false;
-static void crc_init()
-{
-    for (uint32_t i = 0; i < 256; i++) {
-        uint32_t r = i << 24;
-        for (int k = 0; k < 8; k++) r = (r & 0x80000000u) ? (r << 1) ^ 0x04c11db7u : r << 1;
-        crc_table[i] = r;
+struct CrcTable {
+    uint32_t t[256];
+    CrcTable()
+    {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t r = i << 24;
+            for (int k = 0; k < 8; k++) r = (r & 0x80000000u) ? (r << 1) ^ 0x04c11db7u : r << 1;
+            t[i] = r;
+        }
     }
-    crc_ready = true;
-}
+};
 static uint32_t ogg_crc(const uint8_t *d, size_t n, size_t crc_at)
 {
-    if (!crc_ready) crc_init();
+    static const CrcTable table;              // initialised once, thread-safe (readers on several host threads)
     uint32_t c = 0;
     for (size_t i = 0; i < n; i++) {
         const uint8_t b = (i >= crc_at && i < crc_at + 4) ? 0 : d[i];
-        c = (c << 8) ^ crc_table[((c >> 24) ^ b) & 0xff];
+        c = (c << 8) ^ table.t[((c >> 24) ^ b) & 0xff];
     }
     return c;
 }

@@ -11,6 +11,14 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+// pinned staging for one batch's descriptors; `ev` marks the end of the copy that reads it
+struct Staging {
+    void *h = nullptr;
+    size_t cap = 0;
+    cudaEvent_t ev = nullptr;
+    bool pending = false;
+};
+
 struct lwb_ctx {
     int device = 0;
     int sm_count = 0;
@@ -28,7 +36,9 @@ struct lwb_ctx {
     uint64_t launches = 0;
     // grow-only device arenas
     DevBuf coeffs, dense, pcm, spec, x, desc, kinds, ys, chains, ticket, cdesc, cbytes;
-    // pinned staging for descriptors
+    Staging stage[3];              // ring: a batch's descriptors are written while the previous copies may still run
+    int stage_next = 0;
+    // pinned staging for descriptors (four-kernel path)
     void *h_desc = nullptr;
     size_t h_desc_cap = 0;
     size_t x_cap_elems = (size_t)64 << 20;     // IMDCT scratch per round of the generic path (256 MiB)

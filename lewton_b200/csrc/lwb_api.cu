@@ -82,6 +82,16 @@ extern "C" void lwb_ctx_destroy(lwb_ctx *ctx)
                       &ctx->cdesc, &ctx->cbytes})
         if (b->p) cudaFree(b->p);
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
+    for (Staging &st : ctx->stage) {
+        if (st.h) cudaFreeHost(st.h);
+        if (st.ev) cudaEventDestroy(st.ev);
+    }
+    for (cudaEvent_t e : ctx->ev_in) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_done) if (e) cudaEventDestroy(e);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->ev_desc[k]) cudaEventDestroy(ctx->ev_desc[k]);
+        if (ctx->ev_kdone[k]) cudaEventDestroy(ctx->ev_kdone[k]);
+    }
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_in);
     cudaStreamDestroy(ctx->copy_out);

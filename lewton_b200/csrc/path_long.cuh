@@ -14,20 +14,10 @@ struct LongItem {
     bool has_prev;
 };
 
-struct Staging {
-    void *h = nullptr;
-    size_t cap = 0;
-    cudaEvent_t ev = nullptr;
-    bool pending = false;
-};
-static Staging g_stage[4][3];          // per device ordinal (ctx is per device), ring of 3
-static int g_stage_next[4];
-
 static int acquire_staging(lwb_ctx *ctx, size_t bytes, Staging **out)
 {
-    const int d = ctx->device & 3;
-    Staging &st = g_stage[d][g_stage_next[d]];
-    g_stage_next[d] = (g_stage_next[d] + 1) % 3;
+    Staging &st = ctx->stage[ctx->stage_next];
+    ctx->stage_next = (ctx->stage_next + 1) % 3;
     if (!st.ev) CU(ctx, cudaEventCreateWithFlags(&st.ev, cudaEventDisableTiming));
     if (st.pending) {
         CU(ctx, cudaEventSynchronize(st.ev));      // waits for the descriptor copy only, not for kernels
