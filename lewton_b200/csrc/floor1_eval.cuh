@@ -1,0 +1,122 @@
+// floor1_eval.cuh -- floor type 1 evaluation (audio.rs:354-555), integer only.  Host+device (LWB_HD) so
+// that tests/emu/floor1_emu.cpp can run exactly this source on the CPU against the oracle.
+#pragma once
+#include "kernel_long.cuh"      // LWB_HD
+#include "lwb_common.h"
+
+namespace lwb {
+
+// ---------------------------------------------------------------------------------------------
+// floor-1, audio.rs:354-435 -- run by one thread per (packet, channel); <= 65 posts, serial
+// ---------------------------------------------------------------------------------------------
+LWB_HD uint32_t d_render_point(uint32_t x0, uint32_t y0, uint32_t x1,
+                                                   uint32_t y1, uint32_t x)
+{
+    // audio.rs:354-367, u32/i32 wrapping like a release build
+    const int32_t dy = (int32_t)(y1 - y0);
+    const uint32_t adx = x1 - x0;
+    const uint32_t ady = (uint32_t)(dy < 0 ? -dy : dy);
+    const uint32_t off = (ady * (x - x0)) / adx;
+    return dy < 0 ? y0 - off : y0 + off;
+}
+
+// Writes the flagged posts in x order as (sx, sy = y * multiplier); returns their count
+// (+1 if a flat tail to n2 was appended, audio.rs:546-547).
+LWB_HD int d_floor1_posts(const DevFloor1 &fl, const uint32_t *__restrict__ y_in, int n2,
+                              uint16_t *sx, uint16_t *sy)
+{
+    uint32_t fy[LWB_MAX_POSTS];
+    uint64_t flag_lo = 3;        // posts 0..63
+    bool flag64 = false;         // post 64
+    const int np = fl.nposts;
+    const int32_t range = fl.mult == 1 ? 256 : fl.mult == 2 ? 128 : fl.mult == 3 ? 86 : 64;
+    fy[0] = y_in[0];
+    fy[1] = y_in[1];
+    for (int i = 2; i < np; i++) {           // audio.rs:401-429
+        const int li = fl.lo[i], hi = fl.hi[i];
+        const int32_t predicted =
+            (int32_t)d_render_point(fl.x[li], fy[li], fl.x[hi], fy[hi], fl.x[i]);
+        const int32_t val = (int32_t)y_in[i];
+        const int32_t highroom = range - predicted;
+        const int32_t lowroom = predicted;
+        const int32_t room = (highroom < lowroom ? highroom : lowroom) * 2;
+        if (val > 0) {
+            flag_lo |= (1ull << li) | (1ull << hi);     // li, hi < i <= 64
+            if (i < 64) flag_lo |= 1ull << i; else flag64 = true;
+            int32_t r;
+            if (val >= room) {
+                r = highroom > lowroom ? predicted + val - lowroom : predicted - val + highroom - 1;
+            } else {
+                const int32_t t = (val % 2 == 1) ? (-val - 1) : val;
+                r = predicted + (t >> 1);
+            }
+            fy[i] = (uint32_t)r;
+        } else {
+            fy[i] = (uint32_t)predicted;
+        }
+    }
+    int m = 0;
+    uint32_t hx = 0, hy = 0;
+    for (int j = 0; j < np; j++) {           // audio.rs:528-545, in sorted order
+        const int si = fl.sorted[j];
+        const bool flagged = si < 64 ? ((flag_lo >> si) & 1ull) : flag64;
+        if (j == 0 || flagged) {
+            uint32_t v = fy[si];
+            if (v > (uint32_t)range - 1) v = (uint32_t)range - 1;     // audio.rs:431-433
+            hy = v * fl.mult;
+            hx = fl.x[si];
+            sx[m] = (uint16_t)hx;
+            sy[m] = (uint16_t)hy;
+            m++;
+        }
+    }
+    if (hx < (uint32_t)n2) {                 // audio.rs:546-547 flat tail
+        sx[m] = (uint16_t)n2;
+        sy[m] = (uint16_t)hy;
+        m++;
+    }
+    return m;
+}
+
+// Value of the rendered integer curve at bin k: the closed form of render_line (audio.rs:503-524):
+// y0 + sign(dy) * floor(|dy| * (k - x0) / adx) for the segment [x0, x1) containing k.
+LWB_HD uint32_t d_floor1_y_at(const uint16_t *sx, const uint16_t *sy, int m, int k)
+{
+    int lo = 0, hi = m - 1;                  // sx[lo] <= k < sx[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)sx[mid] <= k) lo = mid; else hi = mid;
+    }
+    const int x0 = sx[lo], x1 = sx[lo + 1];
+    const int y0 = sy[lo], y1 = sy[lo + 1];
+    const int dy = y1 - y0;
+    const int ady = dy < 0 ? -dy : dy;
+    const int off = (ady * (k - x0)) / (x1 - x0);
+    return (uint32_t)(dy < 0 ? y0 - off : y0 + off);
+}
+
+// One flagged segment [sx[seg], sx[seg + 1]) of the curve, rendered the way the reference does
+// (render_line, audio.rs:503-524: integer DDA, one division per segment), clipped to n2 bins
+// (audio.rs:548-550).  Curve values fit a byte: posts are clamped to range - 1 and range * multiplier <= 256.
+LWB_HD void d_floor1_render_segment(const uint16_t *sx, const uint16_t *sy, int seg, int n2, uint8_t *curve)
+{
+    const int x0 = sx[seg], x1 = sx[seg + 1];
+    if (x0 >= n2) return;
+    const int y0 = sy[seg], y1 = sy[seg + 1];
+    const int dy = y1 - y0, adx = x1 - x0;
+    int ady = dy < 0 ? -dy : dy;
+    const int base = dy / adx;
+    const int sgn = dy < 0 ? base - 1 : base + 1;
+    ady -= (base < 0 ? -base : base) * adx;
+    const int end = x1 < n2 ? x1 : n2;
+    int y = y0, err = 0;
+    curve[x0] = (uint8_t)y;
+    for (int x = x0 + 1; x < end; x++) {
+        err += ady;
+        if (err >= adx) { err -= adx; y += sgn; }
+        else y += base;
+        curve[x] = (uint8_t)y;
+    }
+}
+
+}  // namespace lwb

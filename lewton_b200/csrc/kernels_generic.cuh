@@ -19,101 +19,13 @@
 
 #include "kernel_long.cuh"
 #include "lwb_common.h"
+#include "floor1_eval.cuh"
 
 namespace lwb {
 
 __constant__ float c_inverse_db[256] = {
 #include "floor1_inverse_db.inc"
 };
-
-// ---------------------------------------------------------------------------------------------
-// floor-1, audio.rs:354-435 -- run by one thread per (packet, channel); <= 65 posts, serial
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t d_render_point(uint32_t x0, uint32_t y0, uint32_t x1,
-                                                   uint32_t y1, uint32_t x)
-{
-    // audio.rs:354-367, u32/i32 wrapping like a release build
-    const int32_t dy = (int32_t)(y1 - y0);
-    const uint32_t adx = x1 - x0;
-    const uint32_t ady = (uint32_t)(dy < 0 ? -dy : dy);
-    const uint32_t off = (ady * (x - x0)) / adx;
-    return dy < 0 ? y0 - off : y0 + off;
-}
-
-// Writes the flagged posts in x order as (sx, sy = y * multiplier); returns their count
-// (+1 if a flat tail to n2 was appended, audio.rs:546-547).
-__device__ int d_floor1_posts(const DevFloor1 &fl, const uint32_t *__restrict__ y_in, int n2,
-                              uint16_t *sx, uint16_t *sy)
-{
-    uint32_t fy[LWB_MAX_POSTS];
-    uint64_t flag_lo = 3;        // posts 0..63
-    bool flag64 = false;         // post 64
-    const int np = fl.nposts;
-    const int32_t range = fl.mult == 1 ? 256 : fl.mult == 2 ? 128 : fl.mult == 3 ? 86 : 64;
-    fy[0] = y_in[0];
-    fy[1] = y_in[1];
-    for (int i = 2; i < np; i++) {           // audio.rs:401-429
-        const int li = fl.lo[i], hi = fl.hi[i];
-        const int32_t predicted =
-            (int32_t)d_render_point(fl.x[li], fy[li], fl.x[hi], fy[hi], fl.x[i]);
-        const int32_t val = (int32_t)y_in[i];
-        const int32_t highroom = range - predicted;
-        const int32_t lowroom = predicted;
-        const int32_t room = (highroom < lowroom ? highroom : lowroom) * 2;
-        if (val > 0) {
-            flag_lo |= (1ull << li) | (1ull << hi);     // li, hi < i <= 64
-            if (i < 64) flag_lo |= 1ull << i; else flag64 = true;
-            int32_t r;
-            if (val >= room) {
-                r = highroom > lowroom ? predicted + val - lowroom : predicted - val + highroom - 1;
-            } else {
-                const int32_t t = (val % 2 == 1) ? (-val - 1) : val;
-                r = predicted + (t >> 1);
-            }
-            fy[i] = (uint32_t)r;
-        } else {
-            fy[i] = (uint32_t)predicted;
-        }
-    }
-    int m = 0;
-    uint32_t hx = 0, hy = 0;
-    for (int j = 0; j < np; j++) {           // audio.rs:528-545, in sorted order
-        const int si = fl.sorted[j];
-        const bool flagged = si < 64 ? ((flag_lo >> si) & 1ull) : flag64;
-        if (j == 0 || flagged) {
-            uint32_t v = fy[si];
-            if (v > (uint32_t)range - 1) v = (uint32_t)range - 1;     // audio.rs:431-433
-            hy = v * fl.mult;
-            hx = fl.x[si];
-            sx[m] = (uint16_t)hx;
-            sy[m] = (uint16_t)hy;
-            m++;
-        }
-    }
-    if (hx < (uint32_t)n2) {                 // audio.rs:546-547 flat tail
-        sx[m] = (uint16_t)n2;
-        sy[m] = (uint16_t)hy;
-        m++;
-    }
-    return m;
-}
-
-// Value of the rendered integer curve at bin k: the closed form of render_line (audio.rs:503-524):
-// y0 + sign(dy) * floor(|dy| * (k - x0) / adx) for the segment [x0, x1) containing k.
-__device__ __forceinline__ uint32_t d_floor1_y_at(const uint16_t *sx, const uint16_t *sy, int m, int k)
-{
-    int lo = 0, hi = m - 1;                  // sx[lo] <= k < sx[hi]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if ((int)sx[mid] <= k) lo = mid; else hi = mid;
-    }
-    const int x0 = sx[lo], x1 = sx[lo + 1];
-    const int y0 = sy[lo], y1 = sy[lo + 1];
-    const int dy = y1 - y0;
-    const int ady = dy < 0 ? -dy : dy;
-    const int off = (ady * (k - x0)) / (x1 - x0);
-    return (uint32_t)(dy < 0 ? y0 - off : y0 + off);
-}
 
 // audio.rs:762-777
 __device__ __forceinline__ void d_inverse_couple(float &m, float &a)
@@ -130,6 +42,8 @@ __device__ __forceinline__ void d_inverse_couple(float &m, float &a)
 
 constexpr int kPrologueThreads = 256;
 constexpr int kPrologueGroup = 8;            // channels whose floor posts sit in smem at once
+// dynamic shared memory of k_prologue: one curve byte per bin for up to 8 channels of the largest block
+inline size_t prologue_smem(int channels, int blocksize_1) { return (size_t)(channels < kPrologueGroup ? channels : kPrologueGroup) << (blocksize_1 - 1); }
 
 // grid.x = packets.  spec[packet] = [channels][n/2] receives floor x decoupled residue.
 __global__ void __launch_bounds__(kPrologueThreads)
@@ -146,10 +60,51 @@ k_prologue(const DevPacket *__restrict__ pkts, const float *__restrict__ residue
     float *out = spec + p.coeff_off;
     const int nsteps = mp.n_coupling;
 
-    // 1. inverse coupling, steps in reverse (audio.rs:991-1002).  Every thread owns its bins
-    //    through all steps, so the working copy in `out` needs no synchronisation.
-    for (int k = threadIdx.x; k < n2; k += kPrologueThreads) {
-        if (C <= 8) {
+    __shared__ uint16_t s_x[kPrologueGroup][LWB_MAX_POSTS + 1];
+    __shared__ uint16_t s_y[kPrologueGroup][LWB_MAX_POSTS + 1];
+    __shared__ int s_m[kPrologueGroup];
+    const uint8_t *kinds = floor_kind + p.pkt_index * C;
+
+    if (C <= kPrologueGroup) {
+        // Up to 8 channels: the floor curves are rendered once into shared memory (one byte per bin) and a
+        // single pass over the bins does the rest, so every value crosses the memory system once.
+        //   a. posts: one lane per channel, serial over <= 65 posts (audio.rs:391-435);
+        //   b. curve: warp w renders channel w, one flagged segment per lane, with the reference's own
+        //      integer DDA (render_line, audio.rs:503-524) -- no search and no division per bin;
+        //   c. bins: load the residues, inverse-couple them in registers (steps in reverse,
+        //      audio.rs:991-1002), multiply by the floor (audio.rs:1006-1039), store.
+        extern __shared__ uint8_t s_curve_raw[];            // [C][n2] bytes: the host passes min(C, 8) * blocksize_1 / 2
+        uint8_t *s_curve = s_curve_raw;
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0 && w < C && kinds[w] == LWB_FLOOR_ONE) {
+            const DevFloor1 &fl = su.floors[mp.floor_of_channel[w]];
+            s_m[w] = d_floor1_posts(fl, floor1_y + (p.pkt_index * C + w) * LWB_MAX_POSTS, n2, s_x[w], s_y[w]);
+        }
+        __syncwarp();
+        if (w < C && kinds[w] == LWB_FLOOR_ONE)
+            for (int seg = lane; seg + 1 < s_m[w]; seg += 32) d_floor1_render_segment(s_x[w], s_y[w], seg, n2, s_curve + (size_t)w * n2);
+        __syncthreads();
+        if (C == 2 && nsteps <= 1) {
+            // the common stereo shape: at most one coupling step, no register-array juggling
+            const bool swapped = nsteps == 1 && mp.mag[0] == 1;       // (magnitude, angle) = (1, 0)
+            const int k0 = kinds[0], k1 = kinds[1];
+            for (int k = threadIdx.x; k < n2; k += kPrologueThreads) {
+                float r0 = res[k], r1 = res[(size_t)n2 + k];
+                if (nsteps == 1) {
+                    if (swapped) d_inverse_couple(r1, r0);
+                    else d_inverse_couple(r0, r1);
+                }
+                float f0 = 0.f, f1 = 0.f;                              // audio.rs:1021-1024
+                if (k0 == LWB_FLOOR_ONE) f0 = c_inverse_db[s_curve[k]];
+                else if (k0 == LWB_FLOOR_DENSE) f0 = dense_floor[p.coeff_off + k];
+                if (k1 == LWB_FLOOR_ONE) f1 = c_inverse_db[s_curve[(size_t)n2 + k]];
+                else if (k1 == LWB_FLOOR_DENSE) f1 = dense_floor[p.coeff_off + (size_t)n2 + k];
+                out[k] = __fmul_rn(f0, r0);                            // audio.rs:1035-1037
+                out[(size_t)n2 + k] = __fmul_rn(f1, r1);
+            }
+            return;
+        }
+        for (int k = threadIdx.x; k < n2; k += kPrologueThreads) {
             float r[8];
 #pragma unroll
             for (int c = 0; c < 8; c++) r[c] = c < C ? res[(size_t)c * n2 + k] : 0.f;
@@ -163,23 +118,33 @@ k_prologue(const DevPacket *__restrict__ pkts, const float *__restrict__ residue
                 for (int c = 0; c < 8; c++) { if (c == mi) r[c] = mv; if (c == ai) r[c] = av; }
             }
 #pragma unroll
-            for (int c = 0; c < 8; c++) if (c < C) out[(size_t)c * n2 + k] = r[c];
-        } else {
-            for (int c = 0; c < C; c++) out[(size_t)c * n2 + k] = res[(size_t)c * n2 + k];
-            for (int s = nsteps - 1; s >= 0; s--) {
-                float mv = out[(size_t)mp.mag[s] * n2 + k], av = out[(size_t)mp.ang[s] * n2 + k];
-                d_inverse_couple(mv, av);
-                out[(size_t)mp.mag[s] * n2 + k] = mv;
-                out[(size_t)mp.ang[s] * n2 + k] = av;
+            for (int c = 0; c < 8; c++) {
+                if (c < C) {
+                    const int kind = kinds[c];
+                    float f = 0.f;
+                    if (kind == LWB_FLOOR_ONE) f = c_inverse_db[s_curve[(size_t)c * n2 + k]];
+                    else if (kind == LWB_FLOOR_DENSE) f = dense_floor[p.coeff_off + (size_t)c * n2 + k];
+                    out[(size_t)c * n2 + k] = __fmul_rn(f, r[c]);
+                }
             }
+        }
+        return;
+    }
+
+    // more than 8 channels: two passes through `out`
+    // 1. inverse coupling, steps in reverse (audio.rs:991-1002).  Every thread owns its bins
+    //    through all steps, so the working copy in `out` needs no synchronisation.
+    for (int k = threadIdx.x; k < n2; k += kPrologueThreads) {
+        for (int c = 0; c < C; c++) out[(size_t)c * n2 + k] = res[(size_t)c * n2 + k];
+        for (int s = nsteps - 1; s >= 0; s--) {
+            float mv = out[(size_t)mp.mag[s] * n2 + k], av = out[(size_t)mp.ang[s] * n2 + k];
+            d_inverse_couple(mv, av);
+            out[(size_t)mp.mag[s] * n2 + k] = mv;
+            out[(size_t)mp.ang[s] * n2 + k] = av;
         }
     }
 
     // 2. floor curve x residue (audio.rs:1006-1039), kPrologueGroup channels at a time
-    __shared__ uint16_t s_x[kPrologueGroup][LWB_MAX_POSTS + 1];
-    __shared__ uint16_t s_y[kPrologueGroup][LWB_MAX_POSTS + 1];
-    __shared__ int s_m[kPrologueGroup];
-    const uint8_t *kinds = floor_kind + p.pkt_index * C;
     for (int c0 = 0; c0 < C; c0 += kPrologueGroup) {
         __syncthreads();
         const int w = threadIdx.x >> 5;

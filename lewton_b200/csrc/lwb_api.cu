@@ -693,7 +693,7 @@ extern "C" int lwb_debug_packet_taps(lwb_stream *s, const lwb_packet *pkt, float
         CU(ctx, cudaMalloc(&tmp_kinds, C));
         CU(ctx, cudaMemcpyAsync(tmp_dense, ones.data(), C * n2 * 4, cudaMemcpyHostToDevice, st));
         CU(ctx, cudaMemcpyAsync(tmp_kinds, kd.data(), C, cudaMemcpyHostToDevice, st));
-        rc = launch(ctx, k_prologue, dim3(1), dim3(kPrologueThreads), 0, dp, (const float *)ctx->coeffs.p,
+        rc = launch(ctx, k_prologue, dim3(1), dim3(kPrologueThreads), prologue_smem(su->channels, su->bs1), dp, (const float *)ctx->coeffs.p,
                     (const float *)tmp_dense, (const uint8_t *)tmp_kinds, (const uint32_t *)ctx->ys.p,
                     (float *)ctx->spec.p);
         if (!rc) {
@@ -705,7 +705,7 @@ extern "C" int lwb_debug_packet_taps(lwb_stream *s, const lwb_packet *pkt, float
         cudaFree(tmp_kinds);
         if (rc) return rc;
     }
-    if ((rc = launch(ctx, k_prologue, dim3(1), dim3(kPrologueThreads), 0, dp, (const float *)ctx->coeffs.p,
+    if ((rc = launch(ctx, k_prologue, dim3(1), dim3(kPrologueThreads), prologue_smem(su->channels, su->bs1), dp, (const float *)ctx->coeffs.p,
                      (const float *)ctx->dense.p, (const uint8_t *)ctx->kinds.p, (const uint32_t *)ctx->ys.p,
                      (float *)ctx->spec.p)))
         return rc;

@@ -67,6 +67,15 @@ static int plan_chain(lwb_chain *c, PlanChain *pc)
     return LWB_OK;
 }
 
+// dynamic shared memory k_prologue needs for the chains of a batch (curve bytes of the largest block)
+static size_t prologue_smem_of(const std::vector<PlanChain> &plan)
+{
+    size_t m = 0;
+    for (const PlanChain &pc : plan)
+        if (pc.c && pc.c->stream) m = std::max(m, prologue_smem(pc.c->stream->setup->channels, pc.c->stream->setup->bs1));
+    return m;
+}
+
 template <typename K, typename... Args>
 static int launch(lwb_ctx *ctx, K kernel, dim3 grid, dim3 block, size_t smem, Args... args)
 {
@@ -174,7 +183,7 @@ static int run_generic(lwb_ctx *ctx, std::vector<PlanChain> &plan, const lwb_bat
         const float *spec = ar.coeffs;
         if (io->entry == LWB_ENTRY_RESIDUE) {
             if ((rc = ensure(ctx, ctx->spec, spec_hi * sizeof(float)))) return rc;
-            if ((rc = launch(ctx, k_prologue, dim3((unsigned)n_desc), dim3(kPrologueThreads), 0, dp, ar.coeffs,
+            if ((rc = launch(ctx, k_prologue, dim3((unsigned)n_desc), dim3(kPrologueThreads), prologue_smem_of(plan), dp, ar.coeffs,
                              ar.dense, ar.kinds, ar.ys, (float *)ctx->spec.p)))
                 return rc;
             spec = (const float *)ctx->spec.p;

@@ -379,7 +379,7 @@ static int run_prologue_all(lwb_ctx *ctx, std::vector<PlanChain> &plan, const De
         }
     }
     CU(ctx, cudaMemcpyAsync(ctx->desc.p, hp, n_desc * sizeof(DevPacket), cudaMemcpyHostToDevice, ctx->stream));
-    return launch(ctx, k_prologue, dim3((unsigned)n_desc), dim3(kPrologueThreads), 0, (const DevPacket *)ctx->desc.p,
+    return launch(ctx, k_prologue, dim3((unsigned)n_desc), dim3(kPrologueThreads), prologue_smem_of(plan), (const DevPacket *)ctx->desc.p,
                   ar.coeffs, ar.dense, ar.kinds, ar.ys, (float *)ctx->spec.p);
 }
 

@@ -384,7 +384,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 CU(ctx, cudaStreamWaitEvent(sm, ctx->ev_in[k], 0));
             }
             if (residue && ck.np_)
-                if ((rc = launch(ctx, k_prologue, dim3((unsigned)ck.np_), dim3(kPrologueThreads), 0,
+                if ((rc = launch(ctx, k_prologue, dim3((unsigned)ck.np_), dim3(kPrologueThreads), prologue_smem(maxc, kLongBs),
                                  (const DevPacket *)(db + off_pro) + ck.p0, d_coeffs, d_dense, d_kinds, d_ys, const_cast<float *>(d_spec))))
                     return rc;
             if ((rc = mixed_launch_rounds(ctx, ml, ck.rounds))) return rc;
