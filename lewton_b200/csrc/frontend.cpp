@@ -41,20 +41,33 @@ struct BitReader {
     size_t len;
     size_t pos = 0;        // bit position
     BitReader(const uint8_t *d, size_t n) : p(d), len(n) {}
+    size_t bits_left() const { return len * 8 - pos; }
+    // the next min(57, bits_left()) bits at least, first bit in bit 0, zero beyond the end of the data
+    uint64_t peek() const
+    {
+        const size_t byte = pos >> 3;
+        uint64_t w = 0;
+        if (byte + 8 <= len) {
+            std::memcpy(&w, p + byte, 8);                   // little endian hosts (x86-64, aarch64)
+        } else {
+            for (size_t i = byte; i < len; i++) w |= (uint64_t)p[i] << (8 * (i - byte));
+        }
+        return w >> (pos & 7);
+    }
     bool read(unsigned nbits, uint64_t *out)
     {
         if (nbits == 0) { *out = 0; return true; }
         if (pos + nbits > len * 8) return false;
-        uint64_t v = 0;
-        size_t bp = pos;
-        unsigned got = 0;
-        while (got < nbits) {
-            const unsigned off = bp & 7, take = std::min(8 - off, nbits - got);
-            v |= (uint64_t)((p[bp >> 3] >> off) & ((1u << take) - 1)) << got;
-            got += take;
-            bp += take;
+        uint64_t v;
+        if (nbits <= 57) {
+            v = peek() & (~0ull >> (64 - nbits));
+        } else {                                             // up to 64 bits: two pieces
+            v = peek() & ((1ull << 32) - 1);
+            pos += 32;
+            v |= (peek() & (~0ull >> (64 - (nbits - 32)))) << 32;
+            pos -= 32;
         }
-        pos = bp;
+        pos += nbits;
         *out = v;
         return true;
     }
@@ -67,9 +80,9 @@ struct BitReader {
     }
     bool flag(bool *out)
     {
-        uint64_t v;
-        if (!read(1, &v)) return false;
-        *out = v == 1;
+        if (pos >= len * 8) return false;
+        *out = (p[pos >> 3] >> (pos & 7)) & 1;
+        pos++;
         return true;
     }
 };
@@ -99,7 +112,9 @@ static inline float float32_unpack(uint32_t val)
 enum { HUFF_OK = 0, HUFF_OVERSPECIFIED, HUFF_UNDERPOPULATED, HUFF_INVALID_SINGLE };
 
 struct Huffman {
+    static constexpr unsigned kPeek = 10;       // first-level lookup: the next 10 bits -> leaf or inner node
     std::vector<uint32_t> prog;
+    std::vector<uint32_t> fast;                 // [1 << kPeek]: (node position << 5) | bits consumed (leaf if prog[pos] has no children)
     bool single = false;        // one entry of length 1: both bit values decode to it (:131-143)
     uint32_t single_payload = 0;
     bool empty = true;          // no used entry: the reference would index out of bounds on a read
@@ -180,7 +195,19 @@ struct Huffman {
             return HUFF_OK;
         }
         if (!t[0].even) return HUFF_UNDERPOPULATED;
-        if (!empty) flatten(t, 0);
+        if (!empty) {
+            flatten(t, 0);
+            // the walk of read() for every 10-bit prefix, done once (the reference unrolls 8 bits, huffman_tree.rs:182-208)
+            fast.resize(1u << kPeek);
+            for (uint32_t bits = 0; bits < (1u << kPeek); bits++) {
+                uint32_t at = 0, used = 0;
+                while (used < kPeek && (prog[at] & 0x80000000u)) {
+                    at = prog[at + 1 + ((bits >> used) & 1)];
+                    used++;
+                }
+                fast[bits] = (at << 5) | used;
+            }
+        }
         return HUFF_OK;
     }
 
@@ -195,14 +222,24 @@ struct Huffman {
             return true;
         }
         if (empty) return false;
-        uint32_t at = 0;
-        for (;;) {
+        // table step: as many of the next 10 bits as the walk needs.  Bits past the end of the packet read
+        // as zero; a codeword that would need them fails exactly like the bit-by-bit walk (which consumes
+        // what is left and then reports the end of the packet).
+        const size_t left = rdr.bits_left();
+        const uint32_t f = fast[rdr.peek() & ((1u << kPeek) - 1)];
+        uint32_t at = f >> 5;
+        const uint32_t used = f & 31;
+        if (used > left) { rdr.pos += left; return false; }
+        rdr.pos += used;
+        uint32_t e = prog[at];
+        while (e & 0x80000000u) {                            // codewords longer than 10 bits: keep walking
             bool b;
             if (!rdr.flag(&b)) return false;
             at = prog[at + 1 + (b ? 1 : 0)];
-            const uint32_t e = prog[at];
-            if (!(e & 0x80000000u)) { *out = e; return true; }
+            e = prog[at];
         }
+        *out = e;
+        return true;
     }
 };
 
@@ -937,7 +974,8 @@ static int residue_decode_inner(BitReader &rdr, uint32_t cur_blocksize, const st
     if (n_to_read == 0) return 0;
     if (cpc == 0) return 1;
     const size_t stride = parts + cpc;
-    std::vector<uint32_t> cls(ch * stride, 0);
+    thread_local std::vector<uint32_t> cls;                 // scratch reused across packets (no allocation per packet)
+    cls.assign(ch * stride, 0);
     for (int pass = 0; pass < 8; pass++) {
         size_t pc = 0;
         while (pc < parts) {
@@ -984,8 +1022,8 @@ static int residue_decode(BitReader &rdr, uint32_t cur_blocksize, const std::vec
         out.assign(ch * vec, 0.f);
         return 0;
     }
-    std::vector<uint8_t> one(1, 0);
-    std::vector<float> inter;
+    thread_local std::vector<uint8_t> one(1, 0);
+    thread_local std::vector<float> inter;
     // cur_blocksize * ch as u16: the product wraps at 16 bits in the reference
     const uint32_t bs2 = (uint32_t)(uint16_t)(cur_blocksize * ch);
     if (residue_decode_inner(rdr, bs2, one, r, codebooks, inter)) return 1;
@@ -1035,8 +1073,9 @@ static int packet_decode(const Headers &h, const uint8_t *packet, size_t len, lw
     out->next_window_flag = ph.next;
     out->n = ph.n;
     // floor_decode, audio.rs:557-586
-    std::vector<uint8_t> no_residue(C);
-    std::vector<float> cosc;
+    thread_local std::vector<uint8_t> no_residue;
+    thread_local std::vector<float> cosc;
+    no_residue.assign(C, 0);
     for (size_t c = 0; c < C; c++) {
         const Floor &fl = h.floors[mp.submap_floors[mp.mux[c]]];
         int fr;
@@ -1064,8 +1103,8 @@ static int packet_decode(const Headers &h, const uint8_t *packet, size_t len, lw
         if (!(no_residue[m] && no_residue[a])) no_residue[m] = no_residue[a] = 0;
     }
     // audio.rs:957-986
-    std::vector<uint8_t> dnd;
-    std::vector<float> vectors;
+    thread_local std::vector<uint8_t> dnd;
+    thread_local std::vector<float> vectors;
     for (size_t i = 0; i < mp.submap_residues.size(); i++) {
         dnd.clear();
         for (size_t j = 0; j < C; j++)
