@@ -976,7 +976,10 @@ static int residue_decode_inner(BitReader &rdr, uint32_t cur_blocksize, const st
     const size_t stride = parts + cpc;
     thread_local std::vector<uint32_t> cls;                 // scratch reused across packets (no allocation per packet)
     cls.assign(ch * stride, 0);
+    unsigned passes_used = 1;                               // pass 0 reads the classifications
+    for (const ResidueBook &rb : r.books) passes_used |= rb.vals_used;
     for (int pass = 0; pass < 8; pass++) {
+        if (!(passes_used & (1u << pass))) continue;         // no class has a book in this pass: nothing is read
         size_t pc = 0;
         while (pc < parts) {
             if (pass == 0) {
