@@ -834,6 +834,9 @@ static int floor0_decode(BitReader &rdr, const std::vector<Codebook> &codebooks,
     const size_t bi = fl.book_list[booknumber];
     if (bi >= codebooks.size()) return FL_UNDECODABLE;      // the reference indexes out of bounds here (header check is `>`)
     const Codebook &cb = codebooks[bi];
+    // floor0_order < 2: the reference's curve computation underflows `(order - 3) / 2` / `(order - 2) / 2` and
+    // panics on the slice index (audio.rs:178-186); a hostile header must not get further than this
+    if (fl.order < 2) return FL_UNDECODABLE;
     coeff->clear();
     float last = 0.f;
     for (;;) {
