@@ -860,7 +860,8 @@ static int floor0_decode(BitReader &rdr, const std::vector<Codebook> &codebooks,
 static void floor0_curve(const std::vector<float> &cosc, uint64_t amplitude, const Floor0 &fl, bool blockflag, uint32_t n, float *out)
 {
     const std::vector<float> &bark_cos = fl.bark_cos_omega[blockflag ? 1 : 0];
-    const float common = (float)amplitude * (float)fl.amplitude_offset / (float)(((uint64_t)1 << fl.amplitude_bits) - 1);
+    const uint64_t max_amp = fl.amplitude_bits >= 64 ? ~0ull : (((uint64_t)1 << fl.amplitude_bits) - 1);   // 64 bits are legal (header.rs:780-787)
+    const float common = (float)amplitude * (float)fl.amplitude_offset / (float)max_amp;
     size_t i = 0;
     size_t w = 0;
     while (i < n) {
