@@ -380,3 +380,20 @@ def test_ogg_paging_round_trip_and_errors():
         fe.OggPacketReader(b"NotAnOggFileAtAllButLongEnoughToHoldAHeader").read_packet()
     hs, serial = fe.read_headers(fe.OggPacketReader(data))
     assert serial == 7 and hs.audio_channels == spec.channels
+
+
+@pytest.mark.parametrize("seed,bs0,bs1,channels,floor0", [(60, 6, 8, 2, True), (61, 9, 13, 1, False), (62, 7, 7, 3, True),
+                                                           (63, 6, 13, 2, False)])
+def test_packet_decode_other_blocksizes(seed, bs0, bs1, channels, floor0):
+    """Blocksizes other than 256/2048 (bark maps, residue limits and floor ranges all scale with them)."""
+    rng = np.random.default_rng(seed)
+    spec = vp.StreamSpec(rng, channels=channels, bs0=bs0, bs1=bs1, floor0=floor0)
+    hdr = fe.Headers(spec.ident_packet(), spec.comment_packet(), spec.setup_packet())
+    assert (hdr.blocksize_0, hdr.blocksize_1) == (bs0, bs1)
+    for k in range(8):
+        mode = int(rng.integers(0, len(spec.modes)))
+        pkt, info = spec.audio_packet(mode, int(rng.integers(0, 2)), int(rng.integers(0, 2)), p_unused=0.2)
+        check_packet(spec, hdr, pkt, info)
+        assert hdr.decoded_sample_count(pkt) == _sample_count(spec, info)
+        if len(pkt) > 4:
+            check_packet(spec, hdr, pkt, info, int(rng.integers(2, len(pkt))))
