@@ -234,7 +234,19 @@ def main():
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - l0
+    # The timed region lasts a few milliseconds, far below nvidia-smi's sampling period: keep the same
+    # step running (untimed) for ~0.5 s so that the clock / throttle samples are taken under this load.
+    try:
+        t_probe = time.perf_counter()
+        while time.perf_counter() - t_probe < 0.5:
+            for _ in range(64):
+                step()
+            ctx.synchronize()
+    except Exception:          # the probe must never cost the measurement
+        pass
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["sampled"] = "during the timed steps and ~0.5 s of the same step repeated right after them"
     t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
