@@ -10,6 +10,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 // the CUDA back half is not linked: the fuzz target is the host parser
 extern "C" {
@@ -100,6 +101,35 @@ int main(int argc, char **argv)
         }
     };
 
+    if (argc > 3 && std::string(argv[3]) == "batch") {
+        // the thread pool of lwf_batcher_decode (for ThreadSanitizer): many jobs over mutated packets; the stub
+        // synthesis call fails with LWB_ERR_NO_DEVICE after the parallel entropy decode has run
+        lwf_batcher *bt = nullptr;
+        if (lwf_batcher_create(reinterpret_cast<lwb_ctx *>(0x10), good, 8, &bt)) return 4;
+        std::vector<float> pcm(1);
+        for (long it = 0; it < iters; it++) {
+            const size_t n_jobs = 64;
+            std::vector<std::vector<Bytes>> store(n_jobs);
+            std::vector<std::vector<const uint8_t *>> ptrs(n_jobs);
+            std::vector<std::vector<size_t>> lens(n_jobs);
+            std::vector<lwf_stream_job> jobs(n_jobs);
+            for (size_t j = 0; j < n_jobs; j++) {
+                for (const Bytes &pk : packets) store[j].push_back((rnd() & 3) ? pk : mutate(pk));
+                for (const Bytes &b : store[j]) { ptrs[j].push_back(b.data()); lens[j].push_back(b.size()); }
+                std::memset(&jobs[j], 0, sizeof(jobs[j]));
+                jobs[j].stream = reinterpret_cast<lwb_stream *>(0x20);
+                jobs[j].n_packets = (uint32_t)store[j].size();
+                jobs[j].packets = ptrs[j].data();
+                jobs[j].lengths = lens[j].data();
+            }
+            const int rc = lwf_batcher_decode(bt, jobs.data(), n_jobs, LWB_OUT_F32_PLANAR, pcm.data());
+            if (rc != LWB_ERR_NO_DEVICE) { std::printf("unexpected rc %d\n", rc); return 5; }
+        }
+        lwf_batcher_destroy(bt);
+        lwf_headers_destroy(good);
+        std::printf("batch iterations %ld ok\n", iters);
+        return 0;
+    }
     for (long it = 0; it < iters; it++) {
         const int what = (int)(rnd() % 4);
         if (what == 0) {                          // hostile setup header, then packets through it

@@ -33,3 +33,6 @@ def test_frontend_survives_mutated_streams(tmp_path):
         assert r.returncode == 0, (seed, r.stdout[-2000:], r.stderr[-4000:])
         fields = dict(zip(r.stdout.split()[::2], r.stdout.split()[1::2]))
         assert int(fields["parsed_ok"]) > 50 and int(fields["decoded_ok"]) > 200 and int(fields["ogg_packets"]) > 200, r.stdout
+        # the batcher's thread pool over mutated packets (the stubbed synthesis call then reports "no device")
+        r = subprocess.run([str(exe), str(corpus), "6", "batch"], capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0 and "ok" in r.stdout, (seed, r.stdout[-500:], r.stderr[-3000:])
