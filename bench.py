@@ -164,6 +164,11 @@ def main():
     ap.add_argument("--packets", type=int, default=16, help="consecutive long packets per stream per step")
     ap.add_argument("--e2e-streams", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="leave the rank's CPU affinity / memory policy alone")
+    ap.add_argument("--strong-streams", type=int, default=4096,
+                    help="BASELINE.json configs[3]: this many stereo streams in TOTAL, sharded over the ranks (0 = skip)")
+    ap.add_argument("--strong-packets", type=int, default=64)
+    ap.add_argument("--sustained-sec", type=float, default=1.0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -177,9 +182,17 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line.  NCCL prints its banner / INFO lines to stdout: instead of silencing
+    # NCCL_DEBUG (which hid the communicator's rank count from whoever launched us), file descriptor 1 is pointed
+    # at stderr for the whole run and the JSON line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    # Host side of e2e: bind this rank to the CPUs / memory of the NUMA node its GPU hangs off BEFORE any pinned
+    # allocation (first touch then lands on the local node); the original mask is restored for the CPU arm.
+    affinity0 = os.sched_getaffinity(0)
+    numa = cabi.lib().lwb_bind_host_to_device(local) if not args.no_numa_bind else -1
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) off it
-        os.environ["NCCL_DEBUG"] = os.environ.get("LWB_NCCL_DEBUG", "WARN")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -234,27 +247,75 @@ def main():
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = ctx.launch_count - l0
-    # The timed region lasts a few milliseconds, far below nvidia-smi's sampling period: keep the same
-    # step running (untimed) for ~0.5 s so that the clock / throttle samples are taken under this load.
-    try:
-        t_probe = time.perf_counter()
-        while time.perf_counter() - t_probe < 0.5:
-            for _ in range(64):
-                step()
-            ctx.synchronize()
-    except Exception:          # the probe must never cost the measurement
-        pass
+    # The timed region lasts a few milliseconds (a burst, far below nvidia-smi's sampling period).  The same step is
+    # then repeated back to back for >= --sustained-sec, timed the same way: that is the sustained value (power
+    # capped clocks), and the window the clock / throttle samples are taken in.
+    n_sus = max(args.steps, int(args.sustained_sec * 1e3 / max(ms_total / args.steps, 1e-3)) + 1)
+    barrier()
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es0.record(stream)
+    for i in range(n_sus):
+        step()
+        if (i & 255) == 255:
+            ctx.synchronize()      # bound the queue depth
+    es1.record(stream)
+    barrier()
+    sus_ms = es0.elapsed_time(es1)
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
-        clocks["sampled"] = "during the timed steps and ~0.5 s of the same step repeated right after them"
-    t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        clocks["sampled"] = f"during the timed steps and the {n_sus} back-to-back steps of the sustained measurement"
+    t = torch.tensor([ms_total, sus_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total, sus_ms = float(t[0].item()), float(t[1].item())
     ms_step = ms_total / args.steps
     # after warm-up every stream has history: every packet emits 1024 samples per channel
     samples_step = S * P * C * N2 * world
     value = samples_step / (ms_step * 1e-3)
+
+    sustained = {"value": samples_step / (sus_ms / n_sus * 1e-3) / 1e6, "unit": "Msamples/s", "steps": n_sus,
+                 "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus}
+    batch.close()
+    for p_ in pwrs:
+        p_.close()
+    del spec, pcm
+
+    # ---- BASELINE.json configs[3] as written: 4096 streams in TOTAL sharded over the ranks (strong scaling) ------
+    strong = None
+    if args.strong_streams:
+        slo, shi = stream_range(args.strong_streams, world, rank)
+        Ss, Ps = shi - slo, args.strong_packets
+        s_stride = Ps * N2
+        s_spec = torch.randn((Ss, Ps, C, N2), generator=gen, device="cuda", dtype=torch.float32) * 1e-2
+        s_pcm = torch.empty((Ss, C, s_stride), device="cuda", dtype=torch.float32)
+        s_pwrs = [L.PreviousWindowRight(su) for _ in range(Ss)]
+        s_modes = np.ones(Ps, np.uint8)
+        s_chains = [L.ChainSpec(s_pwrs[s], s_modes, coeff_offset=s * Ps * C * N2, out_offset=s * C * s_stride,
+                                out_stride=s_stride) for s in range(Ss)]
+        s_batch = L.Batch(ctx, s_chains, cabi.ENTRY_SPECTRUM, cabi.MEM_DEVICE, s_spec.data_ptr(), s_pcm.data_ptr(),
+                          cabi.OUT_F32_PLANAR)
+        for _ in range(max(args.warmup, 3)):
+            s_batch.run()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(args.steps):
+            s_batch.run()
+        s1.record(stream)
+        barrier()
+        ts = torch.tensor([s0.elapsed_time(s1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        s_ms = float(ts.item()) / args.steps
+        strong = {"value": args.strong_streams * Ps * C * N2 / (s_ms * 1e-3) / 1e6, "unit": "Msamples/s",
+                  "scaling": "strong", "streams_total": args.strong_streams, "streams_this_rank": Ss,
+                  "packets_per_stream": Ps, "ms_per_step": s_ms,
+                  "bytes_in_plus_out_per_gpu": Ss * Ps * C * N2 * 8,
+                  "workload": "BASELINE.json configs[3]: batch of 4096 independent stereo streams sharded across the ranks"}
+        s_batch.close()
+        for p_ in s_pwrs:
+            p_.close()
+        del s_spec, s_pcm
 
     # ---- e2e: host (pinned) buffers through the same call --------------------------------------
     Se = min(args.e2e_streams, S)
@@ -308,8 +369,13 @@ def main():
                 "e2e": {"value": e2e_value / 1e6, "unit": "Msamples/s",
                         "h2d_bytes_per_step": Se * P * C * N2 * 4, "d2h_bytes_per_step": Se * C * stride * 4,
                         "streams": Se, "steps": e_steps, "timer": "host wall clock around synchronous calls"},
-                "gpu_launches": int(launches), "host_enqueue_us_per_step": host_us, "clocks": clocks}
+                "sustained": sustained, "strong_scaling": strong,
+                "gpu_launches": int(launches), "host_enqueue_us_per_step": host_us, "clocks": clocks,
+                "host_binding": {"numa_node": int(numa), "cpus": len(os.sched_getaffinity(0)),
+                                 "how": "lwb_bind_host_to_device: CPU affinity + preferred memory node of the GPU's PCIe root"}}
         if not args.no_cpu_baseline:
+            os.sched_setaffinity(0, affinity0)        # the CPU arm gets every core the container has
+            cabi.lib().lwb_bind_host_to_device(-1)    # ... and the default memory policy
             threads = host_threads()
             v1, _, _ = cpu_reference(8, 17, 1, target_sec=0.5)
             v, sec, reps = cpu_reference(8 * threads, 17, threads, target_sec=2.0)
@@ -318,7 +384,7 @@ def main():
                                     "sample": f"{8 * threads} stereo streams x 17 long packets swept {reps}x = "
                                               f"{sec:.2f} s wall on {threads} threads ({sec * threads:.0f} core-s); "
                                               "lewton-equivalent C restatement (oracle/), the crate itself is Rust"}
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define LWB_ABI_VERSION 1
+#define LWB_ABI_VERSION 2          /* 2: lwb_batch_io::floor_memory, lwb_bind_host_to_device */
 #define LWB_MAX_POSTS 65          /* header.rs:873 floor1_values <= 65 */
 #define LWB_MAX_CHANNELS 255      /* audio_channels is a u8, header.rs:190 */
 #define LWB_MAX_COUPLING 256      /* header.rs:998-1001 coupling steps = read_u8 + 1 */
@@ -73,6 +73,12 @@ uint64_t lwb_ctx_launch_count(const lwb_ctx *ctx);
 /* pinned host memory for the host-buffer entry points (optional; plain malloc'd memory works, slower) */
 void *lwb_host_alloc(size_t bytes);
 void lwb_host_free(void *p);
+/* Multi-GPU hosts: bind the calling thread (and the threads it creates) to the CPUs of the NUMA node GPU
+ * `device_ordinal` is attached to and prefer that node's memory, so that pinned buffers allocated afterwards
+ * (lwb_host_alloc, staging) are local to the GPU's PCIe root.  Call once per rank / per feeding thread before
+ * allocating.  Returns the node, or -1 if unknown (nothing changed).  device_ordinal < 0 restores the default
+ * memory policy (the CPU affinity is the caller's to restore).  No reference counterpart: lewton is CPU-only. */
+int lwb_bind_host_to_device(int device_ordinal);
 /* device memory helpers for the *_DEVICE memory space (harnesses without their own allocator) */
 int lwb_device_alloc(lwb_ctx *ctx, size_t bytes, void **out);
 void lwb_device_free(lwb_ctx *ctx, void *p);
@@ -212,10 +218,16 @@ typedef struct lwb_batch_io {
     int memory;                       /* LWB_MEM_*: where coeffs/dense_floor/pcm live              */
     const float *coeffs;              /* spectrum or residue arena                                 */
     const float *dense_floor;         /* same layout as coeffs, or NULL (LWB_ENTRY_RESIDUE)        */
-    const uint8_t *floor_kind;        /* [total_packets][channels]   (LWB_ENTRY_RESIDUE), HOST mem */
-    const uint32_t *floor1_y;         /* [total_packets][channels][LWB_MAX_POSTS], HOST memory     */
+    const uint8_t *floor_kind;        /* [total_packets][channels]   (LWB_ENTRY_RESIDUE), see floor_memory */
+    const uint32_t *floor1_y;         /* [total_packets][channels][LWB_MAX_POSTS], see floor_memory */
     int out_format;                   /* LWB_OUT_*                                                 */
     void *pcm;                        /* output arena                                              */
+    int floor_memory;                 /* LWB_MEM_*: where floor_kind / floor1_y live (0 = host).   *
+                                       * Device arrays are read in place (nothing is uploaded, and   *
+                                       * nothing about them can be validated on the host: a kind    *
+                                       * outside LWB_FLOOR_* acts as LWB_FLOOR_UNUSED); a decode     *
+                                       * server whose entropy stage fills device-visible buffers     *
+                                       * submits residue-entry batches without any per-step copy.   */
 } lwb_batch_io;
 
 /* All chains must use setups with the same channel count per chain's own stream; chains may

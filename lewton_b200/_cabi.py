@@ -64,7 +64,8 @@ class Chain(C.Structure):
 
 class BatchIo(C.Structure):
     _fields_ = [("entry", C.c_int), ("memory", C.c_int), ("coeffs", vp), ("dense_floor", vp),
-                ("floor_kind", vp), ("floor1_y", vp), ("out_format", C.c_int), ("pcm", vp)]
+                ("floor_kind", vp), ("floor1_y", vp), ("out_format", C.c_int), ("pcm", vp),
+                ("floor_memory", C.c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/lewton_b200.h declares
@@ -78,6 +79,7 @@ SYMBOLS = {
     "lwb_ctx_cuda_stream": (vp, [vp]),
     "lwb_ctx_launch_count": (C.c_uint64, [vp]),
     "lwb_host_alloc": (vp, [C.c_size_t]),
+    "lwb_bind_host_to_device": (C.c_int, [C.c_int]),
     "lwb_host_free": (None, [vp]),
     "lwb_device_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
     "lwb_device_free": (None, [vp, vp]),

@@ -407,7 +407,7 @@ class Batch:
     would otherwise exceed the kernel time)."""
 
     def __init__(self, ctx, chains, entry, memory, coeffs, pcm, out_format, floor_kind=None, floor1_y=None,
-                 dense_floor=None):
+                 dense_floor=None, floor_memory=cabi.MEM_HOST):
         self.ctx, self.chains = ctx, list(chains)
         self._keep = (coeffs, pcm, floor_kind, floor1_y, dense_floor)
         self._arr = arr = (cabi.Chain * len(self.chains))()
@@ -433,6 +433,7 @@ class Batch:
         io.entry, io.memory, io.out_format = entry, memory, out_format
         io.coeffs, io.pcm, io.dense_floor = addr(coeffs), addr(pcm), addr(dense_floor)
         io.floor_kind, io.floor1_y = addr(floor_kind), addr(floor1_y)
+        io.floor_memory = floor_memory
         self._n = len(self.chains)
         self._plan = C.c_void_p()
         ctx.check(cabi.lib().lwb_plan_create(ctx._h, self._arr, self._n, C.byref(self._io), C.byref(self._plan)))
@@ -464,10 +465,11 @@ class Batch:
 
 
 def decode_chains(ctx, chains, entry, memory, coeffs, pcm, out_format, floor_kind=None, floor1_y=None,
-                  dense_floor=None):
+                  dense_floor=None, floor_memory=cabi.MEM_HOST):
     """lwb_decode_chains.  coeffs/pcm/dense_floor: numpy arrays (MEM_HOST) or integer device
-    pointers (MEM_DEVICE); floor_kind/floor1_y: numpy arrays (always host)."""
-    b = Batch(ctx, chains, entry, memory, coeffs, pcm, out_format, floor_kind, floor1_y, dense_floor)
+    pointers (MEM_DEVICE); floor_kind/floor1_y: numpy arrays (floor_memory MEM_HOST) or integer
+    device pointers (MEM_DEVICE)."""
+    b = Batch(ctx, chains, entry, memory, coeffs, pcm, out_format, floor_kind, floor1_y, dense_floor, floor_memory)
     try:
         b.run()
         return b.collect()

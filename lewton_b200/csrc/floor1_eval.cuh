@@ -119,4 +119,49 @@ LWB_HD void d_floor1_render_segment(const uint16_t *sx, const uint16_t *sy, int 
     }
 }
 
+// ---- chunked closed-form render (k_floor1_curves) -------------------------------------------
+// floor(N / adx) for N = |dy| * (k - x0) < 2^20 by one multiply-high: M = floor((2^32 - 1) / adx) + 1 is exact
+// whenever N * adx < 2^32 (M * adx = 2^32 + e with e < adx, and the error term N * e / (adx * 2^32) stays below
+// 1 / adx), i.e. for every adx <= 4096.  0 = "divide" (adx == 1, or a segment longer than 4096 bins).
+LWB_HD uint32_t d_floor1_magic(int adx) { return (adx < 2 || adx > 4096) ? 0u : 0xFFFFFFFFu / (uint32_t)adx + 1u; }
+
+LWB_HD uint32_t d_mulhi_u32(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+// 16 consecutive bins [k0, k0 + 16) of the rendered curve (k0 + 16 <= n2 <= last sx), one byte each, as four
+// little-endian words: the closed form of render_line (audio.rs:503-524) per bin, segment found once per chunk
+// and advanced when a bin reaches the next flagged post.  sm[j] = d_floor1_magic(sx[j + 1] - sx[j]).
+LWB_HD void d_floor1_render16(const uint16_t *sx, const uint16_t *sy, const uint32_t *sm, int m, int k0, uint32_t out[4])
+{
+    int lo = 0, hi = m - 1;                  // sx[lo] <= k0 < sx[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)sx[mid] <= k0) lo = mid; else hi = mid;
+    }
+    int x0 = sx[lo], x1 = sx[lo + 1], y0 = sy[lo];
+    int dy = (int)sy[lo + 1] - y0;
+    uint32_t mg = sm[lo];
+    out[0] = out[1] = out[2] = out[3] = 0u;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int k = k0 + i;
+        if (k >= x1) {                       // posts are strictly increasing in x: one step is enough
+            lo++;
+            x0 = x1; x1 = sx[lo + 1]; y0 = sy[lo];
+            dy = (int)sy[lo + 1] - y0;
+            mg = sm[lo];
+        }
+        const uint32_t nn = (uint32_t)(dy < 0 ? -dy : dy) * (uint32_t)(k - x0);
+        const int off = (int)(mg ? d_mulhi_u32(nn, mg) : nn / (uint32_t)(x1 - x0));
+        const int y = dy < 0 ? y0 - off : y0 + off;
+        out[i >> 2] |= ((uint32_t)y & 255u) << (8 * (i & 3));
+    }
+}
+
 }  // namespace lwb

@@ -31,11 +31,12 @@ struct lwb_ctx {
     cudaEvent_t ev_desc[2] = {}, ev_kdone[2] = {};
     int runs_par = 0;
     uint32_t ticket_next = 0;
+    uint64_t epoch = 0;            // batch counter: lwb_stream::busy_epoch == epoch <=> the stream already sits in this batch
     uint64_t state_gen = 1;        // bumped whenever any stream's (has, len) changes: plans key on it
     std::string err;
     uint64_t launches = 0;
     // grow-only device arenas
-    DevBuf coeffs, dense, pcm, spec, x, desc, kinds, ys, chains, ticket, cdesc, cbytes;
+    DevBuf coeffs, dense, pcm, spec, curve, x, desc, kinds, ys, chains, ticket, cdesc, cbytes;
     Staging stage[3];              // ring: a batch's descriptors are written while the previous copies may still run
     int stage_next = 0;
     // pinned staging for descriptors (four-kernel path)
@@ -74,11 +75,24 @@ struct lwb_plan {
     uint32_t n_groups = 0;
     const float *pack = nullptr;
     bool i16 = false;
+    // residue entry: the front-stage descriptors (one DevPacket per packet).  They depend only on the captured
+    // chain / mode arrays, never on stream state, so they stay valid for the plan's lifetime.
+    bool pro_captured = false, pro_fast = false;
+    DevBuf pro;
+    size_t n_pro = 0, pro_smem_old = 0;
+    unsigned pro_C = 0;
+    uint64_t pro_c_lo = 0, pro_c_hi = 0, pro_r_lo = 0, pro_r_hi = 0;
     // captured mixed-path launch sequence (valid while ctx->state_gen == gen)
     bool mixed_captured = false;
     DevBuf mix;
     MixLaunch mix_launch;
     std::vector<MixRound> mix_rounds;
+    // ... residue entry: its front-stage descriptors sit in `mix` too
+    bool mix_pro = false, mix_pro_fast = false, mix_pro_dense = false;
+    const DevPacket *mix_pro_pk = nullptr;
+    size_t mix_pro_n = 0, mix_pro_smem_old = 0;
+    unsigned mix_pro_C = 0;
+    uint64_t mix_pro_c_lo = 0, mix_pro_r_lo = 0, mix_pro_r_hi = 0;
 };
 
 struct lwb_stream {
@@ -129,6 +143,7 @@ static int ensure(lwb_ctx *ctx, DevBuf &b, size_t bytes)
     size_t want = bytes + bytes / 8 + 4096;
     CU(ctx, cudaMalloc(&b.p, want));
     b.cap = want;
+    ctx->state_gen++;              // captured plans may hold pointers into the arena that just moved
     return LWB_OK;
 }
 

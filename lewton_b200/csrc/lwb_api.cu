@@ -5,8 +5,12 @@
 // (it never depends on sample values), so the kernels receive fully resolved descriptors and the
 // device never has to be synchronised to learn a length.
 #include <cuda_runtime.h>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -17,6 +21,7 @@
 #include "kernel_long.cuh"
 #include "kernels_generic.cuh"
 #include "kernel_chain.cuh"
+#include "kernel_prologue.cuh"
 #include "lwb_common.h"
 
 namespace lwb {
@@ -77,7 +82,7 @@ extern "C" void lwb_ctx_destroy(lwb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->coeffs, &ctx->dense, &ctx->pcm, &ctx->spec, &ctx->x, &ctx->desc,
+    for (DevBuf *b : {&ctx->coeffs, &ctx->dense, &ctx->pcm, &ctx->spec, &ctx->curve, &ctx->x, &ctx->desc,
                       &ctx->kinds, &ctx->ys, &ctx->chains, &ctx->ticket, &ctx->runs_buf[0], &ctx->runs_buf[1],
                       &ctx->cdesc, &ctx->cbytes})
         if (b->p) cudaFree(b->p);
@@ -120,6 +125,58 @@ extern "C" void *lwb_host_alloc(size_t bytes)
     return p;
 }
 extern "C" void lwb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// NUMA placement of the host side.  A rank that feeds GPU d through host buffers should run on, and
+// allocate its pinned memory from, the socket GPU d's PCIe root hangs off: with 4 GPUs per socket the
+// copies of all of them otherwise cross the inter-socket link of whichever node the pages landed on.
+// Plain syscalls (no libnuma in this image).  Returns the node, or -1 when it cannot be determined.
+extern "C" int lwb_bind_host_to_device(int device)
+{
+    if (device < 0) {
+        syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+        return -1;
+    }
+    char busid[64] = {0};
+    if (cudaDeviceGetPCIBusId(busid, (int)sizeof(busid) - 1, device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char *c = busid; *c; c++) *c = (char)tolower((unsigned char)*c);
+    char path[160];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", busid);
+    int node = -1;
+    if (FILE *f = fopen(path, "r")) {
+        if (fscanf(f, "%d", &node) != 1) node = -1;
+        fclose(f);
+    }
+    if (node < 0 || node >= 1024) return -1;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    cpu_set_t want, cur;
+    CPU_ZERO(&want);
+    if (FILE *f = fopen(path, "r")) {
+        int a, b;
+        while (fscanf(f, "%d", &a) == 1) {
+            b = a;
+            int ch = fgetc(f);
+            if (ch == '-') {
+                if (fscanf(f, "%d", &b) != 1) break;
+                ch = fgetc(f);
+            }
+            for (int k = a; k <= b && k < CPU_SETSIZE; k++) CPU_SET(k, &want);
+            if (ch != ',') break;
+        }
+        fclose(f);
+    }
+    if (sched_getaffinity(0, sizeof(cur), &cur) == 0) {
+        cpu_set_t both;
+        CPU_AND(&both, &want, &cur);
+        if (CPU_COUNT(&both) > 0) sched_setaffinity(0, sizeof(both), &both);
+    }
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, (unsigned long)(sizeof(mask) * 8));
+    return node;
+}
 
 extern "C" int lwb_device_alloc(lwb_ctx *ctx, size_t bytes, void **out)
 {
@@ -399,18 +456,20 @@ static int decode_chains_impl(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, 
     if (n_chains == 0) return LWB_OK;
     if (!io->coeffs || !io->pcm) return fail(ctx, LWB_ERR_INVALID, "null arena");
     CU(ctx, cudaSetDevice(ctx->device));
-    static uint64_t epoch = 0;
-    epoch++;
+    const uint64_t epoch = ++ctx->epoch;      // per context: concurrent calls on different contexts share nothing
     {
         bool handled = false;
         const char *fg = getenv("LWB_FORCE_GENERIC");
         const bool no_fused = fg && std::strcmp(fg, "2") == 0;
         int rc0 = no_fused ? LWB_OK : try_long(ctx, chains, n_chains, io, epoch, &handled, nullptr, 0, prepared);
         if (rc0 || handled) return rc0;
-        // residue-entry batches of uniform long blocks go prologue + fused kernel (below); everything
-        // else that fits goes to the chain kernel
-        const bool residue_long = !no_fused && !fg && io->entry == LWB_ENTRY_RESIDUE && batch_is_uniform_long(ctx, chains, n_chains, io);
-        if (!residue_long) {
+        // residue-entry batches of uniform long blocks go front stages + fused kernel; everything else that fits
+        // goes to the segmented path or the chain kernel
+        if (!no_fused && !fg) {
+            rc0 = try_long_residue(ctx, chains, n_chains, io, epoch, &handled, prepared);
+            if (rc0 || handled) return rc0;
+        }
+        {
             if (!no_fused) {
                 rc0 = try_mixed(ctx, chains, n_chains, io, epoch, &handled, prepared);
                 if (rc0 || handled) return rc0;
@@ -450,12 +509,8 @@ static int decode_chains_impl(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, 
         if (residue) {
             r_lo = std::min(r_lo, c->packet_index);
             r_hi = std::max<uint64_t>(r_hi, c->packet_index + pc.pk.size());
-            for (uint64_t r = c->packet_index * C; r < (c->packet_index + pc.pk.size()) * C; r++) {
-                const uint8_t kd = io->floor_kind[r];
-                if (kd > LWB_FLOOR_DENSE) return fail(ctx, LWB_ERR_INVALID, "floor_kind out of range");
-                if (kd == LWB_FLOOR_ONE && !io->floor1_y) return fail(ctx, LWB_ERR_INVALID, "floor1_y missing");
-                if (kd == LWB_FLOOR_DENSE) need_dense = true;
-            }
+            int krc = scan_floor_kinds(ctx, io, c->packet_index * C, (c->packet_index + pc.pk.size()) * C, &need_dense);
+            if (krc) return krc;
         }
     }
     if (need_dense && !io->dense_floor) return fail(ctx, LWB_ERR_INVALID, "dense_floor missing");
@@ -486,17 +541,9 @@ static int decode_chains_impl(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, 
             ar.pcm = io->pcm;
         }
         if (residue) {
-            const size_t rows = (size_t)(r_hi - r_lo) * uniform_c;
-            if ((rc = ensure(ctx, ctx->kinds, rows))) return rc;
-            CU(ctx, cudaMemcpyAsync(ctx->kinds.p, io->floor_kind + r_lo * uniform_c, rows, cudaMemcpyHostToDevice, ctx->stream));
-            ar.kinds = (const uint8_t *)ctx->kinds.p;
-            if (io->floor1_y) {
-                if ((rc = ensure(ctx, ctx->ys, rows * LWB_MAX_POSTS * sizeof(uint32_t)))) return rc;
-                CU(ctx, cudaMemcpyAsync(ctx->ys.p, io->floor1_y + r_lo * uniform_c * LWB_MAX_POSTS,
-                                        rows * LWB_MAX_POSTS * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-                ar.ys = (const uint32_t *)ctx->ys.p;
-            }
-            ar.kinds_row0 = r_lo;
+            // absolute packet rows address the (biased) device views: kinds_row0 stays 0
+            if ((rc = stage_floor_arrays(ctx, io, r_lo, r_hi, (unsigned)uniform_c, ctx->stream, &ar.kinds, &ar.ys))) return rc;
+            ar.kinds_row0 = 0;
         }
         if (residue && plan_is_long(plan, io)) {
             // residue entry, uniform long blocks: k_prologue forms the spectrum on the device, the fused
@@ -548,13 +595,29 @@ extern "C" int lwb_plan_create(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains,
 extern "C" void lwb_plan_destroy(lwb_plan *p)
 {
     if (!p) return;
-    if (p->runs.p || p->mix.p) {
+    if (p->runs.p || p->mix.p || p->pro.p) {
         cudaSetDevice(p->ctx->device);
         cudaStreamSynchronize(p->ctx->stream);
         if (p->runs.p) cudaFree(p->runs.p);
         if (p->mix.p) cudaFree(p->mix.p);
+        if (p->pro.p) cudaFree(p->pro.p);
     }
     delete p;
+}
+
+// Replays the captured front stages of a residue-entry plan (device-memory batches only: host-memory batches are
+// never captured as a whole).  Host floor arrays change from step to step and are uploaded again; device floor
+// arrays are read in place.
+static int replay_front_stages(lwb_plan *p)
+{
+    lwb_ctx *ctx = p->ctx;
+    const lwb_batch_io *io = &p->io;
+    const uint8_t *d_kinds;
+    const uint32_t *d_ys;
+    int rc = stage_floor_arrays(ctx, io, p->pro_r_lo, p->pro_r_hi, p->pro_C, ctx->stream, &d_kinds, &d_ys);
+    if (rc) return rc;
+    return launch_prologue(ctx, (const DevPacket *)p->pro.p, p->n_pro, p->pro_C, p->pro_fast, p->pro_smem_old, io->coeffs,
+                           io->dense_floor, d_kinds, d_ys, (float *)ctx->spec.p - p->pro_c_lo, (uint8_t *)ctx->curve.p - p->pro_c_lo);
 }
 
 extern "C" int lwb_plan_execute(lwb_plan *p)
@@ -566,6 +629,10 @@ extern "C" int lwb_plan_execute(lwb_plan *p)
         // descriptors were built -- the per-chain results in the caller's array are still right,
         // the stream states stay (has, 1024): just launch.
         CU(ctx, cudaSetDevice(ctx->device));
+        if (p->pro_captured) {             // residue entry: the front stages write ctx->spec, which the captured runs read
+            int prc = replay_front_stages(p);
+            if (prc) return prc;
+        }
         constexpr uint32_t kTicketPool = 1024;
         if (ctx->ticket_next % kTicketPool == 0)
             CU(ctx, cudaMemsetAsync(ctx->ticket.p, 0, kTicketPool * sizeof(unsigned int), ctx->stream));
@@ -577,6 +644,17 @@ extern "C" int lwb_plan_execute(lwb_plan *p)
     }
     if (p->mixed_captured && p->gen == ctx->state_gen && !getenv("LWB_FORCE_GENERIC")) {
         CU(ctx, cudaSetDevice(ctx->device));
+        if (p->mix_pro) {                  // residue entry: front stages over every packet, then the rounds on ctx->spec
+            const lwb_batch_io *io = &p->io;
+            const uint8_t *d_kinds;
+            const uint32_t *d_ys;
+            int prc = stage_floor_arrays(ctx, io, p->mix_pro_r_lo, p->mix_pro_r_hi, p->mix_pro_C, ctx->stream, &d_kinds, &d_ys);
+            if (prc) return prc;
+            prc = launch_prologue(ctx, p->mix_pro_pk, p->mix_pro_n, p->mix_pro_C, p->mix_pro_fast, p->mix_pro_smem_old, io->coeffs,
+                                  p->mix_pro_dense ? io->dense_floor : nullptr, d_kinds, d_ys, (float *)ctx->spec.p - p->mix_pro_c_lo,
+                                  (uint8_t *)ctx->curve.p - p->mix_pro_c_lo);
+            if (prc) return prc;
+        }
         return mixed_launch_rounds(ctx, p->mix_launch, p->mix_rounds);
     }
     return decode_chains_impl(ctx, p->chains, p->n_chains, &p->io, p);

@@ -184,12 +184,7 @@ static int try_chain(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         if (residue) {
             r_lo = std::min(r_lo, c->packet_index);
             r_hi = std::max<uint64_t>(r_hi, c->packet_index + done);
-            for (uint64_t r = c->packet_index * C; r < (c->packet_index + done) * C; r++) {
-                const uint8_t kd = io->floor_kind[r];
-                if (kd > LWB_FLOOR_DENSE) return fail(ctx, LWB_ERR_INVALID, "floor_kind out of range");
-                if (kd == LWB_FLOOR_ONE && !io->floor1_y) return fail(ctx, LWB_ERR_INVALID, "floor1_y missing");
-                if (kd == LWB_FLOOR_DENSE) need_dense = true;
-            }
+            if ((rc = scan_floor_kinds(ctx, io, c->packet_index * C, (c->packet_index + done) * C, &need_dense))) return rc;
         }
     }
     if (need_dense && !io->dense_floor) return fail(ctx, LWB_ERR_INVALID, "dense_floor missing");
@@ -213,18 +208,7 @@ static int try_chain(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         }
         const uint8_t *d_kinds = nullptr;
         const uint32_t *d_ys = nullptr;
-        if (residue) {
-            const size_t rows = (size_t)(r_hi - r_lo) * uniform_c;
-            if ((rc = ensure(ctx, ctx->kinds, rows))) return rc;
-            CU(ctx, cudaMemcpyAsync(ctx->kinds.p, io->floor_kind + r_lo * uniform_c, rows, cudaMemcpyHostToDevice, sm));
-            d_kinds = (const uint8_t *)ctx->kinds.p - r_lo * uniform_c;
-            if (io->floor1_y) {
-                if ((rc = ensure(ctx, ctx->ys, rows * LWB_MAX_POSTS * 4))) return rc;
-                CU(ctx, cudaMemcpyAsync(ctx->ys.p, io->floor1_y + r_lo * uniform_c * LWB_MAX_POSTS, rows * LWB_MAX_POSTS * 4,
-                                        cudaMemcpyHostToDevice, sm));
-                d_ys = (const uint32_t *)ctx->ys.p - r_lo * uniform_c * LWB_MAX_POSTS;
-            }
-        }
+        if (residue && (rc = stage_floor_arrays(ctx, io, r_lo, r_hi, (unsigned)uniform_c, sm, &d_kinds, &d_ys))) return rc;
         // descriptors and mode bytes share one device buffer; a prepared batch (device memory, spectrum
         // entry) owns it and replays the launch while no stream changes shape
         const bool capture = plan && !host && !residue;

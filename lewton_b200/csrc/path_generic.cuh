@@ -86,6 +86,87 @@ static int launch(lwb_ctx *ctx, K kernel, dim3 grid, dim3 block, size_t smem, Ar
     return LWB_OK;
 }
 
+// Residue entry, front stages for `n_pk` packets of a batch with a uniform channel count C: spec[coeff_off ..] <-
+// floor x inverse-coupled residue (audio.rs:991-1039).  The two-kernel form (kernel_prologue.cuh) needs <= 8
+// channels and 16-byte aligned rows (prologue_is_fast); anything else takes the per-packet-CTA kernel.  `curve` is
+// a byte arena with the element indexing of `spec` (ctx->curve).
+static bool prologue_is_fast(const DevPacket *h_pk, size_t n_pk, unsigned C, const float *res, const float *dense, const float *spec,
+                             const uint8_t *curve)
+{
+    bool fast = C <= 8 && curve && n_pk * (size_t)C < 0xffffffffu && !getenv("LWB_OLD_PROLOGUE");
+    for (size_t i = 0; fast && i < n_pk; i++) {
+        const uint64_t e = h_pk[i].coeff_off;
+        fast = ((reinterpret_cast<uintptr_t>(res + e) | reinterpret_cast<uintptr_t>(spec + e) |
+                 (dense ? reinterpret_cast<uintptr_t>(dense + e) : 0)) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(curve + e) & 3) == 0;
+    }
+    return fast;
+}
+
+static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, size_t n_pk, unsigned C, bool fast, size_t smem_old,
+                           const float *res, const float *dense, const uint8_t *kinds, const uint32_t *ys, float *spec, uint8_t *curve)
+{
+    if (!n_pk) return LWB_OK;
+    if (!fast)
+        return launch(ctx, k_prologue, dim3((unsigned)n_pk), dim3(kPrologueThreads), smem_old, d_pk, res, dense, kinds, ys, spec);
+    const uint32_t rows = (uint32_t)(n_pk * C);
+    int rc = launch(ctx, k_floor1_curves, dim3((rows + kCurveRows - 1) / kCurveRows), dim3(kCurveThreads), 0, d_pk, rows, (int)C, kinds, ys, curve);
+    if (rc) return rc;
+    return launch(ctx, k_prologue3, dim3((unsigned)n_pk), dim3(kPro3Threads), prologue3_smem((int)C), d_pk, res, dense, kinds,
+                  (const uint8_t *)curve, spec);
+}
+static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, const DevPacket *h_pk, size_t n_pk, unsigned C, size_t smem_old,
+                           const float *res, const float *dense, const uint8_t *kinds, const uint32_t *ys, float *spec, uint8_t *curve)
+{
+    return launch_prologue(ctx, d_pk, n_pk, C, prologue_is_fast(h_pk, n_pk, C, res, dense, spec, curve), smem_old, res, dense, kinds, ys,
+                           spec, curve);
+}
+
+// Host-side look at the floor kinds of rows [row_lo, row_hi) (one row per (packet, channel)).  Device-resident
+// floor arrays (io->floor_memory == LWB_MEM_DEVICE) cannot be looked at: they are trusted, and the batch is assumed
+// to carry dense (floor-0) curves exactly when the caller passed a dense_floor arena.
+static int scan_floor_kinds(lwb_ctx *ctx, const lwb_batch_io *io, uint64_t row_lo, uint64_t row_hi, bool *need_dense)
+{
+    if (io->floor_memory == LWB_MEM_DEVICE) {
+        if (io->dense_floor) *need_dense = true;
+        return LWB_OK;
+    }
+    for (uint64_t r = row_lo; r < row_hi; r++) {
+        const uint8_t kd = io->floor_kind[r];
+        if (kd > LWB_FLOOR_DENSE) return fail(ctx, LWB_ERR_INVALID, "floor_kind out of range");
+        if (kd == LWB_FLOOR_ONE && !io->floor1_y) return fail(ctx, LWB_ERR_INVALID, "floor1_y missing");
+        if (kd == LWB_FLOOR_DENSE) *need_dense = true;
+    }
+    return LWB_OK;
+}
+
+// Device view of the floor arrays for packet rows [r_lo, r_hi) of a batch with C channels, biased so that ABSOLUTE
+// row indices address them: host arrays are uploaded to ctx->kinds / ctx->ys on `sm`, device arrays are used in place.
+static int stage_floor_arrays(lwb_ctx *ctx, const lwb_batch_io *io, uint64_t r_lo, uint64_t r_hi, unsigned C, cudaStream_t sm,
+                              const uint8_t **d_kinds, const uint32_t **d_ys)
+{
+    *d_kinds = nullptr;
+    *d_ys = nullptr;
+    if (io->floor_memory == LWB_MEM_DEVICE) {
+        *d_kinds = io->floor_kind;
+        *d_ys = io->floor1_y;
+        return LWB_OK;
+    }
+    if (r_hi <= r_lo) return LWB_OK;
+    int rc;
+    const size_t rows = (size_t)(r_hi - r_lo) * C;
+    if ((rc = ensure(ctx, ctx->kinds, rows))) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->kinds.p, io->floor_kind + r_lo * C, rows, cudaMemcpyHostToDevice, sm));
+    *d_kinds = (const uint8_t *)ctx->kinds.p - r_lo * C;
+    if (io->floor1_y) {
+        if ((rc = ensure(ctx, ctx->ys, rows * LWB_MAX_POSTS * sizeof(uint32_t)))) return rc;
+        CU(ctx, cudaMemcpyAsync(ctx->ys.p, io->floor1_y + r_lo * C * LWB_MAX_POSTS, rows * LWB_MAX_POSTS * sizeof(uint32_t),
+                                cudaMemcpyHostToDevice, sm));
+        *d_ys = (const uint32_t *)ctx->ys.p - r_lo * C * LWB_MAX_POSTS;
+    }
+    return LWB_OK;
+}
+
 struct DevArenas {
     const float *coeffs;      // device
     const float *dense;       // device or null
@@ -182,9 +263,9 @@ static int run_generic(lwb_ctx *ctx, std::vector<PlanChain> &plan, const lwb_bat
         const DevPacket *dp = (const DevPacket *)ctx->desc.p;
         const float *spec = ar.coeffs;
         if (io->entry == LWB_ENTRY_RESIDUE) {
-            if ((rc = ensure(ctx, ctx->spec, spec_hi * sizeof(float)))) return rc;
-            if ((rc = launch(ctx, k_prologue, dim3((unsigned)n_desc), dim3(kPrologueThreads), prologue_smem_of(plan), dp, ar.coeffs,
-                             ar.dense, ar.kinds, ar.ys, (float *)ctx->spec.p)))
+            if ((rc = ensure(ctx, ctx->spec, spec_hi * sizeof(float))) || (rc = ensure(ctx, ctx->curve, spec_hi + 16))) return rc;
+            if ((rc = launch_prologue(ctx, dp, hp, n_desc, maxc, prologue_smem_of(plan), ar.coeffs, ar.dense, ar.kinds, ar.ys,
+                                      (float *)ctx->spec.p, (uint8_t *)ctx->curve.p)))
                 return rc;
             spec = (const float *)ctx->spec.p;
         }

@@ -102,7 +102,7 @@ static bool batch_is_uniform_long(lwb_ctx *ctx, const lwb_chain *chains, size_t 
 // batch is then neither validated as a spectrum entry nor copied.
 static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch,
                     bool *handled, const float *spectrum_dev = nullptr, uint64_t spectrum_base = 0,
-                    lwb_plan *plan = nullptr)
+                    lwb_plan *plan = nullptr, bool capture_with_spectrum_dev = false)
 {
     *handled = false;
     const uint64_t gen_at_entry = ctx->state_gen;
@@ -221,7 +221,8 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
     const int par = ctx->runs_par;
     ctx->runs_par ^= 1;
     // a plan (device-memory batches) owns its descriptor buffer so that later executions can reuse it
-    const bool capture = plan && !host && !spectrum_dev && n_chunks == 1;
+    // (runs that read ctx->spec stay valid because growing any ctx arena bumps state_gen, see ensure())
+    const bool capture = plan && !host && (!spectrum_dev || capture_with_spectrum_dev) && n_chunks == 1;
     DevBuf &rb = capture ? plan->runs : ctx->runs_buf[par];
     if ((rc = ensure(ctx, rb, cap_runs * sizeof(LongRun)))) return rc;
     LongRun *const d_runs_base = (LongRun *)rb.p;
@@ -359,7 +360,7 @@ static int run_prologue_all(lwb_ctx *ctx, std::vector<PlanChain> &plan, const De
     int rc;
     if ((rc = ensure_pinned(ctx, n_desc * sizeof(DevPacket)))) return rc;
     if ((rc = ensure(ctx, ctx->desc, n_desc * sizeof(DevPacket)))) return rc;
-    if ((rc = ensure(ctx, ctx->spec, spec_elems * sizeof(float)))) return rc;
+    if ((rc = ensure(ctx, ctx->spec, spec_elems * sizeof(float))) || (rc = ensure(ctx, ctx->curve, spec_elems + 16))) return rc;
     CU(ctx, cudaStreamSynchronize(ctx->stream));          // pinned descriptor staging is reused
     DevPacket *hp = (DevPacket *)ctx->h_desc;
     size_t di = 0;
@@ -379,7 +380,118 @@ static int run_prologue_all(lwb_ctx *ctx, std::vector<PlanChain> &plan, const De
         }
     }
     CU(ctx, cudaMemcpyAsync(ctx->desc.p, hp, n_desc * sizeof(DevPacket), cudaMemcpyHostToDevice, ctx->stream));
-    return launch(ctx, k_prologue, dim3((unsigned)n_desc), dim3(kPrologueThreads), prologue_smem_of(plan), (const DevPacket *)ctx->desc.p,
-                  ar.coeffs, ar.dense, ar.kinds, ar.ys, (float *)ctx->spec.p);
+    return launch_prologue(ctx, (const DevPacket *)ctx->desc.p, hp, n_desc, plan[0].c->stream->setup->channels, prologue_smem_of(plan),
+                           ar.coeffs, ar.dense, ar.kinds, ar.ys, (float *)ctx->spec.p, (uint8_t *)ctx->curve.p);
 }
 
+
+// Residue-entry batches whose every packet is a long block with long neighbours: the front stages
+// (k_floor1_curves + k_prologue3, or k_prologue) form the spectrum on the device, the fused kernel does the
+// rest.  Planned straight from the chain list like try_long (no per-packet PlanChain vectors); a prepared batch
+// keeps the front-stage descriptors and, for device-memory batches, the fused kernel's runs, so that a replay
+// is three launches with no host work (lwb_plan_execute).
+static int try_long_residue(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch, bool *handled,
+                            lwb_plan *plan)
+{
+    *handled = false;
+    if (io->entry != LWB_ENTRY_RESIDUE || getenv("LWB_FORCE_GENERIC")) return LWB_OK;
+    if (!batch_is_uniform_long(ctx, chains, n_chains, io)) return LWB_OK;
+    if (!io->floor_kind) return fail(ctx, LWB_ERR_INVALID, "residue entry needs floor_kind");
+    unsigned C = 0;
+    size_t n_pk = 0;
+    uint64_t c_lo = ~0ull, c_hi = 0, r_lo = ~0ull, r_hi = 0;
+    bool need_dense = false;
+    int rc;
+    for (size_t i = 0; i < n_chains; i++) {
+        const lwb_chain *c = &chains[i];
+        const unsigned cc = c->stream->setup->channels;
+        if (!C) C = cc;
+        if (C != cc) return fail(ctx, LWB_ERR_INVALID, "residue batches need one channel count");
+        if (!c->n_packets) continue;
+        n_pk += c->n_packets;
+        c_lo = std::min(c_lo, c->coeff_offset);
+        c_hi = std::max(c_hi, c->coeff_offset + (uint64_t)c->n_packets * C * kLongN2);
+        r_lo = std::min(r_lo, c->packet_index);
+        r_hi = std::max<uint64_t>(r_hi, c->packet_index + c->n_packets);
+        if ((rc = scan_floor_kinds(ctx, io, c->packet_index * C, (c->packet_index + c->n_packets) * C, &need_dense))) return rc;
+    }
+    if (need_dense && !io->dense_floor) return fail(ctx, LWB_ERR_INVALID, "dense_floor missing");
+    for (size_t i = 0; i < n_chains; i++) {
+        lwb_stream *s = chains[i].stream;
+        if (s->busy_epoch == epoch) return fail(ctx, LWB_ERR_INVALID, "a stream appears in two chains of one batch");
+        s->busy_epoch = epoch;
+    }
+    *handled = true;
+    if (!n_pk) {
+        for (size_t i = 0; i < n_chains; i++) { chains[i].status = LWB_OK; chains[i].packets_done = 0; chains[i].n_samples = 0; }
+        return LWB_OK;
+    }
+    cudaStream_t sm = ctx->stream;
+    const size_t elems = (size_t)(c_hi - c_lo);
+    const float *d_res = io->coeffs, *d_dense = need_dense ? io->dense_floor : nullptr;
+    if (io->memory == LWB_MEM_HOST) {
+        if ((rc = ensure(ctx, ctx->coeffs, elems * 4))) return rc;
+        CU(ctx, cudaMemcpyAsync(ctx->coeffs.p, io->coeffs + c_lo, elems * 4, cudaMemcpyHostToDevice, sm));
+        d_res = (const float *)ctx->coeffs.p - c_lo;
+        if (need_dense) {
+            if ((rc = ensure(ctx, ctx->dense, elems * 4))) return rc;
+            CU(ctx, cudaMemcpyAsync(ctx->dense.p, io->dense_floor + c_lo, elems * 4, cudaMemcpyHostToDevice, sm));
+            d_dense = (const float *)ctx->dense.p - c_lo;
+        }
+    }
+    if ((rc = ensure(ctx, ctx->spec, elems * 4)) || (rc = ensure(ctx, ctx->curve, elems + 16))) return rc;
+    float *d_spec = (float *)ctx->spec.p - c_lo;
+    uint8_t *d_curve = (uint8_t *)ctx->curve.p - c_lo;
+    const uint8_t *d_kinds;
+    const uint32_t *d_ys;
+    if ((rc = stage_floor_arrays(ctx, io, r_lo, r_hi, C, sm, &d_kinds, &d_ys))) return rc;
+    // front-stage descriptors: absolute element offsets and packet rows (the arena pointers are biased instead)
+    const DevPacket *d_pk;
+    bool fast;
+    const size_t smem_old = prologue_smem((int)C, kLongBs);
+    if (plan && plan->pro_captured && plan->n_pro == n_pk) {
+        d_pk = (const DevPacket *)plan->pro.p;
+        fast = plan->pro_fast;
+    } else {
+        Staging *st;
+        if ((rc = acquire_staging(ctx, n_pk * sizeof(DevPacket), &st))) return rc;
+        DevBuf &db = plan ? plan->pro : ctx->desc;
+        if ((rc = ensure(ctx, db, n_pk * sizeof(DevPacket)))) return rc;
+        DevPacket *hp = (DevPacket *)st->h;
+        size_t di = 0;
+        for (size_t i = 0; i < n_chains; i++) {
+            const lwb_chain *c = &chains[i];
+            const lwb_setup *su = c->stream->setup;
+            for (uint32_t k = 0; k < c->n_packets; k++) {
+                DevPacket &d = hp[di++];
+                std::memset(&d, 0, sizeof(d));
+                d.setup = su->d_setup;
+                d.coeff_off = c->coeff_offset + (uint64_t)k * C * kLongN2;
+                d.pkt_index = c->packet_index + k;
+                d.n = kLongN;
+                d.blockflag = 1;
+                d.mapping = su->host.mode_mapping[c->mode_numbers[k]];
+                d.channels = (uint8_t)C;
+            }
+        }
+        fast = prologue_is_fast(hp, n_pk, C, d_res, d_dense, d_spec, d_curve);
+        CU(ctx, cudaMemcpyAsync(db.p, hp, n_pk * sizeof(DevPacket), cudaMemcpyHostToDevice, sm));
+        CU(ctx, cudaEventRecord(st->ev, sm));
+        st->pending = true;
+        d_pk = (const DevPacket *)db.p;
+        if (plan) {
+            plan->pro_captured = true;
+            plan->pro_fast = fast;
+            plan->n_pro = n_pk;
+            plan->pro_smem_old = smem_old;
+            plan->pro_C = C;
+            plan->pro_c_lo = c_lo; plan->pro_c_hi = c_hi; plan->pro_r_lo = r_lo; plan->pro_r_hi = r_hi;
+        }
+    }
+    if ((rc = launch_prologue(ctx, d_pk, n_pk, C, fast, smem_old, d_res, d_dense, d_kinds, d_ys, d_spec, d_curve))) return rc;
+    bool h2 = false;
+    rc = try_long(ctx, chains, n_chains, io, epoch, &h2, (const float *)ctx->spec.p, c_lo, plan, true);
+    if (rc) return rc;
+    if (!h2) return fail(ctx, LWB_ERR_INVALID, "internal: uniform long residue batch refused by the fused path");
+    return LWB_OK;
+}

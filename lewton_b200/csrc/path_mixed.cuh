@@ -146,12 +146,8 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         if (residue) {
             r_lo = std::min(r_lo, c->packet_index);
             r_hi = std::max<uint64_t>(r_hi, c->packet_index + done);
-            for (uint64_t r = c->packet_index * C; r < (c->packet_index + done) * C; r++) {
-                const uint8_t kd = io->floor_kind[r];
-                if (kd > LWB_FLOOR_DENSE) return fail(ctx, LWB_ERR_INVALID, "floor_kind out of range");
-                if (kd == LWB_FLOOR_ONE && !io->floor1_y) return fail(ctx, LWB_ERR_INVALID, "floor1_y missing");
-                if (kd == LWB_FLOOR_DENSE) need_dense = true;
-            }
+            int krc = scan_floor_kinds(ctx, io, c->packet_index * C, (c->packet_index + done) * C, &need_dense);
+            if (krc) return krc;
         }
     }
     if (need_dense && !io->dense_floor) return fail(ctx, LWB_ERR_INVALID, "dense_floor missing");
@@ -159,7 +155,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
     if (!chain_sees_long) n1max = n0max;
     int wpc = std::max(1, std::min(8, n1max / 1024));
     while (wpc > 1 && (unsigned)wpc * maxc > 32) wpc >>= 1;
-    const int np = chain_np(maxc, n1max, wpc, residue);
+    const int np = chain_np(maxc, n1max, wpc, false);      // residue entry: the front stages run first, the kernels see a spectrum
     const size_t smem = chain_smem(maxc, n1max, np);
     if (max_rounds) {
         const bool host = io->memory == LWB_MEM_HOST;
@@ -193,18 +189,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         }
         const uint8_t *d_kinds = nullptr;
         const uint32_t *d_ys = nullptr;
-        if (residue) {
-            const size_t rows = (size_t)(r_hi - r_lo) * uniform_c;
-            if ((rc = ensure(ctx, ctx->kinds, rows))) return rc;
-            CU(ctx, cudaMemcpyAsync(ctx->kinds.p, io->floor_kind + r_lo * uniform_c, rows, cudaMemcpyHostToDevice, sm));
-            d_kinds = (const uint8_t *)ctx->kinds.p - r_lo * uniform_c;
-            if (io->floor1_y) {
-                if ((rc = ensure(ctx, ctx->ys, rows * LWB_MAX_POSTS * 4))) return rc;
-                CU(ctx, cudaMemcpyAsync(ctx->ys.p, io->floor1_y + r_lo * uniform_c * LWB_MAX_POSTS, rows * LWB_MAX_POSTS * 4,
-                                        cudaMemcpyHostToDevice, sm));
-                d_ys = (const uint32_t *)ctx->ys.p - r_lo * uniform_c * LWB_MAX_POSTS;
-            }
-        }
+        if (residue && (rc = stage_floor_arrays(ctx, io, r_lo, r_hi, (unsigned)uniform_c, sm, &d_kinds, &d_ys))) return rc;
         // descriptors of every round: [LongRun...][ChainDesc...][DevPacket (prologue of the long segments)...][mode bytes]
         // A round with few fused-kernel runs leaves most of the 148 x 8 warps idle and lasts as long as its
         // longest run: such rounds cut their runs (each cut costs one extra IMDCT, the primer packet whose
@@ -247,12 +232,13 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             for (size_t i = ck.i0; i < ck.i1; i++)
                 for (uint32_t q = 0; q < walks[i].n_seg; q++) {
                     const Seg &sg = segs[walks[i].seg0 + q];
-                    if (sg.is_long) { n_runs += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, q); if (residue) n_pro += sg.n; }
+                    if (sg.is_long) n_runs += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, q);
                     else n_cd++;
+                    if (residue) n_pro += sg.n;
                 }
         }
         // a prepared batch (device memory, spectrum entry) owns its descriptors so that later executions replay them
-        const bool capture = plan && !host && !residue;
+        const bool capture = plan && !host;
         DevBuf &dbuf = capture ? plan->mix : ctx->cdesc;
         const size_t off_cd = n_runs * sizeof(LongRun), off_pro = off_cd + n_cd * sizeof(ChainDesc);
         const size_t off_by = off_pro + n_pro * sizeof(DevPacket), total = off_by + boff + 16;
@@ -265,8 +251,8 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         DevPacket *h_pro = (DevPacket *)(hb + off_pro);
         std::memcpy(hb + off_by, bytes.data(), boff);
         const float *d_spec = nullptr;
-        if (residue && n_pro) {
-            if ((rc = ensure(ctx, ctx->spec, (size_t)(c_hi - c_lo) * 4))) return rc;
+        if (residue) {
+            if ((rc = ensure(ctx, ctx->spec, (size_t)(c_hi - c_lo) * 4)) || (rc = ensure(ctx, ctx->curve, (size_t)(c_hi - c_lo) + 16))) return rc;
             d_spec = (const float *)ctx->spec.p - c_lo;          // same element offsets as the coefficient arena
         }
         size_t wr = 0, wc = 0, wp = 0;
@@ -336,6 +322,24 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                     const lwb_chain *c = &chains[i];
                     const lwb_stream *s = c->stream;
                     const lwb_setup *su = s->setup;
+                    if (residue) {
+                        uint64_t co = sg.coeff;
+                        for (uint32_t q = 0; q < sg.n; q++) {
+                            const uint8_t mode = c->mode_numbers[sg.p0 + q];
+                            const bool lng = su->host.mode_blockflag[mode] != 0;
+                            const uint32_t nq = 1u << (lng ? su->bs1 : su->bs0);
+                            DevPacket &dp = h_pro[wp++];
+                            std::memset(&dp, 0, sizeof(dp));
+                            dp.setup = su->d_setup;
+                            dp.coeff_off = co;
+                            dp.pkt_index = c->packet_index + sg.p0 + q;
+                            dp.n = (uint16_t)nq;
+                            dp.blockflag = lng;
+                            dp.mapping = su->host.mode_mapping[mode];
+                            dp.channels = (uint8_t)su->channels;
+                            co += (uint64_t)su->channels * (nq >> 1);
+                        }
+                    }
                     ChainDesc &d = h_cd[wc++];
                     std::memset(&d, 0, sizeof(d));
                     d.setup = su->d_setup;
@@ -369,8 +373,12 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         }
         MixLaunch ml;
         ml.db = db; ml.off_cd = off_cd; ml.off_by = off_by; ml.pack = pack; ml.w_short = w_short; ml.ls = ls_long;
-        ml.i16 = i16; ml.residue = residue; ml.out_format = io->out_format; ml.warps = maxc * wpc; ml.smem = smem;
-        ml.n1max = n1max; ml.wpc = wpc; ml.np = np; ml.coeffs = d_coeffs; ml.dense = d_dense; ml.kinds = d_kinds; ml.ys = d_ys; ml.pcm = d_pcm;
+        ml.i16 = i16; ml.residue = false; ml.out_format = io->out_format; ml.warps = maxc * wpc; ml.smem = smem;
+        ml.n1max = n1max; ml.wpc = wpc; ml.np = np; ml.coeffs = residue ? d_spec : d_coeffs; ml.dense = nullptr; ml.kinds = nullptr; ml.ys = nullptr;
+        ml.pcm = d_pcm;
+        bool pro_fast = false;
+        if (residue && n_pro)
+            pro_fast = prologue_is_fast(h_pro, n_pro, maxc, d_coeffs, need_dense ? d_dense : nullptr, d_spec, (const uint8_t *)ctx->curve.p - c_lo);
         for (size_t k = 0; k < n_chunks; k++) {
             Chunk &ck = chunks[k];
             if (ck.kc_hi <= ck.kc_lo) continue;
@@ -384,8 +392,9 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 CU(ctx, cudaStreamWaitEvent(sm, ctx->ev_in[k], 0));
             }
             if (residue && ck.np_)
-                if ((rc = launch(ctx, k_prologue, dim3((unsigned)ck.np_), dim3(kPrologueThreads), prologue_smem(maxc, kLongBs),
-                                 (const DevPacket *)(db + off_pro) + ck.p0, d_coeffs, d_dense, d_kinds, d_ys, const_cast<float *>(d_spec))))
+                if ((rc = launch_prologue(ctx, (const DevPacket *)(db + off_pro) + ck.p0, ck.np_, maxc, pro_fast, prologue_smem(maxc, kLongBs),
+                                          d_coeffs, need_dense ? d_dense : nullptr, d_kinds, d_ys, const_cast<float *>(d_spec),
+                                          (uint8_t *)ctx->curve.p - c_lo)))
                     return rc;
             if ((rc = mixed_launch_rounds(ctx, ml, ck.rounds))) return rc;
             if (host && ck.ko_hi > ck.ko_lo) {
@@ -400,6 +409,16 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             plan->gen = gen_at_entry;
             plan->mix_launch = ml;
             plan->mix_rounds = std::move(chunks[0].rounds);
+            plan->mix_pro = residue && n_pro;
+            if (plan->mix_pro) {            // replayed by lwb_plan_execute in front of the rounds
+                plan->mix_pro_pk = (const DevPacket *)(db + off_pro);
+                plan->mix_pro_n = n_pro;
+                plan->mix_pro_fast = pro_fast;
+                plan->mix_pro_C = maxc;
+                plan->mix_pro_smem_old = prologue_smem(maxc, kLongBs);
+                plan->mix_pro_c_lo = c_lo; plan->mix_pro_r_lo = r_lo; plan->mix_pro_r_hi = r_hi;
+                plan->mix_pro_dense = need_dense;
+            }
         }
         if (host) {
             CU(ctx, cudaStreamSynchronize(ctx->copy_out));

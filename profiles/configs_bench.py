@@ -4,7 +4,9 @@
 
   long_f32        S x P stereo long packets, spectrum entry, f32 planar           8 B / sample (the headline)
   long_i16        same, i16 planar output                                          6 B / sample
-  long_residue    same, residue entry: coupling (0,1) + floor-1 + multiply         16 B / sample (k_prologue + k_long)
+  long_residue    same, residue entry: coupling (0,1) + floor-1 + multiply; floor posts device-resident
+                  (lwb_batch_io::floor_memory); k_floor1_curves + k_prologue3 + k_long, captured plan   18 B / sample moved, 8 algorithmic
+  long_residue_hostfloors   same with host floor arrays (uploaded every step)
   streaming_p1    one packet per stream per call (state round-trips HBM)           16 B / sample
   config3_6ch     BASELINE.json configs[2] shape: 6 channels, Bernoulli(0.25) short blocks, coupling chain
                   (0,1),(2,3),(0,4), floor-1, residue entry; segmented path (k_prologue + k_long, k_chain)
@@ -73,18 +75,28 @@ def main():
     modes = np.ones(P, np.uint8)
     for case, fmt, entry, bps in (("long_f32", cabi.OUT_F32_PLANAR, cabi.ENTRY_SPECTRUM, 8),
                                   ("long_i16", cabi.OUT_I16_PLANAR, cabi.ENTRY_SPECTRUM, 6),
-                                  ("long_residue", cabi.OUT_F32_PLANAR, cabi.ENTRY_RESIDUE, 16)):
+                                  ("long_residue", cabi.OUT_F32_PLANAR, cabi.ENTRY_RESIDUE, 8),
+                                  ("long_residue_i16", cabi.OUT_I16_PLANAR, cabi.ENTRY_RESIDUE, 6),
+                                  ("long_residue_hostfloors", cabi.OUT_F32_PLANAR, cabi.ENTRY_RESIDUE, 8)):
         pcm = torch.empty(S * C * P * 1024, device="cuda", dtype=torch.float32 if fmt == cabi.OUT_F32_PLANAR else torch.int16)
         pw = [L.PreviousWindowRight(su) for _ in range(S)]
         chains = [L.ChainSpec(pw[s], modes, coeff_offset=s * P * C * 1024, packet_index=s * P, out_offset=s * C * P * 1024,
                               out_stride=P * 1024) for s in range(S)]
-        kw = {}
+        kw, keep = {}, None
         if entry == cabi.ENTRY_RESIDUE:
-            kw = dict(floor_kind=np.full(S * P * C, cabi.FLOOR_ONE, np.uint8), floor1_y=floor_rows(S * P * C, len(floors[0][1]), 1))
+            h_kinds, h_ys = np.full(S * P * C, cabi.FLOOR_ONE, np.uint8), floor_rows(S * P * C, len(floors[0][1]), 1)
+            if case.endswith("hostfloors"):
+                kw = dict(floor_kind=h_kinds, floor1_y=h_ys)
+            else:
+                keep = (torch.from_numpy(h_kinds).cuda(), torch.from_numpy(h_ys.view(np.int32)).cuda())
+                kw = dict(floor_kind=keep[0].data_ptr(), floor1_y=keep[1].data_ptr(), floor_memory=cabi.MEM_DEVICE)
         batch = L.Batch(ctx, chains, entry, cabi.MEM_DEVICE, spec.data_ptr(), pcm.data_ptr(), fmt, **kw)
         ms, host_ms, launches = timed(batch)
         report(case, S * P * C * 1024, ms, host_ms, launches, bps,
-               f"{S} stereo streams x {P} long packets" + (", per-packet floor posts uploaded every step (host arrays)" if kw else ""))
+               f"{S} stereo streams x {P} long packets" +
+               (", floor posts in host arrays, uploaded every step" if case.endswith("hostfloors") else
+                ", floor posts device-resident, front stages + fused kernel replayed from the plan" if kw else ""))
+        del keep
         batch.close()
         for p in pw:
             p.close()
@@ -128,13 +140,42 @@ def main():
     chains = [L.ChainSpec(pw[s], seqs[s][0], seqs[s][1], seqs[s][2], coeff_offset=offs[s], packet_index=s * P3,
                           out_offset=s * C3 * P3 * 1024, out_stride=P3 * 1024) for s in range(S3)]
     rows = S3 * P3 * C3
+    h_kinds, h_ys = np.full(rows, cabi.FLOOR_ONE, np.uint8), floor_rows(rows, len(floors[0][1]), 1)
+    d_kinds, d_ys = torch.from_numpy(h_kinds).cuda(), torch.from_numpy(h_ys.view(np.int32)).cuda()
     batch = L.Batch(ctx, chains, cabi.ENTRY_RESIDUE, cabi.MEM_DEVICE, res.data_ptr(), pcm.data_ptr(), cabi.OUT_F32_PLANAR,
-                    floor_kind=np.full(rows, cabi.FLOOR_ONE, np.uint8), floor1_y=floor_rows(rows, len(floors[0][1]), 1))
+                    floor_kind=d_kinds.data_ptr(), floor1_y=d_ys.data_ptr(), floor_memory=cabi.MEM_DEVICE)
+    # output check on a sample of the streams: a fresh batch run from empty states against the oracle
+    from helpers import RefStream, bits_equal
+    from oracle import oracle
+    oracle.build()
+    pcm.zero_()
+    batch.run()
+    ctx.synchronize()
+    batch.collect()
+    checked = 0
+    for s in (0, 1, S3 // 2, S3 - 1):
+        ref = RefStream(oracle, C3, 8, 11, [(0, 0), (1, 0)], [{"coupling": [(0, 1), (2, 3), (0, 4)], "floor_of_channel": [0] * C3}], floors)
+        bf, prev, nxt = seqs[s]
+        h_res = res[offs[s]:(offs[s + 1] if s + 1 < S3 else coeff_off)].cpu().numpy()
+        pos, parts = 0, []
+        for i in range(P3):
+            n2 = 1024 if bf[i] else 128
+            r = h_res[pos:pos + C3 * n2].reshape(C3, n2)
+            pos += C3 * n2
+            fl = [[int(v) for v in h_ys[(s * P3 + i) * C3 + c][:len(floors[0][1])]] for c in range(C3)]
+            rc, o = ref.packet(int(bf[i]), int(prev[i]), int(nxt[i]), r, fl)
+            assert rc == 0
+            parts.append(o)
+        want = np.concatenate(parts, axis=1)
+        got = pcm[s * C3 * P3 * 1024:(s + 1) * C3 * P3 * 1024].cpu().numpy().reshape(C3, P3 * 1024)[:, :want.shape[1]]
+        assert chains[s].n_samples == want.shape[1] and bits_equal(got, want), f"config3_6ch stream {s} differs from the oracle"
+        checked += 1
     ms, host_ms, launches = timed(batch, reps=5)
     batch.collect()
     samples = sum(ch.n_samples for ch in chains) * C3
     report("config3_6ch", samples, ms, host_ms, launches, 8,
-           f"{S3} streams x {P3} packets x 6 ch, 25 % short blocks, residue entry; host plans every step (no capture for residue entry)")
+           f"{S3} streams x {P3} packets x 6 ch, 25 % short blocks, residue entry, device floor arrays, captured plan; "
+           f"{checked} streams of the first run checked bit-exact against the oracle")
     batch.close()
     ctx.close()
 

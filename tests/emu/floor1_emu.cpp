@@ -8,7 +8,7 @@
 #include "../../lewton_b200/csrc/tables_host.cpp"
 
 extern "C" int lwb_emu_floor1(int mult, const uint32_t *xs, int nposts, const uint32_t *y, int n2,
-                              uint32_t *curve_closed, uint8_t *curve_render)
+                              uint32_t *curve_closed, uint8_t *curve_render, uint8_t *curve_chunks)
 {
     lwb_floor_desc d;
     std::memset(&d, 0, sizeof(d));
@@ -24,5 +24,29 @@ extern "C" int lwb_emu_floor1(int mult, const uint32_t *xs, int nposts, const ui
     for (int k = 0; k < n2; k++) curve_closed[k] = lwb::d_floor1_y_at(sx, sy, m, k);
     std::memset(curve_render, 0xee, (size_t)n2);
     for (int seg = 0; seg + 1 < m; seg++) lwb::d_floor1_render_segment(sx, sy, seg, n2, curve_render);
+    // the chunked closed-form render of k_floor1_curves (16 bins per work item, multiply-high division)
+    uint32_t sm[LWB_MAX_POSTS + 1];
+    for (int j = 0; j + 1 < m; j++) sm[j] = lwb::d_floor1_magic((int)sx[j + 1] - (int)sx[j]);
+    for (int k0 = 0; k0 < n2; k0 += 16) {
+        uint32_t w[4];
+        lwb::d_floor1_render16(sx, sy, sm, m, k0, w);
+        std::memcpy(curve_chunks + k0, w, 16);
+    }
     return 0;
+}
+
+// exactness of the multiply-high division used by d_floor1_render16: every adx, every |dy|, dense t
+extern "C" long lwb_emu_magic_mismatches(int adx_lo, int adx_hi)
+{
+    long bad = 0;
+    for (int adx = adx_lo; adx <= adx_hi; adx++) {
+        const uint32_t mg = lwb::d_floor1_magic(adx);
+        if (!mg) continue;
+        for (uint32_t ady = 0; ady < 256; ady++)
+            for (uint32_t t = 0; t < 4096; t += (t < 64 || t > 4000) ? 1 : 7) {
+                const uint32_t nn = ady * t;
+                if (lwb::d_mulhi_u32(nn, mg) != nn / (uint32_t)adx) bad++;
+            }
+    }
+    return bad;
 }

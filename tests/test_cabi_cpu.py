@@ -28,7 +28,7 @@ def test_header_symbols_exported(lib):
     nm = subprocess.run(["nm", "-D", "--defined-only", _cabi.SO_PATH], capture_output=True, text=True, check=True).stdout
     exported = set(re.findall(r" T (lwb_[a-z0-9_]+)", nm))
     assert declared <= exported, declared - exported
-    assert lib.lwb_abi_version() == 1
+    assert lib.lwb_abi_version() == 2
 
 
 def test_struct_layouts_match_header(lib, tmp_path):

@@ -520,8 +520,8 @@ def test_residue_entry_long_batch_uses_prologue_plus_fused(ctx, oracle, memory, 
             else:
                 assert np.array_equal(pcm[s][:, :n], oracle.quantise_i16(want[s])), (batch, s)
             assert bits_equal(pwrs[s].data(), refs[s].pwr.data())
-    # 2 batches x (prologue + fused kernel) = 4 launches: the generic IMDCT/overlap kernels did not run
-    assert ctx.launch_count - launches0 == 4
+    # 2 batches x (k_floor1_curves + k_prologue3 + fused kernel) = 6 launches: the generic IMDCT/overlap kernels did not run
+    assert ctx.launch_count - launches0 == 6
 
 
 def test_prepared_batch_reuses_descriptors_and_replans_on_state_change(ctx, oracle):
@@ -685,22 +685,37 @@ def test_chain_kernel_vs_four_kernel_path_mixed_sequences(ctx, oracle, channels,
     assert np.array_equal(outs["chain"].view(np.uint8), outs["four"].view(np.uint8))
 
 
-@pytest.mark.parametrize("entry,memory,fmt,seed,bs0", [("spectrum", cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 80, 8),
-                                                       ("spectrum", cabi.MEM_DEVICE, cabi.OUT_I16_PLANAR, 81, 8),
-                                                       ("residue", cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 82, 8),
-                                                       ("residue", cabi.MEM_DEVICE, cabi.OUT_F32_PLANAR, 83, 8),
-                                                       ("spectrum", cabi.MEM_DEVICE, cabi.OUT_F32_PLANAR, 84, 6),
-                                                       ("spectrum", cabi.MEM_HOST, cabi.OUT_I16_PLANAR, 85, 10),
-                                                       ("residue", cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 86, 11)])
-def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle, entry, memory, fmt, seed, bs0):
+# BASELINE.json configs[2]: 5.1 channels, 256/2048 mixed blocks, residue coupling chained through a shared channel
+_COUPLING_51 = [(0, 1), (2, 3), (0, 4)]
+
+
+@pytest.mark.parametrize("entry,memory,fmt,seed,bs0,channels", [
+    ("spectrum", cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 80, 8, 2),
+    ("spectrum", cabi.MEM_DEVICE, cabi.OUT_I16_PLANAR, 81, 8, 2),
+    ("residue", cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 82, 8, 2),
+    ("residue", cabi.MEM_DEVICE, cabi.OUT_F32_PLANAR, 83, 8, 2),
+    ("spectrum", cabi.MEM_DEVICE, cabi.OUT_F32_PLANAR, 84, 6, 2),
+    ("spectrum", cabi.MEM_HOST, cabi.OUT_I16_PLANAR, 85, 10, 2),
+    ("residue", cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 86, 11, 2),
+    # config 3 on the path that serves it: try_mixed -> batched k_prologue (8-way coupled-channel path)
+    # -> k_long with transitional blocks -> k_chain, residue entry, planar f32 and i16, host and device
+    ("residue", cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 87, 8, 6),
+    ("residue", cabi.MEM_DEVICE, cabi.OUT_I16_PLANAR, 88, 8, 6),
+    ("residue", cabi.MEM_DEVICE, cabi.OUT_F32_PLANAR, 89, 8, 6),
+    ("spectrum", cabi.MEM_HOST, cabi.OUT_I16_PLANAR, 90, 8, 6)])
+def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle, entry, memory, fmt, seed, bs0, channels):
     """The standard 256/2048 stream shape: mostly long blocks with bursts of short ones.  The host cuts
     every chain into long-run segments (fused kernel) and the rest (chain kernel) and runs them round
     by round, handing PreviousWindowRight over through the device state.  Bit-exact against the oracle,
-    over two consecutive batches (state carried across), and identical to the chain-kernel-only path."""
+    over two consecutive batches (state carried across), and identical to the chain-kernel-only path.
+    The 6-channel cases are BASELINE.json configs[2]: the coupling steps chain through channel 0
+    (audio.rs:991-1002 applies them in reverse), window shapes per audio.rs:1059-1073."""
     rng = np.random.default_rng(seed)
-    channels, bs1, S, P = 2, 11, 6, 40
+    bs1, S, P = 11, 6, 40
     residue = entry == "residue"
     floors, mappings, modes = _random_packet_case(rng, channels, bs0, bs1)
+    if channels == 6:
+        mappings[0]["coupling"] = list(_COUPLING_51)
     su = make_setup(ctx, channels, bs0, bs1, modes=modes, mappings=mappings, floors=floors)
     f32 = fmt == cabi.OUT_F32_PLANAR
     dt = np.float32 if f32 else np.int16
@@ -926,3 +941,114 @@ def test_prepared_mixed_batch_replays_captured_rounds(ctx, oracle):
     batch.close()
     ctx.device_free(d_in)
     ctx.device_free(d_out)
+
+
+@pytest.mark.parametrize("shape,channels,fmt,floor_mem,seed", [
+    ("long", 2, cabi.OUT_F32_PLANAR, cabi.MEM_DEVICE, 120),
+    ("long", 2, cabi.OUT_I16_PLANAR, cabi.MEM_HOST, 121),
+    ("long", 1, cabi.OUT_F32_PLANAR, cabi.MEM_DEVICE, 122),
+    ("mixed", 6, cabi.OUT_F32_PLANAR, cabi.MEM_DEVICE, 123),
+    ("mixed", 2, cabi.OUT_I16_PLANAR, cabi.MEM_HOST, 124),
+    ("mixed", 6, cabi.OUT_I16_PLANAR, cabi.MEM_DEVICE, 125)])
+def test_prepared_residue_batches_replay_front_stages(ctx, oracle, shape, channels, fmt, floor_mem, seed):
+    """Residue-entry prepared batches in device memory (what a decode server replays step after step): the
+    front stages (k_floor1_curves + k_prologue3: audio.rs:391-555, :991-1039) and the kernels behind them are
+    captured once and replayed with NEW residues and floor posts every step -- from device-resident floor arrays
+    (lwb_batch_io::floor_memory = LWB_MEM_DEVICE, read in place) or host arrays (uploaded again per step).
+    "long": uniform long blocks (front stages + fused kernel); "mixed": 256/2048 sequences incl. the 5.1 coupling
+    chain of BASELINE.json configs[2] (front stages + segmented k_long / k_chain rounds).  Every step is compared
+    with the oracle, which keeps decoding on top of its own state."""
+    rng = np.random.default_rng(seed)
+    bs0, bs1, S, P = 8, 11, 5, 14 if shape == "long" else 26
+    floors, mappings, modes = _random_packet_case(rng, channels, bs0, bs1)
+    if channels == 6:
+        mappings[0]["coupling"] = list(_COUPLING_51)
+    elif channels == 2:
+        mappings[0]["coupling"] = [(1, 0)] if seed % 2 else [(0, 1)]
+    su = make_setup(ctx, channels, bs0, bs1, modes=modes, mappings=mappings, floors=floors)
+    refs = [RefStream(oracle, channels, bs0, bs1, modes, mappings, floors) for _ in range(S)]
+    seqs = []
+    for s in range(S):
+        if shape == "long":
+            bf = np.ones(P, np.uint8)
+        else:
+            bf = (rng.random(P) >= 0.2).astype(np.uint8)
+            bf[0] = bf[-1] = 1                     # decoded repeatedly: the sequence must close on itself
+        prev, nxt = np.ones(P, np.uint8), np.ones(P, np.uint8)
+        for i in range(P):
+            if bf[i]:
+                prev[i] = bf[i - 1] if i else 1
+                nxt[i] = bf[i + 1] if i + 1 < P else 1
+        mode_ids = np.array([int(rng.choice([m for m in range(4) if modes[m][0] == b])) for b in bf], np.uint8)
+        seqs.append((bf, prev, nxt, mode_ids))
+    sizes = [[channels * (1024 if b else 128) for b in seqs[s][0]] for s in range(S)]
+    total = sum(sum(x) for x in sizes)
+    stride = P * 1024
+    f32 = fmt == cabi.OUT_F32_PLANAR
+    pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+    chains, coeff_off = [], 0
+    for s in range(S):
+        chains.append(L.ChainSpec(pwrs[s], seqs[s][3], seqs[s][1], seqs[s][2], coeff_offset=coeff_off, packet_index=s * P,
+                                  out_offset=s * channels * stride, out_stride=stride))
+        coeff_off += sum(sizes[s])
+    d_in = ctx.device_alloc(total * 4)
+    d_out = ctx.device_alloc(S * channels * stride * 4)
+    kinds = np.zeros((S * P, channels), np.uint8)
+    ys = np.zeros((S * P, channels, cabi.MAX_POSTS), np.uint32)
+    if floor_mem == cabi.MEM_DEVICE:
+        d_kinds, d_ys = ctx.device_alloc(kinds.nbytes), ctx.device_alloc(ys.nbytes)
+        batch = L.Batch(ctx, chains, cabi.ENTRY_RESIDUE, cabi.MEM_DEVICE, d_in, d_out, fmt, floor_kind=d_kinds, floor1_y=d_ys,
+                        floor_memory=cabi.MEM_DEVICE)
+    else:
+        batch = L.Batch(ctx, chains, cabi.ENTRY_RESIDUE, cabi.MEM_DEVICE, d_in, d_out, fmt, floor_kind=kinds, floor1_y=ys)
+    counts = []
+    for it in range(4):
+        coeffs, want = [], []
+        for s in range(S):
+            bf, prev, nxt, mode_ids = seqs[s]
+            parts = []
+            for i in range(P):
+                n2 = 1024 if bf[i] else 128
+                res = (rng.standard_normal((channels, n2)) * rng.integers(0, 2, (channels, n2))).astype(np.float32)
+                mp = mappings[modes[mode_ids[i]][1]]
+                fl = []
+                for c in range(channels):
+                    mult, xs = floors[mp["floor_of_channel"][c]]
+                    fl.append(None if rng.random() < 0.1 else random_floor1_y(rng, mult, len(xs)))
+                rc, o = refs[s].packet(int(mode_ids[i]), int(prev[i]), int(nxt[i]), res, fl)
+                assert rc == 0
+                k, y, _ = L.DecodedPacket(int(mode_ids[i]), res, fl).pack()
+                kinds[s * P + i], ys[s * P + i] = k, y
+                parts.append(o)
+                coeffs.append(res.ravel())
+            want.append(np.concatenate(parts, axis=1))
+        ctx.h2d(d_in, np.concatenate(coeffs))
+        if floor_mem == cabi.MEM_DEVICE:
+            ctx.h2d(d_kinds, kinds)
+            ctx.h2d(d_ys, ys)
+        pcm = np.zeros(S * channels * stride, np.float32 if f32 else np.int16)
+        ctx.h2d(d_out, pcm)
+        l0 = ctx.launch_count
+        batch.run()
+        counts.append(ctx.launch_count - l0)
+        ctx.synchronize()
+        ctx.d2h(pcm, d_out)
+        batch.collect()
+        for s in range(S):
+            n = want[s].shape[1]
+            assert chains[s].status == 0 and chains[s].n_samples == n, (it, s, chains[s].status, chains[s].n_samples, n)
+            got = pcm[s * channels * stride:(s + 1) * channels * stride].reshape(channels, stride)[:, :n]
+            if f32:
+                assert bits_equal(got, want[s]), (it, s, mismatch_report(got, want[s]))
+            else:
+                assert np.array_equal(got, oracle.quantise_i16(want[s])), (it, s)
+            assert bits_equal(pwrs[s].data(), refs[s].pwr.data()), (it, s)
+    assert counts[2] == counts[3], counts
+    if shape == "long":
+        assert counts[3] == 3, counts              # k_floor1_curves + k_prologue3 + k_long, nothing else
+    batch.close()
+    ctx.device_free(d_in)
+    ctx.device_free(d_out)
+    if floor_mem == cabi.MEM_DEVICE:
+        ctx.device_free(d_kinds)
+        ctx.device_free(d_ys)
