@@ -120,10 +120,18 @@ LWB_HD void d_floor1_render_segment(const uint16_t *sx, const uint16_t *sy, int 
 }
 
 // ---- chunked closed-form render (k_floor1_curves) -------------------------------------------
-// floor(N / adx) for N = |dy| * (k - x0) < 2^20 by one multiply-high: M = floor((2^32 - 1) / adx) + 1 is exact
-// whenever N * adx < 2^32 (M * adx = 2^32 + e with e < adx, and the error term N * e / (adx * 2^32) stays below
-// 1 / adx), i.e. for every adx <= 4096.  0 = "divide" (adx == 1, or a segment longer than 4096 bins).
-LWB_HD uint32_t d_floor1_magic(int adx) { return (adx < 2 || adx > 4096) ? 0u : 0xFFFFFFFFu / (uint32_t)adx + 1u; }
+// floor(N / adx) for N = |dy| * (k - x0) < 2^20 (|dy| < 2^8, k - x0 < n/2 <= 2^12) by one multiply-high, no
+// division anywhere:  M = floor((2^(32+s) - 1) / adx) + 1,  floor(N / adx) == mulhi(N, M) >> s  whenever
+// N * adx < 2^(32+s)  (M * adx = 2^(32+s) + e with 0 < e <= adx, and the error term N * e / (adx * 2^(32+s)) stays
+// below 1 / adx).  s = 0 covers every adx <= 4096; longer segments (x lists may reach 2^15) take s = 12, where M
+// still fits 32 bits.  adx == 1: the only bin of the segment has N == 0.
+LWB_HD uint32_t d_floor1_magic(int adx, int *shift)
+{
+    *shift = adx > 4096 ? 12 : 0;
+    if (adx < 2) return 1u;
+    const uint64_t one = 1ull << (32 + *shift);
+    return (uint32_t)((one - 1) / (uint64_t)adx + 1);
+}
 
 LWB_HD uint32_t d_mulhi_u32(uint32_t a, uint32_t b)
 {
@@ -134,9 +142,18 @@ LWB_HD uint32_t d_mulhi_u32(uint32_t a, uint32_t b)
 #endif
 }
 
+// Prepares segment j of a row for d_floor1_render16: magic multiplier into sm[j], its shift into the (unused) high
+// byte of sy[j] (curve values are <= 255: posts are clamped to range - 1 and range * multiplier <= 256).
+LWB_HD void d_floor1_prepare_segment(const uint16_t *sx, uint16_t *sy, uint32_t *sm, int j)
+{
+    int sh;
+    sm[j] = d_floor1_magic((int)sx[j + 1] - (int)sx[j], &sh);
+    sy[j] = (uint16_t)((sy[j] & 255u) | ((uint32_t)sh << 8));
+}
+
 // 16 consecutive bins [k0, k0 + 16) of the rendered curve (k0 + 16 <= n2 <= last sx), one byte each, as four
 // little-endian words: the closed form of render_line (audio.rs:503-524) per bin, segment found once per chunk
-// and advanced when a bin reaches the next flagged post.  sm[j] = d_floor1_magic(sx[j + 1] - sx[j]).
+// and advanced when a bin reaches the next flagged post.  Segments prepared by d_floor1_prepare_segment.
 LWB_HD void d_floor1_render16(const uint16_t *sx, const uint16_t *sy, const uint32_t *sm, int m, int k0, uint32_t out[4])
 {
     int lo = 0, hi = m - 1;                  // sx[lo] <= k0 < sx[hi]
@@ -144,23 +161,31 @@ LWB_HD void d_floor1_render16(const uint16_t *sx, const uint16_t *sy, const uint
         const int mid = (lo + hi) >> 1;
         if ((int)sx[mid] <= k0) lo = mid; else hi = mid;
     }
-    int x0 = sx[lo], x1 = sx[lo + 1], y0 = sy[lo];
-    int dy = (int)sy[lo + 1] - y0;
+    int x1 = sx[lo + 1], y0 = sy[lo] & 255, sh = sy[lo] >> 8;
+    int dy = (int)(sy[lo + 1] & 255) - y0;
     uint32_t mg = sm[lo];
-    out[0] = out[1] = out[2] = out[3] = 0u;
+    uint32_t ady = (uint32_t)(dy < 0 ? -dy : dy);
+    int sgn = dy < 0 ? -1 : 1;
+    uint32_t nn = ady * (uint32_t)(k0 - (int)sx[lo]);
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const int k = k0 + i;
-        if (k >= x1) {                       // posts are strictly increasing in x: one step is enough
-            lo++;
-            x0 = x1; x1 = sx[lo + 1]; y0 = sy[lo];
-            dy = (int)sy[lo + 1] - y0;
-            mg = sm[lo];
+    for (int w = 0; w < 4; w++) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            if (k0 + 4 * w + b >= x1) {      // posts are strictly increasing in x: one step is enough
+                lo++;
+                x1 = sx[lo + 1]; y0 = sy[lo] & 255; sh = sy[lo] >> 8;
+                dy = (int)(sy[lo + 1] & 255) - y0;
+                mg = sm[lo];
+                ady = (uint32_t)(dy < 0 ? -dy : dy);
+                sgn = dy < 0 ? -1 : 1;
+                nn = 0;
+            }
+            const int y = y0 + sgn * (int)(d_mulhi_u32(nn, mg) >> sh);      // 0 <= y <= 255
+            word |= (uint32_t)y << (8 * b);
+            nn += ady;
         }
-        const uint32_t nn = (uint32_t)(dy < 0 ? -dy : dy) * (uint32_t)(k - x0);
-        const int off = (int)(mg ? d_mulhi_u32(nn, mg) : nn / (uint32_t)(x1 - x0));
-        const int y = dy < 0 ? y0 - off : y0 + off;
-        out[i >> 2] |= ((uint32_t)y & 255u) << (8 * (i & 3));
+        out[w] = word;
     }
 }
 

@@ -59,7 +59,7 @@ k_floor1_curves(const DevPacket *__restrict__ pkts, uint32_t n_rows, int C, cons
     __syncthreads();
     for (int i = tid; i < kCurveRows * kCurveSeg; i += kCurveThreads) {
         const int r = i / kCurveSeg, j = i - r * kCurveSeg;
-        if (j + 1 < s_m[r]) s_mg[r][j] = d_floor1_magic((int)s_x[r][j + 1] - (int)s_x[r][j]);
+        if (j + 1 < s_m[r]) d_floor1_prepare_segment(s_x[r], s_y[r], s_mg[r], j);
     }
     __syncthreads();
     const int w = tid >> 5, lane = tid & 31;
@@ -83,7 +83,8 @@ k_floor1_curves(const DevPacket *__restrict__ pkts, uint32_t n_rows, int C, cons
 }
 
 constexpr int kPro3Threads = 256;
-inline size_t prologue3_smem(int channels) { return channels > 2 ? (size_t)channels * kPro3Threads * sizeof(float4) : 0; }
+// (two channels with more than one coupling step take the general path too, so they get the staging as well)
+inline size_t prologue3_smem(int channels) { return channels > 1 ? (size_t)channels * kPro3Threads * sizeof(float4) : 0; }
 
 __device__ __forceinline__ float4 d_floor_quad(int kind, const float *__restrict__ s_db, const uint8_t *__restrict__ curve,
                                                const float *__restrict__ dense, uint64_t e)
@@ -96,67 +97,70 @@ __device__ __forceinline__ float4 d_floor_quad(int kind, const float *__restrict
     return make_float4(0.f, 0.f, 0.f, 0.f);                       // audio.rs:1021-1024
 }
 
-// grid = packets.  Requires every coeff_off (and the arena bases) to be multiples of 4 elements.
+// Persistent CTAs striding over the packets (grid = min(packets, a few CTAs per SM)).  Requires every coeff_off
+// (and the arena bases) to be multiples of 4 elements.
 __global__ void __launch_bounds__(kPro3Threads)
-k_prologue3(const DevPacket *__restrict__ pkts, const float *__restrict__ residue, const float *__restrict__ dense_floor,
+k_prologue3(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float *__restrict__ residue, const float *__restrict__ dense_floor,
             const uint8_t *__restrict__ floor_kind, const uint8_t *__restrict__ curve, float *__restrict__ spec)
 {
-    extern __shared__ float4 s_r[];                      // [C][kPro3Threads] when C > 2
+    extern __shared__ float4 s_r[];                      // [C][kPro3Threads] when C > 1
     __shared__ float s_db[256];
-    const DevPacket &p = pkts[blockIdx.x];
-    const DevSetup &su = *p.setup;
-    const DevMapping &mp = su.mappings[p.mapping];
-    const int C = p.channels, n2 = p.n >> 1, nsteps = mp.n_coupling;
     const int tid = threadIdx.x;
     s_db[tid] = c_inverse_db[tid];
     __syncthreads();
-    const uint8_t *kinds = floor_kind + p.pkt_index * C;
-    const uint64_t base = p.coeff_off;
-    if (C <= 2 && nsteps <= 1) {
-        const int k0 = kinds[0], k1 = C == 2 ? kinds[1] : LWB_FLOOR_UNUSED;
-        const bool swapped = nsteps == 1 && mp.mag[0] == 1;          // (magnitude, angle) = (1, 0)
-        for (int q = tid; q < (n2 >> 2); q += kPro3Threads) {
-            const uint64_t e0 = base + 4 * (uint64_t)q, e1 = e0 + n2;
-            float4 r0 = *reinterpret_cast<const float4 *>(residue + e0);
-            float4 r1 = C == 2 ? *reinterpret_cast<const float4 *>(residue + e1) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (nsteps == 1) {
-                if (swapped) {
-                    d_inverse_couple(r1.x, r0.x); d_inverse_couple(r1.y, r0.y);
-                    d_inverse_couple(r1.z, r0.z); d_inverse_couple(r1.w, r0.w);
-                } else {
-                    d_inverse_couple(r0.x, r1.x); d_inverse_couple(r0.y, r1.y);
-                    d_inverse_couple(r0.z, r1.z); d_inverse_couple(r0.w, r1.w);
+    for (uint32_t pk = blockIdx.x; pk < n_pk; pk += gridDim.x) {
+        const DevPacket &p = pkts[pk];
+        const DevSetup &su = *p.setup;
+        const DevMapping &mp = su.mappings[p.mapping];
+        const int C = p.channels, n2 = p.n >> 1, nsteps = mp.n_coupling;
+        const uint8_t *kinds = floor_kind + p.pkt_index * C;
+        const uint64_t base = p.coeff_off;
+        if (C <= 2 && nsteps <= 1) {
+            const int k0 = kinds[0], k1 = C == 2 ? kinds[1] : LWB_FLOOR_UNUSED;
+            const bool swapped = nsteps == 1 && mp.mag[0] == 1;          // (magnitude, angle) = (1, 0)
+            for (int q = tid; q < (n2 >> 2); q += kPro3Threads) {
+                const uint64_t e0 = base + 4 * (uint64_t)q, e1 = e0 + n2;
+                float4 r0 = *reinterpret_cast<const float4 *>(residue + e0);
+                float4 r1 = C == 2 ? *reinterpret_cast<const float4 *>(residue + e1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (nsteps == 1) {
+                    if (swapped) {
+                        d_inverse_couple(r1.x, r0.x); d_inverse_couple(r1.y, r0.y);
+                        d_inverse_couple(r1.z, r0.z); d_inverse_couple(r1.w, r0.w);
+                    } else {
+                        d_inverse_couple(r0.x, r1.x); d_inverse_couple(r0.y, r1.y);
+                        d_inverse_couple(r0.z, r1.z); d_inverse_couple(r0.w, r1.w);
+                    }
+                }
+                const float4 f0 = d_floor_quad(k0, s_db, curve, dense_floor, e0);
+                *reinterpret_cast<float4 *>(spec + e0) =
+                    make_float4(__fmul_rn(f0.x, r0.x), __fmul_rn(f0.y, r0.y), __fmul_rn(f0.z, r0.z), __fmul_rn(f0.w, r0.w));
+                if (C == 2) {
+                    const float4 f1 = d_floor_quad(k1, s_db, curve, dense_floor, e1);
+                    *reinterpret_cast<float4 *>(spec + e1) =
+                        make_float4(__fmul_rn(f1.x, r1.x), __fmul_rn(f1.y, r1.y), __fmul_rn(f1.z, r1.z), __fmul_rn(f1.w, r1.w));
                 }
             }
-            const float4 f0 = d_floor_quad(k0, s_db, curve, dense_floor, e0);
-            *reinterpret_cast<float4 *>(spec + e0) =
-                make_float4(__fmul_rn(f0.x, r0.x), __fmul_rn(f0.y, r0.y), __fmul_rn(f0.z, r0.z), __fmul_rn(f0.w, r0.w));
-            if (C == 2) {
-                const float4 f1 = d_floor_quad(k1, s_db, curve, dense_floor, e1);
-                *reinterpret_cast<float4 *>(spec + e1) =
-                    make_float4(__fmul_rn(f1.x, r1.x), __fmul_rn(f1.y, r1.y), __fmul_rn(f1.z, r1.z), __fmul_rn(f1.w, r1.w));
+            continue;
+        }
+        // general case: the thread's quads of all channels sit in shared memory (dynamic channel indices of the
+        // coupling steps without predicated register arrays); every thread touches only its own column
+        for (int q = tid; q < (n2 >> 2); q += kPro3Threads) {
+            const uint64_t e = base + 4 * (uint64_t)q;
+            for (int c = 0; c < C; c++) s_r[c * kPro3Threads + tid] = *reinterpret_cast<const float4 *>(residue + e + (uint64_t)c * n2);
+            for (int s = nsteps - 1; s >= 0; s--) {                      // audio.rs:991-1002
+                float4 m4 = s_r[mp.mag[s] * kPro3Threads + tid], a4 = s_r[mp.ang[s] * kPro3Threads + tid];
+                d_inverse_couple(m4.x, a4.x); d_inverse_couple(m4.y, a4.y);
+                d_inverse_couple(m4.z, a4.z); d_inverse_couple(m4.w, a4.w);
+                s_r[mp.mag[s] * kPro3Threads + tid] = m4;
+                s_r[mp.ang[s] * kPro3Threads + tid] = a4;
             }
-        }
-        return;
-    }
-    // general case: the thread's quads of all channels sit in shared memory (dynamic channel indices of the
-    // coupling steps without predicated register arrays); every thread touches only its own column
-    for (int q = tid; q < (n2 >> 2); q += kPro3Threads) {
-        const uint64_t e = base + 4 * (uint64_t)q;
-        for (int c = 0; c < C; c++) s_r[c * kPro3Threads + tid] = *reinterpret_cast<const float4 *>(residue + e + (uint64_t)c * n2);
-        for (int s = nsteps - 1; s >= 0; s--) {                      // audio.rs:991-1002
-            float4 m4 = s_r[mp.mag[s] * kPro3Threads + tid], a4 = s_r[mp.ang[s] * kPro3Threads + tid];
-            d_inverse_couple(m4.x, a4.x); d_inverse_couple(m4.y, a4.y);
-            d_inverse_couple(m4.z, a4.z); d_inverse_couple(m4.w, a4.w);
-            s_r[mp.mag[s] * kPro3Threads + tid] = m4;
-            s_r[mp.ang[s] * kPro3Threads + tid] = a4;
-        }
-        for (int c = 0; c < C; c++) {
-            const uint64_t ec = e + (uint64_t)c * n2;
-            const float4 r = s_r[c * kPro3Threads + tid];
-            const float4 f = d_floor_quad(kinds[c], s_db, curve, dense_floor, ec);
-            *reinterpret_cast<float4 *>(spec + ec) =
-                make_float4(__fmul_rn(f.x, r.x), __fmul_rn(f.y, r.y), __fmul_rn(f.z, r.z), __fmul_rn(f.w, r.w));
+            for (int c = 0; c < C; c++) {
+                const uint64_t ec = e + (uint64_t)c * n2;
+                const float4 r = s_r[c * kPro3Threads + tid];
+                const float4 f = d_floor_quad(kinds[c], s_db, curve, dense_floor, ec);
+                *reinterpret_cast<float4 *>(spec + ec) =
+                    make_float4(__fmul_rn(f.x, r.x), __fmul_rn(f.y, r.y), __fmul_rn(f.z, r.z), __fmul_rn(f.w, r.w));
+            }
         }
     }
 }

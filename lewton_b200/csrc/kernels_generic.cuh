@@ -27,17 +27,16 @@ __constant__ float c_inverse_db[256] = {
 #include "floor1_inverse_db.inc"
 };
 
-// audio.rs:762-777
+// audio.rs:762-777, branch-free.  With s = (a > 0), t = (m > 0) (both false for NaN, like the reference's `> 0.`):
+//   v = m + (t == s ? -a : a)   -- m - a and m + (-a) are the same IEEE operation --
+//   s: (m, a) <- (m, v);  !s: (m, a) <- (v, m)
 __device__ __forceinline__ void d_inverse_couple(float &m, float &a)
 {
     const float m0 = m, a0 = a;
-    if (m0 > 0.f) {
-        if (a0 > 0.f) { a = __fsub_rn(m0, a0); }
-        else { a = m0; m = __fadd_rn(m0, a0); }
-    } else {
-        if (a0 > 0.f) { a = __fadd_rn(m0, a0); }
-        else { a = m0; m = __fsub_rn(m0, a0); }
-    }
+    const bool s = a0 > 0.f, t = m0 > 0.f;
+    const float v = __fadd_rn(m0, (t == s) ? -a0 : a0);
+    m = s ? m0 : v;
+    a = s ? v : m0;
 }
 
 constexpr int kPrologueThreads = 256;

@@ -112,8 +112,9 @@ static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, size_t n_pk, uns
     const uint32_t rows = (uint32_t)(n_pk * C);
     int rc = launch(ctx, k_floor1_curves, dim3((rows + kCurveRows - 1) / kCurveRows), dim3(kCurveThreads), 0, d_pk, rows, (int)C, kinds, ys, curve);
     if (rc) return rc;
-    return launch(ctx, k_prologue3, dim3((unsigned)n_pk), dim3(kPro3Threads), prologue3_smem((int)C), d_pk, res, dense, kinds,
-                  (const uint8_t *)curve, spec);
+    const size_t grid = std::min<size_t>(n_pk, (size_t)ctx->sm_count * 8);
+    return launch(ctx, k_prologue3, dim3((unsigned)grid), dim3(kPro3Threads), prologue3_smem((int)C), d_pk, (uint32_t)n_pk, res, dense,
+                  kinds, (const uint8_t *)curve, spec);
 }
 static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, const DevPacket *h_pk, size_t n_pk, unsigned C, size_t smem_old,
                            const float *res, const float *dense, const uint8_t *kinds, const uint32_t *ys, float *spec, uint8_t *curve)

