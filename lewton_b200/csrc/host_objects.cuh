@@ -19,6 +19,14 @@ struct Staging {
     bool pending = false;
 };
 
+// CachedBlocksizeDerived (header_cached.rs:27-31) on the device, shared by all setups of a context with the same tables
+struct CachedTables {
+    DevTables dt;                  // device pointers; dt.pack = the fused kernels' twiddle pack (bs 11: k_long, bs 8: k_short)
+    std::vector<float> a, b, c, w; // host copies: the cache key
+    std::vector<uint32_t> br;
+    std::vector<void *> allocs;
+};
+
 struct lwb_ctx {
     int device = 0;
     int sm_count = 0;
@@ -35,6 +43,7 @@ struct lwb_ctx {
     uint64_t state_gen = 1;        // bumped whenever any stream's (has, len) changes: plans key on it
     std::string err;
     uint64_t launches = 0;
+    std::deque<CachedTables> tables;       // (deque: setups hold copies of dt, growth never moves an entry)
     // grow-only device arenas
     DevBuf coeffs, dense, pcm, spec, curve, x, desc, kinds, ys, chains, ticket, cdesc, cbytes;
     Staging stage[3];              // ring: a batch's descriptors are written while the previous copies may still run
@@ -56,10 +65,10 @@ struct lwb_setup {
     std::vector<DevMapping> mappings;   // host copy (validation)
 };
 
-struct MixRound { size_t r0, nr, c0, nc; };
+struct MixRound { size_t r0, nr, s0, ns, c0, nc; };       // LongRun / ShortRun / ChainDesc ranges of one round
 struct MixLaunch {
-    char *db; size_t off_cd, off_by;
-    const float *pack, *w_short; int ls; bool i16, residue; int out_format; unsigned warps; size_t smem; int n1max, wpc, np;
+    char *db; size_t off_sr, off_cd, off_by;
+    const float *pack, *spack, *w_short; int ls; bool i16, residue; int out_format; unsigned warps; size_t smem; int n1max, wpc, np;
     const float *coeffs, *dense; const uint8_t *kinds; const uint32_t *ys; void *pcm;
 };
 

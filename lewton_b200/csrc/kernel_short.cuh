@@ -1,0 +1,427 @@
+// kernel_short.cuh -- fused IMDCT + window + overlap-add for runs of consecutive SHORT blocks of
+// n = 256 (blocksize_0 = 8, the short block of every 44.1 / 48 kHz Vorbis stream): the register-resident
+// counterpart of kernel_long.cuh for the 6-bit index space.
+//
+// A 256-point block has 64 complex values z_c = U[2c+1] + i U[2c]; a warp holds 512, so it transforms
+// EIGHT consecutive packets of one channel (an "octet") in lockstep: lane = 4 b + l, block b = lane >> 2,
+// and the 4 lanes of a block hold its 64 values as 2 groups x 8 slots, exactly the per-lane shape of the
+// long kernel.  The step-3 stages are a radix-2 DIF FFT over the 6 bits of c: step 2 flips bit 5, stages
+// 0 and 1 flip bits 4 and 3, ld654 covers bits 2, 1, 0 (imdct.rs:385-484), so there are only two phases:
+//     phase A: slot = bits 5,4,3  -> step 0, step 2, stages 0, 1              (imdct.rs:337-452)
+//     phase C: slot = bits 2,1,0  -> ld654, bit-reverse (renaming), step 7, step 8, window / OLA
+// with ONE shared-memory transpose in between (conflict-free for the eight blocks together).  Everything
+// else follows the long kernel: the reference's rounding DAG operation for operation, packed
+// add/sub/mul.rn.f32x2 on (group a, group b) pairs with scalar adds where an operand is a product
+// (no FMA contraction), twiddles from a per-lane pack, spectrum tiles by 1-D TMA into a per-warp ring.
+// Eight consecutive packets are 1024 consecutive PCM samples: block b's previous right half (the only
+// inter-packet state, audio.rs:847-861) is block b-1's p_even, fetched from the neighbouring lanes by
+// shuffle; block 0 takes it from the previous octet (registers) or the stream state (first octet).
+//
+// The lane functions compile for the host too: tests/emu/short_emu.cpp runs the 32 lanes sequentially
+// against the oracle (index maps, swizzle, twiddle pack, bank conflicts) without a GPU.
+#pragma once
+#include "kernel_long.cuh"
+
+namespace lwb {
+
+constexpr int kShortBs = 8;
+constexpr int kShortN = 256;
+constexpr int kShortN2 = 128;
+constexpr int kShortOct = 8;               // blocks a warp transforms together
+
+struct alignas(16) ShortRun {              // 48 bytes
+    const float *in;        // first packet's spectrum (128 floats); next packet at +in_stride
+    void *out;              // first emitted packet's PCM (f32 or i16 elements); next at +128
+    float *state;           // stream state row of this channel (>= 128 floats)
+    uint32_t in_stride;
+    uint32_t n_packets;     // including a primer packet (has_prev == 0: packet 0 emits nothing)
+    uint8_t has_prev;       // 1: packet 0 overlaps with state[0..128)
+    uint8_t write_state;    // 1: store the last packet's right half to state[0..128)
+    uint8_t pad[14];
+};
+static_assert(sizeof(ShortRun) == 48, "ShortRun layout");
+
+// the short pack = kernel_long's pack layout without its phase-B slots
+constexpr int kSpShift = P_B_END - P_A_END;
+LWB_HD constexpr int sp_of(int slot) { return slot < P_A_END ? slot : slot - kSpShift; }
+constexpr int SP_END = P_END - kSpShift;                       // 71
+constexpr int kShortPackFloats = SP_END * 32 * 2;
+
+// Which complex element of its block sits in (l, slot, half), l = lane & 3
+LWB_HD int elemA_s(int l, int slot, int half) { return (half ? 7 - l : l) + 8 * slot; }
+LWB_HD int elemC_s(int l, int slot, int half)
+{
+    const int T = half ? 7 - rev3(l) : rev3(l);
+    return 8 * T + slot;
+}
+// output index m (0..63) of (l, slot, half) AFTER the step-7 half swap of even slots
+LWB_HD int outIndex_s(int l, int slot, int half)
+{
+    const int flip = (slot & 1) ? half : !half;
+    return 8 * rev3(slot) + (flip ? 7 - l : l);
+}
+// word index of complex element c of block b inside a 512-word transpose plane: bank = 4 b + (c1c0 ^ c5c4),
+// distinct over the 32 lanes both when they vary (b, c1c0) -- phase A stores -- and (b, c5c4) -- phase C loads
+LWB_HD int swzS(int b, int c) { return ((c >> 2) << 5) | (b << 2) | ((c & 3) ^ ((c >> 4) & 3)); }
+
+// Host: per-lane pack from the blocksize-8 tables (a, b: 128; c: 64; w: 128).  Only l = lane & 3 matters.
+inline void short_build_pack(const float *a, const float *b, const float *c, const float *w, float *pack)
+{
+    V *P = reinterpret_cast<V *>(pack);
+    for (int lane = 0; lane < 32; lane++) {
+        const int l = lane & 3;
+        auto put = [&](int slot, float x, float y) { P[sp_of(slot) * 32 + lane] = V{x, y}; };
+        float tx[2], ty[2];
+        for (int j = 0; j < 8; j++) {                          // step 0 (imdct.rs:337-371)
+            for (int h = 0; h < 2; h++) {
+                const int cc = elemA_s(l, j, h);
+                const float s = cc < 32 ? -1.0f : 1.0f;        // (-x)*A == x*(-A)
+                tx[h] = s * a[126 - 2 * cc];
+                ty[h] = s * a[127 - 2 * cc];
+            }
+            put(P_S0W0 + j, tx[0], tx[1]);
+            put(P_S0W1 + j, ty[0], ty[1]);
+        }
+        for (int j = 0; j < 4; j++) {                          // step 2 (imdct.rs:385-430)
+            for (int h = 0; h < 2; h++) {
+                const int cc = elemA_s(l, j, h);
+                tx[h] = a[124 - 4 * cc];
+                ty[h] = a[125 - 4 * cc];
+            }
+            put(P_S2W0 + j, tx[0], tx[1]);
+            put(P_S2W1 + j, ty[0], ty[1]);
+        }
+        for (int u = 0; u < 2; u++) {                          // stage 0: a = r * 8, r < n >> 4
+            for (int h = 0; h < 2; h++) {
+                const int r = (~elemA_s(l, 2 + u, h)) & 15;
+                tx[h] = a[8 * r];
+                ty[h] = a[8 * r + 1];
+            }
+            put(P_L0W0 + u, tx[0], tx[1]);
+            put(P_L0W1 + u, ty[0], ty[1]);
+        }
+        for (int h = 0; h < 2; h++) {                          // stage 1: a = r * 16, r < n >> 5
+            const int r = (~elemA_s(l, 1, h)) & 7;
+            tx[h] = a[16 * r];
+            ty[h] = a[16 * r + 1];
+        }
+        put(P_L1W0, tx[0], tx[1]);
+        put(P_L1W1, ty[0], ty[1]);
+        put(P_A2, a[kShortN >> 3], a[kShortN >> 3]);
+        for (int jj = 0; jj < 4; jj++) {                       // step 7 (imdct.rs:533-580)
+            for (int h = 0; h < 2; h++) {
+                const int p = 63 - rev6(elemC_s(l, 2 * jj + 1, h));
+                tx[h] = c[2 * p];
+                ty[h] = c[2 * p + 1];
+            }
+            put(P_S7C0 + jj, tx[0], tx[1]);
+            put(P_S7C1 + jj, ty[0], ty[1]);
+        }
+        for (int j = 0; j < 8; j++) {                          // step 8 + window
+            float b0[2], b1[2], wl[2], wh[2];
+            for (int h = 0; h < 2; h++) {
+                const int m = outIndex_s(l, j, h);
+                const int cp = 63 - m;
+                b0[h] = b[2 * cp];
+                b1[h] = b[2 * cp + 1];
+                wl[h] = w[m];
+                wh[h] = w[127 - m];
+            }
+            put(P_B0 + j, b0[0], b0[1]);
+            put(P_B1 + j, b1[0], b1[1]);
+            put(P_WLO + j, wl[0], wl[1]);
+            put(P_WHI + j, wh[0], wh[1]);
+        }
+    }
+}
+
+// Phase A for one block.  tile = the block's 128 spectrum floats.  Quad #f yields element c = f from
+// (q1, q3) and c = 63 - f from (q0, q2); the lane reads quads #(l + 8 m) and #(7 - l + 8 m), m < 4: they
+// feed slots m and 7 - m of both groups.  Then step 2 (bit 5), stage 0 (bit 4), stage 1 (bit 3).
+template <class TW>
+LWB_HD void phase_a_s(const float *tile, int l, TW tw, V O[8], V E[8])
+{
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const Q4 f1 = ld_q4(tile + 4 * (l + 8 * m));
+        const Q4 f2 = ld_q4(tile + 4 * (7 - l + 8 * m));
+        {
+            const V w0 = tw(P_S0W0 + m), w1 = tw(P_S0W1 + m);
+            const V qa = V{f1.w, f2.w}, qb = V{f1.y, f2.y};
+            O[m] = vsub_p(vmul(qa, w0), vmul(qb, w1));
+            E[m] = vadd_p(vmul(qa, w1), vmul(qb, w0));
+        }
+        {
+            const int j = 7 - m;
+            const V w0 = tw(P_S0W0 + j), w1 = tw(P_S0W1 + j);
+            const V qa = V{f2.x, f1.x}, qb = V{f2.z, f1.z};
+            O[j] = vsub_p(vmul(qa, w0), vmul(qb, w1));
+            E[j] = vadd_p(vmul(qa, w1), vmul(qb, w0));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) bfly(O[j + 4], E[j + 4], O[j], E[j], tw(P_S2W0 + j), tw(P_S2W1 + j));
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const V w0 = tw(P_L0W0 + u), w1 = tw(P_L0W1 + u);
+        bfly(O[2 + u], E[2 + u], O[u], E[u], w0, w1);
+        bfly(O[6 + u], E[6 + u], O[4 + u], E[4 + u], w0, w1);
+    }
+    {
+        const V w0 = tw(P_L1W0), w1 = tw(P_L1W1);
+#pragma unroll
+        for (int j = 1; j < 8; j += 2) bfly(O[j], E[j], O[j - 1], E[j - 1], w0, w1);
+    }
+}
+
+// step 8 for one slot (imdct.rs:589-658):  p_odd = x[m] = -x[127-m],  p_even = x[128+m] = x[255-m]
+LWB_HD void step8_s(V b0, V b1, V Oj, V Ej, V &p_odd, V &p_even)
+{
+    p_odd = vsub_p(vmul(Oj, b1), vmul(Ej, b0));
+    p_even = vnsub_p(vmul(Oj, b0), vmul(Ej, b1));
+}
+// window / overlap-add (audio.rs:1112-1118):  pcm[m] = x[m] w[m] + prev[m] w[127-m],
+// pcm[127-m] = (-p_odd) w[127-m] + prev[127-m] w[m]
+LWB_HD void ola_s(V p_odd, V wlo, V whi, V prev_lo, V prev_hi, V &pcm_lo, V &pcm_hi)
+{
+    pcm_lo = vadd_p(vmul(p_odd, wlo), vmul(prev_lo, whi));
+    pcm_hi = vsub_p(vmul(prev_hi, wlo), vmul(p_odd, whi));
+}
+
+#if defined(__CUDACC__)
+#ifndef LWB_SHORT_WARPS
+#define LWB_SHORT_WARPS 8
+#endif
+#ifndef LWB_SHORT_RING
+#define LWB_SHORT_RING 3
+#endif
+// short-pack slots [kSTwReg0, kSTwReg1) live in registers for the whole kernel
+#ifndef LWB_STW_REG0
+#define LWB_STW_REG0 0
+#endif
+#ifndef LWB_STW_REG1
+#define LWB_STW_REG1 30
+#endif
+constexpr int kShortWarps = LWB_SHORT_WARPS;
+constexpr int kShortRing = LWB_SHORT_RING;
+constexpr int kSTwReg0 = LWB_STW_REG0, kSTwReg1 = LWB_STW_REG1;
+constexpr int kShortTileStride = 576;                         // bytes between the blocks' tiles of a stage: 512 + 64,
+                                                              // so that the LDS.128 of a quarter warp (2 blocks x 4 lanes) hit 8 bank groups
+constexpr int kShortStateOff = kShortOct * kShortTileStride;  // 4608: the run's state row (first octet of a run with history)
+constexpr int kShortStageBytes = kShortStateOff + kShortN2 * 4;   // 5120; the first 4096 bytes double as the transpose scratch
+constexpr int kShortDescSlots = kShortRing + 1;               // run descriptors the producer may be ahead of the consumer
+constexpr size_t kShortSmemBytes = 128 + (size_t)kShortWarps * kShortRing * kShortStageBytes + (size_t)kShortPackFloats * 4 +
+                                   (size_t)kShortWarps * kShortDescSlots * sizeof(ShortRun) + kShortWarps * kShortRing * 8 + 64;
+
+struct TwShort {
+    const V *r;                   // registers: short-pack slots [kSTwReg0, kSTwReg1)
+    const V *lane_base;           // &pack[lane] in shared memory
+    __device__ __forceinline__ V operator()(int slot) const
+    {
+        const int s = sp_of(slot);
+        return (s >= kSTwReg0 && s < kSTwReg1) ? r[s - kSTwReg0] : lane_base[s * 32];
+    }
+};
+
+// runs: one descriptor per run; pack: short_build_pack of the setup's blocksize-8 tables.
+//
+// Runs are dealt to the warps round robin (run r -> warp r mod W): short-block runs are short -- a burst between
+// long blocks is one octet -- so the per-run latencies (descriptor, state row, first tiles) must overlap with the
+// previous runs' arithmetic.  With a static deal every warp knows its future: it PRODUCES a stream of octets
+// (TMA copies of up to eight 512-byte spectrum blocks, plus the 512-byte state row in front of a run with history,
+// all counted on the stage's mbarrier) up to kShortRing stages ahead of where it CONSUMES them, across run
+// boundaries; the descriptor of the run after the one being produced is already on its way into registers.
+template <typename OutT>
+__global__ void __launch_bounds__(kShortWarps * 32, 1)
+k_short(const ShortRun *__restrict__ runs, uint32_t n_runs, const float *__restrict__ pack)
+{
+    extern __shared__ __align__(128) unsigned char smem_s[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = lane & 3, blk = lane >> 2;
+    const uint32_t raw_s = smem_u32(smem_s);
+    unsigned char *base = smem_s + ((128u - (raw_s & 127u)) & 127u);
+    constexpr size_t kRingBytes = (size_t)kShortWarps * kShortRing * kShortStageBytes;
+    unsigned char *ring = base + (size_t)warp * kShortRing * kShortStageBytes;
+    V *s_pack = reinterpret_cast<V *>(base + kRingBytes);
+    uint4 *s_desc = reinterpret_cast<uint4 *>(base + kRingBytes + (size_t)kShortPackFloats * 4) + warp * kShortDescSlots * 3;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + kRingBytes + (size_t)kShortPackFloats * 4 +
+                                                  (size_t)kShortWarps * kShortDescSlots * sizeof(ShortRun)) + warp * kShortRing;
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(pack);
+        float4 *dst = reinterpret_cast<float4 *>(s_pack);
+        for (int i = threadIdx.x; i < kShortPackFloats / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (lane == 0) {
+        for (int i = 0; i < kShortRing; i++) mbar_init(smem_u32(&bars[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    V twR[kSTwReg1 - kSTwReg0 > 0 ? kSTwReg1 - kSTwReg0 : 1];
+#pragma unroll
+    for (int s = kSTwReg0; s < kSTwReg1; s++) twR[s - kSTwReg0] = s_pack[s * 32 + lane];
+    const TwShort tw{twR, s_pack + lane};
+
+    const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars);
+    // Transpose addresses (bytes inside the stage; E plane at +0, O plane at +2048).  4 * swzS(b, c) splits into a
+    // lane part, an additive slot part (an immediate of the access) and a slot part XORed into bits 2..3 -- the stage
+    // bases are 16-byte aligned, so that XOR can be applied to the full address:
+    //   phase A, c = cl + 8 j:   lane part 4 * swzS(b, cl),   + (j << 8),         ^ 4 * (j >> 1)
+    //   phase C, c = 8 T + j:    lane part 4 * swzS(b, 8 T),  + ((j >> 2) << 7),  ^ 4 * (j & 3)
+    const uint32_t wA0 = 4u * (uint32_t)swzS(blk, elemA_s(l, 0, 0)), wA1 = 4u * (uint32_t)swzS(blk, elemA_s(l, 0, 1));
+    const uint32_t wC0 = 4u * (uint32_t)swzS(blk, elemC_s(l, 0, 0)), wC1 = 4u * (uint32_t)swzS(blk, elemC_s(l, 0, 1));
+
+    const uint32_t W = gridDim.x * kShortWarps, gw = blockIdx.x * kShortWarps + warp;
+    if (gw >= n_runs) return;
+    // ---- producer state (warp-uniform) ----
+    uint32_t p_run = gw, p_oct = 0, p_slot = 0, p_stage = 0, in_flight = 0;
+    const uint4 *rq = reinterpret_cast<const uint4 *>(runs);
+    uint4 pd0 = __ldg(rq + 3 * (size_t)p_run), pd1 = __ldg(rq + 3 * (size_t)p_run + 1), pd2 = __ldg(rq + 3 * (size_t)p_run + 2);
+    uint4 nd0 = pd0, nd1 = pd1, nd2 = pd2;                 // descriptor of run p_run + W, loaded one run ahead
+    if (p_run + W < n_runs) {
+        nd0 = __ldg(rq + 3 * (size_t)(p_run + W)); nd1 = __ldg(rq + 3 * (size_t)(p_run + W) + 1); nd2 = __ldg(rq + 3 * (size_t)(p_run + W) + 2);
+    }
+    if (lane == 0) { s_desc[0] = pd0; s_desc[1] = pd1; s_desc[2] = pd2; }
+    __syncwarp();
+    // ShortRun fields inside the three quads: q0 = {in, out}, q1 = {state, in_stride, n_packets}, q2 = {has_prev | write_state << 8, ...}
+    auto produce = [&]() {                                   // whole warp: issue the next octet of the producer's run
+        const float *in = reinterpret_cast<const float *>(((unsigned long long)pd0.y << 32) | pd0.x);
+        const float *state = reinterpret_cast<const float *>(((unsigned long long)pd1.y << 32) | pd1.x);
+        const uint32_t in_stride = pd1.z, npk = pd1.w;
+        const bool with_state = p_oct == 0 && (pd2.x & 0xffu);
+        const uint32_t nb = min((uint32_t)kShortOct, npk - p_oct * kShortOct);
+        const uint32_t bar = bars_s + 8 * p_stage, dst = ring_s + p_stage * kShortStageBytes;
+        if (lane == 0) mbar_expect_tx(bar, (nb + (with_state ? 1u : 0u)) * (uint32_t)(kShortN2 * 4));
+        __syncwarp();
+        if ((uint32_t)lane < nb) {
+            fence_proxy_async();            // the stage was written through the generic proxy (transpose) before
+            tma_load_1d(dst + lane * kShortTileStride, in + (size_t)(p_oct * kShortOct + lane) * in_stride, kShortN2 * 4, bar);
+        } else if (lane == 8 && with_state) {
+            fence_proxy_async();
+            tma_load_1d(dst + kShortStateOff, state, kShortN2 * 4, bar);
+        }
+        p_stage = (p_stage + 1 == (uint32_t)kShortRing) ? 0 : p_stage + 1;
+        in_flight++;
+        if (++p_oct * kShortOct >= npk) {                    // on to the next run of this warp
+            p_run += W;
+            p_oct = 0;
+            pd0 = nd0; pd1 = nd1; pd2 = nd2;
+            if (p_run < n_runs) {
+                p_slot = (p_slot + 1 == (uint32_t)kShortDescSlots) ? 0 : p_slot + 1;
+                if (lane == 0) { s_desc[3 * p_slot] = pd0; s_desc[3 * p_slot + 1] = pd1; s_desc[3 * p_slot + 2] = pd2; }
+                __syncwarp();
+                if (p_run + W < n_runs) {
+                    nd0 = __ldg(rq + 3 * (size_t)(p_run + W)); nd1 = __ldg(rq + 3 * (size_t)(p_run + W) + 1);
+                    nd2 = __ldg(rq + 3 * (size_t)(p_run + W) + 2);
+                }
+            }
+        }
+    };
+    for (int i = 0; i < kShortRing; i++)
+        if (p_run < n_runs) produce();
+
+    uint32_t phase_bits = 0, slot_i = 0, c_slot = 0;
+    for (uint32_t c_run = gw; c_run < n_runs; c_run += W) {
+        const uint4 d0 = s_desc[3 * c_slot], d1 = s_desc[3 * c_slot + 1], d2 = s_desc[3 * c_slot + 2];
+        c_slot = (c_slot + 1 == (uint32_t)kShortDescSlots) ? 0 : c_slot + 1;
+        OutT *out = reinterpret_cast<OutT *>(((unsigned long long)d0.w << 32) | d0.z);
+        float *state = reinterpret_cast<float *>(((unsigned long long)d1.y << 32) | d1.x);
+        const uint32_t npk = d1.w;
+        const bool has_prev = (d2.x & 0xffu) != 0, write_state = ((d2.x >> 8) & 0xffu) != 0;
+        const uint32_t n_oct = (npk + kShortOct - 1) / kShortOct;
+        const uint32_t koff = has_prev ? 0u : 1u;                // packet 0 emits nothing then: packet k lands at 128 (k - 1)
+
+        V carry[8];                                              // p_even of the previous octet (lanes of block 7 matter)
+#pragma unroll
+        for (int j = 0; j < 8; j++) carry[j] = V{0.f, 0.f};
+        V pe[8];
+        for (uint32_t o = 0; o < n_oct; o++) {
+            const uint32_t stage_s = ring_s + slot_i * kShortStageBytes;
+            const unsigned char *stage_p = ring + slot_i * kShortStageBytes;
+            mbar_wait(bars_s + 8 * slot_i, (phase_bits >> slot_i) & 1u);
+            phase_bits ^= 1u << slot_i;
+            V O[8], E[8];
+            phase_a_s(reinterpret_cast<const float *>(stage_p + blk * kShortTileStride), l, tw, O, E);
+            __syncwarp();           // every lane has consumed its quads: the stage becomes the scratch
+            {
+                const uint32_t a0 = stage_s + wA0, a1 = stage_s + wA1;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    sts_eo(((a0 ^ (4u * (j >> 1))) + (j << 8)), E[j].x, O[j].x);
+                    sts_eo(((a1 ^ (4u * (j >> 1))) + (j << 8)), E[j].y, O[j].y);
+                }
+            }
+            __syncwarp();
+            {
+                const uint32_t c0 = stage_s + wC0, c1 = stage_s + wC1;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    lds_eo(((c0 ^ (4u * (j & 3))) + ((j >> 2) << 7)), E[j].x, O[j].x);
+                    lds_eo(((c1 ^ (4u * (j & 3))) + ((j >> 2) << 7)), E[j].y, O[j].y);
+                }
+            }
+            phase_c_fft<1>(tw, &O, &E);
+            const uint32_t k = o * kShortOct + blk;                          // this lane's packet
+            const bool first0 = (o == 0 && blk == 0);
+            const bool emit = k < npk && !(first0 && !has_prev);
+            OutT *ob = out + (ptrdiff_t)((int)k - (int)koff) * kShortN2;
+            const float *st_tile = reinterpret_cast<const float *>(stage_p + kShortStateOff);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                V p_odd;
+                step8_s(tw(P_B0 + j), tw(P_B1 + j), O[j], E[j], p_odd, pe[j]);
+                // previous block's right half: block b-1 of this octet (4 lanes down), or the last block of the
+                // previous octet for block 0
+                V up, cr;
+                up.x = __shfl_up_sync(0xffffffffu, pe[j].x, 4);
+                up.y = __shfl_up_sync(0xffffffffu, pe[j].y, 4);
+                cr.x = __shfl_sync(0xffffffffu, carry[j].x, 28 + l);
+                cr.y = __shfl_sync(0xffffffffu, carry[j].y, 28 + l);
+                V plo = blk ? up : cr, phi = plo;
+                const int mx = outIndex_s(l, j, 0), my = outIndex_s(l, j, 1);
+                if (first0 && has_prev) {                        // an imported state need not be symmetric
+                    plo = V{st_tile[mx], st_tile[my]};
+                    phi = V{st_tile[127 - mx], st_tile[127 - my]};
+                }
+                V lo, hi;
+                ola_s(p_odd, tw(P_WLO + j), tw(P_WHI + j), plo, phi, lo, hi);
+                if (emit) {
+                    st_pcm(ob + mx, lo.x); st_pcm(ob + my, lo.y);
+                    st_pcm(ob + 127 - mx, hi.x); st_pcm(ob + 127 - my, hi.y);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) carry[j] = pe[j];
+            __syncwarp();                                        // scratch and state tile consumed: the stage is free
+            in_flight--;
+            if (p_run < n_runs) produce();
+            slot_i = (slot_i + 1 == (uint32_t)kShortRing) ? 0 : slot_i + 1;
+        }
+        if (write_state && (uint32_t)blk == ((npk - 1) & (kShortOct - 1))) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int mx = outIndex_s(l, j, 0), my = outIndex_s(l, j, 1);
+                state[mx] = pe[j].x; state[my] = pe[j].y;
+                state[127 - mx] = pe[j].x; state[127 - my] = pe[j].y;     // x[128+m] == x[255-m] (imdct.rs:622-649)
+            }
+        }
+    }
+}
+
+inline void short_kernel_configure()
+{
+    cudaFuncSetAttribute(k_short<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmemBytes);
+    cudaFuncSetAttribute(k_short<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmemBytes);
+}
+
+inline int short_launch(cudaStream_t stream, const ShortRun *d_runs, uint32_t n_runs, const float *d_pack, int sm_count, bool i16_out)
+{
+    if (!n_runs) return 0;
+    const uint32_t want = (n_runs + kShortWarps - 1) / kShortWarps;
+    const uint32_t grid = want < (uint32_t)sm_count ? want : (uint32_t)sm_count;
+    if (i16_out) k_short<int16_t><<<grid, kShortWarps * 32, kShortSmemBytes, stream>>>(d_runs, n_runs, d_pack);
+    else k_short<float><<<grid, kShortWarps * 32, kShortSmemBytes, stream>>>(d_runs, n_runs, d_pack);
+    return cudaGetLastError() != cudaSuccess;
+}
+#endif  // __CUDACC__
+
+}  // namespace lwb

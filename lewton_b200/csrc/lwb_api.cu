@@ -14,11 +14,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "kernel_long.cuh"
+#include "kernel_short.cuh"
 #include "kernels_generic.cuh"
 #include "kernel_chain.cuh"
 #include "kernel_prologue.cuh"
@@ -73,6 +75,7 @@ extern "C" int lwb_ctx_create(int device, lwb_ctx **out)
         if (mb >= 1) ctx->x_cap_elems = (size_t)mb << 18;
     }
     long_kernel_configure();
+    short_kernel_configure();
     *out = ctx;
     return LWB_OK;
 }
@@ -86,6 +89,8 @@ extern "C" void lwb_ctx_destroy(lwb_ctx *ctx)
                       &ctx->kinds, &ctx->ys, &ctx->chains, &ctx->ticket, &ctx->runs_buf[0], &ctx->runs_buf[1],
                       &ctx->cdesc, &ctx->cbytes})
         if (b->p) cudaFree(b->p);
+    for (CachedTables &ct : ctx->tables)
+        for (void *p : ct.allocs) cudaFree(p);
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
     for (Staging &st : ctx->stage) {
         if (st.h) cudaFreeHost(st.h);
@@ -277,20 +282,51 @@ extern "C" int lwb_setup_create(lwb_ctx *ctx, const lwb_setup_desc *d, lwb_setup
         } else {
             generate_tables(bs, a.data(), b.data(), c.data(), w.data(), br.data());
         }
-        DevTables &dt = su->host.tab[i];
-        dt.bs = bs;
-        if ((rc = upload(su, a.data(), a.size(), &dt.a)) || (rc = upload(su, b.data(), b.size(), &dt.b)) ||
-            (rc = upload(su, c.data(), c.size(), &dt.c)) || (rc = upload(su, w.data(), w.size(), &dt.window)) ||
-            (rc = upload(su, br.data(), br.size(), &dt.bitrev)))
-            break;
-        dt.pack = nullptr;
-        if (bs == kLongBs) {
-            std::vector<float> pack(kLongPackFloats);
-            long_build_pack(a.data(), b.data(), c.data(), w.data(), pack.data());
-            if ((rc = upload(su, pack.data(), pack.size(), &dt.pack))) break;
+        // Blocksize tables live in the context and are shared by every setup that has the same ones (bit for
+        // bit): streams opened from different headers then still run in one launch of the fused kernels, which
+        // take one twiddle pack per launch.
+        const CachedTables *hit = nullptr;
+        for (const CachedTables &ct : ctx->tables)
+            if (ct.dt.bs == bs && ct.a == a && ct.b == b && ct.c == c && ct.w == w && ct.br == br) { hit = &ct; break; }
+        if (!hit) {
+            CachedTables ct;
+            ct.dt.bs = bs;
+            ct.dt.pad = 0;
+            ct.dt.pack = nullptr;
+            auto up = [&](const void *h, size_t bytes, const void **dev) {
+                void *p = nullptr;
+                if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return LWB_ERR_CUDA;
+                ct.allocs.push_back(p);
+                if (cudaMemcpyAsync(p, h, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return LWB_ERR_CUDA;
+                *dev = p;
+                return LWB_OK;
+            };
+            std::vector<float> pack;
+            if (bs == kLongBs) {
+                pack.resize(kLongPackFloats);
+                long_build_pack(a.data(), b.data(), c.data(), w.data(), pack.data());
+            } else if (bs == kShortBs) {
+                pack.resize(kShortPackFloats);
+                short_build_pack(a.data(), b.data(), c.data(), w.data(), pack.data());
+            }
+            rc = up(a.data(), a.size() * 4, (const void **)&ct.dt.a);
+            if (!rc) rc = up(b.data(), b.size() * 4, (const void **)&ct.dt.b);
+            if (!rc) rc = up(c.data(), c.size() * 4, (const void **)&ct.dt.c);
+            if (!rc) rc = up(w.data(), w.size() * 4, (const void **)&ct.dt.window);
+            if (!rc) rc = up(br.data(), br.size() * 4, (const void **)&ct.dt.bitrev);
+            if (!rc && !pack.empty()) rc = up(pack.data(), pack.size() * 4, (const void **)&ct.dt.pack);
+            // the copies above read from vectors that die here
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = LWB_ERR_CUDA;
+            if (rc) {
+                for (void *p : ct.allocs) cudaFree(p);
+                fail(ctx, rc, "setup: table upload");
+                break;
+            }
+            ct.a = a; ct.b = b; ct.c = c; ct.w = w; ct.br = br;
+            ctx->tables.push_back(std::move(ct));
+            hit = &ctx->tables.back();
         }
-        // the synchronous copies above read from vectors that die here
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = LWB_ERR_CUDA;
+        su->host.tab[i] = hit->dt;
     }
     std::vector<DevFloor1> floors(d->n_floors);
     for (uint32_t i = 0; i < d->n_floors && rc == LWB_OK; i++) rc = prepare_floor1(d->floors[i], &floors[i]);

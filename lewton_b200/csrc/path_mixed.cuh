@@ -1,12 +1,14 @@
 // path_mixed.cuh -- part of the C-ABI translation unit (included by lwb_api.cu, not compiled on its own):
-// mixed short/long streams: segmentation between the fused kernel and the chain kernel, round by round.
+// segmented batches: every chain is cut between the fused long-block kernel, the fused short-block kernel and the
+// chain kernel, round by round.
 #pragma once
 
 // ---------------------------------------------------------------------------------------------
-// Mixed short/long streams (the standard 256/2048 Vorbis shape): each chain is cut into segments
-// -- maximal runs of long blocks with long neighbours go to the fused kernel, everything else to
-// the chain kernel -- and the segments of all chains are executed round by round, handing the
-// overlap state over through the stream's device state (PreviousWindowRight) between launches.
+// Mixed short/long streams (the standard 256/2048 Vorbis shape), and uniform streams of 256-point blocks:
+// each chain is cut into segments -- maximal runs of long blocks (n = 2048) go to the fused kernel k_long,
+// maximal runs of full-window 256-point blocks to its short-block counterpart k_short, everything else to
+// the chain kernel -- and the segments of all chains are executed round by round, handing the overlap
+// state over through the stream's device state (PreviousWindowRight) between launches.
 // ---------------------------------------------------------------------------------------------
 static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch, bool *handled,
                      lwb_plan *plan = nullptr)
@@ -21,19 +23,31 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
     const size_t esz = i16 ? 2 : 4;
     unsigned maxc = 1;
     int n1max = 64, n0max = 64, bs0 = -1;
-    size_t total_packets = 0, long_like = 0;
-    const float *pack = nullptr, *w_short = nullptr;
+    size_t total_packets = 0, fast_like = 0;
+    const float *pack = nullptr, *spack = nullptr, *w_short = nullptr;
     for (size_t i = 0; i < n_chains; i++) {
         const lwb_chain *c = &chains[i];
         if (!c->stream || c->stream->ctx != ctx || (c->n_packets && !c->mode_numbers)) return LWB_OK;
         const lwb_setup *su = c->stream->setup;
-        if (su->channels > 8 || su->bs1 != kLongBs || !su->host.tab[1].pack) return LWB_OK;
-        if (pack && pack != su->host.tab[1].pack) return LWB_OK;
-        pack = su->host.tab[1].pack;
-        // one short window for the whole batch (the fused kernel takes it as a launch argument)
-        if (bs0 >= 0 && (bs0 != su->bs0 || w_short != su->host.tab[0].window)) return LWB_OK;
-        bs0 = su->bs0;
-        w_short = su->host.tab[0].window;
+        if (su->channels > 8) return LWB_OK;
+        // one twiddle pack per launch of each fused kernel (setups with identical tables share theirs, see
+        // lwb_setup_create), and one short window for the long kernel's transitional blocks
+        const bool long_ok = su->bs1 == kLongBs && su->host.tab[1].pack;
+        if (long_ok) {
+            if (pack && pack != su->host.tab[1].pack) return LWB_OK;
+            pack = su->host.tab[1].pack;
+            if (bs0 >= 0 && (bs0 != su->bs0 || w_short != su->host.tab[0].window)) return LWB_OK;
+            bs0 = su->bs0;
+            w_short = su->host.tab[0].window;
+        }
+        bool short_ok[2];
+        for (int f = 0; f < 2; f++) {
+            short_ok[f] = su->host.tab[f].bs == kShortBs && su->host.tab[f].pack && !getenv("LWB_NO_SHORT");
+            if (short_ok[f]) {
+                if (spack && spack != su->host.tab[f].pack) return LWB_OK;
+                spack = su->host.tab[f].pack;
+            }
+        }
         if ((c->out_offset & 3) || (c->out_stride & 3) || (c->coeff_offset & 3)) return LWB_OK;
         maxc = std::max<unsigned>(maxc, su->channels);
         n1max = std::max(n1max, 1 << su->bs1);
@@ -41,17 +55,21 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         total_packets += c->n_packets;
         for (uint32_t k = 0; k < c->n_packets; k++) {
             const uint8_t m = c->mode_numbers[k];
-            if (m < su->n_modes && su->host.mode_blockflag[m]) long_like++;
+            if (m >= su->n_modes) continue;
+            const int f = su->host.mode_blockflag[m];
+            if ((f && long_ok) || short_ok[f]) fast_like++;
         }
     }
-    // worth it only if the fused kernel gets a good share of the packets (every hand-over between the
-    // kernels costs a launch): at least half the packets long blocks
-    if (long_like * 2 < total_packets) return LWB_OK;
-    const int ls_long = (kLongN - (1 << bs0)) >> 2, pl_short = 1 << (bs0 - 1);
+    // worth it only if the fused kernels get a good share of the packets (every hand-over between the
+    // kernels costs a launch): at least half of them
+    if (fast_like * 2 < total_packets) return LWB_OK;
+    const int bs0e = bs0 >= 0 ? bs0 : kShortBs;
+    const int ls_long = (kLongN - (1 << bs0e)) >> 2, pl_short = 1 << (bs0e - 1);
     if (residue && !io->floor_kind) return fail(ctx, LWB_ERR_INVALID, "residue entry needs floor_kind");
     *handled = true;
 
-    struct Seg { bool is_long, first_short, last_short; uint32_t p0, n; bool has; uint32_t plen; uint64_t coeff, pos; };
+    enum { SEG_CHAIN = 0, SEG_LONG = 1, SEG_SHORT = 2 };
+    struct Seg { int kind; bool first_short, last_short; uint32_t p0, n; bool has; uint32_t plen; uint64_t coeff, pos; };
     bool chain_sees_long = false;       // the chain kernel's shared memory is sized for what it actually gets
     struct Walk { uint32_t seg0, n_seg; bool end_has; uint32_t end_plen; bool touched; uint32_t boff; uint64_t coeff_end; };
     std::vector<Walk> walks(n_chains);
@@ -64,7 +82,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
     uint64_t c_lo = ~0ull, c_hi = 0, o_lo = ~0ull, o_hi = 0, r_lo = ~0ull, r_hi = 0;
     int uniform_c = -1;
     bool need_dense = false;
-    std::vector<uint8_t> is_l;           // bit0 fused-kernel packet, bit1 follows a short block, bit2 precedes one
+    std::vector<uint8_t> is_l;           // bit0 k_long packet, bit1 follows a short block, bit2 precedes one; bit3 k_short packet
     for (size_t i = 0; i < n_chains; i++) {
         lwb_chain *c = &chains[i];
         lwb_stream *s = c->stream;
@@ -98,9 +116,12 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             }
             pk[k] = Pk{has, plen, coeff, pos};
             is_l[k] = 0;
-            if (g.blockflag && g.n == (uint32_t)kLongN) {
+            if (g.blockflag && g.n == (uint32_t)kLongN && su->host.tab[1].pack == pack && pack) {
                 const bool fs = g.ls != 0, lsf = g.re != g.n;
                 if (!has || plen == (fs ? (uint32_t)pl_short : (uint32_t)kLongN2)) is_l[k] = 1 | (fs ? 2 : 0) | (lsf ? 4 : 0);
+            } else if (g.n == (uint32_t)kShortN && spack && su->host.tab[g.blockflag].pack == spack && g.ls == 0 &&
+                       g.rs == (uint32_t)kShortN2 && g.re == (uint32_t)kShortN && (!has || plen == (uint32_t)kShortN2)) {
+                is_l[k] = 8;            // a full-window 256-point block on top of an empty or 128-sample state
             }
             bytes[boff + 3 * k] = c->mode_numbers[k];
             bytes[boff + 3 * k + 1] = c->prev_window_flags ? c->prev_window_flags[k] : 1;
@@ -125,15 +146,18 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         uint32_t k = 0;
         while (k < done) {
             uint32_t j = k + 1;
-            if (is_l[k]) {
-                while (j < done && is_l[j] && !(is_l[j - 1] & 4) && !(is_l[j] & 2)) j++;
-                segs.push_back(Seg{true, (is_l[k] & 2) != 0, (is_l[j - 1] & 4) != 0, k, j - k, pk[k].has, pk[k].plen, pk[k].coeff,
+            if (is_l[k] & 1) {
+                while (j < done && (is_l[j] & 1) && !(is_l[j - 1] & 4) && !(is_l[j] & 2)) j++;
+                segs.push_back(Seg{SEG_LONG, (is_l[k] & 2) != 0, (is_l[j - 1] & 4) != 0, k, j - k, pk[k].has, pk[k].plen, pk[k].coeff,
                                      pk[k].pos});
+            } else if (is_l[k] & 8) {
+                while (j < done && (is_l[j] & 8)) j++;
+                segs.push_back(Seg{SEG_SHORT, false, false, k, j - k, pk[k].has, pk[k].plen, pk[k].coeff, pk[k].pos});
             } else {
                 while (j < done && !is_l[j]) j++;
                 for (uint32_t q = k; q < j; q++)
                     if (su->host.mode_blockflag[c->mode_numbers[q]]) chain_sees_long = true;
-                segs.push_back(Seg{false, false, false, k, j - k, pk[k].has, pk[k].plen, pk[k].coeff, pk[k].pos});
+                segs.push_back(Seg{SEG_CHAIN, false, false, k, j - k, pk[k].has, pk[k].plen, pk[k].coeff, pk[k].pos});
             }
             k = j;
         }
@@ -195,29 +219,33 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         // longest run: such rounds cut their runs (each cut costs one extra IMDCT, the primer packet whose
         // right half is all the next piece needs), as the all-long path does.
         const size_t target_runs = (size_t)ctx->sm_count * kLongWarps * 2;
-        constexpr uint32_t kMinCutRun = 6;
+        const size_t target_sruns = (size_t)ctx->sm_count * kShortWarps * 2;
+        constexpr uint32_t kMinCutRun = 6, kMinCutShort = 16;       // packets per piece (a cut costs one more transform)
         struct Chunk {
             size_t i0, i1, p0, np_;                      // chains, prologue packets
             uint64_t kc_lo, kc_hi, ko_lo, ko_hi;         // coefficient / pcm element ranges
-            std::vector<uint32_t> round_cut;
+            std::vector<uint32_t> round_cut, round_cut_s;
             std::vector<MixRound> rounds;
         };
         std::vector<Chunk> chunks(n_chunks);
         auto cuts_of = [&](const Chunk &ck, const Seg &sg, size_t r) {
-            return std::max<uint32_t>(1, std::min(ck.round_cut[r], sg.n / kMinCutRun));
+            return sg.kind == SEG_LONG ? std::max<uint32_t>(1, std::min(ck.round_cut[r], sg.n / kMinCutRun))
+                                       : std::max<uint32_t>(1, std::min(ck.round_cut_s[r], sg.n / kMinCutShort));
         };
-        size_t n_runs = 0, n_cd = 0, n_pro = 0;
+        size_t n_runs = 0, n_sruns = 0, n_cd = 0, n_pro = 0;
         for (size_t k = 0; k < n_chunks; k++) {
             Chunk &ck = chunks[k];
             ck.i0 = n_chains * k / n_chunks;
             ck.i1 = n_chains * (k + 1) / n_chunks;
             ck.kc_lo = ck.ko_lo = ~0ull;
             ck.kc_hi = ck.ko_hi = 0;
-            std::vector<size_t> round_long(max_rounds, 0);
+            std::vector<size_t> round_long(max_rounds, 0), round_short(max_rounds, 0);
             for (size_t i = ck.i0; i < ck.i1; i++) {
                 const unsigned C = chains[i].stream->setup->channels;
-                for (uint32_t q = 0; q < walks[i].n_seg; q++)
-                    if (segs[walks[i].seg0 + q].is_long) round_long[q] += C;
+                for (uint32_t q = 0; q < walks[i].n_seg; q++) {
+                    if (segs[walks[i].seg0 + q].kind == SEG_LONG) round_long[q] += C;
+                    if (segs[walks[i].seg0 + q].kind == SEG_SHORT) round_short[q] += C;
+                }
                 if (!walks[i].n_seg) continue;
                 ck.kc_lo = std::min(ck.kc_lo, chains[i].coeff_offset);
                 ck.kc_hi = std::max(ck.kc_hi, walks[i].coeff_end);
@@ -225,14 +253,19 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 ck.ko_hi = std::max(ck.ko_hi, chains[i].out_offset + (uint64_t)(C - 1) * chains[i].out_stride + chains[i].n_samples);
             }
             ck.round_cut.assign(max_rounds, 1);
+            ck.round_cut_s.assign(max_rounds, 1);
             if (!getenv("LWB_MIXED_NO_CUTS"))
-                for (size_t r = 0; r < max_rounds; r++)
+                for (size_t r = 0; r < max_rounds; r++) {
                     if (round_long[r] && round_long[r] < target_runs)
                         ck.round_cut[r] = (uint32_t)std::min<size_t>(16, (target_runs + round_long[r] - 1) / round_long[r]);
+                    if (round_short[r] && round_short[r] < target_sruns)
+                        ck.round_cut_s[r] = (uint32_t)std::min<size_t>(64, (target_sruns + round_short[r] - 1) / round_short[r]);
+                }
             for (size_t i = ck.i0; i < ck.i1; i++)
                 for (uint32_t q = 0; q < walks[i].n_seg; q++) {
                     const Seg &sg = segs[walks[i].seg0 + q];
-                    if (sg.is_long) n_runs += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, q);
+                    if (sg.kind == SEG_LONG) n_runs += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, q);
+                    else if (sg.kind == SEG_SHORT) n_sruns += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, q);
                     else n_cd++;
                     if (residue) n_pro += sg.n;
                 }
@@ -240,13 +273,14 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         // a prepared batch (device memory, spectrum entry) owns its descriptors so that later executions replay them
         const bool capture = plan && !host;
         DevBuf &dbuf = capture ? plan->mix : ctx->cdesc;
-        const size_t off_cd = n_runs * sizeof(LongRun), off_pro = off_cd + n_cd * sizeof(ChainDesc);
+        const size_t off_sr = n_runs * sizeof(LongRun), off_cd = off_sr + n_sruns * sizeof(ShortRun), off_pro = off_cd + n_cd * sizeof(ChainDesc);
         const size_t off_by = off_pro + n_pro * sizeof(DevPacket), total = off_by + boff + 16;
         Staging *st;
         if ((rc = acquire_staging(ctx, total, &st))) return rc;
         if ((rc = ensure(ctx, dbuf, total))) return rc;
         char *hb = (char *)st->h, *db = (char *)dbuf.p;
         LongRun *h_runs = (LongRun *)hb;
+        ShortRun *h_sr = (ShortRun *)(hb + off_sr);
         ChainDesc *h_cd = (ChainDesc *)(hb + off_cd);
         DevPacket *h_pro = (DevPacket *)(hb + off_pro);
         std::memcpy(hb + off_by, bytes.data(), boff);
@@ -255,12 +289,32 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             if ((rc = ensure(ctx, ctx->spec, (size_t)(c_hi - c_lo) * 4)) || (rc = ensure(ctx, ctx->curve, (size_t)(c_hi - c_lo) + 16))) return rc;
             d_spec = (const float *)ctx->spec.p - c_lo;          // same element offsets as the coefficient arena
         }
-        size_t wr = 0, wc = 0, wp = 0;
+        size_t wr = 0, ws = 0, wc = 0, wp = 0;
+        // front-stage descriptors of one segment (residue entry): one per packet, whatever its blocksize
+        auto emit_pro = [&](const lwb_chain *c, const lwb_setup *su, const Seg &sg) {
+            uint64_t co = sg.coeff;
+            for (uint32_t q = 0; q < sg.n; q++) {
+                const uint8_t mode = c->mode_numbers[sg.p0 + q];
+                const bool lng = su->host.mode_blockflag[mode] != 0;
+                const uint32_t nq = 1u << (lng ? su->bs1 : su->bs0);
+                DevPacket &dp = h_pro[wp++];
+                std::memset(&dp, 0, sizeof(dp));
+                dp.setup = su->d_setup;
+                dp.coeff_off = co;
+                dp.pkt_index = c->packet_index + sg.p0 + q;
+                dp.n = (uint16_t)nq;
+                dp.blockflag = lng;
+                dp.mapping = su->host.mode_mapping[mode];
+                dp.channels = (uint8_t)su->channels;
+                co += (uint64_t)su->channels * (nq >> 1);
+            }
+        };
         for (Chunk &ck : chunks) {
-            ck.rounds.assign(max_rounds, MixRound{0, 0, 0, 0});
+            ck.rounds.assign(max_rounds, MixRound{0, 0, 0, 0, 0, 0});
             ck.p0 = wp;
             for (size_t r = 0; r < max_rounds; r++) {
                 ck.rounds[r].r0 = wr;
+                ck.rounds[r].s0 = ws;
                 ck.rounds[r].c0 = wc;
                 // fused-kernel runs first, longest first (three buckets): the kernel hands runs out in
                 // descriptor order, and a 64-packet run started last would be the whole round's tail
@@ -268,7 +322,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                     for (size_t i = ck.i0; i < ck.i1; i++) {
                         if (r >= walks[i].n_seg) continue;
                         const Seg &sg = segs[walks[i].seg0 + r];
-                        if (!sg.is_long) continue;
+                        if (sg.kind != SEG_LONG) continue;
                         const uint32_t cuts = cuts_of(ck, sg, r), piece = sg.n / cuts;
                         if ((piece >= 32 ? 0 : piece >= 8 ? 1 : 2) != bucket) continue;
                         const lwb_chain *c = &chains[i];
@@ -302,44 +356,52 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                                 }
                             }
                         }
-                        if (residue)
-                            for (uint32_t q = 0; q < sg.n; q++) {
-                                DevPacket &d = h_pro[wp++];
-                                std::memset(&d, 0, sizeof(d));
-                                d.setup = su->d_setup;
-                                d.coeff_off = sg.coeff + (uint64_t)q * C * kLongN2;
-                                d.pkt_index = c->packet_index + sg.p0 + q;
-                                d.n = kLongN;
-                                d.blockflag = 1;
-                                d.mapping = su->host.mode_mapping[c->mode_numbers[sg.p0 + q]];
-                                d.channels = (uint8_t)C;
-                            }
+                        if (residue) emit_pro(c, su, sg);
                     }
+                // short-block runs: one per channel (and per cut) of every short segment of this round
                 for (size_t i = ck.i0; i < ck.i1; i++) {
                     if (r >= walks[i].n_seg) continue;
                     const Seg &sg = segs[walks[i].seg0 + r];
-                    if (sg.is_long) continue;
+                    if (sg.kind != SEG_SHORT) continue;
                     const lwb_chain *c = &chains[i];
                     const lwb_stream *s = c->stream;
                     const lwb_setup *su = s->setup;
-                    if (residue) {
-                        uint64_t co = sg.coeff;
-                        for (uint32_t q = 0; q < sg.n; q++) {
-                            const uint8_t mode = c->mode_numbers[sg.p0 + q];
-                            const bool lng = su->host.mode_blockflag[mode] != 0;
-                            const uint32_t nq = 1u << (lng ? su->bs1 : su->bs0);
-                            DevPacket &dp = h_pro[wp++];
-                            std::memset(&dp, 0, sizeof(dp));
-                            dp.setup = su->d_setup;
-                            dp.coeff_off = co;
-                            dp.pkt_index = c->packet_index + sg.p0 + q;
-                            dp.n = (uint16_t)nq;
-                            dp.blockflag = lng;
-                            dp.mapping = su->host.mode_mapping[mode];
-                            dp.channels = (uint8_t)su->channels;
-                            co += (uint64_t)su->channels * (nq >> 1);
+                    const unsigned C = su->channels;
+                    const uint32_t cuts = cuts_of(ck, sg, r);
+                    const size_t first_emit = sg.has ? (size_t)kShortN2 : 0;       // samples packet 0 emits
+                    for (unsigned ch = 0; ch < C; ch++) {
+                        const float *in0 = (residue ? d_spec : d_coeffs) + sg.coeff + (size_t)ch * kShortN2;
+                        char *out0 = d_pcm + (c->out_offset + (size_t)ch * c->out_stride + sg.pos) * esz;
+                        for (uint32_t k = 0; k < cuts; k++) {
+                            const size_t p0 = (size_t)sg.n * k / cuts, p1 = (size_t)sg.n * (k + 1) / cuts;
+                            ShortRun &sr = h_sr[ws++];
+                            std::memset(&sr, 0, sizeof(sr));
+                            sr.in_stride = (uint32_t)(C * kShortN2);
+                            sr.state = s->d_state + (size_t)ch * state_stride(su);
+                            sr.write_state = (k + 1 == cuts);
+                            if (k == 0) {
+                                sr.in = in0;
+                                sr.out = out0;
+                                sr.n_packets = (uint32_t)(p1 - p0);
+                                sr.has_prev = sg.has;
+                            } else {
+                                sr.in = in0 + (p0 - 1) * (size_t)sr.in_stride;            // primer = packet p0 - 1
+                                sr.out = out0 + (first_emit + (p0 - 1) * (size_t)kShortN2) * esz;
+                                sr.n_packets = (uint32_t)(p1 - p0 + 1);
+                                sr.has_prev = 0;
+                            }
                         }
                     }
+                    if (residue) emit_pro(c, su, sg);
+                }
+                for (size_t i = ck.i0; i < ck.i1; i++) {
+                    if (r >= walks[i].n_seg) continue;
+                    const Seg &sg = segs[walks[i].seg0 + r];
+                    if (sg.kind != SEG_CHAIN) continue;
+                    const lwb_chain *c = &chains[i];
+                    const lwb_stream *s = c->stream;
+                    const lwb_setup *su = s->setup;
+                    if (residue) emit_pro(c, su, sg);
                     ChainDesc &d = h_cd[wc++];
                     std::memset(&d, 0, sizeof(d));
                     d.setup = su->d_setup;
@@ -356,6 +418,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                     d.channels = (uint8_t)su->channels;
                 }
                 ck.rounds[r].nr = wr - ck.rounds[r].r0;
+                ck.rounds[r].ns = ws - ck.rounds[r].s0;
                 ck.rounds[r].nc = wc - ck.rounds[r].c0;
             }
             ck.np_ = wp - ck.p0;
@@ -372,7 +435,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             }
         }
         MixLaunch ml;
-        ml.db = db; ml.off_cd = off_cd; ml.off_by = off_by; ml.pack = pack; ml.w_short = w_short; ml.ls = ls_long;
+        ml.db = db; ml.off_sr = off_sr; ml.off_cd = off_cd; ml.off_by = off_by; ml.pack = pack; ml.spack = spack; ml.w_short = w_short; ml.ls = ls_long;
         ml.i16 = i16; ml.residue = false; ml.out_format = io->out_format; ml.warps = maxc * wpc; ml.smem = smem;
         ml.n1max = n1max; ml.wpc = wpc; ml.np = np; ml.coeffs = residue ? d_spec : d_coeffs; ml.dense = nullptr; ml.kinds = nullptr; ml.ys = nullptr;
         ml.pcm = d_pcm;

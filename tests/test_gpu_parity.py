@@ -761,7 +761,8 @@ def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle
         cases.append((np.concatenate(coeffs), np.concatenate(dense) if residue else None,
                       np.concatenate(kinds) if residue else None, np.concatenate(ys) if residue else None, want, seqs,
                       [r.pwr.data().copy() for r in refs]))
-    variants = [("mixed", None), ("chain", {"LWB_NO_MIXED": "1"})]
+    # "mixed": k_long + k_short (bs0 == 8) + k_chain rounds; "mixed_noshort": short blocks through the chain kernel
+    variants = [("mixed", None), ("chain", {"LWB_NO_MIXED": "1"}), ("mixed_noshort", {"LWB_NO_SHORT": "1"})]
     if memory == cabi.MEM_HOST:
         variants.append(("mixed_chunked", {"LWB_E2E_CHUNKS": "3"}))       # H2D / kernels / D2H pipelined over 3 chunks of chains
     for name, env in variants:
@@ -1052,3 +1053,82 @@ def test_prepared_residue_batches_replay_front_stages(ctx, oracle, shape, channe
     if floor_mem == cabi.MEM_DEVICE:
         ctx.device_free(d_kinds)
         ctx.device_free(d_ys)
+
+
+@pytest.mark.parametrize("channels,P,S,fmt,memory,seed,sweep_setup", [
+    (1, 8, 40, cabi.OUT_F32_PLANAR, cabi.MEM_DEVICE, 200, True),      # the n = 256 sweep shape: bs0 == bs1 == 8, one octet per run
+    (2, 1, 7, cabi.OUT_F32_PLANAR, cabi.MEM_HOST, 201, False),
+    (2, 3, 9, cabi.OUT_I16_PLANAR, cabi.MEM_DEVICE, 202, False),
+    (6, 9, 5, cabi.OUT_F32_PLANAR, cabi.MEM_HOST, 203, False),
+    (1, 131, 3, cabi.OUT_F32_PLANAR, cabi.MEM_DEVICE, 204, False),    # few long chains: runs are cut (primer packets)
+    (2, 40, 300, cabi.OUT_I16_PLANAR, cabi.MEM_HOST, 205, False),     # more runs than warps: several runs per warp, ring crosses run boundaries
+    (3, 17, 2, cabi.OUT_F32_PLANAR, cabi.MEM_DEVICE, 206, True)])
+def test_short_block_kernel_uniform_batches(ctx, oracle, channels, P, S, fmt, memory, seed, sweep_setup):
+    """Chains of 256-point blocks only (BASELINE.json configs[0] / configs[4] shapes) through lwb_decode_chains:
+    the segmented path hands them to k_short (eight consecutive packets per warp step, imdct.rs:291-659 for
+    n = 256 + audio.rs:1079-1154).  Three consecutive batches -- empty state, carried state, carried state -- bit-exact
+    against the oracle and identical to the chain kernel; the state is compared after every batch."""
+    rng = np.random.default_rng(seed)
+    bs0, bs1 = (8, 8) if sweep_setup else (8, 11)
+    modes = [(1, 0)] if sweep_setup else [(0, 0), (1, 0)]
+    su = make_setup(ctx, channels, bs0, bs1, modes=modes)
+    D = min(S, 6)                                   # distinct inputs: the oracle decodes D streams, the GPU all S
+    refs = [RefStream(oracle, channels, bs0, bs1, modes) for _ in range(D)]
+    f32 = fmt == cabi.OUT_F32_PLANAR
+    outs = {}
+    for name, env in (("short", None), ("chain", {"LWB_NO_SHORT": "1"})):
+        pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+        rng_b = np.random.default_rng(seed + 1000)
+        if name == "chain":
+            refs = [RefStream(oracle, channels, bs0, bs1, modes) for _ in range(D)]
+        for batch in range(3):
+            spec_d = (rng_b.standard_normal((D, P, channels, 128)) * (1.0 if batch else 0.05)).astype(np.float32)
+            want = []
+            for d in range(D):
+                parts = []
+                for i in range(P):
+                    rc, o = refs[d].spectrum(0, 1, 1, spec_d[d, i])
+                    assert rc == 0
+                    parts.append(o)
+                want.append(np.concatenate(parts, axis=1))
+            n = want[0].shape[1]
+            spec = np.ascontiguousarray(spec_d[np.arange(S) % D]).ravel()
+            stride = P * 128
+            chains = [L.ChainSpec(pwrs[s], np.zeros(P, np.uint8), coeff_offset=s * P * channels * 128, out_offset=s * channels * stride,
+                                  out_stride=stride) for s in range(S)]
+            pcm = np.zeros(S * channels * stride, np.float32 if f32 else np.int16)
+            if env:
+                os.environ.update(env)
+            l0 = ctx.launch_count
+            try:
+                if memory == cabi.MEM_DEVICE:
+                    d_in, d_out = ctx.device_alloc(spec.nbytes), ctx.device_alloc(pcm.nbytes)
+                    ctx.h2d(d_in, spec)
+                    ctx.h2d(d_out, pcm)
+                    L.decode_chains(ctx, chains, cabi.ENTRY_SPECTRUM, memory, d_in, d_out, fmt)
+                    ctx.synchronize()
+                    ctx.d2h(pcm, d_out)
+                    ctx.device_free(d_in)
+                    ctx.device_free(d_out)
+                else:
+                    L.decode_chains(ctx, chains, cabi.ENTRY_SPECTRUM, memory, spec, pcm, fmt)
+            finally:
+                if env:
+                    for k in env:
+                        del os.environ[k]
+            assert ctx.launch_count - l0 == 1, (name, ctx.launch_count - l0)       # one k_short (or one k_chain) launch
+            outs[(name, batch)] = pcm
+            for s in range(S):
+                assert chains[s].status == 0 and chains[s].n_samples == n, (name, batch, s, chains[s].n_samples, n)
+                got = pcm[s * channels * stride:(s + 1) * channels * stride].reshape(channels, stride)[:, :n]
+                w = want[s % D]
+                if f32:
+                    assert bits_equal(got, w), (name, batch, s, mismatch_report(got, w))
+                else:
+                    assert np.array_equal(got, oracle.quantise_i16(w)), (name, batch, s)
+            for s in range(min(S, 2 * D)):
+                assert bits_equal(pwrs[s].data(), refs[s % D].pwr.data()), (name, batch, s)
+        for p_ in pwrs:
+            p_.close()
+    for batch in range(3):
+        assert np.array_equal(outs[("short", batch)].view(np.uint8), outs[("chain", batch)].view(np.uint8)), batch
