@@ -76,6 +76,7 @@ extern "C" int lwb_ctx_create(int device, lwb_ctx **out)
     }
     long_kernel_configure();
     short_kernel_configure();
+    prologue_kernel_configure();
     *out = ctx;
     return LWB_OK;
 }
@@ -85,7 +86,7 @@ extern "C" void lwb_ctx_destroy(lwb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->coeffs, &ctx->dense, &ctx->pcm, &ctx->spec, &ctx->curve, &ctx->x, &ctx->desc,
+    for (DevBuf *b : {&ctx->coeffs, &ctx->dense, &ctx->pcm, &ctx->spec, &ctx->segtab, &ctx->x, &ctx->desc,
                       &ctx->kinds, &ctx->ys, &ctx->chains, &ctx->ticket, &ctx->runs_buf[0], &ctx->runs_buf[1],
                       &ctx->cdesc, &ctx->cbytes})
         if (b->p) cudaFree(b->p);
@@ -653,7 +654,7 @@ static int replay_front_stages(lwb_plan *p)
     int rc = stage_floor_arrays(ctx, io, p->pro_r_lo, p->pro_r_hi, p->pro_C, ctx->stream, &d_kinds, &d_ys);
     if (rc) return rc;
     return launch_prologue(ctx, (const DevPacket *)p->pro.p, p->n_pro, p->pro_C, p->pro_fast, p->pro_smem_old, io->coeffs,
-                           io->dense_floor, d_kinds, d_ys, (float *)ctx->spec.p - p->pro_c_lo, (uint8_t *)ctx->curve.p - p->pro_c_lo);
+                           io->dense_floor, d_kinds, d_ys, (float *)ctx->spec.p - p->pro_c_lo);
 }
 
 extern "C" int lwb_plan_execute(lwb_plan *p)
@@ -687,8 +688,7 @@ extern "C" int lwb_plan_execute(lwb_plan *p)
             int prc = stage_floor_arrays(ctx, io, p->mix_pro_r_lo, p->mix_pro_r_hi, p->mix_pro_C, ctx->stream, &d_kinds, &d_ys);
             if (prc) return prc;
             prc = launch_prologue(ctx, p->mix_pro_pk, p->mix_pro_n, p->mix_pro_C, p->mix_pro_fast, p->mix_pro_smem_old, io->coeffs,
-                                  p->mix_pro_dense ? io->dense_floor : nullptr, d_kinds, d_ys, (float *)ctx->spec.p - p->mix_pro_c_lo,
-                                  (uint8_t *)ctx->curve.p - p->mix_pro_c_lo);
+                                  p->mix_pro_dense ? io->dense_floor : nullptr, d_kinds, d_ys, (float *)ctx->spec.p - p->mix_pro_c_lo);
             if (prc) return prc;
         }
         return mixed_launch_rounds(ctx, p->mix_launch, p->mix_rounds);

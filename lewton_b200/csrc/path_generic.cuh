@@ -88,39 +88,41 @@ static int launch(lwb_ctx *ctx, K kernel, dim3 grid, dim3 block, size_t smem, Ar
 
 // Residue entry, front stages for `n_pk` packets of a batch with a uniform channel count C: spec[coeff_off ..] <-
 // floor x inverse-coupled residue (audio.rs:991-1039).  The two-kernel form (kernel_prologue.cuh) needs <= 8
-// channels and 16-byte aligned rows (prologue_is_fast); anything else takes the per-packet-CTA kernel.  `curve` is
-// a byte arena with the element indexing of `spec` (ctx->curve).
-static bool prologue_is_fast(const DevPacket *h_pk, size_t n_pk, unsigned C, const float *res, const float *dense, const float *spec,
-                             const uint8_t *curve)
+// channels and 16-byte aligned rows (prologue_is_fast); anything else takes the per-packet-CTA kernel.
+static bool prologue_is_fast(const DevPacket *h_pk, size_t n_pk, unsigned C, const float *res, const float *dense, const float *spec)
 {
-    bool fast = C <= 8 && curve && n_pk * (size_t)C < 0xffffffffu && !getenv("LWB_OLD_PROLOGUE");
+    bool fast = C <= 8 && n_pk * (size_t)C < 0xffffffffu && !getenv("LWB_OLD_PROLOGUE");
     for (size_t i = 0; fast && i < n_pk; i++) {
         const uint64_t e = h_pk[i].coeff_off;
         fast = ((reinterpret_cast<uintptr_t>(res + e) | reinterpret_cast<uintptr_t>(spec + e) |
-                 (dense ? reinterpret_cast<uintptr_t>(dense + e) : 0)) & 15) == 0 &&
-               (reinterpret_cast<uintptr_t>(curve + e) & 3) == 0;
+                 (dense ? reinterpret_cast<uintptr_t>(dense + e) : 0)) & 15) == 0 && h_pk[i].channels == C;
     }
     return fast;
 }
 
 static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, size_t n_pk, unsigned C, bool fast, size_t smem_old,
-                           const float *res, const float *dense, const uint8_t *kinds, const uint32_t *ys, float *spec, uint8_t *curve)
+                           const float *res, const float *dense, const uint8_t *kinds, const uint32_t *ys, float *spec)
 {
     if (!n_pk) return LWB_OK;
     if (!fast)
         return launch(ctx, k_prologue, dim3((unsigned)n_pk), dim3(kPrologueThreads), smem_old, d_pk, res, dense, kinds, ys, spec);
-    const uint32_t rows = (uint32_t)(n_pk * C);
-    int rc = launch(ctx, k_floor1_curves, dim3((rows + kCurveRows - 1) / kCurveRows), dim3(kCurveThreads), 0, d_pk, rows, (int)C, kinds, ys, curve);
+    // per (packet, channel) row: the packed flagged segments of its floor curve + their count (ctx scratch)
+    const size_t rows = n_pk * C, tab_bytes = rows * kSegStride * sizeof(uint4);
+    int rc = ensure(ctx, ctx->segtab, tab_bytes + rows + 64);
     if (rc) return rc;
-    const size_t grid = std::min<size_t>(n_pk, (size_t)ctx->sm_count * 8);
-    return launch(ctx, k_prologue3, dim3((unsigned)grid), dim3(kPro3Threads), prologue3_smem((int)C), d_pk, (uint32_t)n_pk, res, dense,
-                  kinds, (const uint8_t *)curve, spec);
+    uint4 *tab = (uint4 *)ctx->segtab.p;
+    uint8_t *cnt = (uint8_t *)ctx->segtab.p + tab_bytes;
+    rc = launch(ctx, k_floor1_segments, dim3((unsigned)((rows + kSegRows - 1) / kSegRows)), dim3(kSegThreads), 0, d_pk, (uint32_t)rows, (int)C,
+                kinds, ys, tab, cnt);
+    if (rc) return rc;
+    const size_t grid = std::min<size_t>(n_pk, (size_t)ctx->sm_count * (C > 2 ? 4 : 8));
+    return launch(ctx, k_prologue_fused, dim3((unsigned)grid), dim3(kPfThreads), prologue_fused_smem((int)C), d_pk, (uint32_t)n_pk, res, dense,
+                  kinds, (const uint4 *)tab, (const uint8_t *)cnt, spec);
 }
 static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, const DevPacket *h_pk, size_t n_pk, unsigned C, size_t smem_old,
-                           const float *res, const float *dense, const uint8_t *kinds, const uint32_t *ys, float *spec, uint8_t *curve)
+                           const float *res, const float *dense, const uint8_t *kinds, const uint32_t *ys, float *spec)
 {
-    return launch_prologue(ctx, d_pk, n_pk, C, prologue_is_fast(h_pk, n_pk, C, res, dense, spec, curve), smem_old, res, dense, kinds, ys,
-                           spec, curve);
+    return launch_prologue(ctx, d_pk, n_pk, C, prologue_is_fast(h_pk, n_pk, C, res, dense, spec), smem_old, res, dense, kinds, ys, spec);
 }
 
 // Host-side look at the floor kinds of rows [row_lo, row_hi) (one row per (packet, channel)).  Device-resident
@@ -264,9 +266,9 @@ static int run_generic(lwb_ctx *ctx, std::vector<PlanChain> &plan, const lwb_bat
         const DevPacket *dp = (const DevPacket *)ctx->desc.p;
         const float *spec = ar.coeffs;
         if (io->entry == LWB_ENTRY_RESIDUE) {
-            if ((rc = ensure(ctx, ctx->spec, spec_hi * sizeof(float))) || (rc = ensure(ctx, ctx->curve, spec_hi + 16))) return rc;
+            if ((rc = ensure(ctx, ctx->spec, spec_hi * sizeof(float)))) return rc;
             if ((rc = launch_prologue(ctx, dp, hp, n_desc, maxc, prologue_smem_of(plan), ar.coeffs, ar.dense, ar.kinds, ar.ys,
-                                      (float *)ctx->spec.p, (uint8_t *)ctx->curve.p)))
+                                      (float *)ctx->spec.p)))
                 return rc;
             spec = (const float *)ctx->spec.p;
         }

@@ -360,7 +360,7 @@ static int run_prologue_all(lwb_ctx *ctx, std::vector<PlanChain> &plan, const De
     int rc;
     if ((rc = ensure_pinned(ctx, n_desc * sizeof(DevPacket)))) return rc;
     if ((rc = ensure(ctx, ctx->desc, n_desc * sizeof(DevPacket)))) return rc;
-    if ((rc = ensure(ctx, ctx->spec, spec_elems * sizeof(float))) || (rc = ensure(ctx, ctx->curve, spec_elems + 16))) return rc;
+    if ((rc = ensure(ctx, ctx->spec, spec_elems * sizeof(float)))) return rc;
     CU(ctx, cudaStreamSynchronize(ctx->stream));          // pinned descriptor staging is reused
     DevPacket *hp = (DevPacket *)ctx->h_desc;
     size_t di = 0;
@@ -381,12 +381,12 @@ static int run_prologue_all(lwb_ctx *ctx, std::vector<PlanChain> &plan, const De
     }
     CU(ctx, cudaMemcpyAsync(ctx->desc.p, hp, n_desc * sizeof(DevPacket), cudaMemcpyHostToDevice, ctx->stream));
     return launch_prologue(ctx, (const DevPacket *)ctx->desc.p, hp, n_desc, plan[0].c->stream->setup->channels, prologue_smem_of(plan),
-                           ar.coeffs, ar.dense, ar.kinds, ar.ys, (float *)ctx->spec.p, (uint8_t *)ctx->curve.p);
+                           ar.coeffs, ar.dense, ar.kinds, ar.ys, (float *)ctx->spec.p);
 }
 
 
 // Residue-entry batches whose every packet is a long block with long neighbours: the front stages
-// (k_floor1_curves + k_prologue3, or k_prologue) form the spectrum on the device, the fused kernel does the
+// (k_floor1_segments + k_prologue_fused, or k_prologue) form the spectrum on the device, the fused kernel does the
 // rest.  Planned straight from the chain list like try_long (no per-packet PlanChain vectors); a prepared batch
 // keeps the front-stage descriptors and, for device-memory batches, the fused kernel's runs, so that a replay
 // is three launches with no host work (lwb_plan_execute).
@@ -439,9 +439,8 @@ static int try_long_residue(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, co
             d_dense = (const float *)ctx->dense.p - c_lo;
         }
     }
-    if ((rc = ensure(ctx, ctx->spec, elems * 4)) || (rc = ensure(ctx, ctx->curve, elems + 16))) return rc;
+    if ((rc = ensure(ctx, ctx->spec, elems * 4))) return rc;
     float *d_spec = (float *)ctx->spec.p - c_lo;
-    uint8_t *d_curve = (uint8_t *)ctx->curve.p - c_lo;
     const uint8_t *d_kinds;
     const uint32_t *d_ys;
     if ((rc = stage_floor_arrays(ctx, io, r_lo, r_hi, C, sm, &d_kinds, &d_ys))) return rc;
@@ -474,7 +473,7 @@ static int try_long_residue(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, co
                 d.channels = (uint8_t)C;
             }
         }
-        fast = prologue_is_fast(hp, n_pk, C, d_res, d_dense, d_spec, d_curve);
+        fast = prologue_is_fast(hp, n_pk, C, d_res, d_dense, d_spec);
         CU(ctx, cudaMemcpyAsync(db.p, hp, n_pk * sizeof(DevPacket), cudaMemcpyHostToDevice, sm));
         CU(ctx, cudaEventRecord(st->ev, sm));
         st->pending = true;
@@ -488,7 +487,7 @@ static int try_long_residue(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, co
             plan->pro_c_lo = c_lo; plan->pro_c_hi = c_hi; plan->pro_r_lo = r_lo; plan->pro_r_hi = r_hi;
         }
     }
-    if ((rc = launch_prologue(ctx, d_pk, n_pk, C, fast, smem_old, d_res, d_dense, d_kinds, d_ys, d_spec, d_curve))) return rc;
+    if ((rc = launch_prologue(ctx, d_pk, n_pk, C, fast, smem_old, d_res, d_dense, d_kinds, d_ys, d_spec))) return rc;
     bool h2 = false;
     rc = try_long(ctx, chains, n_chains, io, epoch, &h2, (const float *)ctx->spec.p, c_lo, plan, true);
     if (rc) return rc;

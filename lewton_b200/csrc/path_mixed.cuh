@@ -286,7 +286,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         std::memcpy(hb + off_by, bytes.data(), boff);
         const float *d_spec = nullptr;
         if (residue) {
-            if ((rc = ensure(ctx, ctx->spec, (size_t)(c_hi - c_lo) * 4)) || (rc = ensure(ctx, ctx->curve, (size_t)(c_hi - c_lo) + 16))) return rc;
+            if ((rc = ensure(ctx, ctx->spec, (size_t)(c_hi - c_lo) * 4))) return rc;
             d_spec = (const float *)ctx->spec.p - c_lo;          // same element offsets as the coefficient arena
         }
         size_t wr = 0, ws = 0, wc = 0, wp = 0;
@@ -441,7 +441,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         ml.pcm = d_pcm;
         bool pro_fast = false;
         if (residue && n_pro)
-            pro_fast = prologue_is_fast(h_pro, n_pro, maxc, d_coeffs, need_dense ? d_dense : nullptr, d_spec, (const uint8_t *)ctx->curve.p - c_lo);
+            pro_fast = prologue_is_fast(h_pro, n_pro, maxc, d_coeffs, need_dense ? d_dense : nullptr, d_spec);
         for (size_t k = 0; k < n_chunks; k++) {
             Chunk &ck = chunks[k];
             if (ck.kc_hi <= ck.kc_lo) continue;
@@ -456,8 +456,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             }
             if (residue && ck.np_)
                 if ((rc = launch_prologue(ctx, (const DevPacket *)(db + off_pro) + ck.p0, ck.np_, maxc, pro_fast, prologue_smem(maxc, kLongBs),
-                                          d_coeffs, need_dense ? d_dense : nullptr, d_kinds, d_ys, const_cast<float *>(d_spec),
-                                          (uint8_t *)ctx->curve.p - c_lo)))
+                                          d_coeffs, need_dense ? d_dense : nullptr, d_kinds, d_ys, const_cast<float *>(d_spec))))
                     return rc;
             if ((rc = mixed_launch_rounds(ctx, ml, ck.rounds))) return rc;
             if (host && ck.ko_hi > ck.ko_lo) {

@@ -5,7 +5,7 @@
   long_f32        S x P stereo long packets, spectrum entry, f32 planar           8 B / sample (the headline)
   long_i16        same, i16 planar output                                          6 B / sample
   long_residue    same, residue entry: coupling (0,1) + floor-1 + multiply; floor posts device-resident
-                  (lwb_batch_io::floor_memory); k_floor1_curves + k_prologue3 + k_long, captured plan   18 B / sample moved, 8 algorithmic
+                  (lwb_batch_io::floor_memory); k_floor1_segments + k_prologue_fused + k_long, captured plan   18 B / sample moved, 8 algorithmic
   long_residue_hostfloors   same with host floor arrays (uploaded every step)
   streaming_p1    one packet per stream per call (state round-trips HBM)           16 B / sample
   config3_6ch     BASELINE.json configs[2] shape: 6 channels, Bernoulli(0.25) short blocks, coupling chain

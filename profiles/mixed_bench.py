@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""Mixed short/long streams (256/2048, stereo): throughput of the segmented path (fused kernel for long
-runs + chain kernel for the rest, profiles/../lwb_api.cu try_mixed) against the chain kernel alone
+"""Mixed short/long streams (256/2048, stereo): throughput of the segmented path (k_long for long runs, k_short
+for the short bursts, k_chain for the rest; csrc/path_mixed.cuh) against the same without k_short
+(LWB_NO_SHORT=1: short bursts through the chain kernel, the round-1 state) and the chain kernel alone
 (LWB_NO_MIXED=1).  Spectrum entry, f32 planar, device-resident, state carried between steps.
 One JSON line per (p_short, path)."""
 import json
@@ -51,9 +52,9 @@ def main():
             out_off += C * P * 1024          # upper bound per chain
         spec = torch.randn(coeff_off, device="cuda") * 1e-2
         pcm = torch.empty(out_off, device="cuda")
-        for path, env in (("segmented", None), ("chain_only", "1")):
+        for path, env in (("segmented", None), ("segmented_noshort", "LWB_NO_SHORT"), ("chain_only", "LWB_NO_MIXED")):
             if env:
-                os.environ["LWB_NO_MIXED"] = env
+                os.environ[env] = "1"
             pw = [L.PreviousWindowRight(su) for _ in range(S)]
             chains = [L.ChainSpec(pw[s], seqs[s][0], seqs[s][1], seqs[s][2], coeff_offset=offs[s][0], out_offset=offs[s][1],
                                   out_stride=P * 1024) for s in range(S)]
@@ -84,7 +85,7 @@ def main():
             for p in pw:
                 p.close()
             if env:
-                del os.environ["LWB_NO_MIXED"]
+                del os.environ[env]
         del spec, pcm
     su.close()
     ctx.close()

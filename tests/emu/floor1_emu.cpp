@@ -8,7 +8,7 @@
 #include "../../lewton_b200/csrc/tables_host.cpp"
 
 extern "C" int lwb_emu_floor1(int mult, const uint32_t *xs, int nposts, const uint32_t *y, int n2,
-                              uint32_t *curve_closed, uint8_t *curve_render, uint8_t *curve_chunks)
+                              uint32_t *curve_closed, uint8_t *curve_render, uint8_t *curve_chunks, uint8_t *curve_packed)
 {
     lwb_floor_desc d;
     std::memset(&d, 0, sizeof(d));
@@ -31,6 +31,19 @@ extern "C" int lwb_emu_floor1(int mult, const uint32_t *xs, int nposts, const ui
         uint32_t w[4];
         lwb::d_floor1_render16(sx, sy, sm, m, k0, w);
         std::memcpy(curve_chunks + k0, w, 16);
+    }
+    // the packed-segment evaluation of k_prologue_fused: per bin, segment advanced without branches
+    {
+        lwb::Seg4 tab[LWB_MAX_POSTS + 2];
+        uint16_t sx2[LWB_MAX_POSTS + 1], sy2[LWB_MAX_POSTS + 1];
+        const int m2 = lwb::d_floor1_posts(fl, y, n2, sx2, sy2);
+        for (int j = 0; j + 1 < m2; j++) tab[j] = lwb::d_floor1_pack_segment(sx2, sy2, j);
+        tab[m2 - 1] = tab[m2 - 2];                     // sentinel read past the last segment (never selected: x1 >= n2)
+        int seg = 0;
+        for (int k = 0; k < n2; k++) {
+            seg += (k >= (int)(tab[seg].y >> 16));
+            curve_packed[k] = (uint8_t)lwb::d_floor1_seg_y(tab[seg], k);
+        }
     }
     return 0;
 }

@@ -39,10 +39,12 @@ def test_floor1_posts_closed_form_and_dda_render_match_the_oracle(oracle, seed):
         closed = np.zeros(n2, np.uint32)
         render = np.zeros(n2, np.uint8)
         chunks = np.zeros(n2, np.uint8)
+        packed = np.zeros(n2, np.uint8)
         rc = L.lwb_emu_floor1(mult, xa.ctypes.data_as(C.c_void_p), len(xs), ya.ctypes.data_as(C.c_void_p), n2,
                               closed.ctypes.data_as(C.c_void_p), render.ctypes.data_as(C.c_void_p),
-                              chunks.ctypes.data_as(C.c_void_p))
+                              chunks.ctypes.data_as(C.c_void_p), packed.ctypes.data_as(C.c_void_p))
         assert rc == 0
+        assert np.array_equal(packed.astype(np.uint32), want & 255), (seed, case, np.nonzero(packed != (want & 255))[0][:5])
         assert np.array_equal(chunks.astype(np.uint32), want & 255), (seed, case, np.nonzero(chunks != (want & 255))[0][:5])
         assert np.array_equal(closed & 255, want & 255), (seed, case)
         assert np.array_equal(render.astype(np.uint32), want & 255), (seed, case, np.nonzero(render != (want & 255))[0][:5])

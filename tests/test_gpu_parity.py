@@ -520,7 +520,7 @@ def test_residue_entry_long_batch_uses_prologue_plus_fused(ctx, oracle, memory, 
             else:
                 assert np.array_equal(pcm[s][:, :n], oracle.quantise_i16(want[s])), (batch, s)
             assert bits_equal(pwrs[s].data(), refs[s].pwr.data())
-    # 2 batches x (k_floor1_curves + k_prologue3 + fused kernel) = 6 launches: the generic IMDCT/overlap kernels did not run
+    # 2 batches x (k_floor1_segments + k_prologue_fused + fused kernel) = 6 launches: the generic IMDCT/overlap kernels did not run
     assert ctx.launch_count - launches0 == 6
 
 
@@ -953,7 +953,7 @@ def test_prepared_mixed_batch_replays_captured_rounds(ctx, oracle):
     ("mixed", 6, cabi.OUT_I16_PLANAR, cabi.MEM_DEVICE, 125)])
 def test_prepared_residue_batches_replay_front_stages(ctx, oracle, shape, channels, fmt, floor_mem, seed):
     """Residue-entry prepared batches in device memory (what a decode server replays step after step): the
-    front stages (k_floor1_curves + k_prologue3: audio.rs:391-555, :991-1039) and the kernels behind them are
+    front stages (k_floor1_segments + k_prologue_fused: audio.rs:391-555, :991-1039) and the kernels behind them are
     captured once and replayed with NEW residues and floor posts every step -- from device-resident floor arrays
     (lwb_batch_io::floor_memory = LWB_MEM_DEVICE, read in place) or host arrays (uploaded again per step).
     "long": uniform long blocks (front stages + fused kernel); "mixed": 256/2048 sequences incl. the 5.1 coupling
@@ -1046,7 +1046,7 @@ def test_prepared_residue_batches_replay_front_stages(ctx, oracle, shape, channe
             assert bits_equal(pwrs[s].data(), refs[s].pwr.data()), (it, s)
     assert counts[2] == counts[3], counts
     if shape == "long":
-        assert counts[3] == 3, counts              # k_floor1_curves + k_prologue3 + k_long, nothing else
+        assert counts[3] == 3, counts              # k_floor1_segments + k_prologue_fused + k_long, nothing else
     batch.close()
     ctx.device_free(d_in)
     ctx.device_free(d_out)
@@ -1130,5 +1130,6 @@ def test_short_block_kernel_uniform_batches(ctx, oracle, channels, P, S, fmt, me
                 assert bits_equal(pwrs[s].data(), refs[s % D].pwr.data()), (name, batch, s)
         for p_ in pwrs:
             p_.close()
-    for batch in range(3):
-        assert np.array_equal(outs[("short", batch)].view(np.uint8), outs[("chain", batch)].view(np.uint8)), batch
+    if memory == cabi.MEM_DEVICE:       # (host-memory batches copy whole strides back: what lies beyond n_samples is unspecified)
+        for batch in range(3):
+            assert np.array_equal(outs[("short", batch)].view(np.uint8), outs[("chain", batch)].view(np.uint8)), batch
