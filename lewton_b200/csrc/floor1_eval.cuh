@@ -142,27 +142,35 @@ LWB_HD uint32_t d_mulhi_u32(uint32_t a, uint32_t b)
 #endif
 }
 
-// One flagged segment [x0, x1) of a floor curve, packed for per-bin evaluation (k_prologue_fused):
-//   .x = multiply-high magic of adx        .y = x0 | x1 << 16
-//   .z = y0 | |dy| << 8 | shift << 16      .w = sign of dy (+1 / -1)
-// y(k) = y0 + sgn * (mulhi(|dy| * (k - x0), magic) >> shift): the closed form of render_line (audio.rs:503-524).
+// One flagged segment [x0, x1) of a floor curve, packed for per-bin evaluation (k_prologue_fused), laid out so
+// that a bin costs as few instructions as possible:
+//   .x = multiply-high magic of adx
+//   .y = x1 << 16 | y0 << 8 | (shift ? 2 : 0) | (dy < 0 ? 1 : 0)     -- "bin k is past this segment" is the single
+//                                                                       unsigned compare (k << 16 | 0xffff) >= .y
+//   .z = |dy|            .w = -(|dy| * x0)                           -- |dy| * (k - x0) is one multiply-add
+// y(k) = y0 +- (mulhi(|dy| * (k - x0), magic) >> shift): the closed form of render_line (audio.rs:503-524).
 struct Seg4 { uint32_t x, y, z, w; };
 LWB_HD Seg4 d_floor1_pack_segment(const uint16_t *sx, const uint16_t *sy, int j)
 {
     int sh;
     const uint32_t mg = d_floor1_magic((int)sx[j + 1] - (int)sx[j], &sh);
     const int y0 = sy[j] & 255, dy = (int)(sy[j + 1] & 255) - y0;
+    const uint32_t ady = (uint32_t)(dy < 0 ? -dy : dy);
     Seg4 s;
     s.x = mg;
-    s.y = (uint32_t)sx[j] | ((uint32_t)sx[j + 1] << 16);
-    s.z = (uint32_t)y0 | ((uint32_t)(dy < 0 ? -dy : dy) << 8) | ((uint32_t)sh << 16);
-    s.w = (uint32_t)(dy < 0 ? -1 : 1);
+    s.y = ((uint32_t)sx[j + 1] << 16) | ((uint32_t)y0 << 8) | (sh ? 2u : 0u) | (dy < 0 ? 1u : 0u);
+    s.z = ady;
+    s.w = 0u - ady * (uint32_t)sx[j];
     return s;
 }
+LWB_HD bool d_floor1_seg_past(const Seg4 &s, int k) { return (((uint32_t)k << 16) | 0xffffu) >= s.y; }
+template <bool SHIFT>
 LWB_HD uint32_t d_floor1_seg_y(const Seg4 &s, int k)
 {
-    const uint32_t nn = ((s.z >> 8) & 255u) * (uint32_t)(k - (int)(s.y & 0xffffu));
-    return (uint32_t)((int)(s.z & 255u) + (int)s.w * (int)(d_mulhi_u32(nn, s.x) >> (s.z >> 16)));
+    uint32_t q = d_mulhi_u32(s.z * (uint32_t)k + s.w, s.x);
+    if (SHIFT) q >>= (s.y & 2u) ? 12 : 0;
+    const uint32_t y0 = (s.y >> 8) & 255u, neg = 0u - (s.y & 1u);
+    return y0 + ((q ^ neg) - neg);
 }
 
 // Prepares segment j of a row for d_floor1_render16: magic multiplier into sm[j], its shift into the (unused) high

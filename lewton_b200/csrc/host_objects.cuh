@@ -101,6 +101,7 @@ struct lwb_plan {
     const DevPacket *mix_pro_pk = nullptr;
     size_t mix_pro_n = 0, mix_pro_smem_old = 0;
     unsigned mix_pro_C = 0;
+    int mix_pro_n2max = 0;
     uint64_t mix_pro_c_lo = 0, mix_pro_r_lo = 0, mix_pro_r_hi = 0;
 };
 

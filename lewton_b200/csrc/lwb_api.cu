@@ -653,7 +653,7 @@ static int replay_front_stages(lwb_plan *p)
     const uint32_t *d_ys;
     int rc = stage_floor_arrays(ctx, io, p->pro_r_lo, p->pro_r_hi, p->pro_C, ctx->stream, &d_kinds, &d_ys);
     if (rc) return rc;
-    return launch_prologue(ctx, (const DevPacket *)p->pro.p, p->n_pro, p->pro_C, p->pro_fast, p->pro_smem_old, io->coeffs,
+    return launch_prologue(ctx, (const DevPacket *)p->pro.p, p->n_pro, p->pro_C, p->pro_fast, p->pro_smem_old, kLongN2, io->coeffs,
                            io->dense_floor, d_kinds, d_ys, (float *)ctx->spec.p - p->pro_c_lo);
 }
 
@@ -687,7 +687,7 @@ extern "C" int lwb_plan_execute(lwb_plan *p)
             const uint32_t *d_ys;
             int prc = stage_floor_arrays(ctx, io, p->mix_pro_r_lo, p->mix_pro_r_hi, p->mix_pro_C, ctx->stream, &d_kinds, &d_ys);
             if (prc) return prc;
-            prc = launch_prologue(ctx, p->mix_pro_pk, p->mix_pro_n, p->mix_pro_C, p->mix_pro_fast, p->mix_pro_smem_old, io->coeffs,
+            prc = launch_prologue(ctx, p->mix_pro_pk, p->mix_pro_n, p->mix_pro_C, p->mix_pro_fast, p->mix_pro_smem_old, p->mix_pro_n2max, io->coeffs,
                                   p->mix_pro_dense ? io->dense_floor : nullptr, d_kinds, d_ys, (float *)ctx->spec.p - p->mix_pro_c_lo);
             if (prc) return prc;
         }

@@ -100,29 +100,35 @@ static bool prologue_is_fast(const DevPacket *h_pk, size_t n_pk, unsigned C, con
     return fast;
 }
 
-static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, size_t n_pk, unsigned C, bool fast, size_t smem_old,
+// n2max: the largest n/2 among the packets (sizes the per-row bin -> segment index).
+static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, size_t n_pk, unsigned C, bool fast, size_t smem_old, int n2max,
                            const float *res, const float *dense, const uint8_t *kinds, const uint32_t *ys, float *spec)
 {
     if (!n_pk) return LWB_OK;
+    const int words = std::max(1, (n2max + 31) >> 5);
     if (!fast)
         return launch(ctx, k_prologue, dim3((unsigned)n_pk), dim3(kPrologueThreads), smem_old, d_pk, res, dense, kinds, ys, spec);
-    // per (packet, channel) row: the packed flagged segments of its floor curve + their count (ctx scratch)
-    const size_t rows = n_pk * C, tab_bytes = rows * kSegStride * sizeof(uint4);
-    int rc = ensure(ctx, ctx->segtab, tab_bytes + rows + 64);
+    // per (packet, channel) row (ctx scratch): the packed flagged segments of its floor curve, the bin -> segment
+    // index (bitmap + prefix counts) and the segment count
+    const size_t rows = n_pk * C, tab_bytes = rows * kSegStride * sizeof(uint4), ix_bytes = rows * seg_index_stride(words);
+    int rc = ensure(ctx, ctx->segtab, tab_bytes + ix_bytes + rows + 64);
     if (rc) return rc;
     uint4 *tab = (uint4 *)ctx->segtab.p;
-    uint8_t *cnt = (uint8_t *)ctx->segtab.p + tab_bytes;
-    rc = launch(ctx, k_floor1_segments, dim3((unsigned)((rows + kSegRows - 1) / kSegRows)), dim3(kSegThreads), 0, d_pk, (uint32_t)rows, (int)C,
-                kinds, ys, tab, cnt);
+    unsigned char *ix = (unsigned char *)ctx->segtab.p + tab_bytes;
+    uint8_t *cnt = ix + ix_bytes;
+    rc = launch(ctx, k_floor1_segments, dim3((unsigned)((rows + kSegRows - 1) / kSegRows)), dim3(kSegThreads), floor1_segments_smem(words), d_pk,
+                (uint32_t)rows, (int)C, kinds, ys, tab, cnt, ix, words);
     if (rc) return rc;
     const size_t grid = std::min<size_t>(n_pk, (size_t)ctx->sm_count * (C > 2 ? 4 : 8));
     return launch(ctx, k_prologue_fused, dim3((unsigned)grid), dim3(kPfThreads), prologue_fused_smem((int)C), d_pk, (uint32_t)n_pk, res, dense,
-                  kinds, (const uint4 *)tab, (const uint8_t *)cnt, spec);
+                  kinds, (const uint4 *)tab, (const uint8_t *)cnt, (const unsigned char *)ix, words, spec);
 }
 static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, const DevPacket *h_pk, size_t n_pk, unsigned C, size_t smem_old,
                            const float *res, const float *dense, const uint8_t *kinds, const uint32_t *ys, float *spec)
 {
-    return launch_prologue(ctx, d_pk, n_pk, C, prologue_is_fast(h_pk, n_pk, C, res, dense, spec), smem_old, res, dense, kinds, ys, spec);
+    int n2max = 32;
+    for (size_t i = 0; i < n_pk; i++) n2max = std::max(n2max, h_pk[i].n >> 1);
+    return launch_prologue(ctx, d_pk, n_pk, C, prologue_is_fast(h_pk, n_pk, C, res, dense, spec), smem_old, n2max, res, dense, kinds, ys, spec);
 }
 
 // Host-side look at the floor kinds of rows [row_lo, row_hi) (one row per (packet, channel)).  Device-resident

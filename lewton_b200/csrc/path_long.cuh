@@ -487,7 +487,7 @@ static int try_long_residue(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, co
             plan->pro_c_lo = c_lo; plan->pro_c_hi = c_hi; plan->pro_r_lo = r_lo; plan->pro_r_hi = r_hi;
         }
     }
-    if ((rc = launch_prologue(ctx, d_pk, n_pk, C, fast, smem_old, d_res, d_dense, d_kinds, d_ys, d_spec))) return rc;
+    if ((rc = launch_prologue(ctx, d_pk, n_pk, C, fast, smem_old, kLongN2, d_res, d_dense, d_kinds, d_ys, d_spec))) return rc;
     bool h2 = false;
     rc = try_long(ctx, chains, n_chains, io, epoch, &h2, (const float *)ctx->spec.p, c_lo, plan, true);
     if (rc) return rc;

@@ -176,6 +176,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
     }
     if (need_dense && !io->dense_floor) return fail(ctx, LWB_ERR_INVALID, "dense_floor missing");
     int rc = LWB_OK;
+    const int n1max_all = n1max;         // largest blocksize of the batch (front stages); n1max below sizes the chain kernel
     if (!chain_sees_long) n1max = n0max;
     int wpc = std::max(1, std::min(8, n1max / 1024));
     while (wpc > 1 && (unsigned)wpc * maxc > 32) wpc >>= 1;
@@ -455,7 +456,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 CU(ctx, cudaStreamWaitEvent(sm, ctx->ev_in[k], 0));
             }
             if (residue && ck.np_)
-                if ((rc = launch_prologue(ctx, (const DevPacket *)(db + off_pro) + ck.p0, ck.np_, maxc, pro_fast, prologue_smem(maxc, kLongBs),
+                if ((rc = launch_prologue(ctx, (const DevPacket *)(db + off_pro) + ck.p0, ck.np_, maxc, pro_fast, prologue_smem(maxc, kLongBs), n1max_all >> 1,
                                           d_coeffs, need_dense ? d_dense : nullptr, d_kinds, d_ys, const_cast<float *>(d_spec))))
                     return rc;
             if ((rc = mixed_launch_rounds(ctx, ml, ck.rounds))) return rc;
@@ -480,6 +481,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 plan->mix_pro_smem_old = prologue_smem(maxc, kLongBs);
                 plan->mix_pro_c_lo = c_lo; plan->mix_pro_r_lo = r_lo; plan->mix_pro_r_hi = r_hi;
                 plan->mix_pro_dense = need_dense;
+                plan->mix_pro_n2max = n1max_all >> 1;
             }
         }
         if (host) {

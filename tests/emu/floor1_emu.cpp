@@ -41,8 +41,8 @@ extern "C" int lwb_emu_floor1(int mult, const uint32_t *xs, int nposts, const ui
         tab[m2 - 1] = tab[m2 - 2];                     // sentinel read past the last segment (never selected: x1 >= n2)
         int seg = 0;
         for (int k = 0; k < n2; k++) {
-            seg += (k >= (int)(tab[seg].y >> 16));
-            curve_packed[k] = (uint8_t)lwb::d_floor1_seg_y(tab[seg], k);
+            seg += lwb::d_floor1_seg_past(tab[seg], k);
+            curve_packed[k] = (uint8_t)lwb::d_floor1_seg_y<true>(tab[seg], k);
         }
     }
     return 0;
