@@ -118,19 +118,18 @@ template <bool SHIFT>
 __device__ __forceinline__ float4 d_floor_quad_one(const float *__restrict__ s_db, const uint4 *__restrict__ tab,
                                                    const unsigned char *__restrict__ ix, int words, int k0)
 {
-    // segment of bin k0 = (number of flagged posts with x <= k0) - 1; the post at x = 0 is always flagged
+    // segment of bin k = (number of flagged posts with x <= k) - 1; the post at x = 0 is always flagged.  The four
+    // bins of a quad share one bitmap word; each looks its segment up on its own, so that the four table reads are
+    // independent of one another (a chain "entry -> past its end? -> next entry" costs one L1/L2 latency per bin:
+    // ncu had 80 % of the stalls on the long scoreboard).
     const uint32_t bits = __ldg(reinterpret_cast<const uint32_t *>(ix) + (k0 >> 5));
-    int seg = (int)__ldg(ix + (size_t)words * 4 + (k0 >> 5)) + __popc(bits & (0xffffffffu >> (31 - (k0 & 31)))) - 1;
-    float f[4];
-    uint4 P = __ldg(tab + seg);
+    const int pre = (int)__ldg(ix + (size_t)words * 4 + (k0 >> 5)) - 1;
+    uint4 P[4];
 #pragma unroll
-    for (int b = 0; b < 4; b++) {
-        if (b) {
-            seg += d_floor1_seg_past(Seg4{P.x, P.y, P.z, P.w}, k0 + b);      // branch-free: reload (the same entry, mostly)
-            P = __ldg(tab + seg);
-        }
-        f[b] = s_db[d_floor1_seg_y<SHIFT>(Seg4{P.x, P.y, P.z, P.w}, k0 + b) & 255u];
-    }
+    for (int b = 0; b < 4; b++) P[b] = __ldg(tab + pre + __popc(bits & (0xffffffffu >> (31 - ((k0 & 31) + b)))));
+    float f[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) f[b] = s_db[d_floor1_seg_y<SHIFT>(Seg4{P[b].x, P[b].y, P[b].z, P[b].w}, k0 + b) & 255u];
     return make_float4(f[0], f[1], f[2], f[3]);
 }
 __device__ __forceinline__ float4 d_floor_quad(int kind, int cnt, const float *__restrict__ s_db, const uint4 *__restrict__ tab,
@@ -145,7 +144,7 @@ __device__ __forceinline__ float4 d_floor_quad(int kind, int cnt, const float *_
 
 // Persistent CTAs striding over the packets (grid = min(packets, a few CTAs per SM)).  Requires every coeff_off
 // (and the arena bases) to be multiples of 4 elements, <= 8 channels, a uniform channel count C.
-__global__ void __launch_bounds__(kPfThreads)
+__global__ void __launch_bounds__(kPfThreads, 6)
 k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float *__restrict__ residue, const float *__restrict__ dense_floor,
                  const uint8_t *__restrict__ floor_kind, const uint4 *__restrict__ segtab, const uint8_t *__restrict__ seg_cnt,
                  const unsigned char *__restrict__ seg_index, int words, float *__restrict__ spec)
@@ -183,11 +182,12 @@ k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float 
                     }
                 }
                 const float4 f0 = d_floor_quad(k0, c0, s_db, segtab + row0 * kSegStride, seg_index + row0 * ixs, words, 4 * q, dense_floor, e0);
+                float4 f1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (C == 2)
+                    f1 = d_floor_quad(k1, c1, s_db, segtab + (row0 + 1) * kSegStride, seg_index + (row0 + 1) * ixs, words, 4 * q, dense_floor, e1);
                 *reinterpret_cast<float4 *>(spec + e0) =
                     make_float4(__fmul_rn(f0.x, r0.x), __fmul_rn(f0.y, r0.y), __fmul_rn(f0.z, r0.z), __fmul_rn(f0.w, r0.w));
                 if (C == 2) {
-                    const float4 f1 = d_floor_quad(k1, c1, s_db, segtab + (row0 + 1) * kSegStride, seg_index + (row0 + 1) * ixs, words, 4 * q,
-                                                   dense_floor, e1);
                     *reinterpret_cast<float4 *>(spec + e1) =
                         make_float4(__fmul_rn(f1.x, r1.x), __fmul_rn(f1.y, r1.y), __fmul_rn(f1.z, r1.z), __fmul_rn(f1.w, r1.w));
                 }

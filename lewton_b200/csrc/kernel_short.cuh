@@ -205,12 +205,16 @@ LWB_HD void ola_s(V p_odd, V wlo, V whi, V prev_lo, V prev_hi, V &pcm_lo, V &pcm
 constexpr int kShortWarps = LWB_SHORT_WARPS;
 constexpr int kShortRing = LWB_SHORT_RING;
 constexpr int kSTwReg0 = LWB_STW_REG0, kSTwReg1 = LWB_STW_REG1;
-constexpr int kShortTileStride = 576;                         // bytes between the blocks' tiles of a stage: 512 + 64,
-                                                              // so that the LDS.128 of a quarter warp (2 blocks x 4 lanes) hit 8 bank groups
+constexpr int kShortTileStride = 576;                         // bytes between the blocks' tiles of a stage when they are copied
+                                                              // one by one: 512 + 64, so that the LDS.128 of a quarter warp
+                                                              // (2 blocks x 4 lanes) hit 8 bank groups; contiguous input
+                                                              // (one channel) arrives in one copy at stride 512
 constexpr int kShortStateOff = kShortOct * kShortTileStride;  // 4608: the run's state row (first octet of a run with history)
-constexpr int kShortStageBytes = kShortStateOff + kShortN2 * 4;   // 5120; the first 4096 bytes double as the transpose scratch
-constexpr int kShortDescSlots = kShortRing + 1;               // run descriptors the producer may be ahead of the consumer
-constexpr size_t kShortSmemBytes = 128 + (size_t)kShortWarps * kShortRing * kShortStageBytes + (size_t)kShortPackFloats * 4 +
+constexpr int kShortStageBytes = 5120;                        // 4608 + 512; the first 4096 bytes double as the transpose scratch
+                                                              // and then as the PCM staging; a multiple of 1024 (XOR addressing)
+constexpr int kShortFetch = 3;                                // run descriptors are fetched this many runs ahead of the producer
+constexpr int kShortDescSlots = kShortFetch + kShortRing + 2; // descriptor slots a fetch may be ahead of the consumer
+constexpr size_t kShortSmemBytes = 1024 + (size_t)kShortWarps * kShortRing * kShortStageBytes + (size_t)kShortPackFloats * 4 +
                                    (size_t)kShortWarps * kShortDescSlots * sizeof(ShortRun) + kShortWarps * kShortRing * 8 + 64;
 
 struct TwShort {
@@ -223,23 +227,61 @@ struct TwShort {
     }
 };
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+// PCM staging: one sample as OutT (samples.rs:86-103)
+__device__ __forceinline__ void sts_pcm(uint32_t addr, float v, float *) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_pcm(uint32_t addr, float v, int16_t *)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((short)d_sample_i16(v)) : "memory");
+}
+// four staged samples of one lane -> global, streaming
+__device__ __forceinline__ void copy_out4(float *dst, uint32_t src)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src) : "memory");
+    __stcs(reinterpret_cast<float4 *>(dst), v);
+}
+__device__ __forceinline__ void copy_out4(int16_t *dst, uint32_t src)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(src) : "memory");
+    __stcs(reinterpret_cast<uint2 *>(dst), v);
+}
+
 // runs: one descriptor per run; pack: short_build_pack of the setup's blocksize-8 tables.
 //
 // Runs are dealt to the warps round robin (run r -> warp r mod W): short-block runs are short -- a burst between
 // long blocks is one octet -- so the per-run latencies (descriptor, state row, first tiles) must overlap with the
-// previous runs' arithmetic.  With a static deal every warp knows its future: it PRODUCES a stream of octets
-// (TMA copies of up to eight 512-byte spectrum blocks, plus the 512-byte state row in front of a run with history,
-// all counted on the stage's mbarrier) up to kShortRing stages ahead of where it CONSUMES them, across run
-// boundaries; the descriptor of the run after the one being produced is already on its way into registers.
+// previous runs' arithmetic.  With a static deal every warp knows its future:
+//   * descriptors arrive by cp.async in a small shared ring, kShortFetch runs ahead of their first use;
+//   * the warp PRODUCES a stream of octets (TMA copies of up to eight 512-byte spectrum blocks -- one copy when the
+//     blocks are contiguous --, plus the 512-byte state row in front of a run with history, all counted on the stage's
+//     mbarrier) up to kShortRing stages ahead of where it CONSUMES them, across run boundaries.
+// PCM leaves through shared memory: the lanes' samples are staged (swizzled, conflict-free) and go out as one
+// 128-bit (f32) / 64-bit (i16) store per lane and packet, 512 / 256 contiguous bytes per instruction, instead of
+// 16-byte pieces of eight different lines per instruction (ncu: the L1 data pipe was the limiter at 81 %).
 template <typename OutT>
 __global__ void __launch_bounds__(kShortWarps * 32, 1)
 k_short(const ShortRun *__restrict__ runs, uint32_t n_runs, const float *__restrict__ pack)
 {
     extern __shared__ __align__(128) unsigned char smem_s[];
+    constexpr uint32_t ESZ = sizeof(OutT);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l = lane & 3, blk = lane >> 2;
     const uint32_t raw_s = smem_u32(smem_s);
-    unsigned char *base = smem_s + ((128u - (raw_s & 127u)) & 127u);
+    unsigned char *base = smem_s + ((1024u - (raw_s & 1023u)) & 1023u);
     constexpr size_t kRingBytes = (size_t)kShortWarps * kShortRing * kShortStageBytes;
     unsigned char *ring = base + (size_t)warp * kShortRing * kShortStageBytes;
     V *s_pack = reinterpret_cast<V *>(base + kRingBytes);
@@ -261,28 +303,39 @@ k_short(const ShortRun *__restrict__ runs, uint32_t n_runs, const float *__restr
     for (int s = kSTwReg0; s < kSTwReg1; s++) twR[s - kSTwReg0] = s_pack[s * 32 + lane];
     const TwShort tw{twR, s_pack + lane};
 
-    const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars);
+    const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars), desc_s = smem_u32(s_desc);
     // Transpose addresses (bytes inside the stage; E plane at +0, O plane at +2048).  4 * swzS(b, c) splits into a
     // lane part, an additive slot part (an immediate of the access) and a slot part XORed into bits 2..3 -- the stage
-    // bases are 16-byte aligned, so that XOR can be applied to the full address:
+    // bases are 1024-byte aligned, so that XOR can be applied to the full address:
     //   phase A, c = cl + 8 j:   lane part 4 * swzS(b, cl),   + (j << 8),         ^ 4 * (j >> 1)
     //   phase C, c = 8 T + j:    lane part 4 * swzS(b, 8 T),  + ((j >> 2) << 7),  ^ 4 * (j & 3)
     const uint32_t wA0 = 4u * (uint32_t)swzS(blk, elemA_s(l, 0, 0)), wA1 = 4u * (uint32_t)swzS(blk, elemA_s(l, 0, 1));
     const uint32_t wC0 = 4u * (uint32_t)swzS(blk, elemC_s(l, 0, 0)), wC1 = 4u * (uint32_t)swzS(blk, elemC_s(l, 0, 1));
+    // PCM staging: sample m of block b sits in row b (128 samples) at chunk (m >> 2) ^ b, position m & 3 -- the XOR
+    // with b spreads the eight blocks' equal sample indices over the banks.  Lane parts for positions l and 3 - l;
+    // the chunk of a slot is a compile-time constant XORed in.
+    const uint32_t wP0 = (128u * ESZ + 4u * ESZ) * (uint32_t)blk + ESZ * (uint32_t)l;
+    const uint32_t wP1 = (128u * ESZ + 4u * ESZ) * (uint32_t)blk + ESZ * (uint32_t)(3 - l);
 
     const uint32_t W = gridDim.x * kShortWarps, gw = blockIdx.x * kShortWarps + warp;
     if (gw >= n_runs) return;
-    // ---- producer state (warp-uniform) ----
-    uint32_t p_run = gw, p_oct = 0, p_slot = 0, p_stage = 0, in_flight = 0;
     const uint4 *rq = reinterpret_cast<const uint4 *>(runs);
-    uint4 pd0 = __ldg(rq + 3 * (size_t)p_run), pd1 = __ldg(rq + 3 * (size_t)p_run + 1), pd2 = __ldg(rq + 3 * (size_t)p_run + 2);
-    uint4 nd0 = pd0, nd1 = pd1, nd2 = pd2;                 // descriptor of run p_run + W, loaded one run ahead
-    if (p_run + W < n_runs) {
-        nd0 = __ldg(rq + 3 * (size_t)(p_run + W)); nd1 = __ldg(rq + 3 * (size_t)(p_run + W) + 1); nd2 = __ldg(rq + 3 * (size_t)(p_run + W) + 2);
-    }
-    if (lane == 0) { s_desc[0] = pd0; s_desc[1] = pd1; s_desc[2] = pd2; }
+    // ---- descriptor fetch (cp.async groups are per thread: lanes 0..2 copy one quad each, everybody commits / waits) ----
+    uint32_t f_run = gw, f_slot = 0;
+    auto fetch = [&]() {
+        if (lane < 3 && f_run < n_runs) cp_async16(desc_s + f_slot * (uint32_t)sizeof(ShortRun) + lane * 16, rq + 3 * (size_t)f_run + lane);
+        cp_async_commit();
+        f_run += W;
+        f_slot = (f_slot + 1 == (uint32_t)kShortDescSlots) ? 0 : f_slot + 1;
+    };
+#pragma unroll
+    for (int i = 0; i <= kShortFetch; i++) fetch();
+    cp_async_wait<kShortFetch>();
     __syncwarp();
+    // ---- producer state (warp-uniform) ----
     // ShortRun fields inside the three quads: q0 = {in, out}, q1 = {state, in_stride, n_packets}, q2 = {has_prev | write_state << 8, ...}
+    uint32_t p_run = gw, p_oct = 0, p_slot = 0, p_stage = 0;
+    uint4 pd0 = s_desc[0], pd1 = s_desc[1], pd2 = s_desc[2];
     auto produce = [&]() {                                   // whole warp: issue the next octet of the producer's run
         const float *in = reinterpret_cast<const float *>(((unsigned long long)pd0.y << 32) | pd0.x);
         const float *state = reinterpret_cast<const float *>(((unsigned long long)pd1.y << 32) | pd1.x);
@@ -290,30 +343,31 @@ k_short(const ShortRun *__restrict__ runs, uint32_t n_runs, const float *__restr
         const bool with_state = p_oct == 0 && (pd2.x & 0xffu);
         const uint32_t nb = min((uint32_t)kShortOct, npk - p_oct * kShortOct);
         const uint32_t bar = bars_s + 8 * p_stage, dst = ring_s + p_stage * kShortStageBytes;
+        const bool contig = in_stride == (uint32_t)kShortN2;
         if (lane == 0) mbar_expect_tx(bar, (nb + (with_state ? 1u : 0u)) * (uint32_t)(kShortN2 * 4));
         __syncwarp();
-        if ((uint32_t)lane < nb) {
-            fence_proxy_async();            // the stage was written through the generic proxy (transpose) before
+        if (contig) {
+            if (lane == 0) {
+                fence_proxy_async();        // the stage was written through the generic proxy (transpose, staging) before
+                tma_load_1d(dst, in + (size_t)(p_oct * kShortOct) * kShortN2, nb * (uint32_t)(kShortN2 * 4), bar);
+            }
+        } else if ((uint32_t)lane < nb) {
+            fence_proxy_async();
             tma_load_1d(dst + lane * kShortTileStride, in + (size_t)(p_oct * kShortOct + lane) * in_stride, kShortN2 * 4, bar);
-        } else if (lane == 8 && with_state) {
+        }
+        if (lane == 8 && with_state) {
             fence_proxy_async();
             tma_load_1d(dst + kShortStateOff, state, kShortN2 * 4, bar);
         }
         p_stage = (p_stage + 1 == (uint32_t)kShortRing) ? 0 : p_stage + 1;
-        in_flight++;
         if (++p_oct * kShortOct >= npk) {                    // on to the next run of this warp
             p_run += W;
             p_oct = 0;
-            pd0 = nd0; pd1 = nd1; pd2 = nd2;
-            if (p_run < n_runs) {
-                p_slot = (p_slot + 1 == (uint32_t)kShortDescSlots) ? 0 : p_slot + 1;
-                if (lane == 0) { s_desc[3 * p_slot] = pd0; s_desc[3 * p_slot + 1] = pd1; s_desc[3 * p_slot + 2] = pd2; }
-                __syncwarp();
-                if (p_run + W < n_runs) {
-                    nd0 = __ldg(rq + 3 * (size_t)(p_run + W)); nd1 = __ldg(rq + 3 * (size_t)(p_run + W) + 1);
-                    nd2 = __ldg(rq + 3 * (size_t)(p_run + W) + 2);
-                }
-            }
+            p_slot = (p_slot + 1 == (uint32_t)kShortDescSlots) ? 0 : p_slot + 1;
+            fetch();                                         // run p_run + kShortFetch * W
+            cp_async_wait<kShortFetch>();                    // run p_run's descriptor (fetched kShortFetch runs ago) has landed
+            __syncwarp();
+            if (p_run < n_runs) { pd0 = s_desc[3 * p_slot]; pd1 = s_desc[3 * p_slot + 1]; pd2 = s_desc[3 * p_slot + 2]; }
         }
     };
     for (int i = 0; i < kShortRing; i++)
@@ -327,6 +381,7 @@ k_short(const ShortRun *__restrict__ runs, uint32_t n_runs, const float *__restr
         float *state = reinterpret_cast<float *>(((unsigned long long)d1.y << 32) | d1.x);
         const uint32_t npk = d1.w;
         const bool has_prev = (d2.x & 0xffu) != 0, write_state = ((d2.x >> 8) & 0xffu) != 0;
+        const bool contig = d1.z == (uint32_t)kShortN2;
         const uint32_t n_oct = (npk + kShortOct - 1) / kShortOct;
         const uint32_t koff = has_prev ? 0u : 1u;                // packet 0 emits nothing then: packet k lands at 128 (k - 1)
 
@@ -340,7 +395,8 @@ k_short(const ShortRun *__restrict__ runs, uint32_t n_runs, const float *__restr
             mbar_wait(bars_s + 8 * slot_i, (phase_bits >> slot_i) & 1u);
             phase_bits ^= 1u << slot_i;
             V O[8], E[8];
-            phase_a_s(reinterpret_cast<const float *>(stage_p + blk * kShortTileStride), l, tw, O, E);
+            phase_a_s(reinterpret_cast<const float *>(stage_p + blk * (contig ? kShortN2 * 4 : kShortTileStride)), l, tw, O, E);
+            const bool first0 = (o == 0 && blk == 0);
             __syncwarp();           // every lane has consumed its quads: the stage becomes the scratch
             {
                 const uint32_t a0 = stage_s + wA0, a1 = stage_s + wA1;
@@ -359,40 +415,55 @@ k_short(const ShortRun *__restrict__ runs, uint32_t n_runs, const float *__restr
                     lds_eo(((c1 ^ (4u * (j & 3))) + ((j >> 2) << 7)), E[j].y, O[j].y);
                 }
             }
+            __syncwarp();           // scratch consumed: the same bytes now take the PCM staging
             phase_c_fft<1>(tw, &O, &E);
-            const uint32_t k = o * kShortOct + blk;                          // this lane's packet
-            const bool first0 = (o == 0 && blk == 0);
-            const bool emit = k < npk && !(first0 && !has_prev);
-            OutT *ob = out + (ptrdiff_t)((int)k - (int)koff) * kShortN2;
-            const float *st_tile = reinterpret_cast<const float *>(stage_p + kShortStateOff);
+            const uint32_t p0 = stage_s + wP0, p1 = stage_s + wP1;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 V p_odd;
                 step8_s(tw(P_B0 + j), tw(P_B1 + j), O[j], E[j], p_odd, pe[j]);
-                // previous block's right half: block b-1 of this octet (4 lanes down), or the last block of the
-                // previous octet for block 0
-                V up, cr;
-                up.x = __shfl_up_sync(0xffffffffu, pe[j].x, 4);
-                up.y = __shfl_up_sync(0xffffffffu, pe[j].y, 4);
-                cr.x = __shfl_sync(0xffffffffu, carry[j].x, 28 + l);
-                cr.y = __shfl_sync(0xffffffffu, carry[j].y, 28 + l);
-                V plo = blk ? up : cr, phi = plo;
-                const int mx = outIndex_s(l, j, 0), my = outIndex_s(l, j, 1);
-                if (first0 && has_prev) {                        // an imported state need not be symmetric
-                    plo = V{st_tile[mx], st_tile[my]};
-                    phi = V{st_tile[127 - mx], st_tile[127 - my]};
+                // previous block's right half: block b-1 of this octet sits 4 lanes down; block 0 takes the last block of
+                // the previous octet, which the lanes of block 7 (whose own p_even nobody needs before the next octet)
+                // put on the same shuffle
+                const V src = blk == 7 ? carry[j] : pe[j];
+                V plo;
+                plo.x = __shfl_sync(0xffffffffu, src.x, (lane + 28) & 31);
+                plo.y = __shfl_sync(0xffffffffu, src.y, (lane + 28) & 31);
+                V phi = plo;
+                if (first0 && has_prev) {                        // the stream state (an imported one need not be symmetric);
+                    const int mx = outIndex_s(l, j, 0), my = outIndex_s(l, j, 1);      // its tile lies beyond the scratch / staging bytes
+                    const uint32_t sa = stage_s + kShortStateOff;
+                    plo = V{lds_f32(sa + 4 * mx), lds_f32(sa + 4 * my)};
+                    phi = V{lds_f32(sa + 4 * (127 - mx)), lds_f32(sa + 4 * (127 - my))};
                 }
                 V lo, hi;
                 ola_s(p_odd, tw(P_WLO + j), tw(P_WHI + j), plo, phi, lo, hi);
-                if (emit) {
-                    st_pcm(ob + mx, lo.x); st_pcm(ob + my, lo.y);
-                    st_pcm(ob + 127 - mx, hi.x); st_pcm(ob + 127 - my, hi.y);
+                // stage: odd slots hold sample 8 r + l in .x and 8 r + 7 - l in .y, even slots the other way round
+                constexpr uint32_t CH = 4u * ESZ;
+                const int r = rev3(j);
+                const uint32_t cA = CH * (2 * r), cB = CH * (2 * r + 1), cC = CH * (31 - 2 * r), cD = CH * (30 - 2 * r);
+                if (j & 1) {
+                    sts_pcm(p0 ^ cA, lo.x, (OutT *)nullptr); sts_pcm(p1 ^ cB, lo.y, (OutT *)nullptr);
+                    sts_pcm(p1 ^ cC, hi.x, (OutT *)nullptr); sts_pcm(p0 ^ cD, hi.y, (OutT *)nullptr);
+                } else {
+                    sts_pcm(p1 ^ cB, lo.x, (OutT *)nullptr); sts_pcm(p0 ^ cA, lo.y, (OutT *)nullptr);
+                    sts_pcm(p0 ^ cD, hi.x, (OutT *)nullptr); sts_pcm(p1 ^ cC, hi.y, (OutT *)nullptr);
                 }
             }
 #pragma unroll
             for (int j = 0; j < 8; j++) carry[j] = pe[j];
-            __syncwarp();                                        // scratch and state tile consumed: the stage is free
-            in_flight--;
+            __syncwarp();
+            // one packet per instruction: lane L copies samples [4 L, 4 L + 4) of packet 8 o + i
+            {
+                const uint32_t nb = min((uint32_t)kShortOct, npk - o * kShortOct);
+                OutT *og = out + (ptrdiff_t)((int)(o * kShortOct) - (int)koff) * kShortN2 + 4 * lane;
+#pragma unroll
+                for (int i = 0; i < kShortOct; i++) {
+                    if ((uint32_t)i < nb && !(o == 0 && i == 0 && !has_prev))
+                        copy_out4(og + i * kShortN2, stage_s + (128u * ESZ) * i + (4u * ESZ) * (uint32_t)(lane ^ i));
+                }
+            }
+            __syncwarp();                                        // staging and state tile consumed: the stage is free
             if (p_run < n_runs) produce();
             slot_i = (slot_i + 1 == (uint32_t)kShortRing) ? 0 : slot_i + 1;
         }

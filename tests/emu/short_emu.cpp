@@ -132,3 +132,53 @@ extern "C" int lwb_emu_short_run(const float *pack_f, const float *spectrum, int
         }
     return g_conf;
 }
+
+// Worst bank-conflict degree of the PCM staging of kernel_short.cuh (esz = 4: f32, 2: i16): the 32 stores of a
+// (slot, value) and the per-packet vector loads.  Mirrors the address arithmetic of k_short (wP0 / wP1 ^ chunk).
+extern "C" int lwb_emu_short_staging_conflicts(int esz)
+{
+    int worst = 0;
+    auto banks = [&](const int addr[32], int bytes) {
+        // an access of `bytes` per lane is served in groups of 128 / bytes... conservatively: count distinct 32-bit words per bank
+        int lanes_per_phase = bytes >= 16 ? 8 : bytes == 8 ? 16 : 32;
+        for (int ph = 0; ph < 32 / lanes_per_phase; ph++) {
+            int cnt[32] = {0}, word[32][8] = {{0}}, nw[32] = {0};
+            for (int i = 0; i < lanes_per_phase; i++) {
+                const int a = addr[ph * lanes_per_phase + i];
+                for (int w = a >> 2; w < (a + (bytes > 4 ? bytes : 4) + 3) >> 2 && w <= (a + bytes - 1) >> 2; w++) {
+                    const int bk = w & 31;
+                    bool seen = false;
+                    for (int q = 0; q < nw[bk]; q++) seen |= word[bk][q] == w;
+                    if (!seen && nw[bk] < 8) { word[bk][nw[bk]++] = w; cnt[bk]++; }
+                }
+            }
+            for (int b = 0; b < 32; b++) worst = cnt[b] > worst ? cnt[b] : worst;
+        }
+    };
+    const int CH = 4 * esz;
+    for (int j = 0; j < 8; j++) {
+        const int r = rev3(j);
+        const int cA = CH * (2 * r), cB = CH * (2 * r + 1), cC = CH * (31 - 2 * r), cD = CH * (30 - 2 * r);
+        const int consts[4] = {cA, cB, cC, cD};
+        const int which[4] = {0, 1, 1, 0};               // p0 or p1
+        for (int v = 0; v < 4; v++) {
+            int addr[32];
+            for (int lane = 0; lane < 32; lane++) {
+                const int l = lane & 3, b = lane >> 2;
+                const int p = (128 * esz + 4 * esz) * b + esz * (which[v] ? 3 - l : l);
+                addr[lane] = p ^ consts[v];
+                // the staged sample must land where the copy-out expects it: row b, chunk (m >> 2) ^ b, position m & 3
+                const int m_nat = v == 0 ? 8 * r + l : v == 1 ? 8 * r + 7 - l : v == 2 ? 127 - (8 * r + l) : 127 - (8 * r + 7 - l);
+                const int want = 128 * esz * b + 4 * esz * (((m_nat >> 2) ^ b)) + esz * (m_nat & 3);
+                if (addr[lane] != want) return -1;
+            }
+            banks(addr, esz);
+        }
+    }
+    for (int i = 0; i < 8; i++) {
+        int addr[32];
+        for (int lane = 0; lane < 32; lane++) addr[lane] = 128 * esz * i + 4 * esz * (lane ^ i);
+        banks(addr, 4 * esz);
+    }
+    return worst;
+}

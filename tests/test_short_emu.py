@@ -88,3 +88,10 @@ def test_emulated_short_kernel_special_values(emu, pack, oracle):
     emu.lwb_emu_short_run(P(pack), P(spec), 11, 0, P(st), P(out))
     got = out[:10].ravel()
     assert np.all((got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want)))
+
+
+@pytest.mark.parametrize("esz", [4, 2])
+def test_short_kernel_pcm_staging_is_consistent_and_conflict_free(emu, esz):
+    """The swizzled PCM staging of k_short: every staged sample sits where the per-packet vector copy reads it,
+    and neither the 32 staging stores nor the vector loads have shared-memory bank conflicts."""
+    assert emu.lwb_emu_short_staging_conflicts(esz) == 1
