@@ -109,27 +109,30 @@ k_floor1_segments(const DevPacket *__restrict__ pkts, uint32_t n_rows, int C, co
 }
 
 constexpr int kPfThreads = 256;
-// dynamic shared memory: (more than one channel) the coupling staging
-inline size_t prologue_fused_smem(int channels) { return channels > 1 ? (size_t)channels * kPfThreads * sizeof(float4) : 0; }
+constexpr int kPfMaxWords = 128;       // bitmap words per row: n/2 <= 4096 bins
+// dynamic shared memory per channel: the row's segment table and bin -> segment index, and (more than one channel)
+// the coupling staging
+__host__ __device__ inline size_t pf_row_bytes(int words) { return kSegStride * sizeof(uint4) + seg_index_stride(words); }
+inline size_t prologue_fused_smem(int channels, int words)
+{
+    return (size_t)channels * pf_row_bytes(words) + (channels > 1 ? (size_t)channels * kPfThreads * sizeof(float4) : 0);
+}
 
-// Floor values of the 4 bins [k0, k0 + 4) of one channel row.  The row's tables are read through the read-only path:
-// a CTA works on one packet, so its rows (a few hundred bytes each) sit in L1 after the first touch.
+// Floor values of the 4 bins [k0, k0 + 4) of one channel row, tables in shared memory.
 template <bool SHIFT>
 __device__ __forceinline__ float4 d_floor_quad_one(const float *__restrict__ s_db, const uint4 *__restrict__ tab,
                                                    const unsigned char *__restrict__ ix, int words, int k0)
 {
     // segment of bin k = (number of flagged posts with x <= k) - 1; the post at x = 0 is always flagged.  The four
-    // bins of a quad share one bitmap word; each looks its segment up on its own, so that the four table reads are
-    // independent of one another (a chain "entry -> past its end? -> next entry" costs one L1/L2 latency per bin:
-    // ncu had 80 % of the stalls on the long scoreboard).
-    const uint32_t bits = __ldg(reinterpret_cast<const uint32_t *>(ix) + (k0 >> 5));
-    const int pre = (int)__ldg(ix + (size_t)words * 4 + (k0 >> 5)) - 1;
-    uint4 P[4];
-#pragma unroll
-    for (int b = 0; b < 4; b++) P[b] = __ldg(tab + pre + __popc(bits & (0xffffffffu >> (31 - ((k0 & 31) + b)))));
+    // bins of a quad share one bitmap word and look their segments up independently of one another.
+    const uint32_t bits = reinterpret_cast<const uint32_t *>(ix)[k0 >> 5];
+    const int pre = (int)ix[(size_t)words * 4 + (k0 >> 5)] - 1;
     float f[4];
 #pragma unroll
-    for (int b = 0; b < 4; b++) f[b] = s_db[d_floor1_seg_y<SHIFT>(Seg4{P[b].x, P[b].y, P[b].z, P[b].w}, k0 + b) & 255u];
+    for (int b = 0; b < 4; b++) {
+        const uint4 P = tab[pre + __popc(bits & (0xffffffffu >> (31 - ((k0 & 31) + b))))];
+        f[b] = s_db[d_floor1_seg_y<SHIFT>(Seg4{P.x, P.y, P.z, P.w}, k0 + b) & 255u];
+    }
     return make_float4(f[0], f[1], f[2], f[3]);
 }
 __device__ __forceinline__ float4 d_floor_quad(int kind, int cnt, const float *__restrict__ s_db, const uint4 *__restrict__ tab,
@@ -144,7 +147,9 @@ __device__ __forceinline__ float4 d_floor_quad(int kind, int cnt, const float *_
 
 // Persistent CTAs striding over the packets (grid = min(packets, a few CTAs per SM)).  Requires every coeff_off
 // (and the arena bases) to be multiples of 4 elements, <= 8 channels, a uniform channel count C.
-__global__ void __launch_bounds__(kPfThreads, 6)
+// Per packet: every global read the packet needs -- residue quads, the rows' segment tables and indices -- is issued
+// at the top (one exposed memory latency), the tables land in shared memory, and the per-bin work runs out of it.
+__global__ void __launch_bounds__(kPfThreads, 4)
 k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float *__restrict__ residue, const float *__restrict__ dense_floor,
                  const uint8_t *__restrict__ floor_kind, const uint4 *__restrict__ segtab, const uint8_t *__restrict__ seg_cnt,
                  const unsigned char *__restrict__ seg_index, int words, float *__restrict__ spec)
@@ -153,25 +158,48 @@ k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float 
     __shared__ float s_db[256];
     const int tid = threadIdx.x;
     s_db[tid] = c_inverse_db[tid];
-    __syncthreads();
-    float4 *s_r = reinterpret_cast<float4 *>(pf_smem);            // [C][kPfThreads] when C > 1
-    const size_t ixs = seg_index_stride(words);
+    if (blockIdx.x >= n_pk) return;
+    const int C = pkts[blockIdx.x].channels;                      // uniform over the batch
+    const size_t ixs = seg_index_stride(words), rowb = pf_row_bytes(words);
+    const int row_q = (int)(rowb >> 4), tab_q = kSegStride;       // 16-byte quads per row: table, then index
+    float4 *s_r = reinterpret_cast<float4 *>(pf_smem + (size_t)C * rowb);     // [C][kPfThreads] when C > 1
     for (uint32_t pk = blockIdx.x; pk < n_pk; pk += gridDim.x) {
         const DevPacket &p = pkts[pk];
         const DevSetup &su = *p.setup;
         const DevMapping &mp = su.mappings[p.mapping];
-        const int C = p.channels, n2 = p.n >> 1, nsteps = mp.n_coupling;
+        const int n2 = p.n >> 1, nsteps = mp.n_coupling;
         const uint8_t *kinds = floor_kind + p.pkt_index * C;
         const uint64_t base = p.coeff_off;
         const size_t row0 = (size_t)pk * C;
-        if (C <= 2 && nsteps <= 1) {
+        const bool stereo = C <= 2 && nsteps <= 1;
+        // residue quads of this thread (first pass of the bin loop) -- issued before the table copy
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        if (stereo && tid < (n2 >> 2)) {
+            r0 = *reinterpret_cast<const float4 *>(residue + base + 4 * (uint64_t)tid);
+            if (C == 2) r1 = *reinterpret_cast<const float4 *>(residue + base + n2 + 4 * (uint64_t)tid);
+        }
+        __syncthreads();                                          // the previous packet is done with the shared tables
+        for (int i = tid; i < C * row_q; i += kPfThreads) {
+            const int c = i / row_q, j = i - c * row_q;
+            const int cnt = seg_cnt[row0 + c] & 0x7f;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (j < tab_q) { if (j <= cnt && cnt) v = segtab[(row0 + c) * kSegStride + j]; }
+            else if (cnt) v = reinterpret_cast<const uint4 *>(seg_index + (row0 + c) * ixs)[j - tab_q];
+            reinterpret_cast<uint4 *>(pf_smem)[i] = v;
+        }
+        __syncthreads();
+        if (stereo) {
             const int k0 = kinds[0], k1 = C == 2 ? kinds[1] : LWB_FLOOR_UNUSED;
             const int c0 = seg_cnt[row0], c1 = C == 2 ? seg_cnt[row0 + 1] : 0;
             const bool swapped = nsteps == 1 && mp.mag[0] == 1;          // (magnitude, angle) = (1, 0)
+            const uint4 *t0 = reinterpret_cast<const uint4 *>(pf_smem), *t1 = reinterpret_cast<const uint4 *>(pf_smem + rowb);
+            const unsigned char *x0 = pf_smem + (size_t)tab_q * 16, *x1 = x0 + rowb;
             for (int q = tid; q < (n2 >> 2); q += kPfThreads) {
                 const uint64_t e0 = base + 4 * (uint64_t)q, e1 = e0 + n2;
-                float4 r0 = *reinterpret_cast<const float4 *>(residue + e0);
-                float4 r1 = C == 2 ? *reinterpret_cast<const float4 *>(residue + e1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q != tid) {                                   // blocks of more than 1024 bins: further passes
+                    r0 = *reinterpret_cast<const float4 *>(residue + e0);
+                    if (C == 2) r1 = *reinterpret_cast<const float4 *>(residue + e1);
+                }
                 if (nsteps == 1) {
                     if (swapped) {
                         d_inverse_couple(r1.x, r0.x); d_inverse_couple(r1.y, r0.y);
@@ -181,13 +209,11 @@ k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float 
                         d_inverse_couple(r0.z, r1.z); d_inverse_couple(r0.w, r1.w);
                     }
                 }
-                const float4 f0 = d_floor_quad(k0, c0, s_db, segtab + row0 * kSegStride, seg_index + row0 * ixs, words, 4 * q, dense_floor, e0);
-                float4 f1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (C == 2)
-                    f1 = d_floor_quad(k1, c1, s_db, segtab + (row0 + 1) * kSegStride, seg_index + (row0 + 1) * ixs, words, 4 * q, dense_floor, e1);
+                const float4 f0 = d_floor_quad(k0, c0, s_db, t0, x0, words, 4 * q, dense_floor, e0);
                 *reinterpret_cast<float4 *>(spec + e0) =
                     make_float4(__fmul_rn(f0.x, r0.x), __fmul_rn(f0.y, r0.y), __fmul_rn(f0.z, r0.z), __fmul_rn(f0.w, r0.w));
                 if (C == 2) {
+                    const float4 f1 = d_floor_quad(k1, c1, s_db, t1, x1, words, 4 * q, dense_floor, e1);
                     *reinterpret_cast<float4 *>(spec + e1) =
                         make_float4(__fmul_rn(f1.x, r1.x), __fmul_rn(f1.y, r1.y), __fmul_rn(f1.z, r1.z), __fmul_rn(f1.w, r1.w));
                 }
@@ -209,8 +235,8 @@ k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float 
             for (int c = 0; c < C; c++) {
                 const uint64_t ec = e + (uint64_t)c * n2;
                 const float4 r = s_r[c * kPfThreads + tid];
-                const float4 f = d_floor_quad(kinds[c], seg_cnt[row0 + c], s_db, segtab + (row0 + c) * kSegStride, seg_index + (row0 + c) * ixs,
-                                              words, 4 * q, dense_floor, ec);
+                const float4 f = d_floor_quad(kinds[c], seg_cnt[row0 + c], s_db, reinterpret_cast<const uint4 *>(pf_smem + c * rowb),
+                                              pf_smem + c * rowb + (size_t)tab_q * 16, words, 4 * q, dense_floor, ec);
                 *reinterpret_cast<float4 *>(spec + ec) =
                     make_float4(__fmul_rn(f.x, r.x), __fmul_rn(f.y, r.y), __fmul_rn(f.z, r.z), __fmul_rn(f.w, r.w));
             }
@@ -221,6 +247,7 @@ k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float 
 inline void prologue_kernel_configure()
 {
     cudaFuncSetAttribute(k_floor1_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)floor1_segments_smem(128));
+    cudaFuncSetAttribute(k_prologue_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prologue_fused_smem(8, kPfMaxWords));
 }
 
 }  // namespace lwb

@@ -120,7 +120,7 @@ static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, size_t n_pk, uns
                 (uint32_t)rows, (int)C, kinds, ys, tab, cnt, ix, words);
     if (rc) return rc;
     const size_t grid = std::min<size_t>(n_pk, (size_t)ctx->sm_count * (C > 2 ? 4 : 8));
-    return launch(ctx, k_prologue_fused, dim3((unsigned)grid), dim3(kPfThreads), prologue_fused_smem((int)C), d_pk, (uint32_t)n_pk, res, dense,
+    return launch(ctx, k_prologue_fused, dim3((unsigned)grid), dim3(kPfThreads), prologue_fused_smem((int)C, words), d_pk, (uint32_t)n_pk, res, dense,
                   kinds, (const uint4 *)tab, (const uint8_t *)cnt, (const unsigned char *)ix, words, spec);
 }
 static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, const DevPacket *h_pk, size_t n_pk, unsigned C, size_t smem_old,
