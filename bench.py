@@ -275,6 +275,47 @@ def main():
 
     sustained = {"value": samples_step / (sus_ms / n_sus * 1e-3) / 1e6, "unit": "Msamples/s", "steps": n_sus,
                  "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus}
+
+    # ---- batch scatter + compute + PCM gather (north_star: "NCCL over NVLink used only for the batch scatter/gather") ----
+    # The whole batch (world x S streams) starts and ends in rank 0's HBM: grouped ncclSend/ncclRecv out, the same step,
+    # grouped ncclSend/ncclRecv back.  Reported beside the compute-only value; the root's link, not the kernels, bounds it.
+    with_gather = None
+    if world > 1:
+        from lewton_b200.sharding import gather_streams, scatter_streams
+        n_all = S * world
+        spec_all = (torch.randn((n_all, P, C, N2), generator=gen, device="cuda", dtype=torch.float32) * 1e-2) if rank == 0 else None
+        pcm_all = torch.empty((n_all, C, stride), device="cuda", dtype=torch.float32) if rank == 0 else None
+        g_steps = max(3, min(args.steps, 10))
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(g_steps)]
+        with torch.cuda.stream(stream):              # NCCL work is ordered against the library's stream
+            for _ in range(2):
+                scatter_streams(spec_all, spec, n_all)
+                step()
+                gather_streams(pcm, pcm_all, n_all)
+            barrier()
+            for i in range(g_steps):
+                ev[i][0].record(stream)
+                scatter_streams(spec_all, spec, n_all)
+                ev[i][1].record(stream)
+                step()
+                ev[i][2].record(stream)
+                gather_streams(pcm, pcm_all, n_all)
+                ev[i][3].record(stream)
+            barrier()
+        tot = ev[0][0].elapsed_time(ev[-1][3])
+        ph = [sum(ev[i][k].elapsed_time(ev[i][k + 1]) for i in range(g_steps)) / g_steps for k in range(3)]
+        tg = torch.tensor([tot] + ph, device="cuda", dtype=torch.float64)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        g_ms = float(tg[0].item()) / g_steps
+        moved = (world - 1) * S * P * C * N2 * 4          # bytes the root sends (scatter) and receives (gather) per step
+        with_gather = {"value": samples_step / (g_ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": g_ms, "steps": g_steps,
+                       "scatter_ms": float(tg[1].item()), "compute_ms": float(tg[2].item()), "gather_ms": float(tg[3].item()),
+                       "root_bytes_out_per_step": moved, "root_bytes_in_per_step": moved,
+                       "root_scatter_gbs": moved / (float(tg[1].item()) * 1e-3) / 1e9,
+                       "root_gather_gbs": moved / (float(tg[3].item()) * 1e-3) / 1e9,
+                       "how": "torch.distributed batch_isend_irecv (grouped ncclSend/ncclRecv) on the library's stream; "
+                              "the batch starts and ends in rank 0's HBM; phases are max over ranks"}
+        del spec_all, pcm_all
     batch.close()
     for p_ in pwrs:
         p_.close()
@@ -369,7 +410,7 @@ def main():
                 "e2e": {"value": e2e_value / 1e6, "unit": "Msamples/s",
                         "h2d_bytes_per_step": Se * P * C * N2 * 4, "d2h_bytes_per_step": Se * C * stride * 4,
                         "streams": Se, "steps": e_steps, "timer": "host wall clock around synchronous calls"},
-                "sustained": sustained, "strong_scaling": strong,
+                "sustained": sustained, "strong_scaling": strong, "with_gather": with_gather,
                 "gpu_launches": int(launches), "host_enqueue_us_per_step": host_us, "clocks": clocks,
                 "host_binding": {"numa_node": int(numa), "cpus": len(os.sched_getaffinity(0)),
                                  "how": "lwb_bind_host_to_device: CPU affinity + preferred memory node of the GPU's PCIe root"}}

@@ -17,7 +17,7 @@
  *                                :215-251 floor_one_decode, :557-760 floor/residue decode
  *   lwf_decoded_sample_count     audio.rs:874-909 get_decoded_sample_count
  *   lwf_ogg_*                    ogg 0.8.0 PacketReader as used by inside_ogg.rs:16-143
- *   lwf_reader_*                 inside_ogg.rs:60-227 OggStreamReader (read_dec_packet[_itl],
+ *   lwf_reader_*                 inside_ogg.rs:60-313 OggStreamReader (read_dec_packet[_itl], skip_samples_linear, seek_absgp_pg,
  *                                end-of-stream truncation :219-222, absgp accounting :223-227,
  *                                chained streams :118-141)
  * Status codes are lewton_b200.h's LWB_* plus the LWF_* header errors below.
@@ -112,6 +112,14 @@ const lwf_headers *lwf_reader_headers(const lwf_reader *r);
 int lwf_reader_read_dec_packet(lwf_reader *r, int out_format, void *out, size_t capacity_total,
                                size_t *n_samples);
 int lwf_reader_last_absgp(const lwf_reader *r, uint64_t *absgp);   /* returns 0 and sets *absgp if Some */
+/* skip_samples_linear (inside_ogg.rs:244-283): walks packets by their sample counts only, decodes the packet before
+ * the target on a fresh PreviousWindowRight (dropped) and returns the target packet.  *got_packet = 0 <=> Ok((None, _))
+ * (the stream ended first); *left_to_skip = the second element of the reference's tuple. */
+int lwf_reader_skip_samples_linear(lwf_reader *r, size_t to_skip, int out_format, void *out, size_t capacity_total,
+                                   size_t *n_samples, size_t *left_to_skip, int *got_packet);
+/* seek_absgp_pg (inside_ogg.rs:307-313): page-granular seek inside the current logical stream to a position <= absgp;
+ * afterwards get_last_absgp() is None and the next packet returns 0 samples (fresh PreviousWindowRight). */
+int lwf_reader_seek_absgp_pg(lwf_reader *r, uint64_t absgp);
 
 /* ---- many streams at once: host entropy decode on a thread pool, one batched synthesis call ---- */
 /* The shape of a decode server (BASELINE configs 1/3 at scale): packets of many logical streams that

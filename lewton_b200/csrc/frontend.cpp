@@ -1154,7 +1154,8 @@ static uint32_t ogg_crc(const uint8_t *d, size_t n, size_t crc_at)
     return c;
 }
 
-struct OggStreamState { std::vector<uint8_t> partial; bool in_packet = false; bool seen = false; bool ended = false; };
+struct OggStreamState { std::vector<uint8_t> partial; bool in_packet = false; bool seen = false; bool ended = false;
+                        bool drop_continued = false; };   // after a seek: the tail of a packet begun on an earlier page is dropped
 
 struct Ogg {
     const uint8_t *d;
@@ -1198,8 +1199,15 @@ struct Ogg {
         const uint8_t *bp = p + 27 + nseg;
         const size_t q0 = queue.size();
         bool first_in_page = true;
+        bool dropping = st.drop_continued && continued;
+        st.drop_continued = false;
         for (size_t i = 0; i < nseg; i++) {
             const uint8_t l = p[27 + i];
+            if (dropping) {                    // still inside the packet that began before the seek target
+                bp += l;
+                if (l < 255) dropping = false;
+                continue;
+            }
             st.partial.insert(st.partial.end(), bp, bp + l);
             st.in_packet = true;
             bp += l;
@@ -1224,6 +1232,42 @@ struct Ogg {
             if (eos) queue.back().last_stream = true;
         }
         at += total;
+        return LWB_OK;
+    }
+
+    // Page-granular seek inside logical stream `serial` (what ogg 0.8.0's PacketReader::seek_absgp gives
+    // inside_ogg.rs:307-313): the read position moves to the start of the LAST page at or after byte offset `from`
+    // whose granule position is <= goal (the first such page of the stream if none is), so that whatever is decoded
+    // next lies at or before `goal`.  Pages are walked linearly: the data is a memory buffer.
+    int seek_absgp(uint32_t serial, uint64_t goal, size_t from)
+    {
+        size_t pos = from, best = (size_t)-1, first = (size_t)-1;
+        while (pos + 27 <= len) {
+            const uint8_t *p = d + pos;
+            if (std::memcmp(p, "OggS", 4) != 0 || p[4] != 0) return LWF_ERR_OGG;
+            const size_t nseg = p[26];
+            if (pos + 27 + nseg > len) return LWF_ERR_OGG;
+            size_t body = 0;
+            for (size_t i = 0; i < nseg; i++) body += p[27 + i];
+            if (pos + 27 + nseg + body > len) return LWF_ERR_OGG;
+            const uint32_t ps = (uint32_t)p[14] | ((uint32_t)p[15] << 8) | ((uint32_t)p[16] << 16) | ((uint32_t)p[17] << 24);
+            uint64_t g = 0;
+            for (int i = 7; i >= 0; i--) g = (g << 8) | p[6 + i];
+            if (ps == serial) {
+                if (first == (size_t)-1) first = pos;
+                if (g != ~0ull && g <= goal) best = pos;       // (-1: no packet finishes on this page)
+                else if (g != ~0ull && g > goal) break;
+            }
+            pos += 27 + nseg + body;
+        }
+        if (first == (size_t)-1) return LWF_ERR_OGG;
+        at = best != (size_t)-1 ? best : first;
+        queue.clear();
+        qhead = 0;
+        OggStreamState &st = state(serial);
+        st.partial.clear();
+        st.in_packet = false;
+        st.drop_continued = true;
         return LWB_OK;
     }
 
@@ -1415,6 +1459,7 @@ struct lwf_reader {
     uint32_t serial = 0;
     bool has_absgp = false;
     uint64_t absgp = 0;
+    size_t audio_start = 0;        // byte offset of the first page after the current stream's headers
     std::vector<uint8_t> kinds;
     std::vector<uint32_t> ys;
     std::vector<float> dense, residue, scratch;
@@ -1455,6 +1500,7 @@ static int reader_read_headers(lwf_reader *r, const lwf_ogg_packet *first)
     if ((rc = lwb_stream_open(r->ctx, r->setup, &r->pwr))) return rc;
     r->serial = serial;
     r->has_absgp = false;
+    r->audio_start = r->ogg->o.at;
     const size_t C = h->h.ident.audio_channels, n2 = (size_t)1 << (h->h.ident.blocksize_1 - 1);
     r->kinds.assign(C, 0);
     r->ys.assign(C * LWB_MAX_POSTS, 0);
@@ -1514,32 +1560,34 @@ static int reader_decode(lwf_reader *r, const lwf_ogg_packet &pk, int out_format
     return lwb_decode_packet(r->pwr, &p, out_format, out, cap, n);
 }
 
-// read_next_audio_packet (inside_ogg.rs:107-143) + dec_packet_generic (:213-229)
-extern "C" int lwf_reader_read_dec_packet(lwf_reader *r, int out_format, void *out, size_t cap_total, size_t *n_samples)
+// read_next_audio_packet, inside_ogg.rs:107-143
+static int reader_next_audio_packet(lwf_reader *r, lwf_ogg_packet *pk)
 {
-    if (!r || !out || !n_samples) return LWB_ERR_INVALID;
-    *n_samples = 0;
-    lwf_ogg_packet pk;
     int rc;
     for (;;) {
-        if ((rc = lwf_ogg_next_packet(r->ogg, &pk))) return rc;
-        if (pk.stream_serial == r->serial) break;
-        if (!pk.first_in_stream) continue;
+        if ((rc = lwf_ogg_next_packet(r->ogg, pk))) return rc;
+        if (pk->stream_serial == r->serial) return LWB_OK;
+        if (!pk->first_in_stream) continue;
         // a chained stream begins: new headers, new state; its first audio packet is decoded and dropped
-        if ((rc = reader_read_headers(r, &pk))) return rc;
-        if ((rc = lwf_ogg_next_packet(r->ogg, &pk))) return rc;
+        if ((rc = reader_read_headers(r, pk))) return rc;
+        if ((rc = lwf_ogg_next_packet(r->ogg, pk))) return rc;
         const size_t C = r->hdr->h.ident.audio_channels, n1 = (size_t)1 << r->hdr->h.ident.blocksize_1;
         r->scratch.resize(C * n1);
         size_t dropped = 0;
-        if ((rc = reader_decode(r, pk, LWB_OUT_F32_PLANAR, r->scratch.data(), n1, &dropped))) return rc;
+        if ((rc = reader_decode(r, *pk, LWB_OUT_F32_PLANAR, r->scratch.data(), n1, &dropped))) return rc;
         r->has_absgp = true;
-        r->absgp = pk.absgp_page;
-        if ((rc = lwf_ogg_next_packet(r->ogg, &pk))) return rc;
-        break;
+        r->absgp = pk->absgp_page;
+        return lwf_ogg_next_packet(r->ogg, pk);
     }
+}
+
+// dec_packet_generic, inside_ogg.rs:207-229: decode, truncate at the end of the stream, account the granule position
+static int reader_dec_packet(lwf_reader *r, const lwf_ogg_packet &pk, int out_format, void *out, size_t cap_total, size_t *n_samples)
+{
     size_t n = 0;
     const size_t cap = cap_total / r->hdr->h.ident.audio_channels;
-    if ((rc = reader_decode(r, pk, out_format, out, cap, &n))) return rc;
+    int rc = reader_decode(r, pk, out_format, out, cap, &n);
+    if (rc) return rc;
     if (r->has_absgp && pk.last_in_stream) {                      // inside_ogg.rs:219-222
         const uint64_t target = pk.absgp_page > r->absgp ? pk.absgp_page - r->absgp : 0;
         if (target < n) n = (size_t)target;
@@ -1552,6 +1600,83 @@ extern "C" int lwf_reader_read_dec_packet(lwf_reader *r, int out_format, void *o
     }
     *n_samples = n;
     return LWB_OK;
+}
+
+// read_dec_packet_generic, inside_ogg.rs:191-205
+extern "C" int lwf_reader_read_dec_packet(lwf_reader *r, int out_format, void *out, size_t cap_total, size_t *n_samples)
+{
+    if (!r || !out || !n_samples) return LWB_ERR_INVALID;
+    *n_samples = 0;
+    LWF_GUARD(
+        lwf_ogg_packet pk;
+        int rc = reader_next_audio_packet(r, &pk);
+        if (rc) return rc;
+        return reader_dec_packet(r, pk, out_format, out, cap_total, n_samples);
+    )
+}
+
+// skip_samples_linear, inside_ogg.rs:244-283: packets are only measured (get_decoded_sample_count) until the one that
+// holds the target; the packet before it is decoded on a fresh PreviousWindowRight (and dropped) so that the target
+// packet overlaps with the right history, then the target packet is decoded and returned.
+extern "C" int lwf_reader_skip_samples_linear(lwf_reader *r, size_t to_skip, int out_format, void *out, size_t cap_total,
+                                              size_t *n_samples, size_t *left_to_skip, int *got_packet)
+{
+    if (!r || !out || !n_samples || !left_to_skip || !got_packet) return LWB_ERR_INVALID;
+    *n_samples = 0;
+    *got_packet = 0;
+    *left_to_skip = to_skip;
+    LWF_GUARD(
+        std::vector<uint8_t> last;             // Option<Packet>: the packet read before `next`
+        bool have_last = false;
+        lwf_ogg_packet last_pk;
+        std::memset(&last_pk, 0, sizeof(last_pk));
+        for (;;) {
+            lwf_ogg_packet next;
+            int rc = reader_next_audio_packet(r, &next);
+            if (rc == LWF_ERR_NO_MORE_PACKETS) { *left_to_skip = to_skip; return LWB_OK; }      // Ok((None, to_skip))
+            if (rc) return rc;
+            size_t cnt = 0;
+            if ((rc = lwf_decoded_sample_count(r->hdr, next.data, next.len, &cnt))) return rc;
+            if (r->has_absgp && next.last_in_stream) {             // :258-262
+                have_last = false;
+                const uint64_t target = next.absgp_page > r->absgp ? next.absgp_page - r->absgp : 0;
+                if (target < cnt) cnt = (size_t)target;
+            }
+            if (to_skip < cnt) {                                   // :263-271
+                if (have_last) {
+                    lwb_stream_reset(r->pwr);
+                    const size_t C = r->hdr->h.ident.audio_channels, n1 = (size_t)1 << r->hdr->h.ident.blocksize_1;
+                    r->scratch.resize(C * n1);
+                    size_t dropped = 0;
+                    last_pk.data = last.data();
+                    last_pk.len = last.size();
+                    // `next.data` points into the pager's current buffer, which stays valid: nothing is read in between
+                    if ((rc = reader_decode(r, last_pk, LWB_OUT_F32_PLANAR, r->scratch.data(), n1, &dropped))) return rc;
+                }
+                if ((rc = reader_dec_packet(r, next, out_format, out, cap_total, n_samples))) return rc;
+                *got_packet = 1;
+                *left_to_skip = to_skip;
+                return LWB_OK;
+            }
+            to_skip -= cnt;
+            if (r->has_absgp) r->absgp += cnt;                     // :275-277
+            last.assign(next.data, next.data + next.len);
+            last_pk = next;
+            have_last = true;
+        }
+    )
+}
+
+// seek_absgp_pg, inside_ogg.rs:307-313: page-granular seek, then cur_absgp = None and a fresh PreviousWindowRight
+extern "C" int lwf_reader_seek_absgp_pg(lwf_reader *r, uint64_t absgp)
+{
+    if (!r) return LWB_ERR_INVALID;
+    LWF_GUARD(
+        const int rc = r->ogg->o.seek_absgp(r->serial, absgp, r->audio_start);
+        if (rc) return rc;
+        r->has_absgp = false;
+        return lwb_stream_reset(r->pwr);
+    )
 }
 
 extern "C" int lwf_reader_last_absgp(const lwf_reader *r, uint64_t *absgp)

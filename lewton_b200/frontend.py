@@ -21,6 +21,7 @@ from .api import AudioReadError, DecodedPacket, Setup
 SYMBOLS = ["lwf_headers_parse", "lwf_headers_destroy", "lwf_headers_info", "lwf_headers_comment", "lwf_headers_make_setup",
            "lwf_packet_decode", "lwf_decoded_sample_count", "lwf_ogg_open", "lwf_ogg_close", "lwf_ogg_next_packet",
            "lwf_reader_open", "lwf_reader_close", "lwf_reader_headers", "lwf_reader_read_dec_packet", "lwf_reader_last_absgp",
+           "lwf_reader_skip_samples_linear", "lwf_reader_seek_absgp_pg",
            "lwf_batcher_create", "lwf_batcher_destroy", "lwf_batcher_decode", "lwf_batcher_last_timing",
            "lwf_debug_float32_unpack", "lwf_debug_lookup1_values", "lwf_debug_ilog", "lwf_debug_read_bits", "lwf_debug_huffman"]
 
@@ -94,6 +95,8 @@ def lib():
         L.lwf_reader_headers.restype = vp
         L.lwf_reader_read_dec_packet.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz)]
         L.lwf_reader_last_absgp.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.lwf_reader_skip_samples_linear.argtypes = [vp, sz, C.c_int, vp, sz, C.POINTER(sz), C.POINTER(sz), C.POINTER(C.c_int)]
+        L.lwf_reader_seek_absgp_pg.argtypes = [vp, C.c_uint64]
         L.lwf_batcher_create.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
         L.lwf_batcher_destroy.argtypes = [vp]
         L.lwf_batcher_destroy.restype = None
@@ -287,13 +290,21 @@ class OggStreamReader:
         self.headers = Headers(None, None, None, _handle=lib().lwf_reader_headers(self._h))
         self.ident_hdr = self.headers
 
-    def _read(self, fmt, dtype, interleaved):
+    def _read(self, fmt, dtype, interleaved, skip=None):
         total = 255 * 8192 if self._may_chain else self.headers.audio_channels << self.headers.blocksize_1
         if self._buf is None or self._buf.size < total or self._buf.dtype != dtype:
             self._buf = np.zeros(total, dtype)
         buf = self._buf
         n = C.c_size_t()
-        rc = lib().lwf_reader_read_dec_packet(self._h, fmt, buf.ctypes.data, buf.size, C.byref(n))
+        if skip is None:
+            rc = lib().lwf_reader_read_dec_packet(self._h, fmt, buf.ctypes.data, buf.size, C.byref(n))
+        else:
+            left, got = C.c_size_t(), C.c_int()
+            rc = lib().lwf_reader_skip_samples_linear(self._h, skip, fmt, buf.ctypes.data, buf.size, C.byref(n), C.byref(left),
+                                                      C.byref(got))
+            self._skip_left = left.value
+            if rc == 0 and not got.value:
+                return None
         if rc == ERR_NO_MORE_PACKETS:
             return None
         if rc == cabi.ERR_BAD_FORMAT:
@@ -324,6 +335,19 @@ class OggStreamReader:
     def read_dec_packet_f32(self):
         """read_dec_packet_generic::<Vec<Vec<f32>>>"""
         return self._read(cabi.OUT_F32_PLANAR, np.float32, False)
+
+    def skip_samples_linear(self, to_skip, sample="f32"):
+        """inside_ogg.rs:244-283 -> (Option<S>, usize): (planar packet or None, samples left to skip inside it)."""
+        fmt, dt = (cabi.OUT_F32_PLANAR, np.float32) if sample == "f32" else (cabi.OUT_I16_PLANAR, np.int16)
+        pck = self._read(fmt, dt, False, skip=int(to_skip))
+        return pck, self._skip_left
+
+    def seek_absgp_pg(self, absgp):
+        """inside_ogg.rs:307-313: page-granular seek to a position <= absgp; resets cur_absgp and PreviousWindowRight."""
+        rc = lib().lwf_reader_seek_absgp_pg(self._h, int(absgp))
+        if rc >= ERR_OGG:
+            raise OggReadError("code %d" % rc)
+        self.ctx.check(rc)
 
     def get_last_absgp(self):
         v = C.c_uint64()

@@ -299,3 +299,142 @@ def test_hostile_but_parseable_streams_do_not_break_the_gpu_path(ctx, oracle):
         got = rd.read_dec_packet_f32()
         assert bits_equal(np.array(got).reshape(2, -1), w)
     rd.close()
+
+
+def _oracle_stream(oracle, spec):
+    floors = [(f.multiplier, f.x_list) if isinstance(f, vp.Floor1) else (1, [0, 128]) for f in spec.floors]
+    mappings = [{"coupling": m["coupling"], "floor_of_channel": [m["floors"][m["mux"][c]] for c in range(spec.channels)]}
+                for m in spec.mappings]
+    return RefStream(oracle, spec.channels, spec.bs0, spec.bs1, spec.modes, mappings, floors)
+
+
+def _oracle_packet(ref, spec, info):
+    fl_exp, res = spec.expected(info)
+    n2 = info["n"] // 2
+    fl = []
+    for f in fl_exp:
+        if f is None:
+            fl.append(None)
+        elif f[0] == "one":
+            fl.append(list(f[1]))
+        else:
+            fl.append(floor0_expected(f[3], f[1], f[2], info["blockflag"], n2, spec.bs0, spec.bs1))
+    rc, pcm = ref.packet(info["mode"], info["prev"], info["next"], res, fl)
+    assert rc == 0
+    return pcm
+
+
+def _sample_count(spec, info):
+    """audio::get_decoded_sample_count (audio.rs:874-909): right_win_start - left_win_start, whatever the state."""
+    n, n0 = info["n"], 1 << spec.bs0
+    lng = bool(info["blockflag"])
+    ls = 0 if (not lng or info["prev"]) else (n - n0) // 4
+    rs = n // 2 if (not lng or info["next"]) else (3 * n - n0) // 4
+    return rs - ls
+
+
+class _ReaderModel:
+    """The reference's OggStreamReader state machine (inside_ogg.rs:107-313) over the packer's record of a stream,
+    with the oracle as the decoder: what read_dec_packet_generic / skip_samples_linear / seek_absgp_pg must return."""
+
+    def __init__(self, oracle, spec, infos, granules, per_page):
+        self.spec, self.infos, self.gran, self.pp = spec, infos, granules, per_page
+        self.ref = _oracle_stream(oracle, spec)
+        self.idx, self.absgp = 0, None
+
+    def _page(self, i):
+        return i // self.pp
+
+    def _dec(self, i):
+        pcm = _oracle_packet(self.ref, self.spec, self.infos[i])
+        last_in_stream = i == len(self.infos) - 1
+        last_in_page = (i + 1) % self.pp == 0 or last_in_stream
+        n = pcm.shape[1]
+        if self.absgp is not None and last_in_stream:
+            n = min(n, max(self.gran[self._page(i)] - self.absgp, 0))
+        if last_in_page:
+            self.absgp = self.gran[self._page(i)]
+        elif self.absgp is not None:
+            self.absgp += n
+        return pcm[:, :n]
+
+    def read(self):
+        if self.idx >= len(self.infos):
+            return None
+        self.idx += 1
+        return self._dec(self.idx - 1)
+
+    def skip(self, to_skip):
+        last = None
+        while True:
+            if self.idx >= len(self.infos):
+                return None, to_skip
+            i = self.idx
+            self.idx += 1
+            cnt = _sample_count(self.spec, self.infos[i])
+            if self.absgp is not None and i == len(self.infos) - 1:
+                last = None
+                cnt = min(cnt, max(self.gran[self._page(i)] - self.absgp, 0))
+            if to_skip < cnt:
+                if last is not None:
+                    self.ref.pwr.reset()
+                    _oracle_packet(self.ref, self.spec, self.infos[last])
+                return self._dec(i), to_skip
+            to_skip -= cnt
+            if self.absgp is not None:
+                self.absgp += cnt
+            last = i
+
+    def seek(self, goal):
+        pages = [j for j in range(len(self.gran)) if self.gran[j] <= goal]
+        self.idx = (pages[-1] if pages else 0) * self.pp
+        self.absgp = None
+        self.ref.pwr.reset()
+
+
+@pytest.mark.parametrize("seed,channels", [(401, 2), (402, 1), (403, 6)])
+def test_skip_samples_linear_and_seek_absgp_pg(ctx, oracle, seed, channels):
+    """inside_ogg.rs:244-283 and :307-313 through the GPU reader: packets are skipped by their sample counts, the
+    packet before the target is decoded on a fresh PreviousWindowRight and dropped, the target packet comes back
+    with the leftover count; a page-granular seek lands at or before the goal, clears the granule position and the
+    overlap state.  Every returned packet, leftover count and get_last_absgp() value is compared with a model of the
+    reference's state machine that decodes with the oracle."""
+    n_packets, per_page = 23, 3
+    spec, packets, infos = build_stream(seed, channels, False, n_packets)
+    want, _ = oracle_pcm(oracle, spec, infos)
+    gran = page_granules(want, per_page, 11)
+    data = vp.ogg_stream(0x77, [spec.ident_packet(), spec.comment_packet(), spec.setup_packet()], packets, gran, packets_per_page=per_page)
+    rd = fe.OggStreamReader(ctx, data)
+    model = _ReaderModel(oracle, spec, infos, gran, per_page)
+
+    def same(got, w, what):
+        if w is None:
+            assert got is None, what
+            return
+        assert got is not None and len(got) == channels and all(len(g) == w.shape[1] for g in got), (what, w.shape)
+        assert bits_equal(np.array(got).reshape(channels, -1), w), (what, mismatch_report(np.array(got).reshape(channels, -1), w))
+
+    for i in range(2):
+        same(rd.read_dec_packet_f32(), model.read(), ("read", i))
+    # a skip that stays inside the next packet, one that crosses several packets and a page, one that lands in the
+    # truncated last packet, one that runs off the end of the stream
+    for to_skip in (3, 2500, 40, 10 ** 7):
+        got, left = rd.skip_samples_linear(to_skip)
+        w, wleft = model.skip(to_skip)
+        same(got, w, ("skip", to_skip))
+        assert left == wleft and rd.get_last_absgp() == model.absgp, (to_skip, left, wleft, rd.get_last_absgp(), model.absgp)
+        if w is not None and model.idx < n_packets:
+            same(rd.read_dec_packet_f32(), model.read(), ("after skip", to_skip))
+    assert rd.read_dec_packet_f32() is None
+    # seeks: into the middle, before the first page's end, beyond the end, and back to the middle
+    for goal in (gran[3] + 5, 0, gran[-1] + 1000, gran[2]):
+        rd.seek_absgp_pg(goal)
+        model.seek(goal)
+        assert rd.get_last_absgp() is None
+        for k in range(5):
+            w = model.read()
+            same(rd.read_dec_packet_f32(), w, ("after seek", goal, k))
+            assert rd.get_last_absgp() == model.absgp, (goal, k)
+            if w is None:
+                break
+    rd.close()
