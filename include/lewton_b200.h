@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define LWB_ABI_VERSION 2          /* 2: lwb_batch_io::floor_memory, lwb_bind_host_to_device */
+#define LWB_ABI_VERSION 3          /* 2: lwb_batch_io::floor_memory, lwb_bind_host_to_device; 3: LWB_ENTRY_VQ */
 #define LWB_MAX_POSTS 65          /* header.rs:873 floor1_values <= 65 */
 #define LWB_MAX_CHANNELS 255      /* audio_channels is a u8, header.rs:190 */
 #define LWB_MAX_COUPLING 256      /* header.rs:998-1001 coupling steps = read_u8 + 1 */
@@ -122,6 +122,19 @@ typedef struct lwb_mode_desc {       /* header::ModeInfo, header.rs:393-396     
     uint8_t mapping;
 } lwb_mode_desc;
 
+/* Codebook value tables and residue shapes (only for LWB_ENTRY_VQ batches; leave the counts 0 otherwise). */
+typedef struct lwb_codebook_desc {   /* header::Codebook, header.rs:360-368                            */
+    uint16_t dimensions;             /* codebook_dimensions                                            */
+    uint16_t reserved;
+    uint32_t entries;                /* codebook_entries                                               */
+    const float *vq;                 /* codebook_vq_lookup_vec: [entries][dimensions]; NULL = no value mapping */
+} lwb_codebook_desc;
+typedef struct lwb_residue_desc {    /* header::Residue, header.rs:370-379                             */
+    uint8_t residue_type;            /* 0, 1, 2                                                        */
+    uint8_t reserved[3];
+    uint32_t partition_size;         /* residue_partition_size                                         */
+} lwb_residue_desc;
+
 typedef struct lwb_setup_desc {
     uint8_t audio_channels;          /* IdentHeader.audio_channels                                 */
     uint8_t blocksize_0, blocksize_1;/* log2, 6..13, blocksize_0 <= blocksize_1 (header.rs:239-243)    */
@@ -135,6 +148,11 @@ typedef struct lwb_setup_desc {
     const lwb_mapping_desc *mappings;
     uint32_t n_modes;
     const lwb_mode_desc *modes;
+    /* LWB_ENTRY_VQ only (ABI 3; zero / NULL otherwise) */
+    uint32_t n_codebooks;
+    const lwb_codebook_desc *codebooks;
+    uint32_t n_residues;
+    const lwb_residue_desc *residues;
 } lwb_setup_desc;
 
 int lwb_setup_create(lwb_ctx *ctx, const lwb_setup_desc *desc, lwb_setup **out);
@@ -192,7 +210,29 @@ int lwb_decode_spectrum(lwb_stream *s, uint8_t mode_number, int prev_window_flag
 
 /* ---- batches: many streams x consecutive packets in one submission ------------------------- */
 enum { LWB_ENTRY_SPECTRUM = 0,   /* coeffs = floor x residue, enters at audio.rs:1041             */
-       LWB_ENTRY_RESIDUE = 1 };  /* coeffs = residue vectors, enters at audio.rs:988               */
+       LWB_ENTRY_RESIDUE = 1,    /* coeffs = residue vectors, enters at audio.rs:988               */
+       LWB_ENTRY_VQ = 2 };       /* no dense coefficients cross the boundary: the residue vectors are  *
+                                  * accumulated on the device from the packets' VQ entry indices       *
+                                  * (audio.rs:587-717); coeff_offset still lays out the (device-only)   *
+                                  * coefficient arena.  Needs the setup's codebooks / residues, <= 8     *
+                                  * channels, channels * n/2 <= 12288, and every VQ book's dimension      *
+                                  * dividing its residue's partition size.                                */
+/* One VQ vector of a packet's residue, in the order the entropy decoder produces them:
+ * "add codebook `book`'s entry `entry` at `pos`".  The f32 += order of the reference is kept on the device: per
+ * coefficient the contributions are added pass by pass (audio.rs:595, :611); within a pass no two vectors of a
+ * packet touch the same coefficient. */
+typedef struct lwb_vq_record {
+    uint32_t entry_pass_kind;        /* bits 0..23 codebook entry, 24..26 pass (0..7), 27..28 kind:           *
+                                      *   0 contiguous in a channel vector (residue type 1), pos = channel * n/2 + bin
+                                      *   1 strided (type 0, audio.rs:589-597): value j lands at pos + j * step,  *
+                                      *     step = partition_size(aux) / dimensions                               *
+                                      *   2 interleaved (type 2, audio.rs:744-756): pos indexes the interleaved   *
+                                      *     vector of submap `aux`: element t is channel t % ch, bin t / ch       */
+    uint16_t pos;
+    uint8_t book;                    /* codebook index                                                  */
+    uint8_t aux;                     /* kind 1: residue index; kind 2: submap index                     */
+} lwb_vq_record;
+#define LWB_VQ_RECORD(entry, pass, kind) ((uint32_t)(entry) | ((uint32_t)(pass) << 24) | ((uint32_t)(kind) << 27))
 enum { LWB_MEM_HOST = 0, LWB_MEM_DEVICE = 1 };
 
 /* One stream's run of consecutive packets.  Input arenas are chain-major: the chain's packets
@@ -222,6 +262,10 @@ typedef struct lwb_batch_io {
     const uint32_t *floor1_y;         /* [total_packets][channels][LWB_MAX_POSTS], see floor_memory */
     int out_format;                   /* LWB_OUT_*                                                 */
     void *pcm;                        /* output arena                                              */
+    /* LWB_ENTRY_VQ: packet row r (= chain.packet_index + k) owns vq_records[vq_offsets[r] .. vq_offsets[r + 1]);    *
+     * both arrays live where the floor arrays live (floor_memory).                                                 */
+    const lwb_vq_record *vq_records;
+    const uint64_t *vq_offsets;       /* [total_packets + 1]                                        */
     int floor_memory;                 /* LWB_MEM_*: where floor_kind / floor1_y live (0 = host).   *
                                        * Device arrays are read in place (nothing is uploaded, and   *
                                        * nothing about them can be validated on the host: a kind    *

@@ -84,6 +84,14 @@ typedef struct lwf_decoded_packet {
  * LWF_ERR_END_OF_PACKET (header bits missing) or LWB_ERR_BAD_FORMAT (audio.rs:926-930, :975). */
 int lwf_packet_decode(const lwf_headers *h, const uint8_t *packet, size_t len, lwf_decoded_packet *out);
 int lwf_decoded_sample_count(const lwf_headers *h, const uint8_t *packet, size_t len, size_t *n_samples);
+/* The same front half with the residue left as VQ records (audio.rs:587-717): what
+ * residue_packet_decode would have ADDED, vector by vector in decode order, for LWB_ENTRY_VQ batches (out->residue is
+ * not touched and may be NULL).  LWB_ERR_BUFFER if `capacity` records do not suffice (a packet of L bytes never needs
+ * more than 8 L).  lwf_headers_vq_capable: 1 if the stream qualifies (<= 8 channels, every VQ book's dimension
+ * divides its residue's partition size), else the dense path must be used. */
+int lwf_headers_vq_capable(const lwf_headers *h);
+int lwf_packet_decode_vq(const lwf_headers *h, const uint8_t *packet, size_t len, lwf_decoded_packet *out,
+                         lwb_vq_record *records, size_t capacity, size_t *n_records);
 
 /* ---- Ogg paging -------------------------------------------------------------------------------- */
 typedef struct lwf_ogg lwf_ogg;             /* PacketReader over a memory buffer (not copied)      */
@@ -143,6 +151,9 @@ typedef struct lwf_batcher lwf_batcher;
 /* `setup` must come from lwf_headers_make_setup(h, ctx); threads <= 0: one per host CPU */
 int lwf_batcher_create(lwb_ctx *ctx, const lwf_headers *h, int threads, lwf_batcher **out);
 void lwf_batcher_destroy(lwf_batcher *b);
+/* LWB_ENTRY_RESIDUE (default: dense residue vectors cross the boundary) or LWB_ENTRY_VQ (VQ records do; needs
+ * lwf_headers_vq_capable) */
+int lwf_batcher_set_entry(lwf_batcher *b, int entry);
 int lwf_batcher_decode(lwf_batcher *b, lwf_stream_job *jobs, size_t n_jobs, int out_format, void *pcm);
 /* wall-clock seconds of the last lwf_batcher_decode: host entropy decode, synthesis call */
 void lwf_batcher_last_timing(const lwf_batcher *b, double *entropy_seconds, double *synthesis_seconds);

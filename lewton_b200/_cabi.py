@@ -15,7 +15,7 @@ OK, ERR_BAD_FORMAT, ERR_BUFFER, ERR_MISMATCH, ERR_INVALID, ERR_CUDA, ERR_NO_DEVI
 FLOOR_TYPE_ZERO, FLOOR_TYPE_ONE = 0, 1
 FLOOR_UNUSED, FLOOR_ONE, FLOOR_DENSE = 0, 1, 2
 OUT_F32_PLANAR, OUT_I16_PLANAR, OUT_F32_INTERLEAVED, OUT_I16_INTERLEAVED = 0, 1, 2, 3
-ENTRY_SPECTRUM, ENTRY_RESIDUE = 0, 1
+ENTRY_SPECTRUM, ENTRY_RESIDUE, ENTRY_VQ = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 
 vp, u8p, fp, u32p = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_uint32)
@@ -40,12 +40,26 @@ class ModeDesc(C.Structure):
     _fields_ = [("blockflag", C.c_uint8), ("mapping", C.c_uint8)]
 
 
+class CodebookDesc(C.Structure):
+    _fields_ = [("dimensions", C.c_uint16), ("reserved", C.c_uint16), ("entries", C.c_uint32), ("vq", fp)]
+
+
+class ResidueDesc(C.Structure):
+    _fields_ = [("residue_type", C.c_uint8), ("reserved", C.c_uint8 * 3), ("partition_size", C.c_uint32)]
+
+
+class VqRecord(C.Structure):
+    _fields_ = [("entry_pass_kind", C.c_uint32), ("pos", C.c_uint16), ("book", C.c_uint8), ("aux", C.c_uint8)]
+
+
 class SetupDesc(C.Structure):
     _fields_ = [("audio_channels", C.c_uint8), ("blocksize_0", C.c_uint8), ("blocksize_1", C.c_uint8),
                 ("reserved", C.c_uint8), ("tables", TablesRef * 2),
                 ("n_floors", C.c_uint32), ("floors", C.POINTER(FloorDesc)),
                 ("n_mappings", C.c_uint32), ("mappings", C.POINTER(MappingDesc)),
-                ("n_modes", C.c_uint32), ("modes", C.POINTER(ModeDesc))]
+                ("n_modes", C.c_uint32), ("modes", C.POINTER(ModeDesc)),
+                ("n_codebooks", C.c_uint32), ("codebooks", C.POINTER(CodebookDesc)),
+                ("n_residues", C.c_uint32), ("residues", C.POINTER(ResidueDesc))]
 
 
 class Packet(C.Structure):
@@ -65,7 +79,7 @@ class Chain(C.Structure):
 class BatchIo(C.Structure):
     _fields_ = [("entry", C.c_int), ("memory", C.c_int), ("coeffs", vp), ("dense_floor", vp),
                 ("floor_kind", vp), ("floor1_y", vp), ("out_format", C.c_int), ("pcm", vp),
-                ("floor_memory", C.c_int)]
+                ("vq_records", vp), ("vq_offsets", vp), ("floor_memory", C.c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/lewton_b200.h declares

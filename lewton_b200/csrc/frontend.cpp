@@ -933,6 +933,53 @@ static int floor1_decode(BitReader &rdr, const std::vector<Codebook> &codebooks,
     return FL_OK;
 }
 
+// LWB_ENTRY_VQ: instead of adding the VQ vectors into dense residue vectors on the host, the decode emits one
+// record per vector ("codebook b, entry e, at position p") and the device does the additions in the same order.
+struct VqSink {
+    lwb_vq_record *rec = nullptr;
+    size_t cap = 0, n = 0;
+    bool overflow = false;
+    // context of the residue decode in progress
+    size_t base = 0;                  // position of vec_v[0]: channel * n/2 + offset (types 0 / 1) or the interleaved index (type 2)
+    uint8_t pass = 0, kind = 0, aux = 0, book = 0;
+    void put(uint32_t entry, size_t pos)
+    {
+        if (n >= cap || pos > 0xffffu || entry > 0xffffffu) { overflow = true; return; }
+        lwb_vq_record &q = rec[n++];
+        q.entry_pass_kind = LWB_VQ_RECORD(entry, pass, kind);
+        q.pos = (uint16_t)pos;
+        q.book = book;
+        q.aux = aux;
+    }
+};
+
+// residue_packet_read_partition, audio.rs:588-619 with the additions left to the device: 0 ok, 1 end of packet
+static int residue_partition_vq(BitReader &rdr, const Codebook &cb, const Residue &r, size_t vlen, VqSink &sink)
+{
+    uint32_t idx;
+    if (r.type == 0) {
+        const size_t dims = cb.dimensions;
+        if (dims == 0) return 0;
+        const size_t step = r.partition_size / dims;
+        for (size_t i = 0; i < step; i++) {
+            if (!cb.tree.read(rdr, &idx)) return 1;
+            if (i + (dims - 1) * step >= vlen) return 0;    // (slice index out of range: a panic in the reference)
+            sink.put(idx, sink.base + i);
+        }
+    } else {
+        const size_t psize = r.partition_size;
+        size_t i = 0;
+        while (i < psize) {
+            if (!cb.tree.read(rdr, &idx)) return 1;
+            if (i + cb.dimensions > vlen) break;
+            sink.put(idx, sink.base + i);
+            i += cb.dimensions;
+            if (cb.dimensions == 0) break;
+        }
+    }
+    return 0;
+}
+
 // residue_packet_read_partition, audio.rs:588-619: 0 ok, 1 end of packet
 static int residue_partition(BitReader &rdr, const Codebook &cb, const Residue &r, float *v, size_t vlen)
 {
@@ -965,8 +1012,10 @@ static int residue_partition(BitReader &rdr, const Codebook &cb, const Residue &
 }
 
 // residue_packet_decode_inner, audio.rs:621-716.  `vectors`: [ch][blocksize/2], zeroed here.
+// sink != nullptr: VQ records instead of additions (chbase[j] = position of channel j's vector; kind / aux set by the caller)
 static int residue_decode_inner(BitReader &rdr, uint32_t cur_blocksize, const std::vector<uint8_t> &dnd, const Residue &r,
-                                const std::vector<Codebook> &codebooks, std::vector<float> &vectors)
+                                const std::vector<Codebook> &codebooks, std::vector<float> &vectors, VqSink *sink = nullptr,
+                                const size_t *chbase = nullptr)
 {
     const size_t ch = dnd.size(), actual = cur_blocksize / 2;
     const size_t lim_begin = std::min<size_t>(r.begin, actual), lim_end = std::min<size_t>(r.end, actual);
@@ -974,7 +1023,7 @@ static int residue_decode_inner(BitReader &rdr, uint32_t cur_blocksize, const st
     const size_t cpc = classbook.dimensions;
     const size_t n_to_read = lim_end - lim_begin;
     const size_t parts = n_to_read / r.partition_size;
-    vectors.assign(ch * actual, 0.f);
+    if (!sink) vectors.assign(ch * actual, 0.f);
     if (n_to_read == 0) return 0;
     if (cpc == 0) return 1;
     const size_t stride = parts + cpc;
@@ -1007,7 +1056,12 @@ static int residue_decode_inner(BitReader &rdr, uint32_t cur_blocksize, const st
                     if (rb.vals_used & (1u << pass)) {
                         const Codebook &cb = codebooks[rb.val[pass]];
                         if (!cb.has_vq) return 1;           // the reference panics ("must have a value mapping")
-                        if (residue_partition(rdr, cb, r, vectors.data() + j * actual + offs, actual - offs)) return 0;
+                        if (sink) {
+                            sink->pass = (uint8_t)pass;
+                            sink->book = rb.val[pass];
+                            sink->base = chbase[j] + offs;
+                            if (residue_partition_vq(rdr, cb, r, actual - offs, *sink)) return 0;
+                        } else if (residue_partition(rdr, cb, r, vectors.data() + j * actual + offs, actual - offs)) return 0;
                     }
                 }
                 pc++;
@@ -1018,16 +1072,29 @@ static int residue_decode_inner(BitReader &rdr, uint32_t cur_blocksize, const st
 }
 
 // residue_packet_decode, audio.rs:721-760
+// sink != nullptr: records; chbase[j] = position of submap channel j's vector, residue_idx / submap go into the records
 static int residue_decode(BitReader &rdr, uint32_t cur_blocksize, const std::vector<uint8_t> &dnd, const Residue &r,
-                          const std::vector<Codebook> &codebooks, std::vector<float> &out)
+                          const std::vector<Codebook> &codebooks, std::vector<float> &out, VqSink *sink = nullptr,
+                          const size_t *chbase = nullptr, uint8_t residue_idx = 0, uint8_t submap = 0)
 {
     const size_t ch = dnd.size(), vec = cur_blocksize / 2;
-    if (r.type != 2) return residue_decode_inner(rdr, cur_blocksize, dnd, r, codebooks, out);
+    if (r.type != 2) {
+        if (sink) { sink->kind = r.type == 0 ? 1 : 0; sink->aux = residue_idx; }
+        return residue_decode_inner(rdr, cur_blocksize, dnd, r, codebooks, out, sink, chbase);
+    }
     bool any = false;
     for (uint8_t d : dnd) any |= !d;
     if (!any) {
-        out.assign(ch * vec, 0.f);
+        if (!sink) out.assign(ch * vec, 0.f);
         return 0;
+    }
+    if (sink) {                      // one interleaved vector for the whole submap; the device de-interleaves
+        thread_local std::vector<uint8_t> one1(1, 0);
+        const size_t zero = 0;
+        sink->kind = 2;
+        sink->aux = submap;
+        const uint32_t bs2s = (uint32_t)(uint16_t)(cur_blocksize * ch);
+        return residue_decode_inner(rdr, bs2s, one1, r, codebooks, out, sink, &zero);
     }
     thread_local std::vector<uint8_t> one(1, 0);
     thread_local std::vector<float> inter;
@@ -1065,7 +1132,7 @@ static int packet_head(const Headers &h, BitReader &rdr, PacketHead *ph)
     return LWB_OK;
 }
 
-static int packet_decode(const Headers &h, const uint8_t *packet, size_t len, lwf_decoded_packet *out)
+static int packet_decode(const Headers &h, const uint8_t *packet, size_t len, lwf_decoded_packet *out, VqSink *sink = nullptr)
 {
     BitReader rdr(packet, len);
     PacketHead ph;
@@ -1117,6 +1184,14 @@ static int packet_decode(const Headers &h, const uint8_t *packet, size_t len, lw
         for (size_t j = 0; j < C; j++)
             if (mp.mux[j] == i) dnd.push_back(no_residue[j]);
         const Residue &r = h.residues[mp.submap_residues[i]];
+        if (sink) {
+            thread_local std::vector<size_t> chbase;
+            chbase.clear();
+            for (size_t j = 0; j < C; j++)
+                if (mp.mux[j] == i) chbase.push_back(j * n2);
+            if (residue_decode(rdr, ph.n, dnd, r, h.codebooks, vectors, sink, chbase.data(), mp.submap_residues[i], (uint8_t)i)) return LWB_ERR_BAD_FORMAT;
+            continue;
+        }
         if (residue_decode(rdr, ph.n, dnd, r, h.codebooks, vectors)) return LWB_ERR_BAD_FORMAT;
         size_t chn = 0;
         for (size_t j = 0; j < C; j++)
@@ -1404,7 +1479,65 @@ extern "C" int lwf_headers_make_setup(const lwf_headers *h, lwb_ctx *ctx, lwb_se
     d.mappings = maps.data();
     d.n_modes = (uint32_t)modes.size();
     d.modes = modes.data();
+    // LWB_ENTRY_VQ: the codebooks' value tables (codebook_vq_lookup_vec) and the residues' partition sizes
+    std::vector<lwb_codebook_desc> books(s.codebooks.size());
+    for (size_t i = 0; i < s.codebooks.size(); i++) {
+        const lwf::Codebook &cb = s.codebooks[i];
+        books[i].dimensions = cb.dimensions;
+        books[i].reserved = 0;
+        books[i].entries = cb.dimensions ? (uint32_t)(cb.vq.size() / cb.dimensions) : 0;
+        books[i].vq = cb.has_vq && !cb.vq.empty() ? cb.vq.data() : nullptr;
+    }
+    std::vector<lwb_residue_desc> resids(s.residues.size());
+    for (size_t i = 0; i < s.residues.size(); i++) {
+        std::memset(&resids[i], 0, sizeof(resids[i]));
+        resids[i].residue_type = s.residues[i].type;
+        resids[i].partition_size = s.residues[i].partition_size;
+    }
+    if (books.size() <= 256 && resids.size() <= 64) {
+        d.n_codebooks = (uint32_t)books.size();
+        d.codebooks = books.data();
+        d.n_residues = (uint32_t)resids.size();
+        d.residues = resids.data();
+    }
     return lwb_setup_create(ctx, &d, out);
+}
+
+// What LWB_ENTRY_VQ needs from a stream: <= 8 channels, and every VQ book a residue uses has a dimension that divides
+// the residue's partition size (then the vectors of one pass never overlap and the device may add them in parallel).
+extern "C" int lwf_headers_vq_capable(const lwf_headers *h)
+{
+    if (!h) return 0;
+    const lwf::Headers &s = h->h;
+    if (s.ident.audio_channels > 8 || s.codebooks.size() > 256 || s.residues.size() > 64) return 0;
+    for (const lwf::Residue &r : s.residues)
+        for (const lwf::ResidueBook &rb : r.books)
+            for (int p = 0; p < 8; p++)
+                if (rb.vals_used & (1u << p)) {
+                    if (rb.val[p] >= s.codebooks.size()) return 0;
+                    const lwf::Codebook &cb = s.codebooks[rb.val[p]];
+                    if (!cb.has_vq || cb.dimensions == 0 || r.partition_size % cb.dimensions) return 0;
+                }
+    return 1;
+}
+
+extern "C" int lwf_packet_decode_vq(const lwf_headers *h, const uint8_t *packet, size_t len, lwf_decoded_packet *out,
+                                    lwb_vq_record *records, size_t capacity, size_t *n_records)
+{
+    if (!h || (!packet && len) || !out || !out->floor_kind || !out->floor1_y || (!records && capacity) || !n_records) return LWB_ERR_INVALID;
+    for (const auto &fl : h->h.floors)
+        if (fl.type == 0 && !out->dense_floor) return LWB_ERR_INVALID;
+    *n_records = 0;
+    LWF_GUARD(
+        lwf::VqSink sink;
+        sink.rec = records;
+        sink.cap = capacity;
+        const int rc = lwf::packet_decode(h->h, packet, len, out, &sink);
+        if (rc) return rc;
+        if (sink.overflow) return LWB_ERR_BUFFER;
+        *n_records = sink.n;
+        return LWB_OK;
+    )
 }
 
 extern "C" int lwf_packet_decode(const lwf_headers *h, const uint8_t *packet, size_t len, lwf_decoded_packet *out)
@@ -1706,7 +1839,7 @@ struct PinnedBuf {
 };
 
 struct BatchArena {
-    PinnedBuf coeffs, dense, kinds, ys;
+    PinnedBuf coeffs, dense, kinds, ys, vqrec, vqoff;
     std::vector<uint8_t> modes, prevs, nexts;
     std::vector<lwb_chain> chains;
 };
@@ -1716,6 +1849,7 @@ struct lwf_batcher {
     const lwf_headers *hdr = nullptr;
     int threads = 1;
     bool has_floor0 = false;
+    int entry = LWB_ENTRY_RESIDUE;  // LWB_ENTRY_VQ: the residue crosses the boundary as VQ records
     BatchArena arena[2];           // slice i decodes into arena[i & 1] while slice i - 1 is being synthesised
     double t_entropy = 0, t_synth = 0;
 };
@@ -1735,6 +1869,14 @@ extern "C" int lwf_batcher_create(lwb_ctx *ctx, const lwf_headers *h, int thread
 }
 
 extern "C" void lwf_batcher_destroy(lwf_batcher *b) { delete b; }
+
+extern "C" int lwf_batcher_set_entry(lwf_batcher *b, int entry)
+{
+    if (!b || (entry != LWB_ENTRY_RESIDUE && entry != LWB_ENTRY_VQ)) return LWB_ERR_INVALID;
+    if (entry == LWB_ENTRY_VQ && !lwf_headers_vq_capable(b->hdr)) return LWB_ERR_INVALID;
+    b->entry = entry;
+    return LWB_OK;
+}
 
 extern "C" void lwf_batcher_last_timing(const lwf_batcher *b, double *e, double *s)
 {
@@ -1774,9 +1916,14 @@ int batch_entropy(lwf_batcher *b, BatchArena &ar, lwf_stream_job *jobs, size_t j
         pkt_total += plan[j].usable;
     }
     const size_t rows = (size_t)pkt_total * C;
-    if (!ar.coeffs.ensure((size_t)coeff_total * 4 + 16) || !ar.kinds.ensure(rows + 16) || !ar.ys.ensure(rows * LWB_MAX_POSTS * 4 + 16) ||
-        (b->has_floor0 && !ar.dense.ensure((size_t)coeff_total * 4 + 16)))
+    const bool vq = b->entry == LWB_ENTRY_VQ;
+    if ((!vq && !ar.coeffs.ensure((size_t)coeff_total * 4 + 16)) || !ar.kinds.ensure(rows + 16) || !ar.ys.ensure(rows * LWB_MAX_POSTS * 4 + 16) ||
+        (b->has_floor0 && !ar.dense.ensure((size_t)coeff_total * 4 + 16)) || (vq && !ar.vqoff.ensure(((size_t)pkt_total + 1) * 8 + 16)))
         return LWB_ERR_BUFFER;
+    // VQ: every stream's records are collected per job first (their number is only known after the decode), then
+    // packed into one pinned arena with per-packet offsets
+    std::vector<std::vector<lwb_vq_record>> job_recs(vq ? j1 - j0 : 0);
+    uint64_t *vq_off = vq ? (uint64_t *)ar.vqoff.p : nullptr;
     ar.modes.resize(pkt_total);
     ar.prevs.resize(pkt_total);
     ar.nexts.resize(pkt_total);
@@ -1799,9 +1946,23 @@ int batch_entropy(lwf_batcher *b, BatchArena &ar, lwf_stream_job *jobs, size_t j
                     std::memset(&dp, 0, sizeof(dp));
                     dp.floor_kind = kinds + pi * C;
                     dp.floor1_y = ys + pi * C * LWB_MAX_POSTS;
-                    dp.residue = coeffs + coff;
+                    dp.residue = vq ? nullptr : coeffs + coff;
                     dp.dense_floor = dense ? dense + coff : nullptr;
-                    const int rc = lwf::packet_decode(H, job.packets[k], job.lengths[k], &dp);
+                    int rc;
+                    if (vq) {
+                        std::vector<lwb_vq_record> &jr = job_recs[j - j0];
+                        const size_t cur = jr.size(), cap = (size_t)job.lengths[k] * 8 + 16;
+                        jr.resize(cur + cap);
+                        lwf::VqSink sink;
+                        sink.rec = jr.data() + cur;
+                        sink.cap = cap;
+                        rc = lwf::packet_decode(H, job.packets[k], job.lengths[k], &dp, &sink);
+                        if (!rc && sink.overflow) rc = LWB_ERR_BUFFER;
+                        jr.resize(cur + (rc ? 0 : sink.n));
+                        vq_off[pi + 1] = rc ? 0 : sink.n;          // count for now; turned into offsets below
+                    } else {
+                        rc = lwf::packet_decode(H, job.packets[k], job.lengths[k], &dp);
+                    }
                     if (rc) { dec_status[j] = rc; break; }
                     ar.modes[pi] = dp.mode_number;
                     ar.prevs[pi] = dp.prev_window_flag;
@@ -1820,6 +1981,23 @@ int batch_entropy(lwf_batcher *b, BatchArena &ar, lwf_stream_job *jobs, size_t j
     worker();
     for (auto &t : pool) t.join();
     if (failed.load()) return LWB_ERR_BUFFER;
+    if (vq) {
+        // counts -> offsets (rows of packets that were not decoded own no records), then one packed copy
+        vq_off[0] = 0;
+        for (size_t j = j0; j < j1; j++)
+            for (uint32_t k = 0; k < plan[j].usable; k++) {
+                const uint64_t pi = plan[j].pkt0 + k;
+                const uint64_t cnt = k < decoded[j] ? vq_off[pi + 1] : 0;
+                vq_off[pi + 1] = vq_off[pi] + cnt;
+            }
+        const uint64_t total = vq_off[pkt_total];
+        if (!ar.vqrec.ensure((size_t)total * sizeof(lwb_vq_record) + 16)) return LWB_ERR_BUFFER;
+        lwb_vq_record *dst = (lwb_vq_record *)ar.vqrec.p;
+        for (size_t j = j0; j < j1; j++) {
+            const std::vector<lwb_vq_record> &jr = job_recs[j - j0];
+            if (!jr.empty()) std::memcpy(dst + vq_off[plan[j].pkt0], jr.data(), jr.size() * sizeof(lwb_vq_record));
+        }
+    }
     // chains of this slice
     ar.chains.assign(j1 - j0, lwb_chain());
     for (size_t j = j0; j < j1; j++) {
@@ -1842,9 +2020,11 @@ int batch_synth(lwf_batcher *b, BatchArena &ar, int out_format, void *pcm)
 {
     lwb_batch_io io;
     std::memset(&io, 0, sizeof(io));
-    io.entry = LWB_ENTRY_RESIDUE;
+    io.entry = b->entry;
     io.memory = LWB_MEM_HOST;
     io.coeffs = (const float *)ar.coeffs.p;
+    io.vq_records = (const lwb_vq_record *)ar.vqrec.p;
+    io.vq_offsets = (const uint64_t *)ar.vqoff.p;
     io.dense_floor = b->has_floor0 ? (const float *)ar.dense.p : nullptr;
     io.floor_kind = (const uint8_t *)ar.kinds.p;
     io.floor1_y = (const uint32_t *)ar.ys.p;

@@ -113,10 +113,57 @@ constexpr int kPfMaxWords = 128;       // bitmap words per row: n/2 <= 4096 bins
 // dynamic shared memory per channel: the row's segment table and bin -> segment index, and (more than one channel)
 // the coupling staging
 __host__ __device__ inline size_t pf_row_bytes(int words) { return kSegStride * sizeof(uint4) + seg_index_stride(words); }
-inline size_t prologue_fused_smem(int channels, int words)
+// vq_elems: channels * (largest n/2) of a LWB_ENTRY_VQ batch (the residue accumulators), else 0
+inline size_t prologue_fused_smem(int channels, int words, size_t vq_elems = 0)
 {
-    return (size_t)channels * pf_row_bytes(words) + (channels > 1 ? (size_t)channels * kPfThreads * sizeof(float4) : 0);
+    return (size_t)channels * pf_row_bytes(words) + (channels > 1 ? (size_t)channels * kPfThreads * sizeof(float4) : 0) +
+           vq_elems * sizeof(float);
 }
+constexpr size_t kVqMaxElems = 12288;          // 48 KB of accumulators: stereo up to n = 8192, 5.1 up to n = 4096
+
+// LWB_ENTRY_VQ: the packet's residue vectors, accumulated in shared memory from its VQ records in the reference's
+// order (residue_packet_decode_inner, audio.rs:620-717; residue_packet_read_partition, :587-618): per coefficient
+// the f32 additions happen pass by pass; within a pass the vectors of a packet are disjoint, so they run in parallel.
+// acc: [C][n2], zeroed here.  Called by the whole CTA (contains barriers).
+__device__ __forceinline__ void d_vq_accumulate(float *acc, int C, int n2, const DevSetup &su, const DevMapping &mp,
+                                                const lwb_vq_record *__restrict__ rec, uint32_t nrec, int tid)
+{
+    const int total = C * n2;
+    for (int i = tid; i < total; i += kPfThreads) acc[i] = 0.f;
+    __syncthreads();
+    for (uint32_t pass = 0; pass < 8; pass++) {
+        bool any = false;
+        for (uint32_t i = tid; i < nrec; i += kPfThreads) {
+            const lwb_vq_record r = rec[i];
+            if (((r.entry_pass_kind >> 24) & 7u) != pass) continue;
+            any = true;
+            if (r.book >= su.n_books) continue;
+            const DevBook bk = su.books[r.book];
+            const uint32_t e = r.entry_pass_kind & 0xffffffu, kind = (r.entry_pass_kind >> 27) & 3u;
+            if (!bk.vq || e >= bk.entries) continue;
+            const float *__restrict__ v = bk.vq + (size_t)e * bk.dims;
+            if (kind == 0) {                                   // residue type 1: contiguous (audio.rs:599-615)
+                if ((int)r.pos + (int)bk.dims > total) continue;
+                for (int k = 0; k < bk.dims; k++) acc[r.pos + k] = __fadd_rn(acc[r.pos + k], v[k]);
+            } else if (kind == 1) {                            // residue type 0: stride partition_size / dimensions (:589-597)
+                const int step = r.aux < su.n_residues ? (int)(su.res_psize[r.aux] / bk.dims) : 0;
+                if (step <= 0 || (int)r.pos + (bk.dims - 1) * step >= total) continue;
+                for (int k = 0; k < bk.dims; k++) acc[r.pos + k * step] = __fadd_rn(acc[r.pos + k * step], v[k]);
+            } else {                                           // residue type 2: one interleaved vector per submap (:744-756)
+                const int nch = r.aux < LWB_MAX_SUBMAPS ? mp.sub_nch[r.aux] : 0;
+                if (nch <= 0) continue;
+                for (int k = 0; k < bk.dims; k++) {
+                    const int t = r.pos + k, bin = t / nch;
+                    if (bin >= n2) break;
+                    const int a = mp.sub_ch[r.aux][t - bin * nch] * n2 + bin;
+                    acc[a] = __fadd_rn(acc[a], v[k]);
+                }
+            }
+        }
+        __syncthreads_or(any);             // (a barrier; its value is not needed: an empty pass costs one sweep of the records)
+    }
+}
+
 
 // Floor values of the 4 bins [k0, k0 + 4) of one channel row, tables in shared memory.
 template <bool SHIFT>
@@ -149,10 +196,13 @@ __device__ __forceinline__ float4 d_floor_quad(int kind, int cnt, const float *_
 // (and the arena bases) to be multiples of 4 elements, <= 8 channels, a uniform channel count C.
 // Per packet: every global read the packet needs -- residue quads, the rows' segment tables and indices -- is issued
 // at the top (one exposed memory latency), the tables land in shared memory, and the per-bin work runs out of it.
+// VQ: the residue does not come from `residue` but from the packet's VQ records (d_vq_accumulate).
+template <bool VQ>
 __global__ void __launch_bounds__(kPfThreads, 4)
 k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float *__restrict__ residue, const float *__restrict__ dense_floor,
                  const uint8_t *__restrict__ floor_kind, const uint4 *__restrict__ segtab, const uint8_t *__restrict__ seg_cnt,
-                 const unsigned char *__restrict__ seg_index, int words, float *__restrict__ spec)
+                 const unsigned char *__restrict__ seg_index, int words, float *__restrict__ spec,
+                 const lwb_vq_record *__restrict__ vq_rec, const uint64_t *__restrict__ vq_off)
 {
     extern __shared__ __align__(16) unsigned char pf_smem[];
     __shared__ float s_db[256];
@@ -163,6 +213,7 @@ k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float 
     const size_t ixs = seg_index_stride(words), rowb = pf_row_bytes(words);
     const int row_q = (int)(rowb >> 4), tab_q = kSegStride;       // 16-byte quads per row: table, then index
     float4 *s_r = reinterpret_cast<float4 *>(pf_smem + (size_t)C * rowb);     // [C][kPfThreads] when C > 1
+    float *s_acc = reinterpret_cast<float *>(pf_smem + (size_t)C * rowb + (C > 1 ? (size_t)C * kPfThreads * sizeof(float4) : 0));   // VQ: [C][n2]
     for (uint32_t pk = blockIdx.x; pk < n_pk; pk += gridDim.x) {
         const DevPacket &p = pkts[pk];
         const DevSetup &su = *p.setup;
@@ -174,7 +225,7 @@ k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float 
         const bool stereo = C <= 2 && nsteps <= 1;
         // residue quads of this thread (first pass of the bin loop) -- issued before the table copy
         float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-        if (stereo && tid < (n2 >> 2)) {
+        if (!VQ && stereo && tid < (n2 >> 2)) {
             r0 = *reinterpret_cast<const float4 *>(residue + base + 4 * (uint64_t)tid);
             if (C == 2) r1 = *reinterpret_cast<const float4 *>(residue + base + n2 + 4 * (uint64_t)tid);
         }
@@ -187,6 +238,10 @@ k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float 
             else if (cnt) v = reinterpret_cast<const uint4 *>(seg_index + (row0 + c) * ixs)[j - tab_q];
             reinterpret_cast<uint4 *>(pf_smem)[i] = v;
         }
+        if (VQ) {
+            const uint64_t o0 = vq_off[p.pkt_index], o1 = vq_off[p.pkt_index + 1];
+            d_vq_accumulate(s_acc, C, n2, su, mp, vq_rec + o0, (uint32_t)(o1 - o0), tid);
+        }
         __syncthreads();
         if (stereo) {
             const int k0 = kinds[0], k1 = C == 2 ? kinds[1] : LWB_FLOOR_UNUSED;
@@ -196,7 +251,10 @@ k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float 
             const unsigned char *x0 = pf_smem + (size_t)tab_q * 16, *x1 = x0 + rowb;
             for (int q = tid; q < (n2 >> 2); q += kPfThreads) {
                 const uint64_t e0 = base + 4 * (uint64_t)q, e1 = e0 + n2;
-                if (q != tid) {                                   // blocks of more than 1024 bins: further passes
+                if (VQ) {
+                    r0 = *reinterpret_cast<const float4 *>(s_acc + 4 * q);
+                    if (C == 2) r1 = *reinterpret_cast<const float4 *>(s_acc + n2 + 4 * q);
+                } else if (q != tid) {                            // blocks of more than 1024 bins: further passes
                     r0 = *reinterpret_cast<const float4 *>(residue + e0);
                     if (C == 2) r1 = *reinterpret_cast<const float4 *>(residue + e1);
                 }
@@ -224,7 +282,9 @@ k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float 
         // coupling steps without predicated register arrays); every thread touches only its own column
         for (int q = tid; q < (n2 >> 2); q += kPfThreads) {
             const uint64_t e = base + 4 * (uint64_t)q;
-            for (int c = 0; c < C; c++) s_r[c * kPfThreads + tid] = *reinterpret_cast<const float4 *>(residue + e + (uint64_t)c * n2);
+            for (int c = 0; c < C; c++)
+                s_r[c * kPfThreads + tid] = VQ ? *reinterpret_cast<const float4 *>(s_acc + (size_t)c * n2 + 4 * q)
+                                               : *reinterpret_cast<const float4 *>(residue + e + (uint64_t)c * n2);
             for (int s = nsteps - 1; s >= 0; s--) {                      // audio.rs:991-1002
                 float4 m4 = s_r[mp.mag[s] * kPfThreads + tid], a4 = s_r[mp.ang[s] * kPfThreads + tid];
                 d_inverse_couple(m4.x, a4.x); d_inverse_couple(m4.y, a4.y);
@@ -247,7 +307,9 @@ k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float 
 inline void prologue_kernel_configure()
 {
     cudaFuncSetAttribute(k_floor1_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)floor1_segments_smem(128));
-    cudaFuncSetAttribute(k_prologue_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prologue_fused_smem(8, kPfMaxWords));
+    cudaFuncSetAttribute(k_prologue_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prologue_fused_smem(8, kPfMaxWords));
+    cudaFuncSetAttribute(k_prologue_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)prologue_fused_smem(8, kPfMaxWords, kVqMaxElems));
 }
 
 }  // namespace lwb

@@ -86,7 +86,7 @@ extern "C" void lwb_ctx_destroy(lwb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->coeffs, &ctx->dense, &ctx->pcm, &ctx->spec, &ctx->segtab, &ctx->x, &ctx->desc,
+    for (DevBuf *b : {&ctx->coeffs, &ctx->dense, &ctx->pcm, &ctx->spec, &ctx->segtab, &ctx->vqoff, &ctx->vqrec, &ctx->x, &ctx->desc,
                       &ctx->kinds, &ctx->ys, &ctx->chains, &ctx->ticket, &ctx->runs_buf[0], &ctx->runs_buf[1],
                       &ctx->cdesc, &ctx->cbytes})
         if (b->p) cudaFree(b->p);
@@ -357,12 +357,35 @@ extern "C" int lwb_setup_create(lwb_ctx *ctx, const lwb_setup_desc *d, lwb_setup
                 break;
             }
             dm.floor_of_channel[c] = m.submap_floors[m.mux[c]];
+            if (d->audio_channels <= 8) dm.sub_ch[m.mux[c]][dm.sub_nch[m.mux[c]]++] = (uint8_t)c;
         }
     }
     for (uint32_t i = 0; i < d->n_modes && rc == LWB_OK; i++) {
         if (d->modes[i].mapping >= d->n_mappings) { rc = LWB_ERR_BAD_FORMAT; break; }   // header.rs:1067-1072
         su->host.mode_blockflag[i] = d->modes[i].blockflag ? 1 : 0;
         su->host.mode_mapping[i] = d->modes[i].mapping;
+    }
+    // LWB_ENTRY_VQ: codebook value tables and residue partition sizes
+    if (rc == LWB_OK && d->n_codebooks) {
+        if (d->n_codebooks > 256 || !d->codebooks || d->n_residues > (uint32_t)kMaxResidues || (d->n_residues && !d->residues)) {
+            rc = LWB_ERR_INVALID;
+        } else {
+            std::vector<DevBook> books(d->n_codebooks);
+            for (uint32_t i = 0; i < d->n_codebooks && rc == LWB_OK; i++) {
+                const lwb_codebook_desc &cb = d->codebooks[i];
+                books[i].vq = nullptr;
+                books[i].entries = cb.entries;
+                books[i].dims = cb.dimensions;
+                books[i].pad = 0;
+                if (cb.vq && cb.entries && cb.dimensions) rc = upload(su, cb.vq, (size_t)cb.entries * cb.dimensions, &books[i].vq);
+            }
+            if (rc == LWB_OK) rc = upload(su, books.data(), books.size(), &su->host.books);
+            // (the uploads read the caller's tables: done before we return, see the synchronise below)
+            if (rc == LWB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = LWB_ERR_CUDA;
+            su->host.n_books = d->n_codebooks;
+            su->host.n_residues = d->n_residues;
+            for (uint32_t i = 0; i < d->n_residues; i++) su->host.res_psize[i] = d->residues[i].partition_size;
+        }
     }
     if (rc == LWB_OK) rc = upload(su, floors.data(), floors.size(), &su->host.floors);
     if (rc == LWB_OK) rc = upload(su, su->mappings.data(), su->mappings.size(), &su->host.mappings);
@@ -487,11 +510,13 @@ extern "C" int lwb_decoded_sample_count(const lwb_setup *su, uint8_t mode, int p
 static int decode_chains_impl(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, lwb_plan *prepared)
 {
     if (!ctx || (!chains && n_chains) || !io) return LWB_ERR_INVALID;
-    if (io->entry != LWB_ENTRY_SPECTRUM && io->entry != LWB_ENTRY_RESIDUE) return fail(ctx, LWB_ERR_INVALID, "bad entry");
+    if (io->entry != LWB_ENTRY_SPECTRUM && io->entry != LWB_ENTRY_RESIDUE && io->entry != LWB_ENTRY_VQ) return fail(ctx, LWB_ERR_INVALID, "bad entry");
     if (io->memory != LWB_MEM_HOST && io->memory != LWB_MEM_DEVICE) return fail(ctx, LWB_ERR_INVALID, "bad memory space");
     if (io->out_format < 0 || io->out_format > LWB_OUT_I16_INTERLEAVED) return fail(ctx, LWB_ERR_INVALID, "bad out_format");
     if (n_chains == 0) return LWB_OK;
-    if (!io->coeffs || !io->pcm) return fail(ctx, LWB_ERR_INVALID, "null arena");
+    if ((!io->coeffs && io->entry != LWB_ENTRY_VQ) || !io->pcm) return fail(ctx, LWB_ERR_INVALID, "null arena");
+    if (io->entry == LWB_ENTRY_VQ && (!io->vq_records || !io->vq_offsets || !io->floor_kind))
+        return fail(ctx, LWB_ERR_INVALID, "VQ entry needs vq_records, vq_offsets and floor_kind");
     CU(ctx, cudaSetDevice(ctx->device));
     const uint64_t epoch = ++ctx->epoch;      // per context: concurrent calls on different contexts share nothing
     {
@@ -515,7 +540,8 @@ static int decode_chains_impl(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, 
             if (rc0 || handled) return rc0;
         }
     }
-    const bool residue = io->entry == LWB_ENTRY_RESIDUE;
+    const bool vq = io->entry == LWB_ENTRY_VQ;
+    const bool residue = io->entry != LWB_ENTRY_SPECTRUM;
     const bool planar = is_planar(io->out_format);
     std::vector<PlanChain> plan(n_chains);
     uint64_t c_lo = ~0ull, c_hi = 0, o_lo = ~0ull, o_hi = 0, r_lo = ~0ull, r_hi = 0;
@@ -553,16 +579,17 @@ static int decode_chains_impl(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, 
     if (need_dense && !io->dense_floor) return fail(ctx, LWB_ERR_INVALID, "dense_floor missing");
     int rc = LWB_OK;
     if (c_hi > c_lo) {
-        DevArenas ar;
-        std::memset(&ar, 0, sizeof(ar));
+        DevArenas ar = DevArenas();
         const size_t esz = elem_size(io->out_format);
         if (io->memory == LWB_MEM_HOST) {
             // stage: H2D of the used coefficient range, D2H of the used pcm range
-            if ((rc = ensure(ctx, ctx->coeffs, (c_hi - c_lo) * sizeof(float)))) return rc;
             if (o_hi > o_lo && (rc = ensure(ctx, ctx->pcm, (o_hi - o_lo) * esz))) return rc;
-            CU(ctx, cudaMemcpyAsync(ctx->coeffs.p, io->coeffs + c_lo, (c_hi - c_lo) * sizeof(float),
-                                    cudaMemcpyHostToDevice, ctx->stream));
-            ar.coeffs = (const float *)ctx->coeffs.p;
+            if (!vq) {
+                if ((rc = ensure(ctx, ctx->coeffs, (c_hi - c_lo) * sizeof(float)))) return rc;
+                CU(ctx, cudaMemcpyAsync(ctx->coeffs.p, io->coeffs + c_lo, (c_hi - c_lo) * sizeof(float),
+                                        cudaMemcpyHostToDevice, ctx->stream));
+                ar.coeffs = (const float *)ctx->coeffs.p;
+            }
             ar.coeff_base = c_lo;
             if (need_dense) {
                 if ((rc = ensure(ctx, ctx->dense, (c_hi - c_lo) * sizeof(float)))) return rc;
@@ -573,10 +600,11 @@ static int decode_chains_impl(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, 
             ar.pcm = ctx->pcm.p;
             ar.pcm_base = o_lo;
         } else {
-            ar.coeffs = io->coeffs;
+            ar.coeffs = vq ? nullptr : io->coeffs;
             ar.dense = io->dense_floor;
             ar.pcm = io->pcm;
         }
+        if ((rc = stage_vq_arrays(ctx, io, r_lo, r_hi, ctx->stream, &ar.vq))) return rc;
         if (residue) {
             // absolute packet rows address the (biased) device views: kinds_row0 stays 0
             if ((rc = stage_floor_arrays(ctx, io, r_lo, r_hi, (unsigned)uniform_c, ctx->stream, &ar.kinds, &ar.ys))) return rc;
@@ -653,8 +681,10 @@ static int replay_front_stages(lwb_plan *p)
     const uint32_t *d_ys;
     int rc = stage_floor_arrays(ctx, io, p->pro_r_lo, p->pro_r_hi, p->pro_C, ctx->stream, &d_kinds, &d_ys);
     if (rc) return rc;
-    return launch_prologue(ctx, (const DevPacket *)p->pro.p, p->n_pro, p->pro_C, p->pro_fast, p->pro_smem_old, kLongN2, io->coeffs,
-                           io->dense_floor, d_kinds, d_ys, (float *)ctx->spec.p - p->pro_c_lo);
+    VqView vqv;
+    if ((rc = stage_vq_arrays(ctx, io, p->pro_r_lo, p->pro_r_hi, ctx->stream, &vqv))) return rc;
+    return launch_prologue(ctx, (const DevPacket *)p->pro.p, p->n_pro, p->pro_C, p->pro_fast, p->pro_smem_old, kLongN2,
+                           io->entry == LWB_ENTRY_VQ ? nullptr : io->coeffs, io->dense_floor, d_kinds, d_ys, (float *)ctx->spec.p - p->pro_c_lo, vqv);
 }
 
 extern "C" int lwb_plan_execute(lwb_plan *p)
@@ -687,8 +717,11 @@ extern "C" int lwb_plan_execute(lwb_plan *p)
             const uint32_t *d_ys;
             int prc = stage_floor_arrays(ctx, io, p->mix_pro_r_lo, p->mix_pro_r_hi, p->mix_pro_C, ctx->stream, &d_kinds, &d_ys);
             if (prc) return prc;
-            prc = launch_prologue(ctx, p->mix_pro_pk, p->mix_pro_n, p->mix_pro_C, p->mix_pro_fast, p->mix_pro_smem_old, p->mix_pro_n2max, io->coeffs,
-                                  p->mix_pro_dense ? io->dense_floor : nullptr, d_kinds, d_ys, (float *)ctx->spec.p - p->mix_pro_c_lo);
+            VqView vqv;
+            if ((prc = stage_vq_arrays(ctx, io, p->mix_pro_r_lo, p->mix_pro_r_hi, ctx->stream, &vqv))) return prc;
+            prc = launch_prologue(ctx, p->mix_pro_pk, p->mix_pro_n, p->mix_pro_C, p->mix_pro_fast, p->mix_pro_smem_old, p->mix_pro_n2max,
+                                  io->entry == LWB_ENTRY_VQ ? nullptr : io->coeffs, p->mix_pro_dense ? io->dense_floor : nullptr, d_kinds, d_ys,
+                                  (float *)ctx->spec.p - p->mix_pro_c_lo, vqv);
             if (prc) return prc;
         }
         return mixed_launch_rounds(ctx, p->mix_launch, p->mix_rounds);

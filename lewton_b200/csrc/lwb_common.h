@@ -40,7 +40,19 @@ struct DevMapping {           // Mapping (header.rs:384-390) with mux/submap_flo
     uint8_t mag[LWB_MAX_COUPLING];
     uint8_t ang[LWB_MAX_COUPLING];
     uint8_t floor_of_channel[LWB_MAX_CHANNELS + 1];   // submap_floors[mux[ch]]
+    // channels of every submap in ascending order (the order residue type 2 interleaves them in, audio.rs:957-986);
+    // filled for setups with <= 8 channels (LWB_ENTRY_VQ)
+    uint8_t sub_nch[LWB_MAX_SUBMAPS];
+    uint8_t sub_ch[LWB_MAX_SUBMAPS][8];
 };
+
+struct DevBook {              // Codebook (header.rs:360-368): the value table of LWB_ENTRY_VQ
+    const float *vq;          // [entries][dims], or nullptr
+    uint32_t entries;
+    uint16_t dims;
+    uint16_t pad;
+};
+constexpr int kMaxResidues = 64;      // header.rs:973 residue count = read_u6 + 1
 
 struct DevSetup {
     DevTables tab[2];
@@ -49,6 +61,10 @@ struct DevSetup {
     uint8_t channels, bs0, bs1, n_floors;
     uint8_t mode_blockflag[LWB_MAX_MODES];
     uint8_t mode_mapping[LWB_MAX_MODES];
+    // LWB_ENTRY_VQ
+    const DevBook *books;
+    uint32_t n_books, n_residues;
+    uint32_t res_psize[kMaxResidues];  // residue_partition_size
 };
 
 // One packet of a batch; every index/geometry decision is made on the host

@@ -89,6 +89,7 @@ static int try_chain(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
     if (plan) plan->mixed_captured = false;
     if (const char *e = getenv("LWB_FORCE_GENERIC"))
         if (std::strcmp(e, "1") == 0) return LWB_OK;          // "1": the four-kernel path; "2": no fused kernel only
+    if (io->entry == LWB_ENTRY_VQ) return LWB_OK;            // (its residue stage runs inside the kernel, on dense vectors)
     const bool residue = io->entry == LWB_ENTRY_RESIDUE;
     const bool planar = is_planar(io->out_format);
     const size_t esz = elem_size(io->out_format);

@@ -94,18 +94,23 @@ static bool prologue_is_fast(const DevPacket *h_pk, size_t n_pk, unsigned C, con
     bool fast = C <= 8 && n_pk * (size_t)C < 0xffffffffu && !getenv("LWB_OLD_PROLOGUE");
     for (size_t i = 0; fast && i < n_pk; i++) {
         const uint64_t e = h_pk[i].coeff_off;
-        fast = ((reinterpret_cast<uintptr_t>(res + e) | reinterpret_cast<uintptr_t>(spec + e) |
+        fast = (((res ? reinterpret_cast<uintptr_t>(res + e) : 0) | reinterpret_cast<uintptr_t>(spec + e) |
                  (dense ? reinterpret_cast<uintptr_t>(dense + e) : 0)) & 15) == 0 && h_pk[i].channels == C;
     }
     return fast;
 }
 
+// VQ views of a batch (LWB_ENTRY_VQ), device pointers biased like the floor arrays; rec == nullptr otherwise
+struct VqView { const lwb_vq_record *rec = nullptr; const uint64_t *off = nullptr; };
+
 // n2max: the largest n/2 among the packets (sizes the per-row bin -> segment index).
 static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, size_t n_pk, unsigned C, bool fast, size_t smem_old, int n2max,
-                           const float *res, const float *dense, const uint8_t *kinds, const uint32_t *ys, float *spec)
+                           const float *res, const float *dense, const uint8_t *kinds, const uint32_t *ys, float *spec, VqView vq = VqView())
 {
     if (!n_pk) return LWB_OK;
     const int words = std::max(1, (n2max + 31) >> 5);
+    if (vq.rec && (!fast || (size_t)C * n2max > kVqMaxElems))
+        return fail(ctx, LWB_ERR_INVALID, "VQ entry needs <= 8 channels, aligned arenas and channels * n/2 <= 12288");
     if (!fast)
         return launch(ctx, k_prologue, dim3((unsigned)n_pk), dim3(kPrologueThreads), smem_old, d_pk, res, dense, kinds, ys, spec);
     // per (packet, channel) row (ctx scratch): the packed flagged segments of its floor curve, the bin -> segment
@@ -120,15 +125,19 @@ static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, size_t n_pk, uns
                 (uint32_t)rows, (int)C, kinds, ys, tab, cnt, ix, words);
     if (rc) return rc;
     const size_t grid = std::min<size_t>(n_pk, (size_t)ctx->sm_count * (C > 2 ? 4 : 8));
-    return launch(ctx, k_prologue_fused, dim3((unsigned)grid), dim3(kPfThreads), prologue_fused_smem((int)C, words), d_pk, (uint32_t)n_pk, res, dense,
-                  kinds, (const uint4 *)tab, (const uint8_t *)cnt, (const unsigned char *)ix, words, spec);
+    if (vq.rec)
+        return launch(ctx, k_prologue_fused<true>, dim3((unsigned)grid), dim3(kPfThreads), prologue_fused_smem((int)C, words, (size_t)C * n2max), d_pk,
+                      (uint32_t)n_pk, res, dense, kinds, (const uint4 *)tab, (const uint8_t *)cnt, (const unsigned char *)ix, words, spec, vq.rec, vq.off);
+    return launch(ctx, k_prologue_fused<false>, dim3((unsigned)grid), dim3(kPfThreads), prologue_fused_smem((int)C, words), d_pk, (uint32_t)n_pk, res, dense,
+                  kinds, (const uint4 *)tab, (const uint8_t *)cnt, (const unsigned char *)ix, words, spec, (const lwb_vq_record *)nullptr,
+                  (const uint64_t *)nullptr);
 }
 static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, const DevPacket *h_pk, size_t n_pk, unsigned C, size_t smem_old,
-                           const float *res, const float *dense, const uint8_t *kinds, const uint32_t *ys, float *spec)
+                           const float *res, const float *dense, const uint8_t *kinds, const uint32_t *ys, float *spec, VqView vq = VqView())
 {
     int n2max = 32;
     for (size_t i = 0; i < n_pk; i++) n2max = std::max(n2max, h_pk[i].n >> 1);
-    return launch_prologue(ctx, d_pk, n_pk, C, prologue_is_fast(h_pk, n_pk, C, res, dense, spec), smem_old, n2max, res, dense, kinds, ys, spec);
+    return launch_prologue(ctx, d_pk, n_pk, C, prologue_is_fast(h_pk, n_pk, C, res, dense, spec), smem_old, n2max, res, dense, kinds, ys, spec, vq);
 }
 
 // Host-side look at the floor kinds of rows [row_lo, row_hi) (one row per (packet, channel)).  Device-resident
@@ -176,6 +185,30 @@ static int stage_floor_arrays(lwb_ctx *ctx, const lwb_batch_io *io, uint64_t r_l
     return LWB_OK;
 }
 
+// LWB_ENTRY_VQ: device view of the VQ records of packet rows [r_lo, r_hi), biased so that absolute rows / absolute
+// record offsets address it (host arrays are uploaded to ctx->vqoff / ctx->vqrec on `sm`).
+static int stage_vq_arrays(lwb_ctx *ctx, const lwb_batch_io *io, uint64_t r_lo, uint64_t r_hi, cudaStream_t sm, VqView *out)
+{
+    *out = VqView();
+    if (io->entry != LWB_ENTRY_VQ) return LWB_OK;
+    if (io->floor_memory == LWB_MEM_DEVICE) {
+        out->rec = io->vq_records;
+        out->off = io->vq_offsets;
+        return LWB_OK;
+    }
+    if (r_hi <= r_lo) return LWB_OK;
+    int rc;
+    const uint64_t o_lo = io->vq_offsets[r_lo], o_hi = io->vq_offsets[r_hi];
+    if (o_hi < o_lo) return fail(ctx, LWB_ERR_INVALID, "vq_offsets must be non-decreasing");
+    const size_t nrow = (size_t)(r_hi - r_lo) + 1, nrec = (size_t)(o_hi - o_lo);
+    if ((rc = ensure(ctx, ctx->vqoff, nrow * sizeof(uint64_t))) || (rc = ensure(ctx, ctx->vqrec, std::max<size_t>(nrec, 1) * sizeof(lwb_vq_record)))) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->vqoff.p, io->vq_offsets + r_lo, nrow * sizeof(uint64_t), cudaMemcpyHostToDevice, sm));
+    if (nrec) CU(ctx, cudaMemcpyAsync(ctx->vqrec.p, io->vq_records + o_lo, nrec * sizeof(lwb_vq_record), cudaMemcpyHostToDevice, sm));
+    out->off = (const uint64_t *)ctx->vqoff.p - r_lo;
+    out->rec = (const lwb_vq_record *)ctx->vqrec.p - o_lo;
+    return LWB_OK;
+}
+
 struct DevArenas {
     const float *coeffs;      // device
     const float *dense;       // device or null
@@ -185,6 +218,7 @@ struct DevArenas {
     void *pcm;                // device
     uint64_t coeff_base;      // element offset that device coeffs[0] corresponds to
     uint64_t pcm_base;        // element offset that device pcm[0] corresponds to
+    VqView vq;                // LWB_ENTRY_VQ
 };
 
 // Generic path: rounds of packets bounded by the IMDCT scratch.
@@ -271,10 +305,10 @@ static int run_generic(lwb_ctx *ctx, std::vector<PlanChain> &plan, const lwb_bat
         CU(ctx, cudaMemcpyAsync(ctx->desc.p, hp, n_desc * sizeof(DevPacket), cudaMemcpyHostToDevice, ctx->stream));
         const DevPacket *dp = (const DevPacket *)ctx->desc.p;
         const float *spec = ar.coeffs;
-        if (io->entry == LWB_ENTRY_RESIDUE) {
+        if (io->entry != LWB_ENTRY_SPECTRUM) {
             if ((rc = ensure(ctx, ctx->spec, spec_hi * sizeof(float)))) return rc;
             if ((rc = launch_prologue(ctx, dp, hp, n_desc, maxc, prologue_smem_of(plan), ar.coeffs, ar.dense, ar.kinds, ar.ys,
-                                      (float *)ctx->spec.p)))
+                                      (float *)ctx->spec.p, ar.vq)))
                 return rc;
             spec = (const float *)ctx->spec.p;
         }

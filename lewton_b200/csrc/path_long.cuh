@@ -381,7 +381,7 @@ static int run_prologue_all(lwb_ctx *ctx, std::vector<PlanChain> &plan, const De
     }
     CU(ctx, cudaMemcpyAsync(ctx->desc.p, hp, n_desc * sizeof(DevPacket), cudaMemcpyHostToDevice, ctx->stream));
     return launch_prologue(ctx, (const DevPacket *)ctx->desc.p, hp, n_desc, plan[0].c->stream->setup->channels, prologue_smem_of(plan),
-                           ar.coeffs, ar.dense, ar.kinds, ar.ys, (float *)ctx->spec.p);
+                           ar.coeffs, ar.dense, ar.kinds, ar.ys, (float *)ctx->spec.p, ar.vq);
 }
 
 
@@ -394,8 +394,9 @@ static int try_long_residue(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, co
                             lwb_plan *plan)
 {
     *handled = false;
-    if (io->entry != LWB_ENTRY_RESIDUE || getenv("LWB_FORCE_GENERIC")) return LWB_OK;
+    if (io->entry == LWB_ENTRY_SPECTRUM || getenv("LWB_FORCE_GENERIC")) return LWB_OK;
     if (!batch_is_uniform_long(ctx, chains, n_chains, io)) return LWB_OK;
+    const bool vq = io->entry == LWB_ENTRY_VQ;
     if (!io->floor_kind) return fail(ctx, LWB_ERR_INVALID, "residue entry needs floor_kind");
     unsigned C = 0;
     size_t n_pk = 0;
@@ -428,11 +429,13 @@ static int try_long_residue(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, co
     }
     cudaStream_t sm = ctx->stream;
     const size_t elems = (size_t)(c_hi - c_lo);
-    const float *d_res = io->coeffs, *d_dense = need_dense ? io->dense_floor : nullptr;
+    const float *d_res = vq ? nullptr : io->coeffs, *d_dense = need_dense ? io->dense_floor : nullptr;
     if (io->memory == LWB_MEM_HOST) {
-        if ((rc = ensure(ctx, ctx->coeffs, elems * 4))) return rc;
-        CU(ctx, cudaMemcpyAsync(ctx->coeffs.p, io->coeffs + c_lo, elems * 4, cudaMemcpyHostToDevice, sm));
-        d_res = (const float *)ctx->coeffs.p - c_lo;
+        if (!vq) {
+            if ((rc = ensure(ctx, ctx->coeffs, elems * 4))) return rc;
+            CU(ctx, cudaMemcpyAsync(ctx->coeffs.p, io->coeffs + c_lo, elems * 4, cudaMemcpyHostToDevice, sm));
+            d_res = (const float *)ctx->coeffs.p - c_lo;
+        }
         if (need_dense) {
             if ((rc = ensure(ctx, ctx->dense, elems * 4))) return rc;
             CU(ctx, cudaMemcpyAsync(ctx->dense.p, io->dense_floor + c_lo, elems * 4, cudaMemcpyHostToDevice, sm));
@@ -444,6 +447,8 @@ static int try_long_residue(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, co
     const uint8_t *d_kinds;
     const uint32_t *d_ys;
     if ((rc = stage_floor_arrays(ctx, io, r_lo, r_hi, C, sm, &d_kinds, &d_ys))) return rc;
+    VqView vqv;
+    if ((rc = stage_vq_arrays(ctx, io, r_lo, r_hi, sm, &vqv))) return rc;
     // front-stage descriptors: absolute element offsets and packet rows (the arena pointers are biased instead)
     const DevPacket *d_pk;
     bool fast;
@@ -487,7 +492,7 @@ static int try_long_residue(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, co
             plan->pro_c_lo = c_lo; plan->pro_c_hi = c_hi; plan->pro_r_lo = r_lo; plan->pro_r_hi = r_hi;
         }
     }
-    if ((rc = launch_prologue(ctx, d_pk, n_pk, C, fast, smem_old, kLongN2, d_res, d_dense, d_kinds, d_ys, d_spec))) return rc;
+    if ((rc = launch_prologue(ctx, d_pk, n_pk, C, fast, smem_old, kLongN2, d_res, d_dense, d_kinds, d_ys, d_spec, vqv))) return rc;
     bool h2 = false;
     rc = try_long(ctx, chains, n_chains, io, epoch, &h2, (const float *)ctx->spec.p, c_lo, plan, true);
     if (rc) return rc;

@@ -18,7 +18,8 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
     if (plan) plan->mixed_captured = false;
     if (getenv("LWB_FORCE_GENERIC") || getenv("LWB_NO_MIXED")) return LWB_OK;
     if (io->out_format != LWB_OUT_F32_PLANAR && io->out_format != LWB_OUT_I16_PLANAR) return LWB_OK;
-    const bool residue = io->entry == LWB_ENTRY_RESIDUE;
+    const bool vq = io->entry == LWB_ENTRY_VQ;
+    const bool residue = io->entry != LWB_ENTRY_SPECTRUM;
     const bool i16 = io->out_format == LWB_OUT_I16_PLANAR;
     const size_t esz = i16 ? 2 : 4;
     unsigned maxc = 1;
@@ -187,10 +188,13 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         cudaStream_t sm = ctx->stream;
         const float *d_coeffs = io->coeffs, *d_dense = io->dense_floor;
         char *d_pcm = (char *)io->pcm;
+        if (vq) d_coeffs = nullptr;
         if (host) {
-            if ((rc = ensure(ctx, ctx->coeffs, (size_t)(c_hi - c_lo) * 4))) return rc;
             if (o_hi > o_lo && (rc = ensure(ctx, ctx->pcm, (size_t)(o_hi - o_lo) * esz))) return rc;
-            d_coeffs = (const float *)ctx->coeffs.p - c_lo;       // the copies themselves go chunk by chunk, below
+            if (!vq) {
+                if ((rc = ensure(ctx, ctx->coeffs, (size_t)(c_hi - c_lo) * 4))) return rc;
+                d_coeffs = (const float *)ctx->coeffs.p - c_lo;       // the copies themselves go chunk by chunk, below
+            }
             if (need_dense) {
                 if ((rc = ensure(ctx, ctx->dense, (size_t)(c_hi - c_lo) * 4))) return rc;
                 d_dense = (const float *)ctx->dense.p - c_lo;
@@ -215,6 +219,8 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         const uint8_t *d_kinds = nullptr;
         const uint32_t *d_ys = nullptr;
         if (residue && (rc = stage_floor_arrays(ctx, io, r_lo, r_hi, (unsigned)uniform_c, sm, &d_kinds, &d_ys))) return rc;
+        VqView vqv;
+        if ((rc = stage_vq_arrays(ctx, io, r_lo, r_hi, sm, &vqv))) return rc;
         // descriptors of every round: [LongRun...][ChainDesc...][DevPacket (prologue of the long segments)...][mode bytes]
         // A round with few fused-kernel runs leaves most of the 148 x 8 warps idle and lasts as long as its
         // longest run: such rounds cut their runs (each cut costs one extra IMDCT, the primer packet whose
@@ -447,8 +453,9 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             Chunk &ck = chunks[k];
             if (ck.kc_hi <= ck.kc_lo) continue;
             if (host) {
-                CU(ctx, cudaMemcpyAsync((float *)ctx->coeffs.p + (ck.kc_lo - c_lo), io->coeffs + ck.kc_lo, (size_t)(ck.kc_hi - ck.kc_lo) * 4,
-                                        cudaMemcpyHostToDevice, ctx->copy_in));
+                if (!vq)
+                    CU(ctx, cudaMemcpyAsync((float *)ctx->coeffs.p + (ck.kc_lo - c_lo), io->coeffs + ck.kc_lo, (size_t)(ck.kc_hi - ck.kc_lo) * 4,
+                                            cudaMemcpyHostToDevice, ctx->copy_in));
                 if (need_dense)
                     CU(ctx, cudaMemcpyAsync((float *)ctx->dense.p + (ck.kc_lo - c_lo), io->dense_floor + ck.kc_lo,
                                             (size_t)(ck.kc_hi - ck.kc_lo) * 4, cudaMemcpyHostToDevice, ctx->copy_in));
@@ -457,7 +464,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             }
             if (residue && ck.np_)
                 if ((rc = launch_prologue(ctx, (const DevPacket *)(db + off_pro) + ck.p0, ck.np_, maxc, pro_fast, prologue_smem(maxc, kLongBs), n1max_all >> 1,
-                                          d_coeffs, need_dense ? d_dense : nullptr, d_kinds, d_ys, const_cast<float *>(d_spec))))
+                                          d_coeffs, need_dense ? d_dense : nullptr, d_kinds, d_ys, const_cast<float *>(d_spec), vqv)))
                     return rc;
             if ((rc = mixed_launch_rounds(ctx, ml, ck.rounds))) return rc;
             if (host && ck.ko_hi > ck.ko_lo) {

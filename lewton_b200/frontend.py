@@ -19,11 +19,14 @@ from .api import AudioReadError, DecodedPacket, Setup
  ERR_HEADER_IS_AUDIO, ERR_UTF8, ERR_AUDIO_IS_HEADER, ERR_OGG, ERR_NO_MORE_PACKETS) = range(16, 26)
 
 SYMBOLS = ["lwf_headers_parse", "lwf_headers_destroy", "lwf_headers_info", "lwf_headers_comment", "lwf_headers_make_setup",
-           "lwf_packet_decode", "lwf_decoded_sample_count", "lwf_ogg_open", "lwf_ogg_close", "lwf_ogg_next_packet",
+           "lwf_packet_decode", "lwf_packet_decode_vq", "lwf_headers_vq_capable", "lwf_decoded_sample_count", "lwf_ogg_open", "lwf_ogg_close", "lwf_ogg_next_packet",
            "lwf_reader_open", "lwf_reader_close", "lwf_reader_headers", "lwf_reader_read_dec_packet", "lwf_reader_last_absgp",
            "lwf_reader_skip_samples_linear", "lwf_reader_seek_absgp_pg",
-           "lwf_batcher_create", "lwf_batcher_destroy", "lwf_batcher_decode", "lwf_batcher_last_timing",
+           "lwf_batcher_create", "lwf_batcher_destroy", "lwf_batcher_set_entry", "lwf_batcher_decode", "lwf_batcher_last_timing",
            "lwf_debug_float32_unpack", "lwf_debug_lookup1_values", "lwf_debug_ilog", "lwf_debug_read_bits", "lwf_debug_huffman"]
+
+
+VQ_DTYPE = np.dtype([("entry_pass_kind", np.uint32), ("pos", np.uint16), ("book", np.uint8), ("aux", np.uint8)])   # lwb_vq_record
 
 
 class HeaderReadError(Exception):
@@ -100,6 +103,9 @@ def lib():
         L.lwf_batcher_create.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
         L.lwf_batcher_destroy.argtypes = [vp]
         L.lwf_batcher_destroy.restype = None
+        L.lwf_batcher_set_entry.argtypes = [vp, C.c_int]
+        L.lwf_headers_vq_capable.argtypes = [vp]
+        L.lwf_packet_decode_vq.argtypes = [vp, C.c_char_p, sz, vp, vp, sz, C.POINTER(sz)]
         L.lwf_batcher_decode.argtypes = [vp, C.POINTER(_StreamJob), sz, C.c_int, vp]
         L.lwf_batcher_last_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.lwf_batcher_last_timing.restype = None
@@ -192,6 +198,45 @@ class Headers:
         out = DecodedPacket(dp.mode_number, residue, floors, dp.prev_window_flag, dp.next_window_flag)
         out.blockflag, out.n = bool(dp.blockflag), dp.n
         return out
+
+    def vq_capable(self):
+        """True if LWB_ENTRY_VQ applies to this stream (lwf_headers_vq_capable)."""
+        return bool(lib().lwf_headers_vq_capable(self._h))
+
+    def decode_packet_vq(self, packet):
+        """The same front half with the residue left as VQ records: (DecodedPacket with residue None, records) where
+        records is a structured array of cabi.VqRecord (entry_pass_kind, pos, book, aux)."""
+        Cn, n2max = self.audio_channels, (1 << self.blocksize_1) // 2
+        kinds = np.zeros(Cn, np.uint8)
+        ys = np.zeros((Cn, cabi.MAX_POSTS), np.uint32)
+        dense = np.zeros((Cn, n2max), np.float32)
+        dp = _DecodedPacket()
+        dp.floor_kind = kinds.ctypes.data_as(cabi.u8p)
+        dp.floor1_y = ys.ctypes.data_as(cabi.u32p)
+        dp.dense_floor = dense.ctypes.data_as(cabi.fp)
+        cap = len(packet) * 8 + 16
+        recs = np.zeros(cap, VQ_DTYPE)
+        n = C.c_size_t()
+        rc = lib().lwf_packet_decode_vq(self._h, bytes(packet), len(packet), C.byref(dp), recs.ctypes.data, cap, C.byref(n))
+        if rc == cabi.ERR_BAD_FORMAT:
+            raise AudioReadError(rc)
+        if rc:
+            e = AudioReadError(rc)
+            e.kind = {ERR_END_OF_PACKET: "EndOfPacket", ERR_AUDIO_IS_HEADER: "AudioIsHeader"}.get(rc, e.kind)
+            raise e
+        n2 = dp.n // 2
+        floors = []
+        flat_dense = dense.ravel()
+        for c in range(Cn):
+            if kinds[c] == cabi.FLOOR_UNUSED:
+                floors.append(None)
+            elif kinds[c] == cabi.FLOOR_ONE:
+                floors.append(ys[c].copy())
+            else:
+                floors.append(flat_dense[c * n2:(c + 1) * n2].copy())
+        out = DecodedPacket(dp.mode_number, np.zeros((Cn, n2), np.float32), floors, dp.prev_window_flag, dp.next_window_flag)
+        out.blockflag, out.n = bool(dp.blockflag), dp.n
+        return out, recs[: n.value].copy()
 
     def decoded_sample_count(self, packet):
         n = C.c_size_t()
@@ -370,12 +415,16 @@ class StreamBatcher:
     thread pool and synthesise them with one batched call.  jobs: list of (PreviousWindowRight,
     [packet bytes, ...]); PCM lands planar in `pcm` at out_offset = job index * channels * stride."""
 
-    def __init__(self, ctx, headers, threads=0):
+    def __init__(self, ctx, headers, threads=0, entry=cabi.ENTRY_RESIDUE):
         self.ctx, self.headers = ctx, headers
         h = C.c_void_p()
         ctx.check(lib().lwf_batcher_create(ctx._h, headers._h, threads, C.byref(h)))
         self._h = h.value
         ctx._children.add(self)
+        if entry != cabi.ENTRY_RESIDUE:        # LWB_ENTRY_VQ: VQ records instead of dense residue vectors cross the boundary
+            rc = lib().lwf_batcher_set_entry(self._h, entry)
+            if rc:
+                raise AudioReadError(rc, "this stream does not qualify for LWB_ENTRY_VQ (lwf_headers_vq_capable)")
 
     def decode(self, jobs, pcm, stride, out_format=cabi.OUT_F32_PLANAR):
         n = len(jobs)

@@ -18,6 +18,7 @@ int lwb_setup_create(lwb_ctx *, const lwb_setup_desc *, lwb_setup **) { return L
 void lwb_setup_destroy(lwb_setup *) {}
 int lwb_stream_open(lwb_ctx *, const lwb_setup *, lwb_stream **) { return LWB_ERR_NO_DEVICE; }
 void lwb_stream_destroy(lwb_stream *) {}
+int lwb_stream_reset(lwb_stream *) { return LWB_OK; }
 int lwb_decode_packet(lwb_stream *, const lwb_packet *, int, void *, size_t, size_t *) { return LWB_ERR_NO_DEVICE; }
 int lwb_decode_chains(lwb_ctx *, lwb_chain *, size_t, const lwb_batch_io *) { return LWB_ERR_NO_DEVICE; }
 void *lwb_host_alloc(size_t n) { return std::malloc(n); }

@@ -438,3 +438,162 @@ def test_skip_samples_linear_and_seek_absgp_pg(ctx, oracle, seed, channels):
             if w is None:
                 break
     rd.close()
+
+
+@pytest.mark.parametrize("channels,rtype,memory,floor_mem,fmt,seed", [
+    (2, 1, cabi.MEM_HOST, cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 501),
+    (2, 0, cabi.MEM_DEVICE, cabi.MEM_DEVICE, cabi.OUT_F32_PLANAR, 502),
+    (2, 2, cabi.MEM_HOST, cabi.MEM_HOST, cabi.OUT_I16_PLANAR, 503),
+    (6, None, cabi.MEM_DEVICE, cabi.MEM_HOST, cabi.OUT_F32_PLANAR, 504),
+    (1, None, cabi.MEM_HOST, cabi.MEM_HOST, cabi.OUT_I16_INTERLEAVED, 505),
+    (3, 2, cabi.MEM_DEVICE, cabi.MEM_DEVICE, cabi.OUT_I16_PLANAR, 506)])
+def test_vq_entry_accumulates_the_residue_on_the_device(ctx, oracle, channels, rtype, memory, floor_mem, fmt, seed):
+    """LWB_ENTRY_VQ (audio.rs:587-717): no dense coefficients cross the boundary -- the front half
+    hands over VQ records, the device accumulates the residue vectors pass by pass in shared memory and runs the rest
+    of the path.  Every stream is bit-identical to the oracle's decode of what the packer encoded, and the whole PCM
+    arena is identical to the dense residue entry on the same packets -- including streams whose packets were cut at
+    arbitrary bytes (the residue decode keeps what it had, audio.rs:640-716)."""
+    rng = np.random.default_rng(seed)
+    S, P = 7, 9
+    spec = vp.StreamSpec(rng, channels=channels, residue_types=[rtype] if rtype is not None else None)
+    hdr = fe.Headers(spec.ident_packet(), spec.comment_packet(), spec.setup_packet())
+    assert hdr.vq_capable()
+    su = hdr.make_setup(ctx)
+    streams, wants = [], []
+    for s in range(S):
+        seq = consistent_modes(spec, rng, P, p_short=0.3 if s % 2 else 0.0)
+        infos, pkts = [], []
+        for mode, prev, nxt in seq:
+            pk, info = spec.audio_packet(mode, prev, nxt, p_unused=0.1)
+            if s >= S - 2:                               # the last two streams carry truncated packets
+                nb = int(rng.integers((info["header_bits"] + 7) // 8 + 1, len(pk) + 1))
+                pk = pk[:max(nb, 1)]
+            pkts.append(pk)
+            infos.append(info)
+        streams.append((pkts, infos))
+        wants.append(np.concatenate(oracle_pcm(oracle, spec, infos)[0], axis=1) if s < S - 2 else None)
+    f32 = fmt == cabi.OUT_F32_PLANAR
+    dt = np.float32 if f32 else np.int16
+    planar = fmt in (cabi.OUT_F32_PLANAR, cabi.OUT_I16_PLANAR)
+    outs = {}
+    for entry in (cabi.ENTRY_VQ, cabi.ENTRY_RESIDUE):
+        pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+        coeffs, kinds, ys, recs, offs, chains = [], [], [], [], [0], []
+        coeff_off = out_off = 0
+        for s, (pkts, infos) in enumerate(streams):
+            modes, prevs, nexts, n_out, size = [], [], [], 0, 0
+            for pk in pkts:
+                dense = hdr.decode_packet(pk)
+                dp, rr = hdr.decode_packet_vq(pk)
+                k, y, d = dense.pack()
+                assert d is None
+                kinds.append(k)
+                ys.append(y)
+                coeffs.append(dense.residue.ravel())
+                recs.append(rr)
+                offs.append(offs[-1] + len(rr))
+                modes.append(dp.mode_number); prevs.append(dp.prev_window_flag); nexts.append(dp.next_window_flag)
+                size += dense.residue.size
+            stride = P * (1 << spec.bs1) // 2
+            chains.append(L.ChainSpec(pwrs[s], np.array(modes, np.uint8), np.array(prevs, np.uint8), np.array(nexts, np.uint8),
+                                      coeff_offset=coeff_off, packet_index=s * P, out_offset=out_off, out_stride=stride if planar else 0))
+            coeff_off += size
+            out_off += stride * channels
+        coeffs, kinds, ys = np.concatenate(coeffs), np.concatenate(kinds), np.concatenate(ys)
+        recs = np.concatenate(recs) if sum(len(r) for r in recs) else np.zeros(1, fe.VQ_DTYPE)
+        offs = np.array(offs, np.uint64)
+        pcm = np.zeros(out_off, dt)
+        kw = dict(floor_kind=kinds, floor1_y=ys)
+        frees = []
+        if floor_mem == cabi.MEM_DEVICE:
+            for name, arr in (("floor_kind", kinds), ("floor1_y", ys), ("vq_records", recs), ("vq_offsets", offs)):
+                if entry == cabi.ENTRY_RESIDUE and name.startswith("vq"):
+                    continue
+                d = ctx.device_alloc(max(arr.nbytes, 16))
+                ctx.h2d(d, arr)
+                kw[name] = d
+                frees.append(d)
+            kw["floor_memory"] = cabi.MEM_DEVICE
+        elif entry == cabi.ENTRY_VQ:
+            kw.update(vq_records=recs, vq_offsets=offs)
+        if memory == cabi.MEM_HOST:
+            L.decode_chains(ctx, chains, entry, memory, None if entry == cabi.ENTRY_VQ else coeffs, pcm, fmt, **kw)
+        else:
+            d_out = ctx.device_alloc(pcm.nbytes)
+            ctx.h2d(d_out, pcm)
+            d_in = None
+            if entry == cabi.ENTRY_RESIDUE:
+                d_in = ctx.device_alloc(coeffs.nbytes)
+                ctx.h2d(d_in, coeffs)
+            L.decode_chains(ctx, chains, entry, memory, d_in, d_out, fmt, **kw)
+            ctx.synchronize()
+            ctx.d2h(pcm, d_out)
+            ctx.device_free(d_out)
+            if d_in:
+                ctx.device_free(d_in)
+        for d in frees:
+            ctx.device_free(d)
+        outs[entry] = (pcm, [(c.status, c.n_samples) for c in chains], [p.data() for p in pwrs])
+        for p in pwrs:
+            p.close()
+    pcm, res, states = outs[cabi.ENTRY_VQ]
+    stride = P * (1 << spec.bs1) // 2
+    for s in range(S - 2):
+        n = wants[s].shape[1]
+        assert res[s] == (0, n), (s, res[s], n)
+        blk = pcm[s * stride * channels:(s + 1) * stride * channels]
+        got = blk.reshape(channels, stride)[:, :n] if planar else blk[: n * channels].reshape(n, channels).T
+        if f32:
+            assert bits_equal(got, wants[s]), (s, mismatch_report(got, wants[s]))
+        else:
+            assert np.array_equal(got, oracle.quantise_i16(wants[s])), s
+    assert res == outs[cabi.ENTRY_RESIDUE][1]
+    if memory == cabi.MEM_DEVICE:
+        assert np.array_equal(pcm.view(np.uint8), outs[cabi.ENTRY_RESIDUE][0].view(np.uint8)), "VQ entry and dense residue entry differ"
+    else:                      # host batches copy whole strides back: compare what was produced
+        for s in range(S):
+            n = res[s][1]
+            a = pcm[s * stride * channels:(s + 1) * stride * channels]
+            b = outs[cabi.ENTRY_RESIDUE][0][s * stride * channels:(s + 1) * stride * channels]
+            if planar:
+                assert np.array_equal(a.reshape(channels, stride)[:, :n].view(np.uint8), b.reshape(channels, stride)[:, :n].view(np.uint8)), s
+            else:
+                assert np.array_equal(a[: n * channels].view(np.uint8), b[: n * channels].view(np.uint8)), s
+    for a, b in zip(states, outs[cabi.ENTRY_RESIDUE][2]):
+        assert (a is None) == (b is None) and (a is None or bits_equal(a, b))
+
+
+def test_stream_batcher_vq_entry(ctx, oracle):
+    """lwf_batcher with LWB_ENTRY_VQ: the host threads entropy-decode to VQ records, one batched call accumulates and
+    synthesises; bit-identical to the oracle and to the dense batcher."""
+    rng = np.random.default_rng(521)
+    channels, P, S = 2, 10, 16
+    spec = vp.StreamSpec(rng, channels=channels)
+    hdr = fe.Headers(spec.ident_packet(), spec.comment_packet(), spec.setup_packet())
+    su = hdr.make_setup(ctx)
+    distinct = []
+    for d in range(4):
+        seq = consistent_modes(spec, rng, P, p_short=0.2)
+        pkts, infos = [], []
+        for mode, prev, nxt in seq:
+            pk, info = spec.audio_packet(mode, prev, nxt)
+            pkts.append(pk)
+            infos.append(info)
+        distinct.append((pkts, np.concatenate(oracle_pcm(oracle, spec, infos)[0], axis=1)))
+    stride = P * (1 << spec.bs1) // 2
+    results = {}
+    for entry in (cabi.ENTRY_VQ, cabi.ENTRY_RESIDUE):
+        pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+        jobs = [(pwrs[s], list(distinct[s % 4][0])) for s in range(S)]
+        pcm = np.zeros(S * channels * stride, np.float32)
+        bt = fe.StreamBatcher(ctx, hdr, threads=3, entry=entry)
+        res = bt.decode(jobs, pcm, stride)
+        bt.close()
+        results[entry] = pcm
+        for s in range(S):
+            w = distinct[s % 4][1]
+            assert res[s] == (w.shape[1], P, 0), (entry, s, res[s])
+            got = pcm[s * channels * stride:(s + 1) * channels * stride].reshape(channels, stride)[:, : w.shape[1]]
+            assert bits_equal(got, w), (entry, s, mismatch_report(got, w))
+        for p in pwrs:
+            p.close()
