@@ -215,24 +215,28 @@ enum { LWB_ENTRY_SPECTRUM = 0,   /* coeffs = floor x residue, enters at audio.rs
                                   * accumulated on the device from the packets' VQ entry indices       *
                                   * (audio.rs:587-717); coeff_offset still lays out the (device-only)   *
                                   * coefficient arena.  Needs the setup's codebooks / residues, <= 8     *
-                                  * channels, channels * n/2 <= 12288, and every VQ book's dimension      *
-                                  * dividing its residue's partition size.                                */
-/* One VQ vector of a packet's residue, in the order the entropy decoder produces them:
- * "add codebook `book`'s entry `entry` at `pos`".  The f32 += order of the reference is kept on the device: per
- * coefficient the contributions are added pass by pass (audio.rs:595, :611); within a pass no two vectors of a
- * packet touch the same coefficient. */
-typedef struct lwb_vq_record {
-    uint32_t entry_pass_kind;        /* bits 0..23 codebook entry, 24..26 pass (0..7), 27..28 kind:           *
-                                      *   0 contiguous in a channel vector (residue type 1), pos = channel * n/2 + bin
-                                      *   1 strided (type 0, audio.rs:589-597): value j lands at pos + j * step,  *
-                                      *     step = partition_size(aux) / dimensions                               *
-                                      *   2 interleaved (type 2, audio.rs:744-756): pos indexes the interleaved   *
-                                      *     vector of submap `aux`: element t is channel t % ch, bin t / ch       */
-    uint16_t pos;
-    uint8_t book;                    /* codebook index                                                  */
-    uint8_t aux;                     /* kind 1: residue index; kind 2: submap index                     */
-} lwb_vq_record;
-#define LWB_VQ_RECORD(entry, pass, kind) ((uint32_t)(entry) | ((uint32_t)(pass) << 24) | ((uint32_t)(kind) << 27))
+                                  * channels, channels * n/2 <= 12288, VQ books of <= 65536 entries whose   *
+                                  * dimension divides their residue's partition size.                     */
+/* The VQ vectors of a packet's residue, in the order the entropy decoder produces them, as RUNS:
+ * one run = the consecutive vectors one residue_packet_read_partition call reads (audio.rs:587-618) -- same codebook,
+ * same pass, positions in arithmetic progression -- plus one 16-bit codebook entry per vector in a side array.  The
+ * f32 += order of the reference is kept on the device: per coefficient the contributions are added pass by pass
+ * (audio.rs:595, :611); within a pass no two vectors of a packet touch the same coefficient. */
+typedef struct lwb_vq_run {
+    uint16_t pos;                    /* where vector 0 of the run lands (see kind)                          */
+    uint16_t first;                  /* index of its entry in the packet's slice of vq_entries              */
+    uint8_t book;                    /* codebook index                                                      */
+    uint8_t pass_kind;               /* bits 0..2 pass (0..7), bits 3..4 kind:                                *
+                                      *   0 contiguous in a channel vector (residue type 1): pos = channel * n/2 + bin,
+                                      *     vector i at pos + i * dimensions
+                                      *   1 strided (type 0, audio.rs:589-597): vector i at pos + i, its value j at
+                                      *     + j * step, step = partition_size(aux) / dimensions
+                                      *   2 interleaved (type 2, audio.rs:744-756): pos indexes the interleaved vector of
+                                      *     submap `aux` (element t = channel t % ch, bin t / ch), vector i at pos + i * dimensions */
+    uint8_t aux;                     /* kind 1: residue index; kind 2: submap index                          */
+    uint8_t count;                   /* vectors in the run (a longer partition is split)                     */
+} lwb_vq_run;
+#define LWB_VQ_PASS_KIND(pass, kind) ((uint8_t)((pass) | ((kind) << 3)))
 enum { LWB_MEM_HOST = 0, LWB_MEM_DEVICE = 1 };
 
 /* One stream's run of consecutive packets.  Input arenas are chain-major: the chain's packets
@@ -262,10 +266,12 @@ typedef struct lwb_batch_io {
     const uint32_t *floor1_y;         /* [total_packets][channels][LWB_MAX_POSTS], see floor_memory */
     int out_format;                   /* LWB_OUT_*                                                 */
     void *pcm;                        /* output arena                                              */
-    /* LWB_ENTRY_VQ: packet row r (= chain.packet_index + k) owns vq_records[vq_offsets[r] .. vq_offsets[r + 1]);    *
-     * both arrays live where the floor arrays live (floor_memory).                                                 */
-    const lwb_vq_record *vq_records;
-    const uint64_t *vq_offsets;       /* [total_packets + 1]                                        */
+    /* LWB_ENTRY_VQ: the runs / entries of packet row r (= chain.packet_index + k); all four arrays live where the    *
+     * floor arrays live (floor_memory).                                                                            */
+    const lwb_vq_run *vq_runs;
+    const uint64_t *vq_run_offsets;   /* [total_packets + 1]: packet row r owns vq_runs[off[r] .. off[r + 1])          */
+    const uint16_t *vq_entries;
+    const uint64_t *vq_entry_offsets; /* [total_packets + 1]: ... and vq_entries[eoff[r] .. eoff[r + 1])            */
     int floor_memory;                 /* LWB_MEM_*: where floor_kind / floor1_y live (0 = host).   *
                                        * Device arrays are read in place (nothing is uploaded, and   *
                                        * nothing about them can be validated on the host: a kind    *

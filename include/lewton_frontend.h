@@ -84,14 +84,15 @@ typedef struct lwf_decoded_packet {
  * LWF_ERR_END_OF_PACKET (header bits missing) or LWB_ERR_BAD_FORMAT (audio.rs:926-930, :975). */
 int lwf_packet_decode(const lwf_headers *h, const uint8_t *packet, size_t len, lwf_decoded_packet *out);
 int lwf_decoded_sample_count(const lwf_headers *h, const uint8_t *packet, size_t len, size_t *n_samples);
-/* The same front half with the residue left as VQ records (audio.rs:587-717): what
- * residue_packet_decode would have ADDED, vector by vector in decode order, for LWB_ENTRY_VQ batches (out->residue is
- * not touched and may be NULL).  LWB_ERR_BUFFER if `capacity` records do not suffice (a packet of L bytes never needs
- * more than 8 L).  lwf_headers_vq_capable: 1 if the stream qualifies (<= 8 channels, every VQ book's dimension
- * divides its residue's partition size), else the dense path must be used. */
+/* The same front half with the residue left as VQ runs + entries (audio.rs:587-717): what
+ * residue_packet_decode would have ADDED, partition by partition in decode order, for LWB_ENTRY_VQ batches (out->residue
+ * is not touched and may be NULL).  LWB_ERR_BUFFER if the capacities do not suffice (a packet of L bytes never needs
+ * more than 8 L of either).  lwf_headers_vq_capable: 1 if the stream qualifies (<= 8 channels, channels * n/2 <= 12288,
+ * VQ books of <= 65536 entries whose dimension divides their residue's partition size), else the dense path is used. */
 int lwf_headers_vq_capable(const lwf_headers *h);
 int lwf_packet_decode_vq(const lwf_headers *h, const uint8_t *packet, size_t len, lwf_decoded_packet *out,
-                         lwb_vq_record *records, size_t capacity, size_t *n_records);
+                         lwb_vq_run *runs, size_t run_capacity, size_t *n_runs, uint16_t *entries, size_t entry_capacity,
+                         size_t *n_entries);
 
 /* ---- Ogg paging -------------------------------------------------------------------------------- */
 typedef struct lwf_ogg lwf_ogg;             /* PacketReader over a memory buffer (not copied)      */

@@ -48,8 +48,9 @@ class ResidueDesc(C.Structure):
     _fields_ = [("residue_type", C.c_uint8), ("reserved", C.c_uint8 * 3), ("partition_size", C.c_uint32)]
 
 
-class VqRecord(C.Structure):
-    _fields_ = [("entry_pass_kind", C.c_uint32), ("pos", C.c_uint16), ("book", C.c_uint8), ("aux", C.c_uint8)]
+class VqRun(C.Structure):
+    _fields_ = [("pos", C.c_uint16), ("first", C.c_uint16), ("book", C.c_uint8), ("pass_kind", C.c_uint8), ("aux", C.c_uint8),
+                ("count", C.c_uint8)]
 
 
 class SetupDesc(C.Structure):
@@ -79,7 +80,7 @@ class Chain(C.Structure):
 class BatchIo(C.Structure):
     _fields_ = [("entry", C.c_int), ("memory", C.c_int), ("coeffs", vp), ("dense_floor", vp),
                 ("floor_kind", vp), ("floor1_y", vp), ("out_format", C.c_int), ("pcm", vp),
-                ("vq_records", vp), ("vq_offsets", vp), ("floor_memory", C.c_int)]
+                ("vq_runs", vp), ("vq_run_offsets", vp), ("vq_entries", vp), ("vq_entry_offsets", vp), ("floor_memory", C.c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/lewton_b200.h declares

@@ -407,9 +407,10 @@ class Batch:
     would otherwise exceed the kernel time)."""
 
     def __init__(self, ctx, chains, entry, memory, coeffs, pcm, out_format, floor_kind=None, floor1_y=None,
-                 dense_floor=None, floor_memory=cabi.MEM_HOST, vq_records=None, vq_offsets=None):
+                 dense_floor=None, floor_memory=cabi.MEM_HOST, vq=None):
+        """vq: LWB_ENTRY_VQ arrays (runs, run_offsets, entries, entry_offsets): numpy arrays or device pointers."""
         self.ctx, self.chains = ctx, list(chains)
-        self._keep = (coeffs, pcm, floor_kind, floor1_y, dense_floor, vq_records, vq_offsets)
+        self._keep = (coeffs, pcm, floor_kind, floor1_y, dense_floor, vq)
         self._arr = arr = (cabi.Chain * len(self.chains))()
         for i, c in enumerate(self.chains):
             arr[i].stream = c.pwr._h
@@ -434,7 +435,8 @@ class Batch:
         io.coeffs, io.pcm, io.dense_floor = addr(coeffs), addr(pcm), addr(dense_floor)
         io.floor_kind, io.floor1_y = addr(floor_kind), addr(floor1_y)
         io.floor_memory = floor_memory
-        io.vq_records, io.vq_offsets = addr(vq_records), addr(vq_offsets)
+        if vq is not None:
+            io.vq_runs, io.vq_run_offsets, io.vq_entries, io.vq_entry_offsets = (addr(x) for x in vq)
         self._n = len(self.chains)
         self._plan = C.c_void_p()
         ctx.check(cabi.lib().lwb_plan_create(ctx._h, self._arr, self._n, C.byref(self._io), C.byref(self._plan)))
@@ -466,11 +468,11 @@ class Batch:
 
 
 def decode_chains(ctx, chains, entry, memory, coeffs, pcm, out_format, floor_kind=None, floor1_y=None,
-                  dense_floor=None, floor_memory=cabi.MEM_HOST, vq_records=None, vq_offsets=None):
+                  dense_floor=None, floor_memory=cabi.MEM_HOST, vq=None):
     """lwb_decode_chains.  coeffs/pcm/dense_floor: numpy arrays (MEM_HOST) or integer device
     pointers (MEM_DEVICE); floor_kind/floor1_y: numpy arrays (floor_memory MEM_HOST) or integer
     device pointers (MEM_DEVICE)."""
-    b = Batch(ctx, chains, entry, memory, coeffs, pcm, out_format, floor_kind, floor1_y, dense_floor, floor_memory, vq_records, vq_offsets)
+    b = Batch(ctx, chains, entry, memory, coeffs, pcm, out_format, floor_kind, floor1_y, dense_floor, floor_memory, vq)
     try:
         b.run()
         return b.collect()

@@ -933,23 +933,37 @@ static int floor1_decode(BitReader &rdr, const std::vector<Codebook> &codebooks,
     return FL_OK;
 }
 
-// LWB_ENTRY_VQ: instead of adding the VQ vectors into dense residue vectors on the host, the decode emits one
-// record per vector ("codebook b, entry e, at position p") and the device does the additions in the same order.
+// LWB_ENTRY_VQ: instead of adding the VQ vectors into dense residue vectors on the host, the decode emits, per
+// residue_packet_read_partition call, one RUN ("codebook b, pass p, starting at position x") and one 16-bit entry per
+// vector; the device does the additions in the same order.
 struct VqSink {
-    lwb_vq_record *rec = nullptr;
-    size_t cap = 0, n = 0;
+    lwb_vq_run *runs = nullptr;
+    uint16_t *entries = nullptr;
+    size_t run_cap = 0, ent_cap = 0, n_runs = 0, n_ent = 0;
     bool overflow = false;
     // context of the residue decode in progress
     size_t base = 0;                  // position of vec_v[0]: channel * n/2 + offset (types 0 / 1) or the interleaved index (type 2)
     uint8_t pass = 0, kind = 0, aux = 0, book = 0;
-    void put(uint32_t entry, size_t pos)
+    int cur = -1;                     // run being filled
+    void begin() { cur = -1; }
+    // vector number `i` of the partition (its position = base + i * (kind == 1 ? 1 : dims)) holds `entry`
+    void put(uint32_t entry, size_t i, size_t dims)
     {
-        if (n >= cap || pos > 0xffffu || entry > 0xffffffu) { overflow = true; return; }
-        lwb_vq_record &q = rec[n++];
-        q.entry_pass_kind = LWB_VQ_RECORD(entry, pass, kind);
-        q.pos = (uint16_t)pos;
-        q.book = book;
-        q.aux = aux;
+        const size_t pos = base + i * (kind == 1 ? 1 : dims);
+        if (entry > 0xffffu || pos > 0xffffu || n_ent >= ent_cap || n_ent > 0xffffu) { overflow = true; return; }
+        if (cur < 0 || runs[cur].count == 255) {
+            if (n_runs >= run_cap) { overflow = true; return; }
+            cur = (int)n_runs++;
+            lwb_vq_run &r = runs[cur];
+            r.pos = (uint16_t)pos;
+            r.first = (uint16_t)n_ent;
+            r.book = book;
+            r.pass_kind = LWB_VQ_PASS_KIND(pass, kind);
+            r.aux = aux;
+            r.count = 0;
+        }
+        runs[cur].count++;
+        entries[n_ent++] = (uint16_t)entry;
     }
 };
 
@@ -957,6 +971,7 @@ struct VqSink {
 static int residue_partition_vq(BitReader &rdr, const Codebook &cb, const Residue &r, size_t vlen, VqSink &sink)
 {
     uint32_t idx;
+    sink.begin();
     if (r.type == 0) {
         const size_t dims = cb.dimensions;
         if (dims == 0) return 0;
@@ -964,7 +979,7 @@ static int residue_partition_vq(BitReader &rdr, const Codebook &cb, const Residu
         for (size_t i = 0; i < step; i++) {
             if (!cb.tree.read(rdr, &idx)) return 1;
             if (i + (dims - 1) * step >= vlen) return 0;    // (slice index out of range: a panic in the reference)
-            sink.put(idx, sink.base + i);
+            sink.put(idx, i, dims);
         }
     } else {
         const size_t psize = r.partition_size;
@@ -972,9 +987,9 @@ static int residue_partition_vq(BitReader &rdr, const Codebook &cb, const Residu
         while (i < psize) {
             if (!cb.tree.read(rdr, &idx)) return 1;
             if (i + cb.dimensions > vlen) break;
-            sink.put(idx, sink.base + i);
-            i += cb.dimensions;
             if (cb.dimensions == 0) break;
+            sink.put(idx, i / cb.dimensions, cb.dimensions);
+            i += cb.dimensions;
         }
     }
     return 0;
@@ -1510,6 +1525,7 @@ extern "C" int lwf_headers_vq_capable(const lwf_headers *h)
     if (!h) return 0;
     const lwf::Headers &s = h->h;
     if (s.ident.audio_channels > 8 || s.codebooks.size() > 256 || s.residues.size() > 64) return 0;
+    if ((size_t)s.ident.audio_channels << (s.ident.blocksize_1 - 1) > 12288) return 0;       // the device accumulators
     for (const lwf::Residue &r : s.residues)
         for (const lwf::ResidueBook &rb : r.books)
             for (int p = 0; p < 8; p++)
@@ -1517,25 +1533,32 @@ extern "C" int lwf_headers_vq_capable(const lwf_headers *h)
                     if (rb.val[p] >= s.codebooks.size()) return 0;
                     const lwf::Codebook &cb = s.codebooks[rb.val[p]];
                     if (!cb.has_vq || cb.dimensions == 0 || r.partition_size % cb.dimensions) return 0;
+                    if (cb.vq.size() / cb.dimensions > 65536) return 0;                        // entries travel as u16
                 }
     return 1;
 }
 
 extern "C" int lwf_packet_decode_vq(const lwf_headers *h, const uint8_t *packet, size_t len, lwf_decoded_packet *out,
-                                    lwb_vq_record *records, size_t capacity, size_t *n_records)
+                                    lwb_vq_run *runs, size_t run_capacity, size_t *n_runs, uint16_t *entries, size_t entry_capacity,
+                                    size_t *n_entries)
 {
-    if (!h || (!packet && len) || !out || !out->floor_kind || !out->floor1_y || (!records && capacity) || !n_records) return LWB_ERR_INVALID;
+    if (!h || (!packet && len) || !out || !out->floor_kind || !out->floor1_y || (!runs && run_capacity) || (!entries && entry_capacity) ||
+        !n_runs || !n_entries)
+        return LWB_ERR_INVALID;
     for (const auto &fl : h->h.floors)
         if (fl.type == 0 && !out->dense_floor) return LWB_ERR_INVALID;
-    *n_records = 0;
+    *n_runs = *n_entries = 0;
     LWF_GUARD(
         lwf::VqSink sink;
-        sink.rec = records;
-        sink.cap = capacity;
+        sink.runs = runs;
+        sink.run_cap = run_capacity;
+        sink.entries = entries;
+        sink.ent_cap = entry_capacity;
         const int rc = lwf::packet_decode(h->h, packet, len, out, &sink);
         if (rc) return rc;
         if (sink.overflow) return LWB_ERR_BUFFER;
-        *n_records = sink.n;
+        *n_runs = sink.n_runs;
+        *n_entries = sink.n_ent;
         return LWB_OK;
     )
 }
@@ -1839,7 +1862,7 @@ struct PinnedBuf {
 };
 
 struct BatchArena {
-    PinnedBuf coeffs, dense, kinds, ys, vqrec, vqoff;
+    PinnedBuf coeffs, dense, kinds, ys, vqrun, vqent, vqroff, vqeoff;
     std::vector<uint8_t> modes, prevs, nexts;
     std::vector<lwb_chain> chains;
 };
@@ -1918,12 +1941,13 @@ int batch_entropy(lwf_batcher *b, BatchArena &ar, lwf_stream_job *jobs, size_t j
     const size_t rows = (size_t)pkt_total * C;
     const bool vq = b->entry == LWB_ENTRY_VQ;
     if ((!vq && !ar.coeffs.ensure((size_t)coeff_total * 4 + 16)) || !ar.kinds.ensure(rows + 16) || !ar.ys.ensure(rows * LWB_MAX_POSTS * 4 + 16) ||
-        (b->has_floor0 && !ar.dense.ensure((size_t)coeff_total * 4 + 16)) || (vq && !ar.vqoff.ensure(((size_t)pkt_total + 1) * 8 + 16)))
+        (b->has_floor0 && !ar.dense.ensure((size_t)coeff_total * 4 + 16)) || (vq && (!ar.vqroff.ensure(((size_t)pkt_total + 1) * 8 + 16) || !ar.vqeoff.ensure(((size_t)pkt_total + 1) * 8 + 16))))
         return LWB_ERR_BUFFER;
     // VQ: every stream's records are collected per job first (their number is only known after the decode), then
     // packed into one pinned arena with per-packet offsets
-    std::vector<std::vector<lwb_vq_record>> job_recs(vq ? j1 - j0 : 0);
-    uint64_t *vq_off = vq ? (uint64_t *)ar.vqoff.p : nullptr;
+    std::vector<std::vector<lwb_vq_run>> job_runs(vq ? j1 - j0 : 0);
+    std::vector<std::vector<uint16_t>> job_ents(vq ? j1 - j0 : 0);
+    uint64_t *run_off = vq ? (uint64_t *)ar.vqroff.p : nullptr, *ent_off = vq ? (uint64_t *)ar.vqeoff.p : nullptr;
     ar.modes.resize(pkt_total);
     ar.prevs.resize(pkt_total);
     ar.nexts.resize(pkt_total);
@@ -1950,16 +1974,22 @@ int batch_entropy(lwf_batcher *b, BatchArena &ar, lwf_stream_job *jobs, size_t j
                     dp.dense_floor = dense ? dense + coff : nullptr;
                     int rc;
                     if (vq) {
-                        std::vector<lwb_vq_record> &jr = job_recs[j - j0];
-                        const size_t cur = jr.size(), cap = (size_t)job.lengths[k] * 8 + 16;
-                        jr.resize(cur + cap);
+                        std::vector<lwb_vq_run> &jr = job_runs[j - j0];
+                        std::vector<uint16_t> &je = job_ents[j - j0];
+                        const size_t r0 = jr.size(), e0 = je.size(), cap = (size_t)job.lengths[k] * 8 + 16;
+                        jr.resize(r0 + cap);
+                        je.resize(e0 + cap);
                         lwf::VqSink sink;
-                        sink.rec = jr.data() + cur;
-                        sink.cap = cap;
+                        sink.runs = jr.data() + r0;
+                        sink.run_cap = cap;
+                        sink.entries = je.data() + e0;
+                        sink.ent_cap = cap;
                         rc = lwf::packet_decode(H, job.packets[k], job.lengths[k], &dp, &sink);
                         if (!rc && sink.overflow) rc = LWB_ERR_BUFFER;
-                        jr.resize(cur + (rc ? 0 : sink.n));
-                        vq_off[pi + 1] = rc ? 0 : sink.n;          // count for now; turned into offsets below
+                        jr.resize(r0 + (rc ? 0 : sink.n_runs));
+                        je.resize(e0 + (rc ? 0 : sink.n_ent));
+                        run_off[pi + 1] = rc ? 0 : sink.n_runs;      // counts for now; turned into offsets below
+                        ent_off[pi + 1] = rc ? 0 : sink.n_ent;
                     } else {
                         rc = lwf::packet_decode(H, job.packets[k], job.lengths[k], &dp);
                     }
@@ -1982,20 +2012,22 @@ int batch_entropy(lwf_batcher *b, BatchArena &ar, lwf_stream_job *jobs, size_t j
     for (auto &t : pool) t.join();
     if (failed.load()) return LWB_ERR_BUFFER;
     if (vq) {
-        // counts -> offsets (rows of packets that were not decoded own no records), then one packed copy
-        vq_off[0] = 0;
+        // counts -> offsets (rows of packets that were not decoded own nothing), then one packed copy of each array
+        run_off[0] = ent_off[0] = 0;
         for (size_t j = j0; j < j1; j++)
             for (uint32_t k = 0; k < plan[j].usable; k++) {
                 const uint64_t pi = plan[j].pkt0 + k;
-                const uint64_t cnt = k < decoded[j] ? vq_off[pi + 1] : 0;
-                vq_off[pi + 1] = vq_off[pi] + cnt;
+                const bool ok = k < decoded[j];
+                run_off[pi + 1] = run_off[pi] + (ok ? run_off[pi + 1] : 0);
+                ent_off[pi + 1] = ent_off[pi] + (ok ? ent_off[pi + 1] : 0);
             }
-        const uint64_t total = vq_off[pkt_total];
-        if (!ar.vqrec.ensure((size_t)total * sizeof(lwb_vq_record) + 16)) return LWB_ERR_BUFFER;
-        lwb_vq_record *dst = (lwb_vq_record *)ar.vqrec.p;
+        if (!ar.vqrun.ensure((size_t)run_off[pkt_total] * sizeof(lwb_vq_run) + 16) || !ar.vqent.ensure((size_t)ent_off[pkt_total] * 2 + 16))
+            return LWB_ERR_BUFFER;
         for (size_t j = j0; j < j1; j++) {
-            const std::vector<lwb_vq_record> &jr = job_recs[j - j0];
-            if (!jr.empty()) std::memcpy(dst + vq_off[plan[j].pkt0], jr.data(), jr.size() * sizeof(lwb_vq_record));
+            const std::vector<lwb_vq_run> &jr = job_runs[j - j0];
+            const std::vector<uint16_t> &je = job_ents[j - j0];
+            if (!jr.empty()) std::memcpy((lwb_vq_run *)ar.vqrun.p + run_off[plan[j].pkt0], jr.data(), jr.size() * sizeof(lwb_vq_run));
+            if (!je.empty()) std::memcpy((uint16_t *)ar.vqent.p + ent_off[plan[j].pkt0], je.data(), je.size() * sizeof(uint16_t));
         }
     }
     // chains of this slice
@@ -2023,8 +2055,10 @@ int batch_synth(lwf_batcher *b, BatchArena &ar, int out_format, void *pcm)
     io.entry = b->entry;
     io.memory = LWB_MEM_HOST;
     io.coeffs = (const float *)ar.coeffs.p;
-    io.vq_records = (const lwb_vq_record *)ar.vqrec.p;
-    io.vq_offsets = (const uint64_t *)ar.vqoff.p;
+    io.vq_runs = (const lwb_vq_run *)ar.vqrun.p;
+    io.vq_run_offsets = (const uint64_t *)ar.vqroff.p;
+    io.vq_entries = (const uint16_t *)ar.vqent.p;
+    io.vq_entry_offsets = (const uint64_t *)ar.vqeoff.p;
     io.dense_floor = b->has_floor0 ? (const float *)ar.dense.p : nullptr;
     io.floor_kind = (const uint8_t *)ar.kinds.p;
     io.floor1_y = (const uint32_t *)ar.ys.p;

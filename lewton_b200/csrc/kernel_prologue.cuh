@@ -119,51 +119,56 @@ inline size_t prologue_fused_smem(int channels, int words, size_t vq_elems = 0)
     return (size_t)channels * pf_row_bytes(words) + (channels > 1 ? (size_t)channels * kPfThreads * sizeof(float4) : 0) +
            vq_elems * sizeof(float);
 }
+// device view of a batch's VQ arrays (biased so that absolute packet rows / absolute offsets address them)
+struct VqDev { const lwb_vq_run *runs; const uint64_t *run_off; const uint16_t *entries; const uint64_t *ent_off; };
 constexpr size_t kVqMaxElems = 12288;          // 48 KB of accumulators: stereo up to n = 8192, 5.1 up to n = 4096
 
-// LWB_ENTRY_VQ: the packet's residue vectors, accumulated in shared memory from its VQ records in the reference's
+// LWB_ENTRY_VQ: the packet's residue vectors, accumulated in shared memory from its VQ runs in the reference's
 // order (residue_packet_decode_inner, audio.rs:620-717; residue_packet_read_partition, :587-618): per coefficient
-// the f32 additions happen pass by pass; within a pass the vectors of a packet are disjoint, so they run in parallel.
-// acc: [C][n2], zeroed here.  Called by the whole CTA (contains barriers).
+// the f32 additions happen pass by pass; within a pass the vectors of a packet are disjoint, so the runs of a pass
+// go in parallel (one thread per run, its vectors in sequence).  acc: [C][n2], zeroed here.  Called by the whole CTA.
 __device__ __forceinline__ void d_vq_accumulate(float *acc, int C, int n2, const DevSetup &su, const DevMapping &mp,
-                                                const lwb_vq_record *__restrict__ rec, uint32_t nrec, int tid)
+                                                const lwb_vq_run *__restrict__ runs, uint32_t nruns,
+                                                const uint16_t *__restrict__ entries, uint32_t nent, int tid)
 {
     const int total = C * n2;
     for (int i = tid; i < total; i += kPfThreads) acc[i] = 0.f;
     __syncthreads();
     for (uint32_t pass = 0; pass < 8; pass++) {
-        bool any = false;
-        for (uint32_t i = tid; i < nrec; i += kPfThreads) {
-            const lwb_vq_record r = rec[i];
-            if (((r.entry_pass_kind >> 24) & 7u) != pass) continue;
-            any = true;
-            if (r.book >= su.n_books) continue;
+        for (uint32_t i = tid; i < nruns; i += kPfThreads) {
+            const lwb_vq_run r = runs[i];
+            if ((r.pass_kind & 7u) != pass || r.book >= su.n_books) continue;
             const DevBook bk = su.books[r.book];
-            const uint32_t e = r.entry_pass_kind & 0xffffffu, kind = (r.entry_pass_kind >> 27) & 3u;
-            if (!bk.vq || e >= bk.entries) continue;
-            const float *__restrict__ v = bk.vq + (size_t)e * bk.dims;
-            if (kind == 0) {                                   // residue type 1: contiguous (audio.rs:599-615)
-                if ((int)r.pos + (int)bk.dims > total) continue;
-                for (int k = 0; k < bk.dims; k++) acc[r.pos + k] = __fadd_rn(acc[r.pos + k], v[k]);
-            } else if (kind == 1) {                            // residue type 0: stride partition_size / dimensions (:589-597)
-                const int step = r.aux < su.n_residues ? (int)(su.res_psize[r.aux] / bk.dims) : 0;
-                if (step <= 0 || (int)r.pos + (bk.dims - 1) * step >= total) continue;
-                for (int k = 0; k < bk.dims; k++) acc[r.pos + k * step] = __fadd_rn(acc[r.pos + k * step], v[k]);
-            } else {                                           // residue type 2: one interleaved vector per submap (:744-756)
-                const int nch = r.aux < LWB_MAX_SUBMAPS ? mp.sub_nch[r.aux] : 0;
-                if (nch <= 0) continue;
-                for (int k = 0; k < bk.dims; k++) {
-                    const int t = r.pos + k, bin = t / nch;
-                    if (bin >= n2) break;
-                    const int a = mp.sub_ch[r.aux][t - bin * nch] * n2 + bin;
-                    acc[a] = __fadd_rn(acc[a], v[k]);
+            const int kind = (r.pass_kind >> 3) & 3, dims = bk.dims;
+            if (!bk.vq || !dims || (uint32_t)r.first + r.count > nent) continue;
+            const int step = kind == 1 ? (r.aux < su.n_residues ? (int)(su.res_psize[r.aux] / dims) : 0) : 1;
+            const int nch = kind == 2 ? (r.aux < LWB_MAX_SUBMAPS ? mp.sub_nch[r.aux] : 0) : 1;
+            if (step <= 0 || nch <= 0) continue;
+            for (int q = 0; q < r.count; q++) {
+                const uint32_t e = entries[r.first + q];
+                if (e >= bk.entries) continue;
+                const float *__restrict__ v = bk.vq + (size_t)e * dims;
+                if (kind == 0) {                               // residue type 1: contiguous (audio.rs:599-615)
+                    const int p0 = r.pos + q * dims;
+                    if (p0 + dims > total) break;
+                    for (int k = 0; k < dims; k++) acc[p0 + k] = __fadd_rn(acc[p0 + k], v[k]);
+                } else if (kind == 1) {                        // residue type 0: stride partition_size / dimensions (:589-597)
+                    const int p0 = r.pos + q;
+                    if (p0 + (dims - 1) * step >= total) break;
+                    for (int k = 0; k < dims; k++) acc[p0 + k * step] = __fadd_rn(acc[p0 + k * step], v[k]);
+                } else {                                       // residue type 2: one interleaved vector per submap (:744-756)
+                    for (int k = 0; k < dims; k++) {
+                        const int t = r.pos + q * dims + k, bin = t / nch;
+                        if (bin >= n2) break;
+                        const int a = mp.sub_ch[r.aux][t - bin * nch] * n2 + bin;
+                        acc[a] = __fadd_rn(acc[a], v[k]);
+                    }
                 }
             }
         }
-        __syncthreads_or(any);             // (a barrier; its value is not needed: an empty pass costs one sweep of the records)
+        __syncthreads();
     }
 }
-
 
 // Floor values of the 4 bins [k0, k0 + 4) of one channel row, tables in shared memory.
 template <bool SHIFT>
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(kPfThreads, 4)
 k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float *__restrict__ residue, const float *__restrict__ dense_floor,
                  const uint8_t *__restrict__ floor_kind, const uint4 *__restrict__ segtab, const uint8_t *__restrict__ seg_cnt,
                  const unsigned char *__restrict__ seg_index, int words, float *__restrict__ spec,
-                 const lwb_vq_record *__restrict__ vq_rec, const uint64_t *__restrict__ vq_off)
+                 VqDev vq)
 {
     extern __shared__ __align__(16) unsigned char pf_smem[];
     __shared__ float s_db[256];
@@ -239,8 +244,9 @@ k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float 
             reinterpret_cast<uint4 *>(pf_smem)[i] = v;
         }
         if (VQ) {
-            const uint64_t o0 = vq_off[p.pkt_index], o1 = vq_off[p.pkt_index + 1];
-            d_vq_accumulate(s_acc, C, n2, su, mp, vq_rec + o0, (uint32_t)(o1 - o0), tid);
+            const uint64_t o0 = vq.run_off[p.pkt_index], o1 = vq.run_off[p.pkt_index + 1];
+            const uint64_t e0 = vq.ent_off[p.pkt_index], e1 = vq.ent_off[p.pkt_index + 1];
+            d_vq_accumulate(s_acc, C, n2, su, mp, vq.runs + o0, (uint32_t)(o1 - o0), vq.entries + e0, (uint32_t)(e1 - e0), tid);
         }
         __syncthreads();
         if (stereo) {

@@ -515,8 +515,8 @@ static int decode_chains_impl(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, 
     if (io->out_format < 0 || io->out_format > LWB_OUT_I16_INTERLEAVED) return fail(ctx, LWB_ERR_INVALID, "bad out_format");
     if (n_chains == 0) return LWB_OK;
     if ((!io->coeffs && io->entry != LWB_ENTRY_VQ) || !io->pcm) return fail(ctx, LWB_ERR_INVALID, "null arena");
-    if (io->entry == LWB_ENTRY_VQ && (!io->vq_records || !io->vq_offsets || !io->floor_kind))
-        return fail(ctx, LWB_ERR_INVALID, "VQ entry needs vq_records, vq_offsets and floor_kind");
+    if (io->entry == LWB_ENTRY_VQ && (!io->vq_runs || !io->vq_run_offsets || !io->vq_entries || !io->vq_entry_offsets || !io->floor_kind))
+        return fail(ctx, LWB_ERR_INVALID, "VQ entry needs vq_runs, vq_entries, their offsets and floor_kind");
     CU(ctx, cudaSetDevice(ctx->device));
     const uint64_t epoch = ++ctx->epoch;      // per context: concurrent calls on different contexts share nothing
     {

@@ -100,8 +100,8 @@ static bool prologue_is_fast(const DevPacket *h_pk, size_t n_pk, unsigned C, con
     return fast;
 }
 
-// VQ views of a batch (LWB_ENTRY_VQ), device pointers biased like the floor arrays; rec == nullptr otherwise
-struct VqView { const lwb_vq_record *rec = nullptr; const uint64_t *off = nullptr; };
+// VQ views of a batch (LWB_ENTRY_VQ), device pointers biased like the floor arrays; runs == nullptr otherwise
+struct VqView { const lwb_vq_run *runs = nullptr; const uint64_t *run_off = nullptr; const uint16_t *entries = nullptr; const uint64_t *ent_off = nullptr; };
 
 // n2max: the largest n/2 among the packets (sizes the per-row bin -> segment index).
 static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, size_t n_pk, unsigned C, bool fast, size_t smem_old, int n2max,
@@ -109,7 +109,7 @@ static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, size_t n_pk, uns
 {
     if (!n_pk) return LWB_OK;
     const int words = std::max(1, (n2max + 31) >> 5);
-    if (vq.rec && (!fast || (size_t)C * n2max > kVqMaxElems))
+    if (vq.runs && (!fast || (size_t)C * n2max > kVqMaxElems))
         return fail(ctx, LWB_ERR_INVALID, "VQ entry needs <= 8 channels, aligned arenas and channels * n/2 <= 12288");
     if (!fast)
         return launch(ctx, k_prologue, dim3((unsigned)n_pk), dim3(kPrologueThreads), smem_old, d_pk, res, dense, kinds, ys, spec);
@@ -125,12 +125,12 @@ static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, size_t n_pk, uns
                 (uint32_t)rows, (int)C, kinds, ys, tab, cnt, ix, words);
     if (rc) return rc;
     const size_t grid = std::min<size_t>(n_pk, (size_t)ctx->sm_count * (C > 2 ? 4 : 8));
-    if (vq.rec)
+    const VqDev vd{vq.runs, vq.run_off, vq.entries, vq.ent_off};
+    if (vq.runs)
         return launch(ctx, k_prologue_fused<true>, dim3((unsigned)grid), dim3(kPfThreads), prologue_fused_smem((int)C, words, (size_t)C * n2max), d_pk,
-                      (uint32_t)n_pk, res, dense, kinds, (const uint4 *)tab, (const uint8_t *)cnt, (const unsigned char *)ix, words, spec, vq.rec, vq.off);
+                      (uint32_t)n_pk, res, dense, kinds, (const uint4 *)tab, (const uint8_t *)cnt, (const unsigned char *)ix, words, spec, vd);
     return launch(ctx, k_prologue_fused<false>, dim3((unsigned)grid), dim3(kPfThreads), prologue_fused_smem((int)C, words), d_pk, (uint32_t)n_pk, res, dense,
-                  kinds, (const uint4 *)tab, (const uint8_t *)cnt, (const unsigned char *)ix, words, spec, (const lwb_vq_record *)nullptr,
-                  (const uint64_t *)nullptr);
+                  kinds, (const uint4 *)tab, (const uint8_t *)cnt, (const unsigned char *)ix, words, spec, vd);
 }
 static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, const DevPacket *h_pk, size_t n_pk, unsigned C, size_t smem_old,
                            const float *res, const float *dense, const uint8_t *kinds, const uint32_t *ys, float *spec, VqView vq = VqView())
@@ -185,27 +185,36 @@ static int stage_floor_arrays(lwb_ctx *ctx, const lwb_batch_io *io, uint64_t r_l
     return LWB_OK;
 }
 
-// LWB_ENTRY_VQ: device view of the VQ records of packet rows [r_lo, r_hi), biased so that absolute rows / absolute
-// record offsets address it (host arrays are uploaded to ctx->vqoff / ctx->vqrec on `sm`).
+// LWB_ENTRY_VQ: device view of the VQ runs / entries of packet rows [r_lo, r_hi), biased so that absolute rows and
+// absolute offsets address it (host arrays are uploaded to ctx scratch on `sm`: four copies, all small).
 static int stage_vq_arrays(lwb_ctx *ctx, const lwb_batch_io *io, uint64_t r_lo, uint64_t r_hi, cudaStream_t sm, VqView *out)
 {
     *out = VqView();
     if (io->entry != LWB_ENTRY_VQ) return LWB_OK;
     if (io->floor_memory == LWB_MEM_DEVICE) {
-        out->rec = io->vq_records;
-        out->off = io->vq_offsets;
+        out->runs = io->vq_runs;
+        out->run_off = io->vq_run_offsets;
+        out->entries = io->vq_entries;
+        out->ent_off = io->vq_entry_offsets;
         return LWB_OK;
     }
     if (r_hi <= r_lo) return LWB_OK;
     int rc;
-    const uint64_t o_lo = io->vq_offsets[r_lo], o_hi = io->vq_offsets[r_hi];
-    if (o_hi < o_lo) return fail(ctx, LWB_ERR_INVALID, "vq_offsets must be non-decreasing");
-    const size_t nrow = (size_t)(r_hi - r_lo) + 1, nrec = (size_t)(o_hi - o_lo);
-    if ((rc = ensure(ctx, ctx->vqoff, nrow * sizeof(uint64_t))) || (rc = ensure(ctx, ctx->vqrec, std::max<size_t>(nrec, 1) * sizeof(lwb_vq_record)))) return rc;
-    CU(ctx, cudaMemcpyAsync(ctx->vqoff.p, io->vq_offsets + r_lo, nrow * sizeof(uint64_t), cudaMemcpyHostToDevice, sm));
-    if (nrec) CU(ctx, cudaMemcpyAsync(ctx->vqrec.p, io->vq_records + o_lo, nrec * sizeof(lwb_vq_record), cudaMemcpyHostToDevice, sm));
-    out->off = (const uint64_t *)ctx->vqoff.p - r_lo;
-    out->rec = (const lwb_vq_record *)ctx->vqrec.p - o_lo;
+    const uint64_t o_lo = io->vq_run_offsets[r_lo], o_hi = io->vq_run_offsets[r_hi];
+    const uint64_t e_lo = io->vq_entry_offsets[r_lo], e_hi = io->vq_entry_offsets[r_hi];
+    if (o_hi < o_lo || e_hi < e_lo) return fail(ctx, LWB_ERR_INVALID, "vq offsets must be non-decreasing");
+    const size_t nrow = (size_t)(r_hi - r_lo) + 1, nrun = (size_t)(o_hi - o_lo), nent = (size_t)(e_hi - e_lo);
+    const size_t b_off = nrow * sizeof(uint64_t), b_run = std::max<size_t>(nrun, 1) * sizeof(lwb_vq_run);
+    if ((rc = ensure(ctx, ctx->vqoff, 2 * b_off)) || (rc = ensure(ctx, ctx->vqrec, b_run + std::max<size_t>(nent, 1) * sizeof(uint16_t) + 16))) return rc;
+    char *d_off = (char *)ctx->vqoff.p, *d_rec = (char *)ctx->vqrec.p;
+    CU(ctx, cudaMemcpyAsync(d_off, io->vq_run_offsets + r_lo, b_off, cudaMemcpyHostToDevice, sm));
+    CU(ctx, cudaMemcpyAsync(d_off + b_off, io->vq_entry_offsets + r_lo, b_off, cudaMemcpyHostToDevice, sm));
+    if (nrun) CU(ctx, cudaMemcpyAsync(d_rec, io->vq_runs + o_lo, nrun * sizeof(lwb_vq_run), cudaMemcpyHostToDevice, sm));
+    if (nent) CU(ctx, cudaMemcpyAsync(d_rec + b_run, io->vq_entries + e_lo, nent * sizeof(uint16_t), cudaMemcpyHostToDevice, sm));
+    out->run_off = (const uint64_t *)d_off - r_lo;
+    out->ent_off = (const uint64_t *)(d_off + b_off) - r_lo;
+    out->runs = (const lwb_vq_run *)d_rec - o_lo;
+    out->entries = (const uint16_t *)(d_rec + b_run) - e_lo;
     return LWB_OK;
 }
 

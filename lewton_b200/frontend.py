@@ -26,7 +26,8 @@ SYMBOLS = ["lwf_headers_parse", "lwf_headers_destroy", "lwf_headers_info", "lwf_
            "lwf_debug_float32_unpack", "lwf_debug_lookup1_values", "lwf_debug_ilog", "lwf_debug_read_bits", "lwf_debug_huffman"]
 
 
-VQ_DTYPE = np.dtype([("entry_pass_kind", np.uint32), ("pos", np.uint16), ("book", np.uint8), ("aux", np.uint8)])   # lwb_vq_record
+VQ_RUN_DTYPE = np.dtype([("pos", np.uint16), ("first", np.uint16), ("book", np.uint8), ("pass_kind", np.uint8), ("aux", np.uint8),
+                         ("count", np.uint8)])                                              # lwb_vq_run
 
 
 class HeaderReadError(Exception):
@@ -105,7 +106,7 @@ def lib():
         L.lwf_batcher_destroy.restype = None
         L.lwf_batcher_set_entry.argtypes = [vp, C.c_int]
         L.lwf_headers_vq_capable.argtypes = [vp]
-        L.lwf_packet_decode_vq.argtypes = [vp, C.c_char_p, sz, vp, vp, sz, C.POINTER(sz)]
+        L.lwf_packet_decode_vq.argtypes = [vp, C.c_char_p, sz, vp, vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz)]
         L.lwf_batcher_decode.argtypes = [vp, C.POINTER(_StreamJob), sz, C.c_int, vp]
         L.lwf_batcher_last_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.lwf_batcher_last_timing.restype = None
@@ -204,8 +205,8 @@ class Headers:
         return bool(lib().lwf_headers_vq_capable(self._h))
 
     def decode_packet_vq(self, packet):
-        """The same front half with the residue left as VQ records: (DecodedPacket with residue None, records) where
-        records is a structured array of cabi.VqRecord (entry_pass_kind, pos, book, aux)."""
+        """The same front half with the residue left as VQ runs: (DecodedPacket with a zero residue, runs, entries):
+        runs a structured array (lwb_vq_run), entries the uint16 codebook entries they index."""
         Cn, n2max = self.audio_channels, (1 << self.blocksize_1) // 2
         kinds = np.zeros(Cn, np.uint8)
         ys = np.zeros((Cn, cabi.MAX_POSTS), np.uint32)
@@ -215,9 +216,10 @@ class Headers:
         dp.floor1_y = ys.ctypes.data_as(cabi.u32p)
         dp.dense_floor = dense.ctypes.data_as(cabi.fp)
         cap = len(packet) * 8 + 16
-        recs = np.zeros(cap, VQ_DTYPE)
-        n = C.c_size_t()
-        rc = lib().lwf_packet_decode_vq(self._h, bytes(packet), len(packet), C.byref(dp), recs.ctypes.data, cap, C.byref(n))
+        runs, ents = np.zeros(cap, VQ_RUN_DTYPE), np.zeros(cap, np.uint16)
+        n, ne = C.c_size_t(), C.c_size_t()
+        rc = lib().lwf_packet_decode_vq(self._h, bytes(packet), len(packet), C.byref(dp), runs.ctypes.data, cap, C.byref(n),
+                                        ents.ctypes.data, cap, C.byref(ne))
         if rc == cabi.ERR_BAD_FORMAT:
             raise AudioReadError(rc)
         if rc:
@@ -236,7 +238,7 @@ class Headers:
                 floors.append(flat_dense[c * n2:(c + 1) * n2].copy())
         out = DecodedPacket(dp.mode_number, np.zeros((Cn, n2), np.float32), floors, dp.prev_window_flag, dp.next_window_flag)
         out.blockflag, out.n = bool(dp.blockflag), dp.n
-        return out, recs[: n.value].copy()
+        return out, runs[: n.value].copy(), ents[: ne.value].copy()
 
     def decoded_sample_count(self, packet):
         n = C.c_size_t()

@@ -38,13 +38,13 @@ def test_struct_layouts_match_header(lib, tmp_path):
     src.write_text('#include <stdio.h>\n#include "lewton_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(lwb_tables_ref),sizeof(lwb_floor_desc),sizeof(lwb_mapping_desc),sizeof(lwb_mode_desc),"
                    "sizeof(lwb_setup_desc),sizeof(lwb_packet),sizeof(lwb_chain),sizeof(lwb_batch_io));"
-                   'printf("%zu %zu %zu\\n", sizeof(lwb_codebook_desc), sizeof(lwb_residue_desc), sizeof(lwb_vq_record));return 0;}\n')
+                   'printf("%zu %zu %zu\\n", sizeof(lwb_codebook_desc), sizeof(lwb_residue_desc), sizeof(lwb_vq_run));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(t) for t in (_cabi.TablesRef, _cabi.FloorDesc, _cabi.MappingDesc, _cabi.ModeDesc,
                                   _cabi.SetupDesc, _cabi.Packet, _cabi.Chain, _cabi.BatchIo, _cabi.CodebookDesc, _cabi.ResidueDesc,
-                                  _cabi.VqRecord)]
+                                  _cabi.VqRun)]
     assert got == want
 
 

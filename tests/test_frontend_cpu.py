@@ -399,41 +399,43 @@ def test_packet_decode_other_blocksizes(seed, bs0, bs1, channels, floor0):
             check_packet(spec, hdr, pkt, info, int(rng.integers(2, len(pkt))))
 
 
-def vq_accumulate(spec, hdr, dp, recs):
-    """What the device does with a packet's VQ records (kernel_prologue.cuh d_vq_accumulate): per coefficient the f32
+def vq_accumulate(spec, hdr, dp, runs, ents):
+    """What the device does with a packet's VQ runs (kernel_prologue.cuh d_vq_accumulate): per coefficient the f32
     additions happen pass by pass; kinds 0 / 1 / 2 = residue types 1 / 0 / 2 (audio.rs:587-618, :744-756)."""
     C, n2 = spec.channels, dp.n // 2
     acc = np.zeros(C * n2, np.float32)
     mp = spec.mappings[spec.modes[dp.mode_number][1]]
     for p in range(8):
         touched = np.zeros(C * n2, bool)
-        for r in recs:
-            epk = int(r["entry_pass_kind"])
-            if (epk >> 24) & 7 != p:
+        for r in runs:
+            pk = int(r["pass_kind"])
+            if pk & 7 != p:
                 continue
             book = spec.books[int(r["book"])]
-            v = np.asarray(book.vq[epk & 0xffffff], np.float32)
-            kind, pos = (epk >> 27) & 3, int(r["pos"])
-            if kind == 0:
-                idx = pos + np.arange(book.dims)
-            elif kind == 1:
-                step = spec.residues[int(r["aux"])].partition_size // book.dims
-                idx = pos + np.arange(book.dims) * step
-            else:
-                chs = [c for c in range(C) if mp["mux"][c] == int(r["aux"])]
-                t = pos + np.arange(book.dims)
-                keep = (t // len(chs)) < n2
-                t, v = t[keep], v[keep]
-                idx = np.array([chs[i % len(chs)] for i in t], np.int64) * n2 + t // len(chs)
-            assert not touched[idx].any(), "two vectors of one pass overlap"
-            touched[idx] = True
-            acc[idx] = (acc[idx] + v).astype(np.float32)
+            kind, pos, first = (pk >> 3) & 3, int(r["pos"]), int(r["first"])
+            for q in range(int(r["count"])):
+                v = np.asarray(book.vq[int(ents[first + q])], np.float32)
+                if kind == 0:
+                    idx = pos + q * book.dims + np.arange(book.dims)
+                elif kind == 1:
+                    step = spec.residues[int(r["aux"])].partition_size // book.dims
+                    idx = pos + q + np.arange(book.dims) * step
+                else:
+                    chs = [c for c in range(C) if mp["mux"][c] == int(r["aux"])]
+                    t = pos + q * book.dims + np.arange(book.dims)
+                    keep = (t // len(chs)) < n2
+                    t, v = t[keep], v[keep]
+                    idx = np.array([chs[i % len(chs)] for i in t], np.int64) * n2 + t // len(chs)
+                assert not touched[idx].any(), "two vectors of one pass overlap"
+                touched[idx] = True
+                acc[idx] = (acc[idx] + v).astype(np.float32)
     return acc.reshape(C, n2)
 
 
 @pytest.mark.parametrize("seed,channels,rtype", [(60, 2, 0), (61, 2, 1), (62, 2, 2), (63, 6, None), (64, 1, None), (65, 3, 2)])
 def test_vq_records_reproduce_the_dense_residue(seed, channels, rtype):
-    """LWB_ENTRY_VQ's host side: lwf_packet_decode_vq emits one record per VQ vector; adding them up the way the
+    """LWB_ENTRY_VQ's host side: lwf_packet_decode_vq emits one run per partition read and one 16-bit entry per VQ
+    vector; adding them up the way the
     device does (pass by pass) gives, bit for bit, the residue vectors lwf_packet_decode accumulates on the host --
     for whole packets and for packets cut at arbitrary bytes (the reference keeps what was decoded, audio.rs:640-716).
     Floors and mode bits are the same as the dense decode's."""
@@ -446,10 +448,11 @@ def test_vq_records_reproduce_the_dense_residue(seed, channels, rtype):
         cuts = [len(pkt)] + [c for c in rng.integers(1, max(2, len(pkt)), 5).tolist() if c * 8 >= info["header_bits"]]
         for nb in cuts:
             dense = hdr.decode_packet(pkt[:nb])
-            dp, recs = hdr.decode_packet_vq(pkt[:nb])
+            dp, runs, ents = hdr.decode_packet_vq(pkt[:nb])
+            assert int(runs["count"].sum()) == len(ents)
             assert (dp.mode_number, dp.prev_window_flag, dp.next_window_flag, dp.n) == (dense.mode_number, dense.prev_window_flag,
                                                                                       dense.next_window_flag, dense.n)
             for a, b in zip(dp.floors, dense.floors):
                 assert (a is None) == (b is None) and (a is None or np.array_equal(np.asarray(a), np.asarray(b)))
-            got = vq_accumulate(spec, hdr, dp, recs)
+            got = vq_accumulate(spec, hdr, dp, runs, ents)
             assert np.array_equal(got.view(np.uint32), dense.residue.view(np.uint32)), (k, nb, np.abs(got - dense.residue).max())

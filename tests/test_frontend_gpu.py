@@ -466,8 +466,8 @@ def test_vq_entry_accumulates_the_residue_on_the_device(ctx, oracle, channels, r
         for mode, prev, nxt in seq:
             pk, info = spec.audio_packet(mode, prev, nxt, p_unused=0.1)
             if s >= S - 2:                               # the last two streams carry truncated packets
-                nb = int(rng.integers((info["header_bits"] + 7) // 8 + 1, len(pk) + 1))
-                pk = pk[:max(nb, 1)]
+                lo = min((info["header_bits"] + 7) // 8 + 1, len(pk))
+                pk = pk[:int(rng.integers(lo, len(pk) + 1))]
             pkts.append(pk)
             infos.append(info)
         streams.append((pkts, infos))
@@ -478,20 +478,22 @@ def test_vq_entry_accumulates_the_residue_on_the_device(ctx, oracle, channels, r
     outs = {}
     for entry in (cabi.ENTRY_VQ, cabi.ENTRY_RESIDUE):
         pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
-        coeffs, kinds, ys, recs, offs, chains = [], [], [], [], [0], []
+        coeffs, kinds, ys, runs, ents, roffs, eoffs, chains = [], [], [], [], [], [0], [0], []
         coeff_off = out_off = 0
         for s, (pkts, infos) in enumerate(streams):
             modes, prevs, nexts, n_out, size = [], [], [], 0, 0
             for pk in pkts:
                 dense = hdr.decode_packet(pk)
-                dp, rr = hdr.decode_packet_vq(pk)
+                dp, rr, ee = hdr.decode_packet_vq(pk)
                 k, y, d = dense.pack()
                 assert d is None
                 kinds.append(k)
                 ys.append(y)
                 coeffs.append(dense.residue.ravel())
-                recs.append(rr)
-                offs.append(offs[-1] + len(rr))
+                runs.append(rr)
+                ents.append(ee)
+                roffs.append(roffs[-1] + len(rr))
+                eoffs.append(eoffs[-1] + len(ee))
                 modes.append(dp.mode_number); prevs.append(dp.prev_window_flag); nexts.append(dp.next_window_flag)
                 size += dense.residue.size
             stride = P * (1 << spec.bs1) // 2
@@ -500,22 +502,23 @@ def test_vq_entry_accumulates_the_residue_on_the_device(ctx, oracle, channels, r
             coeff_off += size
             out_off += stride * channels
         coeffs, kinds, ys = np.concatenate(coeffs), np.concatenate(kinds), np.concatenate(ys)
-        recs = np.concatenate(recs) if sum(len(r) for r in recs) else np.zeros(1, fe.VQ_DTYPE)
-        offs = np.array(offs, np.uint64)
+        runs = np.concatenate(runs) if roffs[-1] else np.zeros(1, fe.VQ_RUN_DTYPE)
+        ents = np.concatenate(ents) if eoffs[-1] else np.zeros(1, np.uint16)
+        roffs, eoffs = np.array(roffs, np.uint64), np.array(eoffs, np.uint64)
         pcm = np.zeros(out_off, dt)
         kw = dict(floor_kind=kinds, floor1_y=ys)
         frees = []
         if floor_mem == cabi.MEM_DEVICE:
-            for name, arr in (("floor_kind", kinds), ("floor1_y", ys), ("vq_records", recs), ("vq_offsets", offs)):
-                if entry == cabi.ENTRY_RESIDUE and name.startswith("vq"):
-                    continue
+            def dev(arr):
                 d = ctx.device_alloc(max(arr.nbytes, 16))
                 ctx.h2d(d, arr)
-                kw[name] = d
                 frees.append(d)
-            kw["floor_memory"] = cabi.MEM_DEVICE
+                return d
+            kw = dict(floor_kind=dev(kinds), floor1_y=dev(ys), floor_memory=cabi.MEM_DEVICE)
+            if entry == cabi.ENTRY_VQ:
+                kw["vq"] = (dev(runs), dev(roffs), dev(ents), dev(eoffs))
         elif entry == cabi.ENTRY_VQ:
-            kw.update(vq_records=recs, vq_offsets=offs)
+            kw["vq"] = (runs, roffs, ents, eoffs)
         if memory == cabi.MEM_HOST:
             L.decode_chains(ctx, chains, entry, memory, None if entry == cabi.ENTRY_VQ else coeffs, pcm, fmt, **kw)
         else:
