@@ -100,9 +100,17 @@ static bool batch_is_uniform_long(lwb_ctx *ctx, const lwb_chain *chains, size_t 
 // `spectrum_dev`: when non-null the spectrum has already been formed on the device (residue entry:
 // k_prologue wrote it to ctx->spec, element offset `spectrum_base` = its [0]); the input side of the
 // batch is then neither validated as a spectrum entry nor copied.
+// Host-memory pipeline of the residue entries (try_long_residue): the caller has cut the batch into slices of chains
+// and runs try_long once per slice; the PCM staging covers the whole batch, nothing is synchronised per slice.
+struct LongSlice {
+    bool active = false;
+    uint64_t o_lo = 0, o_hi = 0;       // PCM element range of the whole batch (staging base)
+    int ev_slot = 0;                   // which ev_done[] entry orders this slice's D2H
+};
+
 static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch,
                     bool *handled, const float *spectrum_dev = nullptr, uint64_t spectrum_base = 0,
-                    lwb_plan *plan = nullptr, bool capture_with_spectrum_dev = false)
+                    lwb_plan *plan = nullptr, bool capture_with_spectrum_dev = false, LongSlice slice = LongSlice())
 {
     *handled = false;
     const uint64_t gen_at_entry = ctx->state_gen;
@@ -179,6 +187,7 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
         const size_t bytes = (size_t)(c_hi - c_lo) * 4;
         n_chunks = std::min<size_t>(std::max<size_t>(1, bytes >> 25), std::min<size_t>(8, items.size()));   // profiles/e2e_chunks_r1.log
         if (const char *e = getenv("LWB_E2E_CHUNKS")) n_chunks = std::max<size_t>(1, std::min<size_t>((size_t)atol(e), std::min<size_t>(64, items.size())));
+        if (slice.active) n_chunks = 1;                    // the caller's slices are the chunks
     }
     const float *d_coeffs = spectrum_dev ? spectrum_dev : io->coeffs;
     char *d_pcm = (char *)io->pcm;
@@ -189,7 +198,8 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
             d_coeffs = (const float *)ctx->coeffs.p;
             cbase = c_lo;
         }
-        if (o_hi > o_lo && (rc = ensure(ctx, ctx->pcm, (size_t)(o_hi - o_lo) * esz))) return rc;
+        if (slice.active) { o_lo = slice.o_lo; o_hi = slice.o_hi; }      // (already ensured by the caller)
+        else if (o_hi > o_lo && (rc = ensure(ctx, ctx->pcm, (size_t)(o_hi - o_lo) * esz))) return rc;
         d_pcm = (char *)ctx->pcm.p;
         obase = o_lo;
         if (!ctx->ev_in[0])
@@ -199,8 +209,10 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
             }
         // the copy streams must not run ahead of work already queued on the compute stream that
         // still reads/writes the arenas (previous call): order them behind it
-        CU(ctx, cudaEventRecord(ctx->ev_done[64], ctx->stream));
-        CU(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[64], 0));
+        if (!slice.active) {
+            CU(ctx, cudaEventRecord(ctx->ev_done[64], ctx->stream));
+            CU(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[64], 0));
+        }
     }
     // count runs
     std::vector<size_t> cuts(items.size(), 1);
@@ -289,10 +301,13 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
     // this half of the double buffer
     const size_t all_runs = (size_t)(w - h_runs);
     if (!all_runs) return LWB_OK;
-    CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_kdone[par], 0));
-    CU(ctx, cudaMemcpyAsync(d_runs_base, h_runs, all_runs * sizeof(LongRun), cudaMemcpyHostToDevice, ctx->copy_out));
-    CU(ctx, cudaEventRecord(ctx->ev_desc[par], ctx->copy_out));
-    CU(ctx, cudaEventRecord(st->ev, ctx->copy_out));
+    // (slices of a pipelined host batch: on the H2D stream -- behind copy_out's PCM copies the next slice's kernels would wait
+    // for the previous slice's D2H)
+    cudaStream_t ds = slice.active ? ctx->copy_in : ctx->copy_out;
+    CU(ctx, cudaStreamWaitEvent(ds, ctx->ev_kdone[par], 0));
+    CU(ctx, cudaMemcpyAsync(d_runs_base, h_runs, all_runs * sizeof(LongRun), cudaMemcpyHostToDevice, ds));
+    CU(ctx, cudaEventRecord(ctx->ev_desc[par], ds));
+    CU(ctx, cudaEventRecord(st->ev, ds));
     st->pending = true;
     CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_desc[par], 0));
     for (size_t k = 0; k < cplan.size(); k++) {
@@ -310,8 +325,9 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
             return fail(ctx, LWB_ERR_CUDA, "long kernel launch", cudaGetLastError());
         ctx->launches++;
         if (host && cp.ko_hi > cp.ko_lo) {
-            CU(ctx, cudaEventRecord(ctx->ev_done[k], ctx->stream));
-            CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[k], 0));
+            const size_t evk = slice.active ? (size_t)slice.ev_slot : k;
+            CU(ctx, cudaEventRecord(ctx->ev_done[evk], ctx->stream));
+            CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[evk], 0));
             CU(ctx, cudaMemcpyAsync((char *)io->pcm + cp.ko_lo * esz, (char *)ctx->pcm.p + (cp.ko_lo - obase) * esz,
                                     (size_t)(cp.ko_hi - cp.ko_lo) * esz, cudaMemcpyDeviceToHost, ctx->copy_out));
         }
@@ -324,7 +340,7 @@ static int try_long(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_
         plan->pack = pack;
         plan->i16 = i16;
     }
-    if (host) {
+    if (host && !slice.active) {
         CU(ctx, cudaStreamSynchronize(ctx->copy_out));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -429,26 +445,20 @@ static int try_long_residue(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, co
     }
     cudaStream_t sm = ctx->stream;
     const size_t elems = (size_t)(c_hi - c_lo);
+    const bool host = io->memory == LWB_MEM_HOST;
     const float *d_res = vq ? nullptr : io->coeffs, *d_dense = need_dense ? io->dense_floor : nullptr;
-    if (io->memory == LWB_MEM_HOST) {
+    if (host) {
         if (!vq) {
             if ((rc = ensure(ctx, ctx->coeffs, elems * 4))) return rc;
-            CU(ctx, cudaMemcpyAsync(ctx->coeffs.p, io->coeffs + c_lo, elems * 4, cudaMemcpyHostToDevice, sm));
             d_res = (const float *)ctx->coeffs.p - c_lo;
         }
         if (need_dense) {
             if ((rc = ensure(ctx, ctx->dense, elems * 4))) return rc;
-            CU(ctx, cudaMemcpyAsync(ctx->dense.p, io->dense_floor + c_lo, elems * 4, cudaMemcpyHostToDevice, sm));
             d_dense = (const float *)ctx->dense.p - c_lo;
         }
     }
     if ((rc = ensure(ctx, ctx->spec, elems * 4))) return rc;
     float *d_spec = (float *)ctx->spec.p - c_lo;
-    const uint8_t *d_kinds;
-    const uint32_t *d_ys;
-    if ((rc = stage_floor_arrays(ctx, io, r_lo, r_hi, C, sm, &d_kinds, &d_ys))) return rc;
-    VqView vqv;
-    if ((rc = stage_vq_arrays(ctx, io, r_lo, r_hi, sm, &vqv))) return rc;
     // front-stage descriptors: absolute element offsets and packet rows (the arena pointers are biased instead)
     const DevPacket *d_pk;
     bool fast;
@@ -492,10 +502,121 @@ static int try_long_residue(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, co
             plan->pro_c_lo = c_lo; plan->pro_c_hi = c_hi; plan->pro_r_lo = r_lo; plan->pro_r_hi = r_hi;
         }
     }
-    if ((rc = launch_prologue(ctx, d_pk, n_pk, C, fast, smem_old, kLongN2, d_res, d_dense, d_kinds, d_ys, d_spec, vqv))) return rc;
-    bool h2 = false;
-    rc = try_long(ctx, chains, n_chains, io, epoch, &h2, (const float *)ctx->spec.p, c_lo, plan, true);
-    if (rc) return rc;
-    if (!h2) return fail(ctx, LWB_ERR_INVALID, "internal: uniform long residue batch refused by the fused path");
+    if (!host) {
+        const uint8_t *d_kinds;
+        const uint32_t *d_ys;
+        if ((rc = stage_floor_arrays(ctx, io, r_lo, r_hi, C, sm, &d_kinds, &d_ys))) return rc;
+        VqView vqv;
+        if ((rc = stage_vq_arrays(ctx, io, r_lo, r_hi, sm, &vqv))) return rc;
+        if ((rc = launch_prologue(ctx, d_pk, n_pk, C, fast, smem_old, kLongN2, d_res, d_dense, d_kinds, d_ys, d_spec, vqv))) return rc;
+        bool h2 = false;
+        rc = try_long(ctx, chains, n_chains, io, epoch, &h2, (const float *)ctx->spec.p, c_lo, plan, true);
+        if (rc) return rc;
+        if (!h2) return fail(ctx, LWB_ERR_INVALID, "internal: uniform long residue batch refused by the fused path");
+        return LWB_OK;
+    }
+    // Host memory: slices of chains flow through three streams -- copy_in brings a slice's inputs (dense residues, or
+    // VQ runs / entries, and its floor rows), the compute stream runs its front stages and the fused kernel, copy_out
+    // takes its PCM home -- so that H2D, kernels and D2H of consecutive slices overlap (the link is duplex).
+    size_t n_sl = std::min<size_t>(std::max<size_t>(1, (n_pk * (size_t)C * kLongN2 * 4) >> 25), std::min<size_t>(8, n_chains));
+    if (const char *e = getenv("LWB_E2E_CHUNKS")) n_sl = std::max<size_t>(1, std::min<size_t>((size_t)atol(e), std::min<size_t>(32, n_chains)));
+    // whole-batch staging (absolute rows / offsets address it); each slice copies its own part
+    const size_t esz = io->out_format == LWB_OUT_I16_PLANAR ? 2 : 4;
+    uint64_t o_lo = ~0ull, o_hi = 0;
+    for (size_t i = 0; i < n_chains; i++) {
+        const lwb_chain *c = &chains[i];
+        if (!c->n_packets) continue;
+        const uint64_t ns = (uint64_t)(c->n_packets - (c->stream->has ? 0 : 1)) * kLongN2;
+        o_lo = std::min(o_lo, c->out_offset);
+        o_hi = std::max(o_hi, c->out_offset + (uint64_t)(C - 1) * c->out_stride + ns);
+    }
+    if (o_hi > o_lo && (rc = ensure(ctx, ctx->pcm, (size_t)(o_hi - o_lo) * esz))) return rc;
+    const bool host_floors = io->floor_memory != LWB_MEM_DEVICE;
+    const size_t rows_all = (size_t)(r_hi - r_lo) * C;
+    VqView vqv;
+    const uint8_t *d_kinds = io->floor_kind;
+    const uint32_t *d_ys = io->floor1_y;
+    uint64_t vo_lo = 0, ve_lo = 0;
+    if (host_floors) {
+        if ((rc = ensure(ctx, ctx->kinds, rows_all)) || (io->floor1_y && (rc = ensure(ctx, ctx->ys, rows_all * LWB_MAX_POSTS * sizeof(uint32_t))))) return rc;
+        d_kinds = (const uint8_t *)ctx->kinds.p - r_lo * C;
+        d_ys = io->floor1_y ? (const uint32_t *)ctx->ys.p - r_lo * C * LWB_MAX_POSTS : nullptr;
+        if (vq) {
+            vo_lo = io->vq_run_offsets[r_lo];
+            ve_lo = io->vq_entry_offsets[r_lo];
+            const uint64_t vo_hi = io->vq_run_offsets[r_hi], ve_hi = io->vq_entry_offsets[r_hi];
+            if (vo_hi < vo_lo || ve_hi < ve_lo) return fail(ctx, LWB_ERR_INVALID, "vq offsets must be non-decreasing");
+            const size_t b_off = ((size_t)(r_hi - r_lo) + 1) * sizeof(uint64_t), b_run = std::max<size_t>((size_t)(vo_hi - vo_lo), 1) * sizeof(lwb_vq_run);
+            if ((rc = ensure(ctx, ctx->vqoff, 2 * b_off)) ||
+                (rc = ensure(ctx, ctx->vqrec, b_run + std::max<size_t>((size_t)(ve_hi - ve_lo), 1) * sizeof(uint16_t) + 16)))
+                return rc;
+            vqv.run_off = (const uint64_t *)ctx->vqoff.p - r_lo;
+            vqv.ent_off = (const uint64_t *)((char *)ctx->vqoff.p + b_off) - r_lo;
+            vqv.runs = (const lwb_vq_run *)ctx->vqrec.p - vo_lo;
+            vqv.entries = (const uint16_t *)((char *)ctx->vqrec.p + b_run) - ve_lo;
+        }
+    } else if ((rc = stage_vq_arrays(ctx, io, r_lo, r_hi, sm, &vqv))) {
+        return rc;
+    }
+    if (!ctx->ev_in[0])
+        for (int k = 0; k < 65; k++) {
+            if (k < 64) CU(ctx, cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming));
+            CU(ctx, cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming));
+        }
+    // the copy streams must not run ahead of work already queued on the compute stream (previous call, descriptor upload)
+    CU(ctx, cudaEventRecord(ctx->ev_done[64], sm));
+    CU(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[64], 0));
+    CU(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[64], 0));
+    size_t pk0 = 0;
+    for (size_t sl = 0; sl < n_sl; sl++) {
+        const size_t i0 = n_chains * sl / n_sl, i1 = n_chains * (sl + 1) / n_sl;
+        uint64_t sc_lo = ~0ull, sc_hi = 0, sr_lo = ~0ull, sr_hi = 0;
+        size_t npk_sl = 0;
+        for (size_t i = i0; i < i1; i++) {
+            const lwb_chain *c = &chains[i];
+            if (!c->n_packets) continue;
+            npk_sl += c->n_packets;
+            sc_lo = std::min(sc_lo, c->coeff_offset);
+            sc_hi = std::max(sc_hi, c->coeff_offset + (uint64_t)c->n_packets * C * kLongN2);
+            sr_lo = std::min(sr_lo, c->packet_index);
+            sr_hi = std::max<uint64_t>(sr_hi, c->packet_index + c->n_packets);
+        }
+        if (!npk_sl) continue;
+        cudaStream_t ci = ctx->copy_in;
+        if (!vq)
+            CU(ctx, cudaMemcpyAsync((float *)ctx->coeffs.p + (sc_lo - c_lo), io->coeffs + sc_lo, (size_t)(sc_hi - sc_lo) * 4, cudaMemcpyHostToDevice, ci));
+        if (need_dense)
+            CU(ctx, cudaMemcpyAsync((float *)ctx->dense.p + (sc_lo - c_lo), io->dense_floor + sc_lo, (size_t)(sc_hi - sc_lo) * 4, cudaMemcpyHostToDevice, ci));
+        if (host_floors) {
+            const size_t rr = (size_t)(sr_hi - sr_lo) * C;
+            CU(ctx, cudaMemcpyAsync((uint8_t *)ctx->kinds.p + (sr_lo - r_lo) * C, io->floor_kind + sr_lo * C, rr, cudaMemcpyHostToDevice, ci));
+            if (io->floor1_y)
+                CU(ctx, cudaMemcpyAsync((uint32_t *)ctx->ys.p + (sr_lo - r_lo) * C * LWB_MAX_POSTS, io->floor1_y + sr_lo * C * LWB_MAX_POSTS,
+                                        rr * LWB_MAX_POSTS * sizeof(uint32_t), cudaMemcpyHostToDevice, ci));
+            if (vq) {
+                const uint64_t a = io->vq_run_offsets[sr_lo], b = io->vq_run_offsets[sr_hi], ea = io->vq_entry_offsets[sr_lo], eb = io->vq_entry_offsets[sr_hi];
+                const size_t nrow = (size_t)(sr_hi - sr_lo) + 1;
+                CU(ctx, cudaMemcpyAsync(const_cast<uint64_t *>(vqv.run_off) + sr_lo, io->vq_run_offsets + sr_lo, nrow * 8, cudaMemcpyHostToDevice, ci));
+                CU(ctx, cudaMemcpyAsync(const_cast<uint64_t *>(vqv.ent_off) + sr_lo, io->vq_entry_offsets + sr_lo, nrow * 8, cudaMemcpyHostToDevice, ci));
+                if (b > a) CU(ctx, cudaMemcpyAsync(const_cast<lwb_vq_run *>(vqv.runs) + a, io->vq_runs + a, (size_t)(b - a) * sizeof(lwb_vq_run), cudaMemcpyHostToDevice, ci));
+                if (eb > ea) CU(ctx, cudaMemcpyAsync(const_cast<uint16_t *>(vqv.entries) + ea, io->vq_entries + ea, (size_t)(eb - ea) * 2, cudaMemcpyHostToDevice, ci));
+            }
+        }
+        CU(ctx, cudaEventRecord(ctx->ev_in[sl], ci));
+        CU(ctx, cudaStreamWaitEvent(sm, ctx->ev_in[sl], 0));
+        if ((rc = launch_prologue(ctx, d_pk + pk0, npk_sl, C, fast, smem_old, kLongN2, d_res, d_dense, d_kinds, d_ys, d_spec, vqv))) return rc;
+        pk0 += npk_sl;
+        bool h2 = false;
+        LongSlice ls;
+        ls.active = true;
+        ls.o_lo = o_lo;
+        ls.o_hi = o_hi;
+        ls.ev_slot = (int)sl;
+        rc = try_long(ctx, chains + i0, i1 - i0, io, epoch, &h2, (const float *)ctx->spec.p, c_lo, nullptr, false, ls);
+        if (rc) return rc;
+        if (!h2) return fail(ctx, LWB_ERR_INVALID, "internal: uniform long residue batch refused by the fused path");
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->copy_out));
+    CU(ctx, cudaStreamSynchronize(sm));
     return LWB_OK;
 }
