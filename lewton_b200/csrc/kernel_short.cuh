@@ -223,7 +223,7 @@ struct TwShort {
     __device__ __forceinline__ V operator()(int slot) const
     {
         const int s = sp_of(slot);
-        return (s >= kSTwReg0 && s < kSTwReg1) ? r[s - kSTwReg0] : lane_base[s * 32];
+        return (s >= kSTwReg0 && s < kSTwReg1) ? r[s - kSTwReg0] : lane_base[s * 4];
     }
 };
 
@@ -288,11 +288,10 @@ k_short(const ShortRun *__restrict__ runs, uint32_t n_runs, const float *__restr
     uint4 *s_desc = reinterpret_cast<uint4 *>(base + kRingBytes + (size_t)kShortPackFloats * 4) + warp * kShortDescSlots * 3;
     uint64_t *bars = reinterpret_cast<uint64_t *>(base + kRingBytes + (size_t)kShortPackFloats * 4 +
                                                   (size_t)kShortWarps * kShortDescSlots * sizeof(ShortRun)) + warp * kShortRing;
-    {
-        const float4 *src = reinterpret_cast<const float4 *>(pack);
-        float4 *dst = reinterpret_cast<float4 *>(s_pack);
-        for (int i = threadIdx.x; i < kShortPackFloats / 4; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
+    // the pack depends on l = lane & 3 only: the shared copy keeps 4 lanes per slot (32 bytes), so that a warp's
+    // twiddle read is one multicast wavefront instead of two
+    for (int i = threadIdx.x; i < SP_END * 4; i += blockDim.x)
+        s_pack[i] = reinterpret_cast<const V *>(pack)[(i >> 2) * 32 + (i & 3)];
     if (lane == 0) {
         for (int i = 0; i < kShortRing; i++) mbar_init(smem_u32(&bars[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -300,8 +299,8 @@ k_short(const ShortRun *__restrict__ runs, uint32_t n_runs, const float *__restr
     __syncthreads();
     V twR[kSTwReg1 - kSTwReg0 > 0 ? kSTwReg1 - kSTwReg0 : 1];
 #pragma unroll
-    for (int s = kSTwReg0; s < kSTwReg1; s++) twR[s - kSTwReg0] = s_pack[s * 32 + lane];
-    const TwShort tw{twR, s_pack + lane};
+    for (int s = kSTwReg0; s < kSTwReg1; s++) twR[s - kSTwReg0] = s_pack[s * 4 + l];
+    const TwShort tw{twR, s_pack + l};
 
     const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars), desc_s = smem_u32(s_desc);
     // Transpose addresses (bytes inside the stage; E plane at +0, O plane at +2048).  4 * swzS(b, c) splits into a
