@@ -55,9 +55,13 @@ struct alignas(16) LongRun {      // 48 bytes: fetched by the kernel with one 1-
     uint8_t has_prev;       // 1: packet 0 overlaps with `state`;  0: packet 0 emits nothing
     uint8_t write_state;    // 1: store the last packet's right half to `state`
     uint8_t dummy;          // 1: filler partner of an unpaired run: transformed, never stored
-    uint8_t first_short;    // 1: packet 0 follows a short block (previous_window_flag == 0, audio.rs:1059-1065)
+    uint8_t first_short;    // 1: packet 0 follows a short block (previous_window_flag == 0, audio.rs:1059-1065);
+                            // 2: the same, but the short block's kernel runs AFTER this one: packet 0 stores its
+                            //    windowed left slope x[ls + i] w[i] (i < pl) to `state` instead of reading it, and
+                            //    leaves the first pl PCM samples to that kernel (k_short's tail, which adds its half)
     uint8_t last_short;     // 1: the last packet precedes a short block (next_window_flag == 0, audio.rs:1067-1073)
-    uint8_t pad[11];
+    uint8_t pad[3];
+    float *state_out;       // where write_state stores (nullptr: `state`)
 };
 static_assert(sizeof(LongRun) == 48, "LongRun is copied by TMA in 16-byte units");
 
@@ -582,13 +586,16 @@ struct RunCur {
     void *out;
     float *state;
     uint32_t in_stride;
-    uint32_t flags;               // bit0 has_prev, bit1 write_state, bit2 dummy, bit3 first_short, bit4 last_short
+    uint32_t flags;               // bit0 has_prev, bit1 write_state, bit2 dummy, bit3 first_short, bit4 last_short,
+                                  // bit5 first_short == 2 (the left slope is exported, nothing is read from `state`)
+    float *state_out;
 };
 __device__ __forceinline__ RunCur run_cur(const LongRun &r)
 {
     return RunCur{r.in, r.out, r.state, r.in_stride,
                   (uint32_t)(r.has_prev ? 1u : 0u) | (r.write_state ? 2u : 0u) | (r.dummy ? 4u : 0u) |
-                      (r.first_short ? 8u : 0u) | (r.last_short ? 16u : 0u)};
+                      (r.first_short ? 8u : 0u) | (r.last_short ? 16u : 0u) | (r.first_short == 2 ? 32u : 0u),
+                  r.state_out ? r.state_out : r.state};
 }
 
 // samples.rs:92-103 (`Sample for i16`): x * 32768, clamp, truncate toward zero, NaN -> 0
@@ -676,17 +683,24 @@ __device__ __forceinline__ void out_first_short(const TwMix &tw, int lane, const
             pe[b][j] = vnsub_p(vmul(O[b][j], b0), vmul(E[b][j], b1));
             if ((cur[b].flags & 5u) != 1u) continue;           // no history (or a dummy): nothing is emitted
             const float *prev = s_state + b * kLongN2;
+            const bool exported = (cur[b].flags & 32u) != 0;               // the short block's kernel adds prev[i] w[pl-1-i] later
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const float po = h ? p_odd.y : p_odd.x;
                 const int m = r64 + ((h == 0) == nat ? lane : 63 - lane);    // x[m] = p_odd, x[1023 - m] = -p_odd
                 if (m >= ls) {
                     const int i = m - ls;                                      // < pl / 2
-                    st_pcm(out[b] + i, __fadd_rn(__fmul_rn(po, __ldg(w + i)), __fmul_rn(prev[i], __ldg(w + pl - 1 - i))));
+                    const float cw = __fmul_rn(po, __ldg(w + i));
+                    if (exported) cur[b].state[i] = cw;
+                    else st_pcm(out[b] + i, __fadd_rn(cw, __fmul_rn(prev[i], __ldg(w + pl - 1 - i))));
                 }
                 const int i = kLongN2 - 1 - m - ls;                            // >= pl / 2
                 float v = -po;
-                if (i < pl) v = __fadd_rn(__fmul_rn(v, __ldg(w + i)), __fmul_rn(prev[i], __ldg(w + pl - 1 - i)));
+                if (i < pl) {
+                    v = __fmul_rn(v, __ldg(w + i));
+                    if (exported) { cur[b].state[i] = v; continue; }
+                    v = __fadd_rn(v, __fmul_rn(prev[i], __ldg(w + pl - 1 - i)));
+                }
                 st_pcm(out[b] + i, v);
             }
         }
@@ -804,7 +818,7 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
             const float *st[NB];
             uint32_t has[NB];
 #pragma unroll
-            for (int b = 0; b < NB; b++) { st[b] = cur[b].state; has[b] = cur[b].flags & 1u; }
+            for (int b = 0; b < NB; b++) { st[b] = cur[b].state; has[b] = (cur[b].flags & 33u) == 1u; }
             issue_state(st, has);
             for (; lc < (uint32_t)kLongRing && lc < npk; lc++) issue_stage_cur(lc, lc);
             nx_idx = atomicAdd(ticket, 1u);            // not looked at before the next packet
@@ -941,7 +955,7 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
                 const float *st[NB];
                 uint32_t has[NB];
 #pragma unroll
-                for (int b = 0; b < NB; b++) { st[b] = s_next[b].state; has[b] = s_next[b].has_prev; }
+                for (int b = 0; b < NB; b++) { st[b] = s_next[b].state; has[b] = s_next[b].has_prev && s_next[b].first_short != 2; }
                 fence_proxy_async();
                 issue_state(st, has);
                 nx_state_issued = 1;
@@ -965,14 +979,14 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
                         const int m = r64 + (h ? 63 - lane : lane);          // x[1024 + m] = x[2047 - m] = v
                         if (m < ls) {
                             if (emitted) st_pcm(out[b] + m, v);
-                        } else if (keep) {
-                            cur[b].state[m - ls] = v;
-                            cur[b].state[kLongN2 - 1 - ls - m] = v;
+                        } else if (keep && m < kLongN2 - ls) {      // the pl = 1024 - 2 ls samples the short block overlaps with
+                            cur[b].state_out[m - ls] = v;
+                            cur[b].state_out[kLongN2 - 1 - ls - m] = v;
                         }
                     }
                 }
             } else if ((cur[b].flags & 6u) == 2u) {       // write_state and not dummy
-                float *s_lo = cur[b].state + lane, *s_hi = cur[b].state + 63 - lane;
+                float *s_lo = cur[b].state_out + lane, *s_hi = cur[b].state_out + 63 - lane;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const int r64 = 64 * rev3(j);
@@ -1007,7 +1021,7 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
                 const float *st[NB];
                 uint32_t has[NB];
 #pragma unroll
-                for (int b = 0; b < NB; b++) { st[b] = s_next[b].state; has[b] = s_next[b].has_prev; }
+                for (int b = 0; b < NB; b++) { st[b] = s_next[b].state; has[b] = s_next[b].has_prev && s_next[b].first_short != 2; }
                 fence_proxy_async();
                 issue_state(st, has);
             }
@@ -1039,10 +1053,270 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
     }
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// k_long_s: the same transform behind a different driver, for launches made of MANY SHORT runs (the one-pass
+// schedule of mixed long / short streams, path_mixed.cuh: a run is what lies between two bursts of short
+// blocks, often one to three packets).  k_long learns its next group one group ahead (ticket, then descriptor,
+// then tiles), which leaves the ring under-filled and the descriptor latency exposed when groups are shorter
+// than the ring.  Here the deal is static (run r -> warp r mod W), so a warp knows its whole future:
+//   * descriptors arrive by cp.async in a shared ring, kLongFetch runs ahead of the producer;
+//   * the producer cursor walks (run, packet) in processing order and stays exactly kLongRing tiles ahead of
+//     the consumer, across any number of run boundaries;
+//   * the state row of the next run that overlaps with one (has_prev, not exported) is requested as soon as the
+//     state tile is free and that run's descriptor has landed.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLongFetch = 3;
+constexpr int kLongDescSlots = kLongFetch + kLongRing + 3;
+constexpr size_t kLongSmemBytesS = 2048 + (size_t)kLongWarps * (kLongRing + 1) * kLongTileBytes + (size_t)kLongPackFloats * 4 +
+                                   kLongWarps * (kLongRing + 2) * 8 + (size_t)kLongWarps * kLongDescSlots * sizeof(LongRun) + 64;
+
+template <typename OutT>
+__global__ void __launch_bounds__(kLongWarps * 32, 1)
+k_long_s(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restrict__ pack,
+         const float *__restrict__ w_short, int ls)
+{
+    constexpr int NB = 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t raw_s = smem_u32(smem_raw);
+    const uint32_t align_pad = (2048u - (raw_s & 2047u)) & 2047u;
+    unsigned char *base = smem_raw + align_pad;
+    constexpr size_t kTilesBytes = (size_t)kLongWarps * kLongRing * kLongTileBytes;
+    constexpr size_t kStateBytes = (size_t)kLongWarps * kLongTileBytes;
+    float *tiles = reinterpret_cast<float *>(base) + (size_t)warp * kLongRing * kLongN2;
+    float *s_state = reinterpret_cast<float *>(base + kTilesBytes) + (size_t)warp * kLongN2;
+    V *s_pack = reinterpret_cast<V *>(base + kTilesBytes + kStateBytes);
+    unsigned char *tail = base + kTilesBytes + kStateBytes + (size_t)kLongPackFloats * 4;
+    LongRun *s_desc = reinterpret_cast<LongRun *>(tail) + warp * kLongDescSlots;               // 16-aligned
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tail + (size_t)kLongWarps * kLongDescSlots * sizeof(LongRun)) + warp * (kLongRing + 2);
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(pack);
+        float4 *dst = reinterpret_cast<float4 *>(s_pack);
+        for (int i = threadIdx.x; i < kLongPackFloats / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (lane == 0) {
+        for (int i = 0; i < kLongRing + 1; i++) mbar_init(smem_u32(&bars[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    V twR[kTwReg1 - kTwReg0 > 0 ? kTwReg1 - kTwReg0 : 1];
+#pragma unroll
+    for (int s = kTwReg0; s < kTwReg1; s++) twR[s - kTwReg0] = s_pack[s * 32 + lane];
+    const TwMix tw{twR, s_pack + lane};
+
+    const uint32_t tiles_s = smem_u32(tiles), bars_s = smem_u32(bars), desc_s = smem_u32(s_desc);
+    const uint32_t bar_state = bars_s + 8 * kLongRing, state_s = smem_u32(s_state);
+    const uint32_t lA0 = laneA(lane, 0), lA1 = laneA(lane, 1);
+    const uint32_t lB = laneB(lane);
+    const uint32_t lC0 = laneC(lane, 0), lC1 = laneC(lane, 1);
+
+    const uint32_t W = gridDim.x * kLongWarps, gw = blockIdx.x * kLongWarps + warp;
+    if (gw >= n_runs) return;
+    const uint4 *rq = reinterpret_cast<const uint4 *>(runs);
+    uint32_t f_run = gw, f_slot = 0;
+    auto fetch = [&]() {            // cp.async groups are per thread: lanes 0..2 copy one quad each, everybody commits / waits
+        if (lane < 3 && f_run < n_runs) cp_async16(desc_s + f_slot * (uint32_t)sizeof(LongRun) + lane * 16, rq + 3 * (size_t)f_run + lane);
+        cp_async_commit();
+        f_run += W;
+        f_slot = (f_slot + 1 == (uint32_t)kLongDescSlots) ? 0 : f_slot + 1;
+    };
+#pragma unroll
+    for (int i = 0; i <= kLongFetch; i++) fetch();
+    cp_async_wait<kLongFetch>();
+    __syncwarp();
+    // ---- producer (warp-uniform cursor; lane 0 issues) ----
+    uint32_t p_run = gw, p_pkt = 0, p_slot = 0, p_stage = 0;
+    const float *p_in = s_desc[0].in;
+    uint32_t p_stride = s_desc[0].in_stride, p_npk = s_desc[0].n_packets;
+    auto produce = [&]() {
+        if (lane == 0) {
+            fence_proxy_async();          // the stage was written through the generic proxy (transposes) before
+            const uint32_t bar = bars_s + 8 * p_stage;
+            mbar_expect_tx(bar, kLongTileBytes);
+            tma_load_1d(tiles_s + p_stage * kLongTileBytes, p_in + (size_t)p_pkt * p_stride, kLongTileBytes, bar);
+        }
+        p_stage = (p_stage + 1 == (uint32_t)kLongRing) ? 0 : p_stage + 1;
+        if (++p_pkt >= p_npk) {
+            p_run += W;
+            p_pkt = 0;
+            p_slot = (p_slot + 1 == (uint32_t)kLongDescSlots) ? 0 : p_slot + 1;
+            fetch();                      // run p_run + kLongFetch * W
+            cp_async_wait<kLongFetch>();  // run p_run's descriptor has landed
+            __syncwarp();
+            if (p_run < n_runs) { p_in = s_desc[p_slot].in; p_stride = s_desc[p_slot].in_stride; p_npk = s_desc[p_slot].n_packets; }
+        }
+    };
+    for (int i = 0; i < kLongRing; i++)
+        if (p_run < n_runs) produce();
+
+    // ---- state rows: st_run = the run whose row is in the tile or on its way (~0: the tile is free) ----
+    uint32_t st_run = ~0u;
+    auto issue_state = [&](const float *row, uint32_t run) {
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar_state, kLongTileBytes);
+            tma_load_1d(state_s, row, kLongTileBytes, bar_state);
+        }
+        st_run = run;
+    };
+    // first run in [from_run, p_run] that reads a row; the descriptor slots between the consumer and the producer have
+    // landed and are not overwritten before the consumer has passed them
+    auto request_state = [&](uint32_t from_run, uint32_t from_slot) {
+        uint32_t r = from_run, sl = from_slot;
+        while (r < n_runs && r <= p_run) {
+            const LongRun &d = s_desc[sl];
+            if (d.has_prev && d.first_short != 2) {
+                issue_state(d.state, r);
+                return;
+            }
+            r += W;
+            sl = (sl + 1 == (uint32_t)kLongDescSlots) ? 0 : sl + 1;
+        }
+    };
+
+    uint32_t phase_bits = 0, slot_i = 0, c_slot = 0;
+    for (uint32_t c_run = gw; c_run < n_runs; c_run += W) {
+        RunCur cur[NB];
+        cur[0] = run_cur(s_desc[c_slot]);
+        const uint32_t npk = s_desc[c_slot].n_packets;
+        const uint32_t my_slot = c_slot;
+        c_slot = (c_slot + 1 == (uint32_t)kLongDescSlots) ? 0 : c_slot + 1;
+        const bool need_state = (cur[0].flags & 33u) == 1u;
+        if (st_run == ~0u) request_state(c_run, my_slot);
+        V pe[NB][8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) pe[0][j] = V{0.f, 0.f};
+        OutT *out[NB];
+        out[0] = static_cast<OutT *>(cur[0].out);
+
+        for (uint32_t p = 0; p < npk; p++) {
+            const uint32_t stage_s = tiles_s + slot_i * kLongTileBytes;
+            mbar_wait(bars_s + 8 * slot_i, (phase_bits >> slot_i) & 1u);
+            phase_bits ^= 1u << slot_i;
+            V O[NB][8], E[NB][8];
+            {
+                const float *tp[NB];
+                tp[0] = tiles + slot_i * kLongN2;
+                phase_a<NB>(tp, lane, tw, O, E);
+            }
+            __syncwarp();           // every lane has consumed its quads: the tile becomes the scratch
+            {
+                const uint32_t a0 = stage_s + lA0, a1 = stage_s + lA1;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    sts_eo(a0 ^ LWB_KA(j), E[0][j].x, O[0][j].x);
+                    sts_eo(a1 ^ LWB_KA(j), E[0][j].y, O[0][j].y);
+                }
+            }
+            __syncwarp();
+            {
+                const uint32_t b0 = stage_s + lB;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    lds_eo(b0 ^ LWB_KB(j, 0), E[0][j].x, O[0][j].x);
+                    lds_eo(b0 ^ LWB_KB(j, 1), E[0][j].y, O[0][j].y);
+                }
+            }
+            __syncwarp();
+            phase_b<NB>(tw, O, E);
+            {
+                const uint32_t b0 = stage_s + lB;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    sts_eo(b0 ^ LWB_KB(j, 0), E[0][j].x, O[0][j].x);
+                    sts_eo(b0 ^ LWB_KB(j, 1), E[0][j].y, O[0][j].y);
+                }
+            }
+            __syncwarp();
+            {
+                const uint32_t c0 = stage_s + lC0, c1 = stage_s + lC1;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    lds_eo(c0 ^ LWB_KC(j), E[0][j].x, O[0][j].x);
+                    lds_eo(c1 ^ LWB_KC(j), E[0][j].y, O[0][j].y);
+                }
+            }
+            __syncwarp();
+            if (p_run < n_runs) produce();          // the stage is free again
+            phase_c_fft<NB>(tw, O, E);
+            if (p > 0) {
+                out_stage<NB, false, OutT>(tw, lane, O, E, pe, cur, out, s_state);
+            } else {
+                if (need_state) {
+                    if (st_run != c_run) issue_state(cur[0].state, c_run);  // (its descriptor had not landed when the tile came free)
+                    mbar_wait(bar_state, (phase_bits >> 30) & 1u);
+                    phase_bits ^= 1u << 30;
+                }
+                if (cur[0].flags & 8u)
+                    out_first_short<NB, OutT>(tw, lane, O, E, pe, cur, out, s_state, w_short, ls);
+                else
+                    out_stage<NB, true, OutT>(tw, lane, O, E, pe, cur, out, s_state);
+                __syncwarp();
+                if (need_state) {                                           // state tile consumed: on to the next run that needs it
+                    st_run = ~0u;
+                    request_state(c_run + W, c_slot);
+                }
+            }
+            if (p > 0 || (cur[0].flags & 1u)) out[0] += (p == 0 && (cur[0].flags & 8u)) ? kLongN2 - ls : kLongN2;
+            slot_i = (slot_i + 1 == (uint32_t)kLongRing) ? 0 : slot_i + 1;
+        }
+        if ((cur[0].flags & 16u)) {
+            // the last packet precedes a short block: see k_long
+            const bool emitted = (npk > 1 || (cur[0].flags & 1u)) && !(cur[0].flags & 4u);
+            const bool keep = (cur[0].flags & 6u) == 2u;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int r64 = 64 * rev3(j);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const float v = ((j & 1) != 0) == (h == 0) ? pe[0][j].x : pe[0][j].y;
+                    const int m = r64 + (h ? 63 - lane : lane);          // x[1024 + m] = x[2047 - m] = v
+                    if (m < ls) {
+                        if (emitted) st_pcm(out[0] + m, v);
+                    } else if (keep && m < kLongN2 - ls) {
+                        cur[0].state_out[m - ls] = v;
+                        cur[0].state_out[kLongN2 - 1 - ls - m] = v;
+                    }
+                }
+            }
+        } else if ((cur[0].flags & 6u) == 2u) {
+            float *s_lo = cur[0].state_out + lane, *s_hi = cur[0].state_out + 63 - lane;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int r64 = 64 * rev3(j);
+                const float vx = (j & 1) ? pe[0][j].x : pe[0][j].y, vy = (j & 1) ? pe[0][j].y : pe[0][j].x;
+                s_lo[r64] = vx; s_hi[r64] = vy;
+                s_hi[960 - r64] = vx; s_lo[960 - r64] = vy;
+            }
+        }
+    }
+}
+
+inline int long_launch_static(cudaStream_t stream, const LongRun *d_runs, uint32_t n_runs, const float *d_pack, int sm_count,
+                              bool i16_out, const float *d_w_short, int ls)
+{
+    if (!n_runs) return 0;
+    const uint32_t want = (n_runs + kLongWarps - 1) / kLongWarps;
+    const uint32_t grid = want < (uint32_t)sm_count ? want : (uint32_t)sm_count;
+    if (i16_out) k_long_s<int16_t><<<grid, kLongWarps * 32, kLongSmemBytesS, stream>>>(d_runs, n_runs, d_pack, d_w_short, ls);
+    else k_long_s<float><<<grid, kLongWarps * 32, kLongSmemBytesS, stream>>>(d_runs, n_runs, d_pack, d_w_short, ls);
+    return cudaGetLastError() != cudaSuccess;
+}
+
 inline void long_kernel_configure()
 {
     cudaFuncSetAttribute(k_long<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes);
     cudaFuncSetAttribute(k_long<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes);
+    cudaFuncSetAttribute(k_long_s<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytesS);
+    cudaFuncSetAttribute(k_long_s<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytesS);
 }
 
 // d_runs: n_groups * kLongNB descriptors.  Returns 0 on success; `ticket` must point at a zeroed

@@ -36,8 +36,12 @@ struct alignas(16) ShortRun {              // 48 bytes
     uint32_t in_stride;
     uint32_t n_packets;     // including a primer packet (has_prev == 0: packet 0 emits nothing)
     uint8_t has_prev;       // 1: packet 0 overlaps with state[0..128)
-    uint8_t write_state;    // 1: store the last packet's right half to state[0..128)
-    uint8_t pad[14];
+    uint8_t write_state;    // 1: store the last packet's right half to end_ptr[0..128) (`state` if end_ptr is null)
+    uint8_t tail;           // 1: a long block follows whose kernel ran BEFORE this one (LongRun::first_short == 2): end_ptr
+                            //    holds its windowed left slope x[ls + i] w[i]; this run adds its right half's share and
+                            //    stores the 128 samples the two blocks overlap in, right behind its own PCM (audio.rs:1112-1118)
+    uint8_t pad[5];
+    float *end_ptr;
 };
 static_assert(sizeof(ShortRun) == 48, "ShortRun layout");
 
@@ -227,13 +231,6 @@ struct TwShort {
     }
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ float lds_f32(uint32_t addr)
 {
     float v;
@@ -379,7 +376,9 @@ k_short(const ShortRun *__restrict__ runs, uint32_t n_runs, const float *__restr
         OutT *out = reinterpret_cast<OutT *>(((unsigned long long)d0.w << 32) | d0.z);
         float *state = reinterpret_cast<float *>(((unsigned long long)d1.y << 32) | d1.x);
         const uint32_t npk = d1.w;
-        const bool has_prev = (d2.x & 0xffu) != 0, write_state = ((d2.x >> 8) & 0xffu) != 0;
+        const bool has_prev = (d2.x & 0xffu) != 0, write_state = ((d2.x >> 8) & 0xffu) != 0, tail = ((d2.x >> 16) & 0xffu) != 0;
+        float *end_ptr = reinterpret_cast<float *>(((unsigned long long)d2.w << 32) | d2.z);
+        if (!end_ptr) end_ptr = state;
         const bool contig = d1.z == (uint32_t)kShortN2;
         const uint32_t n_oct = (npk + kShortOct - 1) / kShortOct;
         const uint32_t koff = has_prev ? 0u : 1u;                // packet 0 emits nothing then: packet k lands at 128 (k - 1)
@@ -470,8 +469,29 @@ k_short(const ShortRun *__restrict__ runs, uint32_t n_runs, const float *__restr
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int mx = outIndex_s(l, j, 0), my = outIndex_s(l, j, 1);
-                state[mx] = pe[j].x; state[my] = pe[j].y;
-                state[127 - mx] = pe[j].x; state[127 - my] = pe[j].y;     // x[128+m] == x[255-m] (imdct.rs:622-649)
+                end_ptr[mx] = pe[j].x; end_ptr[my] = pe[j].y;
+                end_ptr[127 - mx] = pe[j].x; end_ptr[127 - my] = pe[j].y;     // x[128+m] == x[255-m] (imdct.rs:622-649)
+            }
+        }
+        if (tail && (uint32_t)blk == ((npk - 1) & (kShortOct - 1))) {
+            // pcm[i] = x_long[ls + i] w[i] + prev[i] w[127 - i]: the first product comes from the long kernel, prev is this
+            // block's right half (prev[m] == prev[127 - m] == p_even)
+            OutT *on = out + (size_t)(npk - koff) * kShortN2;
+            float cw[8][4];                              // all loads first: the stores below may alias them as far as the compiler knows
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int mx = outIndex_s(l, j, 0), my = outIndex_s(l, j, 1);
+                cw[j][0] = __ldcg(end_ptr + mx); cw[j][1] = __ldcg(end_ptr + my);
+                cw[j][2] = __ldcg(end_ptr + 127 - mx); cw[j][3] = __ldcg(end_ptr + 127 - my);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int mx = outIndex_s(l, j, 0), my = outIndex_s(l, j, 1);
+                const V wlo = tw(P_WLO + j), whi = tw(P_WHI + j);
+                st_pcm(on + mx, __fadd_rn(cw[j][0], __fmul_rn(pe[j].x, whi.x)));
+                st_pcm(on + my, __fadd_rn(cw[j][1], __fmul_rn(pe[j].y, whi.y)));
+                st_pcm(on + 127 - mx, __fadd_rn(cw[j][2], __fmul_rn(pe[j].x, wlo.x)));
+                st_pcm(on + 127 - my, __fadd_rn(cw[j][3], __fmul_rn(pe[j].y, wlo.y)));
             }
         }
     }

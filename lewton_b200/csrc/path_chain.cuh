@@ -46,18 +46,35 @@ static int launch_chain(lwb_ctx *ctx, int fmt, unsigned n_chains, unsigned warps
 }
 
 // one launch of the fused kernel and one of the chain kernel per round, in stream order
+// One block per row: the stream state the first segment of a chain starts from, moved out of the way of the segment of
+// the same chain that ends the batch -- in the one-pass schedule (path_mixed.cuh) that one may store the new state before
+// the first one has read the old.
+__global__ void k_row_copy(const RowCopy *__restrict__ rc)
+{
+    const RowCopy c = rc[blockIdx.x];
+    for (uint32_t i = threadIdx.x; i < c.n4; i += blockDim.x)
+        reinterpret_cast<float4 *>(c.dst)[i] = reinterpret_cast<const float4 *>(c.src)[i];
+}
+
 static int mixed_launch_rounds(lwb_ctx *ctx, const MixLaunch &ml, const std::vector<MixRound> &rounds)
 {
     constexpr uint32_t kTicketPool = 1024;
     cudaStream_t sm = ctx->stream;
     int rc = LWB_OK;
     for (const MixRound &rd : rounds) {
+        if (rd.nx) {
+            k_row_copy<<<(unsigned)rd.nx, 64, 0, sm>>>((const RowCopy *)(ml.db + ml.off_rc) + rd.x0);
+            if (cudaGetLastError() != cudaSuccess) return fail(ctx, LWB_ERR_CUDA, "row copy launch", cudaGetLastError());
+            ctx->launches++;
+        }
         if (rd.nr) {
             if (ctx->ticket_next % kTicketPool == 0)
                 CU(ctx, cudaMemsetAsync(ctx->ticket.p, 0, kTicketPool * sizeof(unsigned int), sm));
             unsigned int *ticket = (unsigned int *)ctx->ticket.p + (ctx->ticket_next++ % kTicketPool);
             if (kLongNB != 1) return fail(ctx, LWB_ERR_INVALID, "mixed path needs one run per warp");
-            if (long_launch(sm, (const LongRun *)ml.db + rd.r0, (uint32_t)rd.nr, ml.pack, ticket, ctx->sm_count, ml.i16, ml.w_short, ml.ls))
+            // one pass over many short runs: the static deal with its deeper lookahead (k_long_s); rounds: tickets
+            if (ml.flat ? long_launch_static(sm, (const LongRun *)ml.db + rd.r0, (uint32_t)rd.nr, ml.pack, ctx->sm_count, ml.i16, ml.w_short, ml.ls)
+                        : long_launch(sm, (const LongRun *)ml.db + rd.r0, (uint32_t)rd.nr, ml.pack, ticket, ctx->sm_count, ml.i16, ml.w_short, ml.ls))
                 return fail(ctx, LWB_ERR_CUDA, "long kernel launch", cudaGetLastError());
             ctx->launches++;
         }
@@ -226,7 +243,7 @@ static int try_chain(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         CU(ctx, cudaEventRecord(st->ev, sm));
         st->pending = true;
         MixLaunch ml;
-        ml.db = (char *)dbuf.p; ml.off_sr = 0; ml.off_cd = 0; ml.off_by = used_desc; ml.pack = nullptr; ml.spack = nullptr; ml.w_short = nullptr; ml.ls = 0;
+        ml.db = (char *)dbuf.p; ml.off_sr = 0; ml.off_cd = 0; ml.off_rc = 0; ml.flat = false; ml.off_by = used_desc; ml.pack = nullptr; ml.spack = nullptr; ml.w_short = nullptr; ml.ls = 0;
         ml.i16 = false; ml.residue = residue; ml.out_format = io->out_format; ml.warps = maxc * wpc; ml.smem = smem;
         ml.n1max = n1max; ml.wpc = wpc; ml.np = np; ml.coeffs = d_coeffs; ml.dense = d_dense; ml.kinds = d_kinds; ml.ys = d_ys; ml.pcm = d_pcm;
         std::vector<MixRound> rounds(1, MixRound{0, 0, 0, 0, 0, n_launch});

@@ -72,7 +72,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
     enum { SEG_CHAIN = 0, SEG_LONG = 1, SEG_SHORT = 2 };
     struct Seg { int kind; bool first_short, last_short; uint32_t p0, n; bool has; uint32_t plen; uint64_t coeff, pos; };
     bool chain_sees_long = false;       // the chain kernel's shared memory is sized for what it actually gets
-    struct Walk { uint32_t seg0, n_seg; bool end_has; uint32_t end_plen; bool touched; uint32_t boff; uint64_t coeff_end; };
+    struct Walk { uint32_t seg0, n_seg; bool end_has; uint32_t end_plen; bool touched; uint32_t boff; uint64_t coeff_end; size_t slot0; };
     std::vector<Walk> walks(n_chains);
     std::vector<Seg> segs;
     segs.reserve(n_chains * 2);
@@ -177,6 +177,45 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
     }
     if (need_dense && !io->dense_floor) return fail(ctx, LWB_ERR_INVALID, "dense_floor missing");
     int rc = LWB_OK;
+    // One pass instead of rounds: where every chain alternates strictly between long and short segments, the only
+    // thing a segment needs from its predecessor is the pl = 128 samples the two blocks overlap in, and the sum
+    // x[ls + i] w[i] + prev[i] w[pl-1-i] (audio.rs:1112-1118) does not care which of its two products exists first.
+    // So k_long runs ONCE over all long segments -- a run that follows a short block leaves its product in a
+    // boundary slot (LongRun::first_short == 2), a run that precedes one leaves its raw right half in another --
+    // and k_short then runs ONCE over all short segments, reading the one and completing the other (ShortRun::tail).
+    bool flat = max_rounds > 1 && !getenv("LWB_MIXED_ROUNDS");
+    size_t n_slots = 1;                                   // boundary slots of 128 floats: (boundary, channel); slot 0 unused
+    for (size_t i = 0; i < n_chains && flat; i++) {
+        const Walk &w = walks[i];
+        for (uint32_t q = 0; q < w.n_seg && flat; q++) {
+            const Seg &sg = segs[w.seg0 + q];
+            if (sg.kind == SEG_CHAIN) flat = false;
+            else if (q && sg.kind == segs[w.seg0 + q - 1].kind) flat = false;
+            else if (sg.kind == SEG_LONG && ((q && !sg.first_short) || (q + 1 < w.n_seg && !sg.last_short))) flat = false;
+        }
+    }
+    // The stream's state row is read by the chain's first segment and written by its last, which now run in no
+    // particular order: the old state is moved to slots first (k_row_copy) and the first segment reads those.
+    auto needs_precopy = [&](size_t i) { return flat && walks[i].n_seg > 1 && segs[walks[i].seg0].has; };
+    auto pre_units = [&](size_t i) {         // slots per channel: a long block on top of a long one overlaps in 1024 samples
+        const Seg &sg = segs[walks[i].seg0];
+        return (size_t)(sg.kind == SEG_LONG && !sg.first_short ? kLongN2 / kShortN2 : 1);
+    };
+    size_t n_rc = 0;
+    if (flat) {
+        for (size_t i = 0; i < n_chains; i++) {
+            const unsigned C = chains[i].stream->setup->channels;
+            walks[i].slot0 = n_slots;
+            if (walks[i].n_seg > 1) n_slots += (size_t)(walks[i].n_seg - 1) * C;
+            if (needs_precopy(i)) { n_slots += C * pre_units(i); n_rc += C; }       // behind the chain's boundary slots
+        }
+        max_rounds = 1;
+    }
+    // segments of chain i that round r launches: all of them in one pass, else the r-th
+    auto seg_range = [&](size_t i, size_t r, uint32_t *q0, uint32_t *q1) {
+        if (flat) { *q0 = 0; *q1 = walks[i].n_seg; }
+        else { *q0 = (uint32_t)std::min<size_t>(r, walks[i].n_seg); *q1 = (uint32_t)std::min<size_t>(r + 1, walks[i].n_seg); }
+    };
     const int n1max_all = n1max;         // largest blocksize of the batch (front stages); n1max below sizes the chain kernel
     if (!chain_sees_long) n1max = n0max;
     int wpc = std::max(1, std::min(8, n1max / 1024));
@@ -250,8 +289,8 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             for (size_t i = ck.i0; i < ck.i1; i++) {
                 const unsigned C = chains[i].stream->setup->channels;
                 for (uint32_t q = 0; q < walks[i].n_seg; q++) {
-                    if (segs[walks[i].seg0 + q].kind == SEG_LONG) round_long[q] += C;
-                    if (segs[walks[i].seg0 + q].kind == SEG_SHORT) round_short[q] += C;
+                    if (segs[walks[i].seg0 + q].kind == SEG_LONG) round_long[flat ? 0 : q] += C;
+                    if (segs[walks[i].seg0 + q].kind == SEG_SHORT) round_short[flat ? 0 : q] += C;
                 }
                 if (!walks[i].n_seg) continue;
                 ck.kc_lo = std::min(ck.kc_lo, chains[i].coeff_offset);
@@ -271,8 +310,8 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             for (size_t i = ck.i0; i < ck.i1; i++)
                 for (uint32_t q = 0; q < walks[i].n_seg; q++) {
                     const Seg &sg = segs[walks[i].seg0 + q];
-                    if (sg.kind == SEG_LONG) n_runs += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, q);
-                    else if (sg.kind == SEG_SHORT) n_sruns += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, q);
+                    if (sg.kind == SEG_LONG) n_runs += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, flat ? 0 : q);
+                    else if (sg.kind == SEG_SHORT) n_sruns += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, flat ? 0 : q);
                     else n_cd++;
                     if (residue) n_pro += sg.n;
                 }
@@ -281,15 +320,27 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         const bool capture = plan && !host;
         DevBuf &dbuf = capture ? plan->mix : ctx->cdesc;
         const size_t off_sr = n_runs * sizeof(LongRun), off_cd = off_sr + n_sruns * sizeof(ShortRun), off_pro = off_cd + n_cd * sizeof(ChainDesc);
-        const size_t off_by = off_pro + n_pro * sizeof(DevPacket), total = off_by + boff + 16;
+        const size_t off_rc = off_pro + n_pro * sizeof(DevPacket);
+        const size_t off_by = off_rc + n_rc * sizeof(RowCopy), total = off_by + boff + 16;
+        // boundary slots (device only, not part of the upload); k_long's state copy reads 4 KB wherever it reads
+        const size_t off_slots = (total + 511) & ~(size_t)511, slots_bytes = flat ? n_slots * (kShortN2 * 4) + 4096 : 0;
         Staging *st;
         if ((rc = acquire_staging(ctx, total, &st))) return rc;
-        if ((rc = ensure(ctx, dbuf, total))) return rc;
+        if ((rc = ensure(ctx, dbuf, off_slots + slots_bytes))) return rc;
         char *hb = (char *)st->h, *db = (char *)dbuf.p;
+        float *d_slots = (float *)(db + off_slots);
+        auto slot_of = [&](size_t i, uint32_t boundary, unsigned C, unsigned ch) {      // between segments `boundary` and + 1 of chain i
+            return d_slots + (walks[i].slot0 + (size_t)boundary * C + ch) * kShortN2;
+        };
+        auto pre_slot = [&](size_t i, unsigned C, unsigned ch) {                          // copy of the state the chain starts from
+            return d_slots + (walks[i].slot0 + (size_t)(walks[i].n_seg - 1) * C + ch * pre_units(i)) * kShortN2;
+        };
         LongRun *h_runs = (LongRun *)hb;
         ShortRun *h_sr = (ShortRun *)(hb + off_sr);
         ChainDesc *h_cd = (ChainDesc *)(hb + off_cd);
         DevPacket *h_pro = (DevPacket *)(hb + off_pro);
+        RowCopy *h_rc = (RowCopy *)(hb + off_rc);
+        size_t wx = 0;
         std::memcpy(hb + off_by, bytes.data(), boff);
         const float *d_spec = nullptr;
         if (residue) {
@@ -317,18 +368,21 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             }
         };
         for (Chunk &ck : chunks) {
-            ck.rounds.assign(max_rounds, MixRound{0, 0, 0, 0, 0, 0});
+            ck.rounds.assign(max_rounds, MixRound{0, 0, 0, 0, 0, 0, 0, 0});
             ck.p0 = wp;
             for (size_t r = 0; r < max_rounds; r++) {
                 ck.rounds[r].r0 = wr;
                 ck.rounds[r].s0 = ws;
                 ck.rounds[r].c0 = wc;
+                ck.rounds[r].x0 = wx;
                 // fused-kernel runs first, longest first (three buckets): the kernel hands runs out in
                 // descriptor order, and a 64-packet run started last would be the whole round's tail
                 for (int bucket = 0; bucket < 3; bucket++)
                     for (size_t i = ck.i0; i < ck.i1; i++) {
-                        if (r >= walks[i].n_seg) continue;
-                        const Seg &sg = segs[walks[i].seg0 + r];
+                      uint32_t q0, q1;
+                      seg_range(i, r, &q0, &q1);
+                      for (uint32_t q = q0; q < q1; q++) {
+                        const Seg &sg = segs[walks[i].seg0 + q];
                         if (sg.kind != SEG_LONG) continue;
                         const uint32_t cuts = cuts_of(ck, sg, r), piece = sg.n / cuts;
                         if ((piece >= 32 ? 0 : piece >= 8 ? 1 : 2) != bucket) continue;
@@ -349,12 +403,22 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                                 lr.state = s->d_state + (size_t)ch * state_stride(su);
                                 lr.write_state = (k + 1 == cuts);
                                 lr.last_short = (k + 1 == cuts) && sg.last_short;
+                                if (flat && k + 1 == cuts && q + 1 < walks[i].n_seg) lr.state_out = slot_of(i, q, C, ch);
                                 if (k == 0) {
                                     lr.in = in0;
                                     lr.out = out0;
                                     lr.n_packets = (uint32_t)(p1 - p0);
                                     lr.has_prev = sg.has;
                                     lr.first_short = sg.first_short;
+                                    if (flat && q) {            // the short segment in front runs later and completes the overlap
+                                        lr.first_short = 2;
+                                        lr.state_out = lr.state_out ? lr.state_out : lr.state;
+                                        lr.state = slot_of(i, q - 1, C, ch);
+                                    } else if (needs_precopy(i)) {
+                                        lr.state_out = lr.state_out ? lr.state_out : lr.state;
+                                        h_rc[wx++] = RowCopy{lr.state, pre_slot(i, C, ch), (uint32_t)(pre_units(i) * kShortN2 / 4), 0};
+                                        lr.state = pre_slot(i, C, ch);
+                                    }
                                 } else {
                                     lr.in = in0 + (p0 - 1) * (size_t)lr.in_stride;         // primer = packet p0 - 1
                                     lr.out = out0 + (first_emit + (p0 - 1) * (size_t)kLongN2) * esz;
@@ -364,11 +428,14 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                             }
                         }
                         if (residue) emit_pro(c, su, sg);
+                      }
                     }
                 // short-block runs: one per channel (and per cut) of every short segment of this round
                 for (size_t i = ck.i0; i < ck.i1; i++) {
-                    if (r >= walks[i].n_seg) continue;
-                    const Seg &sg = segs[walks[i].seg0 + r];
+                  uint32_t q0, q1;
+                  seg_range(i, r, &q0, &q1);
+                  for (uint32_t q = q0; q < q1; q++) {
+                    const Seg &sg = segs[walks[i].seg0 + q];
                     if (sg.kind != SEG_SHORT) continue;
                     const lwb_chain *c = &chains[i];
                     const lwb_stream *s = c->stream;
@@ -386,11 +453,24 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                             sr.in_stride = (uint32_t)(C * kShortN2);
                             sr.state = s->d_state + (size_t)ch * state_stride(su);
                             sr.write_state = (k + 1 == cuts);
+                            if (flat && k + 1 == cuts && q + 1 < walks[i].n_seg) {      // the long block behind has run already
+                                sr.write_state = 0;
+                                sr.tail = 1;
+                                sr.end_ptr = slot_of(i, q, C, ch);
+                            }
                             if (k == 0) {
                                 sr.in = in0;
                                 sr.out = out0;
                                 sr.n_packets = (uint32_t)(p1 - p0);
                                 sr.has_prev = sg.has;
+                                if (flat && q) {                // the long segment in front left its right half in the slot
+                                    if (!sr.end_ptr) sr.end_ptr = sr.state;
+                                    sr.state = slot_of(i, q - 1, C, ch);
+                                } else if (needs_precopy(i)) {
+                                    if (!sr.end_ptr) sr.end_ptr = sr.state;
+                                    h_rc[wx++] = RowCopy{sr.state, pre_slot(i, C, ch), (uint32_t)(kShortN2 / 4), 0};
+                                    sr.state = pre_slot(i, C, ch);
+                                }
                             } else {
                                 sr.in = in0 + (p0 - 1) * (size_t)sr.in_stride;            // primer = packet p0 - 1
                                 sr.out = out0 + (first_emit + (p0 - 1) * (size_t)kShortN2) * esz;
@@ -400,9 +480,10 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                         }
                     }
                     if (residue) emit_pro(c, su, sg);
+                  }
                 }
                 for (size_t i = ck.i0; i < ck.i1; i++) {
-                    if (r >= walks[i].n_seg) continue;
+                    if (flat || r >= walks[i].n_seg) continue;
                     const Seg &sg = segs[walks[i].seg0 + r];
                     if (sg.kind != SEG_CHAIN) continue;
                     const lwb_chain *c = &chains[i];
@@ -427,6 +508,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 ck.rounds[r].nr = wr - ck.rounds[r].r0;
                 ck.rounds[r].ns = ws - ck.rounds[r].s0;
                 ck.rounds[r].nc = wc - ck.rounds[r].c0;
+                ck.rounds[r].nx = wx - ck.rounds[r].x0;
             }
             ck.np_ = wp - ck.p0;
         }
@@ -441,8 +523,14 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 CU(ctx, cudaEventCreateWithFlags(&ctx->ev_kdone[k], cudaEventDisableTiming));
             }
         }
+        // k_long's driver: the static deal looks further ahead, the tickets balance better -- short runs want the first
+        // (30 % short blocks: 1.18 vs 1.40 ms), long ones the second (2 %: 1.01 vs 0.91 ms; profiles/r2i_mixed.log)
+        size_t long_pk = 0;
+        for (const Seg &sg : segs) long_pk += sg.kind == SEG_LONG ? sg.n : 0;
+        bool long_static = flat && n_runs && long_pk * maxc < 6 * n_runs;
+        if (const char *e = getenv("LWB_LONG_DRIVER")) long_static = flat && e[0] == 's';
         MixLaunch ml;
-        ml.db = db; ml.off_sr = off_sr; ml.off_cd = off_cd; ml.off_by = off_by; ml.pack = pack; ml.spack = spack; ml.w_short = w_short; ml.ls = ls_long;
+        ml.db = db; ml.off_sr = off_sr; ml.off_cd = off_cd; ml.off_by = off_by; ml.off_rc = off_rc; ml.flat = long_static; ml.pack = pack; ml.spack = spack; ml.w_short = w_short; ml.ls = ls_long;
         ml.i16 = i16; ml.residue = false; ml.out_format = io->out_format; ml.warps = maxc * wpc; ml.smem = smem;
         ml.n1max = n1max; ml.wpc = wpc; ml.np = np; ml.coeffs = residue ? d_spec : d_coeffs; ml.dense = nullptr; ml.kinds = nullptr; ml.ys = nullptr;
         ml.pcm = d_pcm;

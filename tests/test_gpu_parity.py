@@ -762,7 +762,12 @@ def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle
                       np.concatenate(kinds) if residue else None, np.concatenate(ys) if residue else None, want, seqs,
                       [r.pwr.data().copy() for r in refs]))
     # "mixed": k_long + k_short (bs0 == 8) + k_chain rounds; "mixed_noshort": short blocks through the chain kernel
-    variants = [("mixed", None), ("chain", {"LWB_NO_MIXED": "1"}), ("mixed_noshort", {"LWB_NO_SHORT": "1"})]
+    # "mixed_rounds": segment by segment, the state handed over between launches (what batches that are not a strict
+    # long / short alternation still do); "mixed" runs k_long once and k_short once when bs0 == 8
+    variants = [("mixed", None), ("chain", {"LWB_NO_MIXED": "1"}), ("mixed_noshort", {"LWB_NO_SHORT": "1"}),
+                ("mixed_rounds", {"LWB_MIXED_ROUNDS": "1"}),
+                # the one-pass schedule under either driver of the long kernel (static deal / tickets)
+                ("mixed_static", {"LWB_LONG_DRIVER": "s"}), ("mixed_tickets", {"LWB_LONG_DRIVER": "t"})]
     if memory == cabi.MEM_HOST:
         variants.append(("mixed_chunked", {"LWB_E2E_CHUNKS": "3"}))       # H2D / kernels / D2H pipelined over 3 chunks of chains
     for name, env in variants:
@@ -803,8 +808,12 @@ def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle
                     for k in env:
                         del os.environ[k]
             n_launch = ctx.launch_count - launches0
-            if name.startswith("mixed"):
-                assert n_launch >= 3, n_launch        # at least fused + chain + fused/chain rounds
+            one_pass = name in ("mixed", "mixed_static", "mixed_tickets") and bs0 == 8
+            if one_pass and memory == cabi.MEM_DEVICE:
+                # (two front stages +) k_long + k_short, no rounds; streams with history: their state rows are copied first
+                assert n_launch == (4 if residue else 2) + (1 if batch else 0), n_launch
+            elif name.startswith("mixed"):
+                assert n_launch >= (2 if one_pass else 3), n_launch      # fused + chain + fused/chain rounds
             else:
                 assert n_launch == 1, n_launch
             outs[(name, batch)] = pcm
@@ -822,6 +831,71 @@ def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle
     for batch in range(2):
         for name, _ in variants[1:]:
             assert np.array_equal(outs[("mixed", batch)].view(np.uint8), outs[(name, batch)].view(np.uint8)), name
+
+
+@pytest.mark.parametrize("fmt,driver,p_short", [(cabi.OUT_F32_PLANAR, "s", 0.3), (cabi.OUT_I16_PLANAR, "s", 0.5),
+                                               (cabi.OUT_F32_PLANAR, "t", 0.3), (cabi.OUT_F32_PLANAR, "s", 0.08)])
+def test_one_pass_schedule_many_runs_per_warp(ctx, oracle, fmt, driver, p_short):
+    """The one-pass schedule of mixed streams at scale: thousands of chains, so every warp of k_long / k_long_s and of
+    k_short walks dozens of one- to three-packet runs, its prefetch (tiles, descriptors, state rows) crossing many run
+    boundaries, every boundary handing 128 samples over through a slot.  Two consecutive batches: the second starts
+    from stream state, which the pass moves out of the way first (k_row_copy).  The chains repeat 6 distinct streams,
+    so the oracle decodes 6 and the comparison covers all."""
+    rng = np.random.default_rng(int(p_short * 100) + (7 if driver == "t" else 0))
+    S, D, P, C = 2000, 6, 24, 2
+    modes = [(0, 0), (1, 0)]
+    su = make_setup(ctx, C, 8, 11, modes=modes)
+    f32 = fmt == cabi.OUT_F32_PLANAR
+    dt = np.float32 if f32 else np.int16
+    seqs = [mode_sequence(rng, 2 * P, p_short=p_short) for _ in range(D)]
+    refs = [RefStream(oracle, C, 8, 11, modes) for _ in range(D)]
+    pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+    os.environ["LWB_LONG_DRIVER"] = driver
+    try:
+        for batch in range(2):
+            want, specs, states = [], [], []
+            for d in range(D):
+                bf, prev, nxt = (a[batch * P:(batch + 1) * P] for a in seqs[d])
+                parts, sp = [], []
+                for i in range(P):
+                    res = rng.standard_normal((C, 1024 if bf[i] else 128)).astype(np.float32)
+                    rc, pcm = refs[d].spectrum(int(bf[i]), int(prev[i]), int(nxt[i]), res)
+                    assert rc == 0
+                    parts.append(pcm)
+                    sp.append(res.ravel())
+                want.append(np.concatenate(parts, axis=1))
+                specs.append(np.concatenate(sp))
+                states.append(refs[d].pwr.data().copy())
+            chains, coeffs, coeff_off, out_off = [], [], 0, 0
+            for s in range(S):
+                d = s % D
+                bf, prev, nxt = (a[batch * P:(batch + 1) * P] for a in seqs[d])
+                n = want[d].shape[1]
+                chains.append(L.ChainSpec(pwrs[s], bf.astype(np.uint8), prev, nxt, coeff_offset=coeff_off, out_offset=out_off,
+                                          out_stride=n))
+                coeffs.append(specs[d])
+                coeff_off += specs[d].size
+                out_off += n * C
+            coeffs = np.concatenate(coeffs)
+            pcm = np.zeros(out_off, dt)
+            launches0 = ctx.launch_count
+            L.decode_chains(ctx, chains, cabi.ENTRY_SPECTRUM, cabi.MEM_HOST, coeffs, pcm, fmt)
+            assert ctx.launch_count - launches0 <= 3 * 8, ctx.launch_count - launches0      # (copy +) k_long + k_short per host chunk
+            pos = 0
+            for s in range(S):
+                d = s % D
+                n = want[d].shape[1]
+                assert chains[s].status == 0 and chains[s].n_samples == n, (batch, s)
+                got = pcm[pos: pos + n * C].reshape(C, n)
+                if f32:
+                    assert bits_equal(got, want[d]), (batch, s, mismatch_report(got, want[d]))
+                else:
+                    assert np.array_equal(got, oracle.quantise_i16(want[d])), (batch, s)
+                pos += n * C
+            for s in range(0, S, 97):
+                assert bits_equal(pwrs[s].data(), states[s % D]), (batch, s)
+    finally:
+        del os.environ["LWB_LONG_DRIVER"]
 
 
 @pytest.mark.parametrize("P", [1, 2, 3, 5, 6])
