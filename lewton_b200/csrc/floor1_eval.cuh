@@ -150,10 +150,14 @@ LWB_HD uint32_t d_mulhi_u32(uint32_t a, uint32_t b)
 //   .z = |dy|            .w = -(|dy| * x0)                           -- |dy| * (k - x0) is one multiply-add
 // y(k) = y0 +- (mulhi(|dy| * (k - x0), magic) >> shift): the closed form of render_line (audio.rs:503-524).
 struct Seg4 { uint32_t x, y, z, w; };
-LWB_HD Seg4 d_floor1_pack_segment(const uint16_t *sx, const uint16_t *sy, int j)
+// magic_tab: d_floor1_magic of every adx in [0, 32768] (kFloor1MagicEntries words), built once per context -- the
+// 64-bit division behind it is ~150 instructions on the device, and a row has up to 66 segments; nullptr: compute it.
+constexpr int kFloor1MagicEntries = 32769;
+LWB_HD Seg4 d_floor1_pack_segment(const uint16_t *sx, const uint16_t *sy, int j, const uint32_t *magic_tab = nullptr)
 {
-    int sh;
-    const uint32_t mg = d_floor1_magic((int)sx[j + 1] - (int)sx[j], &sh);
+    const int adx = (int)sx[j + 1] - (int)sx[j];
+    int sh = adx > 4096 ? 12 : 0;
+    const uint32_t mg = magic_tab && adx >= 0 ? magic_tab[adx] : d_floor1_magic(adx, &sh);
     const int y0 = sy[j] & 255, dy = (int)(sy[j + 1] & 255) - y0;
     const uint32_t ady = (uint32_t)(dy < 0 ? -dy : dy);
     Seg4 s;

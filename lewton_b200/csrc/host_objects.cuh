@@ -45,7 +45,7 @@ struct lwb_ctx {
     uint64_t launches = 0;
     std::deque<CachedTables> tables;       // (deque: setups hold copies of dt, growth never moves an entry)
     // grow-only device arenas
-    DevBuf coeffs, dense, pcm, spec, segtab, vqoff, vqrec, x, desc, kinds, ys, chains, ticket, cdesc, cbytes;
+    DevBuf coeffs, dense, pcm, spec, segtab, vqoff, vqrec, magic, x, desc, kinds, ys, chains, ticket, cdesc, cbytes;
     Staging stage[3];              // ring: a batch's descriptors are written while the previous copies may still run
     int stage_next = 0;
     // pinned staging for descriptors (four-kernel path)

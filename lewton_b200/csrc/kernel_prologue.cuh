@@ -37,7 +37,7 @@ inline size_t floor1_segments_smem(int words) { return (size_t)kSegRows * words 
 __global__ void __launch_bounds__(kSegThreads)
 k_floor1_segments(const DevPacket *__restrict__ pkts, uint32_t n_rows, int C, const uint8_t *__restrict__ floor_kind,
                   const uint32_t *__restrict__ floor1_y, uint4 *__restrict__ segtab, uint8_t *__restrict__ seg_cnt,
-                  unsigned char *__restrict__ seg_index, int words)
+                  unsigned char *__restrict__ seg_index, int words, const uint32_t *__restrict__ magic_tab)
 {
     extern __shared__ uint32_t s_bm[];                  // [kSegRows][words]
     __shared__ uint16_t s_x[kSegRows][kSegStride];
@@ -72,7 +72,7 @@ k_floor1_segments(const DevPacket *__restrict__ pkts, uint32_t n_rows, int C, co
         const int nseg = s_m[r] - 1;
         if (j <= nseg && nseg > 0) {                    // j == nseg: sentinel = a copy of the last segment
             const int jj = j < nseg ? j : nseg - 1;
-            const Seg4 sg = d_floor1_pack_segment(s_x[r], s_y[r], jj);
+            const Seg4 sg = d_floor1_pack_segment(s_x[r], s_y[r], jj, magic_tab);
             segtab[(size_t)(row0 + r) * kSegStride + j] = make_uint4(sg.x, sg.y, sg.z, sg.w);
             if (j < nseg) {
                 const int x0 = s_x[r][j];
@@ -116,8 +116,11 @@ __host__ __device__ inline size_t pf_row_bytes(int words) { return kSegStride * 
 // vq_elems: channels * (largest n/2) of a LWB_ENTRY_VQ batch (the residue accumulators), else 0
 inline size_t prologue_fused_smem(int channels, int words, size_t vq_elems = 0)
 {
-    return (size_t)channels * pf_row_bytes(words) + (channels > 1 ? (size_t)channels * kPfThreads * sizeof(float4) : 0) +
-           vq_elems * sizeof(float);
+    // one or two channels, dense residue: two table buffers (the kernel pipelines the packets) -- they fit where the
+    // general path keeps its coupling staging
+    const size_t staging = channels > 1 ? (size_t)channels * kPfThreads * sizeof(float4) : 0;
+    const size_t second = channels <= 2 && !vq_elems ? (size_t)channels * pf_row_bytes(words) : 0;
+    return (size_t)channels * pf_row_bytes(words) + (staging > second ? staging : second) + vq_elems * sizeof(float);
 }
 // device view of a batch's VQ arrays (biased so that absolute packet rows / absolute offsets address them)
 struct VqDev { const lwb_vq_run *runs; const uint64_t *run_off; const uint16_t *entries; const uint64_t *ent_off; };
@@ -202,6 +205,10 @@ __device__ __forceinline__ float4 d_floor_quad(int kind, int cnt, const float *_
 // Per packet: every global read the packet needs -- residue quads, the rows' segment tables and indices -- is issued
 // at the top (one exposed memory latency), the tables land in shared memory, and the per-bin work runs out of it.
 // VQ: the residue does not come from `residue` but from the packet's VQ records (d_vq_accumulate).
+#ifndef LWB_PF_SERIAL
+#define LWB_PF_SERIAL 0
+#endif
+constexpr bool PF_SERIAL = LWB_PF_SERIAL != 0;
 template <bool VQ>
 __global__ void __launch_bounds__(kPfThreads, 4)
 k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float *__restrict__ residue, const float *__restrict__ dense_floor,
@@ -219,6 +226,100 @@ k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float 
     const int row_q = (int)(rowb >> 4), tab_q = kSegStride;       // 16-byte quads per row: table, then index
     float4 *s_r = reinterpret_cast<float4 *>(pf_smem + (size_t)C * rowb);     // [C][kPfThreads] when C > 1
     float *s_acc = reinterpret_cast<float *>(pf_smem + (size_t)C * rowb + (C > 1 ? (size_t)C * kPfThreads * sizeof(float4) : 0));   // VQ: [C][n2]
+    if (!VQ && C <= 2 && !PF_SERIAL) {
+        // One or two channels, dense residue: the packets are software-pipelined.  While packet k is computed out of one
+        // table buffer, everything packet k + 1 needs is already on its way: its rows' tables by cp.async into the other
+        // buffer, its residue quads and header fields into registers.  One CTA barrier per packet.
+        struct Head { int n2, nsteps, k0, k1, c0, c1; bool swapped; uint64_t base; };
+        const int row_q2 = C * row_q;                                 // quads of one table buffer
+        unsigned char *bufs[2] = {pf_smem, pf_smem + (size_t)C * rowb};
+        auto prefetch = [&](uint32_t pk, int b, Head &h, float4 &a0, float4 &a1) {
+            const DevPacket &p = pkts[pk];
+            const size_t row0 = (size_t)pk * C;
+            for (int i = tid; i < row_q2; i += kPfThreads) {
+                const int c = i / row_q, j = i - c * row_q;
+                const void *src = j < tab_q ? (const void *)(segtab + (row0 + c) * kSegStride + j)
+                                            : (const void *)(reinterpret_cast<const uint4 *>(seg_index + (row0 + c) * ixs) + (j - tab_q));
+                cp_async16(smem_u32(bufs[b]) + 16u * (uint32_t)i, src);
+            }
+            cp_async_commit();
+            const DevSetup &su = *p.setup;
+            const DevMapping &mp = su.mappings[p.mapping];
+            h.n2 = p.n >> 1;
+            h.nsteps = mp.n_coupling;
+            h.swapped = h.nsteps == 1 && mp.mag[0] == 1;
+            h.base = p.coeff_off;
+            const uint8_t *kinds = floor_kind + p.pkt_index * C;
+            h.k0 = kinds[0]; h.k1 = C == 2 ? kinds[1] : LWB_FLOOR_UNUSED;
+            h.c0 = seg_cnt[row0]; h.c1 = C == 2 ? seg_cnt[row0 + 1] : 0;
+            a0 = make_float4(0.f, 0.f, 0.f, 0.f); a1 = a0;
+            if (tid < (h.n2 >> 2)) {
+                a0 = __ldcs(reinterpret_cast<const float4 *>(residue + h.base + 4 * (uint64_t)tid));
+                if (C == 2) a1 = __ldcs(reinterpret_cast<const float4 *>(residue + h.base + h.n2 + 4 * (uint64_t)tid));
+            }
+        };
+        Head h, hn;
+        float4 r0, r1, rn0, rn1;
+        int b = 0;
+        prefetch(blockIdx.x, 0, h, r0, r1);
+        for (uint32_t pk = blockIdx.x; pk < n_pk; pk += gridDim.x, b ^= 1) {
+            cp_async_wait<0>();
+            __syncthreads();              // this packet's tables are in; everybody is done with the other buffer
+            const uint32_t nx = pk + gridDim.x;
+            if (nx < n_pk) prefetch(nx, b ^ 1, hn, rn0, rn1);
+            const uint4 *t0 = reinterpret_cast<const uint4 *>(bufs[b]), *t1 = reinterpret_cast<const uint4 *>(bufs[b] + rowb);
+            const unsigned char *x0 = bufs[b] + (size_t)tab_q * 16, *x1 = x0 + rowb;
+            const int n2 = h.n2;
+            if (h.nsteps <= 1) {
+                for (int q = tid; q < (n2 >> 2); q += kPfThreads) {
+                    const uint64_t e0 = h.base + 4 * (uint64_t)q, e1 = e0 + n2;
+                    if (q != tid) {                               // blocks of more than 1024 bins: further passes
+                        r0 = *reinterpret_cast<const float4 *>(residue + e0);
+                        if (C == 2) r1 = *reinterpret_cast<const float4 *>(residue + e1);
+                    }
+                    if (h.nsteps == 1) {
+                        if (h.swapped) {
+                            d_inverse_couple(r1.x, r0.x); d_inverse_couple(r1.y, r0.y);
+                            d_inverse_couple(r1.z, r0.z); d_inverse_couple(r1.w, r0.w);
+                        } else {
+                            d_inverse_couple(r0.x, r1.x); d_inverse_couple(r0.y, r1.y);
+                            d_inverse_couple(r0.z, r1.z); d_inverse_couple(r0.w, r1.w);
+                        }
+                    }
+                    const float4 f0 = d_floor_quad(h.k0, h.c0, s_db, t0, x0, words, 4 * q, dense_floor, e0);
+                    __stcs(reinterpret_cast<float4 *>(spec + e0),
+                           make_float4(__fmul_rn(f0.x, r0.x), __fmul_rn(f0.y, r0.y), __fmul_rn(f0.z, r0.z), __fmul_rn(f0.w, r0.w)));
+                    if (C == 2) {
+                        const float4 f1 = d_floor_quad(h.k1, h.c1, s_db, t1, x1, words, 4 * q, dense_floor, e1);
+                        __stcs(reinterpret_cast<float4 *>(spec + e1),
+                               make_float4(__fmul_rn(f1.x, r1.x), __fmul_rn(f1.y, r1.y), __fmul_rn(f1.z, r1.z), __fmul_rn(f1.w, r1.w)));
+                    }
+                }
+            } else {
+                // several coupling steps over two channels (legal, never seen): in order, one bin at a time
+                const DevMapping &mp = pkts[pk].setup->mappings[pkts[pk].mapping];
+                for (int q = tid; q < (n2 >> 2); q += kPfThreads) {
+                    const uint64_t e0 = h.base + 4 * (uint64_t)q, e1 = e0 + n2;
+                    float4 v[2];
+                    v[0] = *reinterpret_cast<const float4 *>(residue + e0);
+                    v[1] = *reinterpret_cast<const float4 *>(residue + e1);
+                    for (int s2 = h.nsteps - 1; s2 >= 0; s2--) {
+                        float4 &m4 = v[mp.mag[s2] & 1], &a4 = v[mp.ang[s2] & 1];
+                        d_inverse_couple(m4.x, a4.x); d_inverse_couple(m4.y, a4.y);
+                        d_inverse_couple(m4.z, a4.z); d_inverse_couple(m4.w, a4.w);
+                    }
+                    const float4 f0 = d_floor_quad(h.k0, h.c0, s_db, t0, x0, words, 4 * q, dense_floor, e0);
+                    const float4 f1 = d_floor_quad(h.k1, h.c1, s_db, t1, x1, words, 4 * q, dense_floor, e1);
+                    *reinterpret_cast<float4 *>(spec + e0) =
+                        make_float4(__fmul_rn(f0.x, v[0].x), __fmul_rn(f0.y, v[0].y), __fmul_rn(f0.z, v[0].z), __fmul_rn(f0.w, v[0].w));
+                    *reinterpret_cast<float4 *>(spec + e1) =
+                        make_float4(__fmul_rn(f1.x, v[1].x), __fmul_rn(f1.y, v[1].y), __fmul_rn(f1.z, v[1].z), __fmul_rn(f1.w, v[1].w));
+                }
+            }
+            h = hn; r0 = rn0; r1 = rn1;
+        }
+        return;
+    }
     for (uint32_t pk = blockIdx.x; pk < n_pk; pk += gridDim.x) {
         const DevPacket &p = pkts[pk];
         const DevSetup &su = *p.setup;

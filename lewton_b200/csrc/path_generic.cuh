@@ -118,11 +118,20 @@ static int launch_prologue(lwb_ctx *ctx, const DevPacket *d_pk, size_t n_pk, uns
     const size_t rows = n_pk * C, tab_bytes = rows * kSegStride * sizeof(uint4), ix_bytes = rows * seg_index_stride(words);
     int rc = ensure(ctx, ctx->segtab, tab_bytes + ix_bytes + rows + 64);
     if (rc) return rc;
+    if (!ctx->magic.p) {            // multiply-high magics of every segment length, once per context
+        std::vector<uint32_t> mt(kFloor1MagicEntries);
+        for (int adx = 0; adx < kFloor1MagicEntries; adx++) {
+            int sh;
+            mt[adx] = d_floor1_magic(adx, &sh);
+        }
+        if ((rc = ensure(ctx, ctx->magic, mt.size() * sizeof(uint32_t)))) return rc;
+        CU(ctx, cudaMemcpy(ctx->magic.p, mt.data(), mt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     uint4 *tab = (uint4 *)ctx->segtab.p;
     unsigned char *ix = (unsigned char *)ctx->segtab.p + tab_bytes;
     uint8_t *cnt = ix + ix_bytes;
     rc = launch(ctx, k_floor1_segments, dim3((unsigned)((rows + kSegRows - 1) / kSegRows)), dim3(kSegThreads), floor1_segments_smem(words), d_pk,
-                (uint32_t)rows, (int)C, kinds, ys, tab, cnt, ix, words);
+                (uint32_t)rows, (int)C, kinds, ys, tab, cnt, ix, words, (const uint32_t *)ctx->magic.p);
     if (rc) return rc;
     const size_t grid = std::min<size_t>(n_pk, (size_t)ctx->sm_count * (C > 2 ? 4 : 8));
     const VqDev vd{vq.runs, vq.run_off, vq.entries, vq.ent_off};

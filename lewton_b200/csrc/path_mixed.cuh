@@ -10,6 +10,28 @@
 // the chain kernel -- and the segments of all chains are executed round by round, handing the overlap
 // state over through the stream's device state (PreviousWindowRight) between launches.
 // ---------------------------------------------------------------------------------------------
+// Static deals (run r -> warp r mod W: k_long_s, k_short) finish with their most loaded warp: order the runs so that
+// the W columns carry equal packet counts -- longest first, dealt boustrophedon (row 0 left to right, row 1 right to
+// left, ...).  With random run lengths an unordered deal leaves the slowest of 1184 warps a third above the mean.
+template <typename Run>
+static void balance_static_deal(Run *runs, size_t n, size_t W, std::vector<Run> &tmp)
+{
+    if (n <= W || W < 2) return;
+    uint32_t maxp = 0;
+    for (size_t i = 0; i < n; i++) maxp = std::max(maxp, runs[i].n_packets);
+    std::vector<size_t> start(maxp + 2, 0);
+    for (size_t i = 0; i < n; i++) start[maxp - runs[i].n_packets + 1]++;          // counting sort, descending
+    for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
+    tmp.resize(n);
+    const size_t full_rows = n / W;
+    for (size_t i = 0; i < n; i++) {
+        const size_t k = start[maxp - runs[i].n_packets]++;
+        const size_t row = k / W, col = k % W;
+        tmp[(row & 1) && row < full_rows ? row * W + (W - 1 - col) : k] = runs[i];
+    }
+    std::memcpy(runs, tmp.data(), n * sizeof(Run));
+}
+
 static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch, bool *handled,
                      lwb_plan *plan = nullptr)
 {
@@ -348,6 +370,8 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             d_spec = (const float *)ctx->spec.p - c_lo;          // same element offsets as the coefficient arena
         }
         size_t wr = 0, ws = 0, wc = 0, wp = 0;
+        std::vector<LongRun> tmp_lr;
+        std::vector<ShortRun> tmp_sr;
         // front-stage descriptors of one segment (residue entry): one per packet, whatever its blocksize
         auto emit_pro = [&](const lwb_chain *c, const lwb_setup *su, const Seg &sg) {
             uint64_t co = sg.coeff;
@@ -507,6 +531,13 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 }
                 ck.rounds[r].nr = wr - ck.rounds[r].r0;
                 ck.rounds[r].ns = ws - ck.rounds[r].s0;
+                if (flat && !getenv("LWB_NO_BALANCE")) {
+                    auto warps_of = [&](size_t n, int per_cta) {
+                        return std::min<size_t>((n + per_cta - 1) / per_cta, (size_t)ctx->sm_count) * per_cta;
+                    };
+                    balance_static_deal(h_runs + ck.rounds[r].r0, ck.rounds[r].nr, warps_of(ck.rounds[r].nr, kLongWarps), tmp_lr);
+                    balance_static_deal(h_sr + ck.rounds[r].s0, ck.rounds[r].ns, warps_of(ck.rounds[r].ns, kShortWarps), tmp_sr);
+                }
                 ck.rounds[r].nc = wc - ck.rounds[r].c0;
                 ck.rounds[r].nx = wx - ck.rounds[r].x0;
             }
@@ -523,11 +554,10 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 CU(ctx, cudaEventCreateWithFlags(&ctx->ev_kdone[k], cudaEventDisableTiming));
             }
         }
-        // k_long's driver: the static deal looks further ahead, the tickets balance better -- short runs want the first
-        // (30 % short blocks: 1.18 vs 1.40 ms), long ones the second (2 %: 1.01 vs 0.91 ms; profiles/r2i_mixed.log)
-        size_t long_pk = 0;
-        for (const Seg &sg : segs) long_pk += sg.kind == SEG_LONG ? sg.n : 0;
-        bool long_static = flat && n_runs && long_pk * maxc < 6 * n_runs;
+        // k_long's driver in one pass: the static deal (k_long_s) -- it looks further ahead than the tickets, and with the
+        // balanced order it is ahead at every share of short blocks (2 / 10 / 30 %: 0.886 / 1.014 / 1.131 ms against
+        // 0.895 / 1.031 / 1.212 ms, profiles/r2i_mixed.log)
+        bool long_static = flat;
         if (const char *e = getenv("LWB_LONG_DRIVER")) long_static = flat && e[0] == 's';
         MixLaunch ml;
         ml.db = db; ml.off_sr = off_sr; ml.off_cd = off_cd; ml.off_by = off_by; ml.off_rc = off_rc; ml.flat = long_static; ml.pack = pack; ml.spack = spack; ml.w_short = w_short; ml.ls = ls_long;
