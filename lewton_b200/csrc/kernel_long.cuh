@@ -588,14 +588,22 @@ struct RunCur {
     uint32_t in_stride;
     uint32_t flags;               // bit0 has_prev, bit1 write_state, bit2 dummy, bit3 first_short, bit4 last_short,
                                   // bit5 first_short == 2 (the left slope is exported, nothing is read from `state`)
-    float *state_out;
 };
 __device__ __forceinline__ RunCur run_cur(const LongRun &r)
 {
     return RunCur{r.in, r.out, r.state, r.in_stride,
                   (uint32_t)(r.has_prev ? 1u : 0u) | (r.write_state ? 2u : 0u) | (r.dummy ? 4u : 0u) |
-                      (r.first_short ? 8u : 0u) | (r.last_short ? 16u : 0u) | (r.first_short == 2 ? 32u : 0u),
-                  r.state_out ? r.state_out : r.state};
+                      (r.first_short ? 8u : 0u) | (r.last_short ? 16u : 0u)};
+}
+// k_long_s (one-pass schedule of mixed streams): a run may store its end state somewhere else than where it started from
+struct RunCurS : RunCur { float *state_out; };
+__device__ __forceinline__ RunCurS run_cur_s(const LongRun &r)
+{
+    RunCurS c;
+    static_cast<RunCur &>(c) = run_cur(r);
+    c.flags |= r.first_short == 2 ? 32u : 0u;
+    c.state_out = r.state_out ? r.state_out : r.state;
+    return c;
 }
 
 // samples.rs:92-103 (`Sample for i16`): x * 32768, clamp, truncate toward zero, NaN -> 0
@@ -617,9 +625,9 @@ __device__ __forceinline__ void st_pcm(int16_t *p, float v) { __stcs(reinterpret
 // run -- its previous right half comes from the stream state (staged in shared memory by TMA
 // while the run's first tile was in flight) if has_prev, else nothing is emitted.  Streaming
 // stores: PCM is written once and never read back by this kernel.
-template <int NB, bool FIRST, typename OutT>
+template <int NB, bool FIRST, typename OutT, typename RC = RunCur>
 __device__ __forceinline__ void out_stage(const TwMix &tw, int lane, const V O[NB][8], const V E[NB][8], V pe[NB][8],
-                                          const RunCur cur[NB], OutT *out[NB], const float *s_state)
+                                          const RC cur[NB], OutT *out[NB], const float *s_state)
 {
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -666,9 +674,9 @@ __device__ __forceinline__ void out_stage(const TwMix &tw, int lane, const V O[N
 // (2048 - n0) / 4), the saved right half is pl = n0 / 2 samples long, and the packet emits
 // x[ls .. 1024): pl windowed samples, then the rest of the left half as is (audio.rs:1112-1120).
 // Rare (once per burst of short blocks), so plain scalar code; w = the short window slope.
-template <int NB, typename OutT>
+template <int NB, typename OutT, typename RC = RunCur, bool EXPORT = false>
 __device__ __forceinline__ void out_first_short(const TwMix &tw, int lane, const V O[NB][8], const V E[NB][8], V pe[NB][8],
-                                                const RunCur cur[NB], OutT *out[NB], const float *s_state,
+                                                const RC cur[NB], OutT *out[NB], const float *s_state,
                                                 const float *__restrict__ w, int ls)
 {
     const int pl = kLongN2 - 2 * ls;
@@ -683,7 +691,7 @@ __device__ __forceinline__ void out_first_short(const TwMix &tw, int lane, const
             pe[b][j] = vnsub_p(vmul(O[b][j], b0), vmul(E[b][j], b1));
             if ((cur[b].flags & 5u) != 1u) continue;           // no history (or a dummy): nothing is emitted
             const float *prev = s_state + b * kLongN2;
-            const bool exported = (cur[b].flags & 32u) != 0;               // the short block's kernel adds prev[i] w[pl-1-i] later
+            const bool exported = EXPORT && (cur[b].flags & 32u) != 0;     // the short block's kernel adds prev[i] w[pl-1-i] later
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const float po = h ? p_odd.y : p_odd.x;
@@ -818,7 +826,7 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
             const float *st[NB];
             uint32_t has[NB];
 #pragma unroll
-            for (int b = 0; b < NB; b++) { st[b] = cur[b].state; has[b] = (cur[b].flags & 33u) == 1u; }
+            for (int b = 0; b < NB; b++) { st[b] = cur[b].state; has[b] = cur[b].flags & 1u; }
             issue_state(st, has);
             for (; lc < (uint32_t)kLongRing && lc < npk; lc++) issue_stage_cur(lc, lc);
             nx_idx = atomicAdd(ticket, 1u);            // not looked at before the next packet
@@ -955,7 +963,7 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
                 const float *st[NB];
                 uint32_t has[NB];
 #pragma unroll
-                for (int b = 0; b < NB; b++) { st[b] = s_next[b].state; has[b] = s_next[b].has_prev && s_next[b].first_short != 2; }
+                for (int b = 0; b < NB; b++) { st[b] = s_next[b].state; has[b] = s_next[b].has_prev; }
                 fence_proxy_async();
                 issue_state(st, has);
                 nx_state_issued = 1;
@@ -980,13 +988,13 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
                         if (m < ls) {
                             if (emitted) st_pcm(out[b] + m, v);
                         } else if (keep && m < kLongN2 - ls) {      // the pl = 1024 - 2 ls samples the short block overlaps with
-                            cur[b].state_out[m - ls] = v;
-                            cur[b].state_out[kLongN2 - 1 - ls - m] = v;
+                            cur[b].state[m - ls] = v;
+                            cur[b].state[kLongN2 - 1 - ls - m] = v;
                         }
                     }
                 }
             } else if ((cur[b].flags & 6u) == 2u) {       // write_state and not dummy
-                float *s_lo = cur[b].state_out + lane, *s_hi = cur[b].state_out + 63 - lane;
+                float *s_lo = cur[b].state + lane, *s_hi = cur[b].state + 63 - lane;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const int r64 = 64 * rev3(j);
@@ -1021,7 +1029,7 @@ k_long(const LongRun *__restrict__ runs, uint32_t n_groups, const float *__restr
                 const float *st[NB];
                 uint32_t has[NB];
 #pragma unroll
-                for (int b = 0; b < NB; b++) { st[b] = s_next[b].state; has[b] = s_next[b].has_prev && s_next[b].first_short != 2; }
+                for (int b = 0; b < NB; b++) { st[b] = s_next[b].state; has[b] = s_next[b].has_prev; }
                 fence_proxy_async();
                 issue_state(st, has);
             }
@@ -1184,8 +1192,8 @@ k_long_s(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restr
 
     uint32_t phase_bits = 0, slot_i = 0, c_slot = 0;
     for (uint32_t c_run = gw; c_run < n_runs; c_run += W) {
-        RunCur cur[NB];
-        cur[0] = run_cur(s_desc[c_slot]);
+        RunCurS cur[NB];
+        cur[0] = run_cur_s(s_desc[c_slot]);
         const uint32_t npk = s_desc[c_slot].n_packets;
         const uint32_t my_slot = c_slot;
         c_slot = (c_slot + 1 == (uint32_t)kLongDescSlots) ? 0 : c_slot + 1;
@@ -1248,7 +1256,7 @@ k_long_s(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restr
             if (p_run < n_runs) produce();          // the stage is free again
             phase_c_fft<NB>(tw, O, E);
             if (p > 0) {
-                out_stage<NB, false, OutT>(tw, lane, O, E, pe, cur, out, s_state);
+                out_stage<NB, false, OutT, RunCurS>(tw, lane, O, E, pe, cur, out, s_state);
             } else {
                 if (need_state) {
                     if (st_run != c_run) issue_state(cur[0].state, c_run);  // (its descriptor had not landed when the tile came free)
@@ -1256,9 +1264,9 @@ k_long_s(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restr
                     phase_bits ^= 1u << 30;
                 }
                 if (cur[0].flags & 8u)
-                    out_first_short<NB, OutT>(tw, lane, O, E, pe, cur, out, s_state, w_short, ls);
+                    out_first_short<NB, OutT, RunCurS, true>(tw, lane, O, E, pe, cur, out, s_state, w_short, ls);
                 else
-                    out_stage<NB, true, OutT>(tw, lane, O, E, pe, cur, out, s_state);
+                    out_stage<NB, true, OutT, RunCurS>(tw, lane, O, E, pe, cur, out, s_state);
                 __syncwarp();
                 if (need_state) {                                           // state tile consumed: on to the next run that needs it
                     st_run = ~0u;

@@ -497,10 +497,232 @@ k_short(const ShortRun *__restrict__ runs, uint32_t n_runs, const float *__restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_short_g: bursts.  Between two long blocks a stream has one to a few short blocks; k_short would spend a whole octet
+// iteration on each such run with one or two of its eight block positions occupied.  Here the eight block positions of
+// a warp belong to EIGHT DIFFERENT runs of equal length (a "group"; the host sorts the short runs by length and pads
+// each length class with dummies) which advance in lockstep, one packet per iteration -- so block position b's previous
+// right half is simply its own p_even of the iteration before (registers, no shuffle), or its run's state tile in
+// iteration 0.  Descriptors: 8 ShortRun per group (dummy: in == nullptr).  Same static deal, descriptor ring and
+// producer / consumer stages as k_short; a stage carries the eight state tiles behind the eight spectrum tiles.
+// ---------------------------------------------------------------------------------------------
+constexpr int kShortGRing = 2;
+constexpr int kShortGStageBytes = kShortOct * kShortTileStride + kShortOct * kShortN2 * 4 + 512;     // 4608 + 4096 -> 9216 (1024-aligned)
+constexpr int kShortGFetch = 2;
+constexpr int kShortGDescSlots = kShortGFetch + kShortGRing + 3;
+constexpr size_t kShortGDescBytes = (size_t)kShortOct * sizeof(ShortRun);                                  // 384
+constexpr size_t kShortGSmemBytes = 1024 + (size_t)kShortWarps * kShortGRing * kShortGStageBytes + (size_t)kShortPackFloats * 4 +
+                                    (size_t)kShortWarps * kShortGDescSlots * kShortGDescBytes + kShortWarps * kShortGRing * 8 + 64;
+static_assert(kShortGStageBytes % 1024 == 0, "XOR addressing of the transposes needs 1024-aligned stages");
+
+template <typename OutT>
+__global__ void __launch_bounds__(kShortWarps * 32, 1)
+k_short_g(const ShortRun *__restrict__ runs, uint32_t n_groups, const float *__restrict__ pack)
+{
+    extern __shared__ __align__(128) unsigned char smem_s[];
+    constexpr uint32_t ESZ = sizeof(OutT);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = lane & 3, blk = lane >> 2;
+    const uint32_t raw_s = smem_u32(smem_s);
+    unsigned char *base = smem_s + ((1024u - (raw_s & 1023u)) & 1023u);
+    constexpr size_t kRingBytes = (size_t)kShortWarps * kShortGRing * kShortGStageBytes;
+    unsigned char *ring = base + (size_t)warp * kShortGRing * kShortGStageBytes;
+    V *s_pack = reinterpret_cast<V *>(base + kRingBytes);
+    ShortRun *s_desc = reinterpret_cast<ShortRun *>(base + kRingBytes + (size_t)kShortPackFloats * 4) + warp * kShortGDescSlots * kShortOct;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + kRingBytes + (size_t)kShortPackFloats * 4 +
+                                                  (size_t)kShortWarps * kShortGDescSlots * kShortGDescBytes) + warp * kShortGRing;
+    for (int i = threadIdx.x; i < SP_END * 4; i += blockDim.x)
+        s_pack[i] = reinterpret_cast<const V *>(pack)[(i >> 2) * 32 + (i & 3)];
+    if (lane == 0) {
+        for (int i = 0; i < kShortGRing; i++) mbar_init(smem_u32(&bars[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    V twR[kSTwReg1 - kSTwReg0 > 0 ? kSTwReg1 - kSTwReg0 : 1];
+#pragma unroll
+    for (int s = kSTwReg0; s < kSTwReg1; s++) twR[s - kSTwReg0] = s_pack[s * 4 + l];
+    const TwShort tw{twR, s_pack + l};
+
+    const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars), desc_s = smem_u32(s_desc);
+    const uint32_t wA0 = 4u * (uint32_t)swzS(blk, elemA_s(l, 0, 0)), wA1 = 4u * (uint32_t)swzS(blk, elemA_s(l, 0, 1));
+    const uint32_t wC0 = 4u * (uint32_t)swzS(blk, elemC_s(l, 0, 0)), wC1 = 4u * (uint32_t)swzS(blk, elemC_s(l, 0, 1));
+    const uint32_t wP0 = (128u * ESZ + 4u * ESZ) * (uint32_t)blk + ESZ * (uint32_t)l;
+    const uint32_t wP1 = (128u * ESZ + 4u * ESZ) * (uint32_t)blk + ESZ * (uint32_t)(3 - l);
+    constexpr uint32_t kStateOff = kShortOct * kShortTileStride;               // state tile of block b at + 512 b
+
+    const uint32_t W = gridDim.x * kShortWarps, gw = blockIdx.x * kShortWarps + warp;
+    if (gw >= n_groups) return;
+    const uint4 *rq = reinterpret_cast<const uint4 *>(runs);
+    constexpr uint32_t kQuads = (uint32_t)(kShortGDescBytes / 16);             // 24 quads per group: lanes 0..23 copy one each
+    uint32_t f_grp = gw, f_slot = 0;
+    auto fetch = [&]() {
+        if ((uint32_t)lane < kQuads && f_grp < n_groups)
+            cp_async16(desc_s + f_slot * (uint32_t)kShortGDescBytes + lane * 16, rq + (size_t)kQuads * f_grp + lane);
+        cp_async_commit();
+        f_grp += W;
+        f_slot = (f_slot + 1 == (uint32_t)kShortGDescSlots) ? 0 : f_slot + 1;
+    };
+#pragma unroll
+    for (int i = 0; i <= kShortGFetch; i++) fetch();
+    cp_async_wait<kShortGFetch>();
+    __syncwarp();
+    // ---- producer: iteration p_t of group p_grp; lane b < 8 issues block position b's copies ----
+    uint32_t p_grp = gw, p_t = 0, p_slot = 0, p_stage = 0;
+    auto produce = [&]() {
+        const ShortRun *g = s_desc + p_slot * kShortOct;
+        const uint32_t npk = g[0].n_packets;
+        const bool mine = lane < kShortOct && g[lane & 7].in != nullptr;
+        const bool st = mine && p_t == 0 && g[lane & 7].has_prev;
+        const uint32_t n_tiles = (uint32_t)__popc(__ballot_sync(0xffffffffu, mine)) + (uint32_t)__popc(__ballot_sync(0xffffffffu, st));
+        const uint32_t bar = bars_s + 8 * p_stage, dst = ring_s + p_stage * kShortGStageBytes;
+        if (lane == 0) mbar_expect_tx(bar, n_tiles * (uint32_t)(kShortN2 * 4));
+        __syncwarp();
+        if (mine) {
+            fence_proxy_async();
+            tma_load_1d(dst + lane * kShortTileStride, g[lane].in + (size_t)p_t * g[lane].in_stride, kShortN2 * 4, bar);
+            if (st) tma_load_1d(dst + kStateOff + lane * (kShortN2 * 4), g[lane].state, kShortN2 * 4, bar);
+        }
+        p_stage = (p_stage + 1 == (uint32_t)kShortGRing) ? 0 : p_stage + 1;
+        if (++p_t >= npk) {
+            p_grp += W;
+            p_t = 0;
+            p_slot = (p_slot + 1 == (uint32_t)kShortGDescSlots) ? 0 : p_slot + 1;
+            fetch();
+            cp_async_wait<kShortGFetch>();
+            __syncwarp();
+        }
+    };
+    for (int i = 0; i < kShortGRing; i++)
+        if (p_grp < n_groups) produce();
+
+    uint32_t phase_bits = 0, slot_i = 0, c_slot = 0;
+    for (uint32_t c_grp = gw; c_grp < n_groups; c_grp += W) {
+        const ShortRun *g = s_desc + c_slot * kShortOct;
+        c_slot = (c_slot + 1 == (uint32_t)kShortGDescSlots) ? 0 : c_slot + 1;
+        // (the descriptor slot of the group being consumed is never the target of a fetch: the ring has two slots to spare)
+        const uint32_t npk = g[0].n_packets;
+        const bool valid = g[blk].in != nullptr, has_prev = valid && g[blk].has_prev;
+        uint32_t emit0 = 0;               // bit i: position i emits in iteration 0; bit 8 + i: position i is not a dummy
+#pragma unroll
+        for (int i = 0; i < kShortOct; i++)
+            if (g[i].in != nullptr) emit0 |= (g[i].has_prev ? 1u : 0u) << i | 256u << i;
+        V pe[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) pe[j] = V{0.f, 0.f};
+        for (uint32_t t = 0; t < npk; t++) {
+            const uint32_t stage_s = ring_s + slot_i * kShortGStageBytes;
+            const unsigned char *stage_p = ring + slot_i * kShortGStageBytes;
+            mbar_wait(bars_s + 8 * slot_i, (phase_bits >> slot_i) & 1u);
+            phase_bits ^= 1u << slot_i;
+            V O[8], E[8];
+            phase_a_s(reinterpret_cast<const float *>(stage_p + blk * kShortTileStride), l, tw, O, E);
+            __syncwarp();           // every lane has consumed its quads: the stage becomes the scratch
+            {
+                const uint32_t a0 = stage_s + wA0, a1 = stage_s + wA1;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    sts_eo(((a0 ^ (4u * (j >> 1))) + (j << 8)), E[j].x, O[j].x);
+                    sts_eo(((a1 ^ (4u * (j >> 1))) + (j << 8)), E[j].y, O[j].y);
+                }
+            }
+            __syncwarp();
+            {
+                const uint32_t c0 = stage_s + wC0, c1 = stage_s + wC1;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    lds_eo(((c0 ^ (4u * (j & 3))) + ((j >> 2) << 7)), E[j].x, O[j].x);
+                    lds_eo(((c1 ^ (4u * (j & 3))) + ((j >> 2) << 7)), E[j].y, O[j].y);
+                }
+            }
+            __syncwarp();           // scratch consumed: the same bytes now take the PCM staging
+            phase_c_fft<1>(tw, &O, &E);
+            const uint32_t p0 = stage_s + wP0, p1 = stage_s + wP1;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                V p_odd, lo, hi;
+                V plo = pe[j];                                   // the position's own right half of the iteration before
+                step8_s(tw(P_B0 + j), tw(P_B1 + j), O[j], E[j], p_odd, pe[j]);
+                V phi = plo;
+                if (t == 0 && has_prev) {                        // the run's state tile (an imported state need not be symmetric);
+                    const int mx = outIndex_s(l, j, 0), my = outIndex_s(l, j, 1);      // it lies beyond the scratch / staging bytes
+                    const uint32_t sa = stage_s + kStateOff + (uint32_t)blk * (kShortN2 * 4);
+                    plo = V{lds_f32(sa + 4 * mx), lds_f32(sa + 4 * my)};
+                    phi = V{lds_f32(sa + 4 * (127 - mx)), lds_f32(sa + 4 * (127 - my))};
+                }
+                ola_s(p_odd, tw(P_WLO + j), tw(P_WHI + j), plo, phi, lo, hi);
+                constexpr uint32_t CH = 4u * ESZ;
+                const int r = rev3(j);
+                const uint32_t cA = CH * (2 * r), cB = CH * (2 * r + 1), cC = CH * (31 - 2 * r), cD = CH * (30 - 2 * r);
+                if (j & 1) {
+                    sts_pcm(p0 ^ cA, lo.x, (OutT *)nullptr); sts_pcm(p1 ^ cB, lo.y, (OutT *)nullptr);
+                    sts_pcm(p1 ^ cC, hi.x, (OutT *)nullptr); sts_pcm(p0 ^ cD, hi.y, (OutT *)nullptr);
+                } else {
+                    sts_pcm(p1 ^ cB, lo.x, (OutT *)nullptr); sts_pcm(p0 ^ cA, lo.y, (OutT *)nullptr);
+                    sts_pcm(p0 ^ cD, hi.x, (OutT *)nullptr); sts_pcm(p1 ^ cC, hi.y, (OutT *)nullptr);
+                }
+            }
+            __syncwarp();
+            // one packet per instruction: lane L copies samples [4 L, 4 L + 4) of position i's packet t
+#pragma unroll
+            for (int i = 0; i < kShortOct; i++) {
+                const bool emits = (emit0 >> (8 + i)) & 1u ? (t > 0 || ((emit0 >> i) & 1u)) : false;
+                if (emits) {
+                    const uint32_t koff = ((emit0 >> i) & 1u) ? 0u : 1u;
+                    copy_out4(static_cast<OutT *>(g[i].out) + (size_t)(t - koff) * kShortN2 + 4 * lane,
+                              stage_s + (128u * ESZ) * i + (4u * ESZ) * (uint32_t)(lane ^ i));
+                }
+            }
+            __syncwarp();                                        // staging consumed: the stage is free
+            if (p_grp < n_groups) produce();
+            slot_i = (slot_i + 1 == (uint32_t)kShortGRing) ? 0 : slot_i + 1;
+        }
+        float *end_ptr = g[blk].end_ptr ? g[blk].end_ptr : g[blk].state;
+        if (valid && g[blk].write_state) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int mx = outIndex_s(l, j, 0), my = outIndex_s(l, j, 1);
+                end_ptr[mx] = pe[j].x; end_ptr[my] = pe[j].y;
+                end_ptr[127 - mx] = pe[j].x; end_ptr[127 - my] = pe[j].y;
+            }
+        }
+        if (valid && g[blk].tail) {
+            OutT *on = static_cast<OutT *>(g[blk].out) + (size_t)(npk - (has_prev ? 0u : 1u)) * kShortN2;
+            float cw[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int mx = outIndex_s(l, j, 0), my = outIndex_s(l, j, 1);
+                cw[j][0] = __ldcg(end_ptr + mx); cw[j][1] = __ldcg(end_ptr + my);
+                cw[j][2] = __ldcg(end_ptr + 127 - mx); cw[j][3] = __ldcg(end_ptr + 127 - my);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int mx = outIndex_s(l, j, 0), my = outIndex_s(l, j, 1);
+                const V wlo = tw(P_WLO + j), whi = tw(P_WHI + j);
+                st_pcm(on + mx, __fadd_rn(cw[j][0], __fmul_rn(pe[j].x, whi.x)));
+                st_pcm(on + my, __fadd_rn(cw[j][1], __fmul_rn(pe[j].y, whi.y)));
+                st_pcm(on + 127 - mx, __fadd_rn(cw[j][2], __fmul_rn(pe[j].x, wlo.x)));
+                st_pcm(on + 127 - my, __fadd_rn(cw[j][3], __fmul_rn(pe[j].y, wlo.y)));
+            }
+        }
+    }
+}
+
+inline int short_launch_groups(cudaStream_t stream, const ShortRun *d_runs, uint32_t n_groups, const float *d_pack, int sm_count, bool i16_out)
+{
+    if (!n_groups) return 0;
+    const uint32_t want = (n_groups + kShortWarps - 1) / kShortWarps;
+    const uint32_t grid = want < (uint32_t)sm_count ? want : (uint32_t)sm_count;
+    if (i16_out) k_short_g<int16_t><<<grid, kShortWarps * 32, kShortGSmemBytes, stream>>>(d_runs, n_groups, d_pack);
+    else k_short_g<float><<<grid, kShortWarps * 32, kShortGSmemBytes, stream>>>(d_runs, n_groups, d_pack);
+    return cudaGetLastError() != cudaSuccess;
+}
+
 inline void short_kernel_configure()
 {
     cudaFuncSetAttribute(k_short<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmemBytes);
     cudaFuncSetAttribute(k_short<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortSmemBytes);
+    cudaFuncSetAttribute(k_short_g<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortGSmemBytes);
+    cudaFuncSetAttribute(k_short_g<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShortGSmemBytes);
 }
 
 inline int short_launch(cudaStream_t stream, const ShortRun *d_runs, uint32_t n_runs, const float *d_pack, int sm_count, bool i16_out)

@@ -83,6 +83,11 @@ static int mixed_launch_rounds(lwb_ctx *ctx, const MixLaunch &ml, const std::vec
                 return fail(ctx, LWB_ERR_CUDA, "short kernel launch", cudaGetLastError());
             ctx->launches++;
         }
+        if (rd.ng) {             // bursts: eight short runs of equal length per warp (k_short_g)
+            if (short_launch_groups(sm, (const ShortRun *)(ml.db + ml.off_sg) + rd.g0 * kShortOct, (uint32_t)rd.ng, ml.spack, ctx->sm_count, ml.i16))
+                return fail(ctx, LWB_ERR_CUDA, "short burst kernel launch", cudaGetLastError());
+            ctx->launches++;
+        }
         if (rd.nc) {
             const ChainDesc *dcd = (const ChainDesc *)(ml.db + ml.off_cd) + rd.c0;
             const uint8_t *dby = (const uint8_t *)(ml.db + ml.off_by);
@@ -243,7 +248,7 @@ static int try_chain(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         CU(ctx, cudaEventRecord(st->ev, sm));
         st->pending = true;
         MixLaunch ml;
-        ml.db = (char *)dbuf.p; ml.off_sr = 0; ml.off_cd = 0; ml.off_rc = 0; ml.flat = false; ml.off_by = used_desc; ml.pack = nullptr; ml.spack = nullptr; ml.w_short = nullptr; ml.ls = 0;
+        ml.db = (char *)dbuf.p; ml.off_sr = 0; ml.off_cd = 0; ml.off_rc = 0; ml.off_sg = 0; ml.flat = false; ml.off_by = used_desc; ml.pack = nullptr; ml.spack = nullptr; ml.w_short = nullptr; ml.ls = 0;
         ml.i16 = false; ml.residue = residue; ml.out_format = io->out_format; ml.warps = maxc * wpc; ml.smem = smem;
         ml.n1max = n1max; ml.wpc = wpc; ml.np = np; ml.coeffs = d_coeffs; ml.dense = d_dense; ml.kinds = d_kinds; ml.ys = d_ys; ml.pcm = d_pcm;
         std::vector<MixRound> rounds(1, MixRound{0, 0, 0, 0, 0, n_launch});

@@ -31,6 +31,8 @@ static void balance_static_deal(Run *runs, size_t n, size_t W, std::vector<Run> 
     }
     std::memcpy(runs, tmp.data(), n * sizeof(Run));
 }
+// a group of k_short_g: eight runs of one length (the deal above moves it as a unit)
+struct ShortGroup { ShortRun r[kShortOct]; uint32_t n_packets; };
 
 static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch, bool *handled,
                      lwb_plan *plan = nullptr)
@@ -300,7 +302,9 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             return sg.kind == SEG_LONG ? std::max<uint32_t>(1, std::min(ck.round_cut[r], sg.n / kMinCutRun))
                                        : std::max<uint32_t>(1, std::min(ck.round_cut_s[r], sg.n / kMinCutShort));
         };
-        size_t n_runs = 0, n_sruns = 0, n_cd = 0, n_pro = 0;
+        size_t n_runs = 0, n_sruns = 0, n_cd = 0, n_pro = 0, n_burst = 0;
+        // one pass: short segments of fewer than eight packets go to k_short_g, eight of equal length per warp
+        const bool bursts = flat && !getenv("LWB_NO_BURSTS");
         for (size_t k = 0; k < n_chunks; k++) {
             Chunk &ck = chunks[k];
             ck.i0 = n_chains * k / n_chunks;
@@ -333,7 +337,10 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 for (uint32_t q = 0; q < walks[i].n_seg; q++) {
                     const Seg &sg = segs[walks[i].seg0 + q];
                     if (sg.kind == SEG_LONG) n_runs += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, flat ? 0 : q);
-                    else if (sg.kind == SEG_SHORT) n_sruns += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, flat ? 0 : q);
+                    else if (sg.kind == SEG_SHORT) {
+                        n_sruns += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, flat ? 0 : q);
+                        if (bursts && sg.n < (uint32_t)kShortOct) n_burst += chains[i].stream->setup->channels;
+                    }
                     else n_cd++;
                     if (residue) n_pro += sg.n;
                 }
@@ -343,7 +350,10 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         DevBuf &dbuf = capture ? plan->mix : ctx->cdesc;
         const size_t off_sr = n_runs * sizeof(LongRun), off_cd = off_sr + n_sruns * sizeof(ShortRun), off_pro = off_cd + n_cd * sizeof(ChainDesc);
         const size_t off_rc = off_pro + n_pro * sizeof(DevPacket);
-        const size_t off_by = off_rc + n_rc * sizeof(RowCopy), total = off_by + boff + 16;
+        // burst groups: every length class of every chunk is padded to a multiple of eight runs
+        const size_t sg_cap = n_burst ? n_burst + n_chunks * (size_t)(kShortOct * kShortOct) : 0;
+        const size_t off_sg = (off_rc + n_rc * sizeof(RowCopy) + 15) & ~(size_t)15;
+        const size_t off_by = off_sg + sg_cap * sizeof(ShortRun), total = off_by + boff + 16;
         // boundary slots (device only, not part of the upload); k_long's state copy reads 4 KB wherever it reads
         const size_t off_slots = (total + 511) & ~(size_t)511, slots_bytes = flat ? n_slots * (kShortN2 * 4) + 4096 : 0;
         Staging *st;
@@ -362,7 +372,10 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
         ChainDesc *h_cd = (ChainDesc *)(hb + off_cd);
         DevPacket *h_pro = (DevPacket *)(hb + off_pro);
         RowCopy *h_rc = (RowCopy *)(hb + off_rc);
-        size_t wx = 0;
+        ShortRun *h_sg = (ShortRun *)(hb + off_sg);
+        size_t wx = 0, wg = 0;                      // wg: groups written
+        std::vector<ShortRun> burst_runs;
+        std::vector<ShortGroup> groups, tmp_g;
         std::memcpy(hb + off_by, bytes.data(), boff);
         const float *d_spec = nullptr;
         if (residue) {
@@ -392,13 +405,15 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             }
         };
         for (Chunk &ck : chunks) {
-            ck.rounds.assign(max_rounds, MixRound{0, 0, 0, 0, 0, 0, 0, 0});
+            ck.rounds.assign(max_rounds, MixRound{0, 0, 0, 0, 0, 0, 0, 0, 0, 0});
             ck.p0 = wp;
             for (size_t r = 0; r < max_rounds; r++) {
                 ck.rounds[r].r0 = wr;
                 ck.rounds[r].s0 = ws;
                 ck.rounds[r].c0 = wc;
                 ck.rounds[r].x0 = wx;
+                ck.rounds[r].g0 = wg;
+                burst_runs.clear();
                 // fused-kernel runs first, longest first (three buckets): the kernel hands runs out in
                 // descriptor order, and a 64-packet run started last would be the whole round's tail
                 for (int bucket = 0; bucket < 3; bucket++)
@@ -472,7 +487,9 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                         char *out0 = d_pcm + (c->out_offset + (size_t)ch * c->out_stride + sg.pos) * esz;
                         for (uint32_t k = 0; k < cuts; k++) {
                             const size_t p0 = (size_t)sg.n * k / cuts, p1 = (size_t)sg.n * (k + 1) / cuts;
-                            ShortRun &sr = h_sr[ws++];
+                            const bool burst = bursts && sg.n < (uint32_t)kShortOct;
+                            if (burst) burst_runs.emplace_back();
+                            ShortRun &sr = burst ? burst_runs.back() : h_sr[ws++];
                             std::memset(&sr, 0, sizeof(sr));
                             sr.in_stride = (uint32_t)(C * kShortN2);
                             sr.state = s->d_state + (size_t)ch * state_stride(su);
@@ -531,6 +548,28 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 }
                 ck.rounds[r].nr = wr - ck.rounds[r].r0;
                 ck.rounds[r].ns = ws - ck.rounds[r].s0;
+                if (!burst_runs.empty()) {
+                    // length classes, longest first, each padded with dummies (in == nullptr) to whole groups
+                    groups.clear();
+                    for (uint32_t len = kShortOct; len-- > 1;) {
+                        size_t in_class = 0;
+                        for (const ShortRun &br : burst_runs) {
+                            if (br.n_packets != len) continue;
+                            if (in_class % kShortOct == 0) {
+                                groups.emplace_back();
+                                std::memset(&groups.back(), 0, sizeof(ShortGroup));
+                                groups.back().n_packets = len;
+                                for (int k = 0; k < kShortOct; k++) groups.back().r[k].n_packets = len;
+                            }
+                            groups.back().r[in_class++ % kShortOct] = br;
+                        }
+                    }
+                    const size_t Wg = std::min<size_t>((groups.size() + kShortWarps - 1) / kShortWarps, (size_t)ctx->sm_count) * kShortWarps;
+                    if (!getenv("LWB_NO_BALANCE")) balance_static_deal(groups.data(), groups.size(), Wg, tmp_g);
+                    if ((wg + groups.size()) * kShortOct > sg_cap) return fail(ctx, LWB_ERR_INVALID, "burst group area too small");
+                    for (const ShortGroup &gr : groups) std::memcpy(h_sg + (wg++) * kShortOct, gr.r, sizeof(gr.r));
+                }
+                ck.rounds[r].ng = wg - ck.rounds[r].g0;
                 if (flat && !getenv("LWB_NO_BALANCE")) {
                     auto warps_of = [&](size_t n, int per_cta) {
                         return std::min<size_t>((n + per_cta - 1) / per_cta, (size_t)ctx->sm_count) * per_cta;
@@ -554,13 +593,12 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 CU(ctx, cudaEventCreateWithFlags(&ctx->ev_kdone[k], cudaEventDisableTiming));
             }
         }
-        // k_long's driver in one pass: the static deal (k_long_s) -- it looks further ahead than the tickets, and with the
-        // balanced order it is ahead at every share of short blocks (2 / 10 / 30 %: 0.886 / 1.014 / 1.131 ms against
-        // 0.895 / 1.031 / 1.212 ms, profiles/r2i_mixed.log)
-        bool long_static = flat;
-        if (const char *e = getenv("LWB_LONG_DRIVER")) long_static = flat && e[0] == 's';
+        // k_long's driver in one pass: the static deal (k_long_s, the only one that knows boundary slots) -- it looks
+        // further ahead than the tickets, and with the balanced order it was ahead of them at every share of short blocks
+        // when both could run this schedule (2 / 10 / 30 %: 0.886 / 1.014 / 1.131 ms against 0.895 / 1.031 / 1.212 ms)
+        const bool long_static = flat;
         MixLaunch ml;
-        ml.db = db; ml.off_sr = off_sr; ml.off_cd = off_cd; ml.off_by = off_by; ml.off_rc = off_rc; ml.flat = long_static; ml.pack = pack; ml.spack = spack; ml.w_short = w_short; ml.ls = ls_long;
+        ml.db = db; ml.off_sr = off_sr; ml.off_cd = off_cd; ml.off_by = off_by; ml.off_rc = off_rc; ml.off_sg = off_sg; ml.flat = long_static; ml.pack = pack; ml.spack = spack; ml.w_short = w_short; ml.ls = ls_long;
         ml.i16 = i16; ml.residue = false; ml.out_format = io->out_format; ml.warps = maxc * wpc; ml.smem = smem;
         ml.n1max = n1max; ml.wpc = wpc; ml.np = np; ml.coeffs = residue ? d_spec : d_coeffs; ml.dense = nullptr; ml.kinds = nullptr; ml.ys = nullptr;
         ml.pcm = d_pcm;
