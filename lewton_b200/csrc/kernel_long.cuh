@@ -669,16 +669,28 @@ __device__ __forceinline__ void out_stage(const TwMix &tw, int lane, const V O[N
     }
 }
 
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // Packet 0 of a run that follows a short block (previous_window_flag == 0): the left window slope
 // is the short one, centred in the left half (audio.rs:1059-1065 -> window_left_start = ls =
 // (2048 - n0) / 4), the saved right half is pl = n0 / 2 samples long, and the packet emits
 // x[ls .. 1024): pl windowed samples, then the rest of the left half as is (audio.rs:1112-1120).
 // Rare (once per burst of short blocks), so plain scalar code; w = the short window slope.
-template <int NB, typename OutT, typename RC = RunCur, bool EXPORT = false>
+// EXPORT: k_long_s -- runs may export their left slope (flags bit 5), and the slope is read from its shared-memory copy
+// at w_s (through __ldg from global memory the four products of a lane each waited for an L2 round trip: 3.4 % of
+// k_long_s's stall samples on the 6-channel config)
+// LS: ls as a compile-time constant (0: use the argument) -- with it every position test below folds per slot.
+template <int NB, typename OutT, typename RC = RunCur, bool EXPORT = false, int LS = 0>
 __device__ __forceinline__ void out_first_short(const TwMix &tw, int lane, const V O[NB][8], const V E[NB][8], V pe[NB][8],
                                                 const RC cur[NB], OutT *out[NB], const float *s_state,
-                                                const float *__restrict__ w, int ls)
+                                                const float *__restrict__ w, int ls_arg, uint32_t w_s = 0)
 {
+    const int ls = LS ? LS : ls_arg;
     const int pl = kLongN2 - 2 * ls;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -696,18 +708,22 @@ __device__ __forceinline__ void out_first_short(const TwMix &tw, int lane, const
             for (int h = 0; h < 2; h++) {
                 const float po = h ? p_odd.y : p_odd.x;
                 const int m = r64 + ((h == 0) == nat ? lane : 63 - lane);    // x[m] = p_odd, x[1023 - m] = -p_odd
-                if (m >= ls) {
+                // x[m] lies on the slope iff m >= ls, and so does its mirror image (1023 - m - ls < pl <=> m >= ls); with
+                // a compile-time ls that is a multiple of 64 the test is a property of the slot
+                static_assert(LS % 64 == 0, "LS must be a multiple of 64");
+                const bool on_slope = LS ? (r64 >= LS) : (m >= ls);
+                if (on_slope) {
                     const int i = m - ls;                                      // < pl / 2
-                    const float cw = __fmul_rn(po, __ldg(w + i));
+                    const float cw = __fmul_rn(po, (EXPORT ? lds_f32(w_s + 4u * (uint32_t)i) : __ldg(w + i)));
                     if (exported) cur[b].state[i] = cw;
-                    else st_pcm(out[b] + i, __fadd_rn(cw, __fmul_rn(prev[i], __ldg(w + pl - 1 - i))));
+                    else st_pcm(out[b] + i, __fadd_rn(cw, __fmul_rn(prev[i], (EXPORT ? lds_f32(w_s + 4u * (uint32_t)(pl - 1 - i)) : __ldg(w + pl - 1 - i)))));
                 }
                 const int i = kLongN2 - 1 - m - ls;                            // >= pl / 2
                 float v = -po;
-                if (i < pl) {
-                    v = __fmul_rn(v, __ldg(w + i));
+                if (on_slope) {
+                    v = __fmul_rn(v, (EXPORT ? lds_f32(w_s + 4u * (uint32_t)i) : __ldg(w + i)));
                     if (exported) { cur[b].state[i] = v; continue; }
-                    v = __fadd_rn(v, __fmul_rn(prev[i], __ldg(w + pl - 1 - i)));
+                    v = __fadd_rn(v, __fmul_rn(prev[i], (EXPORT ? lds_f32(w_s + 4u * (uint32_t)(pl - 1 - i)) : __ldg(w + pl - 1 - i))));
                 }
                 st_pcm(out[b] + i, v);
             }
@@ -1083,15 +1099,18 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // ---------------------------------------------------------------------------------------------
 constexpr int kLongFetch = 3;
 constexpr int kLongDescSlots = kLongFetch + kLongRing + 3;
+constexpr int kLongSlopeMax = 512;       // floats of the short window slope kept in shared memory (blocksize_0 <= 1024)
 constexpr size_t kLongSmemBytesS = 2048 + (size_t)kLongWarps * (kLongRing + 1) * kLongTileBytes + (size_t)kLongPackFloats * 4 +
-                                   kLongWarps * (kLongRing + 2) * 8 + (size_t)kLongWarps * kLongDescSlots * sizeof(LongRun) + 64;
+                                   kLongWarps * (kLongRing + 2) * 8 + (size_t)kLongWarps * kLongDescSlots * sizeof(LongRun) +
+                                   kLongSlopeMax * sizeof(float) + 64;
 
-template <typename OutT>
+template <typename OutT, int LS>
 __global__ void __launch_bounds__(kLongWarps * 32, 1)
 k_long_s(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restrict__ pack,
-         const float *__restrict__ w_short, int ls)
+         const float *__restrict__ w_short, int ls_arg)
 {
     constexpr int NB = 1;
+    const int ls = LS ? LS : ls_arg;          // LS = 448: blocksize_0 = 256, the only short size the one-pass schedule has
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t raw_s = smem_u32(smem_raw);
@@ -1105,6 +1124,13 @@ k_long_s(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restr
     unsigned char *tail = base + kTilesBytes + kStateBytes + (size_t)kLongPackFloats * 4;
     LongRun *s_desc = reinterpret_cast<LongRun *>(tail) + warp * kLongDescSlots;               // 16-aligned
     uint64_t *bars = reinterpret_cast<uint64_t *>(tail + (size_t)kLongWarps * kLongDescSlots * sizeof(LongRun)) + warp * (kLongRing + 2);
+    float *s_w = reinterpret_cast<float *>(tail + (size_t)kLongWarps * kLongDescSlots * sizeof(LongRun) + (size_t)kLongWarps * (kLongRing + 2) * 8);
+    {
+        const int pl = kLongN2 - 2 * ls;                     // the short slope: pl floats (0 when no run of the launch needs it)
+        if (w_short)                                         // (pl <= kLongSlopeMax: the host checks)
+            for (int i = threadIdx.x; i < pl && i < kLongSlopeMax; i += blockDim.x) s_w[i] = __ldg(w_short + i);
+    }
+    const uint32_t w_s = smem_u32(s_w);
     {
         const float4 *src = reinterpret_cast<const float4 *>(pack);
         float4 *dst = reinterpret_cast<float4 *>(s_pack);
@@ -1264,7 +1290,7 @@ k_long_s(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restr
                     phase_bits ^= 1u << 30;
                 }
                 if (cur[0].flags & 8u)
-                    out_first_short<NB, OutT, RunCurS, true>(tw, lane, O, E, pe, cur, out, s_state, w_short, ls);
+                    out_first_short<NB, OutT, RunCurS, true, LS>(tw, lane, O, E, pe, cur, out, s_state, w_short, ls, w_s);
                 else
                     out_stage<NB, true, OutT, RunCurS>(tw, lane, O, E, pe, cur, out, s_state);
                 __syncwarp();
@@ -1287,7 +1313,8 @@ k_long_s(const LongRun *__restrict__ runs, uint32_t n_runs, const float *__restr
                 for (int h = 0; h < 2; h++) {
                     const float v = ((j & 1) != 0) == (h == 0) ? pe[0][j].x : pe[0][j].y;
                     const int m = r64 + (h ? 63 - lane : lane);          // x[1024 + m] = x[2047 - m] = v
-                    if (m < ls) {
+                    const bool before = LS ? (r64 < LS) : (m < ls);      // (a multiple of 64: a property of the slot)
+                    if (before) {
                         if (emitted) st_pcm(out[0] + m, v);
                     } else if (keep && m < kLongN2 - ls) {
                         cur[0].state_out[m - ls] = v;
@@ -1314,8 +1341,14 @@ inline int long_launch_static(cudaStream_t stream, const LongRun *d_runs, uint32
     if (!n_runs) return 0;
     const uint32_t want = (n_runs + kLongWarps - 1) / kLongWarps;
     const uint32_t grid = want < (uint32_t)sm_count ? want : (uint32_t)sm_count;
-    if (i16_out) k_long_s<int16_t><<<grid, kLongWarps * 32, kLongSmemBytesS, stream>>>(d_runs, n_runs, d_pack, d_w_short, ls);
-    else k_long_s<float><<<grid, kLongWarps * 32, kLongSmemBytesS, stream>>>(d_runs, n_runs, d_pack, d_w_short, ls);
+    constexpr int kLs256 = (kLongN - 256) / 4;
+    if (ls == kLs256) {
+        if (i16_out) k_long_s<int16_t, kLs256><<<grid, kLongWarps * 32, kLongSmemBytesS, stream>>>(d_runs, n_runs, d_pack, d_w_short, ls);
+        else k_long_s<float, kLs256><<<grid, kLongWarps * 32, kLongSmemBytesS, stream>>>(d_runs, n_runs, d_pack, d_w_short, ls);
+    } else {
+        if (i16_out) k_long_s<int16_t, 0><<<grid, kLongWarps * 32, kLongSmemBytesS, stream>>>(d_runs, n_runs, d_pack, d_w_short, ls);
+        else k_long_s<float, 0><<<grid, kLongWarps * 32, kLongSmemBytesS, stream>>>(d_runs, n_runs, d_pack, d_w_short, ls);
+    }
     return cudaGetLastError() != cudaSuccess;
 }
 
@@ -1323,8 +1356,10 @@ inline void long_kernel_configure()
 {
     cudaFuncSetAttribute(k_long<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes);
     cudaFuncSetAttribute(k_long<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes);
-    cudaFuncSetAttribute(k_long_s<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytesS);
-    cudaFuncSetAttribute(k_long_s<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytesS);
+    cudaFuncSetAttribute(k_long_s<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytesS);
+    cudaFuncSetAttribute(k_long_s<int16_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytesS);
+    cudaFuncSetAttribute(k_long_s<float, (kLongN - 256) / 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytesS);
+    cudaFuncSetAttribute(k_long_s<int16_t, (kLongN - 256) / 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytesS);
 }
 
 // d_runs: n_groups * kLongNB descriptors.  Returns 0 on success; `ticket` must point at a zeroed

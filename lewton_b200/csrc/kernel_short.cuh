@@ -231,12 +231,6 @@ struct TwShort {
     }
 };
 
-__device__ __forceinline__ float lds_f32(uint32_t addr)
-{
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-    return v;
-}
 // PCM staging: one sample as OutT (samples.rs:86-103)
 __device__ __forceinline__ void sts_pcm(uint32_t addr, float v, float *) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_pcm(uint32_t addr, float v, int16_t *)
