@@ -1097,6 +1097,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   * the state row of the next run that overlaps with one (has_prev, not exported) is requested as soon as the
 //     state tile is free and that run's descriptor has landed.
 // ---------------------------------------------------------------------------------------------
+constexpr int kLongLs256 = (kLongN - 256) / 4;      // ls of a long block next to a 256-point block
 constexpr int kLongFetch = 3;
 constexpr int kLongDescSlots = kLongFetch + kLongRing + 3;
 constexpr int kLongSlopeMax = 512;       // floats of the short window slope kept in shared memory (blocksize_0 <= 1024)
@@ -1341,14 +1342,11 @@ inline int long_launch_static(cudaStream_t stream, const LongRun *d_runs, uint32
     if (!n_runs) return 0;
     const uint32_t want = (n_runs + kLongWarps - 1) / kLongWarps;
     const uint32_t grid = want < (uint32_t)sm_count ? want : (uint32_t)sm_count;
-    constexpr int kLs256 = (kLongN - 256) / 4;
-    if (ls == kLs256) {
-        if (i16_out) k_long_s<int16_t, kLs256><<<grid, kLongWarps * 32, kLongSmemBytesS, stream>>>(d_runs, n_runs, d_pack, d_w_short, ls);
-        else k_long_s<float, kLs256><<<grid, kLongWarps * 32, kLongSmemBytesS, stream>>>(d_runs, n_runs, d_pack, d_w_short, ls);
-    } else {
-        if (i16_out) k_long_s<int16_t, 0><<<grid, kLongWarps * 32, kLongSmemBytesS, stream>>>(d_runs, n_runs, d_pack, d_w_short, ls);
-        else k_long_s<float, 0><<<grid, kLongWarps * 32, kLongSmemBytesS, stream>>>(d_runs, n_runs, d_pack, d_w_short, ls);
-    }
+    // only blocksize_0 = 256 is instantiated: it is the one short size the one-pass schedule exists for (k_short), and
+    // the runtime-ls variant of this kernel makes ptxas 12.9 crash
+    if (ls != kLongLs256) return 1;
+    if (i16_out) k_long_s<int16_t, kLongLs256><<<grid, kLongWarps * 32, kLongSmemBytesS, stream>>>(d_runs, n_runs, d_pack, d_w_short, ls);
+    else k_long_s<float, kLongLs256><<<grid, kLongWarps * 32, kLongSmemBytesS, stream>>>(d_runs, n_runs, d_pack, d_w_short, ls);
     return cudaGetLastError() != cudaSuccess;
 }
 
@@ -1356,10 +1354,8 @@ inline void long_kernel_configure()
 {
     cudaFuncSetAttribute(k_long<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes);
     cudaFuncSetAttribute(k_long<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytes);
-    cudaFuncSetAttribute(k_long_s<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytesS);
-    cudaFuncSetAttribute(k_long_s<int16_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytesS);
-    cudaFuncSetAttribute(k_long_s<float, (kLongN - 256) / 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytesS);
-    cudaFuncSetAttribute(k_long_s<int16_t, (kLongN - 256) / 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytesS);
+    cudaFuncSetAttribute(k_long_s<float, kLongLs256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytesS);
+    cudaFuncSetAttribute(k_long_s<int16_t, kLongLs256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemBytesS);
 }
 
 // d_runs: n_groups * kLongNB descriptors.  Returns 0 on success; `ticket` must point at a zeroed

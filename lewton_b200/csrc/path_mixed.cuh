@@ -207,7 +207,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
     // So k_long runs ONCE over all long segments -- a run that follows a short block leaves its product in a
     // boundary slot (LongRun::first_short == 2), a run that precedes one leaves its raw right half in another --
     // and k_short then runs ONCE over all short segments, reading the one and completing the other (ShortRun::tail).
-    bool flat = max_rounds > 1 && !getenv("LWB_MIXED_ROUNDS");
+    bool flat = max_rounds > 1 && !getenv("LWB_MIXED_ROUNDS") && ls_long == kLongLs256;      // (k_long_s exists for blocksize_0 = 256)
     size_t n_slots = 1;                                   // boundary slots of 128 floats: (boundary, channel); slot 0 unused
     for (size_t i = 0; i < n_chains && flat; i++) {
         const Walk &w = walks[i];
