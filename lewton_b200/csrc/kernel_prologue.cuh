@@ -233,14 +233,15 @@ k_prologue_fused(const DevPacket *__restrict__ pkts, uint32_t n_pk, const float 
         struct Head { int n2, nsteps, k0, k1, c0, c1; bool swapped; uint64_t base; };
         const int row_q2 = C * row_q;                                 // quads of one table buffer
         unsigned char *bufs[2] = {pf_smem, pf_smem + (size_t)C * rowb};
+        const uint32_t bufs_s[2] = {smem_u32(bufs[0]), smem_u32(bufs[1])};
         auto prefetch = [&](uint32_t pk, int b, Head &h, float4 &a0, float4 &a1) {
             const DevPacket &p = pkts[pk];
             const size_t row0 = (size_t)pk * C;
-            for (int i = tid; i < row_q2; i += kPfThreads) {
-                const int c = i / row_q, j = i - c * row_q;
+            for (int i = tid; i < row_q2; i += kPfThreads) {        // (one pass: <= 2 rows of <= 109 quads)
+                const int c = i >= row_q ? 1 : 0, j = i - (c ? row_q : 0);
                 const void *src = j < tab_q ? (const void *)(segtab + (row0 + c) * kSegStride + j)
                                             : (const void *)(reinterpret_cast<const uint4 *>(seg_index + (row0 + c) * ixs) + (j - tab_q));
-                cp_async16(smem_u32(bufs[b]) + 16u * (uint32_t)i, src);
+                cp_async16(bufs_s[b] + 16u * (uint32_t)i, src);
             }
             cp_async_commit();
             const DevSetup &su = *p.setup;
