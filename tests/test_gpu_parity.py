@@ -835,6 +835,76 @@ def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle
             assert np.array_equal(outs[("mixed", batch)].view(np.uint8), outs[(name, batch)].view(np.uint8)), name
 
 
+@pytest.mark.parametrize("fmt,seed,p_bad", [(cabi.OUT_F32_PLANAR, 300, 0.0), (cabi.OUT_I16_PLANAR, 301, 0.0),
+                                            (cabi.OUT_F32_PLANAR, 302, 0.08), (cabi.OUT_I16_PLANAR, 303, 0.3)])
+def test_segmented_paths_agree_with_chain_kernel_on_arbitrary_flags(ctx, fmt, seed, p_bad):
+    """Differential: whatever the caller passes as previous / next window flags -- consistent with the neighbouring
+    packets or not -- and wherever a chain stops on a bad mode number, the segmented schedules (one pass where every
+    chain alternates cleanly between long and short segments, rounds as soon as one does not) must produce the same
+    bytes, statuses, sample counts and end states as the chain kernel alone.  p_bad = 0: consistent flags (all chains
+    take the one-pass schedule); otherwise that share of the flags is flipped and a few mode numbers are invalid.
+    Three consecutive batches, so every schedule starts from every kind of state the others left."""
+    rng = np.random.default_rng(seed)
+    S, P, C = 96, 20, 2
+    modes = [(0, 0), (1, 0)]
+    su = make_setup(ctx, C, 8, 11, modes=modes)
+    f32 = fmt == cabi.OUT_F32_PLANAR
+    dt = np.float32 if f32 else np.int16
+    batches = []
+    for b in range(3):
+        seqs = []
+        for s in range(S):
+            bf, prev, nxt = mode_sequence(rng, P, p_short=float(rng.choice([0.1, 0.3, 0.6])))
+            mode_ids = bf.astype(np.uint8)
+            if p_bad:
+                flip = rng.random(P) < p_bad
+                prev = np.where(flip, 1 - prev, prev).astype(np.uint8)
+                flip = rng.random(P) < p_bad
+                nxt = np.where(flip, 1 - nxt, nxt).astype(np.uint8)
+                if rng.random() < 0.2:
+                    mode_ids[int(rng.integers(0, P))] = 7             # no such mode: the chain stops there
+            seqs.append((mode_ids, prev, nxt))
+        n_coeff = sum(int(sum(C * (1024 if m == 1 else 128) for m in sq[0])) for sq in seqs)
+        batches.append((seqs, (rng.standard_normal(n_coeff) * 0.1).astype(np.float32)))
+    results = {}
+    for name, env in (("segmented", None), ("rounds", {"LWB_MIXED_ROUNDS": "1"}), ("chain", {"LWB_NO_MIXED": "1"})):
+        pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+        log = []
+        if env:
+            os.environ.update(env)
+        try:
+            for seqs, coeffs in batches:
+                chains, coeff_off = [], 0
+                stride = P * 1536          # (a long block in front of a short one emits up to 1472 samples)
+                for s in range(S):
+                    mode_ids, prev, nxt = seqs[s]
+                    chains.append(L.ChainSpec(pwrs[s], mode_ids, prev, nxt, coeff_offset=coeff_off, out_offset=s * C * stride,
+                                              out_stride=stride))
+                    coeff_off += int(sum(C * (1024 if m == 1 else 128) for m in mode_ids))
+                pcm = np.zeros(S * C * stride, dt)
+                L.decode_chains(ctx, chains, cabi.ENTRY_SPECTRUM, cabi.MEM_HOST, coeffs, pcm, fmt)
+                rows = pcm.reshape(S, C, stride)
+                log.append(([(c.status, c.n_samples, c.packets_done) for c in chains],
+                            [rows[s, :, :chains[s].n_samples].copy() for s in range(S)],
+                            [None if p.is_empty() else p.data().copy() for p in pwrs]))
+        finally:
+            if env:
+                for k in env:
+                    del os.environ[k]
+        results[name] = log
+    for name in ("segmented", "rounds"):
+        for b in range(3):
+            st_a, pcm_a, pw_a = results[name][b]
+            st_c, pcm_c, pw_c = results["chain"][b]
+            assert st_a == st_c, (name, b)
+            for s in range(S):
+                assert np.array_equal(pcm_a[s].view(np.uint8), pcm_c[s].view(np.uint8)), (name, b, s)
+                assert (pw_a[s] is None) == (pw_c[s] is None), (name, b, s)
+                assert pw_a[s] is None or bits_equal(pw_a[s], pw_c[s]), (name, b, s)
+    if not p_bad:
+        assert all(st == 0 for st, _, _ in results["segmented"][0][0])
+
+
 @pytest.mark.parametrize("fmt,bursts,p_short", [(cabi.OUT_F32_PLANAR, True, 0.3), (cabi.OUT_I16_PLANAR, True, 0.5),
                                                (cabi.OUT_F32_PLANAR, False, 0.3), (cabi.OUT_F32_PLANAR, True, 0.08)])
 def test_one_pass_schedule_many_runs_per_warp(ctx, oracle, fmt, bursts, p_short):
