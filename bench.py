@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--strong-streams", type=int, default=4096,
                     help="BASELINE.json configs[3]: this many stereo streams in TOTAL, sharded over the ranks (0 = skip)")
     ap.add_argument("--strong-packets", type=int, default=64)
+    ap.add_argument("--mixed-streams", type=int, default=2048,
+                    help="streams per GPU of the mixed short/long measurement (0: skip)")
     ap.add_argument("--sustained-sec", type=float, default=1.0)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -358,6 +360,57 @@ def main():
             p_.close()
         del s_spec, s_pcm
 
+    # ---- mixed 256/2048 streams (the shape of every 44.1 / 48 kHz Vorbis file): 10 % short blocks in bursts between the
+    # long runs, spectrum entry, device-resident; the one-pass schedule of path_mixed.cuh (k_long_s + k_short / k_short_g)
+    mixed = None
+    if args.mixed_streams:
+        Sm, Pm, p_short = args.mixed_streams, 64, 0.10
+        rng_m = np.random.default_rng(7 + rank)
+        m_seqs, m_offs, c_off = [], [], 0
+        for s_ in range(Sm):
+            bf = (rng_m.random(Pm) >= p_short).astype(np.uint8)
+            bf[0] = bf[-1] = 1                        # the same packets every step on top of the last step's state
+            prev, nxt = np.ones(Pm, np.uint8), np.ones(Pm, np.uint8)
+            for i in range(Pm):
+                if bf[i]:
+                    prev[i] = bf[i - 1] if i else 1
+                    nxt[i] = bf[i + 1] if i + 1 < Pm else 1
+            m_seqs.append((bf, prev, nxt))
+            m_offs.append(c_off)
+            c_off += int(sum(C * (N2 if b else 128) for b in bf))
+        m_spec = torch.randn(c_off, generator=gen, device="cuda", dtype=torch.float32) * 1e-2
+        m_pcm = torch.empty(Sm * C * Pm * N2, device="cuda", dtype=torch.float32)
+        m_pwrs = [L.PreviousWindowRight(su) for _ in range(Sm)]
+        m_chains = [L.ChainSpec(m_pwrs[s_], m_seqs[s_][0], m_seqs[s_][1], m_seqs[s_][2], coeff_offset=m_offs[s_],
+                                out_offset=s_ * C * Pm * N2, out_stride=Pm * N2) for s_ in range(Sm)]
+        m_batch = L.Batch(ctx, m_chains, cabi.ENTRY_SPECTRUM, cabi.MEM_DEVICE, m_spec.data_ptr(), m_pcm.data_ptr(),
+                          cabi.OUT_F32_PLANAR)
+        for _ in range(max(args.warmup, 3)):
+            m_batch.run()
+        barrier()
+        launches_m0 = ctx.launch_count
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record(stream)
+        for _ in range(args.steps):
+            m_batch.run()
+        m1.record(stream)
+        barrier()
+        tm = torch.tensor([m0.elapsed_time(m1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        m_ms = float(tm.item()) / args.steps
+        m_samples = c_off            # steady state: every packet emits n/2 samples per channel, i.e. one per coefficient
+        mixed = {"value": m_samples * world / (m_ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": m_ms,
+                 "streams_per_gpu": Sm, "packets_per_stream": Pm, "short_block_share": p_short,
+                 "launches_per_step": (ctx.launch_count - launches_m0) / args.steps,
+                 "achieved_gbs": m_samples * 8 / (m_ms * 1e-3) / 1e9,
+                 "workload": "stereo 256/2048 streams, bursts of short blocks between long runs, spectrum entry, f32 planar, "
+                             "device-resident, state carried from step to step"}
+        m_batch.close()
+        for p_ in m_pwrs:
+            p_.close()
+        del m_spec, m_pcm
+
     # ---- e2e: host (pinned) buffers through the same call --------------------------------------
     Se = min(args.e2e_streams, S)
     h_spec = np.ctypeslib.as_array((np.ctypeslib.ctypes.c_float * (Se * P * C * N2)).from_address(
@@ -389,6 +442,8 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
+        if mixed:
+            mixed["frac_of_hbm_peak"] = mixed["achieved_gbs"] / peak
         per_gpu = value / world
         achieved = per_gpu * ALG_BYTES_PER_SAMPLE / 1e9
         traffic, traffic_src = ncu_traffic(S, P)
@@ -410,7 +465,7 @@ def main():
                 "e2e": {"value": e2e_value / 1e6, "unit": "Msamples/s",
                         "h2d_bytes_per_step": Se * P * C * N2 * 4, "d2h_bytes_per_step": Se * C * stride * 4,
                         "streams": Se, "steps": e_steps, "timer": "host wall clock around synchronous calls"},
-                "sustained": sustained, "strong_scaling": strong, "with_gather": with_gather,
+                "sustained": sustained, "strong_scaling": strong, "with_gather": with_gather, "mixed_streams": mixed,
                 "gpu_launches": int(launches), "host_enqueue_us_per_step": host_us, "clocks": clocks,
                 "host_binding": {"numa_node": int(numa), "cpus": len(os.sched_getaffinity(0)),
                                  "how": "lwb_bind_host_to_device: CPU affinity + preferred memory node of the GPU's PCIe root"}}

@@ -35,6 +35,17 @@ def check_no_fma(so=SO):
     return len(bad)
 
 
+def hot_kernel_registers(log):
+    """Registers per thread of k_long<float> / k_long<int16_t> from ptxas -v output.  The headline kernel is bound by
+    per-warp latency and touchy about its allocation: at 254-255 registers (two more live values, or a changed helper
+    template that only its sibling k_long_s uses) it lost 3-4 % (A/B on one box); 250 / 252 is the
+    allocation the measured numbers belong to."""
+    regs = {}
+    for m in re.finditer(r"Compiling entry function '(_ZN3lwb6k_longI([fs])EE[^']*)'.*?Used (\d+) registers", log, re.S):
+        regs["k_long<float>" if m.group(2) == "f" else "k_long<int16_t>"] = int(m.group(3))
+    return regs
+
+
 def build(force=False, verbose=False):
     if force or _stale():
         if shutil.which("nvcc") is None:
@@ -45,6 +56,10 @@ def build(force=False, verbose=False):
             print(r.stderr)
         if r.returncode:
             raise RuntimeError("nvcc build of liblewton_b200.so failed")
+        regs = hot_kernel_registers(r.stdout + r.stderr)
+        if any(v > 252 for v in regs.values()):
+            print(f"lewton_b200 build: WARNING: {regs} -- k_long above 252 registers has measured 3-4 % slower; "
+                  "look at what changed in kernel_long.cuh's shared helpers")
         n = check_no_fma()
         if n:
             os.remove(SO)

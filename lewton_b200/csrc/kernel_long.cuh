@@ -720,7 +720,7 @@ __device__ __forceinline__ void out_first_short(const TwMix &tw, int lane, const
                 }
                 const int i = kLongN2 - 1 - m - ls;                            // >= pl / 2
                 float v = -po;
-                if (on_slope) {
+                if (LS ? on_slope : (i < pl)) {
                     v = __fmul_rn(v, (EXPORT ? lds_f32(w_s + 4u * (uint32_t)i) : __ldg(w + i)));
                     if (exported) { cur[b].state[i] = v; continue; }
                     v = __fadd_rn(v, __fmul_rn(prev[i], (EXPORT ? lds_f32(w_s + 4u * (uint32_t)(pl - 1 - i)) : __ldg(w + pl - 1 - i))));
