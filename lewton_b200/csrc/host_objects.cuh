@@ -65,7 +65,8 @@ struct lwb_setup {
     std::vector<DevMapping> mappings;   // host copy (validation)
 };
 
-struct MixRound { size_t r0, nr, s0, ns, c0, nc, x0, nx, g0, ng; };   // LongRun / ShortRun / ChainDesc / RowCopy / burst-group ranges of one round
+struct MixRound { size_t r0, nr, s0, ns, c0, nc, x0, nx, g0, ng, flat; };   // LongRun / ShortRun / ChainDesc / RowCopy / burst-group ranges of one
+                                                                            // round; flat: the one-pass round (static deal, k_long_s)
 struct RowCopy { const float *src; float *dst; uint32_t n4, pad; };  // n4 float4s, copied in front of the round's kernels
 struct MixLaunch {
     char *db; size_t off_sr, off_cd, off_by, off_rc, off_sg;

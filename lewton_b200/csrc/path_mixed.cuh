@@ -207,20 +207,42 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
     // So k_long runs ONCE over all long segments -- a run that follows a short block leaves its product in a
     // boundary slot (LongRun::first_short == 2), a run that precedes one leaves its raw right half in another --
     // and k_short then runs ONCE over all short segments, reading the one and completing the other (ShortRun::tail).
-    bool flat = max_rounds > 1 && !getenv("LWB_MIXED_ROUNDS") && ls_long == kLongLs256;      // (k_long_s exists for blocksize_0 = 256)
+    // Per chain: chains that are not such an alternation (a segment for the chain kernel, inconsistent window flags)
+    // keep the rounds -- round r + 1 = their segment r -- behind the pass (round 0) of all the others.
+    const bool flat_enabled = max_rounds > 1 && !getenv("LWB_MIXED_ROUNDS") && ls_long == kLongLs256;   // (k_long_s exists for blocksize_0 = 256)
+    std::vector<uint8_t> chain_flat(n_chains, 0);
+    bool flat = false;                                    // some chain takes the pass
     size_t n_slots = 1;                                   // boundary slots of 128 floats: (boundary, channel); slot 0 unused
-    for (size_t i = 0; i < n_chains && flat; i++) {
+    size_t rounds_rest = 0;                               // rounds of the chains that do not
+    for (size_t i = 0; i < n_chains; i++) {
         const Walk &w = walks[i];
-        for (uint32_t q = 0; q < w.n_seg && flat; q++) {
+        bool ok = flat_enabled && w.n_seg > 0;
+        for (uint32_t q = 0; q < w.n_seg && ok; q++) {
             const Seg &sg = segs[w.seg0 + q];
-            if (sg.kind == SEG_CHAIN) flat = false;
-            else if (q && sg.kind == segs[w.seg0 + q - 1].kind) flat = false;
-            else if (sg.kind == SEG_LONG && ((q && !sg.first_short) || (q + 1 < w.n_seg && !sg.last_short))) flat = false;
+            if (sg.kind == SEG_CHAIN) ok = false;
+            else if (q && sg.kind == segs[w.seg0 + q - 1].kind) ok = false;
+            else if (sg.kind == SEG_LONG && ((q && !sg.first_short) || (q + 1 < w.n_seg && !sg.last_short))) ok = false;
+        }
+        chain_flat[i] = ok;
+        if (ok) flat = true;
+        else rounds_rest = std::max<size_t>(rounds_rest, w.n_seg);
+    }
+    // the pass costs three or four launches of its own: not worth it beside the rounds of a batch that is mostly unclean
+    {
+        size_t pk_flat = 0, pk_all = 0;
+        for (size_t i = 0; i < n_chains; i++) {
+            pk_all += chains[i].packets_done;
+            if (chain_flat[i]) pk_flat += chains[i].packets_done;
+        }
+        if (!flat_enabled || pk_flat * 2 < pk_all) {
+            std::fill(chain_flat.begin(), chain_flat.end(), 0);
+            flat = false;
         }
     }
+    const size_t round_base = flat ? 1 : 0;               // first round of the chains outside the pass
     // The stream's state row is read by the chain's first segment and written by its last, which now run in no
     // particular order: the old state is moved to slots first (k_row_copy) and the first segment reads those.
-    auto needs_precopy = [&](size_t i) { return flat && walks[i].n_seg > 1 && segs[walks[i].seg0].has; };
+    auto needs_precopy = [&](size_t i) { return chain_flat[i] && walks[i].n_seg > 1 && segs[walks[i].seg0].has; };
     auto pre_units = [&](size_t i) {         // slots per channel: a long block on top of a long one overlaps in 1024 samples
         const Seg &sg = segs[walks[i].seg0];
         return (size_t)(sg.kind == SEG_LONG && !sg.first_short ? kLongN2 / kShortN2 : 1);
@@ -228,18 +250,24 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
     size_t n_rc = 0;
     if (flat) {
         for (size_t i = 0; i < n_chains; i++) {
+            if (!chain_flat[i]) continue;
             const unsigned C = chains[i].stream->setup->channels;
             walks[i].slot0 = n_slots;
             if (walks[i].n_seg > 1) n_slots += (size_t)(walks[i].n_seg - 1) * C;
             if (needs_precopy(i)) { n_slots += C * pre_units(i); n_rc += C; }       // behind the chain's boundary slots
         }
-        max_rounds = 1;
+        max_rounds = round_base + rounds_rest;
     }
-    // segments of chain i that round r launches: all of them in one pass, else the r-th
+    // segments of chain i that round r launches: all of them in round 0 for a chain in the pass, else segment r - round_base
     auto seg_range = [&](size_t i, size_t r, uint32_t *q0, uint32_t *q1) {
-        if (flat) { *q0 = 0; *q1 = walks[i].n_seg; }
-        else { *q0 = (uint32_t)std::min<size_t>(r, walks[i].n_seg); *q1 = (uint32_t)std::min<size_t>(r + 1, walks[i].n_seg); }
+        if (chain_flat[i]) { *q0 = 0; *q1 = r == 0 ? walks[i].n_seg : 0; }
+        else if (r < round_base) { *q0 = *q1 = 0; }
+        else {
+            *q0 = (uint32_t)std::min<size_t>(r - round_base, walks[i].n_seg);
+            *q1 = (uint32_t)std::min<size_t>(r - round_base + 1, walks[i].n_seg);
+        }
     };
+    auto round_of = [&](size_t i, uint32_t q) { return chain_flat[i] ? (size_t)0 : round_base + q; };
     const int n1max_all = n1max;         // largest blocksize of the batch (front stages); n1max below sizes the chain kernel
     if (!chain_sees_long) n1max = n0max;
     int wpc = std::max(1, std::min(8, n1max / 1024));
@@ -315,8 +343,8 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             for (size_t i = ck.i0; i < ck.i1; i++) {
                 const unsigned C = chains[i].stream->setup->channels;
                 for (uint32_t q = 0; q < walks[i].n_seg; q++) {
-                    if (segs[walks[i].seg0 + q].kind == SEG_LONG) round_long[flat ? 0 : q] += C;
-                    if (segs[walks[i].seg0 + q].kind == SEG_SHORT) round_short[flat ? 0 : q] += C;
+                    if (segs[walks[i].seg0 + q].kind == SEG_LONG) round_long[round_of(i, q)] += C;
+                    if (segs[walks[i].seg0 + q].kind == SEG_SHORT) round_short[round_of(i, q)] += C;
                 }
                 if (!walks[i].n_seg) continue;
                 ck.kc_lo = std::min(ck.kc_lo, chains[i].coeff_offset);
@@ -336,10 +364,10 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             for (size_t i = ck.i0; i < ck.i1; i++)
                 for (uint32_t q = 0; q < walks[i].n_seg; q++) {
                     const Seg &sg = segs[walks[i].seg0 + q];
-                    if (sg.kind == SEG_LONG) n_runs += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, flat ? 0 : q);
+                    if (sg.kind == SEG_LONG) n_runs += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, round_of(i, q));
                     else if (sg.kind == SEG_SHORT) {
-                        n_sruns += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, flat ? 0 : q);
-                        if (bursts && sg.n < (uint32_t)kShortOct) n_burst += chains[i].stream->setup->channels;
+                        n_sruns += (size_t)chains[i].stream->setup->channels * cuts_of(ck, sg, round_of(i, q));
+                        if (bursts && chain_flat[i] && sg.n < (uint32_t)kShortOct) n_burst += chains[i].stream->setup->channels;
                     }
                     else n_cd++;
                     if (residue) n_pro += sg.n;
@@ -405,7 +433,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
             }
         };
         for (Chunk &ck : chunks) {
-            ck.rounds.assign(max_rounds, MixRound{0, 0, 0, 0, 0, 0, 0, 0, 0, 0});
+            ck.rounds.assign(max_rounds, MixRound{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0});
             ck.p0 = wp;
             for (size_t r = 0; r < max_rounds; r++) {
                 ck.rounds[r].r0 = wr;
@@ -442,14 +470,14 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                                 lr.state = s->d_state + (size_t)ch * state_stride(su);
                                 lr.write_state = (k + 1 == cuts);
                                 lr.last_short = (k + 1 == cuts) && sg.last_short;
-                                if (flat && k + 1 == cuts && q + 1 < walks[i].n_seg) lr.state_out = slot_of(i, q, C, ch);
+                                if (chain_flat[i] && k + 1 == cuts && q + 1 < walks[i].n_seg) lr.state_out = slot_of(i, q, C, ch);
                                 if (k == 0) {
                                     lr.in = in0;
                                     lr.out = out0;
                                     lr.n_packets = (uint32_t)(p1 - p0);
                                     lr.has_prev = sg.has;
                                     lr.first_short = sg.first_short;
-                                    if (flat && q) {            // the short segment in front runs later and completes the overlap
+                                    if (chain_flat[i] && q) {   // the short segment in front runs later and completes the overlap
                                         lr.first_short = 2;
                                         lr.state_out = lr.state_out ? lr.state_out : lr.state;
                                         lr.state = slot_of(i, q - 1, C, ch);
@@ -487,14 +515,14 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                         char *out0 = d_pcm + (c->out_offset + (size_t)ch * c->out_stride + sg.pos) * esz;
                         for (uint32_t k = 0; k < cuts; k++) {
                             const size_t p0 = (size_t)sg.n * k / cuts, p1 = (size_t)sg.n * (k + 1) / cuts;
-                            const bool burst = bursts && sg.n < (uint32_t)kShortOct;
+                            const bool burst = bursts && chain_flat[i] && sg.n < (uint32_t)kShortOct;
                             if (burst) burst_runs.emplace_back();
                             ShortRun &sr = burst ? burst_runs.back() : h_sr[ws++];
                             std::memset(&sr, 0, sizeof(sr));
                             sr.in_stride = (uint32_t)(C * kShortN2);
                             sr.state = s->d_state + (size_t)ch * state_stride(su);
                             sr.write_state = (k + 1 == cuts);
-                            if (flat && k + 1 == cuts && q + 1 < walks[i].n_seg) {      // the long block behind has run already
+                            if (chain_flat[i] && k + 1 == cuts && q + 1 < walks[i].n_seg) {      // the long block behind has run already
                                 sr.write_state = 0;
                                 sr.tail = 1;
                                 sr.end_ptr = slot_of(i, q, C, ch);
@@ -504,7 +532,7 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                                 sr.out = out0;
                                 sr.n_packets = (uint32_t)(p1 - p0);
                                 sr.has_prev = sg.has;
-                                if (flat && q) {                // the long segment in front left its right half in the slot
+                                if (chain_flat[i] && q) {       // the long segment in front left its right half in the slot
                                     if (!sr.end_ptr) sr.end_ptr = sr.state;
                                     sr.state = slot_of(i, q - 1, C, ch);
                                 } else if (needs_precopy(i)) {
@@ -524,8 +552,10 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                   }
                 }
                 for (size_t i = ck.i0; i < ck.i1; i++) {
-                    if (flat || r >= walks[i].n_seg) continue;
-                    const Seg &sg = segs[walks[i].seg0 + r];
+                    uint32_t q0, q1;
+                    seg_range(i, r, &q0, &q1);
+                    if (q0 >= q1) continue;
+                    const Seg &sg = segs[walks[i].seg0 + q0];
                     if (sg.kind != SEG_CHAIN) continue;
                     const lwb_chain *c = &chains[i];
                     const lwb_stream *s = c->stream;
@@ -570,7 +600,8 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                     for (const ShortGroup &gr : groups) std::memcpy(h_sg + (wg++) * kShortOct, gr.r, sizeof(gr.r));
                 }
                 ck.rounds[r].ng = wg - ck.rounds[r].g0;
-                if (flat && !getenv("LWB_NO_BALANCE")) {
+                ck.rounds[r].flat = flat && r == 0;
+                if (flat && r == 0 && !getenv("LWB_NO_BALANCE")) {
                     auto warps_of = [&](size_t n, int per_cta) {
                         return std::min<size_t>((n + per_cta - 1) / per_cta, (size_t)ctx->sm_count) * per_cta;
                     };
