@@ -624,12 +624,8 @@ static int try_mixed(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb
                 CU(ctx, cudaEventCreateWithFlags(&ctx->ev_kdone[k], cudaEventDisableTiming));
             }
         }
-        // k_long's driver in one pass: the static deal (k_long_s, the only one that knows boundary slots) -- it looks
-        // further ahead than the tickets, and with the balanced order it was ahead of them at every share of short blocks
-        // when both could run this schedule (2 / 10 / 30 %: 0.886 / 1.014 / 1.131 ms against 0.895 / 1.031 / 1.212 ms)
-        const bool long_static = flat;
         MixLaunch ml;
-        ml.db = db; ml.off_sr = off_sr; ml.off_cd = off_cd; ml.off_by = off_by; ml.off_rc = off_rc; ml.off_sg = off_sg; ml.flat = long_static; ml.pack = pack; ml.spack = spack; ml.w_short = w_short; ml.ls = ls_long;
+        ml.db = db; ml.off_sr = off_sr; ml.off_cd = off_cd; ml.off_by = off_by; ml.off_rc = off_rc; ml.off_sg = off_sg; ml.pack = pack; ml.spack = spack; ml.w_short = w_short; ml.ls = ls_long;
         ml.i16 = i16; ml.residue = false; ml.out_format = io->out_format; ml.warps = maxc * wpc; ml.smem = smem;
         ml.n1max = n1max; ml.wpc = wpc; ml.np = np; ml.coeffs = residue ? d_spec : d_coeffs; ml.dense = nullptr; ml.kinds = nullptr; ml.ys = nullptr;
         ml.pcm = d_pcm;
