@@ -1,14 +1,17 @@
 // path_mixed.cuh -- part of the C-ABI translation unit (included by lwb_api.cu, not compiled on its own):
-// segmented batches: every chain is cut between the fused long-block kernel, the fused short-block kernel and the
-// chain kernel, round by round.
+// segmented batches: every chain is cut between the fused long-block kernels, the fused short-block kernels and the
+// chain kernel; well-formed 256/2048 chains run in one pass (k_long_s once, then k_short / k_short_g once), the rest
+// round by round.
 #pragma once
 
 // ---------------------------------------------------------------------------------------------
 // Mixed short/long streams (the standard 256/2048 Vorbis shape), and uniform streams of 256-point blocks:
-// each chain is cut into segments -- maximal runs of long blocks (n = 2048) go to the fused kernel k_long,
-// maximal runs of full-window 256-point blocks to its short-block counterpart k_short, everything else to
-// the chain kernel -- and the segments of all chains are executed round by round, handing the overlap
-// state over through the stream's device state (PreviousWindowRight) between launches.
+// each chain is cut into segments -- maximal runs of long blocks (n = 2048) go to the fused kernel k_long / k_long_s,
+// maximal runs of full-window 256-point blocks to its short-block counterparts k_short / k_short_g, everything else to
+// the chain kernel.  Chains that alternate cleanly between long and short segments are executed in ONE PASS (round 0:
+// all their long segments, then all their short ones, 128-sample boundary slots in between, see try_mixed); the
+// segments of the other chains round by round behind it, handing the overlap state over through the stream's device
+// state (PreviousWindowRight) between launches.
 // ---------------------------------------------------------------------------------------------
 // Static deals (run r -> warp r mod W: k_long_s, k_short) finish with their most loaded warp: order the runs so that
 // the W columns carry equal packet counts -- longest first, dealt boustrophedon (row 0 left to right, row 1 right to
