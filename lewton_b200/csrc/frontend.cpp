@@ -1443,20 +1443,26 @@ extern "C" int lwf_headers_info(const lwf_headers *h, lwf_info *out)
 extern "C" size_t lwf_headers_comment(const lwf_headers *h, int index, char *buf, size_t cap)
 {
     if (!h) return 0;
-    std::string s;
-    if (index < 0) s = h->h.vendor;
-    else if ((size_t)index < h->h.comments.size()) s = h->h.comments[index].first + "=" + h->h.comments[index].second;
-    if (buf && cap) {
-        const size_t k = std::min(cap - 1, s.size());
-        std::memcpy(buf, s.data(), k);
-        buf[k] = 0;
+    try {
+        std::string s;
+        if (index < 0) s = h->h.vendor;
+        else if ((size_t)index < h->h.comments.size()) s = h->h.comments[index].first + "=" + h->h.comments[index].second;
+        if (buf && cap) {
+            const size_t k = std::min(cap - 1, s.size());
+            std::memcpy(buf, s.data(), k);
+            buf[k] = 0;
+        }
+        return s.size();
+    } catch (...) {                  // nothing may unwind across the C ABI
+        if (buf && cap) buf[0] = 0;
+        return 0;
     }
-    return s.size();
 }
 
 extern "C" int lwf_headers_make_setup(const lwf_headers *h, lwb_ctx *ctx, lwb_setup **out)
 {
     if (!h || !ctx || !out) return LWB_ERR_INVALID;
+    LWF_GUARD(
     const lwf::Headers &s = h->h;
     std::vector<lwb_floor_desc> floors(s.floors.size());
     for (size_t i = 0; i < s.floors.size(); i++) {
@@ -1516,6 +1522,7 @@ extern "C" int lwf_headers_make_setup(const lwf_headers *h, lwb_ctx *ctx, lwb_se
         d.residues = resids.data();
     }
     return lwb_setup_create(ctx, &d, out);
+    )
 }
 
 // What LWB_ENTRY_VQ needs from a stream: <= 8 channels, and every VQ book a residue uses has a dimension that divides
@@ -1640,14 +1647,20 @@ static int reader_read_headers(lwf_reader *r, const lwf_ogg_packet *first)
     if (first) pk = *first;
     else if ((rc = lwf_ogg_next_packet(r->ogg, &pk))) return rc == LWF_ERR_NO_MORE_PACKETS ? LWF_ERR_OGG : rc;
     ident.assign(pk.data, pk.data + pk.len);
-    const uint32_t serial = pk.stream_serial;
+    // At the start of the data packets of other logical streams are skipped until the comment and the setup header of
+    // the ident packet's stream arrive (read_headers, inside_ogg.rs:30-47).  In front of a chained stream the reference
+    // takes the NEXT TWO packets, whatever their serial, and then adopts the setup packet's serial (:124-137): a foreign
+    // packet in between fails there as a bad header, and so it does here.
+    const bool chained = first != nullptr;
+    uint32_t serial = pk.stream_serial;
     do {
         if ((rc = lwf_ogg_next_packet(r->ogg, &pk))) return rc == LWF_ERR_NO_MORE_PACKETS ? LWF_ERR_OGG : rc;
-    } while (pk.stream_serial != serial);
+    } while (!chained && pk.stream_serial != serial);
     comment.assign(pk.data, pk.data + pk.len);
     do {
         if ((rc = lwf_ogg_next_packet(r->ogg, &pk))) return rc == LWF_ERR_NO_MORE_PACKETS ? LWF_ERR_OGG : rc;
-    } while (pk.stream_serial != serial);
+    } while (!chained && pk.stream_serial != serial);
+    if (chained) serial = pk.stream_serial;
     lwf_headers *h = nullptr;
     if ((rc = lwf_headers_parse(ident.data(), ident.size(), comment.data(), comment.size(), pk.data, pk.len, &h))) return rc;
     reader_drop_stream(r);
@@ -1673,7 +1686,15 @@ extern "C" int lwf_reader_open(lwb_ctx *ctx, const uint8_t *data, size_t len, lw
     r->ctx = ctx;
     int rc = lwf_ogg_open(data, len, &r->ogg);
     if (rc) return rc;
-    rc = reader_read_headers(r.get(), nullptr);
+    try {
+        rc = reader_read_headers(r.get(), nullptr);
+    } catch (const std::bad_alloc &) {
+        rc = LWB_ERR_BUFFER;
+    } catch (const std::length_error &) {
+        rc = LWB_ERR_BUFFER;
+    } catch (...) {
+        rc = LWB_ERR_INVALID;
+    }
     if (rc) {
         reader_drop_stream(r.get());
         lwf_ogg_close(r->ogg);
@@ -2007,7 +2028,13 @@ int batch_entropy(lwf_batcher *b, BatchArena &ar, lwf_stream_job *jobs, size_t j
     };
     const int nt = (int)std::min<size_t>((size_t)b->threads, std::max<size_t>(1, j1 - j0));
     std::vector<std::thread> pool;
-    for (int t = 1; t < nt; t++) pool.emplace_back(worker);
+    try {
+        pool.reserve((size_t)nt);
+        for (int t = 1; t < nt; t++) pool.emplace_back(worker);
+    } catch (...) {
+        // no more threads to be had (std::system_error) or no memory for the vector: go on with the workers that did
+        // start -- they share the job counter, so the work is the same -- instead of unwinding past joinable threads
+    }
     worker();
     for (auto &t : pool) t.join();
     if (failed.load()) return LWB_ERR_BUFFER;

@@ -356,10 +356,12 @@ class OggStreamReader:
             return None
         if rc == cabi.ERR_BAD_FORMAT:
             raise AudioReadError(rc)
-        if 16 <= rc <= 23:
+        if rc in (ERR_END_OF_PACKET, ERR_AUDIO_IS_HEADER):
             e = AudioReadError(rc)
-            e.kind = {ERR_END_OF_PACKET: "EndOfPacket", ERR_AUDIO_IS_HEADER: "AudioIsHeader"}.get(rc, "Header error %d" % rc)
+            e.kind = {ERR_END_OF_PACKET: "EndOfPacket", ERR_AUDIO_IS_HEADER: "AudioIsHeader"}[rc]
             raise e
+        if 16 <= rc <= 23:               # the headers of a chained stream (inside_ogg.rs:118-137): VorbisError::BadHeader
+            raise HeaderReadError(rc)
         if rc >= ERR_OGG:
             raise OggReadError("code %d" % rc)
         self.ctx.check(rc)

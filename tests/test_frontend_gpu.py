@@ -117,6 +117,45 @@ def test_ogg_stream_reader_end_to_end(ctx, oracle, seed, channels, floor0):
         rd.close()
 
 
+def _split_pages(data):
+    pages, at = [], 0
+    while at < len(data):
+        assert data[at:at + 4] == b"OggS"
+        nseg = data[at + 26]
+        ln = 27 + nseg + sum(data[at + 27: at + 27 + nseg])
+        pages.append(data[at: at + ln])
+        at += ln
+    return pages
+
+
+def test_chained_stream_headers_take_the_next_two_packets(ctx, oracle):
+    """inside_ogg.rs:124-137: in front of a chained stream the reference reads the comment and the setup header with
+    read_packet_expected, i.e. the next two packets whatever their serial -- unlike read_headers at the start of the
+    data (:30-47), which skips other streams' packets.  A foreign packet between the ident and the comment header of the
+    second stream is therefore a bad header, not something to skip."""
+    a = build_stream(211, 2, False, 4)
+    b = build_stream(212, 1, False, 4)
+    want_a, _ = oracle_pcm(oracle, a[0], a[2])
+    want_b, _ = oracle_pcm(oracle, b[0], b[2])
+    sa = vp.ogg_stream(11, [a[0].ident_packet(), a[0].comment_packet(), a[0].setup_packet()], a[1], page_granules(want_a, 2, 0), 2)
+    pb = _split_pages(vp.ogg_stream(22, [b[0].ident_packet(), b[0].comment_packet(), b[0].setup_packet()], b[1],
+                                    page_granules(want_b, 2, 0), 2))
+    foreign = vp.ogg_page(33, 0, 0, [(b"not a vorbis header", True)], bos=True)
+    # the same foreign page in front of the FIRST stream's comment header is skipped (read_headers)
+    pa = _split_pages(sa)
+    rd = fe.OggStreamReader(ctx, pa[0] + foreign + b"".join(pa[1:]))
+    for w in want_a:
+        assert bits_equal(np.array(rd.read_dec_packet_f32()).reshape(2, -1), w)
+    rd.close()
+    # ... but not in front of the chained stream's
+    rd = fe.OggStreamReader(ctx, sa + pb[0] + foreign + b"".join(pb[1:]))
+    for w in want_a:
+        assert bits_equal(np.array(rd.read_dec_packet_f32()).reshape(2, -1), w)
+    with pytest.raises(fe.HeaderReadError):
+        rd.read_dec_packet_f32()
+    rd.close()
+
+
 def test_chained_streams_reset_the_decoder(ctx, oracle):
     """inside_ogg.rs:118-141: a new logical stream (other serial, bos page) brings new headers and a fresh
     PreviousWindowRight; its first audio packet is decoded and dropped, reading continues with the second."""
