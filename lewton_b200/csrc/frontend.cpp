@@ -1886,6 +1886,8 @@ struct BatchArena {
     PinnedBuf coeffs, dense, kinds, ys, vqrun, vqent, vqroff, vqeoff;
     std::vector<uint8_t> modes, prevs, nexts;
     std::vector<lwb_chain> chains;
+    std::vector<std::vector<lwb_vq_run>> job_runs;      // LWB_ENTRY_VQ: per-job records before they are packed (kept
+    std::vector<std::vector<uint16_t>> job_ents;        // across calls: their capacity is what the next batch needs too)
 };
 
 struct lwf_batcher {
@@ -1966,8 +1968,12 @@ int batch_entropy(lwf_batcher *b, BatchArena &ar, lwf_stream_job *jobs, size_t j
         return LWB_ERR_BUFFER;
     // VQ: every stream's records are collected per job first (their number is only known after the decode), then
     // packed into one pinned arena with per-packet offsets
-    std::vector<std::vector<lwb_vq_run>> job_runs(vq ? j1 - j0 : 0);
-    std::vector<std::vector<uint16_t>> job_ents(vq ? j1 - j0 : 0);
+    std::vector<std::vector<lwb_vq_run>> &job_runs = ar.job_runs;
+    std::vector<std::vector<uint16_t>> &job_ents = ar.job_ents;
+    if (vq) {
+        if (job_runs.size() < j1 - j0) { job_runs.resize(j1 - j0); job_ents.resize(j1 - j0); }
+        for (size_t j = 0; j < j1 - j0; j++) { job_runs[j].clear(); job_ents[j].clear(); }
+    }
     uint64_t *run_off = vq ? (uint64_t *)ar.vqroff.p : nullptr, *ent_off = vq ? (uint64_t *)ar.vqeoff.p : nullptr;
     ar.modes.resize(pkt_total);
     ar.prevs.resize(pkt_total);
@@ -1980,6 +1986,8 @@ int batch_entropy(lwf_batcher *b, BatchArena &ar, lwf_stream_job *jobs, size_t j
     std::atomic<int> failed(0);
     auto worker = [&]() {
         try {
+            std::vector<lwb_vq_run> scratch_runs;        // LWB_ENTRY_VQ: one packet's records (see below)
+            std::vector<uint16_t> scratch_ents;
             for (;;) {
                 const size_t j = next_job.fetch_add(1);
                 if (j >= j1) break;
@@ -1997,18 +2005,22 @@ int batch_entropy(lwf_batcher *b, BatchArena &ar, lwf_stream_job *jobs, size_t j
                     if (vq) {
                         std::vector<lwb_vq_run> &jr = job_runs[j - j0];
                         std::vector<uint16_t> &je = job_ents[j - j0];
-                        const size_t r0 = jr.size(), e0 = je.size(), cap = (size_t)job.lengths[k] * 8 + 16;
-                        jr.resize(r0 + cap);
-                        je.resize(e0 + cap);
+                        // decoded into the thread's scratch (a packet of b bytes holds fewer than 8 b codewords), then only
+                        // what it produced is appended (growing the job's vectors to the bound first meant zero-filling
+                        // ~22 KB per 280-byte packet)
+                        const size_t cap = (size_t)job.lengths[k] * 8 + 16;
+                        if (scratch_runs.size() < cap) { scratch_runs.resize(cap); scratch_ents.resize(cap); }
                         lwf::VqSink sink;
-                        sink.runs = jr.data() + r0;
+                        sink.runs = scratch_runs.data();
                         sink.run_cap = cap;
-                        sink.entries = je.data() + e0;
+                        sink.entries = scratch_ents.data();
                         sink.ent_cap = cap;
                         rc = lwf::packet_decode(H, job.packets[k], job.lengths[k], &dp, &sink);
                         if (!rc && sink.overflow) rc = LWB_ERR_BUFFER;
-                        jr.resize(r0 + (rc ? 0 : sink.n_runs));
-                        je.resize(e0 + (rc ? 0 : sink.n_ent));
+                        if (!rc) {
+                            jr.insert(jr.end(), scratch_runs.data(), scratch_runs.data() + sink.n_runs);
+                            je.insert(je.end(), scratch_ents.data(), scratch_ents.data() + sink.n_ent);
+                        }
                         run_off[pi + 1] = rc ? 0 : sink.n_runs;      // counts for now; turned into offsets below
                         ent_off[pi + 1] = rc ? 0 : sink.n_ent;
                     } else {
@@ -2050,12 +2062,27 @@ int batch_entropy(lwf_batcher *b, BatchArena &ar, lwf_stream_job *jobs, size_t j
             }
         if (!ar.vqrun.ensure((size_t)run_off[pkt_total] * sizeof(lwb_vq_run) + 16) || !ar.vqent.ensure((size_t)ent_off[pkt_total] * 2 + 16))
             return LWB_ERR_BUFFER;
-        for (size_t j = j0; j < j1; j++) {
-            const std::vector<lwb_vq_run> &jr = job_runs[j - j0];
-            const std::vector<uint16_t> &je = job_ents[j - j0];
-            if (!jr.empty()) std::memcpy((lwb_vq_run *)ar.vqrun.p + run_off[plan[j].pkt0], jr.data(), jr.size() * sizeof(lwb_vq_run));
-            if (!je.empty()) std::memcpy((uint16_t *)ar.vqent.p + ent_off[plan[j].pkt0], je.data(), je.size() * sizeof(uint16_t));
+        // ~3 KB per stereo long packet: copied by the pool as well (one thread took as long over it as the whole pool
+        // over the entropy decode, profiles/r2j_stream_bench.jsonl)
+        std::atomic<size_t> next_copy(j0);
+        auto copier = [&]() {
+            for (;;) {
+                const size_t j = next_copy.fetch_add(1);
+                if (j >= j1) return;
+                const std::vector<lwb_vq_run> &jr = job_runs[j - j0];
+                const std::vector<uint16_t> &je = job_ents[j - j0];
+                if (!jr.empty()) std::memcpy((lwb_vq_run *)ar.vqrun.p + run_off[plan[j].pkt0], jr.data(), jr.size() * sizeof(lwb_vq_run));
+                if (!je.empty()) std::memcpy((uint16_t *)ar.vqent.p + ent_off[plan[j].pkt0], je.data(), je.size() * sizeof(uint16_t));
+            }
+        };
+        std::vector<std::thread> cpool;
+        try {
+            cpool.reserve((size_t)nt);
+            for (int t = 1; t < nt; t++) cpool.emplace_back(copier);
+        } catch (...) {
         }
+        copier();
+        for (auto &t : cpool) t.join();
     }
     // chains of this slice
     ar.chains.assign(j1 - j0, lwb_chain());

@@ -47,10 +47,13 @@ def main():
     pcm_host = np.ctypeslib.as_array((np.ctypeslib.ctypes.c_float * (S * C * stride)).from_address(
         L._cabi.lib().lwb_host_alloc(S * C * stride * 4)))
     packet_bytes = sum(len(p) for d in range(D) for p in distinct[d]) / D
+    # SB_ENTRY=vq: the residue crosses the boundary as VQ records (LWB_ENTRY_VQ) instead of dense vectors
+    entry_name = os.environ.get("SB_ENTRY", "residue")
+    entry = L._cabi.ENTRY_VQ if entry_name == "vq" else L._cabi.ENTRY_RESIDUE
     for threads in sorted({1, 4, host_threads()}):
         pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
         jobs = [(pwrs[s], distinct[s % D]) for s in range(S)]
-        bt = fe.StreamBatcher(ctx, hdr, threads=threads)
+        bt = fe.StreamBatcher(ctx, hdr, threads=threads, entry=entry)
         res = bt.decode(jobs, pcm_host, stride)          # first call: streams start empty
         samples = sum(r[0] for r in res) * C
         assert all(r[2] == 0 for r in res)
@@ -64,7 +67,7 @@ def main():
             ent.append(bt.entropy_seconds)
             syn.append(bt.synthesis_seconds)
         w, e, s_ = min(wall), min(ent), min(syn)
-        print(json.dumps({"streams": S, "packets_per_stream": P, "channels": C, "host_threads": threads,
+        print(json.dumps({"entry": entry_name, "streams": S, "packets_per_stream": P, "channels": C, "host_threads": threads,
                           "avg_packet_bytes": packet_bytes, "channel_samples": samples,
                           "wall_ms": w * 1e3, "entropy_decode_ms": e * 1e3, "synthesis_call_ms": s_ * 1e3,
                           "e2e_msamples_per_s": samples / w / 1e6,
