@@ -166,6 +166,9 @@ uint8_t lwf_debug_ilog(uint64_t v);                                  /* lib.rs:1
 size_t lwf_debug_read_bits(const uint8_t *data, size_t len, const uint8_t *widths, size_t n, uint64_t *out);
 int lwf_debug_huffman(const uint8_t *lengths, size_t n, const uint8_t *data, size_t len, uint32_t *out,
                       size_t max_out, size_t *n_out);                /* huffman_tree.rs:113-214      */
+/* timing aid: the n packets decoded `reps` times inside one call (vq != 0: records instead of dense residues);
+ * seconds, < 0 on error (profiles/frontend_bench.py) */
+double lwf_debug_decode_loop(const lwf_headers *h, const uint8_t *const *packets, const size_t *lens, size_t n, int reps, int vq);
 
 #ifdef __cplusplus
 }

@@ -2175,6 +2175,39 @@ extern "C" int lwf_batcher_decode(lwf_batcher *b, lwf_stream_job *jobs, size_t n
 // debug taps for the known-answer tests of the reference's own unit tests (bitpacking.rs:316-334,
 // :488-600, huffman_tree.rs:262-330, header.rs:650-671)
 // ---------------------------------------------------------------------------------------------
+// Timing aid (profiles/frontend_bench.py): decodes the n packets `reps` times inside one call, so that the number is the
+// decoder's and not the caller's; vq != 0: records instead of dense residue vectors.  Returns seconds, < 0 on error.
+extern "C" double lwf_debug_decode_loop(const lwf_headers *h, const uint8_t *const *packets, const size_t *lens, size_t n, int reps, int vq)
+{
+    if (!h || !packets || !lens) return -1.0;
+    try {
+        const size_t C = h->h.ident.audio_channels, n2 = (size_t)1 << (h->h.ident.blocksize_1 - 1);
+        std::vector<uint8_t> kinds(C);
+        std::vector<uint32_t> ys(C * LWB_MAX_POSTS);
+        std::vector<float> dense(C * n2), res(C * n2);
+        size_t cap = 16;
+        for (size_t i = 0; i < n; i++) cap = std::max(cap, lens[i] * 8 + 16);
+        std::vector<lwb_vq_run> runs(cap);
+        std::vector<uint16_t> ents(cap);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int r = 0; r < reps; r++)
+            for (size_t i = 0; i < n; i++) {
+                lwf_decoded_packet dp;
+                std::memset(&dp, 0, sizeof(dp));
+                dp.floor_kind = kinds.data();
+                dp.floor1_y = ys.data();
+                dp.dense_floor = dense.data();
+                dp.residue = vq ? nullptr : res.data();
+                lwf::VqSink sink;
+                sink.runs = runs.data(); sink.run_cap = cap; sink.entries = ents.data(); sink.ent_cap = cap;
+                if (lwf::packet_decode(h->h, packets[i], lens[i], &dp, vq ? &sink : nullptr)) return -2.0;
+            }
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    } catch (...) {
+        return -3.0;
+    }
+}
+
 extern "C" float lwf_debug_float32_unpack(uint32_t v) { return lwf::float32_unpack(v); }
 extern "C" uint32_t lwf_debug_lookup1_values(uint32_t entries, uint16_t dims) { return lwf::lookup1_values(entries, dims); }
 extern "C" uint8_t lwf_debug_ilog(uint64_t v) { return lwf::ilog(v); }

@@ -39,6 +39,18 @@ def main():
             L.lwf_packet_decode(hdr._h, p, len(p), C.byref(dp))
             n += 1
     dt = time.perf_counter() - t0
+    # the same inside one C call (no ctypes overhead), dense and VQ-record output
+    arr = (C.c_char_p * len(pk))(*pk)
+    lens = (C.c_size_t * len(pk))(*[len(p) for p in pk])
+    L.lwf_debug_decode_loop.restype = C.c_double
+    L.lwf_debug_decode_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+    inner = {}
+    for name, vq in (("dense", 0), ("vq", 1)):
+        L.lwf_debug_decode_loop(hdr._h, arr, lens, len(pk), 50, vq)
+        sec = min(L.lwf_debug_decode_loop(hdr._h, arr, lens, len(pk), 500, vq) for _ in range(5))
+        inner[name + "_us_per_packet"] = sec / (500 * len(pk)) * 1e6
+        inner[name + "_msamples_per_s_per_thread"] = 500 * len(pk) * 2048 / sec / 1e6
+    print(json.dumps(inner))
     print(json.dumps({"us_per_packet": dt / n * 1e6, "packets_per_s": n / dt, "msamples_per_s_per_thread": n * 2048 / dt / 1e6,
                       "avg_packet_bytes": sum(map(len, pk)) / len(pk), "note": "includes ~1 us of ctypes call overhead per packet"}))
 
