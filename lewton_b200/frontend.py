@@ -23,7 +23,8 @@ SYMBOLS = ["lwf_headers_parse", "lwf_headers_destroy", "lwf_headers_info", "lwf_
            "lwf_reader_open", "lwf_reader_close", "lwf_reader_headers", "lwf_reader_read_dec_packet", "lwf_reader_last_absgp",
            "lwf_reader_skip_samples_linear", "lwf_reader_seek_absgp_pg",
            "lwf_batcher_create", "lwf_batcher_destroy", "lwf_batcher_set_entry", "lwf_batcher_decode", "lwf_batcher_last_timing",
-           "lwf_debug_float32_unpack", "lwf_debug_lookup1_values", "lwf_debug_ilog", "lwf_debug_read_bits", "lwf_debug_huffman"]
+           "lwf_debug_float32_unpack", "lwf_debug_lookup1_values", "lwf_debug_ilog", "lwf_debug_read_bits", "lwf_debug_huffman",
+           "lwf_debug_decode_loop"]
 
 
 VQ_RUN_DTYPE = np.dtype([("pos", np.uint16), ("first", np.uint16), ("book", np.uint8), ("pass_kind", np.uint8), ("aux", np.uint8),
