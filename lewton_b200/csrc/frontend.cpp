@@ -114,7 +114,8 @@ enum { HUFF_OK = 0, HUFF_OVERSPECIFIED, HUFF_UNDERPOPULATED, HUFF_INVALID_SINGLE
 struct Huffman {
     static constexpr unsigned kPeek = 10;       // first-level lookup: the next 10 bits -> leaf or inner node
     std::vector<uint32_t> prog;
-    std::vector<uint32_t> fast;                 // [1 << kPeek]: (node position << 5) | bits consumed (leaf if prog[pos] has no children)
+    std::vector<uint32_t> fast;                 // [1 << kPeek]: (payload << 5) | bits consumed for codewords of <= kPeek bits,
+                                                // else 1 << 31 | (node position << 5) | kPeek
     bool single = false;        // one entry of length 1: both bit values decode to it (:131-143)
     uint32_t single_payload = 0;
     bool empty = true;          // no used entry: the reference would index out of bounds on a read
@@ -199,13 +200,21 @@ struct Huffman {
             flatten(t, 0);
             // the walk of read() for every 10-bit prefix, done once (the reference unrolls 8 bits, huffman_tree.rs:182-208)
             fast.resize(1u << kPeek);
+            // (node positions must fit 26 bits beside the flag and the bit count: a tree of more than ~11 M entries -- legal,
+            // never seen -- is walked from the root, bit by bit)
+            const bool walk_only = prog.size() >= (1u << 26);
             for (uint32_t bits = 0; bits < (1u << kPeek); bits++) {
+                if (walk_only) { fast[bits] = 0x80000000u; continue; }
                 uint32_t at = 0, used = 0;
                 while (used < kPeek && (prog[at] & 0x80000000u)) {
                     at = prog[at + 1 + ((bits >> used) & 1)];
                     used++;
                 }
-                fast[bits] = (at << 5) | used;
+                // a codeword that ends within the peeked bits: the entry carries the payload itself (one load per
+                // symbol instead of two dependent ones); else bit 31 and the node to go on from
+                const uint32_t e = prog[at];
+                if (e & 0x80000000u) fast[bits] = 0x80000000u | (at << 5) | used;
+                else fast[bits] = (e << 5) | used;
             }
         }
         return HUFF_OK;
@@ -227,10 +236,11 @@ struct Huffman {
         // what is left and then reports the end of the packet).
         const size_t left = rdr.bits_left();
         const uint32_t f = fast[rdr.peek() & ((1u << kPeek) - 1)];
-        uint32_t at = f >> 5;
         const uint32_t used = f & 31;
         if (used > left) { rdr.pos += left; return false; }
         rdr.pos += used;
+        if (!(f & 0x80000000u)) { *out = f >> 5; return true; }
+        uint32_t at = (f & 0x7fffffffu) >> 5;
         uint32_t e = prog[at];
         while (e & 0x80000000u) {                            // codewords longer than 10 bits: keep walking
             bool b;
