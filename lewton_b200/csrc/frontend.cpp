@@ -980,26 +980,31 @@ struct VqSink {
 // residue_packet_read_partition, audio.rs:588-619 with the additions left to the device: 0 ok, 1 end of packet
 static int residue_partition_vq(BitReader &rdr, const Codebook &cb, const Residue &r, size_t vlen, VqSink &sink)
 {
+    // The loop bounds and early exits are residue_partition's; per symbol only the codeword is read and its entry stored
+    // (positions advance by a constant, the run header is written once per 255 entries).
     uint32_t idx;
     sink.begin();
+    const size_t dims = cb.dimensions;
     if (r.type == 0) {
-        const size_t dims = cb.dimensions;
         if (dims == 0) return 0;
         const size_t step = r.partition_size / dims;
+        const bool fits = (dims - 1) * step < vlen;          // i + (dims - 1) * step >= vlen first fails at i = vlen - (dims - 1) * step
+        const size_t ok_until = fits ? vlen - (dims - 1) * step : 0;
         for (size_t i = 0; i < step; i++) {
             if (!cb.tree.read(rdr, &idx)) return 1;
-            if (i + (dims - 1) * step >= vlen) return 0;    // (slice index out of range: a panic in the reference)
+            if (i >= ok_until) return 0;                     // (slice index out of range: a panic in the reference)
             sink.put(idx, i, dims);
         }
     } else {
         const size_t psize = r.partition_size;
-        size_t i = 0;
+        size_t i = 0, v = 0;
         while (i < psize) {
             if (!cb.tree.read(rdr, &idx)) return 1;
-            if (i + cb.dimensions > vlen) break;
-            if (cb.dimensions == 0) break;
-            sink.put(idx, i / cb.dimensions, cb.dimensions);
-            i += cb.dimensions;
+            if (i + dims > vlen) break;
+            if (dims == 0) break;
+            sink.put(idx, v, dims);
+            i += dims;
+            v++;
         }
     }
     return 0;
