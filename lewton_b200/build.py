@@ -12,8 +12,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liblewton_b200.so")
-SOURCES = ["lwb_api.cu", "host_objects.cuh", "path_generic.cuh", "path_long.cuh", "path_chain.cuh", "path_mixed.cuh",
-           "tables_host.cpp", "frontend.cpp", "lwb_common.h", "kernels_generic.cuh", "kernel_long.cuh", "kernel_short.cuh", "kernel_chain.cuh", "kernel_prologue.cuh", "floor1_eval.cuh",
+SOURCES = ["lwb_api.cu", "host_objects.cuh", "path_generic.cuh", "path_long.cuh", "path_chain.cuh", "path_mixed.cuh", "path_mid.cuh",
+           "tables_host.cpp", "frontend.cpp", "lwb_common.h", "kernels_generic.cuh", "kernel_long.cuh", "kernel_short.cuh", "kernel_mid.cuh", "kernel_chain.cuh", "kernel_prologue.cuh", "floor1_eval.cuh",
            "floor1_inverse_db.inc", "Makefile"]
 
 

@@ -21,6 +21,7 @@
 
 #include "kernel_long.cuh"
 #include "kernel_short.cuh"
+#include "kernel_mid.cuh"
 #include "kernels_generic.cuh"
 #include "kernel_chain.cuh"
 #include "kernel_prologue.cuh"
@@ -76,6 +77,7 @@ extern "C" int lwb_ctx_create(int device, lwb_ctx **out)
     }
     long_kernel_configure();
     short_kernel_configure();
+    mid_kernel_configure();
     prologue_kernel_configure();
     *out = ctx;
     return LWB_OK;
@@ -309,6 +311,9 @@ extern "C" int lwb_setup_create(lwb_ctx *ctx, const lwb_setup_desc *d, lwb_setup
             } else if (bs == kShortBs) {
                 pack.resize(kShortPackFloats);
                 short_build_pack(a.data(), b.data(), c.data(), w.data(), pack.data());
+            } else if (bs == kMidBs) {
+                pack.resize(kLongPackFloats);
+                mid_build_pack(a.data(), b.data(), c.data(), w.data(), pack.data());
             }
             rc = up(a.data(), a.size() * 4, (const void **)&ct.dt.a);
             if (!rc) rc = up(b.data(), b.size() * 4, (const void **)&ct.dt.b);
@@ -506,6 +511,7 @@ extern "C" int lwb_decoded_sample_count(const lwb_setup *su, uint8_t mode, int p
 #include "path_long.cuh"
 #include "path_chain.cuh"
 #include "path_mixed.cuh"
+#include "path_mid.cuh"
 
 static int decode_chains_impl(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, lwb_plan *prepared)
 {
@@ -533,6 +539,8 @@ static int decode_chains_impl(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, 
         }
         {
             if (!no_fused) {
+                rc0 = try_mid(ctx, chains, n_chains, io, epoch, &handled, prepared);
+                if (rc0 || handled) return rc0;
                 rc0 = try_mixed(ctx, chains, n_chains, io, epoch, &handled, prepared);
                 if (rc0 || handled) return rc0;
             }

@@ -1,0 +1,156 @@
+// path_mid.cuh -- part of the C-ABI translation unit (included by lwb_api.cu, not compiled on its own):
+// batches whose every packet is a full-window block of n = 1024 (blocksize 10) go to k_mid (kernel_mid.cuh): spectrum
+// entry, planar f32 / i16, <= 8 channels.  The descriptors, the staging of host arenas and the capture by a prepared
+// batch follow try_chain; the launch goes through mixed_launch_rounds (MixRound::nm).
+#pragma once
+
+struct MidGroup { LongRun r[2]; uint32_t n_packets; };
+
+static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch, bool *handled,
+                   lwb_plan *plan = nullptr)
+{
+    *handled = false;
+    const uint64_t gen_at_entry = ctx->state_gen;
+    if (getenv("LWB_FORCE_GENERIC") || getenv("LWB_NO_MID")) return LWB_OK;
+    if (io->entry != LWB_ENTRY_SPECTRUM) return LWB_OK;
+    if (io->out_format != LWB_OUT_F32_PLANAR && io->out_format != LWB_OUT_I16_PLANAR) return LWB_OK;
+    const bool i16 = io->out_format == LWB_OUT_I16_PLANAR;
+    const size_t esz = i16 ? 2 : 4;
+    const float *pack = nullptr;
+    // pass 1, no side effects: every packet a full-window 1024-point block on top of no state or a 512-sample one
+    size_t n_runs = 0;
+    for (size_t i = 0; i < n_chains; i++) {
+        const lwb_chain *c = &chains[i];
+        if (!c->stream || c->stream->ctx != ctx || (c->n_packets && !c->mode_numbers)) return LWB_OK;
+        const lwb_setup *su = c->stream->setup;
+        if (su->channels > 8 || su->bs1 != kMidBs || !su->host.tab[1].pack) return LWB_OK;
+        if (pack && pack != su->host.tab[1].pack) return LWB_OK;
+        pack = su->host.tab[1].pack;
+        if ((c->out_offset & 3) || (c->out_stride & 3) || (c->coeff_offset & 3)) return LWB_OK;
+        if (c->stream->has && c->stream->plen != (uint32_t)kMidN2) return LWB_OK;
+        for (uint32_t k = 0; k < c->n_packets; k++) {
+            Geom g;
+            if (geometry(su, c->mode_numbers[k], c->prev_window_flags ? c->prev_window_flags[k] : 1,
+                         c->next_window_flags ? c->next_window_flags[k] : 1, &g))
+                return LWB_OK;                                  // a bad mode number: the chain kernel reports it in place
+            if (g.n != (uint32_t)kMidN || g.ls != 0 || g.rs != (uint32_t)kMidN2 || g.re != (uint32_t)kMidN) return LWB_OK;
+        }
+        if (c->n_packets) {
+            if (c->out_stride < (uint64_t)c->n_packets * kMidN2) return LWB_OK;     // (the chain kernel words the error)
+            n_runs += su->channels;
+        }
+    }
+    if (!pack || !n_runs) return LWB_OK;
+    *handled = true;
+    if (plan) plan->mixed_captured = false;
+
+    const bool host = io->memory == LWB_MEM_HOST;
+    cudaStream_t sm = ctx->stream;
+    int rc;
+    uint64_t c_lo = ~0ull, c_hi = 0, o_lo = ~0ull, o_hi = 0;
+    for (size_t i = 0; i < n_chains; i++) {
+        lwb_chain *c = &chains[i];
+        lwb_stream *s = c->stream;
+        if (s->busy_epoch == epoch) return fail(ctx, LWB_ERR_INVALID, "a stream appears in two chains of one batch");
+        s->busy_epoch = epoch;
+        const unsigned C = s->setup->channels;
+        c->status = LWB_OK;
+        c->packets_done = c->n_packets;
+        c->n_samples = c->n_packets ? (uint32_t)((c->n_packets - (s->has ? 0u : 1u)) * (uint32_t)kMidN2) : 0u;
+        if (!c->n_packets) continue;
+        c_lo = std::min(c_lo, c->coeff_offset);
+        c_hi = std::max(c_hi, c->coeff_offset + (uint64_t)c->n_packets * C * kMidN2);
+        o_lo = std::min(o_lo, c->out_offset);
+        o_hi = std::max(o_hi, c->out_offset + (uint64_t)(C - 1) * c->out_stride + c->n_samples);
+    }
+    const float *d_coeffs = io->coeffs;
+    char *d_pcm = (char *)io->pcm;
+    if (host) {
+        if ((rc = ensure(ctx, ctx->coeffs, (size_t)(c_hi - c_lo) * 4))) return rc;
+        if (o_hi > o_lo && (rc = ensure(ctx, ctx->pcm, (size_t)(o_hi - o_lo) * esz))) return rc;
+        CU(ctx, cudaMemcpyAsync(ctx->coeffs.p, io->coeffs + c_lo, (size_t)(c_hi - c_lo) * 4, cudaMemcpyHostToDevice, sm));
+        d_coeffs = (const float *)ctx->coeffs.p - c_lo;
+        d_pcm = (char *)ctx->pcm.p - o_lo * esz;
+    }
+    // runs, then groups of two runs of equal length (an odd one gets a dummy partner), longest first, dealt balanced
+    std::vector<LongRun> runs;
+    runs.reserve(n_runs);
+    for (size_t i = 0; i < n_chains; i++) {
+        const lwb_chain *c = &chains[i];
+        if (!c->n_packets) continue;
+        const lwb_stream *s = c->stream;
+        const lwb_setup *su = s->setup;
+        const unsigned C = su->channels;
+        for (unsigned ch = 0; ch < C; ch++) {
+            LongRun lr;
+            std::memset(&lr, 0, sizeof(lr));
+            lr.in = d_coeffs + c->coeff_offset + (size_t)ch * kMidN2;
+            lr.out = d_pcm + (c->out_offset + (size_t)ch * c->out_stride) * esz;
+            lr.state = s->d_state + (size_t)ch * state_stride(su);
+            lr.in_stride = (uint32_t)(C * kMidN2);
+            lr.n_packets = c->n_packets;
+            lr.has_prev = s->has;
+            lr.write_state = 1;
+            runs.push_back(lr);
+        }
+    }
+    std::stable_sort(runs.begin(), runs.end(), [](const LongRun &a, const LongRun &b) { return a.n_packets > b.n_packets; });
+    std::vector<MidGroup> groups, tmp_g;
+    groups.reserve(runs.size() / 2 + 8);
+    for (size_t i = 0; i < runs.size();) {
+        MidGroup g;
+        g.r[0] = runs[i];
+        g.n_packets = runs[i].n_packets;
+        if (i + 1 < runs.size() && runs[i + 1].n_packets == runs[i].n_packets) {
+            g.r[1] = runs[i + 1];
+            i += 2;
+        } else {
+            g.r[1] = runs[i];                     // reads valid memory, stores nothing
+            g.r[1].dummy = 1;
+            g.r[1].write_state = 0;
+            g.r[1].has_prev = 0;
+            i += 1;
+        }
+        groups.push_back(g);
+    }
+    const size_t Wg = std::min<size_t>((groups.size() + kLongWarps - 1) / kLongWarps, (size_t)ctx->sm_count) * kLongWarps;
+    balance_static_deal(groups.data(), groups.size(), Wg, tmp_g);
+    const size_t bytes = groups.size() * 2 * sizeof(LongRun);
+    Staging *st;
+    if ((rc = acquire_staging(ctx, bytes, &st))) return rc;
+    LongRun *h = (LongRun *)st->h;
+    for (size_t k = 0; k < groups.size(); k++) { h[2 * k] = groups[k].r[0]; h[2 * k + 1] = groups[k].r[1]; }
+    const bool capture = plan && !host;
+    DevBuf &dbuf = capture ? plan->mix : ctx->cdesc;
+    if ((rc = ensure(ctx, dbuf, bytes + 16))) return rc;
+    CU(ctx, cudaMemcpyAsync(dbuf.p, h, bytes, cudaMemcpyHostToDevice, sm));
+    CU(ctx, cudaEventRecord(st->ev, sm));
+    st->pending = true;
+    MixLaunch ml;
+    std::memset(&ml, 0, sizeof(ml));
+    ml.db = (char *)dbuf.p;
+    ml.mpack = pack;
+    ml.i16 = i16;
+    ml.out_format = io->out_format;
+    ml.pcm = d_pcm;
+    MixRound rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.nm = groups.size();
+    std::vector<MixRound> rounds(1, rd);
+    if ((rc = mixed_launch_rounds(ctx, ml, rounds))) return rc;
+    if (capture) {
+        plan->mixed_captured = true;
+        plan->gen = gen_at_entry;
+        plan->mix_launch = ml;
+        plan->mix_rounds = std::move(rounds);
+        plan->mix_pro = false;
+    }
+    if (host) {
+        if (o_hi > o_lo)
+            CU(ctx, cudaMemcpyAsync((char *)io->pcm + o_lo * esz, ctx->pcm.p, (size_t)(o_hi - o_lo) * esz, cudaMemcpyDeviceToHost, sm));
+        CU(ctx, cudaStreamSynchronize(sm));
+    }
+    for (size_t i = 0; i < n_chains; i++)
+        if (chains[i].n_packets) set_stream_state(chains[i].stream, true, (uint32_t)kMidN2);
+    return LWB_OK;
+}

@@ -835,6 +835,89 @@ def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle
             assert np.array_equal(outs[("mixed", batch)].view(np.uint8), outs[(name, batch)].view(np.uint8)), name
 
 
+@pytest.mark.parametrize("channels,fmt,memory,seed", [(1, cabi.OUT_F32_PLANAR, cabi.MEM_DEVICE, 400), (2, cabi.OUT_I16_PLANAR, cabi.MEM_HOST, 401),
+                                                      (6, cabi.OUT_F32_PLANAR, cabi.MEM_HOST, 402), (3, cabi.OUT_I16_PLANAR, cabi.MEM_DEVICE, 403)])
+def test_mid_block_kernel_uniform_batches(ctx, oracle, channels, fmt, memory, seed):
+    """Uniform 1024-point streams (blocksize 10) through k_mid: two runs per warp in lockstep, so chains of different
+    lengths exercise the pairing by length and the dummy partner of an odd run, many chains the static deal with several
+    groups per warp; three consecutive batches carry the state (none, then 512 samples); bit-exact against the oracle and
+    byte-identical to the chain kernel (LWB_NO_MID=1)."""
+    rng = np.random.default_rng(seed)
+    S = 700 if channels == 1 else 257
+    D = 5
+    modes = [(1, 0)]
+    su = make_setup(ctx, channels, 10, 10, modes=modes)
+    f32 = fmt == cabi.OUT_F32_PLANAR
+    dt = np.float32 if f32 else np.int16
+    lens = [int(rng.integers(1, 7)) for _ in range(D)]
+    refs = [RefStream(oracle, channels, 10, 10, modes) for _ in range(D)]
+    outs = {}
+    batches = []
+    for b in range(3):
+        specs = [rng.standard_normal((lens[d], channels, 512)).astype(np.float32) for d in range(D)]
+        want = []
+        for d in range(D):
+            parts = []
+            for i in range(lens[d]):
+                rc, pcm = refs[d].spectrum(0, 1, 1, specs[d][i])
+                assert rc == 0
+                parts.append(pcm)
+            want.append((np.concatenate(parts, axis=1), refs[d].pwr.data().copy()))
+        batches.append((specs, want))
+    for name, env in (("mid", None), ("chain", {"LWB_NO_MID": "1"})):
+        pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+        if env:
+            os.environ.update(env)
+        try:
+            for b, (specs, want) in enumerate(batches):
+                chains, coeffs, coeff_off, out_off = [], [], 0, 0
+                for s in range(S):
+                    d = s % D
+                    stride = lens[d] * 512
+                    chains.append(L.ChainSpec(pwrs[s], np.zeros(lens[d], np.uint8), coeff_offset=coeff_off, out_offset=out_off,
+                                              out_stride=stride))
+                    coeffs.append(specs[d].ravel())
+                    coeff_off += specs[d].size
+                    out_off += stride * channels
+                coeffs = np.concatenate(coeffs)
+                pcm = np.zeros(out_off, dt)
+                launches0 = ctx.launch_count
+                if memory == cabi.MEM_DEVICE:
+                    d_in, d_out = ctx.device_alloc(coeffs.nbytes), ctx.device_alloc(pcm.nbytes)
+                    ctx.h2d(d_in, coeffs)
+                    L.decode_chains(ctx, chains, cabi.ENTRY_SPECTRUM, memory, d_in, d_out, fmt)
+                    ctx.d2h(pcm, d_out)
+                    ctx.device_free(d_in)
+                    ctx.device_free(d_out)
+                else:
+                    L.decode_chains(ctx, chains, cabi.ENTRY_SPECTRUM, memory, coeffs, pcm, fmt)
+                assert ctx.launch_count - launches0 == 1
+                pos = 0
+                got_all = []
+                for s in range(S):
+                    d = s % D
+                    stride = lens[d] * 512
+                    n = want[d][0].shape[1]
+                    assert chains[s].status == 0 and chains[s].n_samples == n, (name, b, s)
+                    got = pcm[pos: pos + stride * channels].reshape(channels, stride)[:, :n]
+                    if f32:
+                        assert bits_equal(got, want[d][0]), (name, b, s, mismatch_report(got, want[d][0]))
+                    else:
+                        assert np.array_equal(got, oracle.quantise_i16(want[d][0])), (name, b, s)
+                    got_all.append(got.copy())
+                    pos += stride * channels
+                for s in range(0, S, 41):
+                    assert bits_equal(pwrs[s].data(), want[s % D][1]), (name, b, s)
+                outs[(name, b)] = got_all
+        finally:
+            if env:
+                for k in env:
+                    del os.environ[k]
+    for b in range(3):
+        for s in range(S):
+            assert np.array_equal(outs[("mid", b)][s].view(np.uint8), outs[("chain", b)][s].view(np.uint8)), (b, s)
+
+
 @pytest.mark.parametrize("fmt,seed,p_bad", [(cabi.OUT_F32_PLANAR, 300, 0.0), (cabi.OUT_I16_PLANAR, 301, 0.0),
                                             (cabi.OUT_F32_PLANAR, 302, 0.08), (cabi.OUT_I16_PLANAR, 303, 0.3),
                                             (cabi.OUT_F32_PLANAR, 304, 0.004), (cabi.OUT_I16_PLANAR, 305, 0.01)])
