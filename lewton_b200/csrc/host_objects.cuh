@@ -71,7 +71,7 @@ struct MixRound { size_t r0, nr, s0, ns, c0, nc, x0, nx, g0, ng, flat, nm; };   
 struct RowCopy { const float *src; float *dst; uint32_t n4, pad; };  // n4 float4s, copied in front of the round's kernels
 struct MixLaunch {
     char *db; size_t off_sr, off_cd, off_by, off_rc, off_sg;
-    const float *pack, *spack, *w_short, *mpack; int ls; bool i16, residue; int out_format; unsigned warps; size_t smem; int n1max, wpc, np;
+    const float *pack, *spack, *w_short, *mpack; int ls, mid_kb; bool i16, residue; int out_format; unsigned warps; size_t smem; int n1max, wpc, np;
     const float *coeffs, *dense; const uint8_t *kinds; const uint32_t *ys; void *pcm;
 };
 

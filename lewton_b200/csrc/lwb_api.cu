@@ -311,9 +311,12 @@ extern "C" int lwb_setup_create(lwb_ctx *ctx, const lwb_setup_desc *d, lwb_setup
             } else if (bs == kShortBs) {
                 pack.resize(kShortPackFloats);
                 short_build_pack(a.data(), b.data(), c.data(), w.data(), pack.data());
-            } else if (bs == kMidBs) {
+            } else if (bs == 10) {
                 pack.resize(kLongPackFloats);
-                mid_build_pack(a.data(), b.data(), c.data(), w.data(), pack.data());
+                mid_build_pack<1>(a.data(), b.data(), c.data(), w.data(), pack.data());
+            } else if (bs == 9) {
+                pack.resize(kLongPackFloats);
+                mid_build_pack<2>(a.data(), b.data(), c.data(), w.data(), pack.data());
             }
             rc = up(a.data(), a.size() * 4, (const void **)&ct.dt.a);
             if (!rc) rc = up(b.data(), b.size() * 4, (const void **)&ct.dt.b);

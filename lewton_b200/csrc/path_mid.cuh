@@ -1,10 +1,10 @@
 // path_mid.cuh -- part of the C-ABI translation unit (included by lwb_api.cu, not compiled on its own):
-// batches whose every packet is a full-window block of n = 1024 (blocksize 10) go to k_mid (kernel_mid.cuh): spectrum
-// entry, planar f32 / i16, <= 8 channels.  The descriptors, the staging of host arenas and the capture by a prepared
+// batches whose every packet is a full-window block of n = 1024 or of n = 512 (blocksize 10 / 9) go to k_mid
+// (kernel_mid.cuh): spectrum entry, planar f32 / i16, <= 8 channels.  The descriptors, the staging of host arenas and the capture by a prepared
 // batch follow try_chain; the launch goes through mixed_launch_rounds (MixRound::nm).
 #pragma once
 
-struct MidGroup { LongRun r[2]; uint32_t n_packets; };
+struct MidGroup { LongRun r[4]; uint32_t n_packets; };
 
 static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch, bool *handled,
                    lwb_plan *plan = nullptr)
@@ -17,30 +17,34 @@ static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_b
     const bool i16 = io->out_format == LWB_OUT_I16_PLANAR;
     const size_t esz = i16 ? 2 : 4;
     const float *pack = nullptr;
-    // pass 1, no side effects: every packet a full-window 1024-point block on top of no state or a 512-sample one
+    int kb = 0;                                              // 1: n = 1024, 2: n = 512 (one size per batch: one pack)
+    // pass 1, no side effects: every packet a full-window block of that size on top of no state or an n/2-sample one
     size_t n_runs = 0;
     for (size_t i = 0; i < n_chains; i++) {
         const lwb_chain *c = &chains[i];
         if (!c->stream || c->stream->ctx != ctx || (c->n_packets && !c->mode_numbers)) return LWB_OK;
         const lwb_setup *su = c->stream->setup;
-        if (su->channels > 8 || su->bs1 != kMidBs || !su->host.tab[1].pack) return LWB_OK;
+        if (su->channels > 8 || (su->bs1 != 10 && su->bs1 != 9) || !su->host.tab[1].pack) return LWB_OK;
         if (pack && pack != su->host.tab[1].pack) return LWB_OK;
         pack = su->host.tab[1].pack;
+        kb = 11 - su->bs1;
         if ((c->out_offset & 3) || (c->out_stride & 3) || (c->coeff_offset & 3)) return LWB_OK;
-        if (c->stream->has && c->stream->plen != (uint32_t)kMidN2) return LWB_OK;
+        const uint32_t n_blk = 2048u >> kb, n2_blk = n_blk >> 1;
+        if (c->stream->has && c->stream->plen != n2_blk) return LWB_OK;
         for (uint32_t k = 0; k < c->n_packets; k++) {
             Geom g;
             if (geometry(su, c->mode_numbers[k], c->prev_window_flags ? c->prev_window_flags[k] : 1,
                          c->next_window_flags ? c->next_window_flags[k] : 1, &g))
                 return LWB_OK;                                  // a bad mode number: the chain kernel reports it in place
-            if (g.n != (uint32_t)kMidN || g.ls != 0 || g.rs != (uint32_t)kMidN2 || g.re != (uint32_t)kMidN) return LWB_OK;
+            if (g.n != n_blk || g.ls != 0 || g.rs != n2_blk || g.re != n_blk) return LWB_OK;
         }
         if (c->n_packets) {
-            if (c->out_stride < (uint64_t)c->n_packets * kMidN2) return LWB_OK;     // (the chain kernel words the error)
+            if (c->out_stride < (uint64_t)c->n_packets * n2_blk) return LWB_OK;     // (the chain kernel words the error)
             n_runs += su->channels;
         }
     }
     if (!pack || !n_runs) return LWB_OK;
+    const size_t kMidN2 = 1024u >> kb, NBg = (size_t)1 << kb;
     *handled = true;
     if (plan) plan->mixed_captured = false;
 
@@ -96,30 +100,29 @@ static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_b
     }
     std::stable_sort(runs.begin(), runs.end(), [](const LongRun &a, const LongRun &b) { return a.n_packets > b.n_packets; });
     std::vector<MidGroup> groups, tmp_g;
-    groups.reserve(runs.size() / 2 + 8);
+    groups.reserve(runs.size() / NBg + 8);
     for (size_t i = 0; i < runs.size();) {
         MidGroup g;
-        g.r[0] = runs[i];
+        std::memset(&g, 0, sizeof(g));
         g.n_packets = runs[i].n_packets;
-        if (i + 1 < runs.size() && runs[i + 1].n_packets == runs[i].n_packets) {
-            g.r[1] = runs[i + 1];
-            i += 2;
-        } else {
-            g.r[1] = runs[i];                     // reads valid memory, stores nothing
-            g.r[1].dummy = 1;
-            g.r[1].write_state = 0;
-            g.r[1].has_prev = 0;
-            i += 1;
+        size_t k = 0;
+        while (k < NBg && i < runs.size() && runs[i].n_packets == g.n_packets) g.r[k++] = runs[i++];
+        for (; k < NBg; k++) {                    // dummies: read valid memory, store nothing
+            g.r[k] = g.r[0];
+            g.r[k].dummy = 1;
+            g.r[k].write_state = 0;
+            g.r[k].has_prev = 0;
         }
         groups.push_back(g);
     }
     const size_t Wg = std::min<size_t>((groups.size() + kLongWarps - 1) / kLongWarps, (size_t)ctx->sm_count) * kLongWarps;
     balance_static_deal(groups.data(), groups.size(), Wg, tmp_g);
-    const size_t bytes = groups.size() * 2 * sizeof(LongRun);
+    const size_t bytes = groups.size() * NBg * sizeof(LongRun);
     Staging *st;
     if ((rc = acquire_staging(ctx, bytes, &st))) return rc;
     LongRun *h = (LongRun *)st->h;
-    for (size_t k = 0; k < groups.size(); k++) { h[2 * k] = groups[k].r[0]; h[2 * k + 1] = groups[k].r[1]; }
+    for (size_t k = 0; k < groups.size(); k++)
+        for (size_t b = 0; b < NBg; b++) h[NBg * k + b] = groups[k].r[b];
     const bool capture = plan && !host;
     DevBuf &dbuf = capture ? plan->mix : ctx->cdesc;
     if ((rc = ensure(ctx, dbuf, bytes + 16))) return rc;
@@ -130,6 +133,7 @@ static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_b
     std::memset(&ml, 0, sizeof(ml));
     ml.db = (char *)dbuf.p;
     ml.mpack = pack;
+    ml.mid_kb = kb;
     ml.i16 = i16;
     ml.out_format = io->out_format;
     ml.pcm = d_pcm;

@@ -63,7 +63,7 @@ def main():
             samples = chains_n * pk * n2          # steady state: every packet emits n/2 samples
             line = {"n": n, "blocks": chains_n * pk, "ms": ms, "msamples_per_s": samples / ms / 1e3,
                     "achieved_gbs": samples * 8 / ms / 1e6, "frac_of_hbm_peak": samples * 8 / ms / 1e6 / peak,
-                    "path": "fused k_long" if bs == 11 else "fused k_short" if bs == 8 else "fused k_mid" if bs == 10 else "chain kernel"}
+                    "path": "fused k_long" if bs == 11 else "fused k_short" if bs == 8 else "fused k_mid" if bs in (9, 10) else "chain kernel"}
             print(json.dumps(line), flush=True)
             batch.close()
             for p in pw:

@@ -835,26 +835,30 @@ def test_mixed_streams_are_segmented_between_fused_and_chain_kernels(ctx, oracle
             assert np.array_equal(outs[("mixed", batch)].view(np.uint8), outs[(name, batch)].view(np.uint8)), name
 
 
-@pytest.mark.parametrize("channels,fmt,memory,seed", [(1, cabi.OUT_F32_PLANAR, cabi.MEM_DEVICE, 400), (2, cabi.OUT_I16_PLANAR, cabi.MEM_HOST, 401),
-                                                      (6, cabi.OUT_F32_PLANAR, cabi.MEM_HOST, 402), (3, cabi.OUT_I16_PLANAR, cabi.MEM_DEVICE, 403)])
-def test_mid_block_kernel_uniform_batches(ctx, oracle, channels, fmt, memory, seed):
-    """Uniform 1024-point streams (blocksize 10) through k_mid: two runs per warp in lockstep, so chains of different
-    lengths exercise the pairing by length and the dummy partner of an odd run, many chains the static deal with several
-    groups per warp; three consecutive batches carry the state (none, then 512 samples); bit-exact against the oracle and
-    byte-identical to the chain kernel (LWB_NO_MID=1)."""
+@pytest.mark.parametrize("bs,channels,fmt,memory,seed", [
+    (10, 1, cabi.OUT_F32_PLANAR, cabi.MEM_DEVICE, 400), (10, 2, cabi.OUT_I16_PLANAR, cabi.MEM_HOST, 401),
+    (10, 6, cabi.OUT_F32_PLANAR, cabi.MEM_HOST, 402), (10, 3, cabi.OUT_I16_PLANAR, cabi.MEM_DEVICE, 403),
+    (9, 1, cabi.OUT_F32_PLANAR, cabi.MEM_DEVICE, 404), (9, 2, cabi.OUT_I16_PLANAR, cabi.MEM_HOST, 405),
+    (9, 5, cabi.OUT_F32_PLANAR, cabi.MEM_HOST, 406), (9, 3, cabi.OUT_I16_PLANAR, cabi.MEM_DEVICE, 407)])
+def test_mid_block_kernel_uniform_batches(ctx, oracle, bs, channels, fmt, memory, seed):
+    """Uniform 1024- and 512-point streams (blocksize 10 / 9) through k_mid: two / four runs per warp in lockstep, so
+    chains of different lengths exercise the grouping by length and the dummy partners of a short group, many chains the
+    static deal with several groups per warp; three consecutive batches carry the state (none, then n/2 samples);
+    bit-exact against the oracle and byte-identical to the chain kernel (LWB_NO_MID=1)."""
+    n2 = 1 << (bs - 1)
     rng = np.random.default_rng(seed)
     S = 700 if channels == 1 else 257
     D = 5
     modes = [(1, 0)]
-    su = make_setup(ctx, channels, 10, 10, modes=modes)
+    su = make_setup(ctx, channels, bs, bs, modes=modes)
     f32 = fmt == cabi.OUT_F32_PLANAR
     dt = np.float32 if f32 else np.int16
     lens = [int(rng.integers(1, 7)) for _ in range(D)]
-    refs = [RefStream(oracle, channels, 10, 10, modes) for _ in range(D)]
+    refs = [RefStream(oracle, channels, bs, bs, modes) for _ in range(D)]
     outs = {}
     batches = []
     for b in range(3):
-        specs = [rng.standard_normal((lens[d], channels, 512)).astype(np.float32) for d in range(D)]
+        specs = [rng.standard_normal((lens[d], channels, n2)).astype(np.float32) for d in range(D)]
         want = []
         for d in range(D):
             parts = []
@@ -873,7 +877,7 @@ def test_mid_block_kernel_uniform_batches(ctx, oracle, channels, fmt, memory, se
                 chains, coeffs, coeff_off, out_off = [], [], 0, 0
                 for s in range(S):
                     d = s % D
-                    stride = lens[d] * 512
+                    stride = lens[d] * n2
                     chains.append(L.ChainSpec(pwrs[s], np.zeros(lens[d], np.uint8), coeff_offset=coeff_off, out_offset=out_off,
                                               out_stride=stride))
                     coeffs.append(specs[d].ravel())
@@ -896,7 +900,7 @@ def test_mid_block_kernel_uniform_batches(ctx, oracle, channels, fmt, memory, se
                 got_all = []
                 for s in range(S):
                     d = s % D
-                    stride = lens[d] * 512
+                    stride = lens[d] * n2
                     n = want[d][0].shape[1]
                     assert chains[s].status == 0 and chains[s].n_samples == n, (name, b, s)
                     got = pcm[pos: pos + stride * channels].reshape(channels, stride)[:, :n]

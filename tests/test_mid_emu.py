@@ -26,8 +26,8 @@ def build_emu():
 def emu():
     L = C.CDLL(build_emu())
     vp = C.c_void_p
-    L.lwb_emu_mid_build_pack.argtypes = [vp] * 5
-    L.lwb_emu_mid_run.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    L.lwb_emu_mid_build_pack.argtypes = [C.c_int] + [vp] * 5
+    L.lwb_emu_mid_run.argtypes = [C.c_int, vp, vp, C.c_int, vp, vp, vp]
     return L
 
 
@@ -35,58 +35,63 @@ def P(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-@pytest.fixture(scope="module")
-def pack(emu, oracle):
-    t = oracle.tables(10)
+@pytest.fixture(scope="module", params=[1, 2], ids=["n1024", "n512"])
+def kb_pack(request, emu, oracle):
+    kb = request.param
+    t = oracle.tables(11 - kb)
     pk = np.zeros(emu.lwb_emu_mid_pack_floats(), np.float32)
-    emu.lwb_emu_mid_build_pack(P(t.a), P(t.b), P(t.c), P(t.window), P(pk))
-    return pk
+    emu.lwb_emu_mid_build_pack(kb, P(t.a), P(t.b), P(t.c), P(t.window), P(pk))
+    return kb, pk
 
 
-def oracle_run(oracle, spec, state):
-    pwr = oracle.Pwr(1, 10)
+def oracle_run(oracle, bs, spec, state):
+    pwr = oracle.Pwr(1, bs)
     if state is not None:
         pwr.set_data(state[None, :])
     outs = []
     for p in range(spec.shape[0]):
-        rc, pcm = oracle.synth_spectrum(10, 10, 1, 1, 1, spec[p:p + 1], pwr)
+        rc, pcm = oracle.synth_spectrum(bs, bs, 1, 1, 1, spec[p:p + 1], pwr)
         assert rc == 0
         outs.append(pcm[0])
     return np.concatenate(outs), pwr.data()[0]
 
 
-@pytest.mark.parametrize("seed,npk,prev,scale", [(20, 4, (0, 0), 1.0), (21, 3, (1, 0), 1.0), (22, 1, (0, 1), 1e-2), (23, 5, (1, 1), 1.0),
-                                                 (24, 2, (1, 1), 1e-30), (25, 2, (0, 0), 1e30)])
-def test_emulated_mid_kernel_matches_oracle(emu, pack, oracle, seed, npk, prev, scale):
-    """Two runs in lockstep, like a warp of k_mid; imported states are NOT symmetric."""
+@pytest.mark.parametrize("seed,npk,prev,scale", [(20, 4, (0, 0, 1, 0), 1.0), (21, 3, (1, 0, 0, 1), 1.0), (22, 1, (0, 1, 1, 1), 1e-2),
+                                                 (23, 5, (1, 1, 0, 0), 1.0), (24, 2, (1, 1, 1, 1), 1e-30), (25, 2, (0, 0, 0, 0), 1e30)])
+def test_emulated_mid_kernel_matches_oracle(emu, kb_pack, oracle, seed, npk, prev, scale):
+    """2^KB runs in lockstep, like a warp of k_mid; imported states are NOT symmetric."""
+    kb, pack = kb_pack
+    nb, n2, bs = 1 << kb, 1024 >> kb, 11 - kb
     rng = np.random.default_rng(seed)
-    spec = (rng.standard_normal((2, npk, 512)) * scale).astype(np.float32)
-    states = (rng.standard_normal((2, 512)) * scale).astype(np.float32)
+    spec = (rng.standard_normal((nb, npk, n2)) * scale).astype(np.float32)
+    states = (rng.standard_normal((nb, n2)) * scale).astype(np.float32)
     st = states.copy()
-    out = np.zeros((2, npk, 512), np.float32)
-    hp = np.array(prev, np.int32)
-    conflicts = emu.lwb_emu_mid_run(P(pack), P(spec), npk, P(hp), P(st), P(out))
+    out = np.zeros((nb, npk, n2), np.float32)
+    hp = np.array(prev[:nb], np.int32)
+    conflicts = emu.lwb_emu_mid_run(kb, P(pack), P(spec), npk, P(hp), P(st), P(out))
     assert conflicts == 1, "shared-memory transposes must be bank-conflict free"
-    for b in range(2):
-        want, want_state = oracle_run(oracle, spec[b], states[b] if prev[b] else None)
-        emitted = npk if prev[b] else npk - 1
+    for b in range(nb):
+        want, want_state = oracle_run(oracle, bs, spec[b], states[b] if hp[b] else None)
+        emitted = npk if hp[b] else npk - 1
         got = out[b, :emitted].ravel()
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), b
         assert np.array_equal(st[b].view(np.uint32), want_state.view(np.uint32)), b
 
 
-def test_emulated_mid_kernel_special_values(emu, pack, oracle):
+def test_emulated_mid_kernel_special_values(emu, kb_pack, oracle):
+    kb, pack = kb_pack
+    nb, n2, bs = 1 << kb, 1024 >> kb, 11 - kb
     rng = np.random.default_rng(9)
-    spec = rng.standard_normal((2, 3, 512)).astype(np.float32)
+    spec = rng.standard_normal((nb, 3, n2)).astype(np.float32)
     spec[0, 0, :64] = 1e-42          # denormals
     spec[0, 1, 5] = np.inf
     spec[1, 1, 77] = np.nan
     spec[1, 2] = 0.0
-    st = np.zeros((2, 512), np.float32)
-    out = np.zeros((2, 3, 512), np.float32)
-    emu.lwb_emu_mid_run(P(pack), P(spec), 3, P(np.zeros(2, np.int32)), P(st), P(out))
-    for b in range(2):
-        want, _ = oracle_run(oracle, spec[b], None)
+    st = np.zeros((nb, n2), np.float32)
+    out = np.zeros((nb, 3, n2), np.float32)
+    emu.lwb_emu_mid_run(kb, P(pack), P(spec), 3, P(np.zeros(nb, np.int32)), P(st), P(out))
+    for b in range(nb):
+        want, _ = oracle_run(oracle, bs, spec[b], None)
         got = out[b, :2].ravel()
         same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
         assert np.all(same), b
