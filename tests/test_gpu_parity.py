@@ -1125,6 +1125,53 @@ def test_fused_kernel_many_short_runs_per_warp(ctx, oracle, P):
         p_.close()
 
 
+@pytest.mark.parametrize("bs", [10, 9])
+def test_prepared_mid_batch_replays(ctx, oracle, bs):
+    """A prepared batch of uniform 1024- / 512-point chains in device memory (k_mid): the first execution plans and runs,
+    the second re-plans (the streams now hold state), later ones replay the captured launch.  Every execution is checked
+    against the oracle, which decodes the same packets again on top of its own state."""
+    rng = np.random.default_rng(500 + bs)
+    channels, S, P = 2, 37, 5
+    n2 = 1 << (bs - 1)
+    modes = [(1, 0)]
+    su = make_setup(ctx, channels, bs, bs, modes=modes)
+    refs = [RefStream(oracle, channels, bs, bs, modes) for _ in range(S)]
+    specs = rng.standard_normal((S, P, channels, n2)).astype(np.float32)
+    pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+    stride = P * n2
+    chains = [L.ChainSpec(pwrs[s], np.zeros(P, np.uint8), coeff_offset=s * P * channels * n2, out_offset=s * channels * stride,
+                          out_stride=stride) for s in range(S)]
+    d_in = ctx.device_alloc(specs.nbytes)
+    d_out = ctx.device_alloc(S * channels * stride * 4)
+    ctx.h2d(d_in, specs.ravel())
+    batch = L.Batch(ctx, chains, cabi.ENTRY_SPECTRUM, cabi.MEM_DEVICE, d_in, d_out, cabi.OUT_F32_PLANAR)
+    for it in range(4):
+        pcm = np.full(S * channels * stride, np.nan, np.float32)
+        ctx.h2d(d_out, pcm)
+        l0 = ctx.launch_count
+        batch.run()
+        assert ctx.launch_count - l0 == 1
+        ctx.synchronize()
+        ctx.d2h(pcm, d_out)
+        batch.collect()
+        for s in range(S):
+            parts = []
+            for i in range(P):
+                rc, o = refs[s].spectrum(0, 1, 1, specs[s, i])
+                assert rc == 0
+                parts.append(o)
+            want = np.concatenate(parts, axis=1)
+            n = want.shape[1]
+            assert chains[s].status == 0 and chains[s].n_samples == n, (it, s)
+            got = pcm[s * channels * stride: (s + 1) * channels * stride].reshape(channels, stride)[:, :n]
+            assert bits_equal(got, want), (it, s, mismatch_report(got, want))
+    for s in range(0, S, 7):
+        assert bits_equal(pwrs[s].data(), refs[s].pwr.data()), s
+    batch.close()
+    ctx.device_free(d_in)
+    ctx.device_free(d_out)
+
+
 def test_prepared_mixed_batch_replays_captured_rounds(ctx, oracle):
     """A prepared batch of mixed short/long chains in device memory: the first execution plans and
     runs, the second re-plans (the streams now hold state), later ones replay the captured launch
