@@ -1,6 +1,7 @@
 // path_mid.cuh -- part of the C-ABI translation unit (included by lwb_api.cu, not compiled on its own):
 // batches whose every packet is a full-window block of n = 1024 or of n = 512 (blocksize 10 / 9) go to k_mid
-// (kernel_mid.cuh): spectrum entry, planar f32 / i16, <= 8 channels.  The descriptors, the staging of host arenas and the capture by a prepared
+// (kernel_mid.cuh): planar f32 / i16, <= 8 channels; the residue entry runs the front stages (k_floor1_segments +
+// k_prologue_fused, kernel_prologue.cuh) over all packets first and hand k_mid the spectrum arena.  The descriptors, the staging of host arenas and the capture by a prepared
 // batch follow try_chain; the launch goes through mixed_launch_rounds (MixRound::nm).
 #pragma once
 
@@ -12,8 +13,11 @@ static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_b
     *handled = false;
     const uint64_t gen_at_entry = ctx->state_gen;
     if (getenv("LWB_FORCE_GENERIC") || getenv("LWB_NO_MID")) return LWB_OK;
-    if (io->entry != LWB_ENTRY_SPECTRUM) return LWB_OK;
     if (io->out_format != LWB_OUT_F32_PLANAR && io->out_format != LWB_OUT_I16_PLANAR) return LWB_OK;
+    const bool vq = io->entry == LWB_ENTRY_VQ, residue = io->entry != LWB_ENTRY_SPECTRUM;
+    if (residue && !io->floor_kind) return LWB_OK;            // (the chain kernel words the error)
+    if (vq) return LWB_OK;                                    // (VQ records of such streams: the general path, as before)
+    int uniform_c = -1;
     const bool i16 = io->out_format == LWB_OUT_I16_PLANAR;
     const size_t esz = i16 ? 2 : 4;
     const float *pack = nullptr;
@@ -25,6 +29,10 @@ static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_b
         if (!c->stream || c->stream->ctx != ctx || (c->n_packets && !c->mode_numbers)) return LWB_OK;
         const lwb_setup *su = c->stream->setup;
         if (su->channels > 8 || (su->bs1 != 10 && su->bs1 != 9) || !su->host.tab[1].pack) return LWB_OK;
+        if (residue) {                                        // the front stages want one channel count per batch
+            if (uniform_c < 0) uniform_c = (int)su->channels;
+            if (uniform_c != (int)su->channels) return LWB_OK;
+        }
         if (pack && pack != su->host.tab[1].pack) return LWB_OK;
         pack = su->host.tab[1].pack;
         kb = 11 - su->bs1;
@@ -51,13 +59,21 @@ static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_b
     const bool host = io->memory == LWB_MEM_HOST;
     cudaStream_t sm = ctx->stream;
     int rc;
-    uint64_t c_lo = ~0ull, c_hi = 0, o_lo = ~0ull, o_hi = 0;
+    uint64_t c_lo = ~0ull, c_hi = 0, o_lo = ~0ull, o_hi = 0, r_lo = ~0ull, r_hi = 0;
+    bool need_dense = false;
+    size_t n_pk = 0;
     for (size_t i = 0; i < n_chains; i++) {
         lwb_chain *c = &chains[i];
         lwb_stream *s = c->stream;
         if (s->busy_epoch == epoch) return fail(ctx, LWB_ERR_INVALID, "a stream appears in two chains of one batch");
         s->busy_epoch = epoch;
         const unsigned C = s->setup->channels;
+        if (residue && c->n_packets) {
+            r_lo = std::min(r_lo, c->packet_index);
+            r_hi = std::max<uint64_t>(r_hi, c->packet_index + c->n_packets);
+            if ((rc = scan_floor_kinds(ctx, io, c->packet_index * C, (c->packet_index + c->n_packets) * C, &need_dense))) return rc;
+            n_pk += c->n_packets;
+        }
         c->status = LWB_OK;
         c->packets_done = c->n_packets;
         c->n_samples = c->n_packets ? (uint32_t)((c->n_packets - (s->has ? 0u : 1u)) * (uint32_t)kMidN2) : 0u;
@@ -67,14 +83,61 @@ static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_b
         o_lo = std::min(o_lo, c->out_offset);
         o_hi = std::max(o_hi, c->out_offset + (uint64_t)(C - 1) * c->out_stride + c->n_samples);
     }
-    const float *d_coeffs = io->coeffs;
+    if (need_dense && !io->dense_floor) return fail(ctx, LWB_ERR_INVALID, "dense_floor missing");
+    const float *d_coeffs = vq ? nullptr : io->coeffs, *d_dense = need_dense ? io->dense_floor : nullptr;
     char *d_pcm = (char *)io->pcm;
     if (host) {
-        if ((rc = ensure(ctx, ctx->coeffs, (size_t)(c_hi - c_lo) * 4))) return rc;
         if (o_hi > o_lo && (rc = ensure(ctx, ctx->pcm, (size_t)(o_hi - o_lo) * esz))) return rc;
-        CU(ctx, cudaMemcpyAsync(ctx->coeffs.p, io->coeffs + c_lo, (size_t)(c_hi - c_lo) * 4, cudaMemcpyHostToDevice, sm));
-        d_coeffs = (const float *)ctx->coeffs.p - c_lo;
+        if (!vq) {
+            if ((rc = ensure(ctx, ctx->coeffs, (size_t)(c_hi - c_lo) * 4))) return rc;
+            CU(ctx, cudaMemcpyAsync(ctx->coeffs.p, io->coeffs + c_lo, (size_t)(c_hi - c_lo) * 4, cudaMemcpyHostToDevice, sm));
+            d_coeffs = (const float *)ctx->coeffs.p - c_lo;
+        }
+        if (need_dense) {
+            if ((rc = ensure(ctx, ctx->dense, (size_t)(c_hi - c_lo) * 4))) return rc;
+            CU(ctx, cudaMemcpyAsync(ctx->dense.p, io->dense_floor + c_lo, (size_t)(c_hi - c_lo) * 4, cudaMemcpyHostToDevice, sm));
+            d_dense = (const float *)ctx->dense.p - c_lo;
+        }
         d_pcm = (char *)ctx->pcm.p - o_lo * esz;
+    }
+    if (residue) {
+        // front stages over every packet of the batch: residue (or VQ records) + floors -> spectrum arena, same element
+        // offsets as the coefficient arena
+        if ((rc = ensure(ctx, ctx->spec, (size_t)(c_hi - c_lo) * 4))) return rc;
+        float *d_spec = (float *)ctx->spec.p - c_lo;
+        Staging *stp;
+        if ((rc = acquire_staging(ctx, n_pk * sizeof(DevPacket), &stp))) return rc;
+        if ((rc = ensure(ctx, ctx->desc, n_pk * sizeof(DevPacket)))) return rc;
+        DevPacket *hp = (DevPacket *)stp->h;
+        size_t di = 0;
+        for (size_t i = 0; i < n_chains; i++) {
+            const lwb_chain *c = &chains[i];
+            const lwb_setup *su = c->stream->setup;
+            for (uint32_t k = 0; k < c->n_packets; k++) {
+                DevPacket &d = hp[di++];
+                std::memset(&d, 0, sizeof(d));
+                d.setup = su->d_setup;
+                d.coeff_off = c->coeff_offset + (uint64_t)k * su->channels * kMidN2;
+                d.pkt_index = c->packet_index + k;
+                d.n = (uint16_t)(2 * kMidN2);
+                d.blockflag = 1;
+                d.mapping = su->host.mode_mapping[c->mode_numbers[k]];
+                d.channels = (uint8_t)su->channels;
+            }
+        }
+        const bool fast = prologue_is_fast(hp, n_pk, (unsigned)uniform_c, d_coeffs, d_dense, d_spec);
+        CU(ctx, cudaMemcpyAsync(ctx->desc.p, hp, n_pk * sizeof(DevPacket), cudaMemcpyHostToDevice, sm));
+        CU(ctx, cudaEventRecord(stp->ev, sm));
+        stp->pending = true;
+        const uint8_t *d_kinds = nullptr;
+        const uint32_t *d_ys = nullptr;
+        if ((rc = stage_floor_arrays(ctx, io, r_lo, r_hi, (unsigned)uniform_c, sm, &d_kinds, &d_ys))) return rc;
+        VqView vqv;
+        if ((rc = stage_vq_arrays(ctx, io, r_lo, r_hi, sm, &vqv))) return rc;
+        if ((rc = launch_prologue(ctx, (const DevPacket *)ctx->desc.p, n_pk, (unsigned)uniform_c, fast, prologue_smem(uniform_c, 11 - kb),
+                                  (int)kMidN2, d_coeffs, d_dense, d_kinds, d_ys, d_spec, vqv)))
+            return rc;
+        d_coeffs = d_spec;                                  // k_mid reads the spectrum
     }
     // runs, then groups of two runs of equal length (an odd one gets a dummy partner), longest first, dealt balanced
     std::vector<LongRun> runs;
@@ -123,7 +186,7 @@ static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_b
     LongRun *h = (LongRun *)st->h;
     for (size_t k = 0; k < groups.size(); k++)
         for (size_t b = 0; b < NBg; b++) h[NBg * k + b] = groups[k].r[b];
-    const bool capture = plan && !host;
+    const bool capture = plan && !host && !residue;         // (the front stages are not part of a captured launch here)
     DevBuf &dbuf = capture ? plan->mix : ctx->cdesc;
     if ((rc = ensure(ctx, dbuf, bytes + 16))) return rc;
     CU(ctx, cudaMemcpyAsync(dbuf.p, h, bytes, cudaMemcpyHostToDevice, sm));

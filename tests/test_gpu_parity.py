@@ -1125,6 +1125,90 @@ def test_fused_kernel_many_short_runs_per_warp(ctx, oracle, P):
         p_.close()
 
 
+@pytest.mark.parametrize("bs,channels,fmt,memory,seed", [(10, 2, cabi.OUT_F32_PLANAR, cabi.MEM_HOST, 420), (10, 6, cabi.OUT_I16_PLANAR, cabi.MEM_DEVICE, 421),
+                                                         (9, 2, cabi.OUT_F32_PLANAR, cabi.MEM_DEVICE, 422), (9, 3, cabi.OUT_I16_PLANAR, cabi.MEM_HOST, 423)])
+def test_mid_block_kernel_residue_entry(ctx, oracle, bs, channels, fmt, memory, seed):
+    """Residue entry in front of k_mid: full packets (coupling, floor-1 / dense / unused floors) of uniform 1024- / 512-point
+    streams: k_floor1_segments + k_prologue_fused form the spectrum, k_mid transforms it; bit-exact against the oracle over
+    two batches and byte-identical to the chain kernel (LWB_NO_MID=1), which does the same work inside one kernel."""
+    rng = np.random.default_rng(seed)
+    S, P = 9, 4
+    n2 = 1 << (bs - 1)
+    floors, mappings, modes = _random_packet_case(rng, channels, bs, bs)
+    su = make_setup(ctx, channels, bs, bs, modes=modes, mappings=mappings, floors=floors)
+    f32 = fmt == cabi.OUT_F32_PLANAR
+    dt = np.float32 if f32 else np.int16
+    refs = [RefStream(oracle, channels, bs, bs, modes, mappings, floors) for _ in range(S)]
+    batches = []
+    for b in range(2):
+        coeffs, dense, kinds, ys, want, seqs = [], [], [], [], [], []
+        for s in range(S):
+            mode_ids = rng.integers(0, len(modes), P).astype(np.uint8)
+            parts = []
+            for i in range(P):
+                res = (rng.standard_normal((channels, n2)) * rng.integers(0, 2, (channels, n2))).astype(np.float32)
+                mp = mappings[modes[mode_ids[i]][1]]
+                fl = []
+                for c in range(channels):
+                    mult, xs = floors[mp["floor_of_channel"][c]]
+                    r = rng.random()
+                    fl.append(None if r < 0.15 else (rng.random(n2).astype(np.float32) if r < 0.25 else random_floor1_y(rng, mult, len(xs))))
+                rc, pcm = refs[s].packet(int(mode_ids[i]), 1, 1, res, fl)
+                assert rc == 0
+                parts.append(pcm)
+                k, y, d = L.DecodedPacket(int(mode_ids[i]), res, fl).pack()
+                coeffs.append(res.ravel())
+                dense.append((d if d is not None else np.zeros_like(res)).ravel())
+                kinds.append(k)
+                ys.append(y)
+            want.append(np.concatenate(parts, axis=1))
+            seqs.append(mode_ids)
+        batches.append((np.concatenate(coeffs), np.concatenate(dense), np.concatenate(kinds), np.concatenate(ys), want, seqs,
+                        [r.pwr.data().copy() for r in refs]))
+    outs = {}
+    for name, env in (("mid", None), ("chain", {"LWB_NO_MID": "1"})):
+        pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
+        if env:
+            os.environ.update(env)
+        try:
+            for b, (coeffs, dense, kinds, ys, want, seqs, end_state) in enumerate(batches):
+                stride = P * n2
+                chains = [L.ChainSpec(pwrs[s], seqs[s], coeff_offset=s * P * channels * n2, packet_index=s * P,
+                                      out_offset=s * channels * stride, out_stride=stride) for s in range(S)]
+                pcm = np.zeros(S * channels * stride, dt)
+                launches0 = ctx.launch_count
+                if memory == cabi.MEM_DEVICE:
+                    d_in, d_out, d_dense = ctx.device_alloc(coeffs.nbytes), ctx.device_alloc(pcm.nbytes), ctx.device_alloc(dense.nbytes)
+                    ctx.h2d(d_in, coeffs)
+                    ctx.h2d(d_dense, dense)
+                    L.decode_chains(ctx, chains, cabi.ENTRY_RESIDUE, memory, d_in, d_out, fmt, floor_kind=kinds, floor1_y=ys, dense_floor=d_dense)
+                    ctx.d2h(pcm, d_out)
+                    for h in (d_in, d_out, d_dense):
+                        ctx.device_free(h)
+                else:
+                    L.decode_chains(ctx, chains, cabi.ENTRY_RESIDUE, memory, coeffs, pcm, fmt, floor_kind=kinds, floor1_y=ys, dense_floor=dense)
+                assert ctx.launch_count - launches0 == (3 if name == "mid" else 1)
+                for s in range(S):
+                    n = want[s].shape[1]
+                    assert chains[s].status == 0 and chains[s].n_samples == n, (name, b, s)
+                    got = pcm[s * channels * stride: (s + 1) * channels * stride].reshape(channels, stride)[:, :n]
+                    if f32:
+                        assert bits_equal(got, want[s]), (name, b, s, mismatch_report(got, want[s]))
+                    else:
+                        assert np.array_equal(got, oracle.quantise_i16(want[s])), (name, b, s)
+                    assert bits_equal(pwrs[s].data(), end_state[s]), (name, b, s)
+                # (only the samples produced: the slack of every row is whatever the arena held)
+                outs[(name, b)] = [pcm[s * channels * stride: (s + 1) * channels * stride].reshape(channels, stride)[:, :want[s].shape[1]].copy()
+                                   for s in range(S)]
+        finally:
+            if env:
+                for k in env:
+                    del os.environ[k]
+    for b in range(2):
+        for s in range(S):
+            assert np.array_equal(outs[("mid", b)][s].view(np.uint8), outs[("chain", b)][s].view(np.uint8)), (b, s)
+
+
 @pytest.mark.parametrize("bs", [10, 9])
 def test_prepared_mid_batch_replays(ctx, oracle, bs):
     """A prepared batch of uniform 1024- / 512-point chains in device memory (k_mid): the first execution plans and runs,
