@@ -6,6 +6,12 @@
 #pragma once
 
 struct MidGroup { LongRun r[4]; uint32_t n_packets; };
+static size_t n_pk_all(const lwb_chain *chains, size_t n_chains)
+{
+    size_t n = 0;
+    for (size_t i = 0; i < n_chains; i++) n += chains[i].n_packets;
+    return n;
+}
 
 static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_batch_io *io, uint64_t epoch, bool *handled,
                    lwb_plan *plan = nullptr)
@@ -100,6 +106,14 @@ static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_b
         }
         d_pcm = (char *)ctx->pcm.p - o_lo * esz;
     }
+    // A prepared batch in device memory owns its descriptors (run groups, then the front stages' packet list) and replays
+    // them while no stream changes shape (lwb_plan_execute: mix_pro, then the round).
+    const bool capture = plan && !host;
+    DevBuf &dbuf = capture ? plan->mix : ctx->cdesc;
+    const size_t NBcap = (size_t)1 << kb;
+    const size_t off_pro = (n_runs * NBcap * sizeof(LongRun) + 15) & ~(size_t)15;      // (an upper bound: every run its own group)
+    if ((rc = ensure(ctx, dbuf, off_pro + (residue ? n_pk_all(chains, n_chains) * sizeof(DevPacket) : 0) + 16))) return rc;
+    bool pro_fast = false;
     if (residue) {
         // front stages over every packet of the batch: residue (or VQ records) + floors -> spectrum arena, same element
         // offsets as the coefficient arena
@@ -107,7 +121,6 @@ static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_b
         float *d_spec = (float *)ctx->spec.p - c_lo;
         Staging *stp;
         if ((rc = acquire_staging(ctx, n_pk * sizeof(DevPacket), &stp))) return rc;
-        if ((rc = ensure(ctx, ctx->desc, n_pk * sizeof(DevPacket)))) return rc;
         DevPacket *hp = (DevPacket *)stp->h;
         size_t di = 0;
         for (size_t i = 0; i < n_chains; i++) {
@@ -126,7 +139,8 @@ static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_b
             }
         }
         const bool fast = prologue_is_fast(hp, n_pk, (unsigned)uniform_c, d_coeffs, d_dense, d_spec);
-        CU(ctx, cudaMemcpyAsync(ctx->desc.p, hp, n_pk * sizeof(DevPacket), cudaMemcpyHostToDevice, sm));
+        DevPacket *d_pro = (DevPacket *)((char *)dbuf.p + off_pro);
+        CU(ctx, cudaMemcpyAsync(d_pro, hp, n_pk * sizeof(DevPacket), cudaMemcpyHostToDevice, sm));
         CU(ctx, cudaEventRecord(stp->ev, sm));
         stp->pending = true;
         const uint8_t *d_kinds = nullptr;
@@ -134,7 +148,8 @@ static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_b
         if ((rc = stage_floor_arrays(ctx, io, r_lo, r_hi, (unsigned)uniform_c, sm, &d_kinds, &d_ys))) return rc;
         VqView vqv;
         if ((rc = stage_vq_arrays(ctx, io, r_lo, r_hi, sm, &vqv))) return rc;
-        if ((rc = launch_prologue(ctx, (const DevPacket *)ctx->desc.p, n_pk, (unsigned)uniform_c, fast, prologue_smem(uniform_c, 11 - kb),
+        pro_fast = fast;
+        if ((rc = launch_prologue(ctx, d_pro, n_pk, (unsigned)uniform_c, fast, prologue_smem(uniform_c, 11 - kb),
                                   (int)kMidN2, d_coeffs, d_dense, d_kinds, d_ys, d_spec, vqv)))
             return rc;
         d_coeffs = d_spec;                                  // k_mid reads the spectrum
@@ -186,9 +201,7 @@ static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_b
     LongRun *h = (LongRun *)st->h;
     for (size_t k = 0; k < groups.size(); k++)
         for (size_t b = 0; b < NBg; b++) h[NBg * k + b] = groups[k].r[b];
-    const bool capture = plan && !host && !residue;         // (the front stages are not part of a captured launch here)
-    DevBuf &dbuf = capture ? plan->mix : ctx->cdesc;
-    if ((rc = ensure(ctx, dbuf, bytes + 16))) return rc;
+    if (bytes > off_pro) return fail(ctx, LWB_ERR_INVALID, "internal: more run groups than runs");
     CU(ctx, cudaMemcpyAsync(dbuf.p, h, bytes, cudaMemcpyHostToDevice, sm));
     CU(ctx, cudaEventRecord(st->ev, sm));
     st->pending = true;
@@ -210,7 +223,17 @@ static int try_mid(lwb_ctx *ctx, lwb_chain *chains, size_t n_chains, const lwb_b
         plan->gen = gen_at_entry;
         plan->mix_launch = ml;
         plan->mix_rounds = std::move(rounds);
-        plan->mix_pro = false;
+        plan->mix_pro = residue;
+        if (residue) {                      // replayed by lwb_plan_execute in front of the round
+            plan->mix_pro_pk = (const DevPacket *)((char *)dbuf.p + off_pro);
+            plan->mix_pro_n = n_pk;
+            plan->mix_pro_fast = pro_fast;
+            plan->mix_pro_C = (unsigned)uniform_c;
+            plan->mix_pro_smem_old = prologue_smem(uniform_c, 11 - kb);
+            plan->mix_pro_c_lo = c_lo; plan->mix_pro_r_lo = r_lo; plan->mix_pro_r_hi = r_hi;
+            plan->mix_pro_dense = need_dense;
+            plan->mix_pro_n2max = (int)kMidN2;
+        }
     }
     if (host) {
         if (o_hi > o_lo)

@@ -1141,10 +1141,11 @@ def test_mid_block_kernel_residue_entry(ctx, oracle, bs, channels, fmt, memory, 
     refs = [RefStream(oracle, channels, bs, bs, modes, mappings, floors) for _ in range(S)]
     batches = []
     for b in range(2):
-        coeffs, dense, kinds, ys, want, seqs = [], [], [], [], [], []
+        coeffs, dense, kinds, ys, want, seqs, raw = [], [], [], [], [], [], []
         for s in range(S):
             mode_ids = rng.integers(0, len(modes), P).astype(np.uint8)
             parts = []
+            raw.append([])
             for i in range(P):
                 res = (rng.standard_normal((channels, n2)) * rng.integers(0, 2, (channels, n2))).astype(np.float32)
                 mp = mappings[modes[mode_ids[i]][1]]
@@ -1156,6 +1157,7 @@ def test_mid_block_kernel_residue_entry(ctx, oracle, bs, channels, fmt, memory, 
                 rc, pcm = refs[s].packet(int(mode_ids[i]), 1, 1, res, fl)
                 assert rc == 0
                 parts.append(pcm)
+                raw[-1].append((int(mode_ids[i]), res, fl))
                 k, y, d = L.DecodedPacket(int(mode_ids[i]), res, fl).pack()
                 coeffs.append(res.ravel())
                 dense.append((d if d is not None else np.zeros_like(res)).ravel())
@@ -1164,14 +1166,14 @@ def test_mid_block_kernel_residue_entry(ctx, oracle, bs, channels, fmt, memory, 
             want.append(np.concatenate(parts, axis=1))
             seqs.append(mode_ids)
         batches.append((np.concatenate(coeffs), np.concatenate(dense), np.concatenate(kinds), np.concatenate(ys), want, seqs,
-                        [r.pwr.data().copy() for r in refs]))
+                        [r.pwr.data().copy() for r in refs], raw))
     outs = {}
     for name, env in (("mid", None), ("chain", {"LWB_NO_MID": "1"})):
         pwrs = [L.PreviousWindowRight(su) for _ in range(S)]
         if env:
             os.environ.update(env)
         try:
-            for b, (coeffs, dense, kinds, ys, want, seqs, end_state) in enumerate(batches):
+            for b, (coeffs, dense, kinds, ys, want, seqs, end_state, _raw) in enumerate(batches):
                 stride = P * n2
                 chains = [L.ChainSpec(pwrs[s], seqs[s], coeff_offset=s * P * channels * n2, packet_index=s * P,
                                       out_offset=s * channels * stride, out_stride=stride) for s in range(S)]
@@ -1207,6 +1209,42 @@ def test_mid_block_kernel_residue_entry(ctx, oracle, bs, channels, fmt, memory, 
     for b in range(2):
         for s in range(S):
             assert np.array_equal(outs[("mid", b)][s].view(np.uint8), outs[("chain", b)][s].view(np.uint8)), (b, s)
+    if memory == cabi.MEM_DEVICE:
+        # a prepared batch: plans, re-plans once the streams hold state, then replays front stages + k_mid from the plan
+        coeffs, dense, kinds, ys, _want, seqs, _end, raw = batches[0]
+        refs2 = [RefStream(oracle, channels, bs, bs, modes, mappings, floors) for _ in range(S)]
+        pwrs2 = [L.PreviousWindowRight(su) for _ in range(S)]
+        stride = P * n2
+        chains = [L.ChainSpec(pwrs2[s], seqs[s], coeff_offset=s * P * channels * n2, packet_index=s * P,
+                              out_offset=s * channels * stride, out_stride=stride) for s in range(S)]
+        d_in, d_dense = ctx.device_alloc(coeffs.nbytes), ctx.device_alloc(dense.nbytes)
+        d_out = ctx.device_alloc(S * channels * stride * dt().itemsize)
+        ctx.h2d(d_in, coeffs)
+        ctx.h2d(d_dense, dense)
+        batch = L.Batch(ctx, chains, cabi.ENTRY_RESIDUE, cabi.MEM_DEVICE, d_in, d_out, fmt, floor_kind=kinds, floor1_y=ys, dense_floor=d_dense)
+        for it in range(4):
+            pcm = np.zeros(S * channels * stride, dt)
+            batch.run()
+            ctx.synchronize()
+            ctx.d2h(pcm, d_out)
+            batch.collect()
+            for s in range(S):
+                parts = []
+                for mode, res, fl in raw[s]:
+                    rc, o = refs2[s].packet(mode, 1, 1, res, fl)
+                    assert rc == 0
+                    parts.append(o)
+                w = np.concatenate(parts, axis=1)
+                n = w.shape[1]
+                assert chains[s].status == 0 and chains[s].n_samples == n, (it, s)
+                got = pcm[s * channels * stride: (s + 1) * channels * stride].reshape(channels, stride)[:, :n]
+                if f32:
+                    assert bits_equal(got, w), ("plan", it, s, mismatch_report(got, w))
+                else:
+                    assert np.array_equal(got, oracle.quantise_i16(w)), ("plan", it, s)
+        batch.close()
+        for h in (d_in, d_dense, d_out):
+            ctx.device_free(h)
 
 
 @pytest.mark.parametrize("bs", [10, 9])
